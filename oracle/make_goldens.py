@@ -1,0 +1,97 @@
+"""Generate ``tests/golden/*.npz`` by running the UNMODIFIED reference under ``oracle/harness.py``.
+
+Run in the build container only (needs /root/reference):  ``python -m oracle.make_goldens``
+Each file holds, per (scenario, species, iteration, day) cell: the slot-tagged draws the reference consumed, and
+the reference's own outputs (Daily row, State_Daily rows, per-fish states / fp32 rates / survival flags), plus the
+routing tables captured from the reference's ``movement()`` and the Route_Flows / Unit_Hours frames.
+TEST INFRASTRUCTURE.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+from . import fixtures, harness, replay, stryke_oracle as O
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+CASES = {
+    # name: (fixture function name, kwargs, seed, {species: family})
+    "c2_kaplan_francis": ("c2_facility", dict(n_fish=250, iterations=2, days=2), 1, {}),
+    "c2_barotrauma": ("c2_facility", dict(n_fish=250, iterations=1, days=2, baro=True), 2, {}),
+    "c4_propeller_baro": ("c4_barotrauma", dict(n_fish=250, iterations=1, days=2, habitat="Benthic"), 3, {}),
+    "c5_cascade": ("c5_cascade", dict(n_fish=200, iterations=1, days=2), 4, {}),
+    "c1_single_unit": ("c1_single_unit", dict(iterations=2, days=60), 5, {"Micropterus": "Centrarchidae"}),
+    "c3_population": ("c3_population", dict(n_species=4, iterations=2, days=8), 6,
+                      {"Ambloplites": "Centrarchidae", "Micropterus": "Centrarchidae", "Lepomis": "Centrarchidae"}),
+    "c2_low_flow": ("c2_facility", dict(n_fish=120, iterations=1, days=3, curr_Q=600.0), 7, {}),
+}
+
+
+def build_case(name):
+    fn, kw, seed, fam = CASES[name]
+    prj = getattr(fixtures, fn)(**kw)
+    sim, store, rec = harness.run_reference(prj, seed=seed)
+    model = O.Model.from_project(prj)
+    node_idx = {nd: i for i, nd in enumerate(model.nodes)}
+    daily = store["Daily"]
+    sd = store["State_Daily"] if "State_Daily" in store else None
+    simtabs = {k: store[k] for k in store.keys() if "simulations" in k}
+    pops = {(r["Species"], r["Scenario"]): r for r in prj["population"]}
+    M = len(model.moves)
+    out = {}
+    cells_meta = []
+    assert len(rec.cells) == len(daily)
+    for ci, cell in enumerate(rec.cells):
+        drow = daily.iloc[ci]
+        spc, scen = drow["species"].strip(), drow["scenario"].strip()
+        prow = pops[(spc, scen)]
+        p = f"c{ci}_"
+        cm = dict(scenario=scen, species=spc, iteration=int(drow["iteration"]), day=str(drow["day"]),
+                  curr_Q=cell["curr_Q"], presence=cell["presence"], tot_hours=cell["tot_hours"], hours=cell["hours"],
+                  count_draw=replay.cell_count_draw(cell), n=(cell["moves"][0]["n"] if cell["moves"] else 0))
+        cells_meta.append(cm)
+        out[p + "daily"] = drow.iloc[6:].to_numpy(dtype=float).astype(np.int64)
+        if not cell["moves"]:
+            continue
+        for k, v in replay.pack_cell(cell, prow).items():
+            out[p + k] = v
+        sub = sd[(sd.scenario == scen) & (sd.species == spc) & (sd.iteration == drow["iteration"]) & (sd.day == drow["day"])]
+        out[p + "sd_move"] = sub["move"].to_numpy(dtype=np.int32)
+        out[p + "sd_state"] = np.array([node_idx[s] for s in sub["state"]], dtype=np.int32)
+        out[p + "sd_vals"] = sub[["successes", "count"]].to_numpy(dtype=np.float64)
+        f = simtabs[f"/simulations/{scen}/{spc}"]
+        f = f[(f.iteration == drow["iteration"]) & (f.day == drow["day"])]
+        out[p + "states"] = np.stack([np.array([node_idx[s] for s in f[f"state_{k}"].astype(str)], dtype=np.int16) for k in range(M)])
+        out[p + "rates"] = np.stack([f[f"rates_{k}"].to_numpy(dtype=np.float32) for k in range(M)])
+        out[p + "survival"] = np.stack([f[f"survival_{k}"].to_numpy(dtype=np.uint8) for k in range(M)])
+    routing = [dict(cell=c, location=loc, locs=locs, probs=[float(x) for x in p]) for (c, loc), (locs, p) in rec.routing.items()]
+
+    def frame(key):
+        if key not in store:
+            return []
+        df = store[key].copy()
+        df["day"] = df["day"].astype(str)
+        return json.loads(df.to_json(orient="records"))
+    meta = dict(case=name, fixture=fn, kwargs=kw, seed=seed, families=fam, cells=cells_meta, routing=routing,
+                route_flows=frame("Route_Flows"), unit_hours=frame("Unit_Hours"), nodes=model.nodes, moves=M,
+                numpy=np.__version__, reference="knebiolo/stryke @ /root/reference (unmodified, oracle/harness.py)")
+    out["meta"] = np.array(json.dumps(meta))
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **out)
+    return path, len(rec.cells)
+
+
+def main(argv):
+    names = argv or list(CASES)
+    for nm in names:
+        path, nc = build_case(nm)
+        print(f"{nm}: {nc} cells -> {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
