@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py — simulated fish-passages/s of the B200 passage engine (BASELINE.json metric) and of the CPU baseline.
+
+  python bench.py [--gpus N --steps K --warmup W] [--workload c2|c3|c5] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A *step* is one pass of the hot path (count -> scan -> passage kernels) over the workload's cells with a fresh Philox
+seed.  Default workload ``c2`` = BASELINE.json configs[1]: synthetic 3-unit Kaplan+Kaplan+Francis facility with bypass
+and spill, 1e6 fish/iteration x 1000 iterations (x 1 day) on one B200 = 1e9 fish-passages per step.  With N ranks every
+rank simulates its own 1000 iterations (weak scaling; iterations are independent, the Philox counter is keyed by the
+global iteration id) and the tally arrays are summed with ONE NCCL all-reduce per step.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+# Algorithmic lane-ops per fish-passage (DESIGN.md §"Roofline"): Philox blocks x 44 + length 24 + per-move work.
+ALGO_LANE_OPS = {"c2": 330.0, "c3": 330.0, "c5": 1250.0}
+
+
+def workload_project(name, n_fish, iterations, days):
+    from oracle import fixtures
+    if name == "c2":
+        return fixtures.c2_facility(n_fish=n_fish, iterations=iterations, days=days, curr_Q=9000.0)
+    if name == "c5":
+        return fixtures.c5_cascade(n_fish=n_fish, iterations=iterations, days=days, curr_Q=9000.0)
+    if name == "c3":
+        return fixtures.c3_population(n_species=20, iterations=iterations, days=days, curr_Q=9000.0)
+    raise SystemExit(f"unknown workload {name}")
+
+
+def build_plan(prj, name):
+    os.environ.setdefault("STRYKE_MAX_DAILY_FISH", "2000000000")
+    os.environ.setdefault("STRYKE_MAX_DAILY_STATE_ROWS", "2000000000000")
+    import gpu_util as G
+    sim, plan = G.make_plan(prj, name)
+    return sim, plan
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = []
+        for i, nm in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_port_rate(name, n_fish, cells, procs, seed=0):
+    """The oracle (NumPy port of the reference path) on the host cores: fish-passages/s over ``cells`` cells of
+    ``n_fish`` fish each, fanned out over ``procs`` processes (the reference itself is single-threaded)."""
+    import multiprocessing as mp
+    per = max(1, cells // procs)
+    t0 = time.perf_counter()
+    if procs == 1:
+        done = _cpu_worker((name, n_fish, per, seed))
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            done = sum(pool.map(_cpu_worker, [(name, n_fish, per, seed + i) for i in range(procs)]))
+    dt = time.perf_counter() - t0
+    return done / dt, done, dt
+
+
+def _cpu_worker(args):
+    name, n_fish, cells, seed = args
+    from oracle import stryke_oracle as O
+    prj = workload_project(name, n_fish, cells, 1)
+    out = O.run_project(prj, seed=seed)
+    return int(sum(int(r["daily"][0]) for r in out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"])
+    ap.add_argument("--fish", type=int, default=None, help="fish per cell (fixed-count workloads)")
+    ap.add_argument("--iterations", type=int, default=None)
+    ap.add_argument("--days", type=int, default=None)
+    ap.add_argument("--precision", type=int, default=32)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    defaults = {"c2": (1_000_000, 1000, 1), "c5": (250_000, 400, 1), "c3": (0, 1000, 365)}[args.workload]
+    n_fish = args.fish if args.fish is not None else defaults[0]
+    iterations = args.iterations if args.iterations is not None else defaults[1]
+    days = args.days if args.days is not None else defaults[2]
+    nproc = os.cpu_count() or 1
+    workload_desc = {"c2": f"C2: 3-unit Kaplan+Kaplan+Francis facility, bypass+spill, 9 nodes, 6 moves; {n_fish} fish/iteration x "
+                           f"{iterations} iterations x {days} day(s) per GPU",
+                     "c5": f"C5: 5-dam cascade, 40 nodes, 22 moves; {n_fish} fish x {iterations} iterations x {days} day(s) per GPU",
+                     "c3": f"C3: population mode, 20 species x {days} days x {iterations} iterations per GPU, EPRI-fitted entrainment"}[args.workload]
+
+    # ---------------------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        # The reference is pure Python and cannot travel to the GPU box; its path is timed through the NumPy port
+        # (oracle/stryke_oracle.py) on all host cores, on a bounded sample of the same workload.
+        if rank != 0:
+            return
+        sample_fish = 200_000 if args.workload != "c3" else 0
+        cells = nproc
+        vals = []
+        for i in range(args.warmup + args.steps):
+            rate, done, dt = cpu_port_rate(args.workload, sample_fish, cells, nproc, seed=100 + i)
+            if i >= args.warmup:
+                vals.append((rate, done, dt))
+        rate = float(np.mean([v[0] for v in vals]))
+        line = {"impl": "reference", "metric": "simulated fish-passages/sec (route+strike+survival)", "value": rate,
+                "unit": "fish-passages/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": float(np.mean([v[2] for v in vals]) * 1e3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_desc},
+                "cpu_baseline": {"value": rate, "unit": "fish-passages/s", "cores": nproc, "kind": "port",
+                                 "sample": f"{cells} cells x {sample_fish} fish per step, {nproc} processes (NumPy port of Stryke/stryke.py:2897-3383; "
+                                           "the unmodified reference measured 2087 fish-passages/s on one core, BASELINE.md §2)"},
+                "e2e": {"value": rate, "unit": "fish-passages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---------------------------------------------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    from stryke_b200 import _abi, engine
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    prj = workload_project(args.workload, n_fish, iterations, days)
+    with contextlib.redirect_stdout(io.StringIO()):
+        sim, plan_h = build_plan(prj, f"bench_{args.workload}_{rank}")
+    # partition-independent Philox keys: this rank's iterations are global iterations [rank*I, (rank+1)*I)
+    cell_id = plan_h.cell_id + np.uint64(rank) * np.uint64(1 << 40)
+    species = plan_h.species_table
+    plan = engine.Plan(plan_h.fac, plan_h.days, species, plan_h.cell_day, plan_h.cell_species, cell_id,
+                       device=local_rank, precision=args.precision, seed=0x5EED, max_daily_fish=2_000_000_000)
+    t_n, t_daily, t_sd = plan.allocate()
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    stream = torch.cuda.current_stream()
+
+    def step(seed):
+        # fresh Philox key per step
+        plan.set_seed(seed)
+        plan.launch(t_n, t_daily, t_sd)
+        if world > 1:
+            dist.all_reduce(t_daily)
+            dist.all_reduce(t_sd)
+
+    for i in range(args.warmup):
+        step(1000 + i)
+        flush_buf.fill_(i)
+    torch.cuda.synchronize()
+    fish_per_step = plan.status()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = engine.launch_count()
+    evs = []
+    for i in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step(2000 + i)
+        e1.record(stream)
+        evs.append((e0, e1))
+        flush_buf.fill_(i + 1)     # L2 flush between timed steps (256 MiB > 126 MB L2), outside the event pairs
+    torch.cuda.synchronize()
+    launches = engine.launch_count() - launches0
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    plan.status()
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    t_fish = torch.tensor([float(fish_per_step)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_fish, op=dist.ReduceOp.SUM)
+    ms_total, fish_all = float(t_ms.item()), float(t_fish.item())
+    value = fish_all * args.steps / (ms_total * 1e-3)
+
+    # ---- roofline of the dominant kernel (passage_kernel): instruction-issue bound ----------------------------
+    peak_ops, cal_ms = engine.calibrate_issue(local_rank, stream.cuda_stream)
+    algo = ALGO_LANE_OPS[args.workload]
+    per_gpu_rate = fish_per_step * args.steps / (ms_total * 1e-3)
+    achieved = per_gpu_rate * algo
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "r01_passage_metrics.json")
+    inst_per_fish = None
+    if os.path.isfile(prof):
+        with open(prof) as fh:
+            pj = json.load(fh)
+        traffic = pj.get("dram_bytes_per_launch")
+        inst_per_fish = pj.get("thread_inst_per_fish")
+    roofline = {"bound": "issue", "achieved": achieved / 1e12, "peak": peak_ops / 1e12, "unit": "Tlane-op/s",
+                "frac": achieved / peak_ops, "traffic": traffic,
+                "note": "neither HBM nor tensor binds this path (SURVEY.md §8d): bound = SM instruction issue (INT32 Philox + FP32/SFU). "
+                        f"achieved = {algo:.0f} algorithmic lane-ops per fish-passage (DESIGN.md) x fish-passages/s per GPU; peak = lane-ops/s of "
+                        "an independent IMAD+LOP3 stream measured live by stryke_b200_calibrate_issue on this GPU",
+                "executed_thread_inst_per_fish_ncu": inst_per_fish,
+                "hbm": {"achieved_GBps": (plan.n_cells * (4 + 20 + plan.n_pairs * 8) * 2) / (ms_total / args.steps * 1e-3) / 1e9,
+                        "peak_GBps": _measured_peak()}}
+
+    # ---- e2e: the C-ABI call with HOST buffers (tables H2D, kernels, tallies D2H inside the timed region) ---------
+    e2e = None
+    if rank == 0 or world > 1:
+        h2d = sum(a.nbytes for a in (plan_h.fac.node_kind, plan_h.fac.node_apriori, plan_h.fac.node_unit, plan_h.fac.edge_off,
+                                     plan_h.fac.edge_dst, plan_h.fac.unit_static, plan_h.days.edge_cdf, plan_h.days.node_stay,
+                                     plan_h.days.unit_coef, plan_h.days.curr_Q, species, plan_h.cell_day, plan_h.cell_species, cell_id))
+        d2h = plan.n_cells * (4 + _abi.DAILY_W * 4 + plan.n_pairs * 8)
+        e2e_steps = max(2, min(args.steps, 3))
+        engine.run_cells(plan_h.fac, plan_h.days, species, plan_h.cell_day, plan_h.cell_species, cell_id, device=local_rank,
+                         precision=args.precision, seed=1, max_daily_fish=2_000_000_000)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            r = engine.run_cells(plan_h.fac, plan_h.days, species, plan_h.cell_day, plan_h.cell_species, cell_id,
+                                 device=local_rank, precision=args.precision, seed=3000 + i, max_daily_fish=2_000_000_000)
+            if world > 1:
+                td = torch.from_numpy(r.daily.view(np.int32)).to(f"cuda:{local_rank}")
+                dist.all_reduce(td)
+                td.cpu()
+        dt = time.perf_counter() - t0
+        t_dt = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if world > 1:
+            dist.all_reduce(t_dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": fish_all * e2e_steps / float(t_dt.item()), "unit": "fish-passages/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "how": "stryke_b200_run through ctypes: host tables in, count+scan+passage kernels, host tallies out; wall clock"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample_fish = 200_000 if args.workload != "c3" else 0
+        rate, done, dt = cpu_port_rate(args.workload, sample_fish, nproc, nproc, seed=5)
+        cpu = {"value": rate, "unit": "fish-passages/s", "cores": nproc, "kind": "port",
+               "sample": f"{done} fish-passages in {dt:.1f} s: {nproc} cells x {sample_fish} fish, {nproc} processes (NumPy port "
+                         "oracle/stryke_oracle.py; unmodified reference: 2087 fish-passages/s/core, BASELINE.md §2)"}
+    if rank == 0:
+        line = {"metric": "simulated fish-passages/sec (route+strike+survival)", "value": value, "unit": "fish-passages/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic",
+                "config": {"workload": workload_desc, "rng": "Philox4x32-10 keyed (seed; cell id, fish, slot)",
+                           "l2": "256 MiB flush write between timed steps; kernel inputs are < 64 KiB of tables",
+                           "fish_passages_per_step": fish_all, "cells_per_gpu": plan.n_cells,
+                           "collective": "NCCL all_reduce(sum) of Daily + State_Daily tallies per step" if world > 1 else "none"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": sampler.summary()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as fh:
+            return json.load(fh).get("hbm_gbs")
+    return 6650.0
+
+
+if __name__ == "__main__":
+    main()

@@ -123,8 +123,8 @@ class Recorder:
 
     Slots per (move k, evaluation e) where e = 0 is ``np.vectorize``'s probe call on fish 0 (the "ghost",
     SURVEY.md Appendix E3) and e = f + 1 is fish f:
-      rR      value returned by ``np.random.uniform(0.3, 1.0, 1)``             (stryke.py:900)
-      depth   value returned by ``np.random.uniform(depth_1, depth_2, 1)``     (stryke.py:1494)
+      rR      raw uniform behind ``np.random.uniform(0.3, 1.0, 1)``            (stryke.py:900)
+      depth   raw uniform behind ``np.random.uniform(depth_1, depth_2, 1)``    (stryke.py:1494)
       cause   up to 4 values of ``np.random.random()``                         (stryke.py:1545-1560)
       route   the uniform consumed by ``np.random.choice(locs, p=probs)``      (stryke.py:2058)
     plus ``dice[k, f]`` (stryke.py:3189), the presence uniform (stryke.py:3026) and the PCG64 draws.
@@ -155,6 +155,17 @@ class Recorder:
         o_sample = np.random.random_sample
 
         def uniform(low=0.0, high=1.0, size=None):
+            if rec.cur is not None and rec._ctx is not None and rec._ctx[0] == "surv" and size == 1:
+                # legacy RandomState.uniform is ``low + (high - low) * random_sample()`` (verified bit-exact in
+                # tests/test_oracle_vs_reference.py); record the raw uniform so it can be injected on the device
+                u = o_sample(1)
+                v = low + (high - low) * u
+                e = rec._ctx[1]
+                if float(low) == 0.3 and float(high) == 1.0:
+                    rec._move()["rR"][e] = float(u[0])
+                else:
+                    rec._move()["depth"][e] = float(u[0])
+                return v
             v = o_uniform(low, high, size)
             if rec.cur is None:
                 return v
@@ -164,12 +175,6 @@ class Recorder:
                 # dice vector, stryke.py:3189 -> a new move begins
                 rec.cur["moves"].append(dict(dice=np.array(v, dtype=float), n=int(np.size(v)), surv_calls=0,
                                              move_calls=0, rR={}, depth={}, cause={}, route={}))
-            elif rec._ctx is not None and rec._ctx[0] == "surv":
-                e = rec._ctx[1]
-                if float(low) == 0.3 and float(high) == 1.0:
-                    rec._move()["rR"][e] = float(v[0])
-                else:
-                    rec._move()["depth"][e] = float(v[0])
             return v
 
         def random(size=None):

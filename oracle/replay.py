@@ -7,15 +7,21 @@ import numpy as np
 from . import stryke_oracle as O
 
 
-def cell_lengths(cell, pop_row):
-    """Fish lengths (ft) of a recorded cell: the last PCG64 ``standard_normal`` batch (stryke.py:3070)."""
+def cell_normals(cell):
+    """Standard normals behind the fish lengths: the last PCG64 ``standard_normal`` batch (stryke.py:3070)."""
     normals = [p for p in cell["pcg"] if p[0] == "standard_normal"]
     if not cell["moves"]:
         return np.zeros(0)
     n = cell["moves"][0]["n"]
     z = normals[-1][-1]
     assert z.shape[0] == n, (z.shape, n)
-    return O.lengths_from_normals(z, pop_row["length shape"], pop_row["length location"], pop_row["length scale"])
+    return z
+
+
+def cell_lengths(cell, pop_row):
+    """Fish lengths (ft) of a recorded cell."""
+    return O.lengths_from_normals(cell_normals(cell), pop_row["length shape"], pop_row["length location"],
+                                  pop_row["length scale"])
 
 
 def cell_count_draw(cell):
@@ -57,18 +63,18 @@ def draws_from_recording(cell, pop_row):
             if e > 0:
                 route[k, e - 1] = v
     return O.Draws(lengths_ft=cell_lengths(cell, pop_row), dice=dice, rR=rR, depth_u=depth, cause=cause, route=route,
-                   depth_is_value=True, ghost_rR=g_rR, ghost_depth=g_depth, ghost_cause=g_cause)
+                   ghost_rR=g_rR, ghost_depth=g_depth, ghost_cause=g_cause)
 
 
 def pack_cell(cell, pop_row):
     """Flat dict of arrays for ``np.savez`` (tests/golden/*.npz)."""
     d = draws_from_recording(cell, pop_row)
-    return dict(lengths_ft=d.lengths_ft, dice=d.dice, rR=d.rR, depth=d.depth_u, cause=d.cause, route=d.route,
+    return dict(lengths_ft=d.lengths_ft, length_z=cell_normals(cell), dice=d.dice, rR=d.rR, depth=d.depth_u, cause=d.cause, route=d.route,
                 ghost_rR=d.ghost_rR, ghost_depth=d.ghost_depth, ghost_cause=d.ghost_cause)
 
 
 def unpack_cell(z, prefix=""):
     g = lambda k: z[prefix + k]
     return O.Draws(lengths_ft=g("lengths_ft"), dice=g("dice"), rR=g("rR"), depth_u=g("depth"), cause=g("cause"),
-                   route=g("route"), depth_is_value=True, ghost_rR=g("ghost_rR"), ghost_depth=g("ghost_depth"),
+                   route=g("route"), ghost_rR=g("ghost_rR"), ghost_depth=g("ghost_depth"),
                    ghost_cause=g("ghost_cause"))

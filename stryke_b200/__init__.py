@@ -1,0 +1,10 @@
+"""stryke_b200 — B200-native engine for stryke's individual-based Monte Carlo fish-passage simulation.
+
+``from stryke_b200 import simulation`` mirrors ``Stryke.stryke.simulation`` (reference: Stryke/stryke.py:249).
+The per-fish work exists only as sm_100a CUDA behind the C ABI in include/stryke_b200.h; importing the package
+does not need a GPU, running a simulation does (there is no CPU fallback).
+"""
+from .simulation import simulation  # noqa: F401
+
+__all__ = ["simulation"]
+__version__ = "0.1.0"

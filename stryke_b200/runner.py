@@ -1,0 +1,318 @@
+"""``simulation.run()`` — orchestration of one Monte Carlo run on the GPU (reference: Stryke/stryke.py:2620-3517).
+
+Host work: validation, per-unit dictionaries, hydrographs, daily operating hours, one routing/strike table per
+(scenario, day); then ONE call into the CUDA engine for every (scenario, species, iteration, day) cell, and the
+assembly of the reference's result frames (Daily, State_Daily, Route_Flows, Unit_Hours) from the tally arrays.
+"""
+from __future__ import annotations
+
+import logging
+import math
+import os
+from dataclasses import dataclass
+
+import numpy as np
+import pandas as pd
+
+from . import _abi, engine, tables
+from .store import open_store
+
+logger = logging.getLogger(__name__)
+
+CFS_TO_CMS = 0.02831683199881    # stryke.py:3253
+
+
+def _flag(name, default="0"):
+    return str(os.environ.get(name, default)).strip().lower() in ("1", "true", "yes", "on")
+
+
+@dataclass
+class Group:
+    """All cells of one (scenario, species): ``iterations`` x ``days`` of them."""
+    scen_index: int
+    scenario: str
+    scen_num: object
+    season: object
+    species: str
+    species_index: int
+    iterations: int
+    day0: int            # first row of this scenario in the day tables
+    n_days: int
+    cell0: int = 0       # first cell of the group in engine order (day-major, iteration-minor)
+    n_active_days: int = 0
+
+
+class RunPlan:
+    """Everything ``run()`` derives on the host before the device call."""
+
+    def __init__(self, sim):
+        self.sim = sim
+        sim._validate_unit_params_required_fields()
+        sim._route_flow_logged_keys = set()
+        sim._mortality_components = {"impingement": 0, "blade_strike": 0, "barotrauma": 0, "latent": 0}
+        sim.create_route()
+        if not hasattr(sim, "moves") or sim.moves is None:
+            raise RuntimeError("moves not initialized; create_route() must set moves before run.")
+        self.ctx = tables.RunContext(sim)
+        self.fac = tables.build_facility(sim, self.ctx)
+        sim.barotrauma_required = self.fac.barotrauma
+        self.day_rows = []          # (scenario, curr_Q)
+        self.day_dates = []
+        self.groups = []
+        self.species_params = []
+        self.scen_days = {}
+        self._enumerate()
+        self.days = tables.build_days(sim, self.ctx, self.fac, self.day_rows)
+        tables.finalize_levels(self.fac, self.days)
+        self._hours()
+        self._cells()
+
+    # ---- scenario / species enumeration (stryke.py:2806-2897) -----------------------------------------------
+    def _enumerate(self):
+        sim = self.sim
+        total = len(sim.flow_scenarios)
+        for si, scen in enumerate(sim.flow_scenarios):
+            print(f"[INFO] Processing scenario {si + 1} of {total}: {scen}", flush=True)
+            if not hasattr(sim, "flow_scenarios_df") or sim.flow_scenarios_df is None:
+                raise ValueError("flow_scenarios_df is missing; cannot process scenarios.")
+            sdf = sim.flow_scenarios_df[sim.flow_scenarios_df["Scenario"] == scen]
+            if sdf.empty:
+                raise ValueError(f"Scenario '{scen}' not found in flow_scenarios_df.")
+            col = lambda c: sdf.iat[0, sdf.columns.get_loc(c)]
+            scen_num, season, scenario, months = col("Scenario Number"), col("Season"), col("Scenario"), col("Months")
+            sim.discharge_type = "hydrograph" if col("Flow") == "hydrograph" else "fixed"
+            if isinstance(months, (int, np.integer)):
+                months = [int(months)]
+            else:
+                months = [int(m) for m in str(months).split(",")]
+            if not hasattr(sim, "operating_scenarios_df") or sim.operating_scenarios_df is None:
+                raise ValueError("operating_scenarios_df is missing; cannot process operating scenarios.")
+            if sim.operating_scenarios_df[sim.operating_scenarios_df["Scenario"] == scenario].empty:
+                raise ValueError(f"Scenario '{scenario}' not found in operating_scenarios_df.")
+            if sim.discharge_type == "hydrograph":
+                flow_df = sim.create_hydrograph("hydrograph", scen, months, sim.flow_scenarios_df)
+            else:
+                flow_df = sim.create_hydrograph("fixed", scen, months, sim.flow_scenarios_df, fixed_discharge=col("Flow"))
+            n_days = len(flow_df)
+            print(f"[INFO] Scenario '{scenario}' will simulate {n_days} days", flush=True)
+            day0 = len(self.day_rows)
+            for q, day in zip(flow_df["DAvgFlow_prorate"].values, flow_df["datetimeUTC"].values):
+                self.day_rows.append((scenario, float(q)))
+                self.day_dates.append(pd.to_datetime(day))
+            self.scen_days[scenario] = (day0, n_days)
+            for spc in sim.pop.Species.unique():
+                dat = sim.pop[(sim.pop["Scenario"] == scenario) & (sim.pop.Species == spc)]
+                if dat.empty:
+                    continue
+                iterations = int(dat.iat[0, dat.columns.get_loc("Iterations")])
+                self.species_params.append(tables.species_row(sim, dat))
+                self.groups.append(Group(si, scenario, scen_num, season, str(dat.iat[0, dat.columns.get_loc("Species")]),
+                                         len(self.species_params) - 1, iterations, day0, n_days))
+                print(f"[INFO] Simulating species: {self.groups[-1].species} with {iterations} iterations", flush=True)
+
+    # ---- daily operating hours (stryke.py:2979, :3025) ------------------------------------------------------
+    def _hours(self):
+        sim = self.sim
+        n = len(self.day_rows)
+        self.tot_hours = np.zeros(n)
+        self.hours = [None] * n
+        self.peaking = False
+        fp = sim.facility_params
+        ops = fp["Operations"].astype(str).values if "Operations" in fp.columns else []
+        self.peaking = any(o != "run-of-river" for o in ops)
+        cache = {}
+        for d, (scenario, q) in enumerate(self.day_rows):
+            key = (scenario, q)
+            if self.peaking or key not in cache:
+                th, _, hd, _ = sim.daily_hours(self.ctx.q_dict(q, scenario), scenario)
+                cache[key] = (float(np.sum(th)), dict(hd))
+            self.tot_hours[d], self.hours[d] = cache[key]
+
+    # ---- the cell list, engine order: group -> day -> iteration ----------------------------------------------
+    def _cells(self):
+        day_idx, sp_idx, ids = [], [], []
+        c0 = 0
+        max_it = max([g.iterations for g in self.groups] + [1])
+        max_days = max([g.n_days for g in self.groups] + [1])
+        n_sp = max(len(self.species_params), 1)
+        for g in self.groups:
+            g.cell0 = c0
+            if self.peaking:
+                # hours are random per (species, iteration, day) in a peaking plant; drawn on the host like the
+                # reference does (SURVEY.md §8 f-4 "next" row) — every cell keeps its own draw
+                active = np.ones(g.n_days, bool)
+            else:
+                active = self.tot_hours[g.day0:g.day0 + g.n_days] > 0
+            days = np.nonzero(active)[0]
+            g.active_days = days
+            g.n_active_days = len(days)
+            dd = np.repeat(days, g.iterations)
+            ii = np.tile(np.arange(g.iterations), len(days))
+            day_idx.append((g.day0 + dd).astype(np.int32))
+            sp_idx.append(np.full(dd.shape[0], g.species_index, np.int32))
+            ids.append((((np.uint64(g.scen_index) * np.uint64(n_sp) + np.uint64(g.species_index)) * np.uint64(max_it)
+                         + ii.astype(np.uint64)) * np.uint64(max_days) + dd.astype(np.uint64)))
+            c0 += dd.shape[0]
+        cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
+        self.cell_day, self.cell_species, self.cell_id = cat(day_idx, np.int32), cat(sp_idx, np.int32), cat(ids, np.uint64)
+        self.n_cells = c0
+
+    @property
+    def species_table(self):
+        return np.stack(self.species_params) if self.species_params else np.zeros((0, _abi.SPECIES_W))
+
+    def fish_cap(self):
+        """Effective per-cell population cap: STRYKE_MAX_DAILY_FISH (stryke.py:2610, :3052) and
+        STRYKE_MAX_DAILY_STATE_ROWS / len(moves) (stryke.py:3059-3067)."""
+        max_fish = int(os.environ.get("STRYKE_MAX_DAILY_FISH", "100000"))
+        max_rows = int(os.environ.get("STRYKE_MAX_DAILY_STATE_ROWS", "2000000"))
+        return max_fish, max_rows, max(1, len(self.sim.moves))
+
+    def check_fixed_counts(self):
+        max_fish, max_rows, M = self.fish_cap()
+        for g in self.groups:
+            p = self.species_params[g.species_index]
+            if int(p[12]) != _abi.ENT["fixed"]:
+                continue
+            n = int(p[18]) or 1
+            if n > max_fish:
+                raise ValueError(f"Population size n={n} exceeds STRYKE_MAX_DAILY_FISH={max_fish} for species "
+                                 f"'{g.species}', scenario '{g.scenario}'. Reduce entrainment parameters or increase "
+                                 "STRYKE_MAX_DAILY_FISH deliberately.")
+            if n * M > max_rows:
+                raise ValueError(f"Estimated daily state rows {n * M} exceed STRYKE_MAX_DAILY_STATE_ROWS={max_rows} "
+                                 f"(n={n}, moves={M}, species='{g.species}', scenario='{g.scenario}').")
+
+
+def run_simulation(sim, injected=None, trace=None):
+    """Body of ``simulation.run()``."""
+    print("[DEBUG RUN START] ========== SIMULATION BEGINNING ==========", flush=True)
+    print(f"[DEBUG RUN START] Project: {getattr(sim, 'project_name', 'UNKNOWN')}", flush=True)
+    print(f"[DEBUG RUN START] Population records: {len(sim.pop) if hasattr(sim, 'pop') else 'NO POP DATA'}", flush=True)
+    print(f"[DEBUG RUN START] Unit params: {len(sim.unit_params) if hasattr(sim, 'unit_params') else 'NO UNITS'} units", flush=True)
+    plan = RunPlan(sim)
+    plan.check_fixed_counts()
+    max_fish, max_rows, M = plan.fish_cap()
+    cap = min(max_fish, max_rows // M)
+    try:
+        res = engine.run_cells(plan.fac, plan.days, plan.species_table, plan.cell_day, plan.cell_species, plan.cell_id,
+                               device=sim.device, precision=sim.precision, seed=sim.seed, max_daily_fish=cap,
+                               injected=injected, trace=trace)
+    except _abi.StrykeError as exc:
+        if exc.code == _abi.E_MAX_FISH:
+            raise ValueError(f"{exc}. Adjust entrainment inputs or raise STRYKE_MAX_DAILY_FISH / "
+                             "STRYKE_MAX_DAILY_STATE_ROWS deliberately.") from exc
+        raise
+    sim._last_plan, sim._last_result = plan, res
+    frames = assemble_frames(sim, plan, res)
+    with open_store(sim.hdf_path, mode="a") as hdf:
+        for key, df in frames.items():
+            if df is not None and len(df):
+                kw = {}
+                if key == "State_Daily":
+                    kw = dict(min_itemsize={"scenario": 128, "species": 128, "state": 256})
+                elif key in ("Route_Flows", "Unit_Hours"):
+                    kw = dict(min_itemsize={"scenario": 128, "route": 256})
+                hdf.append(key, df, **kw)
+    for g in plan.groups:
+        print(f"[INFO] ✅ Completed scenario '{g.scenario}' for species {g.species}", flush=True)
+    print("[INFO] ✅ All scenarios complete! Finalizing results...", flush=True)
+    print("[INFO] 💾 Simulation data saved successfully", flush=True)
+    return None
+
+
+def assemble_frames(sim, plan: RunPlan, res: engine.CellResult):
+    """Tally arrays -> the reference's result frames, in the reference's row order
+    (scenario -> species -> iteration -> day; stryke.py:3256-3383, :3433-3502)."""
+    fac = plan.fac
+    P = fac.n_pairs
+    metric = sim.output_units == "metric"
+    dates = np.array(plan.day_dates, dtype="datetime64[ns]")
+    pair_name = np.array([fac.node_names[v] for v in fac.pair_node], dtype=object)
+    # State_Daily rows of one cell come out of a groupby per move: moves ascending, states alphabetical (:3319-3324)
+    pair_order = np.array(sorted(range(P), key=lambda p: (int(fac.pair_move[p]), str(pair_name[p]))), dtype=np.int64)
+    daily_parts, sd_parts, rf_parts, uh_parts = [], [], [], []
+    logged = sim._route_flow_logged_keys
+    for g in plan.groups:
+        D, I = g.n_active_days, g.iterations
+        if D == 0 or I == 0:
+            continue
+        sl = slice(g.cell0, g.cell0 + D * I)
+        # engine order (day, iteration) -> reference order (iteration, day)
+        n = res.cell_n[sl].reshape(D, I).T.astype(np.int64)
+        dl = res.daily[sl].reshape(D, I, _abi.DAILY_W).transpose(1, 0, 2).astype(np.int64)
+        sd = res.state_daily[sl].reshape(D, I, P, 2).transpose(1, 0, 2, 3)
+        day_rows = g.day0 + g.active_days
+        flow = plan.days.curr_Q[day_rows] * (CFS_TO_CMS if metric else 1.0)
+        it_col = np.repeat(np.arange(I, dtype=np.int64), D)
+        day_col = np.tile(dates[day_rows], I)
+        ent, sur = dl[..., 0].ravel(), dl[..., 1].ravel()
+        gate = ent > 0                                              # stryke.py:3359
+        daily_parts.append(pd.DataFrame({
+            "species": "{:50}".format(g.species), "scenario": "{:50}".format(g.scenario), "season": "{:50}".format(g.season),
+            "iteration": it_col, "day": day_col, "flow": np.tile(flow.astype(np.float64), I),
+            "pop_size": n.ravel(), "num_entrained": ent, "num_survived": sur, "num_mortality": ent - sur,
+            "mortality_impingement": np.where(gate, dl[..., 2].ravel(), 0),
+            "mortality_blade_strike": np.where(gate, dl[..., 3].ravel(), 0),
+            "mortality_barotrauma": np.where(gate, dl[..., 4].ravel(), 0)}))
+        cnt = sd[..., 1].reshape(I * D, P)[:, pair_order]
+        suc = sd[..., 0].reshape(I * D, P)[:, pair_order]
+        ci, pi = np.nonzero(cnt)
+        if ci.size:
+            sd_parts.append(pd.DataFrame({
+                "scenario": str(g.scenario), "species": str(g.species), "iteration": it_col[ci].astype(int),
+                "day": day_col[ci], "move": fac.pair_move[pair_order][pi].astype(int),
+                "state": pair_name[pair_order][pi].astype(str), "successes": suc[ci, pi].astype(float),
+                "count": cnt[ci, pi].astype(float)}))
+        # Route_Flows / Unit_Hours: once per (scenario, iteration, day), by the first species that gets there (:3437)
+        fresh = np.array([(g.scenario, i, int(d)) not in logged for i in range(I) for d in day_rows])
+        if fresh.any():
+            rf, uh = _route_and_hours(sim, plan, g, suc.reshape(I, D, P), pair_order, fresh.reshape(I, D), day_rows, dates)
+            rf_parts += rf
+            uh_parts += uh
+            for i in range(I):
+                for d in day_rows:
+                    logged.add((g.scenario, i, int(d)))
+    cat = lambda parts: pd.concat(parts, ignore_index=True) if parts else None
+    return {"Daily": cat(daily_parts), "State_Daily": cat(sd_parts), "Route_Flows": cat(rf_parts), "Unit_Hours": cat(uh_parts)}
+
+
+def _route_and_hours(sim, plan, g, suc, pair_order, fresh, day_rows, dates):
+    """Route_Flows (stryke.py:3433-3462): the flows ``movement`` recorded for the successors of every node a live
+    fish stood at before the last move; Unit_Hours (stryke.py:3463-3502): hours_dict x the day's allocation."""
+    fac = plan.fac
+    I, D, P = suc.shape
+    moves = fac.pair_move[pair_order]
+    nodes = fac.pair_node[pair_order]
+    last = fac.n_moves - 1
+    rf_rows, uh_rows = [], []
+    unit_pos = {u: j for j, u in enumerate(fac.unit_names)}
+    for j, d in enumerate(day_rows):
+        its = np.nonzero(fresh[:, j])[0]
+        if its.size == 0:
+            continue
+        stay = plan.days.node_stay[d]
+        hours = plan.hours[d] or {}
+        alloc = {str(u): float(plan.days.unit_Q[d, unit_pos[u]]) for u in fac.unit_names}
+        if hours:
+            names = list(hours.keys())
+            uh_rows.append(pd.DataFrame({
+                "scenario": str(g.scenario), "iteration": np.repeat(its, len(names)).astype(int), "day": dates[d],
+                "route": np.tile(np.array(names, dtype=object), its.size).astype(str),
+                "hours": np.tile(np.array([float(hours[k]) for k in names]), its.size),
+                "discharge_cfs": np.tile(np.array([alloc.get(str(k), np.nan) for k in names]), its.size)}))
+        live = suc[its, j, :] > 0                                   # (len(its), P): a live fish stood at this pair
+        for r, i in enumerate(its):
+            rec = {}
+            for p in np.nonzero(live[r] & (moves < last))[0]:
+                v = int(nodes[p])
+                if stay[v]:
+                    continue
+                lo, hi = fac.edge_off[v], fac.edge_off[v + 1]
+                for name, q in zip(fac.succ_order[v], plan.days.edge_flow[d, lo:hi]):
+                    rec[name] = float(q)
+            if rec:
+                rf_rows.append(pd.DataFrame({"scenario": str(g.scenario), "iteration": int(i), "day": dates[d],
+                                             "route": np.array(list(rec.keys()), dtype=object).astype(str),
+                                             "discharge_cfs": list(rec.values())}))
+    return rf_rows, uh_rows
