@@ -138,6 +138,7 @@ typedef struct StrykeOpts {
   int32_t  blocks_per_sm;       /* 0 = default                                                             */
   const StrykeInjected* injected;  /* NULL = native Philox                                                 */
   const StrykeTrace*    trace;     /* NULL = tallies only (needs fish_off: injected mode or fixed counts)   */
+  int32_t  kernel_variant;      /* 0 = auto (fp32 + native RNG + no trace -> passage_fast_kernel), 1 = always the general passage_kernel */
 } StrykeOpts;
 
 /* Host-side result buffers, caller-allocated. */

@@ -54,7 +54,8 @@ class Trace(C.Structure):
 
 class Opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("precision", C.c_int32), ("seed", C.c_uint64), ("max_daily_fish", C.c_int32),
-                ("blocks_per_sm", C.c_int32), ("injected", C.POINTER(Injected)), ("trace", C.POINTER(Trace))]
+                ("blocks_per_sm", C.c_int32), ("injected", C.POINTER(Injected)), ("trace", C.POINTER(Trace)),
+                ("kernel_variant", C.c_int32)]
 
 
 class Tallies(C.Structure):

@@ -23,6 +23,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <vector>
@@ -503,10 +504,11 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
       const bool prev_alive = alive;
       float rate32 = 0.f;
       int slot = mv.slot_base;
-      const int s_dice = slot; slot += (mv.need & NEED_DICE) ? 1 : 0;
+      // words are laid out in consumption order: rR, depth, cause, dice, route
       const int s_rr = slot;   slot += (mv.need & NEED_RR) ? 1 : 0;
       const int s_dep = slot;  slot += (mv.need & NEED_DEPTH) ? 1 : 0;
       const int s_cau = slot;  slot += (mv.need & NEED_CAUSE) ? 1 : 0;
+      const int s_dice = slot; slot += (mv.need & NEED_DICE) ? 1 : 0;
       const int s_rt = slot;
       uint32_t w_rr = 0, w_dep = 0, w_cau = 0;
       if (!INJECT) {   // warp-uniform draws for this move (refill points are identical for every lane)
@@ -529,7 +531,8 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
             Real rR = (Real)0.75;
             if (nd.kind == STRYKE_KIND_KAPLAN) {
               if (INJECT) rR = (Real)add_(0.3, mul_(sub_(1.0, 0.3), P.inj.rR[(int64_t)k * NF + gi]));
-              else rR = (Real)0.3 + (Real)0.7 * u_co<Real>(w_rr);
+              else if (sizeof(Real) == 8) rR = (Real)(0.3 + 0.7 * (double)u_co<Real>(w_rr));
+              else rR = (Real)fmaf(0.7f, (float)u_co<Real>(w_rr), 0.3f);
             }
             if (sizeof(Real) == 8) strike = (Real)strike_surv64(nd.kind, (const double*)uc, (double)L, (double)rR);
             else strike = (Real)strike_surv32(nd.kind, (const float*)uc, (float)L, (float)rR);
@@ -658,6 +661,10 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
   if (cur_cell >= 0) flush(cur_cell);
 }
 
+}  // namespace stryke
+#include "passage_fast.cuh"
+namespace stryke {
+
 // ------------------------------------------------------------------------------------------------------------------
 // small utility kernels: per-fish probability functions, Philox KAT, issue-rate calibration
 // ------------------------------------------------------------------------------------------------------------------
@@ -721,6 +728,7 @@ static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches{0};
 
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+static inline uint32_t __float_as_uint_host(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 #define CK(expr)                                                                                           \
   do {                                                                                                     \
     cudaError_t e_ = (expr);                                                                               \
@@ -759,6 +767,10 @@ struct StrykePlan {
       cell_species, cell_id, tile_off, fish_off, part, err;
   DevBuf i_fish_off, i_presence, i_count, i_z, i_dice, i_rR, i_depth, i_cause, i_route, i_grR, i_gdepth, i_gcause;
   DevBuf t_len32, t_len64, t_state, t_rate, t_surv, t_strike, t_baro;
+  DevBuf fast_nodes;
+  FastTables fast{};
+  size_t fast_smem_bytes = 0;
+  bool use_fast = false;
   int64_t trace_fish = 0;
   bool has_trace = false, trace_probs = false;
 };
@@ -963,6 +975,24 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
   pl->smem = (size_t)SL.total;
   if (pl->smem > 200 * 1024) return fail(STRYKE_E_LIMIT, "facility tables do not fit in shared memory");
   pl->blocks_per_sm = o->blocks_per_sm;
+  // ---- throughput variant: fp32, native Philox, tallies only ---------------------------------------------------------
+  pl->use_fast = pl->precision == 32 && !pl->inject && !pl->has_trace && o->kernel_variant != 1;
+  if (pl->use_fast) {
+    std::vector<uint2> fn(f->n_nodes);
+    for (int i = 0; i < f->n_nodes; ++i) {
+      fn[i].x = __float_as_uint_host(nodes[i].apriori32);
+      fn[i].y = pack_node(nodes[i].edge_off, nodes[i].deg, nodes[i].kind, nodes[i].hasU, nodes[i].unit);
+    }
+    CK(upload(pl->fast_nodes, fn.data(), fn.size()));
+    for (int k = 0; k < f->n_moves; ++k) {
+      pl->fast.moves[k] = moves[k];
+      int md = 0;
+      for (int p = moves[k].level_begin; p < moves[k].level_end; ++p) md = std::max(md, (int)nodes[pnode[p]].deg);
+      pl->fast.max_deg[k] = (uint8_t)md;
+    }
+    for (int p = 0; p < f->n_pairs; ++p) pl->fast.pair_node[p] = pnode[p];
+    pl->fast_smem_bytes = (size_t)fast_smem(f->n_nodes, f->n_units, f->n_edges, pl->n_species_staged).total;
+  }
   CK(cudaDeviceSynchronize());
   guard.p = nullptr;
   *out = pl;
@@ -994,6 +1024,30 @@ static int launch_passage_pr(StrykePlan* pl, cudaStream_t st) {
   }
 }
 
+template <int PR, bool BARO>
+static int launch_fast(StrykePlan* pl, cudaStream_t st) {
+  auto kern = passage_fast_kernel<PR, BARO>;
+  if (pl->fast_smem_bytes > 48 * 1024)
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem_bytes));
+  int bps = pl->blocks_per_sm;
+  if (bps <= 0) {
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, BLOCK, pl->fast_smem_bytes));
+    if (bps < 1) bps = 1;
+  }
+  kern<<<pl->n_sm * bps, BLOCK, pl->fast_smem_bytes, st>>>(pl->K, pl->fast, pl->fast_nodes.as<uint2>(), pl->n_species_staged);
+  g_launches++;
+  CK(cudaGetLastError());
+  return STRYKE_OK;
+}
+static int launch_fast_any(StrykePlan* pl, cudaStream_t st) {
+  const bool b = pl->K.barotrauma != 0;
+  switch (pl->pr) {
+    case 1: return b ? launch_fast<1, true>(pl, st) : launch_fast<1, false>(pl, st);
+    case 2: return b ? launch_fast<2, true>(pl, st) : launch_fast<2, false>(pl, st);
+    default: return b ? launch_fast<4, true>(pl, st) : launch_fast<4, false>(pl, st);
+  }
+}
+
 extern "C" {
 
 int stryke_b200_plan_launch(StrykePlan* pl, int32_t* d_cell_n, uint32_t* d_daily, uint32_t* d_state_daily, void* stream) {
@@ -1014,6 +1068,7 @@ int stryke_b200_plan_launch(StrykePlan* pl, int32_t* d_cell_n, uint32_t* d_daily
   scan_final<<<pl->nb_scan, SCAN_T, 0, st>>>(d_cell_n, pl->n_cells, pl->part.as<int64_t>(), pl->tile_off.as<int64_t>(), pl->fish_off.as<int64_t>());
   g_launches += 4;
   CK(cudaGetLastError());
+  if (pl->use_fast) return launch_fast_any(pl, st);
   if (pl->precision == 64) return pl->inject ? launch_passage_pr<double, true>(pl, st) : launch_passage_pr<double, false>(pl, st);
   return pl->inject ? launch_passage_pr<float, true>(pl, st) : launch_passage_pr<float, false>(pl, st);
 }

@@ -1,0 +1,269 @@
+// passage_fast.cuh — the throughput variant of the passage kernel: fp32 arithmetic, native Philox stream, tallies only.
+//
+// Same algorithm, same Philox word schedule and same fp32 formulas as passage_kernel<float, false, PR> (which is
+// validated bit-for-bit against the reference in injected mode), restructured for instruction issue, the roofline
+// that binds this path:
+//   * the per-move records and the (move, node) pair list live in the kernel parameter (constant) bank, so every
+//     loop bound and "does this level need a draw" test is warp-uniform: no BSSY/BSYNC reconvergence code;
+//   * the per-fish branchy code of node_surv_rate (stryke.py:1396-1572) is straight-line predicated arithmetic: one
+//     unified strike formula (Kaplan and linear runners differ only in staged coefficients), selects instead of ifs;
+//   * node records are one 8-byte shared-memory load, unit coefficients one 16-byte load;
+//   * Philox words are popped in consumption order, so exactly ceil(W/4) blocks are generated per fish.
+// tests/test_gpu_native_rng.py::test_fast_kernel_equals_general_kernel requires identical tallies from both.
+#pragma once
+
+namespace stryke {
+
+struct FastTables {                 // by-value kernel parameter (constant bank), 664 bytes
+  MoveRec moves[STRYKE_MAX_MOVES];
+  uint8_t pair_node[STRYKE_MAX_PAIRS];
+  uint8_t max_deg[STRYKE_MAX_MOVES];   // largest out-degree among the nodes of each level (uniform route-loop bound)
+};
+
+// FastNode.y: edge_off[0:11) deg[11:19) kind[19:22) hasU[22] unit[23:30)
+__host__ __device__ inline uint32_t pack_node(int edge_off, int deg, int kind, int hasU, int unit) {
+  return (uint32_t)edge_off | ((uint32_t)deg << 11) | ((uint32_t)kind << 19) | ((uint32_t)(hasU ? 1 : 0) << 22) |
+         ((uint32_t)(unit < 0 ? 0 : unit) << 23);
+}
+
+struct FastSmem {
+  int nodes, edge_dst, ustatic, uc1, species, warp0, warp_stride, cdf, ucoef, stay, total;
+};
+__host__ __device__ inline FastSmem fast_smem(int n_nodes, int n_units, int n_edges, int n_species_staged) {
+  auto al = [](int x) { return (x + 15) & ~15; };
+  FastSmem L;
+  int o = 0;
+  L.nodes = o; o = al(o + n_nodes * 8);
+  L.edge_dst = o; o = al(o + n_edges);
+  L.ustatic = o; o = al(o + n_units * 16);
+  L.uc1 = o; o = al(o + n_units * 4);
+  L.species = o; o = al(o + n_species_staged * SPW * 4);
+  L.warp0 = o;
+  int w = 0;
+  L.cdf = w; w = al(w + n_edges * 4);
+  L.ucoef = w; w = al(w + n_units * 16);
+  L.stay = w; w = al(w + n_nodes);
+  L.warp_stride = w;
+  L.total = o + w * WARPS;
+  return L;
+}
+
+struct WordStream {   // Philox words in consumption order; `pos` only ever changes under warp-uniform control flow
+  uint32_t c0, c1, c2, k0, k1, w0, w1, w2, w3;
+  int pos;
+  __device__ __forceinline__ void init(uint32_t fish, uint64_t cell_id, uint32_t seed_lo, uint32_t seed_hi) {
+    c0 = fish; c1 = (uint32_t)cell_id; c2 = (uint32_t)(cell_id >> 32); k0 = seed_lo; k1 = seed_hi; pos = 0;
+  }
+  __device__ __forceinline__ uint32_t pop() {
+    if ((pos & 3) == 0) {
+      uint32_t w[4];
+      Philox::block(c0, c1, c2, (uint32_t)(pos >> 2), k0, k1, w);
+      w0 = w[0]; w1 = w[1]; w2 = w[2]; w3 = w[3];
+    }
+    const uint32_t r = w0;
+    w0 = w1; w1 = w2; w2 = w3;
+    ++pos;
+    return r;
+  }
+};
+
+template <int PR, bool BARO>
+__global__ void __launch_bounds__(BLOCK, 4) passage_fast_kernel(const KParams P, const __grid_constant__ FastTables FT,
+                                                                const uint2* __restrict__ g_nodes, const int n_species_staged) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const FastSmem SL = fast_smem(P.n_nodes, P.n_units, P.n_edges, n_species_staged);
+  uint2* s_nodes = reinterpret_cast<uint2*>(smem + SL.nodes);
+  uint8_t* s_edge_dst = smem + SL.edge_dst;
+  float4* s_ustatic = reinterpret_cast<float4*>(smem + SL.ustatic);     // rack, intake_vel, fb_depth, c0
+  float* s_uc1 = reinterpret_cast<float*>(smem + SL.uc1);               // c1
+  float* s_species = reinterpret_cast<float*>(smem + SL.species);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned char* wbase = smem + SL.warp0 + wid * SL.warp_stride;
+  float* s_cdf = reinterpret_cast<float*>(wbase + SL.cdf);
+  float4* s_ucoef = reinterpret_cast<float4*>(wbase + SL.ucoef);        // fa, fb, fc, has_flow
+  uint8_t* s_stay = wbase + SL.stay;
+
+  for (int i = threadIdx.x; i < P.n_nodes; i += BLOCK) s_nodes[i] = g_nodes[i];
+  for (int i = threadIdx.x; i < P.n_edges; i += BLOCK) s_edge_dst[i] = P.edge_dst[i];
+  for (int u = threadIdx.x; u < P.n_units; u += BLOCK) {
+    const double* us = P.unit_static + u * STRYKE_UNIT_STATIC_W;
+    const double p2 = P_ATM + RHO * G_SI * (us[3] * FT2M);
+    s_ustatic[u] = make_float4((float)us[0], (float)us[1], (float)us[2], (float)(P_ATM / p2));
+    s_uc1[u] = (float)(RHO * G_SI * FT2M / p2);
+  }
+  for (int i = threadIdx.x; i < n_species_staged * SPW; i += BLOCK)
+    s_species[i] = (float)P.species[(i / SPW) * STRYKE_SPECIES_W + (i % SPW)];
+  __syncthreads();
+
+  const int64_t T = P.tile_off[P.n_cells];
+  const int64_t G = (int64_t)gridDim.x * WARPS, gw = (int64_t)blockIdx.x * WARPS + wid;
+  const int64_t t0 = (T / G) * gw + min(gw, T % G), t1 = t0 + T / G + (gw < T % G ? 1 : 0);
+  if (t0 >= t1) return;
+  int64_t c;
+  {
+    int64_t lo = 0, hi = P.n_cells;
+    while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (P.tile_off[mid] <= t0) lo = mid; else hi = mid; }
+    c = lo;
+  }
+  int64_t c_end = P.tile_off[c + 1], c_begin = P.tile_off[c];
+  int cur_day = -1;
+  int64_t cur_cell = -1;
+  float sp_ls = 0, sp_ll = 0, sp_lsc = 0, sp_lm = 0, sp_lsd = 0, sp_wr = 0, sp_uc = 0, sp_d1 = 0, sp_dd = 0, sp_b0 = 0, sp_b1 = 0;
+  int sp_mode = 0, n_c = 0;
+  uint64_t cid = 0;
+  uint32_t acc_suc[PR], acc_cnt[PR], acc_daily = 0;
+#pragma unroll
+  for (int r = 0; r < PR; ++r) { acc_suc[r] = 0; acc_cnt[r] = 0; }
+
+  auto flush = [&](int64_t cell) {
+#pragma unroll
+    for (int r = 0; r < PR; ++r) {
+      const int p = r * 32 + lane;
+      if (p < P.n_pairs && acc_cnt[r]) {
+        uint32_t* dst = P.state_daily + ((size_t)cell * P.n_pairs + p) * 2;
+        if (acc_suc[r]) atomicAdd(dst, acc_suc[r]);
+        atomicAdd(dst + 1, acc_cnt[r]);
+      }
+      acc_suc[r] = 0; acc_cnt[r] = 0;
+    }
+    if (lane < STRYKE_DAILY_W && acc_daily) atomicAdd(P.daily + (size_t)cell * STRYKE_DAILY_W + lane, acc_daily);
+    acc_daily = 0;
+  };
+
+  const int n_moves = P.n_moves;
+  for (int64_t t = t0; t < t1; ++t) {
+    while (t >= c_end) { ++c; c_begin = c_end; c_end = P.tile_off[c + 1]; }
+    if (c != cur_cell) {
+      if (cur_cell >= 0) flush(cur_cell);
+      cur_cell = c;
+      n_c = P.cell_n[c];
+      cid = P.cell_id[c];
+      const int s = P.cell_species[c];
+      if (s < n_species_staged) {
+        const float* q = s_species + s * SPW;
+        sp_ls = q[0]; sp_ll = q[1]; sp_lsc = q[2]; sp_lm = q[3]; sp_lsd = q[4]; sp_mode = (int)q[5];
+        sp_wr = q[6]; sp_uc = q[7]; sp_d1 = q[8]; sp_dd = q[9] - q[8]; sp_b0 = q[10] * 1.44269504f; sp_b1 = q[11];
+      } else {
+        const double* q = P.species + (int64_t)s * STRYKE_SPECIES_W;
+        sp_ls = (float)q[0]; sp_ll = (float)q[1]; sp_lsc = (float)q[2]; sp_lm = (float)q[3]; sp_lsd = (float)q[4];
+        sp_mode = (int)q[5]; sp_wr = (float)q[6]; sp_uc = (float)q[7]; sp_d1 = (float)q[8];
+        sp_dd = (float)q[9] - (float)q[8]; sp_b0 = (float)q[10] * 1.44269504f; sp_b1 = (float)q[11];
+      }
+      const int d = P.cell_day[c];
+      if (d != cur_day) {
+        cur_day = d;
+        __syncwarp();
+        const double* cdf = P.edge_cdf + (size_t)d * P.n_edges;
+        for (int i = lane; i < P.n_edges; i += 32) s_cdf[i] = (float)cdf[i];
+        const uint8_t* st = P.node_stay + (size_t)d * P.n_nodes;
+        for (int i = lane; i < P.n_nodes; i += 32) s_stay[i] = st[i];
+        const double* uc = P.unit_coef + (size_t)d * P.n_units * STRYKE_UNIT_COEF_W;
+        for (int u = lane; u < P.n_units; u += 32) {
+          const double* r = uc + u * STRYKE_UNIT_COEF_W;
+          const double lnd = r[0] * r[1] / r[2];
+          const bool kap = r[4] != 0.0 || r[5] != 0.0;
+          // linear runners use the Kaplan formula with fa = 0, fb = 1, rR = 1:  p = fc * L * rsqrt(1) * (1*1 + 0)
+          s_ucoef[u] = make_float4(kap ? (float)(r[3] / r[4]) : 0.f, kap ? (float)(1.0 / r[5]) : 1.f,
+                                   kap ? (float)lnd : (float)(lnd * r[3]), (float)r[6]);
+        }
+        __syncwarp();
+      }
+    }
+    const int fish = (int)((t - c_begin) * 32 + lane);
+    const bool active = fish < n_c;
+
+    WordStream rng;
+    rng.init((uint32_t)fish, cid, P.seed_lo, P.seed_hi);
+    // ---- (2) length -------------------------------------------------------------------------------------------
+    const uint32_t wa = rng.pop(), wb = rng.pop();
+    const float z = std_normal(u_oc<float>(wa), u_co<float>(wb));
+    float L;
+    if (sp_mode == 0) L = fminf(fabsf(fmaf(__expf(sp_ls * z), sp_lsc, sp_ll)), 150.f) * 0.0328084f;
+    else L = fabsf(fmaf(sp_lsd, z, sp_lm)) * (1.f / 12.f);
+    const float blocked_w = L * sp_wr;
+
+    int loc = P.start_node;
+    bool alive = active;
+    int best_rank = 255;
+    bool ent_surv = false;
+    uint32_t cz = 0;
+
+    for (int k = 0; k < n_moves; ++k) {
+      const MoveRec mv = FT.moves[k];                    // constant bank: uniform
+      const uint2 nd = s_nodes[loc];
+      const uint32_t pk = nd.y;
+      const int kind = (pk >> 19) & 7, deg = (pk >> 11) & 0xff, eoff = pk & 0x7ff;
+      const bool prev_alive = alive;
+      float rate = alive ? __uint_as_float(nd.x) : 0.f;
+      if (mv.need & NEED_CAUSE) {                        // this level has turbine nodes (uniform)
+        const float u_rr = (mv.need & NEED_RR) ? u_co<float>(rng.pop()) : 0.f;
+        float u_dep = 0.f;
+        if (BARO) u_dep = u_co<float>(rng.pop());
+        const float u_cau = u_co<float>(rng.pop());
+        const bool turb = alive && kind != STRYKE_KIND_APRIORI;
+        const int unit = turb ? (int)((pk >> 23) & 0x7f) : 0;
+        const float4 us = s_ustatic[unit];
+        const float4 uc = s_ucoef[unit];
+        const bool blocked = blocked_w > us.x;                               // stryke.py:1419
+        const float imp = (blocked && sp_uc < us.y) ? 0.f : 1.f;             // stryke.py:1420-1423
+        const bool kap = kind == STRYKE_KIND_KAPLAN;
+        const float rR = kap ? fmaf(0.7f, u_rr, 0.3f) : 1.f;
+        const float inv = kap ? rsqrtf(fmaf(rR, rR, uc.x * uc.x)) : 1.f;   // exact 1 for the linear runners
+        float p = uc.z * L * inv * fmaf(rR, uc.y, __fdividef(uc.x * 0.318309886f, rR));
+        p = uc.w > 0.f ? p : INFINITY;
+        const float strike = blocked ? 1.f : __saturatef(1.f - p);
+        float baro = 1.f;
+        if (BARO) {
+          const float depth = us.z * fmaf(sp_dd, u_dep, sp_d1);
+          const float ratio = fmaf(s_uc1[unit], depth, us.w);
+          const float e = exp2f(fmaf(sp_b1, __log2f(ratio), sp_b0));
+          baro = blocked ? 1.f : __fdividef(1.f, 1.f + e);
+        }
+        const float a2 = imp * strike, a3 = a2 * baro;
+        rate = turb ? a3 : rate;
+        const uint32_t code = u_cau >= imp ? 1u : u_cau >= a2 ? (1u << 8) : u_cau >= a3 ? (1u << 16) : 0u;
+        cz += turb ? code : 0u;
+      }
+      bool surv;
+      if (mv.need & NEED_DICE) surv = alive && (u_oc<float>(rng.pop()) <= rate);
+      else surv = alive && rate >= 1.0f;
+
+      for (int p = mv.level_begin; p < mv.level_end; ++p) {                  // uniform bounds
+        const bool here = loc == (int)FT.pair_node[p];
+        const uint32_t bc = __ballot_sync(0xffffffffu, prev_alive && here);
+        const uint32_t bs = __ballot_sync(0xffffffffu, surv && here);
+#pragma unroll
+        for (int r = 0; r < PR; ++r)
+          if ((p >> 5) == r && (p & 31) == lane) { acc_cnt[r] += __popc(bc); acc_suc[r] += __popc(bs); }
+      }
+      const bool newU = ((pk >> 22) & 1u) && active && (int)mv.lex < best_rank;
+      best_rank = newU ? (int)mv.lex : best_rank;
+      ent_surv = newU ? surv : ent_surv;
+
+      if (k < n_moves - 1) {
+        const bool go = surv && deg > 0 && !s_stay[loc];
+        int j = 0;
+        if (mv.need & NEED_ROUTE) {
+          const float u = u_co<float>(rng.pop());
+          const int md = FT.max_deg[k];
+          for (int e = 0; e < md - 1; ++e) j += (e < deg - 1 && s_cdf[eoff + e] <= u) ? 1 : 0;
+        }
+        loc = go ? (int)s_edge_dst[eoff + j] : loc;
+      }
+      alive = surv;
+    }
+    const bool ent = active && best_rank < 255;
+    const uint32_t b_ent = __ballot_sync(0xffffffffu, ent);
+    const uint32_t b_sur = __ballot_sync(0xffffffffu, ent && ent_surv);
+    uint32_t r_imp = 0, r_bld = 0, r_bar = 0;
+    if (__ballot_sync(0xffffffffu, cz != 0)) {
+      r_imp = __reduce_add_sync(0xffffffffu, cz & 0xffu);
+      r_bld = __reduce_add_sync(0xffffffffu, (cz >> 8) & 0xffu);
+      r_bar = __reduce_add_sync(0xffffffffu, (cz >> 16) & 0xffu);
+    }
+    acc_daily += lane == 0 ? __popc(b_ent) : lane == 1 ? __popc(b_sur) : lane == 2 ? r_imp : lane == 3 ? r_bld : lane == 4 ? r_bar : 0u;
+  }
+  if (cur_cell >= 0) flush(cur_cell);
+}
+
+}  // namespace stryke

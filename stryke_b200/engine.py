@@ -80,8 +80,9 @@ class CellResult:
     trace: TraceBuffers | None = None
 
 
-def _opts(device, precision, seed, max_daily_fish, blocks_per_sm, injected, trace, keep):
+def _opts(device, precision, seed, max_daily_fish, blocks_per_sm, injected, trace, keep, kernel_variant=0):
     o = _abi.Opts()
+    o.kernel_variant = int(kernel_variant)
     o.device, o.precision, o.seed = int(device), int(precision), int(seed) & 0xFFFFFFFFFFFFFFFF
     o.max_daily_fish, o.blocks_per_sm = int(max_daily_fish), int(blocks_per_sm)
     if injected is not None:
@@ -110,12 +111,12 @@ def _tables(fac: FacilityTables, days: DayTables, species: np.ndarray, cell_day,
 
 def run_cells(fac, days, species, cell_day, cell_species, cell_id, *, device=0, precision=32, seed=0,
               max_daily_fish=100000, blocks_per_sm=0, injected: Injected | None = None,
-              trace: TraceBuffers | None = None) -> CellResult:
+              trace: TraceBuffers | None = None, kernel_variant=0) -> CellResult:
     """One call of ``stryke_b200_run``: everything between the presence roll and the Daily / State_Daily tallies
     (stryke.py:3025-3366) for the listed cells, on the GPU, host buffers in and out."""
     keep = []
     f, d, st, cl = _tables(fac, days, species, cell_day, cell_species, cell_id, keep)
-    o = _opts(device, precision, seed, max_daily_fish, blocks_per_sm, injected, trace, keep)
+    o = _opts(device, precision, seed, max_daily_fish, blocks_per_sm, injected, trace, keep, kernel_variant)
     n = int(cl.n_cells)
     out_n = np.zeros(n, np.int32)
     out_d = np.zeros((n, _abi.DAILY_W), np.uint32)
@@ -130,10 +131,10 @@ class Plan:
     """Device-resident tables + asynchronous launches into caller-owned device buffers."""
 
     def __init__(self, fac, days, species, cell_day, cell_species, cell_id, *, device=0, precision=32, seed=0,
-                 max_daily_fish=100000, blocks_per_sm=0, injected=None, trace=None):
+                 max_daily_fish=100000, blocks_per_sm=0, injected=None, trace=None, kernel_variant=0):
         self._keep = []
         f, d, st, cl = _tables(fac, days, species, cell_day, cell_species, cell_id, self._keep)
-        o = _opts(device, precision, seed, max_daily_fish, blocks_per_sm, injected, trace, self._keep)
+        o = _opts(device, precision, seed, max_daily_fish, blocks_per_sm, injected, trace, self._keep, kernel_variant)
         self.n_cells, self.n_pairs, self.device = int(cl.n_cells), fac.n_pairs, int(device)
         self._h = C.c_void_p()
         _abi.check(_abi.lib().stryke_b200_plan_create(C.byref(f), C.byref(d), C.byref(st), C.byref(cl), C.byref(o),

@@ -1,0 +1,258 @@
+"""``simulation.summary()`` — reference: Stryke/stryke.py:3520-4101 (host-side, runs once per project).
+
+Works from the ``Daily`` and ``State_Daily`` tables ``run()`` wrote (the ``simulations/{scen}/{spc}`` per-fish table
+is optional in the reference and not produced here): whole-project and per-(move, state) survival probabilities
+with empirical mean / std and bootstrap 95 % intervals, the yearly entrainment / mortality summary with 1-in-N day
+quantiles, and the unit-level driver diagnostics.  The bootstrap is vectorised: the reference's
+``n_bootstrap`` sequential ``np.random.choice(data, size=len(data))`` calls consume the global MT19937 stream exactly
+like one ``np.random.randint(0, n, size=(n_bootstrap, n))`` call, so under the same ``np.random.seed`` the intervals
+are identical (``bootstrap_mean_ci``, stryke.py:143-162).
+"""
+from __future__ import annotations
+
+import logging
+import os
+
+import numpy as np
+import pandas as pd
+
+from .store import open_store
+
+logger = logging.getLogger(__name__)
+
+BETA_CAPTION = (
+    "Means shown are empirical averages of per-iteration, per-day survival probabilities. "
+    "95% intervals are bootstrap estimates. Direct beta distribution fits are sensitive to values exactly 0 or 1 "
+    "and are not used for the reported mean.")
+
+
+def summarize_ci(series):
+    """stryke.py:136-140."""
+    return pd.Series({"mean": series.mean(), "lower_95_CI": np.percentile(series, 2.5),
+                      "upper_95_CI": np.percentile(series, 97.5)})
+
+
+def bootstrap_mean_ci(data, n_bootstrap=10000, ci=95, chunk_elems=1 << 24):
+    """Mean and bootstrap interval of ``data`` (stryke.py:143-162), resamples drawn ``chunk`` rows at a time."""
+    data = np.array(data)
+    n = len(data)
+    means = np.empty(n_bootstrap)
+    rows = max(1, int(chunk_elems // max(n, 1)))
+    for lo in range(0, n_bootstrap, rows):
+        hi = min(n_bootstrap, lo + rows)
+        idx = np.random.randint(0, n, size=(hi - lo, n))
+        means[lo:hi] = data[idx].mean(axis=1)
+    lower = np.percentile(means, (100 - ci) / 2)
+    upper = np.percentile(means, 100 - (100 - ci) / 2)
+    return np.mean(data), lower, upper
+
+
+def _mean_std_ci(prob_values, n_bootstrap=2000):
+    s = pd.Series(prob_values)
+    mean, std = s.mean(), s.std()
+    if len(prob_values) < 2:
+        return mean, std, mean, mean
+    _, lcl, ucl = bootstrap_mean_ci(prob_values, n_bootstrap=n_bootstrap, ci=95)
+    return mean, std, lcl, ucl
+
+
+def summarize(sim):
+    if not hasattr(sim, "wks_dir"):
+        sim.wks_dir = None
+    hdf_path = os.path.join(sim.proj_dir, "%s.h5" % sim.output_name)
+    with open_store(hdf_path, mode="r") as store:
+        sim.beta_dict = {}
+        species = store["Population"].Species.unique()
+        scens = store["Flow Scenarios"].Scenario.unique()
+        sim.daily_summary = store["Daily"].copy()
+        num_cols = list(sim.daily_summary.columns[6:])
+        sim.daily_summary[num_cols] = sim.daily_summary[num_cols].astype(float)      # stryke.py:3564
+        sim.daily_summary["species_norm"] = sim.daily_summary["species"].astype(str).str.strip()
+        sim.daily_summary["scenario_norm"] = sim.daily_summary["scenario"].astype(str).str.strip()
+        print("\n" + "=" * 60, flush=True)
+        print("SIMULATION SUMMARY STATISTICS", flush=True)
+        print("=" * 60, flush=True)
+        state_daily = store["State_Daily"].copy() if "State_Daily" in store else None
+        if state_daily is not None:
+            state_daily["day"] = pd.to_datetime(state_daily["day"])
+            state_daily["move"] = pd.to_numeric(state_daily["move"], errors="coerce").fillna(0).astype(int)
+            for c in ("successes", "count"):
+                state_daily[c] = pd.to_numeric(state_daily[c], errors="coerce").fillna(0.0)
+            for c in ("scenario", "species"):
+                state_daily[c] = state_daily[c].astype(str).str.strip()
+            state_daily["state"] = state_daily["state"].astype(str)
+        moves = [int(m) for m in sim.moves]
+        final_move = max(moves) if moves else 0
+        for spc in species:
+            for scen in scens:
+                if state_daily is None:
+                    logger.warning("Missing simulation data for key 'simulations/%s/%s'", scen, spc)
+                    continue
+                state_dat = state_daily[(state_daily["scenario"] == str(scen).strip())
+                                        & (state_daily["species"] == str(spc).strip())]
+                if state_dat.empty:
+                    logger.warning("Missing simulation aggregates for scenario '%s' species '%s'", scen, spc)
+                    continue
+                # whole-project survival per (iteration, day): successes at the final move / pop_size (:3616-3637)
+                sub = sim.daily_summary[(sim.daily_summary["species_norm"] == str(spc).strip())
+                                        & (sim.daily_summary["scenario_norm"] == str(scen).strip())][["iteration", "day", "pop_size"]].copy()
+                sub["day"] = pd.to_datetime(sub["day"])
+                sub = sub.groupby(["iteration", "day"], as_index=False)["pop_size"].max()
+                fin = state_dat[state_dat["move"] == final_move]
+                if fin.empty:
+                    fin = pd.DataFrame(columns=["iteration", "day", "successes"])
+                else:
+                    fin = fin.groupby(["iteration", "day"], as_index=False)["successes"].sum()
+                whole = sub.merge(fin, on=["iteration", "day"], how="left")
+                whole["successes"] = whole["successes"].fillna(0.0)
+                whole["count"] = whole["pop_size"].astype(float)
+                whole["prob"] = np.where(whole["count"] > 0, whole["successes"] / whole["count"], 0.0)
+                probs = whole["prob"].values
+                if probs.size == 0:
+                    raise ValueError(f"No survival probability data for scenario '{scen}' species '{spc}'.")
+                sim.beta_caption = BETA_CAPTION
+                sim.beta_dict["%s_%s_%s" % (scen, spc, "whole")] = [scen, spc, "whole", *_mean_std_ci(probs)]
+                for l in moves:
+                    rs = state_dat[state_dat["move"] == int(l)][["iteration", "day", "state", "successes", "count"]].copy()
+                    if rs.empty:
+                        continue
+                    rs["prob"] = np.where(rs["count"] > 0, rs["successes"] / rs["count"], 0.0)
+                    for m in rs["state"].unique():
+                        pv = rs[rs["state"] == m]["prob"].values
+                        if pv.size == 0:
+                            continue
+                        sim.beta_dict["%s_%s_%s" % (scen, spc, m)] = [scen, spc, m, *_mean_std_ci(pv)]
+        sim.beta_df = pd.DataFrame.from_dict(sim.beta_dict, orient="index",
+                                             columns=["scenario number", "species", "state", "survival rate", "variance", "ll", "ul"])
+        st = sim.beta_df["state"].astype(str)
+        sim.beta_df_units_only = sim.beta_df[(st != "whole") & (~st.str.contains("river_node", case=False, na=False))
+                                             & (~st.str.contains("^river$", case=False, na=False, regex=True))][
+            ["state", "survival rate", "variance", "ll", "ul"]].copy()
+        sim.beta_df_units_only.rename(columns={"state": "Passage Route", "survival rate": "Mean", "variance": "Variance",
+                                               "ll": "Lower 95% CI", "ul": "Upper 95% CI"}, inplace=True)
+        sim.cum_sum = yearly_summary(sim.daily_summary)
+        if sim.wks_dir and str(sim.wks_dir).endswith((".xlsx", ".xls")):
+            try:
+                from . import xlsx
+                xlsx.append_sheets(sim.wks_dir, {"beta fit": sim.beta_df, "daily summary": sim.daily_summary,
+                                                 "yearly summary": sim.cum_sum})
+            except (PermissionError, FileNotFoundError, OSError, ValueError) as exc:
+                raise RuntimeError(f"Failed to write Excel summaries to {sim.wks_dir}: {exc}") from exc
+        else:
+            logger.info("Web app mode detected - Excel export skipped (results in HDF5 only)")
+        sim.driver_diagnostics = driver_diagnostics(
+            store["Unit_Parameters"] if "Unit_Parameters" in store else None,
+            store["Route_Flows"] if "Route_Flows" in store else None,
+            store["Unit_Hours"] if "Unit_Hours" in store else None, sim.beta_df_units_only)
+        print("=" * 60 + "\n", flush=True)
+    with open_store(hdf_path, mode="a") as store:
+        kw = dict(format="table", data_columns=True)
+        store.put("Daily_Summary", sim.daily_summary, **kw)
+        store.put("Beta_Distributions", sim.beta_df, **kw)
+        store.put("Beta_Distributions_Units", sim.beta_df_units_only, **kw)
+        store.put("Yearly_Summary", sim.cum_sum, **kw)
+        if isinstance(getattr(sim, "driver_diagnostics", None), pd.DataFrame):
+            store.put("Driver_Diagnostics", sim.driver_diagnostics, **kw)
+    return None
+
+
+def yearly_summary(daily):
+    """Per (species, scenario): entrainment probability, yearly totals with 95 % percentiles over iterations, bootstrap
+    means and 1-in-10/100/1000-day quantiles of daily entrainment and mortality (stryke.py:3770-3862)."""
+    cols = ["species", "scenario", "prob_entrainment", "mean_yearly_entrainment", "lcl_yearly_entrainment",
+            "ucl_yearly_entrainment", "1_in_10_day_entrainment", "1_in_100_day_entrainment", "1_in_1000_day_entrainment",
+            "mean_yearly_mortality", "lcl_yearly_mortality", "ucl_yearly_mortality", "1_in_10_day_mortality",
+            "1_in_100_day_mortality", "1_in_1000_day_mortality"]
+    out = {c: [] for c in cols}
+    groups = daily.groupby(["species", "scenario", "iteration"])[["pop_size", "num_survived", "num_entrained"]].sum().reset_index()
+    for fishy in groups.species.unique():
+        for scen in groups.scenario.unique():
+            out["species"].append(fishy)
+            out["scenario"].append(scen)
+            day_dat = daily[(daily.species == fishy) & (daily.scenario == scen)]
+            if len(day_dat) == 0:
+                for c in cols[2:]:
+                    out[c].append(0.0)
+                continue
+            df = day_dat[["day", "iteration", "num_entrained", "num_survived", "pop_size"]].copy()
+            df["num_mortalities"] = df["num_entrained"] - df["num_survived"]
+            per_it = df.groupby("iteration")[["pop_size", "num_entrained"]].sum()
+            probs = np.where(per_it["pop_size"] > 0, per_it["num_entrained"] / per_it["pop_size"].where(per_it["pop_size"] > 0, 1.0), 0.0)
+            out["prob_entrainment"].append(float(np.mean(probs)) if len(probs) else 0.0)
+            bootstrap_mean_ci(df["num_entrained"])      # drawn by the reference (:3832-3833); results unused there too
+            bootstrap_mean_ci(df["num_mortalities"])
+            q = {T: 1 - 1 / T for T in (10, 100, 1000)}
+            year = df.groupby(["iteration"])[["num_entrained", "num_mortalities"]].sum().apply(summarize_ci)
+            for what, col in (("entrainment", "num_entrained"), ("mortality", "num_mortalities")):
+                out[f"mean_yearly_{what}"].append(year.at["mean", col])
+                out[f"lcl_yearly_{what}"].append(year.at["lower_95_CI", col])
+                out[f"ucl_yearly_{what}"].append(year.at["upper_95_CI", col])
+                for T, level in q.items():
+                    out[f"1_in_{T}_day_{what}"].append(df[col].quantile(level))
+    return pd.DataFrame.from_dict(out, orient="columns")
+
+
+def driver_diagnostics(unit_params, route_flows, unit_hours, beta_units):
+    """Unit-level diagnostics table (stryke.py:3913-4084)."""
+    if not isinstance(unit_params, pd.DataFrame) or unit_params.empty:
+        logger.info("Driver diagnostics skipped: Unit_Parameters missing or empty.")
+        return None
+    diag = unit_params.copy()
+    diag["route"] = diag.index.astype(str)
+    pref = ["H", "RPM", "D", "N", "Qopt", "Qcap", "D1", "D2", "B", "ada", "intake_vel", "ps_D", "ps_length", "fb_depth",
+            "submergence_depth", "elevation_head"]
+    diag = diag[["route"] + [c for c in pref if c in diag.columns]].reset_index(drop=True)
+    if isinstance(beta_units, pd.DataFrame) and not beta_units.empty:
+        bu = beta_units.rename(columns={"Passage Route": "route", "state": "route", "Mean": "survival_mean",
+                                        "survival rate": "survival_mean", "Variance": "survival_variance",
+                                        "variance": "survival_variance", "Lower 95% CI": "survival_lcl", "ll": "survival_lcl",
+                                        "Upper 95% CI": "survival_ucl", "ul": "survival_ucl"})
+        keep = [c for c in ("route", "survival_mean", "survival_variance", "survival_lcl", "survival_ucl") if c in bu.columns]
+        if "route" in keep and len(keep) > 1:
+            bu = bu[keep].groupby("route", as_index=False)[keep[1:]].mean()
+            diag = diag.merge(bu, on="route", how="left")
+    have_rf = isinstance(route_flows, pd.DataFrame) and not route_flows.empty and {"route", "discharge_cfs"} <= set(route_flows.columns)
+    if have_rf:
+        rf = route_flows.copy()
+        rf["route"] = rf["route"].astype(str)
+        mean_q = rf.groupby("route")["discharge_cfs"].mean()
+        diag = diag.merge(mean_q.rename("mean_discharge_cfs"), left_on="route", right_index=True, how="left")
+        unit_mean = mean_q[mean_q.index.isin(set(diag["route"].dropna().astype(str)))]
+        share = None
+        if float(unit_mean.sum()) > 0:
+            share = unit_mean / float(unit_mean.sum())
+        elif float(mean_q.sum()) > 0:
+            share = mean_q / float(mean_q.sum())
+        if share is not None:
+            diag = diag.merge(share.rename("flow_share"), left_on="route", right_index=True, how="left")
+    if "flow_share" in diag.columns and "survival_mean" in diag.columns:
+        diag["mortality_weight"] = diag["flow_share"] * (1 - diag["survival_mean"])
+    dispatch = None
+    if isinstance(unit_hours, pd.DataFrame) and not unit_hours.empty and "Qopt" in diag.columns:
+        uh = unit_hours.copy()
+        if {"route", "hours"} <= set(uh.columns):
+            uh["route"] = uh["route"].astype(str)
+            uh["hours"] = pd.to_numeric(uh["hours"], errors="coerce")
+            if "discharge_cfs" in uh.columns:
+                uh["discharge_cfs"] = pd.to_numeric(uh["discharge_cfs"], errors="coerce")
+                dispatch = uh
+            elif have_rf:
+                dispatch = rf.merge(uh, on=["scenario", "iteration", "day", "route"], how="outer")
+                dispatch["hours"] = pd.to_numeric(dispatch["hours"], errors="coerce")
+                dispatch["discharge_cfs"] = pd.to_numeric(dispatch["discharge_cfs"], errors="coerce")
+    if isinstance(dispatch, pd.DataFrame) and not dispatch.empty:
+        dispatch = dispatch.merge(diag[["route", "Qopt"]], on="route", how="left")
+        dispatch["Qopt"] = pd.to_numeric(dispatch["Qopt"], errors="coerce")
+        dispatch = dispatch[(dispatch["hours"] > 0.0) & (dispatch["Qopt"] > 0.0) & dispatch["discharge_cfs"].notna()].copy()
+        if not dispatch.empty:
+            off = (dispatch["discharge_cfs"] - dispatch["Qopt"]).abs() / dispatch["Qopt"] * 100.0
+            outside = (dispatch["discharge_cfs"] < dispatch["Qopt"] * 0.9) | (dispatch["discharge_cfs"] > dispatch["Qopt"] * 1.1)
+            dispatch["hours_outside_band"] = dispatch["hours"] * outside.astype(float)
+            dispatch["abs_pct_off_hours"] = off * dispatch["hours"]
+            hs = dispatch.groupby("route").agg(total_hours=("hours", "sum"), hours_outside_band=("hours_outside_band", "sum"),
+                                               abs_pct_off_hours=("abs_pct_off_hours", "sum"))
+            hs["mean_abs_pct_off_qopt"] = hs["abs_pct_off_hours"] / hs["total_hours"]
+            hs["pct_hours_outside_qopt_band"] = hs["hours_outside_band"] / hs["total_hours"] * 100.0
+            diag = diag.merge(hs[["total_hours", "mean_abs_pct_off_qopt", "pct_hours_outside_qopt_band"]],
+                              left_on="route", right_index=True, how="left")
+    return diag

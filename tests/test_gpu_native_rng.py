@@ -1,0 +1,187 @@
+"""Native-RNG (Philox4x32-10) tests on the GPU: statistical parity with the oracle at alpha = 0.01 (Bonferroni over
+the tests of one case), partition independence, determinism and size-independent conservation properties at the
+BASELINE.json sizes."""
+import numpy as np
+import pytest
+from scipy import stats
+
+from oracle import fixtures, stryke_oracle as O
+import gpu_util as G
+from stryke_b200 import engine
+from stryke_b200.engine import TraceBuffers
+
+pytestmark = pytest.mark.gpu
+ALPHA = 0.01
+
+
+def native(plan, precision=32, seed=11, trace=None, cells=None, blocks_per_sm=0, cap=10 ** 9):
+    sel = slice(None) if cells is None else cells
+    return engine.run_cells(plan.fac, plan.days, plan.species_table, plan.cell_day[sel], plan.cell_species[sel],
+                            plan.cell_id[sel], precision=precision, seed=seed, max_daily_fish=cap, trace=trace,
+                            blocks_per_sm=blocks_per_sm)
+
+
+def oracle_cells(prj, n_cells, seed=3):
+    """Oracle tallies with NumPy's own stream, same projects, for two-sample comparisons."""
+    out = O.run_project(prj, seed=seed, max_cells=n_cells)
+    return out
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+@pytest.mark.parametrize("fixture,kw", [("c2_facility", dict(n_fish=400000, iterations=2, days=2)),
+                                        ("c2_facility", dict(n_fish=300000, iterations=1, days=2, baro=True)),
+                                        ("c5_cascade", dict(n_fish=150000, iterations=1, days=2)),
+                                        ("c4_barotrauma", dict(n_fish=200000, iterations=1, days=2))])
+def test_route_and_survival_counts_match_oracle_distribution(fixture, kw, precision):
+    prj = getattr(fixtures, fixture)(**kw)
+    sim, plan = G.make_plan(prj, fixture)
+    res = native(plan, precision=precision)
+    ref = oracle_cells(prj, plan.n_cells)
+    ref_idx = G.reference_cell_index(plan)
+    tests = []
+    for c, r in enumerate(ref_idx):
+        got = G.state_daily_dict(plan, res.state_daily[c])
+        want = ref[r]["state_daily"]
+        assert set(got) == set(want), (set(got) ^ set(want))
+        moves = sorted({k for k, _ in got})
+        for k in moves:
+            nodes = sorted(nd for kk, nd in got if kk == k)
+            if len(nodes) > 1:      # routing: homogeneity of the count vectors (GPU vs oracle)
+                tab = np.array([[got[(k, nd)][1] for nd in nodes], [want[(k, nd)][1] for nd in nodes]])
+                tab = tab[:, tab.sum(axis=0) > 0]
+                tests.append(("route", c, k, stats.chi2_contingency(tab)[1]))
+            for nd in nodes:        # survival: two-proportion test
+                s1, n1 = got[(k, nd)]
+                s2, n2 = want[(k, nd)]
+                if 0 < s1 + s2 < n1 + n2:
+                    tab = np.array([[s1, n1 - s1], [s2, n2 - s2]])
+                    tests.append(("surv", c, (k, nd), stats.chi2_contingency(tab, correction=False)[1]))
+        # Daily: entrained / survived / cause counters as proportions of pop_size
+        g7, w7 = G.full_daily(res.cell_n[c], res.daily[c]), ref[r]["daily"]
+        assert g7[0] == w7[0]
+        for j in (1, 2, 4, 5, 6):
+            if 0 < g7[j] + w7[j] < 2 * g7[0]:
+                tab = np.array([[g7[j], g7[0] - g7[j]], [w7[j], w7[0] - w7[j]]])
+                tests.append(("daily", c, j, stats.chi2_contingency(tab, correction=False)[1]))
+    assert len(tests) > 5
+    worst = min(tests, key=lambda t: t[-1])
+    assert worst[-1] > ALPHA / len(tests), (worst, len(tests))
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+def test_length_distribution_ks(precision):
+    prj = fixtures.c2_facility(n_fish=500000, iterations=1, days=1)
+    sim, plan = G.make_plan(prj, "len")
+    tr = TraceBuffers.allocate(plan.fac.n_moves, 500000, probs=False)
+    native(plan, precision=precision, trace=tr)
+    prow = prj["population"][0]
+    rng = np.random.default_rng(5)
+    want = O.lengths_from_normals(rng.standard_normal(500000), prow["length shape"], prow["length location"], prow["length scale"])
+    p = stats.ks_2samp(tr.length_ft64, want).pvalue
+    assert p > ALPHA, p
+
+
+def test_daily_entrainment_count_distribution_ks():
+    """Population mode (step 1): per-cell n for Pareto / Log Normal / Weibull species vs the oracle's draws, and the
+    presence frequency vs occur_prob."""
+    prj = fixtures.c3_population(n_species=4, iterations=1500, days=4)
+    sim, plan = G.make_plan(prj, "count")
+    res = native(plan, precision=32, cap=10 ** 7)
+    rng = np.random.default_rng(9)
+    tests = []
+    for g in plan.groups:
+        prow = [p for p in prj["population"] if p["Species"] == g.species][0]
+        for j, d in enumerate(g.active_days):
+            q = plan.days.curr_Q[g.day0 + d]
+            n = res.cell_n[g.cell0 + j * g.iterations: g.cell0 + (j + 1) * g.iterations].astype(np.int64)
+            present = n > 0
+            tests.append(("presence", g.species, d, stats.binomtest(int(present.sum()), len(n), prow["occur_prob"]).pvalue))
+            K = 4000
+            if prow["dist"] == "Pareto":
+                fl, fh, _ = O.pareto_truncation_window(prow["shape"], prow["location"], prow["scale"], prow["max_ent_rate"])
+                draws = rng.uniform(fl, fh, K)
+            elif prow["dist"] == "Log Normal":
+                draws = rng.standard_normal(K)
+            else:
+                draws = rng.random(K)
+            want = np.array([O.daily_fish_count(O.entrainment_rate(prow["dist"], prow["shape"], prow["location"], prow["scale"],
+                                                                   prow["max_ent_rate"], u), q) for u in draws])
+            tests.append(("count", g.species, d, stats.ks_2samp(n[present], want).pvalue))
+    worst = min(tests, key=lambda t: t[-1])
+    assert worst[-1] > ALPHA / len(tests), worst
+
+
+def test_results_do_not_depend_on_partition_or_grid():
+    """Philox is keyed by (seed, cell id, fish, slot): any subset of cells, in any launch geometry, gives the same
+    tallies — the property the multi-GPU sharding relies on."""
+    prj = fixtures.c3_population(n_species=3, iterations=40, days=6)
+    sim, plan = G.make_plan(prj, "part")
+    full = native(plan, seed=77, cap=10 ** 7)
+    half = plan.n_cells // 2
+    a = native(plan, seed=77, cells=slice(0, half), cap=10 ** 7)
+    b = native(plan, seed=77, cells=slice(half, None), cap=10 ** 7)
+    assert np.array_equal(full.cell_n, np.concatenate([a.cell_n, b.cell_n]))
+    assert np.array_equal(full.daily, np.concatenate([a.daily, b.daily]))
+    assert np.array_equal(full.state_daily, np.concatenate([a.state_daily, b.state_daily]))
+    one = native(plan, seed=77, blocks_per_sm=1, cap=10 ** 7)
+    assert np.array_equal(full.daily, one.daily) and np.array_equal(full.state_daily, one.state_daily)
+    other = native(plan, seed=78, cap=10 ** 7)
+    assert not np.array_equal(full.daily, other.daily)
+    perm = np.random.default_rng(0).permutation(plan.n_cells)
+    sh = engine.run_cells(plan.fac, plan.days, plan.species_table, plan.cell_day[perm], plan.cell_species[perm],
+                          plan.cell_id[perm], precision=32, seed=77, max_daily_fish=10 ** 7)
+    assert np.array_equal(sh.daily, full.daily[perm]) and np.array_equal(sh.state_daily, full.state_daily[perm])
+
+
+@pytest.mark.parametrize("fixture,kw", [("c2_facility", dict(n_fish=1_000_000, iterations=12, days=1)),
+                                        ("c5_cascade", dict(n_fish=400_000, iterations=6, days=1))])
+def test_full_size_conservation_properties(fixture, kw):
+    """BASELINE.json cell sizes: fish are conserved move to move, nothing is counted twice, tallies are bounded."""
+    prj = getattr(fixtures, fixture)(**kw)
+    sim, plan = G.make_plan(prj, "cons")
+    res = native(plan, seed=5)
+    fac = plan.fac
+    n = kw["n_fish"]
+    sd = res.state_daily.astype(np.int64)
+    assert (res.cell_n == n).all()
+    for k in range(fac.n_moves):
+        sl = slice(fac.level_off[k], fac.level_off[k + 1])
+        count_k = sd[:, sl, 1].sum(axis=1)
+        if k == 0:
+            assert (count_k == n).all()
+        else:
+            prev = slice(fac.level_off[k - 1], fac.level_off[k])
+            assert np.array_equal(count_k, sd[:, prev, 0].sum(axis=1))      # alive after k-1 == counted at k
+    assert (sd[..., 0] <= sd[..., 1]).all()
+    d = res.daily.astype(np.int64)
+    assert (d[:, 1] <= d[:, 0]).all() and (d[:, 0] <= n).all()
+    # every fish that reached a node whose name contains 'U' alive is entrained; dead ones keep their state, so
+    # num_entrained equals the live arrivals at the first level that has U nodes
+    first_U = min(int(fac.pair_move[p]) for p in range(fac.n_pairs) if fac.node_has_U[fac.pair_node[p]])
+    arrivals = sum(sd[:, p, 1] for p in range(fac.n_pairs)
+                   if int(fac.pair_move[p]) == first_U and fac.node_has_U[fac.pair_node[p]])
+    if fixture == "c2_facility":
+        assert np.array_equal(d[:, 0], arrivals)
+    again = native(plan, seed=5)
+    assert np.array_equal(again.state_daily, res.state_daily) and np.array_equal(again.daily, res.daily)
+
+
+@pytest.mark.parametrize("fixture,kw", [("c2_facility", dict(n_fish=300000, iterations=3, days=2)),
+                                        ("c2_facility", dict(n_fish=200000, iterations=2, days=2, baro=True)),
+                                        ("c2_facility", dict(n_fish=50000, iterations=2, days=3, curr_Q=600.0)),
+                                        ("c5_cascade", dict(n_fish=100000, iterations=2, days=2)),
+                                        ("c4_barotrauma", dict(n_fish=100000, iterations=2, days=2, habitat="Benthic")),
+                                        ("c1_single_unit", dict(iterations=50, days=40, fish=3000.0)),
+                                        ("c3_population", dict(n_species=4, iterations=60, days=10))])
+def test_fast_kernel_equals_general_kernel(fixture, kw):
+    """passage_fast_kernel (throughput variant) vs passage_kernel<float, native> (the template that is validated
+    bit-for-bit against the reference in injected mode): same Philox words, same fp32 formulas -> identical tallies."""
+    prj = getattr(fixtures, fixture)(**kw)
+    sim, plan = G.make_plan(prj, "fast")
+    args = (plan.fac, plan.days, plan.species_table, plan.cell_day, plan.cell_species, plan.cell_id)
+    fast = engine.run_cells(*args, precision=32, seed=99, max_daily_fish=10 ** 8, kernel_variant=0)
+    gen = engine.run_cells(*args, precision=32, seed=99, max_daily_fish=10 ** 8, kernel_variant=1)
+    assert fast.cell_n.sum() > 0
+    assert np.array_equal(fast.cell_n, gen.cell_n)
+    assert np.array_equal(fast.daily, gen.daily)
+    assert np.array_equal(fast.state_daily, gen.state_daily)

