@@ -48,11 +48,14 @@ struct __align__(4) NodeRec {   // 12 bytes
 
 enum : uint8_t { NEED_DICE = 1, NEED_RR = 2, NEED_DEPTH = 4, NEED_CAUSE = 8, NEED_ROUTE = 16 };
 
-struct __align__(4) MoveRec {   // 8 bytes
+struct __align__(4) MoveRec {   // 12 bytes
   uint8_t lex;                  // rank of "state_k" in lexicographic column order (stryke.py:3272)
   uint8_t need;                 // NEED_* : which draws this move can consume (static facility property)
-  uint16_t slot_base;           // first Philox word slot of this move
+  uint16_t slot_base;           // first Philox word slot of this move's rR / depth / cause / dice words (one block)
   uint16_t level_begin, level_end;  // reachable pairs of this move in pair_node[]
+  uint16_t slot_route;          // Philox word slot of the routing draw
+  uint8_t max_deg;              // largest out-degree among the nodes of this level
+  uint8_t pad;
 };
 
 struct InjectedDev {
@@ -115,6 +118,14 @@ __device__ __forceinline__ double baro_surv64(double depth_ft, double tail_ft, d
   const double e = exp(add_(b0, mul_(b1, log(div_(p1, p2)))));
   return sub_(1.0, div_(e, add_(1.0, e)));
 }
+// single-MUFU approximations (no denormal / range fix-up code): arguments are known to be normal and in range
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float cos_2pi(float turns) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(turns * 6.283185307f)); return y; }
+
 // ---- fp32 throughput flavour: folded per-(day, unit) coefficients, MUFU intrinsics ---------------------------------
 //   Kaplan: tan a = fa / rR  =>  cos a = rR * rsqrt(rR^2 + fa^2), sin a = fa * rsqrt(rR^2 + fa^2)
 //           p = fc * L * rsqrt(rR^2 + fa^2) * (rR * fb + fa / (pi rR))
@@ -122,8 +133,8 @@ __device__ __forceinline__ float strike_surv32(int kind, const float* uc, float 
   float p;
   if (kind == STRYKE_KIND_KAPLAN) {
     const float fa = uc[0], fb = uc[1];
-    const float inv = rsqrtf(fmaf(rR, rR, fa * fa));
-    p = uc[2] * L * inv * fmaf(rR, fb, __fdividef(fa * 0.318309886f, rR));
+    const float inv = rsqrt_approx(fmaf(rR, rR, fa * fa));
+    p = uc[2] * L * inv * fmaf(rR, fb, fa * 0.318309886f * rcp_approx(rR));
   } else {
     p = uc[2] * L;
   }
@@ -132,8 +143,8 @@ __device__ __forceinline__ float strike_surv32(int kind, const float* uc, float 
 }
 __device__ __forceinline__ float baro_surv32(float depth_ft, float c0, float c1, float b0l2e, float b1) {
   const float ratio = fmaf(c1, depth_ft, c0);                 // P1/P2
-  const float e = exp2f(fmaf(b1, __log2f(ratio), b0l2e));     // exp(b0 + b1 ln ratio)
-  return __fdividef(1.f, 1.f + e);                            // 1 - e/(1+e)
+  const float e = ex2_approx(fmaf(b1, lg2_approx(ratio), b0l2e));   // exp(b0 + b1 ln ratio)
+  return rcp_approx(1.f + e);                                       // 1 - e/(1+e)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -160,9 +171,10 @@ template <> __device__ __forceinline__ float u_oc<float>(uint32_t x) { return (f
 template <> __device__ __forceinline__ double u_co<double>(uint32_t x) { return (double)x * 2.3283064365386963e-10; }
 template <> __device__ __forceinline__ double u_oc<double>(uint32_t x) { return ((double)x + 1.0) * 2.3283064365386963e-10; }
 
-__device__ __forceinline__ float std_normal(float u1_oc, float u2_co) {   // Box-Muller, MUFU lg2/sqrt/cos
-  return sqrtf(-2.f * __logf(u1_oc)) * __cosf(6.283185307f * u2_co);
+__device__ __forceinline__ float std_normal(float u1_oc, float u2_co) {   // Box-Muller: MUFU lg2, sqrt, cos
+  return sqrt_approx(-1.3862943611f * lg2_approx(u1_oc)) * cos_2pi(u2_co);   // -2 ln u = -2 ln2 lg2 u
 }
+__device__ __forceinline__ float exp_approx(float x) { return ex2_approx(x * 1.44269504f); }
 __device__ __forceinline__ double std_normal(double u1_oc, double u2_co) {
   return sqrt(-2.0 * log(u1_oc)) * cospi(2.0 * u2_co);
 }
@@ -486,7 +498,7 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
         L = (Real)div_(fabs(add_((double)sp_lm, mul_((double)sp_lsd, (double)z))), 12.0);
       }
     } else {
-      if (sp_mode == 0) L = (Real)(fminf(fabsf(fmaf(__expf((float)sp_ls * (float)z), (float)sp_lsc, (float)sp_ll)), 150.f) * 0.0328084f);
+      if (sp_mode == 0) L = (Real)(fminf(fabsf(fmaf(exp_approx((float)sp_ls * (float)z), (float)sp_lsc, (float)sp_ll)), 150.f) * 0.0328084f);
       else L = (Real)(fabsf(fmaf((float)sp_lsd, (float)z, (float)sp_lm)) * (1.f / 12.f));
     }
     if (P.trace.length_ft64 && active) { P.trace.length_ft64[gi] = (double)L; if (P.trace.length_ft) P.trace.length_ft[gi] = (float)L; }
@@ -508,8 +520,8 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
       const int s_rr = slot;   slot += (mv.need & NEED_RR) ? 1 : 0;
       const int s_dep = slot;  slot += (mv.need & NEED_DEPTH) ? 1 : 0;
       const int s_cau = slot;  slot += (mv.need & NEED_CAUSE) ? 1 : 0;
-      const int s_dice = slot; slot += (mv.need & NEED_DICE) ? 1 : 0;
-      const int s_rt = slot;
+      const int s_dice = slot;
+      const int s_rt = mv.slot_route;
       uint32_t w_rr = 0, w_dep = 0, w_cau = 0;
       if (!INJECT) {   // warp-uniform draws for this move (refill points are identical for every lane)
         if (mv.need & NEED_RR) w_rr = rng.word(s_rr);
@@ -874,8 +886,17 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
       if (k < f->n_moves - 1 && r.deg > 1) need |= NEED_ROUTE;
     }
     m.need = need;
+    // the (<= 4) per-node words of a move never straddle a Philox block; the routing word follows
+    const int n_a = __builtin_popcount(need & (NEED_RR | NEED_DEPTH | NEED_CAUSE | NEED_DICE));
+    if ((slot & 3) + n_a > 4) slot = (slot + 3) & ~3;
     m.slot_base = (uint16_t)slot;
-    slot += __builtin_popcount(need);
+    slot += n_a;
+    m.slot_route = (uint16_t)slot;
+    slot += (need & NEED_ROUTE) ? 1 : 0;
+    int md = 0;
+    for (int p = m.level_begin; p < m.level_end; ++p) md = std::max(md, (int)nodes[pnode[p]].deg);
+    m.max_deg = (uint8_t)md;
+    m.pad = 0;
   }
   CK(upload(pl->nodes, nodes.data(), nodes.size()));
   CK(upload(pl->edge_dst, edst.data(), edst.size()));
@@ -984,12 +1005,7 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
       fn[i].y = pack_node(nodes[i].edge_off, nodes[i].deg, nodes[i].kind, nodes[i].hasU, nodes[i].unit);
     }
     CK(upload(pl->fast_nodes, fn.data(), fn.size()));
-    for (int k = 0; k < f->n_moves; ++k) {
-      pl->fast.moves[k] = moves[k];
-      int md = 0;
-      for (int p = moves[k].level_begin; p < moves[k].level_end; ++p) md = std::max(md, (int)nodes[pnode[p]].deg);
-      pl->fast.max_deg[k] = (uint8_t)md;
-    }
+    for (int k = 0; k < f->n_moves; ++k) pl->fast.moves[k] = moves[k];
     for (int p = 0; p < f->n_pairs; ++p) pl->fast.pair_node[p] = pnode[p];
     pl->fast_smem_bytes = (size_t)fast_smem(f->n_nodes, f->n_units, f->n_edges, pl->n_species_staged).total;
   }

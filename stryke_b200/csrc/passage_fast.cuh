@@ -1,23 +1,24 @@
 // passage_fast.cuh — the throughput variant of the passage kernel: fp32 arithmetic, native Philox stream, tallies only.
 //
-// Same algorithm, same Philox word schedule and same fp32 formulas as passage_kernel<float, false, PR> (which is
+// Same algorithm, same Philox word slots and same fp32 formulas as passage_kernel<float, false, PR> (which is
 // validated bit-for-bit against the reference in injected mode), restructured for instruction issue, the roofline
 // that binds this path:
-//   * the per-move records and the (move, node) pair list live in the kernel parameter (constant) bank, so every
-//     loop bound and "does this level need a draw" test is warp-uniform: no BSSY/BSYNC reconvergence code;
-//   * the per-fish branchy code of node_surv_rate (stryke.py:1396-1572) is straight-line predicated arithmetic: one
+//   * the warp index is made provably warp-uniform (shuffle), and the per-move records + the (move, node) pair list
+//     live in the kernel parameter (constant) bank: the tile / cell / move / pair loops, every "does this level need
+//     a draw" test and the Philox refill decisions run on the uniform datapath with no BSSY/BSYNC reconvergence code;
+//   * the branchy per-fish code of node_surv_rate (stryke.py:1396-1572) is straight-line predicated arithmetic: one
 //     unified strike formula (Kaplan and linear runners differ only in staged coefficients), selects instead of ifs;
 //   * node records are one 8-byte shared-memory load, unit coefficients one 16-byte load;
-//   * Philox words are popped in consumption order, so exactly ceil(W/4) blocks are generated per fish.
+//   * three Philox refill sites in the whole kernel (length block, per-node words, routing word), so the code stays
+//     inside the instruction cache.
 // tests/test_gpu_native_rng.py::test_fast_kernel_equals_general_kernel requires identical tallies from both.
 #pragma once
 
 namespace stryke {
 
-struct FastTables {                 // by-value kernel parameter (constant bank), 664 bytes
+struct FastTables {                 // by-value kernel parameter (constant bank)
   MoveRec moves[STRYKE_MAX_MOVES];
   uint8_t pair_node[STRYKE_MAX_PAIRS];
-  uint8_t max_deg[STRYKE_MAX_MOVES];   // largest out-degree among the nodes of each level (uniform route-loop bound)
 };
 
 // FastNode.y: edge_off[0:11) deg[11:19) kind[19:22) hasU[22] unit[23:30)
@@ -48,22 +49,17 @@ __host__ __device__ inline FastSmem fast_smem(int n_nodes, int n_units, int n_ed
   return L;
 }
 
-struct WordStream {   // Philox words in consumption order; `pos` only ever changes under warp-uniform control flow
+// The current Philox block; `cur` and every slot index are warp-uniform.
+struct BlockRng {
   uint32_t c0, c1, c2, k0, k1, w0, w1, w2, w3;
-  int pos;
-  __device__ __forceinline__ void init(uint32_t fish, uint64_t cell_id, uint32_t seed_lo, uint32_t seed_hi) {
-    c0 = fish; c1 = (uint32_t)cell_id; c2 = (uint32_t)(cell_id >> 32); k0 = seed_lo; k1 = seed_hi; pos = 0;
+  int cur;
+  __device__ __forceinline__ void refill(int b) {
+    uint32_t w[4];
+    Philox::block(c0, c1, c2, (uint32_t)b, k0, k1, w);
+    w0 = w[0]; w1 = w[1]; w2 = w[2]; w3 = w[3]; cur = b;
   }
-  __device__ __forceinline__ uint32_t pop() {
-    if ((pos & 3) == 0) {
-      uint32_t w[4];
-      Philox::block(c0, c1, c2, (uint32_t)(pos >> 2), k0, k1, w);
-      w0 = w[0]; w1 = w[1]; w2 = w[2]; w3 = w[3];
-    }
-    const uint32_t r = w0;
-    w0 = w1; w1 = w2; w2 = w3;
-    ++pos;
-    return r;
+  __device__ __forceinline__ uint32_t at(int i) const {   // i in 0..3, uniform
+    return (i & 2) ? ((i & 1) ? w3 : w2) : ((i & 1) ? w1 : w0);
   }
 };
 
@@ -77,7 +73,8 @@ __global__ void __launch_bounds__(BLOCK, 4) passage_fast_kernel(const KParams P,
   float4* s_ustatic = reinterpret_cast<float4*>(smem + SL.ustatic);     // rack, intake_vel, fb_depth, c0
   float* s_uc1 = reinterpret_cast<float*>(smem + SL.uc1);               // c1
   float* s_species = reinterpret_cast<float*>(smem + SL.species);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   unsigned char* wbase = smem + SL.warp0 + wid * SL.warp_stride;
   float* s_cdf = reinterpret_cast<float*>(wbase + SL.cdf);
   float4* s_ucoef = reinterpret_cast<float4*>(wbase + SL.ucoef);        // fa, fb, fc, has_flow
@@ -162,7 +159,7 @@ __global__ void __launch_bounds__(BLOCK, 4) passage_fast_kernel(const KParams P,
           const double* r = uc + u * STRYKE_UNIT_COEF_W;
           const double lnd = r[0] * r[1] / r[2];
           const bool kap = r[4] != 0.0 || r[5] != 0.0;
-          // linear runners use the Kaplan formula with fa = 0, fb = 1, rR = 1:  p = fc * L * rsqrt(1) * (1*1 + 0)
+          // linear runners use the Kaplan formula with fa = 0, fb = 1, rR = 1, inv = 1:  p = fc * L
           s_ucoef[u] = make_float4(kap ? (float)(r[3] / r[4]) : 0.f, kap ? (float)(1.0 / r[5]) : 1.f,
                                    kap ? (float)lnd : (float)(lnd * r[3]), (float)r[6]);
         }
@@ -172,13 +169,13 @@ __global__ void __launch_bounds__(BLOCK, 4) passage_fast_kernel(const KParams P,
     const int fish = (int)((t - c_begin) * 32 + lane);
     const bool active = fish < n_c;
 
-    WordStream rng;
-    rng.init((uint32_t)fish, cid, P.seed_lo, P.seed_hi);
-    // ---- (2) length -------------------------------------------------------------------------------------------
-    const uint32_t wa = rng.pop(), wb = rng.pop();
-    const float z = std_normal(u_oc<float>(wa), u_co<float>(wb));
+    BlockRng rng;
+    rng.c0 = (uint32_t)fish; rng.c1 = (uint32_t)cid; rng.c2 = (uint32_t)(cid >> 32); rng.k0 = P.seed_lo; rng.k1 = P.seed_hi;
+    rng.refill(0);
+    // ---- (2) length: words 0, 1 ----------------------------------------------------------------------------------
+    const float z = std_normal(u_oc<float>(rng.w0), u_co<float>(rng.w1));
     float L;
-    if (sp_mode == 0) L = fminf(fabsf(fmaf(__expf(sp_ls * z), sp_lsc, sp_ll)), 150.f) * 0.0328084f;
+    if (sp_mode == 0) L = fminf(fabsf(fmaf(exp_approx(sp_ls * z), sp_lsc, sp_ll)), 150.f) * 0.0328084f;
     else L = fabsf(fmaf(sp_lsd, z, sp_lm)) * (1.f / 12.f);
     const float blocked_w = L * sp_wr;
 
@@ -189,17 +186,21 @@ __global__ void __launch_bounds__(BLOCK, 4) passage_fast_kernel(const KParams P,
     uint32_t cz = 0;
 
     for (int k = 0; k < n_moves; ++k) {
-      const MoveRec mv = FT.moves[k];                    // constant bank: uniform
+      const MoveRec mv = FT.moves[k];                    // constant bank, uniform index
       const uint2 nd = s_nodes[loc];
       const uint32_t pk = nd.y;
       const int kind = (pk >> 19) & 7, deg = (pk >> 11) & 0xff, eoff = pk & 0x7ff;
       const bool prev_alive = alive;
       float rate = alive ? __uint_as_float(nd.x) : 0.f;
+      int slot = mv.slot_base;
+      if (mv.need & (NEED_CAUSE | NEED_DICE)) {
+        if ((slot >> 2) != rng.cur) rng.refill(slot >> 2);         // refill site A (uniform)
+      }
       if (mv.need & NEED_CAUSE) {                        // this level has turbine nodes (uniform)
-        const float u_rr = (mv.need & NEED_RR) ? u_co<float>(rng.pop()) : 0.f;
-        float u_dep = 0.f;
-        if (BARO) u_dep = u_co<float>(rng.pop());
-        const float u_cau = u_co<float>(rng.pop());
+        float u_rr = 0.f, u_dep = 0.f;
+        if (mv.need & NEED_RR) { u_rr = u_co<float>(rng.at(slot & 3)); ++slot; }
+        if (BARO) { u_dep = u_co<float>(rng.at(slot & 3)); ++slot; }
+        const float u_cau = u_co<float>(rng.at(slot & 3)); ++slot;
         const bool turb = alive && kind != STRYKE_KIND_APRIORI;
         const int unit = turb ? (int)((pk >> 23) & 0x7f) : 0;
         const float4 us = s_ustatic[unit];
@@ -208,16 +209,16 @@ __global__ void __launch_bounds__(BLOCK, 4) passage_fast_kernel(const KParams P,
         const float imp = (blocked && sp_uc < us.y) ? 0.f : 1.f;             // stryke.py:1420-1423
         const bool kap = kind == STRYKE_KIND_KAPLAN;
         const float rR = kap ? fmaf(0.7f, u_rr, 0.3f) : 1.f;
-        const float inv = kap ? rsqrtf(fmaf(rR, rR, uc.x * uc.x)) : 1.f;   // exact 1 for the linear runners
-        float p = uc.z * L * inv * fmaf(rR, uc.y, __fdividef(uc.x * 0.318309886f, rR));
+        const float inv = kap ? rsqrt_approx(fmaf(rR, rR, uc.x * uc.x)) : 1.f;   // exact 1 for the linear runners
+        float p = uc.z * L * inv * fmaf(rR, uc.y, uc.x * 0.318309886f * rcp_approx(rR));
         p = uc.w > 0.f ? p : INFINITY;
         const float strike = blocked ? 1.f : __saturatef(1.f - p);
         float baro = 1.f;
         if (BARO) {
           const float depth = us.z * fmaf(sp_dd, u_dep, sp_d1);
           const float ratio = fmaf(s_uc1[unit], depth, us.w);
-          const float e = exp2f(fmaf(sp_b1, __log2f(ratio), sp_b0));
-          baro = blocked ? 1.f : __fdividef(1.f, 1.f + e);
+          const float e = ex2_approx(fmaf(sp_b1, lg2_approx(ratio), sp_b0));
+          baro = blocked ? 1.f : rcp_approx(1.f + e);
         }
         const float a2 = imp * strike, a3 = a2 * baro;
         rate = turb ? a3 : rate;
@@ -225,16 +226,18 @@ __global__ void __launch_bounds__(BLOCK, 4) passage_fast_kernel(const KParams P,
         cz += turb ? code : 0u;
       }
       bool surv;
-      if (mv.need & NEED_DICE) surv = alive && (u_oc<float>(rng.pop()) <= rate);
+      if (mv.need & NEED_DICE) surv = alive && (u_oc<float>(rng.at(slot & 3)) <= rate);
       else surv = alive && rate >= 1.0f;
 
+#pragma unroll 1
       for (int p = mv.level_begin; p < mv.level_end; ++p) {                  // uniform bounds
         const bool here = loc == (int)FT.pair_node[p];
         const uint32_t bc = __ballot_sync(0xffffffffu, prev_alive && here);
         const uint32_t bs = __ballot_sync(0xffffffffu, surv && here);
+        const bool mine = (p & 31) == lane;
 #pragma unroll
         for (int r = 0; r < PR; ++r)
-          if ((p >> 5) == r && (p & 31) == lane) { acc_cnt[r] += __popc(bc); acc_suc[r] += __popc(bs); }
+          if ((p >> 5) == r && mine) { acc_cnt[r] += __popc(bc); acc_suc[r] += __popc(bs); }
       }
       const bool newU = ((pk >> 22) & 1u) && active && (int)mv.lex < best_rank;
       best_rank = newU ? (int)mv.lex : best_rank;
@@ -244,8 +247,11 @@ __global__ void __launch_bounds__(BLOCK, 4) passage_fast_kernel(const KParams P,
         const bool go = surv && deg > 0 && !s_stay[loc];
         int j = 0;
         if (mv.need & NEED_ROUTE) {
-          const float u = u_co<float>(rng.pop());
-          const int md = FT.max_deg[k];
+          const int sr = mv.slot_route;
+          if ((sr >> 2) != rng.cur) rng.refill(sr >> 2);                     // refill site B (uniform)
+          const float u = u_co<float>(rng.at(sr & 3));
+          const int md = mv.max_deg;
+#pragma unroll 1
           for (int e = 0; e < md - 1; ++e) j += (e < deg - 1 && s_cdf[eoff + e] <= u) ? 1 : 0;
         }
         loc = go ? (int)s_edge_dst[eoff + j] : loc;
