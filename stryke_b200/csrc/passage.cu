@@ -782,6 +782,7 @@ struct StrykePlan {
   DevBuf fast_nodes;
   FastTables fast{};
   size_t fast_smem_bytes = 0;
+  int fast_stride = 1;
   bool use_fast = false;
   int64_t trace_fish = 0;
   bool has_trace = false, trace_probs = false;
@@ -999,15 +1000,27 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
   // ---- throughput variant: fp32, native Philox, tallies only ---------------------------------------------------------
   pl->use_fast = pl->precision == 32 && !pl->inject && !pl->has_trace && o->kernel_variant != 1;
   if (pl->use_fast) {
+    int stride = 1;
+    for (int i = 0; i < f->n_nodes; ++i) stride = std::max(stride, (int)nodes[i].deg);
+    pl->fast_stride = stride;
+    pl->fast_smem_bytes = (size_t)fast_smem(f->n_nodes, f->n_units, stride, pl->n_species_staged).total;
+    if (pl->fast_smem_bytes > 96 * 1024) pl->use_fast = false;   // very wide graphs: the general kernel's CSR layout
+  }
+  if (pl->use_fast) {
     std::vector<uint2> fn(f->n_nodes);
     for (int i = 0; i < f->n_nodes; ++i) {
       fn[i].x = __float_as_uint_host(nodes[i].apriori32);
-      fn[i].y = pack_node(nodes[i].edge_off, nodes[i].deg, nodes[i].kind, nodes[i].hasU, nodes[i].unit);
+      fn[i].y = pack_node(nodes[i].kind, nodes[i].hasU, nodes[i].unit);
     }
     CK(upload(pl->fast_nodes, fn.data(), fn.size()));
-    for (int k = 0; k < f->n_moves; ++k) pl->fast.moves[k] = moves[k];
+    for (int k = 0; k < f->n_moves; ++k) {
+      MoveRec m = moves[k];
+      const NodeRec& n0 = nodes[pnode[m.level_begin]];
+      m.pad = pnode[m.level_begin];
+      if (m.need == 0 && m.level_end - m.level_begin == 1 && !n0.hasU) m.need |= NEED_TRIVIAL;
+      pl->fast.moves[k] = m;
+    }
     for (int p = 0; p < f->n_pairs; ++p) pl->fast.pair_node[p] = pnode[p];
-    pl->fast_smem_bytes = (size_t)fast_smem(f->n_nodes, f->n_units, f->n_edges, pl->n_species_staged).total;
   }
   CK(cudaDeviceSynchronize());
   guard.p = nullptr;
@@ -1050,7 +1063,7 @@ static int launch_fast(StrykePlan* pl, cudaStream_t st) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, BLOCK, pl->fast_smem_bytes));
     if (bps < 1) bps = 1;
   }
-  kern<<<pl->n_sm * bps, BLOCK, pl->fast_smem_bytes, st>>>(pl->K, pl->fast, pl->fast_nodes.as<uint2>(), pl->n_species_staged);
+  kern<<<pl->n_sm * bps, BLOCK, pl->fast_smem_bytes, st>>>(pl->K, pl->fast, pl->fast_nodes.as<uint2>(), pl->fast_stride, pl->n_species_staged);
   g_launches++;
   CK(cudaGetLastError());
   return STRYKE_OK;

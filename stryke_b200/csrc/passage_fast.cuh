@@ -6,82 +6,78 @@
 //   * the warp index is made provably warp-uniform (shuffle), and the per-move records + the (move, node) pair list
 //     live in the kernel parameter (constant) bank: the tile / cell / move / pair loops, every "does this level need
 //     a draw" test and the Philox refill decisions run on the uniform datapath with no BSSY/BSYNC reconvergence code;
+//   * levels that consist of one a-priori node with survival 1.0 and a single successor (river nodes, forebays,
+//     tailraces: most levels of a real facility) take a ~10-instruction path: every live fish is there, survives and
+//     moves on, so the tally is one ballot;
 //   * the branchy per-fish code of node_surv_rate (stryke.py:1396-1572) is straight-line predicated arithmetic: one
 //     unified strike formula (Kaplan and linear runners differ only in staged coefficients), selects instead of ifs;
-//   * node records are one 8-byte shared-memory load, unit coefficients one 16-byte load;
-//   * three Philox refill sites in the whole kernel (length block, per-node words, routing word), so the code stays
-//     inside the instruction cache.
+//   * the day's routing table is staged per warp as fixed-stride rows (cdf padded with 2.0, successor ids padded with
+//     the node itself; "fish stays today" rows point at themselves), so the categorical draw is a predicate-free
+//     count of cdf[e] <= u and the move is one byte load;
+//   * three Philox refill sites in the whole kernel (length block, per-node words, routing word); the key schedule
+//     comes straight from the constant bank (uniform adds).
 // tests/test_gpu_native_rng.py::test_fast_kernel_equals_general_kernel requires identical tallies from both.
 #pragma once
 
 namespace stryke {
 
-struct FastTables {                 // by-value kernel parameter (constant bank)
+constexpr uint8_t NEED_TRIVIAL = 32;   // MoveRec.need: single a-priori node, survival 1.0, <= 1 successor, no 'U'
+
+struct FastTables {                    // by-value kernel parameter (constant bank)
   MoveRec moves[STRYKE_MAX_MOVES];
   uint8_t pair_node[STRYKE_MAX_PAIRS];
 };
 
-// FastNode.y: edge_off[0:11) deg[11:19) kind[19:22) hasU[22] unit[23:30)
-__host__ __device__ inline uint32_t pack_node(int edge_off, int deg, int kind, int hasU, int unit) {
-  return (uint32_t)edge_off | ((uint32_t)deg << 11) | ((uint32_t)kind << 19) | ((uint32_t)(hasU ? 1 : 0) << 22) |
-         ((uint32_t)(unit < 0 ? 0 : unit) << 23);
+// FastNode.y: kind[0:3) hasU[3] unit[4:11)
+__host__ __device__ inline uint32_t pack_node(int kind, int hasU, int unit) {
+  return (uint32_t)kind | ((uint32_t)(hasU ? 1 : 0) << 3) | ((uint32_t)(unit < 0 ? 0 : unit) << 4);
 }
 
 struct FastSmem {
-  int nodes, edge_dst, ustatic, uc1, species, warp0, warp_stride, cdf, ucoef, stay, total;
+  int nodes, ustatic, uc1, species, warp0, warp_stride, cdf, dst, ucoef, total;
 };
-__host__ __device__ inline FastSmem fast_smem(int n_nodes, int n_units, int n_edges, int n_species_staged) {
+__host__ __device__ inline FastSmem fast_smem(int n_nodes, int n_units, int stride, int n_species_staged) {
   auto al = [](int x) { return (x + 15) & ~15; };
   FastSmem L;
   int o = 0;
   L.nodes = o; o = al(o + n_nodes * 8);
-  L.edge_dst = o; o = al(o + n_edges);
   L.ustatic = o; o = al(o + n_units * 16);
   L.uc1 = o; o = al(o + n_units * 4);
   L.species = o; o = al(o + n_species_staged * SPW * 4);
   L.warp0 = o;
   int w = 0;
-  L.cdf = w; w = al(w + n_edges * 4);
+  L.cdf = w; w = al(w + n_nodes * stride * 4);
   L.ucoef = w; w = al(w + n_units * 16);
-  L.stay = w; w = al(w + n_nodes);
+  L.dst = w; w = al(w + n_nodes * stride);
   L.warp_stride = w;
   L.total = o + w * WARPS;
   return L;
 }
 
-// The current Philox block; `cur` and every slot index are warp-uniform.
-struct BlockRng {
-  uint32_t c0, c1, c2, k0, k1, w0, w1, w2, w3;
-  int cur;
-  __device__ __forceinline__ void refill(int b) {
-    uint32_t w[4];
-    Philox::block(c0, c1, c2, (uint32_t)b, k0, k1, w);
-    w0 = w[0]; w1 = w[1]; w2 = w[2]; w3 = w[3]; cur = b;
-  }
-  __device__ __forceinline__ uint32_t at(int i) const {   // i in 0..3, uniform
-    return (i & 2) ? ((i & 1) ? w3 : w2) : ((i & 1) ? w1 : w0);
-  }
-};
+// acc_a += a, acc_b += b on the lane whose id equals `p` (one ISETP + two predicated adds)
+__device__ __forceinline__ void add_if_lane(uint32_t& acc_a, uint32_t& acc_b, int p, int lane_id, uint32_t a, uint32_t b) {
+  asm("{\n\t.reg .pred q;\n\tsetp.eq.s32 q, %2, %3;\n\t@q add.u32 %0, %0, %4;\n\t@q add.u32 %1, %1, %5;\n\t}"
+      : "+r"(acc_a), "+r"(acc_b) : "r"(p), "r"(lane_id), "r"(a), "r"(b));
+}
 
 template <int PR, bool BARO>
 __global__ void __launch_bounds__(BLOCK, 4) passage_fast_kernel(const KParams P, const __grid_constant__ FastTables FT,
-                                                                const uint2* __restrict__ g_nodes, const int n_species_staged) {
+                                                                const uint2* __restrict__ g_nodes, const int stride,
+                                                                const int n_species_staged) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const FastSmem SL = fast_smem(P.n_nodes, P.n_units, P.n_edges, n_species_staged);
+  const FastSmem SL = fast_smem(P.n_nodes, P.n_units, stride, n_species_staged);
   uint2* s_nodes = reinterpret_cast<uint2*>(smem + SL.nodes);
-  uint8_t* s_edge_dst = smem + SL.edge_dst;
   float4* s_ustatic = reinterpret_cast<float4*>(smem + SL.ustatic);     // rack, intake_vel, fb_depth, c0
   float* s_uc1 = reinterpret_cast<float*>(smem + SL.uc1);               // c1
   float* s_species = reinterpret_cast<float*>(smem + SL.species);
   const int lane = threadIdx.x & 31;
   const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   unsigned char* wbase = smem + SL.warp0 + wid * SL.warp_stride;
-  float* s_cdf = reinterpret_cast<float*>(wbase + SL.cdf);
+  float* s_cdf = reinterpret_cast<float*>(wbase + SL.cdf);              // [n_nodes][stride], padded with 2.0
   float4* s_ucoef = reinterpret_cast<float4*>(wbase + SL.ucoef);        // fa, fb, fc, has_flow
-  uint8_t* s_stay = wbase + SL.stay;
+  uint8_t* s_dst = wbase + SL.dst;                                      // [n_nodes][stride], padded with the node itself
 
   for (int i = threadIdx.x; i < P.n_nodes; i += BLOCK) s_nodes[i] = g_nodes[i];
-  for (int i = threadIdx.x; i < P.n_edges; i += BLOCK) s_edge_dst[i] = P.edge_dst[i];
   for (int u = threadIdx.x; u < P.n_units; u += BLOCK) {
     const double* us = P.unit_static + u * STRYKE_UNIT_STATIC_W;
     const double p2 = P_ATM + RHO * G_SI * (us[3] * FT2M);
@@ -107,10 +103,11 @@ __global__ void __launch_bounds__(BLOCK, 4) passage_fast_kernel(const KParams P,
   int64_t cur_cell = -1;
   float sp_ls = 0, sp_ll = 0, sp_lsc = 0, sp_lm = 0, sp_lsd = 0, sp_wr = 0, sp_uc = 0, sp_d1 = 0, sp_dd = 0, sp_b0 = 0, sp_b1 = 0;
   int sp_mode = 0, n_c = 0;
-  uint64_t cid = 0;
+  uint32_t cid_lo = 0, cid_hi = 0;
   uint32_t acc_suc[PR], acc_cnt[PR], acc_daily = 0;
+  int lane_r[PR];
 #pragma unroll
-  for (int r = 0; r < PR; ++r) { acc_suc[r] = 0; acc_cnt[r] = 0; }
+  for (int r = 0; r < PR; ++r) { acc_suc[r] = 0; acc_cnt[r] = 0; lane_r[r] = lane + 32 * r; }
 
   auto flush = [&](int64_t cell) {
 #pragma unroll
@@ -134,7 +131,8 @@ __global__ void __launch_bounds__(BLOCK, 4) passage_fast_kernel(const KParams P,
       if (cur_cell >= 0) flush(cur_cell);
       cur_cell = c;
       n_c = P.cell_n[c];
-      cid = P.cell_id[c];
+      const uint64_t cid = P.cell_id[c];
+      cid_lo = (uint32_t)cid; cid_hi = (uint32_t)(cid >> 32);
       const int s = P.cell_species[c];
       if (s < n_species_staged) {
         const float* q = s_species + s * SPW;
@@ -147,13 +145,18 @@ __global__ void __launch_bounds__(BLOCK, 4) passage_fast_kernel(const KParams P,
         sp_dd = (float)q[9] - (float)q[8]; sp_b0 = (float)q[10] * 1.44269504f; sp_b1 = (float)q[11];
       }
       const int d = P.cell_day[c];
-      if (d != cur_day) {
+      if (d != cur_day) {   // stage the day's routing rows and unit coefficients in this warp's slot
         cur_day = d;
         __syncwarp();
         const double* cdf = P.edge_cdf + (size_t)d * P.n_edges;
-        for (int i = lane; i < P.n_edges; i += 32) s_cdf[i] = (float)cdf[i];
         const uint8_t* st = P.node_stay + (size_t)d * P.n_nodes;
-        for (int i = lane; i < P.n_nodes; i += 32) s_stay[i] = st[i];
+        for (int i = lane; i < P.n_nodes * stride; i += 32) {
+          const int v = i / stride, e = i - v * stride;
+          const NodeRec nr = P.nodes[v];
+          const bool real = e < (int)nr.deg && !st[v];
+          s_cdf[i] = real ? (float)cdf[nr.edge_off + e] : 2.0f;
+          s_dst[i] = real ? P.edge_dst[nr.edge_off + e] : (uint8_t)v;
+        }
         const double* uc = P.unit_coef + (size_t)d * P.n_units * STRYKE_UNIT_COEF_W;
         for (int u = lane; u < P.n_units; u += 32) {
           const double* r = uc + u * STRYKE_UNIT_COEF_W;
@@ -169,11 +172,14 @@ __global__ void __launch_bounds__(BLOCK, 4) passage_fast_kernel(const KParams P,
     const int fish = (int)((t - c_begin) * 32 + lane);
     const bool active = fish < n_c;
 
-    BlockRng rng;
-    rng.c0 = (uint32_t)fish; rng.c1 = (uint32_t)cid; rng.c2 = (uint32_t)(cid >> 32); rng.k0 = P.seed_lo; rng.k1 = P.seed_hi;
-    rng.refill(0);
+    // ---- Philox: counter (fish, cell id, block), key = seed (constant bank) -------------------------------------
+    uint32_t w[4];
+    int cur_b = 0;
+    Philox::block((uint32_t)fish, cid_lo, cid_hi, 0u, P.seed_lo, P.seed_hi, w);
+    auto word = [&](int i) -> uint32_t { return (i & 2) ? ((i & 1) ? w[3] : w[2]) : ((i & 1) ? w[1] : w[0]); };
+
     // ---- (2) length: words 0, 1 ----------------------------------------------------------------------------------
-    const float z = std_normal(u_oc<float>(rng.w0), u_co<float>(rng.w1));
+    const float z = std_normal(u_oc<float>(w[0]), u_co<float>(w[1]));
     float L;
     if (sp_mode == 0) L = fminf(fabsf(fmaf(exp_approx(sp_ls * z), sp_lsc, sp_ll)), 150.f) * 0.0328084f;
     else L = fabsf(fmaf(sp_lsd, z, sp_lm)) * (1.f / 12.f);
@@ -187,22 +193,34 @@ __global__ void __launch_bounds__(BLOCK, 4) passage_fast_kernel(const KParams P,
 
     for (int k = 0; k < n_moves; ++k) {
       const MoveRec mv = FT.moves[k];                    // constant bank, uniform index
+      if (mv.need & NEED_TRIVIAL) {
+        // one a-priori node, survival 1.0, at most one successor, no 'U' in its name: every live fish is here,
+        // survives (stryke.py:3210 with rate 1.0) and moves to the only successor (or stays, stryke.py:1849-1855)
+        const uint32_t pc = __popc(__ballot_sync(0xffffffffu, alive));
+#pragma unroll
+        for (int r = 0; r < PR; ++r) add_if_lane(acc_cnt[r], acc_suc[r], mv.level_begin, lane_r[r], pc, pc);
+        if (k < n_moves - 1) loc = alive ? (int)s_dst[(int)mv.pad * stride] : loc;
+        continue;
+      }
       const uint2 nd = s_nodes[loc];
       const uint32_t pk = nd.y;
-      const int kind = (pk >> 19) & 7, deg = (pk >> 11) & 0xff, eoff = pk & 0x7ff;
+      const int kind = pk & 7;
       const bool prev_alive = alive;
       float rate = alive ? __uint_as_float(nd.x) : 0.f;
       int slot = mv.slot_base;
       if (mv.need & (NEED_CAUSE | NEED_DICE)) {
-        if ((slot >> 2) != rng.cur) rng.refill(slot >> 2);         // refill site A (uniform)
+        if ((slot >> 2) != cur_b) {                      // refill site A (uniform)
+          cur_b = slot >> 2;
+          Philox::block((uint32_t)fish, cid_lo, cid_hi, (uint32_t)cur_b, P.seed_lo, P.seed_hi, w);
+        }
       }
       if (mv.need & NEED_CAUSE) {                        // this level has turbine nodes (uniform)
         float u_rr = 0.f, u_dep = 0.f;
-        if (mv.need & NEED_RR) { u_rr = u_co<float>(rng.at(slot & 3)); ++slot; }
-        if (BARO) { u_dep = u_co<float>(rng.at(slot & 3)); ++slot; }
-        const float u_cau = u_co<float>(rng.at(slot & 3)); ++slot;
+        if (mv.need & NEED_RR) { u_rr = u_co<float>(word(slot & 3)); ++slot; }
+        if (BARO) { u_dep = u_co<float>(word(slot & 3)); ++slot; }
+        const float u_cau = u_co<float>(word(slot & 3)); ++slot;
         const bool turb = alive && kind != STRYKE_KIND_APRIORI;
-        const int unit = turb ? (int)((pk >> 23) & 0x7f) : 0;
+        const int unit = turb ? (int)((pk >> 4) & 0x7f) : 0;
         const float4 us = s_ustatic[unit];
         const float4 uc = s_ucoef[unit];
         const bool blocked = blocked_w > us.x;                               // stryke.py:1419
@@ -226,35 +244,39 @@ __global__ void __launch_bounds__(BLOCK, 4) passage_fast_kernel(const KParams P,
         cz += turb ? code : 0u;
       }
       bool surv;
-      if (mv.need & NEED_DICE) surv = alive && (u_oc<float>(rng.at(slot & 3)) <= rate);
+      if (mv.need & NEED_DICE) surv = alive && (u_oc<float>(word(slot & 3)) <= rate);
       else surv = alive && rate >= 1.0f;
 
+      // ---- (6) State_Daily: lane p owns pair p ---------------------------------------------------------------------
+      const int key_c = prev_alive ? loc : 0x1ff, key_s = surv ? loc : 0x1ff;
 #pragma unroll 1
       for (int p = mv.level_begin; p < mv.level_end; ++p) {                  // uniform bounds
-        const bool here = loc == (int)FT.pair_node[p];
-        const uint32_t bc = __ballot_sync(0xffffffffu, prev_alive && here);
-        const uint32_t bs = __ballot_sync(0xffffffffu, surv && here);
-        const bool mine = (p & 31) == lane;
+        const int node = (int)FT.pair_node[p];
+        const uint32_t pc = __popc(__ballot_sync(0xffffffffu, key_c == node));
+        const uint32_t ps = __popc(__ballot_sync(0xffffffffu, key_s == node));
 #pragma unroll
-        for (int r = 0; r < PR; ++r)
-          if ((p >> 5) == r && mine) { acc_cnt[r] += __popc(bc); acc_suc[r] += __popc(bs); }
+        for (int r = 0; r < PR; ++r) add_if_lane(acc_cnt[r], acc_suc[r], p, lane_r[r], pc, ps);
       }
-      const bool newU = ((pk >> 22) & 1u) && active && (int)mv.lex < best_rank;
+      const bool newU = ((pk >> 3) & 1u) && active && (int)mv.lex < best_rank;
       best_rank = newU ? (int)mv.lex : best_rank;
       ent_surv = newU ? surv : ent_surv;
 
+      // ---- (3) movement --------------------------------------------------------------------------------------------
       if (k < n_moves - 1) {
-        const bool go = surv && deg > 0 && !s_stay[loc];
+        const int row = loc * stride;
         int j = 0;
         if (mv.need & NEED_ROUTE) {
           const int sr = mv.slot_route;
-          if ((sr >> 2) != rng.cur) rng.refill(sr >> 2);                     // refill site B (uniform)
-          const float u = u_co<float>(rng.at(sr & 3));
+          if ((sr >> 2) != cur_b) {                                          // refill site B (uniform)
+            cur_b = sr >> 2;
+            Philox::block((uint32_t)fish, cid_lo, cid_hi, (uint32_t)cur_b, P.seed_lo, P.seed_hi, w);
+          }
+          const float u = u_co<float>(word(sr & 3));
           const int md = mv.max_deg;
 #pragma unroll 1
-          for (int e = 0; e < md - 1; ++e) j += (e < deg - 1 && s_cdf[eoff + e] <= u) ? 1 : 0;
+          for (int e = 0; e < md - 1; ++e) j += (s_cdf[row + e] <= u) ? 1 : 0;   // searchsorted(cdf, u, 'right')
         }
-        loc = go ? (int)s_edge_dst[eoff + j] : loc;
+        loc = surv ? (int)s_dst[row + j] : loc;
       }
       alive = surv;
     }
