@@ -28,8 +28,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-# Algorithmic lane-ops per fish-passage (DESIGN.md §"Roofline"): Philox blocks x 44 + length 24 + per-move work.
-ALGO_LANE_OPS = {"c2": 330.0, "c3": 330.0, "c5": 1250.0}
+# Algorithmic lane-ops per fish-passage (derivation: DESIGN.md §4 "Roofline").
+ALGO_LANE_OPS = {"c2": 350.0, "c3": 350.0, "c5": 1250.0}
 
 
 def workload_project(name, n_fish, iterations, days):
@@ -82,27 +82,35 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_port_rate(name, n_fish, cells, procs, seed=0):
-    """The oracle (NumPy port of the reference path) on the host cores: fish-passages/s over ``cells`` cells of
-    ``n_fish`` fish each, fanned out over ``procs`` processes (the reference itself is single-threaded)."""
+CPU_SAMPLE = {"c2": dict(n_fish=200_000, iterations=24, days=1), "c5": dict(n_fish=100_000, iterations=12, days=1),
+              "c3": dict(n_fish=0, iterations=2, days=40)}    # per worker process and per step
+
+
+def cpu_port_rate(name, procs, seed=0, scale=1):
+    """The oracle (NumPy port of the reference path, oracle/stryke_oracle.run_project) on the host cores, fanned out
+    over ``procs`` processes (the reference itself is single-threaded): a bounded sample of the same workload."""
     import multiprocessing as mp
-    per = max(1, cells // procs)
+    cfg = dict(CPU_SAMPLE[name])
+    cfg["iterations"] = max(1, cfg["iterations"] * scale)
     t0 = time.perf_counter()
     if procs == 1:
-        done = _cpu_worker((name, n_fish, per, seed))
+        parts = [_cpu_worker((name, cfg, seed))]
     else:
         with mp.get_context("fork").Pool(procs) as pool:
-            done = sum(pool.map(_cpu_worker, [(name, n_fish, per, seed + i) for i in range(procs)]))
+            parts = pool.map(_cpu_worker, [(name, cfg, seed + i) for i in range(procs)])
     dt = time.perf_counter() - t0
-    return done / dt, done, dt
+    done, cells = sum(p[0] for p in parts), sum(p[1] for p in parts)
+    desc = (f"{done} fish-passages ({cells} cells) in {dt:.1f} s on {procs} processes: per process "
+            f"{cfg['iterations']} iterations x {cfg['days']} day(s)" + (f" x {cfg['n_fish']} fish" if cfg["n_fish"] else " x 20 species, EPRI counts"))
+    return done / dt, done, dt, desc
 
 
 def _cpu_worker(args):
-    name, n_fish, cells, seed = args
+    name, cfg, seed = args
     from oracle import stryke_oracle as O
-    prj = workload_project(name, n_fish, cells, 1)
+    prj = workload_project(name, cfg["n_fish"], cfg["iterations"], cfg["days"])
     out = O.run_project(prj, seed=seed)
-    return int(sum(int(r["daily"][0]) for r in out))
+    return int(sum(int(r["daily"][0]) for r in out)), len(out)
 
 
 def main():
@@ -139,22 +147,20 @@ def main():
         # (oracle/stryke_oracle.py) on all host cores, on a bounded sample of the same workload.
         if rank != 0:
             return
-        sample_fish = 200_000 if args.workload != "c3" else 0
-        cells = nproc
-        vals = []
+        vals, desc = [], ""
         for i in range(args.warmup + args.steps):
-            rate, done, dt = cpu_port_rate(args.workload, sample_fish, cells, nproc, seed=100 + i)
+            rate, done, dt, desc = cpu_port_rate(args.workload, nproc, seed=100 + i)
             if i >= args.warmup:
                 vals.append((rate, done, dt))
-        rate = float(np.mean([v[0] for v in vals]))
+        rate = float(sum(v[1] for v in vals) / sum(v[2] for v in vals))
         line = {"impl": "reference", "metric": "simulated fish-passages/sec (route+strike+survival)", "value": rate,
                 "unit": "fish-passages/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": float(np.mean([v[2] for v in vals]) * 1e3), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_desc},
                 "cpu_baseline": {"value": rate, "unit": "fish-passages/s", "cores": nproc, "kind": "port",
-                                 "sample": f"{cells} cells x {sample_fish} fish per step, {nproc} processes (NumPy port of Stryke/stryke.py:2897-3383; "
-                                           "the unmodified reference measured 2087 fish-passages/s on one core, BASELINE.md §2)"},
+                                 "sample": f"per step: {desc} (NumPy port of Stryke/stryke.py:2897-3383; the unmodified "
+                                           "reference measured 2087 fish-passages/s on one core, BASELINE.md §2)"},
                 "e2e": {"value": rate, "unit": "fish-passages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
@@ -236,10 +242,12 @@ def main():
         inst_per_fish = pj.get("thread_inst_per_fish")
     roofline = {"bound": "issue", "achieved": achieved / 1e12, "peak": peak_ops / 1e12, "unit": "Tlane-op/s",
                 "frac": achieved / peak_ops, "traffic": traffic,
-                "note": "neither HBM nor tensor binds this path (SURVEY.md §8d): bound = SM instruction issue (INT32 Philox + FP32/SFU). "
-                        f"achieved = {algo:.0f} algorithmic lane-ops per fish-passage (DESIGN.md) x fish-passages/s per GPU; peak = lane-ops/s of "
-                        "an independent IMAD+LOP3 stream measured live by stryke_b200_calibrate_issue on this GPU",
+                "note": "neither HBM nor tensor binds this path (SURVEY.md §8d): bound = SM instruction issue (INT32 Philox + FP32/MUFU). "
+                        f"achieved = {algo:.0f} algorithmic lane-ops per fish-passage (DESIGN.md §4) x fish-passages/s per GPU; peak = lane-ops/s of "
+                        "an 8 FFMA + 8 LOP3 per-iteration independent-chain stream (both half-rate pipes busy: 1 warp instruction per scheduler "
+                        "per cycle) measured live by stryke_b200_calibrate_issue on this GPU; traffic = DRAM bytes per launch (ncu)",
                 "executed_thread_inst_per_fish_ncu": inst_per_fish,
+                "issue_utilisation_executed": (per_gpu_rate * inst_per_fish / peak_ops) if inst_per_fish and args.workload == "c2" else None,
                 "hbm": {"achieved_GBps": (plan.n_cells * (4 + 20 + plan.n_pairs * 8) * 2) / (ms_total / args.steps * 1e-3) / 1e9,
                         "peak_GBps": _measured_peak()}}
 
@@ -250,19 +258,29 @@ def main():
                                      plan_h.fac.edge_dst, plan_h.fac.unit_static, plan_h.days.edge_cdf, plan_h.days.node_stay,
                                      plan_h.days.unit_coef, plan_h.days.curr_Q, species, plan_h.cell_day, plan_h.cell_species, cell_id))
         d2h = plan.n_cells * (4 + _abi.DAILY_W * 4 + plan.n_pairs * 8)
-        e2e_steps = max(2, min(args.steps, 3))
-        engine.run_cells(plan_h.fac, plan_h.days, species, plan_h.cell_day, plan_h.cell_species, cell_id, device=local_rank,
-                         precision=args.precision, seed=1, max_daily_fish=2_000_000_000)
+        e2e_steps = max(2, min(args.steps, 5))
+
+        def pinned(a):      # host buffers of the call live in pinned memory (full PCIe rate for both directions)
+            t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            return t.numpy()
+        h_day, h_spc, h_id = pinned(plan_h.cell_day), pinned(plan_h.cell_species), pinned(cell_id)
+        out = (pinned(np.zeros(plan.n_cells, np.int32)), pinned(np.zeros((plan.n_cells, _abi.DAILY_W), np.uint32)),
+               pinned(np.zeros((plan.n_cells, plan.n_pairs, 2), np.uint32)))
+        dev = f"cuda:{local_rank}"
+        engine.run_cells(plan_h.fac, plan_h.days, species, h_day, h_spc, h_id, device=local_rank, precision=args.precision,
+                         seed=1, max_daily_fish=2_000_000_000, out=out)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
-            r = engine.run_cells(plan_h.fac, plan_h.days, species, plan_h.cell_day, plan_h.cell_species, cell_id,
-                                 device=local_rank, precision=args.precision, seed=3000 + i, max_daily_fish=2_000_000_000)
-            if world > 1:
-                td = torch.from_numpy(r.daily.view(np.int32)).to(f"cuda:{local_rank}")
+            r = engine.run_cells(plan_h.fac, plan_h.days, species, h_day, h_spc, h_id, device=local_rank,
+                                 precision=args.precision, seed=3000 + i, max_daily_fish=2_000_000_000, out=out)
+            if world > 1:   # the public multi-GPU call ends with the tally all-reduce
+                td = torch.from_numpy(r.daily.view(np.int32)).to(dev, non_blocking=True)
+                ts = torch.from_numpy(r.state_daily.view(np.int32)).to(dev, non_blocking=True)
                 dist.all_reduce(td)
-                td.cpu()
+                dist.all_reduce(ts)
+                td.cpu(), ts.cpu()
         dt = time.perf_counter() - t0
         t_dt = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local_rank}")
         if world > 1:
@@ -273,11 +291,10 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sample_fish = 200_000 if args.workload != "c3" else 0
-        rate, done, dt = cpu_port_rate(args.workload, sample_fish, nproc, nproc, seed=5)
+        rate, done, dt, desc = cpu_port_rate(args.workload, nproc, seed=5, scale=2)
         cpu = {"value": rate, "unit": "fish-passages/s", "cores": nproc, "kind": "port",
-               "sample": f"{done} fish-passages in {dt:.1f} s: {nproc} cells x {sample_fish} fish, {nproc} processes (NumPy port "
-                         "oracle/stryke_oracle.py; unmodified reference: 2087 fish-passages/s/core, BASELINE.md §2)"}
+               "sample": f"{desc} (NumPy port oracle/stryke_oracle.py; unmodified reference: 2087 fish-passages/s/core, "
+                         "BASELINE.md §2)"}
     if rank == 0:
         line = {"metric": "simulated fish-passages/sec (route+strike+survival)", "value": value, "unit": "fish-passages/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,

@@ -145,7 +145,18 @@ def c3_population(n_species=4, iterations=2, days=5, curr_Q=9000.0, scenarios=("
                                 shape=sp["shape"], location=sp["location"], scale=sp["scale"], dist=sp["dist"],
                                 max_ent_rate=sp["max_ent_rate"]))
     prj["population"] = pop
-    prj["flow_scenarios"] = _scenario_rows(list(scenarios), months=_months_for(days))
+    start = "2023-03-01"
+    if days > 300:   # a full synthetic year: lognormal-ish seasonal hydrograph around curr_Q
+        start = "2023-01-01"
+        rs = np.random.RandomState(1)
+        q = curr_Q * np.exp(0.35 * np.sin(2 * np.pi * (np.arange(days) - 60) / 365.0) + 0.25 * rs.standard_normal(days))
+        import datetime as _dt
+        d0 = _dt.date.fromisoformat(start)
+        prj["hydrograph"] = [dict(Date=(d0 + _dt.timedelta(days=i)).isoformat(), Discharge=float(q[i])) for i in range(days)]
+    prj["flow_scenarios"] = _scenario_rows(list(scenarios), months=_months_for(days, start))
+    if len(scenarios) > 1:   # one hydrograph, scaled per scenario through Prorate (x0.5 .. x2)
+        for r, k in zip(prj["flow_scenarios"], np.linspace(0.5, 2.0, len(scenarios))):
+            r["Prorate"] = float(k)
     prj["facility_params"] = [dict(prj["facility_params"][0], Scenario=s) for s in scenarios]
     prj["operating_scenarios"] = [dict(r, Scenario=s) for s in scenarios for r in prj["operating_scenarios"][:3]]
     return prj

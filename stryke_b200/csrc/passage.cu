@@ -21,6 +21,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -717,19 +718,28 @@ __global__ void philox_kernel(int64_t n, const uint32_t* __restrict__ ctr, const
   Philox::block(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1], w);
   out[4 * i] = w[0]; out[4 * i + 1] = w[1]; out[4 * i + 2] = w[2]; out[4 * i + 3] = w[3];
 }
-// 8 independent IMAD + 8 independent LOP3 chains per thread: the two issue pipes Philox lives on
+// Issue-rate calibration: per loop iteration exactly 8 independent FFMA (fma pipe) + 8 independent 3-input LOP3 (alu
+// pipe) per thread, written in PTX so the count is exact; a warp scheduler can issue one of them per cycle when both
+// half-rate pipes are kept busy, which is the ceiling the passage kernel is measured against.
 constexpr int CAL_ITERS = 4096, CAL_OPS = 16;
 __global__ void __launch_bounds__(256) calibrate_kernel(uint32_t* out, uint32_t seed) {
-  uint32_t a[8], b[8];
+  float x[8];
+  uint32_t b[8];
+  const float m = 1.0f + 1e-7f * (float)(seed & 7), c = 1e-9f * (float)(threadIdx.x & 3);
+  const uint32_t k1 = seed * 2654435761u, k2 = ~seed | 0x01010101u;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { a[i] = seed + threadIdx.x * 8 + i; b[i] = seed ^ (blockIdx.x * 8 + i); }
+  for (int i = 0; i < 8; ++i) { x[i] = (float)(threadIdx.x + i); b[i] = seed ^ (blockIdx.x * 8 + i); }
+#pragma unroll 1
   for (int it = 0; it < CAL_ITERS; ++it) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { a[i] = a[i] * 0xD2511F53u + b[i]; b[i] = (b[i] ^ a[(i + 1) & 7]) & (seed | a[i]); }
+    for (int i = 0; i < 8; ++i) {
+      asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(x[i]) : "f"(m), "f"(c));
+      asm volatile("lop3.b32 %0, %0, %1, %2, 0x6a;" : "+r"(b[i]) : "r"(k1), "r"(k2));   // b ^ (k1 & k2)
+    }
   }
   uint32_t s = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s += a[i] ^ b[i];
+  for (int i = 0; i < 8; ++i) s += __float_as_uint(x[i]) ^ b[i];
   if (s == 0x12345678u) out[0] = s;   // never true in practice; keeps the chains live
 }
 
@@ -748,13 +758,31 @@ static inline uint32_t __float_as_uint_host(float f) { uint32_t u; memcpy(&u, &f
       return fail(STRYKE_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));                      \
   } while (0)
 
+// Device buffers come from the stream-ordered pool of the legacy default stream (cudaMallocAsync): after the first
+// call the pool keeps its memory (release threshold = max), so the one-shot host-buffer entry point does not pay
+// cudaMalloc/cudaFree for its ~30 tables on every call.
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t b) { bytes = b; return cudaMalloc(&p, b ? b : 16); }
+  ~DevBuf() { if (p) cudaFreeAsync(p, 0); }
+  cudaError_t alloc(size_t b) { bytes = b; return cudaMallocAsync(&p, b ? b : 16, 0); }
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
+static int device_sm_count(int device, int* n_sm) {
+  static int cache[64] = {0};
+  if (device >= 0 && device < 64 && cache[device] > 0) { *n_sm = cache[device]; return 0; }
+  int v = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+  if (e != cudaSuccess) return 1;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  if (device >= 0 && device < 64) cache[device] = v;
+  *n_sm = v;
+  return 0;
+}
 template <typename T>
 static cudaError_t upload(DevBuf& d, const T* h, size_t n, cudaStream_t st = 0) {
   cudaError_t e = d.alloc(n * sizeof(T));
@@ -830,7 +858,11 @@ int stryke_b200_device_count(void) {
 }
 
 int stryke_b200_plan_destroy(StrykePlan* plan) {
-  if (plan) { cudaSetDevice(plan->device); delete plan; }
+  if (plan) {
+    cudaSetDevice(plan->device);
+    cudaDeviceSynchronize();      // launches on other streams may still read the tables
+    delete plan;
+  }
   return STRYKE_OK;
 }
 
@@ -848,9 +880,7 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
   pl->device = o->device; pl->precision = o->precision; pl->max_daily_fish = o->max_daily_fish;
   pl->inject = o->injected != nullptr;
   pl->n_cells = c->n_cells;
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, o->device));
-  pl->n_sm = prop.multiProcessorCount;
+  if (device_sm_count(o->device, &pl->n_sm)) return fail(STRYKE_E_CUDA, "cannot query the SM count");
 
   // ---- static facility records -----------------------------------------------------------------------------------
   std::vector<NodeRec> nodes(f->n_nodes);
@@ -1022,7 +1052,7 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
     }
     for (int p = 0; p < f->n_pairs; ++p) pl->fast.pair_node[p] = pnode[p];
   }
-  CK(cudaDeviceSynchronize());
+  CK(cudaStreamSynchronize(0));      // uploads done: the caller may release its host tables
   guard.p = nullptr;
   *out = pl;
   return STRYKE_OK;
@@ -1053,9 +1083,9 @@ static int launch_passage_pr(StrykePlan* pl, cudaStream_t st) {
   }
 }
 
-template <int PR, bool BARO>
+template <int PR, bool BARO, int MINB>
 static int launch_fast(StrykePlan* pl, cudaStream_t st) {
-  auto kern = passage_fast_kernel<PR, BARO>;
+  auto kern = passage_fast_kernel<PR, BARO, MINB>;
   if (pl->fast_smem_bytes > 48 * 1024)
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem_bytes));
   int bps = pl->blocks_per_sm;
@@ -1068,13 +1098,20 @@ static int launch_fast(StrykePlan* pl, cudaStream_t st) {
   CK(cudaGetLastError());
   return STRYKE_OK;
 }
-static int launch_fast_any(StrykePlan* pl, cudaStream_t st) {
+template <int MINB>
+static int launch_fast_minb(StrykePlan* pl, cudaStream_t st) {
   const bool b = pl->K.barotrauma != 0;
   switch (pl->pr) {
-    case 1: return b ? launch_fast<1, true>(pl, st) : launch_fast<1, false>(pl, st);
-    case 2: return b ? launch_fast<2, true>(pl, st) : launch_fast<2, false>(pl, st);
-    default: return b ? launch_fast<4, true>(pl, st) : launch_fast<4, false>(pl, st);
+    case 1: return b ? launch_fast<1, true, MINB>(pl, st) : launch_fast<1, false, MINB>(pl, st);
+    case 2: return b ? launch_fast<2, true, MINB>(pl, st) : launch_fast<2, false, MINB>(pl, st);
+    default: return b ? launch_fast<4, true, MINB>(pl, st) : launch_fast<4, false, MINB>(pl, st);
   }
+}
+static int launch_fast_any(StrykePlan* pl, cudaStream_t st) {
+  static const int minb = [] { const char* e = getenv("STRYKE_B200_MINB"); return e ? atoi(e) : 4; }();
+  if (minb == 5) return launch_fast_minb<5>(pl, st);
+  if (minb == 6) return launch_fast_minb<6>(pl, st);
+  return launch_fast_minb<4>(pl, st);
 }
 
 extern "C" {
@@ -1255,11 +1292,11 @@ int stryke_b200_calibrate_issue(int device, void* stream, double* lane_ops_per_s
   if (stryke_b200_device_count() <= 0) return fail(STRYKE_E_NOGPU, "no CUDA device visible: stryke_b200 has no CPU fallback");
   CK(cudaSetDevice(device));
   cudaStream_t st = (cudaStream_t)stream;
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
+  int n_sm = 0;
+  if (device_sm_count(device, &n_sm)) return fail(STRYKE_E_CUDA, "cannot query the SM count");
   DevBuf o;
   CK(o.alloc(16));
-  const int grid = prop.multiProcessorCount * 8;
+  const int grid = n_sm * 8;
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   calibrate_kernel<<<grid, 256, 0, st>>>(o.as<uint32_t>(), 12345u);   // warm-up

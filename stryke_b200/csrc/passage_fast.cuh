@@ -60,8 +60,8 @@ __device__ __forceinline__ void add_if_lane(uint32_t& acc_a, uint32_t& acc_b, in
       : "+r"(acc_a), "+r"(acc_b) : "r"(p), "r"(lane_id), "r"(a), "r"(b));
 }
 
-template <int PR, bool BARO>
-__global__ void __launch_bounds__(BLOCK, 4) passage_fast_kernel(const KParams P, const __grid_constant__ FastTables FT,
+template <int PR, bool BARO, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) passage_fast_kernel(const KParams P, const __grid_constant__ FastTables FT,
                                                                 const uint2* __restrict__ g_nodes, const int stride,
                                                                 const int n_species_staged) {
   extern __shared__ __align__(16) unsigned char smem[];

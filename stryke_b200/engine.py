@@ -111,16 +111,22 @@ def _tables(fac: FacilityTables, days: DayTables, species: np.ndarray, cell_day,
 
 def run_cells(fac, days, species, cell_day, cell_species, cell_id, *, device=0, precision=32, seed=0,
               max_daily_fish=100000, blocks_per_sm=0, injected: Injected | None = None,
-              trace: TraceBuffers | None = None, kernel_variant=0) -> CellResult:
+              trace: TraceBuffers | None = None, kernel_variant=0, out=None) -> CellResult:
     """One call of ``stryke_b200_run``: everything between the presence roll and the Daily / State_Daily tallies
     (stryke.py:3025-3366) for the listed cells, on the GPU, host buffers in and out."""
     keep = []
     f, d, st, cl = _tables(fac, days, species, cell_day, cell_species, cell_id, keep)
     o = _opts(device, precision, seed, max_daily_fish, blocks_per_sm, injected, trace, keep, kernel_variant)
     n = int(cl.n_cells)
-    out_n = np.zeros(n, np.int32)
-    out_d = np.zeros((n, _abi.DAILY_W), np.uint32)
-    out_s = np.zeros((n, fac.n_pairs, 2), np.uint32)
+    if out is not None:      # caller-owned (e.g. pinned) host buffers
+        out_n, out_d, out_s = out
+        assert out_n.dtype == np.int32 and out_n.shape == (n,) and out_n.flags["C_CONTIGUOUS"]
+        assert out_d.dtype == np.uint32 and out_d.shape == (n, _abi.DAILY_W) and out_d.flags["C_CONTIGUOUS"]
+        assert out_s.dtype == np.uint32 and out_s.shape == (n, fac.n_pairs, 2) and out_s.flags["C_CONTIGUOUS"]
+    else:
+        out_n = np.zeros(n, np.int32)
+        out_d = np.zeros((n, _abi.DAILY_W), np.uint32)
+        out_s = np.zeros((n, fac.n_pairs, 2), np.uint32)
     t = _abi.Tallies()
     t.cell_n, t.daily, t.state_daily = _abi.ptr(out_n), _abi.ptr(out_d), _abi.ptr(out_s)
     _abi.check(_abi.lib().stryke_b200_run(C.byref(f), C.byref(d), C.byref(st), C.byref(cl), C.byref(o), C.byref(t)))

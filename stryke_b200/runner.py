@@ -156,6 +156,39 @@ class RunPlan:
         cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
         self.cell_day, self.cell_species, self.cell_id = cat(day_idx, np.int32), cat(sp_idx, np.int32), cat(ids, np.uint64)
         self.n_cells = c0
+        self.cell_hours = {}
+        if self.peaking:
+            self._peaking_hours()
+
+    def _peaking_hours(self):
+        """Peaking / pumped-storage plants (stryke.py:2405-2431): per (species, iteration, day) every unit flips a
+        not-operating coin and draws lognormal hours clipped to [0, 24]; a cell with no operating unit is skipped
+        altogether (stryke.py:3025).  Drawn here with NumPy, vectorised over the group's cells (same distributions,
+        not the reference's draw order)."""
+        from scipy.stats import lognorm
+        sim = self.sim
+        for gi, g in enumerate(self.groups):
+            ops = sim.operating_scenarios_df[sim.operating_scenarios_df.Scenario == g.scenario].reset_index(drop=True)
+            keys, cols = [], []
+            D, I = g.n_active_days, g.iterations
+            for fac in ops.Facility.unique():
+                fac_type = sim.facility_params.at[fac, "Operations"]
+                if isinstance(fac_type, pd.Series):
+                    fac_type = fac_type.iloc[0]
+                fu = sim.unit_params[sim.unit_params.Facility == fac].sort_values(by="op_order")
+                for pos, (uname, row) in enumerate(fu.iterrows()):
+                    orow = ops[(ops.Facility == fac) & (ops.Unit == row["Unit"])]
+                    if orow.empty:
+                        continue
+                    o = orow.iloc[0]
+                    keys.append(str(uname))
+                    if fac_type == "run-of-river":
+                        cols.append(np.full((D, I), float(o["Hours"])))
+                    else:
+                        off = np.random.uniform(0, 1, (D, I)) <= float(o["Prob_Not_Op"])
+                        hrs = np.clip(lognorm.rvs(o["shape"], o["location"], o["scale"], size=(D, I)), 0.0, 24.0)
+                        cols.append(np.where(off, 0.0, hrs))
+            self.cell_hours[gi] = (keys, np.stack(cols, axis=-1) if cols else np.zeros((D, I, 0)))
 
     @property
     def species_table(self):
@@ -232,12 +265,15 @@ def assemble_frames(sim, plan: RunPlan, res: engine.CellResult):
     # State_Daily rows of one cell come out of a groupby per move: moves ascending, states alphabetical (:3319-3324)
     pair_order = np.array(sorted(range(P), key=lambda p: (int(fac.pair_move[p]), str(pair_name[p]))), dtype=np.int64)
     daily_parts, sd_parts, rf_parts, uh_parts = [], [], [], []
-    logged = sim._route_flow_logged_keys
-    for g in plan.groups:
+    logged = {}     # scenario -> bool[iteration, day row]: Route_Flows / Unit_Hours already written (stryke.py:3437)
+    for gi, g in enumerate(plan.groups):
         D, I = g.n_active_days, g.iterations
         if D == 0 or I == 0:
             continue
         sl = slice(g.cell0, g.cell0 + D * I)
+        keep = np.ones((I, D), bool)          # peaking plants: cells whose units all sat idle produce no rows (:3025)
+        if gi in plan.cell_hours:
+            keep = (plan.cell_hours[gi][1].sum(axis=-1) > 0).T
         # engine order (day, iteration) -> reference order (iteration, day)
         n = res.cell_n[sl].reshape(D, I).T.astype(np.int64)
         dl = res.daily[sl].reshape(D, I, _abi.DAILY_W).transpose(1, 0, 2).astype(np.int64)
@@ -248,15 +284,16 @@ def assemble_frames(sim, plan: RunPlan, res: engine.CellResult):
         day_col = np.tile(dates[day_rows], I)
         ent, sur = dl[..., 0].ravel(), dl[..., 1].ravel()
         gate = ent > 0                                              # stryke.py:3359
-        daily_parts.append(pd.DataFrame({
+        daily = pd.DataFrame({
             "species": "{:50}".format(g.species), "scenario": "{:50}".format(g.scenario), "season": "{:50}".format(g.season),
             "iteration": it_col, "day": day_col, "flow": np.tile(flow.astype(np.float64), I),
             "pop_size": n.ravel(), "num_entrained": ent, "num_survived": sur, "num_mortality": ent - sur,
             "mortality_impingement": np.where(gate, dl[..., 2].ravel(), 0),
             "mortality_blade_strike": np.where(gate, dl[..., 3].ravel(), 0),
-            "mortality_barotrauma": np.where(gate, dl[..., 4].ravel(), 0)}))
-        cnt = sd[..., 1].reshape(I * D, P)[:, pair_order]
-        suc = sd[..., 0].reshape(I * D, P)[:, pair_order]
+            "mortality_barotrauma": np.where(gate, dl[..., 4].ravel(), 0)})
+        daily_parts.append(daily if keep.all() else daily[keep.ravel()])
+        cnt = sd[..., 1].reshape(I * D, P)[:, pair_order] * keep.reshape(I * D, 1)
+        suc = sd[..., 0].reshape(I * D, P)[:, pair_order] * keep.reshape(I * D, 1)
         ci, pi = np.nonzero(cnt)
         if ci.size:
             sd_parts.append(pd.DataFrame({
@@ -265,26 +302,31 @@ def assemble_frames(sim, plan: RunPlan, res: engine.CellResult):
                 "state": pair_name[pair_order][pi].astype(str), "successes": suc[ci, pi].astype(float),
                 "count": cnt[ci, pi].astype(float)}))
         # Route_Flows / Unit_Hours: once per (scenario, iteration, day), by the first species that gets there (:3437)
-        fresh = np.array([(g.scenario, i, int(d)) not in logged for i in range(I) for d in day_rows])
+        n_rows = len(plan.day_rows)
+        done = logged.setdefault(g.scenario, np.zeros((0, n_rows), bool))
+        if done.shape[0] < I:
+            done = np.vstack([done, np.zeros((I - done.shape[0], n_rows), bool)])
+        fresh = ~done[:I][:, day_rows]
         if fresh.any():
-            rf, uh = _route_and_hours(sim, plan, g, suc.reshape(I, D, P), pair_order, fresh.reshape(I, D), day_rows, dates)
+            hours = plan.cell_hours.get(gi)
+            rf, uh = _route_and_hours(plan, g, suc.reshape(I, D, P), pair_order, fresh, day_rows, dates, hours)
             rf_parts += rf
             uh_parts += uh
-            for i in range(I):
-                for d in day_rows:
-                    logged.add((g.scenario, i, int(d)))
+        done[:I, day_rows] = True
+        logged[g.scenario] = done
     cat = lambda parts: pd.concat(parts, ignore_index=True) if parts else None
     return {"Daily": cat(daily_parts), "State_Daily": cat(sd_parts), "Route_Flows": cat(rf_parts), "Unit_Hours": cat(uh_parts)}
 
 
-def _route_and_hours(sim, plan, g, suc, pair_order, fresh, day_rows, dates):
+def _route_and_hours(plan, g, suc, pair_order, fresh, day_rows, dates, cell_hours):
     """Route_Flows (stryke.py:3433-3462): the flows ``movement`` recorded for the successors of every node a live
-    fish stood at before the last move; Unit_Hours (stryke.py:3463-3502): hours_dict x the day's allocation."""
+    fish stood at before the last move; Unit_Hours (stryke.py:3463-3502): hours_dict x the day's allocation.
+    Cells of one day that saw live fish at the same set of nodes share their records, so the work is per (day,
+    distinct live set), not per cell."""
     fac = plan.fac
     I, D, P = suc.shape
-    moves = fac.pair_move[pair_order]
+    movable = fac.pair_move[pair_order] < fac.n_moves - 1
     nodes = fac.pair_node[pair_order]
-    last = fac.n_moves - 1
     rf_rows, uh_rows = [], []
     unit_pos = {u: j for j, u in enumerate(fac.unit_names)}
     for j, d in enumerate(day_rows):
@@ -292,27 +334,34 @@ def _route_and_hours(sim, plan, g, suc, pair_order, fresh, day_rows, dates):
         if its.size == 0:
             continue
         stay = plan.days.node_stay[d]
-        hours = plan.hours[d] or {}
         alloc = {str(u): float(plan.days.unit_Q[d, unit_pos[u]]) for u in fac.unit_names}
-        if hours:
-            names = list(hours.keys())
+        if cell_hours is not None:                 # peaking plant: every cell has its own hours
+            names, H = cell_hours[0], cell_hours[1][j][its]
+        else:
+            names = list((plan.hours[d] or {}).keys())
+            H = np.tile(np.array([float(plan.hours[d][k]) for k in names]), (its.size, 1)) if names else None
+        if names:
             uh_rows.append(pd.DataFrame({
                 "scenario": str(g.scenario), "iteration": np.repeat(its, len(names)).astype(int), "day": dates[d],
-                "route": np.tile(np.array(names, dtype=object), its.size).astype(str),
-                "hours": np.tile(np.array([float(hours[k]) for k in names]), its.size),
+                "route": np.tile(np.array(names, dtype=object), its.size).astype(str), "hours": H.ravel(),
                 "discharge_cfs": np.tile(np.array([alloc.get(str(k), np.nan) for k in names]), its.size)}))
-        live = suc[its, j, :] > 0                                   # (len(its), P): a live fish stood at this pair
-        for r, i in enumerate(its):
+        live = (suc[its, j, :] > 0) & movable[None, :]              # a live fish stood at this pair before a move
+        masks, inverse = np.unique(live, axis=0, return_inverse=True)
+        inverse = np.asarray(inverse).ravel()
+        for m, mask in enumerate(masks):
             rec = {}
-            for p in np.nonzero(live[r] & (moves < last))[0]:
+            for p in np.nonzero(mask)[0]:
                 v = int(nodes[p])
                 if stay[v]:
                     continue
                 lo, hi = fac.edge_off[v], fac.edge_off[v + 1]
                 for name, q in zip(fac.succ_order[v], plan.days.edge_flow[d, lo:hi]):
                     rec[name] = float(q)
-            if rec:
-                rf_rows.append(pd.DataFrame({"scenario": str(g.scenario), "iteration": int(i), "day": dates[d],
-                                             "route": np.array(list(rec.keys()), dtype=object).astype(str),
-                                             "discharge_cfs": list(rec.values())}))
+            if not rec:
+                continue
+            who = its[inverse == m]
+            routes = np.array(list(rec.keys()), dtype=object).astype(str)
+            rf_rows.append(pd.DataFrame({"scenario": str(g.scenario), "iteration": np.repeat(who, len(routes)).astype(int),
+                                         "day": dates[d], "route": np.tile(routes, who.size),
+                                         "discharge_cfs": np.tile(np.array(list(rec.values())), who.size)}))
     return rf_rows, uh_rows

@@ -500,8 +500,16 @@ class simulation:
 
     def population_sim(self, output_units, spc_df, curr_Q):
         """Daily entrainment count for one cell (stryke.py:2505-2618), drawn on the device."""
-        fake = simulation.__new__(simulation)
-        params = tables.species_row(self if hasattr(self, "_fish_family") else fake, spc_df.assign(occur_prob=1.0))
+        col = lambda c: spc_df.iat[0, spc_df.columns.get_loc(c)]
+        params = np.zeros(_abi.SPECIES_W)
+        params[2], params[6] = 1.0, 0.10          # a dummy length distribution: only the count kernel's output is used
+        params[12] = _abi.ENT.get(col("dist"), _abi.ENT["Weibull"])
+        params[13], params[14], params[15] = float(col("shape")), float(col("location")), float(col("scale"))
+        try:
+            params[16] = float(spc_df.max_ent_rate.values[0])
+        except Exception:
+            params[16] = np.nan
+        params[17] = 1.0
         fac = _single_node_tables()
         days = tables.DayTables(np.array([float(curr_Q)]), np.zeros((1, 0)), np.ones((1, 1), np.uint8),
                                 np.zeros((1, 0, _abi.UNIT_COEF_W)), np.zeros((1, 0)), np.zeros((1, 0)))

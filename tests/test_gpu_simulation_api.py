@@ -124,3 +124,24 @@ def test_population_cap_raises_like_the_reference(tmp_path, monkeypatch):
     monkeypatch.setenv("STRYKE_MAX_DAILY_FISH", "100000")
     with contextlib.redirect_stdout(io.StringIO()), pytest.raises(ValueError, match="exceeds STRYKE_MAX_DAILY_FISH"):
         sim2.run()
+
+
+def test_peaking_plant_hours_gate_and_unit_hours(tmp_path):
+    """Peaking / pumped-storage operations (stryke.py:2405-2431): per-cell not-operating coin + lognormal hours; cells
+    whose units all sat idle write no Daily row; Unit_Hours carries the per-cell hours."""
+    prj = fixtures.peaking_facility(n_fish=500, iterations=40, days=6)
+    sim = fresh_sim(prj, tmp_path, "peaking")
+    np.random.seed(11)
+    with contextlib.redirect_stdout(io.StringIO()):
+        sim.run()
+    with open_store(sim.hdf_path, mode="r") as st:
+        daily, uh = st["Daily"], st["Unit_Hours"]
+    n_cells = 40 * 6
+    p_idle = 0.35 * 0.55 * 0.75            # all three units not operating
+    assert len(uh) == n_cells * 3 and uh["hours"].between(0, 24).all()
+    tot = uh.groupby(["iteration", "day"])["hours"].sum()
+    assert len(daily) == int((tot > 0).sum()) and len(daily) < n_cells
+    assert abs((tot == 0).mean() - p_idle) < 4 * np.sqrt(p_idle * (1 - p_idle) / n_cells)
+    assert (daily["pop_size"] == 500).all()
+    idle_u1 = (uh[uh.route == "U1"]["hours"] == 0).mean()
+    assert abs(idle_u1 - 0.35) < 0.13
