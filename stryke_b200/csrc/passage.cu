@@ -167,8 +167,9 @@ struct FishRng {
 };
 template <typename Real> __device__ __forceinline__ Real u_co(uint32_t x);   // [0,1)
 template <typename Real> __device__ __forceinline__ Real u_oc(uint32_t x);   // (0,1]
-template <> __device__ __forceinline__ float u_co<float>(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }
-template <> __device__ __forceinline__ float u_oc<float>(uint32_t x) { return (float)((x >> 8) + 1u) * 5.9604644775390625e-8f; }
+// 23 random mantissa bits under exponent 0: v in [1, 2); one ALU op + one FADD, no integer->float conversion (XU pipe)
+template <> __device__ __forceinline__ float u_co<float>(uint32_t x) { return __uint_as_float((x >> 9) | 0x3f800000u) - 1.0f; }
+template <> __device__ __forceinline__ float u_oc<float>(uint32_t x) { return 2.0f - __uint_as_float((x >> 9) | 0x3f800000u); }
 template <> __device__ __forceinline__ double u_co<double>(uint32_t x) { return (double)x * 2.3283064365386963e-10; }
 template <> __device__ __forceinline__ double u_oc<double>(uint32_t x) { return ((double)x + 1.0) * 2.3283064365386963e-10; }
 
@@ -516,12 +517,8 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
       const NodeRec nd = s_nodes[loc];
       const bool prev_alive = alive;
       float rate32 = 0.f;
-      int slot = mv.slot_base;
-      // words are laid out in consumption order: rR, depth, cause, dice, route
-      const int s_rr = slot;   slot += (mv.need & NEED_RR) ? 1 : 0;
-      const int s_dep = slot;  slot += (mv.need & NEED_DEPTH) ? 1 : 0;
-      const int s_cau = slot;  slot += (mv.need & NEED_CAUSE) ? 1 : 0;
-      const int s_dice = slot;
+      // a level with per-node draws owns one Philox block: rR, depth, cause, dice at fixed positions 0..3
+      const int s_rr = mv.slot_base, s_dep = mv.slot_base + 1, s_cau = mv.slot_base + 2, s_dice = mv.slot_base + 3;
       const int s_rt = mv.slot_route;
       uint32_t w_rr = 0, w_dep = 0, w_cau = 0;
       if (!INJECT) {   // warp-uniform draws for this move (refill points are identical for every lane)
@@ -718,28 +715,26 @@ __global__ void philox_kernel(int64_t n, const uint32_t* __restrict__ ctr, const
   Philox::block(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1], w);
   out[4 * i] = w[0]; out[4 * i + 1] = w[1]; out[4 * i + 2] = w[2]; out[4 * i + 3] = w[3];
 }
-// Issue-rate calibration: per loop iteration exactly 8 independent FFMA (fma pipe) + 8 independent 3-input LOP3 (alu
-// pipe) per thread, written in PTX so the count is exact; a warp scheduler can issue one of them per cycle when both
-// half-rate pipes are kept busy, which is the ceiling the passage kernel is measured against.
-constexpr int CAL_ITERS = 4096, CAL_OPS = 16;
+// Issue-rate calibration: 16 independent FFMA chains per thread, 128 FFMA per loop iteration (PTX, so the count is
+// exact).  FFMA issues at one warp instruction per scheduler per cycle (both FP32 datapaths of an SM sub-partition),
+// so the achieved FFMA lane-ops/s is the measured instruction-issue ceiling the passage kernel is compared with.
+constexpr int CAL_ITERS = 1024, CAL_OPS = 128;
 __global__ void __launch_bounds__(256) calibrate_kernel(uint32_t* out, uint32_t seed) {
-  float x[8];
-  uint32_t b[8];
+  float x[16];
   const float m = 1.0f + 1e-7f * (float)(seed & 7), c = 1e-9f * (float)(threadIdx.x & 3);
-  const uint32_t k1 = seed * 2654435761u, k2 = ~seed | 0x01010101u;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { x[i] = (float)(threadIdx.x + i); b[i] = seed ^ (blockIdx.x * 8 + i); }
+  for (int i = 0; i < 16; ++i) x[i] = (float)(threadIdx.x + i);
 #pragma unroll 1
   for (int it = 0; it < CAL_ITERS; ++it) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(x[i]) : "f"(m), "f"(c));
-      asm volatile("lop3.b32 %0, %0, %1, %2, 0x6a;" : "+r"(b[i]) : "r"(k1), "r"(k2));   // b ^ (k1 & k2)
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(x[i]) : "f"(m), "f"(c));
     }
   }
   uint32_t s = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s += __float_as_uint(x[i]) ^ b[i];
+  for (int i = 0; i < 16; ++i) s += __float_as_uint(x[i]);
   if (s == 0x12345678u) out[0] = s;   // never true in practice; keeps the chains live
 }
 
@@ -898,7 +893,11 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
   for (int e = 0; e < f->n_edges; ++e) edst[e] = (uint8_t)f->edge_dst[e];
   for (int p = 0; p < f->n_pairs; ++p) pnode[p] = (uint8_t)f->pair_node[p];
   std::vector<MoveRec> moves(f->n_moves);
-  int slot = 2;   // words 0,1: the length draw
+  // Philox word layout (shared by both passage kernels): block 0 words 0,1 = length draw.  Every level with per-node
+  // draws owns a fresh block (rR, depth, cause, dice at positions 0..3).  A routing word takes a free position of the
+  // block that is current at that point of the move loop, else opens a new block.
+  int next_block = 1, cur_block = 0;
+  std::vector<int> free_pos = {2, 3};
   for (int k = 0; k < f->n_moves; ++k) {
     MoveRec& m = moves[k];
     m.lex = f->move_lex_rank[k];
@@ -917,13 +916,22 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
       if (k < f->n_moves - 1 && r.deg > 1) need |= NEED_ROUTE;
     }
     m.need = need;
-    // the (<= 4) per-node words of a move never straddle a Philox block; the routing word follows
-    const int n_a = __builtin_popcount(need & (NEED_RR | NEED_DEPTH | NEED_CAUSE | NEED_DICE));
-    if ((slot & 3) + n_a > 4) slot = (slot + 3) & ~3;
-    m.slot_base = (uint16_t)slot;
-    slot += n_a;
-    m.slot_route = (uint16_t)slot;
-    slot += (need & NEED_ROUTE) ? 1 : 0;
+    m.slot_base = 0;
+    m.slot_route = 0;
+    if (need & (NEED_RR | NEED_DEPTH | NEED_CAUSE | NEED_DICE)) {
+      cur_block = next_block++;
+      m.slot_base = (uint16_t)(4 * cur_block);
+      free_pos.clear();
+      if (!(need & NEED_RR)) free_pos.push_back(0);
+      if (!(need & NEED_DEPTH)) free_pos.push_back(1);
+      if (!(need & NEED_CAUSE)) free_pos.push_back(2);
+      if (!(need & NEED_DICE)) free_pos.push_back(3);
+    }
+    if (need & NEED_ROUTE) {
+      if (free_pos.empty()) { cur_block = next_block++; free_pos = {0, 1, 2, 3}; }
+      m.slot_route = (uint16_t)(4 * cur_block + free_pos.front());
+      free_pos.erase(free_pos.begin());
+    }
     int md = 0;
     for (int p = m.level_begin; p < m.level_end; ++p) md = std::max(md, (int)nodes[pnode[p]].deg);
     m.max_deg = (uint8_t)md;

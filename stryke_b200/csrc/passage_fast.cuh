@@ -207,18 +207,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) passage_fast_kernel(const KParams
       const int kind = pk & 7;
       const bool prev_alive = alive;
       float rate = alive ? __uint_as_float(nd.x) : 0.f;
-      int slot = mv.slot_base;
-      if (mv.need & (NEED_CAUSE | NEED_DICE)) {
-        if ((slot >> 2) != cur_b) {                      // refill site A (uniform)
-          cur_b = slot >> 2;
-          Philox::block((uint32_t)fish, cid_lo, cid_hi, (uint32_t)cur_b, P.seed_lo, P.seed_hi, w);
-        }
+      if (mv.need & (NEED_CAUSE | NEED_DICE)) {          // refill site A (uniform): this level owns a fresh block,
+        cur_b = mv.slot_base >> 2;                       // rR, depth, cause, dice at fixed positions 0..3
+        Philox::block((uint32_t)fish, cid_lo, cid_hi, (uint32_t)cur_b, P.seed_lo, P.seed_hi, w);
       }
       if (mv.need & NEED_CAUSE) {                        // this level has turbine nodes (uniform)
-        float u_rr = 0.f, u_dep = 0.f;
-        if (mv.need & NEED_RR) { u_rr = u_co<float>(word(slot & 3)); ++slot; }
-        if (BARO) { u_dep = u_co<float>(word(slot & 3)); ++slot; }
-        const float u_cau = u_co<float>(word(slot & 3)); ++slot;
+        const float u_rr = u_co<float>(w[0]);
+        const float u_dep = BARO ? u_co<float>(w[1]) : 0.f;
+        const float u_cau = u_co<float>(w[2]);
         const bool turb = alive && kind != STRYKE_KIND_APRIORI;
         const int unit = turb ? (int)((pk >> 4) & 0x7f) : 0;
         const float4 us = s_ustatic[unit];
@@ -244,7 +240,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) passage_fast_kernel(const KParams
         cz += turb ? code : 0u;
       }
       bool surv;
-      if (mv.need & NEED_DICE) surv = alive && (u_oc<float>(word(slot & 3)) <= rate);
+      if (mv.need & NEED_DICE) surv = alive && (u_oc<float>(w[3]) <= rate);
       else surv = alive && rate >= 1.0f;
 
       // ---- (6) State_Daily: lane p owns pair p ---------------------------------------------------------------------
