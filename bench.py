@@ -126,6 +126,7 @@ def main():
     ap.add_argument("--precision", type=int, default=32)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--kernel-variant", type=int, default=0, help="0 auto, 1 general, 2 generic throughput, 3 NVRTC-specialised")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -179,7 +180,8 @@ def main():
     cell_id = plan_h.cell_id + np.uint64(rank) * np.uint64(1 << 40)
     species = plan_h.species_table
     plan = engine.Plan(plan_h.fac, plan_h.days, species, plan_h.cell_day, plan_h.cell_species, cell_id,
-                       device=local_rank, precision=args.precision, seed=0x5EED, max_daily_fish=2_000_000_000)
+                       device=local_rank, precision=args.precision, seed=0x5EED, max_daily_fish=2_000_000_000,
+                       kernel_variant=args.kernel_variant)
     t_n, t_daily, t_sd = plan.allocate()
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
     stream = torch.cuda.current_stream()
@@ -268,13 +270,14 @@ def main():
                pinned(np.zeros((plan.n_cells, plan.n_pairs, 2), np.uint32)))
         dev = f"cuda:{local_rank}"
         engine.run_cells(plan_h.fac, plan_h.days, species, h_day, h_spc, h_id, device=local_rank, precision=args.precision,
-                         seed=1, max_daily_fish=2_000_000_000, out=out)
+                         seed=1, max_daily_fish=2_000_000_000, out=out, kernel_variant=args.kernel_variant)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
             r = engine.run_cells(plan_h.fac, plan_h.days, species, h_day, h_spc, h_id, device=local_rank,
-                                 precision=args.precision, seed=3000 + i, max_daily_fish=2_000_000_000, out=out)
+                                 precision=args.precision, seed=3000 + i, max_daily_fish=2_000_000_000, out=out,
+                                 kernel_variant=args.kernel_variant)
             if world > 1:   # the public multi-GPU call ends with the tally all-reduce
                 td = torch.from_numpy(r.daily.view(np.int32)).to(dev, non_blocking=True)
                 ts = torch.from_numpy(r.state_daily.view(np.int32)).to(dev, non_blocking=True)
@@ -302,7 +305,7 @@ def main():
                 "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic",
                 "config": {"workload": workload_desc, "rng": "Philox4x32-10 keyed (seed; cell id, fish, slot)",
                            "l2": "256 MiB flush write between timed steps; kernel inputs are < 64 KiB of tables",
-                           "fish_passages_per_step": fish_all, "cells_per_gpu": plan.n_cells,
+                           "fish_passages_per_step": fish_all, "cells_per_gpu": plan.n_cells, "kernel": plan.kernel(),
                            "collective": "NCCL all_reduce(sum) of Daily + State_Daily tallies per step" if world > 1 else "none"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": sampler.summary()}

@@ -138,7 +138,9 @@ typedef struct StrykeOpts {
   int32_t  blocks_per_sm;       /* 0 = default                                                             */
   const StrykeInjected* injected;  /* NULL = native Philox                                                 */
   const StrykeTrace*    trace;     /* NULL = tallies only (needs fish_off: injected mode or fixed counts)   */
-  int32_t  kernel_variant;      /* 0 = auto (fp32 + native RNG + no trace -> passage_fast_kernel), 1 = always the general passage_kernel */
+  int32_t  kernel_variant;      /* 0 = auto; 1 = general passage_kernel; 2 = throughput kernel, generic tables (ahead-of-time);
+                                   3 = throughput kernel specialised for the facility with NVRTC (error if unavailable).
+                                   auto: fp32 + native RNG + no trace -> throughput kernel, specialised when the run is large */
 } StrykeOpts;
 
 /* Host-side result buffers, caller-allocated. */
@@ -166,6 +168,9 @@ int stryke_b200_plan_create(const StrykeFacility* fac, const StrykeDayTables* da
                             const StrykeCells* cells, const StrykeOpts* opts, StrykePlan** plan);
 int stryke_b200_plan_launch(StrykePlan* plan, int32_t* d_cell_n, uint32_t* d_daily, uint32_t* d_state_daily,
                             void* stream);
+const char* stryke_b200_plan_kernel(const StrykePlan* plan);      /* which passage kernel the plan will launch */
+int stryke_b200_set_source_dir(const char* dir);                 /* directory holding passage_fast.cuh / passage_common.cuh (run-time specialisation) */
+int stryke_b200_jit_selftest(void);                              /* compiles a specialised kernel with NVRTC; needs no GPU */
 int stryke_b200_plan_set_seed(StrykePlan* plan, uint64_t seed);   /* Philox key of the next launches */
 int stryke_b200_plan_status(StrykePlan* plan, void* stream, int64_t* n_fish_total);   /* syncs the stream; reports STRYKE_E_MAX_FISH etc. */
 int stryke_b200_plan_fetch_trace(StrykePlan* plan, const StrykeTrace* host_trace, void* stream);

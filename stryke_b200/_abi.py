@@ -89,6 +89,11 @@ def lib():
     L.stryke_b200_plan_create.argtypes = [P(Facility), P(DayTables), P(SpeciesTable), P(Cells), P(Opts), P(_p)]
     L.stryke_b200_plan_launch.argtypes = [_p, _p, _p, _p, _p]
     L.stryke_b200_plan_set_seed.argtypes = [_p, C.c_uint64]
+    L.stryke_b200_plan_kernel.argtypes = [_p]
+    L.stryke_b200_plan_kernel.restype = C.c_char_p
+    L.stryke_b200_set_source_dir.argtypes = [C.c_char_p]
+    L.stryke_b200_set_source_dir.restype = C.c_int
+    L.stryke_b200_jit_selftest.restype = C.c_int
     L.stryke_b200_plan_status.argtypes = [_p, _p, P(C.c_int64)]
     L.stryke_b200_plan_fetch_trace.argtypes = [_p, P(Trace), _p]
     L.stryke_b200_plan_destroy.argtypes = [_p]
@@ -99,12 +104,13 @@ def lib():
     for name in ("run", "plan_create", "plan_launch", "plan_set_seed", "plan_status", "plan_fetch_trace", "plan_destroy",
                  "strike_survival", "baro_survival", "philox", "calibrate_issue"):
         getattr(L, "stryke_b200_" + name).restype = C.c_int
+    L.stryke_b200_set_source_dir(os.path.join(_HERE, "csrc").encode())
     _lib = L
     return L
 
 
 EXPORTS = ["stryke_b200_last_error", "stryke_b200_abi_version", "stryke_b200_device_count", "stryke_b200_launch_count",
-           "stryke_b200_run", "stryke_b200_plan_create", "stryke_b200_plan_launch", "stryke_b200_plan_set_seed", "stryke_b200_plan_status",
+           "stryke_b200_run", "stryke_b200_plan_create", "stryke_b200_plan_launch", "stryke_b200_plan_kernel", "stryke_b200_set_source_dir", "stryke_b200_jit_selftest", "stryke_b200_plan_set_seed", "stryke_b200_plan_status",
            "stryke_b200_plan_fetch_trace", "stryke_b200_plan_destroy", "stryke_b200_strike_survival",
            "stryke_b200_baro_survival", "stryke_b200_philox", "stryke_b200_calibrate_issue"]
 

@@ -29,66 +29,18 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
+#include <fstream>
+#include <map>
+#include <mutex>
+#include <sstream>
+
 #include "../../include/stryke_b200.h"
-#include "philox.cuh"
+#include "passage_common.cuh"
+#include "passage_fast.cuh"
 
 namespace stryke {
-
-// ------------------------------------------------------------------------------------------------------------------
-// device-side table records
-// ------------------------------------------------------------------------------------------------------------------
-struct __align__(4) NodeRec {   // 12 bytes
-  float apriori32;              // np.float32(surv_dict[node]) (stryke.py:1405, :1575)
-  int16_t edge_off;
-  uint8_t deg;
-  uint8_t kind;
-  int8_t unit;
-  uint8_t hasU;
-  uint16_t pad;
-};
-
-enum : uint8_t { NEED_DICE = 1, NEED_RR = 2, NEED_DEPTH = 4, NEED_CAUSE = 8, NEED_ROUTE = 16 };
-
-struct __align__(4) MoveRec {   // 12 bytes
-  uint8_t lex;                  // rank of "state_k" in lexicographic column order (stryke.py:3272)
-  uint8_t need;                 // NEED_* : which draws this move can consume (static facility property)
-  uint16_t slot_base;           // first Philox word slot of this move's rR / depth / cause / dice words (one block)
-  uint16_t level_begin, level_end;  // reachable pairs of this move in pair_node[]
-  uint16_t slot_route;          // Philox word slot of the routing draw
-  uint8_t max_deg;              // largest out-degree among the nodes of this level
-  uint8_t pad;
-};
-
-struct InjectedDev {
-  const int64_t* fish_off;
-  const double *presence, *count_draw, *length_z, *dice, *rR, *depth, *cause, *route;
-  const double *ghost_rR, *ghost_depth, *ghost_cause;
-};
-struct TraceDev {
-  float* length_ft; double* length_ft64; uint8_t* state; float* rate; uint8_t* survival; double* strike; double* baro;
-};
-
-struct KParams {
-  const NodeRec* nodes; const uint8_t* edge_dst; const MoveRec* moves; const uint8_t* pair_node;
-  const double* unit_static;
-  int n_nodes, n_units, n_moves, n_edges, n_pairs, start_node, barotrauma;
-  const double* edge_cdf; const uint8_t* node_stay; const double* unit_coef;
-  const double* species; int n_species;
-  const int32_t* cell_day; const int32_t* cell_species; const uint64_t* cell_id;
-  const int32_t* cell_n; const int64_t* tile_off; const int64_t* fish_off; int64_t n_cells;
-  uint32_t* daily; uint32_t* state_daily;
-  uint32_t seed_lo, seed_hi;
-  int64_t n_fish_total;
-  InjectedDev inj; TraceDev trace;
-};
-
-constexpr double P_ATM = 101325.0;    // scipy.constants.atm (stryke.py:1472)
-constexpr double G_SI = 9.80665;      // scipy.constants.g   (stryke.py:1471)
-constexpr double RHO = 998.2;         // stryke.py:1473
-constexpr double FT2M = 0.3048;       // stryke.py:1497
-constexpr double CM2FT = 0.0328084;   // stryke.py:3077
-constexpr int SPW = 12;               // per-fish species words staged in shared memory
-constexpr int USW = 6;                // per-unit static words staged: rack, intake_vel, fb_depth, tail_depth, c0, c1
 
 // fp64: the reference's operation order with every rounding kept (no FMA contraction)
 __device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
@@ -119,14 +71,6 @@ __device__ __forceinline__ double baro_surv64(double depth_ft, double tail_ft, d
   const double e = exp(add_(b0, mul_(b1, log(div_(p1, p2)))));
   return sub_(1.0, div_(e, add_(1.0, e)));
 }
-// single-MUFU approximations (no denormal / range fix-up code): arguments are known to be normal and in range
-__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float cos_2pi(float turns) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(turns * 6.283185307f)); return y; }
-
 // ---- fp32 throughput flavour: folded per-(day, unit) coefficients, MUFU intrinsics ---------------------------------
 //   Kaplan: tan a = fa / rR  =>  cos a = rR * rsqrt(rR^2 + fa^2), sin a = fa * rsqrt(rR^2 + fa^2)
 //           p = fc * L * rsqrt(rR^2 + fa^2) * (rR * fb + fa / (pi rR))
@@ -165,18 +109,6 @@ struct FishRng {
     return (s & 2) ? ((s & 1) ? w[3] : w[2]) : ((s & 1) ? w[1] : w[0]);
   }
 };
-template <typename Real> __device__ __forceinline__ Real u_co(uint32_t x);   // [0,1)
-template <typename Real> __device__ __forceinline__ Real u_oc(uint32_t x);   // (0,1]
-// 23 random mantissa bits under exponent 0: v in [1, 2); one ALU op + one FADD, no integer->float conversion (XU pipe)
-template <> __device__ __forceinline__ float u_co<float>(uint32_t x) { return __uint_as_float((x >> 9) | 0x3f800000u) - 1.0f; }
-template <> __device__ __forceinline__ float u_oc<float>(uint32_t x) { return 2.0f - __uint_as_float((x >> 9) | 0x3f800000u); }
-template <> __device__ __forceinline__ double u_co<double>(uint32_t x) { return (double)x * 2.3283064365386963e-10; }
-template <> __device__ __forceinline__ double u_oc<double>(uint32_t x) { return ((double)x + 1.0) * 2.3283064365386963e-10; }
-
-__device__ __forceinline__ float std_normal(float u1_oc, float u2_co) {   // Box-Muller: MUFU lg2, sqrt, cos
-  return sqrt_approx(-1.3862943611f * lg2_approx(u1_oc)) * cos_2pi(u2_co);   // -2 ln u = -2 ln2 lg2 u
-}
-__device__ __forceinline__ float exp_approx(float x) { return ex2_approx(x * 1.44269504f); }
 __device__ __forceinline__ double std_normal(double u1_oc, double u2_co) {
   return sqrt(-2.0 * log(u1_oc)) * cospi(2.0 * u2_co);
 }
@@ -333,7 +265,6 @@ __global__ void __launch_bounds__(SCAN_T) scan_final(const int32_t* __restrict__
 // ------------------------------------------------------------------------------------------------------------------
 // (2)-(6) the passage kernel
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int BLOCK = 256, WARPS = BLOCK / 32;
 
 struct SmemLayout {   // byte offsets into dynamic shared memory (all 16-byte aligned)
   int nodes, edge_dst, moves, pair_node, ustatic, species, warp0, warp_stride, cdf, stay, ucoef, total;
@@ -671,10 +602,6 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
   if (cur_cell >= 0) flush(cur_cell);
 }
 
-}  // namespace stryke
-#include "passage_fast.cuh"
-namespace stryke {
-
 // ------------------------------------------------------------------------------------------------------------------
 // small utility kernels: per-fish probability functions, Philox KAT, issue-rate calibration
 // ------------------------------------------------------------------------------------------------------------------
@@ -807,9 +734,17 @@ struct StrykePlan {
   size_t fast_smem_bytes = 0;
   int fast_stride = 1;
   bool use_fast = false;
+  cudaKernel_t jit_kernel = nullptr;
+  std::string kernel_name = "passage_kernel (general)";
   int64_t trace_fish = 0;
   bool has_trace = false, trace_probs = false;
 };
+
+namespace jit {
+static std::string generate(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int stride, int pr, bool baro);
+static const std::vector<char>* compile(const std::string& src, std::string* err);
+static int load(int device, const std::string& src, const std::vector<char>& bin, cudaKernel_t* kern, std::string* err);
+}  // namespace jit
 
 static int validate(const StrykeFacility* f, const StrykeDayTables* d, const StrykeSpeciesTable* s,
                     const StrykeCells* c, const StrykeOpts* o) {
@@ -1059,7 +994,33 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
       pl->fast.moves[k] = m;
     }
     for (int p = 0; p < f->n_pairs; ++p) pl->fast.pair_node[p] = pnode[p];
+    pl->kernel_name = "passage_fast_kernel (generic tables, ahead-of-time)";
+    // ---- specialise for this facility when the run is large enough to amortise a ~1-3 s compile ---------------------
+    double fish_hint = 0.0;
+    for (int64_t i = 0; i < c->n_cells; ++i) {
+      const double* sp = s->params + (size_t)c->cell_species[i] * STRYKE_SPECIES_W;
+      fish_hint += (int)sp[12] == STRYKE_ENT_FIXED ? sp[18] : 50.0;
+    }
+    const char* env = getenv("STRYKE_B200_JIT");
+    const bool want = o->kernel_variant == 3 || (o->kernel_variant == 0 && !(env && env[0] == '0') &&
+                                                 ((env && env[0] == '1') || fish_hint >= 2.0e7));
+    if (want) {
+      std::vector<MoveRec> mv(pl->fast.moves, pl->fast.moves + f->n_moves);
+      const std::string src = jit::generate(mv, pnode, pl->fast_stride, pl->pr, f->barotrauma != 0);
+      std::string err;
+      const std::vector<char>* bin = jit::compile(src, &err);
+      cudaKernel_t k = nullptr;
+      if (bin && jit::load(o->device, src, *bin, &k, &err) == 0) {
+        pl->jit_kernel = k;
+        pl->kernel_name = "passage_spec (tables specialised with NVRTC)";
+      } else if (o->kernel_variant == 3) {
+        return fail(STRYKE_E_CUDA, "kernel specialisation failed: " + err);
+      }
+    }
+  } else {
+    pl->kernel_name = "passage_kernel (general)";
   }
+  if (o->kernel_variant == 3 && !pl->jit_kernel) return fail(STRYKE_E_ARG, "kernel_variant 3 needs fp32, native RNG, no trace");
   CK(cudaStreamSynchronize(0));      // uploads done: the caller may release its host tables
   guard.p = nullptr;
   *out = pl;
@@ -1115,10 +1076,149 @@ static int launch_fast_minb(StrykePlan* pl, cudaStream_t st) {
     default: return b ? launch_fast<4, true, MINB>(pl, st) : launch_fast<4, false, MINB>(pl, st);
   }
 }
+// ------------------------------------------------------------------------------------------------------------------
+// Run-time specialisation of the throughput kernel (NVRTC).  The hand-written body passage_fast_body<> is compiled
+// once per facility shape with a table provider whose per-move records, pair list and row stride are compile-time
+// constants generated from the plan: the move loop unrolls, every "does this level need a draw" test, Philox slot and
+// pair index folds to an immediate.  libnvrtc is loaded lazily with dlopen; when it is not available the plan simply
+// keeps the ahead-of-time generic instantiation (same results, tested).
+// ------------------------------------------------------------------------------------------------------------------
+namespace jit {
+typedef struct _nvrtcProgram* nvrtcProgram;
+struct Api {
+  int (*create)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  int (*compile)(nvrtcProgram, int, const char* const*) = nullptr;
+  int (*log_size)(nvrtcProgram, size_t*) = nullptr;
+  int (*log)(nvrtcProgram, char*) = nullptr;
+  int (*cubin_size)(nvrtcProgram, size_t*) = nullptr;
+  int (*cubin)(nvrtcProgram, char*) = nullptr;
+  int (*destroy)(nvrtcProgram*) = nullptr;
+  bool ok = false;
+};
+static Api& api() {
+  static Api a = [] {
+    Api x;
+    void* h = nullptr;
+    for (const char* name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"}) {
+      h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (h) break;
+    }
+    if (!h) return x;
+    x.create = (decltype(x.create))dlsym(h, "nvrtcCreateProgram");
+    x.compile = (decltype(x.compile))dlsym(h, "nvrtcCompileProgram");
+    x.log_size = (decltype(x.log_size))dlsym(h, "nvrtcGetProgramLogSize");
+    x.log = (decltype(x.log))dlsym(h, "nvrtcGetProgramLog");
+    x.cubin_size = (decltype(x.cubin_size))dlsym(h, "nvrtcGetCUBINSize");
+    x.cubin = (decltype(x.cubin))dlsym(h, "nvrtcGetCUBIN");
+    x.destroy = (decltype(x.destroy))dlsym(h, "nvrtcDestroyProgram");
+    x.ok = x.create && x.compile && x.log_size && x.log && x.cubin_size && x.cubin && x.destroy;
+    return x;
+  }();
+  return a;
+}
+static std::string g_source_dir;
+static std::mutex g_mu;
+static std::map<std::string, std::vector<char>> g_cubins;        // generated source -> cubin
+struct Loaded { cudaLibrary_t lib; cudaKernel_t kern; };
+static std::map<std::pair<int, std::string>, Loaded> g_loaded;   // (device, source) -> loaded kernel
+
+static bool read_file(const std::string& path, std::string* out) {
+  std::ifstream f(path);
+  if (!f) return false;
+  std::stringstream ss;
+  ss << f.rdbuf();
+  *out = ss.str();
+  return true;
+}
+
+// The table provider + kernel entry for one plan.
+static std::string generate(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int stride, int pr, bool baro) {
+  std::ostringstream o;
+  const int M = (int)moves.size(), P = (int)pairs.size();
+  o << "#define STRYKE_NVRTC 1\n#include \"passage_fast.cuh\"\nnamespace stryke {\nstruct SpecJit {\n"
+    << "  static constexpr bool kStatic = true;\n"
+    << "  static constexpr int M = " << M << ", STRIDE = " << stride << ", UNROLL_K = " << (M <= 32 ? M : 1) << ", UNROLL_P = 8;\n"
+    << "  static __device__ constexpr MoveRec move(const FastTables&, int k) {\n    constexpr MoveRec T[" << M << "] = {";
+  for (int k = 0; k < M; ++k) {
+    const MoveRec& m = moves[k];
+    o << (k ? ", " : "") << "{" << (int)m.lex << ", " << (int)m.need << ", " << m.slot_base << ", " << m.level_begin << ", "
+      << m.level_end << ", " << m.slot_route << ", " << (int)m.max_deg << ", " << (int)m.pad << "}";
+  }
+  o << "};\n    return T[k];\n  }\n  static __device__ constexpr int pair_node(const FastTables&, int p) {\n    constexpr uint8_t N[" << P << "] = {";
+  for (int p = 0; p < P; ++p) o << (p ? ", " : "") << (int)pairs[p];
+  o << "};\n    return (int)N[p];\n  }\n};\n}  // namespace stryke\n"
+    << "extern \"C\" __global__ void __launch_bounds__(256, 4) passage_spec(const stryke::KParams P, const stryke::FastTables FT,\n"
+    << "    const uint2* __restrict__ g_nodes, const int stride, const int n_species_staged) {\n"
+    << "  stryke::passage_fast_body<stryke::SpecJit, " << pr << ", " << (baro ? "true" : "false") << ">(P, FT, g_nodes, stride, n_species_staged);\n}\n";
+  return o.str();
+}
+
+// nullptr + message on failure
+static const std::vector<char>* compile(const std::string& src, std::string* err) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  auto it = g_cubins.find(src);
+  if (it != g_cubins.end()) return &it->second;
+  Api& a = api();
+  if (!a.ok) { *err = "libnvrtc not available"; return nullptr; }
+  std::string fast, common;
+  if (g_source_dir.empty() || !read_file(g_source_dir + "/passage_fast.cuh", &fast) || !read_file(g_source_dir + "/passage_common.cuh", &common)) {
+    *err = "kernel sources not found (stryke_b200_set_source_dir)";
+    return nullptr;
+  }
+  const char* headers[2] = {fast.c_str(), common.c_str()};
+  const char* names[2] = {"passage_fast.cuh", "passage_common.cuh"};
+  nvrtcProgram prog = nullptr;
+  if (a.create(&prog, src.c_str(), "passage_spec.cu", 2, headers, names) != 0) { *err = "nvrtcCreateProgram failed"; return nullptr; }
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+  const int rc = a.compile(prog, 3, opts);
+  if (rc != 0) {
+    size_t n = 0;
+    a.log_size(prog, &n);
+    std::string log(n, '\0');
+    if (n) a.log(prog, &log[0]);
+    a.destroy(&prog);
+    *err = "NVRTC compile failed: " + log.substr(0, 2000);
+    return nullptr;
+  }
+  size_t n = 0;
+  a.cubin_size(prog, &n);
+  std::vector<char> bin(n);
+  a.cubin(prog, bin.data());
+  a.destroy(&prog);
+  return &(g_cubins[src] = std::move(bin));
+}
+
+static int load(int device, const std::string& src, const std::vector<char>& bin, cudaKernel_t* kern, std::string* err) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  auto key = std::make_pair(device, src);
+  auto it = g_loaded.find(key);
+  if (it == g_loaded.end()) {
+    Loaded l{};
+    cudaError_t e = cudaLibraryLoadData(&l.lib, bin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&l.kern, l.lib, "passage_spec");
+    if (e != cudaSuccess) { *err = std::string("loading the specialised kernel failed: ") + cudaGetErrorString(e); cudaGetLastError(); return 1; }
+    it = g_loaded.emplace(key, l).first;
+  }
+  *kern = it->second.kern;
+  return 0;
+}
+}  // namespace jit
+
+static int launch_jit(StrykePlan* pl, cudaStream_t st) {
+  const void* fn = (const void*)pl->jit_kernel;
+  if (pl->fast_smem_bytes > 48 * 1024)
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem_bytes));
+  int bps = pl->blocks_per_sm;
+  if (bps <= 0) bps = std::max(1, std::min(4, (int)((200 * 1024) / std::max<size_t>(pl->fast_smem_bytes, 1))));
+  const uint2* nodes = pl->fast_nodes.as<uint2>();
+  void* args[] = {(void*)&pl->K, (void*)&pl->fast, (void*)&nodes, (void*)&pl->fast_stride, (void*)&pl->n_species_staged};
+  CK(cudaLaunchKernel(fn, dim3(pl->n_sm * bps), dim3(BLOCK), args, pl->fast_smem_bytes, st));
+  g_launches++;
+  return STRYKE_OK;
+}
+
 static int launch_fast_any(StrykePlan* pl, cudaStream_t st) {
-  static const int minb = [] { const char* e = getenv("STRYKE_B200_MINB"); return e ? atoi(e) : 4; }();
-  if (minb == 5) return launch_fast_minb<5>(pl, st);
-  if (minb == 6) return launch_fast_minb<6>(pl, st);
+  if (pl->jit_kernel) return launch_jit(pl, st);
   return launch_fast_minb<4>(pl, st);
 }
 
@@ -1145,6 +1245,27 @@ int stryke_b200_plan_launch(StrykePlan* pl, int32_t* d_cell_n, uint32_t* d_daily
   if (pl->use_fast) return launch_fast_any(pl, st);
   if (pl->precision == 64) return pl->inject ? launch_passage_pr<double, true>(pl, st) : launch_passage_pr<double, false>(pl, st);
   return pl->inject ? launch_passage_pr<float, true>(pl, st) : launch_passage_pr<float, false>(pl, st);
+}
+
+int stryke_b200_set_source_dir(const char* dir) {
+  if (!dir) return fail(STRYKE_E_ARG, "null argument");
+  std::lock_guard<std::mutex> lock(jit::g_mu);
+  jit::g_source_dir = dir;
+  return STRYKE_OK;
+}
+
+const char* stryke_b200_plan_kernel(const StrykePlan* pl) { return pl ? pl->kernel_name.c_str() : ""; }
+
+// Compile (not load) the specialised kernel for a small built-in facility shape: needs libnvrtc, no GPU.
+int stryke_b200_jit_selftest(void) {
+  std::vector<MoveRec> mv = {{0, 32, 0, 0, 1, 0, 1, 0}, {1, 16, 0, 1, 2, 2, 5, 1}, {2, 11, 4, 2, 7, 0, 1, 2},
+                             {3, 32, 0, 7, 8, 0, 1, 7}, {4, 32, 0, 8, 9, 0, 1, 8}, {5, 32, 0, 9, 10, 0, 0, 8}};
+  std::vector<uint8_t> pairs = {0, 1, 2, 3, 4, 5, 6, 7, 8, 8};
+  for (int baro = 0; baro < 2; ++baro) {
+    std::string err;
+    if (!jit::compile(jit::generate(mv, pairs, 5, 1, baro != 0), &err)) return fail(STRYKE_E_CUDA, err);
+  }
+  return STRYKE_OK;
 }
 
 int stryke_b200_plan_set_seed(StrykePlan* pl, uint64_t seed) {

@@ -14,14 +14,20 @@
 //   * the day's routing table is staged per warp as fixed-stride rows (cdf padded with 2.0, successor ids padded with
 //     the node itself; "fish stays today" rows point at themselves), so the categorical draw is a predicate-free
 //     count of cdf[e] <= u and the move is one byte load;
-//   * three Philox refill sites in the whole kernel (length block, per-node words, routing word); the key schedule
+//   * a level with per-node draws owns one Philox block (rR, depth, cause, dice at positions 0..3); the key schedule
 //     comes straight from the constant bank (uniform adds).
-// tests/test_gpu_native_rng.py::test_fast_kernel_equals_general_kernel requires identical tallies from both.
+//
+// The body is a template over a *table provider*.  RuntimeTables (ahead-of-time build) reads the per-move records from
+// the constant bank.  At plan creation the host can also generate a provider whose tables are compile-time constants of
+// the plan's facility and compile this same body with NVRTC (jit_specialise() in passage.cu): the move loop then unrolls
+// completely and every need test, word slot and pair index folds away — measured 347 executed instructions per tile of
+// 32 fish on the C2 facility against 660 for the generic instantiation.
+// tests/test_gpu_native_rng.py requires identical tallies from the general kernel, the generic and the specialised
+// instantiation of this body.
 #pragma once
+#include "passage_common.cuh"
 
 namespace stryke {
-
-constexpr uint8_t NEED_TRIVIAL = 32;   // MoveRec.need: single a-priori node, survival 1.0, <= 1 successor, no 'U'
 
 struct FastTables {                    // by-value kernel parameter (constant bank)
   MoveRec moves[STRYKE_MAX_MOVES];
@@ -37,18 +43,17 @@ struct FastSmem {
   int nodes, ustatic, uc1, species, warp0, warp_stride, cdf, dst, ucoef, total;
 };
 __host__ __device__ inline FastSmem fast_smem(int n_nodes, int n_units, int stride, int n_species_staged) {
-  auto al = [](int x) { return (x + 15) & ~15; };
   FastSmem L;
   int o = 0;
-  L.nodes = o; o = al(o + n_nodes * 8);
-  L.ustatic = o; o = al(o + n_units * 16);
-  L.uc1 = o; o = al(o + n_units * 4);
-  L.species = o; o = al(o + n_species_staged * SPW * 4);
+  L.nodes = o; o = (o + n_nodes * 8 + 15) & ~15;
+  L.ustatic = o; o = (o + n_units * 16 + 15) & ~15;
+  L.uc1 = o; o = (o + n_units * 4 + 15) & ~15;
+  L.species = o; o = (o + n_species_staged * SPW * 4 + 15) & ~15;
   L.warp0 = o;
   int w = 0;
-  L.cdf = w; w = al(w + n_nodes * stride * 4);
-  L.ucoef = w; w = al(w + n_units * 16);
-  L.dst = w; w = al(w + n_nodes * stride);
+  L.cdf = w; w = (w + n_nodes * stride * 4 + 15) & ~15;
+  L.ucoef = w; w = (w + n_units * 16 + 15) & ~15;
+  L.dst = w; w = (w + n_nodes * stride + 15) & ~15;
   L.warp_stride = w;
   L.total = o + w * WARPS;
   return L;
@@ -60,10 +65,18 @@ __device__ __forceinline__ void add_if_lane(uint32_t& acc_a, uint32_t& acc_b, in
       : "+r"(acc_a), "+r"(acc_b) : "r"(p), "r"(lane_id), "r"(a), "r"(b));
 }
 
-template <int PR, bool BARO, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) passage_fast_kernel(const KParams P, const __grid_constant__ FastTables FT,
-                                                                const uint2* __restrict__ g_nodes, const int stride,
-                                                                const int n_species_staged) {
+// Table provider of the generic instantiation: per-move records and pair list from the constant bank at run time.
+struct RuntimeTables {
+  static constexpr bool kStatic = false;
+  static constexpr int M = 1, STRIDE = 1, UNROLL_K = 1, UNROLL_P = 1;
+  static __device__ __forceinline__ MoveRec move(const FastTables& FT, int k) { return FT.moves[k]; }
+  static __device__ __forceinline__ int pair_node(const FastTables& FT, int p) { return (int)FT.pair_node[p]; }
+};
+
+template <class TP, int PR, bool BARO>
+__device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTables& FT, const uint2* __restrict__ g_nodes,
+                                                  const int stride_rt, const int n_species_staged) {
+  const int stride = TP::kStatic ? TP::STRIDE : stride_rt;
   extern __shared__ __align__(16) unsigned char smem[];
   const FastSmem SL = fast_smem(P.n_nodes, P.n_units, stride, n_species_staged);
   uint2* s_nodes = reinterpret_cast<uint2*>(smem + SL.nodes);
@@ -90,7 +103,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) passage_fast_kernel(const KParams
 
   const int64_t T = P.tile_off[P.n_cells];
   const int64_t G = (int64_t)gridDim.x * WARPS, gw = (int64_t)blockIdx.x * WARPS + wid;
-  const int64_t t0 = (T / G) * gw + min(gw, T % G), t1 = t0 + T / G + (gw < T % G ? 1 : 0);
+  const int64_t t0 = (T / G) * gw + (gw < T % G ? gw : T % G), t1 = t0 + T / G + (gw < T % G ? 1 : 0);
   if (t0 >= t1) return;
   int64_t c;
   {
@@ -124,7 +137,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) passage_fast_kernel(const KParams
     acc_daily = 0;
   };
 
-  const int n_moves = P.n_moves;
+  const int n_moves = TP::kStatic ? TP::M : P.n_moves;
   for (int64_t t = t0; t < t1; ++t) {
     while (t >= c_end) { ++c; c_begin = c_end; c_end = P.tile_off[c + 1]; }
     if (c != cur_cell) {
@@ -191,8 +204,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) passage_fast_kernel(const KParams
     bool ent_surv = false;
     uint32_t cz = 0;
 
+#pragma unroll(TP::UNROLL_K)
     for (int k = 0; k < n_moves; ++k) {
-      const MoveRec mv = FT.moves[k];                    // constant bank, uniform index
+      const MoveRec mv = TP::move(FT, k);                // constant bank (uniform index) or compile-time constant
       if (mv.need & NEED_TRIVIAL) {
         // one a-priori node, survival 1.0, at most one successor, no 'U' in its name: every live fish is here,
         // survives (stryke.py:3210 with rate 1.0) and moves to the only successor (or stays, stryke.py:1849-1855)
@@ -225,7 +239,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) passage_fast_kernel(const KParams
         const float rR = kap ? fmaf(0.7f, u_rr, 0.3f) : 1.f;
         const float inv = kap ? rsqrt_approx(fmaf(rR, rR, uc.x * uc.x)) : 1.f;   // exact 1 for the linear runners
         float p = uc.z * L * inv * fmaf(rR, uc.y, uc.x * 0.318309886f * rcp_approx(rR));
-        p = uc.w > 0.f ? p : INFINITY;
+        p = uc.w > 0.f ? p : __int_as_float(0x7f800000);                     // no flow: p_strike = inf (Appendix E10)
         const float strike = blocked ? 1.f : __saturatef(1.f - p);
         float baro = 1.f;
         if (BARO) {
@@ -245,9 +259,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) passage_fast_kernel(const KParams
 
       // ---- (6) State_Daily: lane p owns pair p ---------------------------------------------------------------------
       const int key_c = prev_alive ? loc : 0x1ff, key_s = surv ? loc : 0x1ff;
-#pragma unroll 1
+#pragma unroll(TP::UNROLL_P)
       for (int p = mv.level_begin; p < mv.level_end; ++p) {                  // uniform bounds
-        const int node = (int)FT.pair_node[p];
+        const int node = TP::pair_node(FT, p);
         const uint32_t pc = __popc(__ballot_sync(0xffffffffu, key_c == node));
         const uint32_t ps = __popc(__ballot_sync(0xffffffffu, key_s == node));
 #pragma unroll
@@ -269,7 +283,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) passage_fast_kernel(const KParams
           }
           const float u = u_co<float>(word(sr & 3));
           const int md = mv.max_deg;
-#pragma unroll 1
+#pragma unroll(TP::UNROLL_P)
           for (int e = 0; e < md - 1; ++e) j += (s_cdf[row + e] <= u) ? 1 : 0;   // searchsorted(cdf, u, 'right')
         }
         loc = surv ? (int)s_dst[row + j] : loc;
@@ -289,5 +303,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) passage_fast_kernel(const KParams
   }
   if (cur_cell >= 0) flush(cur_cell);
 }
+
+#ifndef STRYKE_NVRTC
+// ahead-of-time instantiation: tables from the constant bank
+template <int PR, bool BARO, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) passage_fast_kernel(const KParams P, const __grid_constant__ FastTables FT,
+                                                                const uint2* __restrict__ g_nodes, const int stride,
+                                                                const int n_species_staged) {
+  passage_fast_body<RuntimeTables, PR, BARO>(P, FT, g_nodes, stride, n_species_staged);
+}
+#endif
 
 }  // namespace stryke

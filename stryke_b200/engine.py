@@ -162,6 +162,10 @@ class Plan:
         _abi.check(_abi.lib().stryke_b200_plan_launch(self._h, C.c_void_p(cell_n.data_ptr()), C.c_void_p(daily.data_ptr()),
                                                       C.c_void_p(state_daily.data_ptr()), C.c_void_p(stream)))
 
+    def kernel(self):
+        """Name of the passage kernel this plan launches (general / generic throughput / NVRTC-specialised)."""
+        return _abi.lib().stryke_b200_plan_kernel(self._h).decode()
+
     def set_seed(self, seed):
         _abi.check(_abi.lib().stryke_b200_plan_set_seed(self._h, C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF)))
 

@@ -362,7 +362,7 @@ class simulation:
                 fac_type = fac_type.iloc[0]
             fac_units = self.unit_params[self.unit_params.Facility == facility]
             if not fac_units.index.equals(pd.RangeIndex(len(fac_units))):
-                fac_units = fac_units.reset_index(drop=False)
+                fac_units = fac_units.reset_index(drop=fac_units.index.name in fac_units.columns)
             fac_units = fac_units.sort_values(by="op_order")
 
             def unit_key(i, row):

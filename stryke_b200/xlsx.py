@@ -179,20 +179,41 @@ def _cell_xml(ref, v):
     return f'<c r="{ref}" t="inlineStr"><is><t xml:space="preserve">{escape(str(v))}</t></is></c>'
 
 
-def _sheet_xml(df):
-    df = df.reset_index()
+def _sheet_xml(df, startrow=0, startcol=0, index=True):
+    if index:
+        df = df.reset_index()
     out = ['<?xml version="1.0" encoding="UTF-8" standalone="yes"?>',
            '<worksheet xmlns="http://schemas.openxmlformats.org/spreadsheetml/2006/main"><sheetData>']
-    header = "".join(_cell_xml(f"{col_letters(j)}1", "" if str(c) == "index" else str(c)) for j, c in enumerate(df.columns))
-    out.append(f'<row r="1">{header}</row>')
-    for i, row in enumerate(df.itertuples(index=False), start=2):
-        out.append(f'<row r="{i}">' + "".join(_cell_xml(f"{col_letters(j)}{i}", v) for j, v in enumerate(row)) + "</row>")
+    r0 = startrow + 1
+    header = "".join(_cell_xml(f"{col_letters(startcol + j)}{r0}", "" if str(c) == "index" else str(c))
+                     for j, c in enumerate(df.columns))
+    out.append(f'<row r="{r0}">{header}</row>')
+    for i, row in enumerate(df.itertuples(index=False), start=r0 + 1):
+        out.append(f'<row r="{i}">' + "".join(_cell_xml(f"{col_letters(startcol + j)}{i}", v) for j, v in enumerate(row)) + "</row>")
     out.append("</sheetData></worksheet>")
     return "".join(out)
 
 
-def append_sheets(path, frames):
-    """Add (or replace) worksheets in an existing workbook."""
+def new_workbook(path):
+    """Write an empty workbook (no sheets yet) that ``append_sheets`` can extend."""
+    with zipfile.ZipFile(path, "w", zipfile.ZIP_DEFLATED) as z:
+        z.writestr("[Content_Types].xml",
+                   '<?xml version="1.0" encoding="UTF-8" standalone="yes"?><Types xmlns="http://schemas.openxmlformats.org/package/2006/content-types">'
+                   '<Default Extension="xml" ContentType="application/xml"/>'
+                   '<Default Extension="rels" ContentType="application/vnd.openxmlformats-package.relationships+xml"/>'
+                   '<Override PartName="/xl/workbook.xml" ContentType="application/vnd.openxmlformats-officedocument.spreadsheetml.sheet.main+xml"/></Types>')
+        z.writestr("_rels/.rels",
+                   '<?xml version="1.0" encoding="UTF-8" standalone="yes"?><Relationships xmlns="http://schemas.openxmlformats.org/package/2006/relationships">'
+                   '<Relationship Id="rId1" Type="http://schemas.openxmlformats.org/officeDocument/2006/relationships/officeDocument" Target="xl/workbook.xml"/></Relationships>')
+        z.writestr("xl/workbook.xml",
+                   '<?xml version="1.0" encoding="UTF-8" standalone="yes"?><workbook xmlns="http://schemas.openxmlformats.org/spreadsheetml/2006/main" '
+                   'xmlns:r="http://schemas.openxmlformats.org/officeDocument/2006/relationships"><sheets></sheets></workbook>')
+        z.writestr("xl/_rels/workbook.xml.rels",
+                   '<?xml version="1.0" encoding="UTF-8" standalone="yes"?><Relationships xmlns="http://schemas.openxmlformats.org/package/2006/relationships"></Relationships>')
+
+
+def append_sheets(path, frames, startrow=0, startcol=0, index=True):
+    """Add worksheets to an existing workbook.  ``startrow`` / ``startcol`` may be ints or {sheet: int} dicts."""
     with zipfile.ZipFile(path) as z:
         parts = {n: z.read(n) for n in z.namelist()}
     wb = parts["xl/workbook.xml"].decode("utf-8")
@@ -206,7 +227,8 @@ def append_sheets(path, frames):
             raise ValueError(f"Sheet '{name}' already exists and if_sheet_exists is set to 'error'.")
         sid, rid, fid = max(sheet_ids + [0]) + 1, max(rel_ids + [0]) + 1, max(files + [0]) + 1
         sheet_ids.append(sid); rel_ids.append(rid); files.append(fid)
-        parts[f"xl/worksheets/sheet{fid}.xml"] = _sheet_xml(df).encode("utf-8")
+        pick = lambda v: v.get(name, 0) if isinstance(v, dict) else v
+        parts[f"xl/worksheets/sheet{fid}.xml"] = _sheet_xml(df, pick(startrow), pick(startcol), index).encode("utf-8")
         wb = wb.replace("</sheets>", f'<sheet name="{escape(name)}" sheetId="{sid}" r:id="rId{rid}"/></sheets>')
         rels = rels.replace("</Relationships>",
                             f'<Relationship Id="rId{rid}" Type="http://schemas.openxmlformats.org/officeDocument/2006/relationships/worksheet" '
