@@ -30,8 +30,10 @@
 #include <vector>
 
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <fstream>
+#include <iterator>
 #include <map>
 #include <mutex>
 #include <sstream>
@@ -742,7 +744,7 @@ struct StrykePlan {
 
 namespace jit {
 static std::string generate(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int stride, int pr, bool baro);
-static const std::vector<char>* compile(const std::string& src, std::string* err);
+static const std::vector<char>* compile(const std::string& src, std::string* err, bool fresh = false);
 static int load(int device, const std::string& src, const std::vector<char>& bin, cudaKernel_t* kern, std::string* err);
 }  // namespace jit
 
@@ -1154,16 +1156,34 @@ static std::string generate(const std::vector<MoveRec>& moves, const std::vector
 }
 
 // nullptr + message on failure
-static const std::vector<char>* compile(const std::string& src, std::string* err) {
+static const std::vector<char>* compile(const std::string& src, std::string* err, bool fresh) {
   std::lock_guard<std::mutex> lock(g_mu);
   auto it = g_cubins.find(src);
-  if (it != g_cubins.end()) return &it->second;
+  if (it != g_cubins.end() && !fresh) return &it->second;
   Api& a = api();
   if (!a.ok) { *err = "libnvrtc not available"; return nullptr; }
   std::string fast, common;
   if (g_source_dir.empty() || !read_file(g_source_dir + "/passage_fast.cuh", &fast) || !read_file(g_source_dir + "/passage_common.cuh", &common)) {
     *err = "kernel sources not found (stryke_b200_set_source_dir)";
     return nullptr;
+  }
+  // on-disk cache of compiled specialisations: key = FNV-1a of (generated source, both headers, target)
+  uint64_t h = 1469598103934665603ull;
+  const std::string* parts[3] = {&src, &fast, &common};
+  for (const std::string* part : parts)
+    for (unsigned char ch : *part) { h ^= ch; h *= 1099511628211ull; }
+  std::string dir;
+  if (const char* e = getenv("STRYKE_B200_CACHE_DIR")) dir = e;
+  else dir = g_source_dir + "/../.jit_cache";      // inside the package directory
+  char name[64];
+  snprintf(name, sizeof name, "/sm_100a_%016llx.cubin", (unsigned long long)h);
+  const std::string path = dir + name;
+  if (!fresh) {
+    std::ifstream f(path, std::ios::binary);
+    if (f) {
+      std::vector<char> bin((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+      if (bin.size() > 1024) return &(g_cubins[src] = std::move(bin));
+    }
   }
   const char* headers[2] = {fast.c_str(), common.c_str()};
   const char* names[2] = {"passage_fast.cuh", "passage_common.cuh"};
@@ -1185,6 +1205,11 @@ static const std::vector<char>* compile(const std::string& src, std::string* err
   std::vector<char> bin(n);
   a.cubin(prog, bin.data());
   a.destroy(&prog);
+  if (system(("mkdir -p '" + dir + "' 2>/dev/null").c_str()) == 0) {      // best effort; a read-only home is fine
+    const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+    std::ofstream f(tmp, std::ios::binary);
+    if (f && f.write(bin.data(), (std::streamsize)bin.size())) { f.close(); rename(tmp.c_str(), path.c_str()); }
+  }
   return &(g_cubins[src] = std::move(bin));
 }
 
@@ -1263,7 +1288,7 @@ int stryke_b200_jit_selftest(void) {
   std::vector<uint8_t> pairs = {0, 1, 2, 3, 4, 5, 6, 7, 8, 8};
   for (int baro = 0; baro < 2; ++baro) {
     std::string err;
-    if (!jit::compile(jit::generate(mv, pairs, 5, 1, baro != 0), &err)) return fail(STRYKE_E_CUDA, err);
+    if (!jit::compile(jit::generate(mv, pairs, 5, 1, baro != 0), &err, /*fresh=*/true)) return fail(STRYKE_E_CUDA, err);
   }
   return STRYKE_OK;
 }
