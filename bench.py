@@ -246,8 +246,8 @@ def main():
                 "frac": achieved / peak_ops, "traffic": traffic,
                 "note": "neither HBM nor tensor binds this path (SURVEY.md §8d): bound = SM instruction issue (INT32 Philox + FP32/MUFU). "
                         f"achieved = {algo:.0f} algorithmic lane-ops per fish-passage (DESIGN.md §4) x fish-passages/s per GPU; peak = lane-ops/s of "
-                        "an 8 FFMA + 8 LOP3 per-iteration independent-chain stream (both half-rate pipes busy: 1 warp instruction per scheduler "
-                        "per cycle) measured live by stryke_b200_calibrate_issue on this GPU; traffic = DRAM bytes per launch (ncu)",
+                        "16 independent FFMA chains per thread at full occupancy (1 warp instruction per scheduler per cycle) measured live by "
+                        "stryke_b200_calibrate_issue on this GPU; traffic = DRAM bytes per launch (ncu)",
                 "executed_thread_inst_per_fish_ncu": inst_per_fish,
                 "issue_utilisation_executed": (per_gpu_rate * inst_per_fish / peak_ops) if inst_per_fish and args.workload == "c2" else None,
                 "hbm": {"achieved_GBps": (plan.n_cells * (4 + 20 + plan.n_pairs * 8) * 2) / (ms_total / args.steps * 1e-3) / 1e9,
