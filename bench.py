@@ -52,34 +52,67 @@ def build_plan(prj, name):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md clocks line): NVML polled every 2 ms
+    (the same counters ``nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*`` prints), with the
+    nvidia-smi command itself as the fallback when the NVML binding is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.stop_flag = index, False
+        self.sm, self.mx, self.reasons, self.source = [], [], set(), "nvml"
+        self.nv = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it lists plain ordinals
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                phys = int(vis.split(",")[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
+            self.nv = pynvml
+        except Exception:
+            self.nv, self.source = None, "nvidia-smi"
+
+    def _nvml_sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        for nm, bit in zip(self.NAMES, (nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                                        nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(nm)
+
+    def _smi_sample(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [x.strip() for x in out.split(",")] if out else []
+        if r and r[0].replace(".", "").isdigit():
+            self.sm.append(float(r[0]))
+        if len(r) > 1 and r[1].replace(".", "").isdigit():
+            self.mx.append(float(r[1]))
+        for i, nm in enumerate(self.NAMES):
+            if len(r) > 3 + i and r[3 + i].lower().startswith("active"):
+                self.reasons.add(nm)
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                if self.nv is not None:
+                    self._nvml_sample()
+                else:
+                    self._smi_sample()
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.002 if self.nv is not None else 0.05)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = []
-        for i, nm in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
-            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows):
-                reasons.append(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 CPU_SAMPLE = {"c2": dict(n_fish=200_000, iterations=24, days=1), "c5": dict(n_fish=100_000, iterations=12, days=1),

@@ -891,7 +891,7 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
   CK(pl->fish_off.alloc((size_t)(c->n_cells + 1) * sizeof(int64_t)));
   pl->nb_scan = (int)((c->n_cells + SCAN_CH - 1) / SCAN_CH);
   CK(pl->part.alloc((size_t)(pl->nb_scan > 0 ? pl->nb_scan : 1) * 2 * sizeof(int64_t)));
-  CK(pl->err.alloc(sizeof(unsigned long long)));
+  CK(pl->err.alloc(2 * sizeof(unsigned long long)));    // [0] error word of count_kernel, [1] chunk counter of the throughput kernels
 
   KParams& K = pl->K;
   K.nodes = pl->nodes.as<NodeRec>(); K.edge_dst = pl->edge_dst.as<uint8_t>(); K.moves = pl->moves.as<MoveRec>();
@@ -904,6 +904,9 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
   K.tile_off = pl->tile_off.as<int64_t>(); K.fish_off = pl->fish_off.as<int64_t>(); K.n_cells = c->n_cells;
   K.seed_lo = (uint32_t)o->seed; K.seed_hi = (uint32_t)(o->seed >> 32);
   K.n_fish_total = 0;
+  K.work_counter = pl->err.as<unsigned long long>() + 1;
+  K.chunk_tiles = 64;
+  if (const char* e = getenv("STRYKE_B200_CHUNK_TILES")) K.chunk_tiles = std::max(1, atoi(e));
 
   // ---- injected draws ----------------------------------------------------------------------------------------------
   int64_t NF = 0;
@@ -1258,7 +1261,7 @@ int stryke_b200_plan_launch(StrykePlan* pl, int32_t* d_cell_n, uint32_t* d_daily
   if (pl->n_cells == 0) return STRYKE_OK;
   CK(cudaMemsetAsync(d_daily, 0, (size_t)pl->n_cells * STRYKE_DAILY_W * 4, st));
   CK(cudaMemsetAsync(d_state_daily, 0, (size_t)pl->n_cells * K.n_pairs * 2 * 4, st));
-  CK(cudaMemsetAsync(pl->err.p, 0, sizeof(unsigned long long), st));
+  CK(cudaMemsetAsync(pl->err.p, 0, 2 * sizeof(unsigned long long), st));
   const int cb = (int)((pl->n_cells + 255) / 256);
   if (pl->inject) count_kernel<true><<<cb, 256, 0, st>>>(K, pl->day_Q.as<double>(), d_cell_n, pl->max_daily_fish, pl->err.as<unsigned long long>());
   else count_kernel<false><<<cb, 256, 0, st>>>(K, pl->day_Q.as<double>(), d_cell_n, pl->max_daily_fish, pl->err.as<unsigned long long>());

@@ -110,6 +110,8 @@ struct KParams {
   uint32_t seed_lo, seed_hi;
   int64_t n_fish_total;
   InjectedDev inj; TraceDev trace;
+  unsigned long long* work_counter;   // throughput kernels: next chunk of tiles to hand out (zeroed before every launch)
+  int chunk_tiles;                    // tiles per chunk
 };
 
 constexpr double P_ATM = 101325.0;    // scipy.constants.atm (stryke.py:1472)

@@ -101,17 +101,13 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
     s_species[i] = (float)P.species[(i / SPW) * STRYKE_SPECIES_W + (i % SPW)];
   __syncthreads();
 
+  // Work distribution: chunks of P.chunk_tiles consecutive tiles handed out through one global counter (the first
+  // chunk of every warp is its own global index, later ones come from the counter).  The SM's warp arbiter does not
+  // share issue slots evenly, so equal static ranges finish unevenly and leave the SM short of warps at the end.
   const int64_t T = P.tile_off[P.n_cells];
-  const int64_t G = (int64_t)gridDim.x * WARPS, gw = (int64_t)blockIdx.x * WARPS + wid;
-  const int64_t t0 = (T / G) * gw + (gw < T % G ? gw : T % G), t1 = t0 + T / G + (gw < T % G ? 1 : 0);
-  if (t0 >= t1) return;
-  int64_t c;
-  {
-    int64_t lo = 0, hi = P.n_cells;
-    while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (P.tile_off[mid] <= t0) lo = mid; else hi = mid; }
-    c = lo;
-  }
-  int64_t c_end = P.tile_off[c + 1], c_begin = P.tile_off[c];
+  const int64_t G = (int64_t)gridDim.x * WARPS, CH = P.chunk_tiles;
+  int64_t chunk = (int64_t)blockIdx.x * WARPS + wid;
+  int64_t c = -1, c_begin = 0, c_end = 0;             // current cell and its tile range [c_begin, c_end)
   int cur_day = -1;
   int64_t cur_cell = -1;
   float sp_ls = 0, sp_ll = 0, sp_lsc = 0, sp_lm = 0, sp_lsd = 0, sp_wr = 0, sp_uc = 0, sp_d1 = 0, sp_dd = 0, sp_b0 = 0, sp_b1 = 0;
@@ -138,6 +134,20 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   };
 
   const int n_moves = TP::kStatic ? TP::M : P.n_moves;
+  for (;;) {
+  const int64_t t0 = chunk * CH;
+  if (t0 >= T) break;
+  const int64_t t1 = t0 + CH < T ? t0 + CH : T;
+  {   // fetch the next chunk index now, use it after this chunk
+    unsigned long long nx = 0;
+    if (lane == 0) nx = atomicAdd(P.work_counter, 1ull);
+    chunk = G + (int64_t)__shfl_sync(0xffffffffu, nx, 0);
+  }
+  if (t0 >= c_end) {        // not a continuation: last cell with tile_off[c] <= t0 (cells without fish have empty ranges)
+    int64_t lo = c < 0 ? 0 : c, hi = P.n_cells;
+    while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (P.tile_off[mid] <= t0) lo = mid; else hi = mid; }
+    c = lo; c_begin = P.tile_off[c]; c_end = P.tile_off[c + 1];
+  }
   for (int64_t t = t0; t < t1; ++t) {
     while (t >= c_end) { ++c; c_begin = c_end; c_end = P.tile_off[c + 1]; }
     if (c != cur_cell) {
@@ -300,6 +310,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
       r_bar = __reduce_add_sync(0xffffffffu, (cz >> 16) & 0xffu);
     }
     acc_daily += lane == 0 ? __popc(b_ent) : lane == 1 ? __popc(b_sur) : lane == 2 ? r_imp : lane == 3 ? r_bld : lane == 4 ? r_bar : 0u;
+  }
   }
   if (cur_cell >= 0) flush(cur_cell);
 }
