@@ -743,7 +743,17 @@ struct StrykePlan {
 };
 
 namespace jit {
-static std::string generate(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int stride, int pr, bool baro);
+// Layout of the packed per-lane tallies of the specialised kernel (LevelTally / FieldRec in passage_fast.cuh).
+struct TallyPlan {
+  int NW = 0, HOLD = 1, W_ES = 0, B_ES = 0, W_CAUSE = 0;
+  std::vector<LevelTally> lv;
+  std::vector<FieldRec> fields;
+  std::vector<int> node_local;       // local index of every node inside its (non-trivial, multi-node) level, -1 = none
+};
+static TallyPlan plan_tally(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int n_nodes);
+struct Dims { int n_nodes, n_units, n_species_staged, start_node; };
+static std::string generate(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int stride, int pr, bool baro,
+                            const TallyPlan& T, const Dims& D);
 static const std::vector<char>* compile(const std::string& src, std::string* err, bool fresh = false);
 static int load(int device, const std::string& src, const std::vector<char>& bin, cudaKernel_t* kern, std::string* err);
 }  // namespace jit
@@ -903,6 +913,7 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
   K.cell_day = pl->cell_day.as<int32_t>(); K.cell_species = pl->cell_species.as<int32_t>(); K.cell_id = pl->cell_id.as<uint64_t>();
   K.tile_off = pl->tile_off.as<int64_t>(); K.fish_off = pl->fish_off.as<int64_t>(); K.n_cells = c->n_cells;
   K.seed_lo = (uint32_t)o->seed; K.seed_hi = (uint32_t)(o->seed >> 32);
+  Philox::key_schedule(o->seed, K.ks);
   K.n_fish_total = 0;
   K.work_counter = pl->err.as<unsigned long long>() + 1;
   K.chunk_tiles = 64;
@@ -985,12 +996,6 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
     if (pl->fast_smem_bytes > 96 * 1024) pl->use_fast = false;   // very wide graphs: the general kernel's CSR layout
   }
   if (pl->use_fast) {
-    std::vector<uint2> fn(f->n_nodes);
-    for (int i = 0; i < f->n_nodes; ++i) {
-      fn[i].x = __float_as_uint_host(nodes[i].apriori32);
-      fn[i].y = pack_node(nodes[i].kind, nodes[i].hasU, nodes[i].unit);
-    }
-    CK(upload(pl->fast_nodes, fn.data(), fn.size()));
     for (int k = 0; k < f->n_moves; ++k) {
       MoveRec m = moves[k];
       const NodeRec& n0 = nodes[pnode[m.level_begin]];
@@ -999,6 +1004,13 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
       pl->fast.moves[k] = m;
     }
     for (int p = 0; p < f->n_pairs; ++p) pl->fast.pair_node[p] = pnode[p];
+    const jit::TallyPlan tally = jit::plan_tally(std::vector<MoveRec>(pl->fast.moves, pl->fast.moves + f->n_moves), pnode, f->n_nodes);
+    std::vector<uint2> fn(f->n_nodes);
+    for (int i = 0; i < f->n_nodes; ++i) {
+      fn[i].x = __float_as_uint_host(nodes[i].apriori32);
+      fn[i].y = pack_node(nodes[i].kind, nodes[i].hasU, nodes[i].unit, tally.NW && tally.node_local[i] > 0 ? tally.node_local[i] : 0);
+    }
+    CK(upload(pl->fast_nodes, fn.data(), fn.size()));
     pl->kernel_name = "passage_fast_kernel (generic tables, ahead-of-time)";
     // ---- specialise for this facility when the run is large enough to amortise a ~1-3 s compile ---------------------
     double fish_hint = 0.0;
@@ -1011,7 +1023,8 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
                                                  ((env && env[0] == '1') || fish_hint >= 2.0e7));
     if (want) {
       std::vector<MoveRec> mv(pl->fast.moves, pl->fast.moves + f->n_moves);
-      const std::string src = jit::generate(mv, pnode, pl->fast_stride, pl->pr, f->barotrauma != 0);
+      const std::string src = jit::generate(mv, pnode, pl->fast_stride, pl->pr, f->barotrauma != 0, tally,
+                                                jit::Dims{f->n_nodes, f->n_units, pl->n_species_staged, f->start_node});
       std::string err;
       const std::vector<char>* bin = jit::compile(src, &err);
       cudaKernel_t k = nullptr;
@@ -1136,13 +1149,95 @@ static bool read_file(const std::string& path, std::string* out) {
   return true;
 }
 
+
+// NW stays 0 (ballot tallies) when the facility does not fit the scheme: move loop not unrolled (> 32 moves), too many
+// words for the register file, a node whose local index differs between two levels, > 40 nodes in one level.
+static TallyPlan plan_tally(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int n_nodes) {
+  TallyPlan T;
+  const int M = (int)moves.size();
+  T.node_local.assign((size_t)std::max(n_nodes, 1), -1);
+  if (M > 32) return T;
+  std::vector<int> fill;             // 6-bit fields used in every word (5 per word)
+  auto alloc = [&](int n) {          // n <= 5 contiguous fields inside one word -> (word, first bit)
+    for (size_t w = 0; w < fill.size(); ++w)
+      if (fill[w] + n <= 5) { const int b = 6 * fill[w]; fill[w] += n; return std::make_pair((int)w, b); }
+    fill.push_back(n);
+    return std::make_pair((int)fill.size() - 1, 0);
+  };
+  auto field = [&](int w, int sh, int bits, int target, int p0, int len) {
+    T.fields.push_back(FieldRec{(uint8_t)w, (uint8_t)sh, (uint8_t)bits, (uint8_t)target, (uint8_t)p0, (uint8_t)len});
+  };
+  int n_cause = 0;
+  T.lv.assign((size_t)M, LevelTally{});
+  for (int k = 0; k < M; ++k) {
+    const MoveRec& m = moves[k];
+    const int n = m.level_end - m.level_begin;
+    if (m.need & NEED_CAUSE) ++n_cause;
+    if (m.need & NEED_TRIVIAL) {
+      if (k > 0 && (moves[k - 1].need & NEED_TRIVIAL)) continue;          // inside a run: alive cannot change
+      int run = 1;
+      while (k + run < M && (moves[k + run].need & NEED_TRIVIAL)) ++run;   // one pair per trivial level, consecutive
+      const auto a = alloc(1);
+      T.lv[k] = LevelTally{1, (uint8_t)a.first, (uint8_t)a.second, 0, 0, 1};
+      field(a.first, a.second, 6, 2, m.level_begin, run);
+    } else if (n <= 5) {
+      const auto a = alloc(n), b = alloc(n);
+      T.lv[k] = LevelTally{(uint8_t)(n == 1 ? 2 : 3), (uint8_t)a.first, (uint8_t)a.second, (uint8_t)b.first, (uint8_t)b.second, 1};
+      for (int i = 0; i < n; ++i) {
+        field(a.first, a.second + 6 * i, 6, 0, m.level_begin + i, 1);
+        field(b.first, b.second + 6 * i, 6, 1, m.level_begin + i, 1);
+      }
+    } else {
+      if (n > 40) return TallyPlan{};
+      const int nwl = (n + 4) / 5;
+      const int wc = (int)fill.size();
+      for (int j = 0; j < 2 * nwl; ++j) fill.push_back(5);
+      T.lv[k] = LevelTally{4, (uint8_t)wc, 0, (uint8_t)(wc + nwl), 0, (uint8_t)nwl};
+      for (int i = 0; i < n; ++i) {
+        field(wc + i / 5, 6 * (i % 5), 6, 0, m.level_begin + i, 1);
+        field(wc + nwl + i / 5, 6 * (i % 5), 6, 1, m.level_begin + i, 1);
+      }
+    }
+    if (!(m.need & NEED_TRIVIAL) && n > 1)
+      for (int i = 0; i < n; ++i) {
+        const int v = pairs[m.level_begin + i];
+        if (v >= (int)T.node_local.size()) T.node_local.resize((size_t)v + 1, -1);
+        if (T.node_local[v] >= 0 && T.node_local[v] != i) return TallyPlan{};
+        T.node_local[v] = i;
+      }
+  }
+  const auto es = alloc(2);
+  T.W_ES = es.first; T.B_ES = es.second;
+  field(es.first, es.second, 6, 3, 0, 1);
+  field(es.first, es.second + 6, 6, 3, 1, 1);
+  T.W_CAUSE = (int)fill.size();
+  fill.push_back(5);
+  for (int j = 0; j < 3; ++j) field(T.W_CAUSE, 10 * j, 10, 3, 2 + j, 1);
+  T.HOLD = std::min(63, 1023 / std::max(1, n_cause));
+  if ((int)fill.size() > 24 || T.fields.size() > 250 || T.HOLD < 4) return TallyPlan{};
+  T.NW = (int)fill.size();
+  return T;
+}
+
+// resident 256-thread blocks per SM the specialised kernel is compiled for (register budget: 4 -> 64, 3 -> 80, 2 -> 128)
+static int spec_min_blocks() {
+  const char* e = getenv("STRYKE_B200_SPEC_MINB");
+  const int v = e ? atoi(e) : 3;      // measured on B200: 3 (80 registers) beats 4 (64, rematerialises) and 2
+  return v >= 1 && v <= 8 ? v : 3;
+}
+
 // The table provider + kernel entry for one plan.
-static std::string generate(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int stride, int pr, bool baro) {
+static std::string generate(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int stride, int pr, bool baro,
+                            const TallyPlan& T, const Dims& D) {
   std::ostringstream o;
   const int M = (int)moves.size(), P = (int)pairs.size();
   o << "#define STRYKE_NVRTC 1\n#include \"passage_fast.cuh\"\nnamespace stryke {\nstruct SpecJit {\n"
     << "  static constexpr bool kStatic = true;\n"
     << "  static constexpr int M = " << M << ", STRIDE = " << stride << ", UNROLL_K = " << (M <= 32 ? M : 1) << ", UNROLL_P = 8;\n"
+    << "  static constexpr int N_NODES = " << D.n_nodes << ", N_UNITS = " << D.n_units << ", N_PAIRS = " << P
+    << ", N_SPECIES_STAGED = " << D.n_species_staged << ", START_NODE = " << D.start_node << ";\n"
+    << "  static constexpr int NW = " << T.NW << ", NF = " << (T.NW ? (int)T.fields.size() : 0) << ", HOLD = " << T.HOLD
+    << ", W_ES = " << T.W_ES << ", B_ES = " << T.B_ES << ", W_CAUSE = " << T.W_CAUSE << ";\n"
     << "  static __device__ constexpr MoveRec move(const FastTables&, int k) {\n    constexpr MoveRec T[" << M << "] = {";
   for (int k = 0; k < M; ++k) {
     const MoveRec& m = moves[k];
@@ -1151,8 +1246,25 @@ static std::string generate(const std::vector<MoveRec>& moves, const std::vector
   }
   o << "};\n    return T[k];\n  }\n  static __device__ constexpr int pair_node(const FastTables&, int p) {\n    constexpr uint8_t N[" << P << "] = {";
   for (int p = 0; p < P; ++p) o << (p ? ", " : "") << (int)pairs[p];
-  o << "};\n    return (int)N[p];\n  }\n};\n}  // namespace stryke\n"
-    << "extern \"C\" __global__ void __launch_bounds__(256, 4) passage_spec(const stryke::KParams P, const stryke::FastTables FT,\n"
+  o << "};\n    return (int)N[p];\n  }\n";
+  if (T.NW) {
+    o << "  static __device__ constexpr LevelTally tally(int k) {\n    constexpr LevelTally T[" << M << "] = {";
+    for (int k = 0; k < M; ++k) {
+      const LevelTally& l = T.lv[k];
+      o << (k ? ", " : "") << "{" << (int)l.kind << ", " << (int)l.wc << ", " << (int)l.bc << ", " << (int)l.ws << ", " << (int)l.bs << ", " << (int)l.nwl << "}";
+    }
+    o << "};\n    return T[k];\n  }\n  static __device__ constexpr FieldRec field(int f) {\n    constexpr FieldRec T[" << T.fields.size() << "] = {";
+    for (size_t f = 0; f < T.fields.size(); ++f) {
+      const FieldRec& r = T.fields[f];
+      o << (f ? ", " : "") << "{" << (int)r.w << ", " << (int)r.sh << ", " << (int)r.bits << ", " << (int)r.target << ", " << (int)r.p0 << ", " << (int)r.len << "}";
+    }
+    o << "};\n    return T[f];\n  }\n";
+  } else {
+    o << "  static __device__ constexpr LevelTally tally(int) { return LevelTally{}; }\n"
+      << "  static __device__ constexpr FieldRec field(int) { return FieldRec{}; }\n";
+  }
+  o << "};\n}  // namespace stryke\n"
+    << "extern \"C\" __global__ void __launch_bounds__(256, " << spec_min_blocks() << ") passage_spec(const stryke::KParams P, const stryke::FastTables FT,\n"
     << "    const uint2* __restrict__ g_nodes, const int stride, const int n_species_staged) {\n"
     << "  stryke::passage_fast_body<stryke::SpecJit, " << pr << ", " << (baro ? "true" : "false") << ">(P, FT, g_nodes, stride, n_species_staged);\n}\n";
   return o.str();
@@ -1237,7 +1349,7 @@ static int launch_jit(StrykePlan* pl, cudaStream_t st) {
   if (pl->fast_smem_bytes > 48 * 1024)
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem_bytes));
   int bps = pl->blocks_per_sm;
-  if (bps <= 0) bps = std::max(1, std::min(4, (int)((200 * 1024) / std::max<size_t>(pl->fast_smem_bytes, 1))));
+  if (bps <= 0) bps = std::max(1, std::min(jit::spec_min_blocks(), (int)((200 * 1024) / std::max<size_t>(pl->fast_smem_bytes, 1))));
   const uint2* nodes = pl->fast_nodes.as<uint2>();
   void* args[] = {(void*)&pl->K, (void*)&pl->fast, (void*)&nodes, (void*)&pl->fast_stride, (void*)&pl->n_species_staged};
   CK(cudaLaunchKernel(fn, dim3(pl->n_sm * bps), dim3(BLOCK), args, pl->fast_smem_bytes, st));
@@ -1291,7 +1403,9 @@ int stryke_b200_jit_selftest(void) {
   std::vector<uint8_t> pairs = {0, 1, 2, 3, 4, 5, 6, 7, 8, 8};
   for (int baro = 0; baro < 2; ++baro) {
     std::string err;
-    if (!jit::compile(jit::generate(mv, pairs, 5, 1, baro != 0), &err, /*fresh=*/true)) return fail(STRYKE_E_CUDA, err);
+    const jit::TallyPlan T = jit::plan_tally(mv, pairs, 9);
+    if (!T.NW) return fail(STRYKE_E_CUDA, "packed tally layout failed for the self-test facility");
+    if (!jit::compile(jit::generate(mv, pairs, 5, 1, baro != 0, T, jit::Dims{9, 3, 1, 0}), &err, /*fresh=*/true)) return fail(STRYKE_E_CUDA, err);
   }
   return STRYKE_OK;
 }
@@ -1299,6 +1413,7 @@ int stryke_b200_jit_selftest(void) {
 int stryke_b200_plan_set_seed(StrykePlan* pl, uint64_t seed) {
   if (!pl) return fail(STRYKE_E_ARG, "null plan");
   pl->K.seed_lo = (uint32_t)seed; pl->K.seed_hi = (uint32_t)(seed >> 32);
+  Philox::key_schedule(seed, pl->K.ks);
   return STRYKE_OK;
 }
 

@@ -61,6 +61,21 @@ struct Philox {
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
   }
+
+  // the same 10 rounds with the key schedule precomputed by the host (ks[2r], ks[2r+1]): when ks lives in the kernel
+  // parameter bank the round keys are constant-bank operands of the XORs instead of 18 uniform adds per block
+  __device__ static __forceinline__ void block_ks(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                  const uint32_t (&ks)[20], uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) round(c0, c1, c2, c3, ks[2 * r], ks[2 * r + 1]);
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+  }
+#ifndef STRYKE_NVRTC
+  __host__ static inline void key_schedule(uint64_t seed, uint32_t ks[20]) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { ks[2 * r] = k0; ks[2 * r + 1] = k1; k0 += W0; k1 += W1; }
+  }
+#endif
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -110,6 +125,7 @@ struct KParams {
   uint32_t seed_lo, seed_hi;
   int64_t n_fish_total;
   InjectedDev inj; TraceDev trace;
+  uint32_t ks[20];                    // Philox key schedule of (seed_lo, seed_hi), throughput kernels
   unsigned long long* work_counter;   // throughput kernels: next chunk of tiles to hand out (zeroed before every launch)
   int chunk_tiles;                    // tiles per chunk
 };

@@ -34,16 +34,20 @@ struct FastTables {                    // by-value kernel parameter (constant ba
   uint8_t pair_node[STRYKE_MAX_PAIRS];
 };
 
-// FastNode.y: kind[0:3) hasU[3] unit[4:11)
-__host__ __device__ inline uint32_t pack_node(int kind, int hasU, int unit) {
-  return (uint32_t)kind | ((uint32_t)(hasU ? 1 : 0) << 3) | ((uint32_t)(unit < 0 ? 0 : unit) << 4);
+// FastNode.y: kind[0:3) hasU[3] unit[4:11); packed tallies: word offset of the node inside its level [24:27),
+// 6 * (local index mod 5) [27:32)
+__host__ __device__ inline uint32_t pack_node(int kind, int hasU, int unit, int local_index = 0) {
+  return (uint32_t)kind | ((uint32_t)(hasU ? 1 : 0) << 3) | ((uint32_t)(unit < 0 ? 0 : unit) << 4) |
+         ((uint32_t)(local_index / 5) << 24) | ((uint32_t)(6 * (local_index % 5)) << 27);
 }
 
 struct FastSmem {
   int nodes, ustatic, uc1, species, warp0, warp_stride, cdf, dst, ucoef, total;
 };
-__host__ __device__ inline FastSmem fast_smem(int n_nodes, int n_units, int stride, int n_species_staged) {
-  FastSmem L;
+// floats per row of the staged routing cdf: the stride-1 thresholds a draw is compared with, padded to whole float4s
+__host__ __device__ constexpr int cdf_row(int stride) { return stride <= 5 ? 4 : ((stride - 1 + 3) & ~3); }
+__host__ __device__ constexpr FastSmem fast_smem(int n_nodes, int n_units, int stride, int n_species_staged) {
+  FastSmem L{};
   int o = 0;
   L.nodes = o; o = (o + n_nodes * 8 + 15) & ~15;
   L.ustatic = o; o = (o + n_units * 16 + 15) & ~15;
@@ -51,7 +55,7 @@ __host__ __device__ inline FastSmem fast_smem(int n_nodes, int n_units, int stri
   L.species = o; o = (o + n_species_staged * SPW * 4 + 15) & ~15;
   L.warp0 = o;
   int w = 0;
-  L.cdf = w; w = (w + n_nodes * stride * 4 + 15) & ~15;
+  L.cdf = w; w = (w + n_nodes * cdf_row(stride) * 4 + 15) & ~15;
   L.ucoef = w; w = (w + n_units * 16 + 15) & ~15;
   L.dst = w; w = (w + n_nodes * stride + 15) & ~15;
   L.warp_stride = w;
@@ -65,20 +69,55 @@ __device__ __forceinline__ void add_if_lane(uint32_t& acc_a, uint32_t& acc_b, in
       : "+r"(acc_a), "+r"(acc_b) : "r"(p), "r"(lane_id), "r"(a), "r"(b));
 }
 
+// -1 when a <= b, else 0 (one FSET)
+__device__ __forceinline__ int le_mask(float a, float b) {
+  int r;
+  asm("set.le.s32.f32 %0, %1, %2;" : "=r"(r) : "f"(a), "f"(b));
+  return r;
+}
+
+// acc += a on the lane whose id equals `p`
+__device__ __forceinline__ void add_if_lane1(uint32_t& acc, int p, int lane_id, uint32_t a) {
+  asm("{\n\t.reg .pred q;\n\tsetp.eq.s32 q, %1, %2;\n\t@q add.u32 %0, %0, %3;\n\t}" : "+r"(acc) : "r"(p), "r"(lane_id), "r"(a));
+}
+
+// Packed per-lane tallies (specialised instantiation only; the layout is generated per facility by the host,
+// jit::plan_tally in passage.cu).  Every lane counts ITS OWN fish in 6-bit fields of a few registers ("tally words"):
+// one field per (move, node) pair for arrivals and one for survivors, one per run of trivial levels, two for the
+// Daily entrained / survived flags; the three mortality causes use 10-bit fields (a fish rolls a cause at every turbine
+// level, stryke.py:1545-1560).  A tile adds at most 1 to a 6-bit field, so the words are only reduced across the warp
+// (one REDUX per field, added to the lane that owns the pair) every HOLD tiles or when the cell changes — instead of
+// two ballots + two popcounts + predicated adds per pair and tile.
+struct LevelTally { uint8_t kind, wc, bc, ws, bs, nwl; };     // kind: 0 nothing (inside a trivial run), 1 head of a trivial
+                                                              // run (field wc/bc), 2 one node, 3 <= 5 nodes (field base +
+                                                              // 6 * local index, from the node record), 4 > 5 nodes
+struct FieldRec { uint8_t w, sh, bits, target, p0, len; };    // target: 0 arrivals of pair p0, 1 survivors of pair p0,
+                                                              // 2 both for pairs [p0, p0+len), 3 Daily column p0
+
 // Table provider of the generic instantiation: per-move records and pair list from the constant bank at run time.
 struct RuntimeTables {
   static constexpr bool kStatic = false;
   static constexpr int M = 1, STRIDE = 1, UNROLL_K = 1, UNROLL_P = 1;
+  static constexpr int N_NODES = 0, N_UNITS = 0, N_PAIRS = 0, N_SPECIES_STAGED = 0, START_NODE = 0;   // run-time (KParams)
+  static constexpr int NW = 0, NF = 0, HOLD = 1, W_ES = 0, B_ES = 0, W_CAUSE = 0;   // no packed tallies: ballots per pair
   static __device__ __forceinline__ MoveRec move(const FastTables& FT, int k) { return FT.moves[k]; }
   static __device__ __forceinline__ int pair_node(const FastTables& FT, int p) { return (int)FT.pair_node[p]; }
+  static __device__ __forceinline__ LevelTally tally(int) { return LevelTally{}; }
+  static __device__ __forceinline__ FieldRec field(int) { return FieldRec{}; }
 };
 
 template <class TP, int PR, bool BARO>
 __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTables& FT, const uint2* __restrict__ g_nodes,
                                                   const int stride_rt, const int n_species_staged) {
+  // facility dimensions: compile-time constants in the specialised instantiation (the shared-memory layout folds to
+  // immediates), kernel parameters otherwise
   const int stride = TP::kStatic ? TP::STRIDE : stride_rt;
+  const int n_nodes = TP::kStatic ? TP::N_NODES : P.n_nodes, n_units = TP::kStatic ? TP::N_UNITS : P.n_units;
+  const int n_pairs = TP::kStatic ? TP::N_PAIRS : P.n_pairs, start_node = TP::kStatic ? TP::START_NODE : P.start_node;
+  const int n_sp = TP::kStatic ? TP::N_SPECIES_STAGED : n_species_staged;
+  const int crow = cdf_row(stride);
   extern __shared__ __align__(16) unsigned char smem[];
-  const FastSmem SL = fast_smem(P.n_nodes, P.n_units, stride, n_species_staged);
+  const FastSmem SL = fast_smem(n_nodes, n_units, stride, n_sp);
   uint2* s_nodes = reinterpret_cast<uint2*>(smem + SL.nodes);
   float4* s_ustatic = reinterpret_cast<float4*>(smem + SL.ustatic);     // rack, intake_vel, fb_depth, c0
   float* s_uc1 = reinterpret_cast<float*>(smem + SL.uc1);               // c1
@@ -86,18 +125,18 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   const int lane = threadIdx.x & 31;
   const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   unsigned char* wbase = smem + SL.warp0 + wid * SL.warp_stride;
-  float* s_cdf = reinterpret_cast<float*>(wbase + SL.cdf);              // [n_nodes][stride], padded with 2.0
+  float* s_cdf = reinterpret_cast<float*>(wbase + SL.cdf);              // [n_nodes][cdf_row(stride)], padded with 2.0
   float4* s_ucoef = reinterpret_cast<float4*>(wbase + SL.ucoef);        // fa, fb, fc, has_flow
   uint8_t* s_dst = wbase + SL.dst;                                      // [n_nodes][stride], padded with the node itself
 
-  for (int i = threadIdx.x; i < P.n_nodes; i += BLOCK) s_nodes[i] = g_nodes[i];
-  for (int u = threadIdx.x; u < P.n_units; u += BLOCK) {
+  for (int i = threadIdx.x; i < n_nodes; i += BLOCK) s_nodes[i] = g_nodes[i];
+  for (int u = threadIdx.x; u < n_units; u += BLOCK) {
     const double* us = P.unit_static + u * STRYKE_UNIT_STATIC_W;
     const double p2 = P_ATM + RHO * G_SI * (us[3] * FT2M);
     s_ustatic[u] = make_float4((float)us[0], (float)us[1], (float)us[2], (float)(P_ATM / p2));
     s_uc1[u] = (float)(RHO * G_SI * FT2M / p2);
   }
-  for (int i = threadIdx.x; i < n_species_staged * SPW; i += BLOCK)
+  for (int i = threadIdx.x; i < n_sp * SPW; i += BLOCK)
     s_species[i] = (float)P.species[(i / SPW) * STRYKE_SPECIES_W + (i % SPW)];
   __syncthreads();
 
@@ -118,12 +157,41 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
 #pragma unroll
   for (int r = 0; r < PR; ++r) { acc_suc[r] = 0; acc_cnt[r] = 0; lane_r[r] = lane + 32 * r; }
 
+  constexpr bool PK = TP::NW > 0;                     // packed per-lane tallies (see LevelTally)
+  uint32_t W[PK ? TP::NW : 1];
+#pragma unroll
+  for (int j = 0; j < (PK ? TP::NW : 1); ++j) W[j] = 0;
+  int held = 0;                                       // tiles accumulated in W since the last drain
+  auto drain = [&]() {                                // W (per-lane fields) -> warp sums -> the lanes that own the pairs
+    if constexpr (PK) {
+#pragma unroll
+      for (int f = 0; f < TP::NF; ++f) {
+        const FieldRec F = TP::field(f);
+        const uint32_t v = __reduce_add_sync(0xffffffffu, (W[F.w] >> F.sh) & ((1u << F.bits) - 1u));
+        if (F.target == 3) {
+          add_if_lane1(acc_daily, F.p0, lane, v);
+        } else {
+#pragma unroll
+          for (int r = 0; r < PR; ++r) {
+            if (F.p0 + F.len <= 32 * r || F.p0 >= 32 * (r + 1)) continue;
+            const bool mine = (unsigned)(lane_r[r] - (int)F.p0) < (unsigned)F.len;
+            if (F.target != 1) acc_cnt[r] += mine ? v : 0u;
+            if (F.target != 0) acc_suc[r] += mine ? v : 0u;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < TP::NW; ++j) W[j] = 0;
+      held = 0;
+    }
+  };
+
   auto flush = [&](int64_t cell) {
 #pragma unroll
     for (int r = 0; r < PR; ++r) {
       const int p = r * 32 + lane;
-      if (p < P.n_pairs && acc_cnt[r]) {
-        uint32_t* dst = P.state_daily + ((size_t)cell * P.n_pairs + p) * 2;
+      if (p < n_pairs && acc_cnt[r]) {
+        uint32_t* dst = P.state_daily + ((size_t)cell * n_pairs + p) * 2;
         if (acc_suc[r]) atomicAdd(dst, acc_suc[r]);
         atomicAdd(dst + 1, acc_cnt[r]);
       }
@@ -143,21 +211,38 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
     if (lane == 0) nx = atomicAdd(P.work_counter, 1ull);
     chunk = G + (int64_t)__shfl_sync(0xffffffffu, nx, 0);
   }
+  bool fresh = false;       // the tile about to be simulated is the first one this warp sees of cell c
   if (t0 >= c_end) {        // not a continuation: last cell with tile_off[c] <= t0 (cells without fish have empty ranges)
     int64_t lo = c < 0 ? 0 : c, hi = P.n_cells;
     while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (P.tile_off[mid] <= t0) lo = mid; else hi = mid; }
     c = lo; c_begin = P.tile_off[c]; c_end = P.tile_off[c + 1];
+    fresh = true;
   }
-  for (int64_t t = t0; t < t1; ++t) {
-    while (t >= c_end) { ++c; c_begin = c_end; c_end = P.tile_off[c + 1]; }
-    if (c != cur_cell) {
-      if (cur_cell >= 0) flush(cur_cell);
+  // 32-bit bookkeeping inside the chunk: tiles left in the current cell, index of the tile's first fish
+  const int64_t room = c_end - t0;
+  int left = room < (int64_t)(1 << 30) ? (int)room : (1 << 30);
+  int fish_base = (int)(t0 - c_begin) * 32;
+  const int nt = (int)(t1 - t0);
+  for (int it = 0; it < nt; ++it, --left, fish_base += 32) {
+    if (left == 0) {
+      do { ++c; c_begin = c_end; c_end = P.tile_off[c + 1]; } while (c_end == c_begin);
+      const int64_t rm = c_end - c_begin;
+      left = rm < (int64_t)(1 << 30) ? (int)rm : (1 << 30);
+      fish_base = 0;
+      fresh = true;
+    }
+    if (fresh) {
+      fresh = false;
+      if (cur_cell >= 0) {
+        if (PK && held) drain();
+        flush(cur_cell);
+      }
       cur_cell = c;
       n_c = P.cell_n[c];
       const uint64_t cid = P.cell_id[c];
       cid_lo = (uint32_t)cid; cid_hi = (uint32_t)(cid >> 32);
       const int s = P.cell_species[c];
-      if (s < n_species_staged) {
+      if (s < n_sp) {
         const float* q = s_species + s * SPW;
         sp_ls = q[0]; sp_ll = q[1]; sp_lsc = q[2]; sp_lm = q[3]; sp_lsd = q[4]; sp_mode = (int)q[5];
         sp_wr = q[6]; sp_uc = q[7]; sp_d1 = q[8]; sp_dd = q[9] - q[8]; sp_b0 = q[10] * 1.44269504f; sp_b1 = q[11];
@@ -172,16 +257,19 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         cur_day = d;
         __syncwarp();
         const double* cdf = P.edge_cdf + (size_t)d * P.n_edges;
-        const uint8_t* st = P.node_stay + (size_t)d * P.n_nodes;
-        for (int i = lane; i < P.n_nodes * stride; i += 32) {
+        const uint8_t* st = P.node_stay + (size_t)d * n_nodes;
+        for (int i = lane; i < n_nodes * crow; i += 32) {
+          const int v = i / crow, e = i - v * crow;
+          const NodeRec nr = P.nodes[v];
+          s_cdf[i] = (e < (int)nr.deg && !st[v]) ? (float)cdf[nr.edge_off + e] : 2.0f;
+        }
+        for (int i = lane; i < n_nodes * stride; i += 32) {
           const int v = i / stride, e = i - v * stride;
           const NodeRec nr = P.nodes[v];
-          const bool real = e < (int)nr.deg && !st[v];
-          s_cdf[i] = real ? (float)cdf[nr.edge_off + e] : 2.0f;
-          s_dst[i] = real ? P.edge_dst[nr.edge_off + e] : (uint8_t)v;
+          s_dst[i] = (e < (int)nr.deg && !st[v]) ? P.edge_dst[nr.edge_off + e] : (uint8_t)v;
         }
-        const double* uc = P.unit_coef + (size_t)d * P.n_units * STRYKE_UNIT_COEF_W;
-        for (int u = lane; u < P.n_units; u += 32) {
+        const double* uc = P.unit_coef + (size_t)d * n_units * STRYKE_UNIT_COEF_W;
+        for (int u = lane; u < n_units; u += 32) {
           const double* r = uc + u * STRYKE_UNIT_COEF_W;
           const double lnd = r[0] * r[1] / r[2];
           const bool kap = r[4] != 0.0 || r[5] != 0.0;
@@ -192,13 +280,13 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         __syncwarp();
       }
     }
-    const int fish = (int)((t - c_begin) * 32 + lane);
+    const int fish = fish_base + lane;
     const bool active = fish < n_c;
 
     // ---- Philox: counter (fish, cell id, block), key = seed (constant bank) -------------------------------------
     uint32_t w[4];
     int cur_b = 0;
-    Philox::block((uint32_t)fish, cid_lo, cid_hi, 0u, P.seed_lo, P.seed_hi, w);
+    Philox::block_ks((uint32_t)fish, cid_lo, cid_hi, 0u, P.ks, w);
     auto word = [&](int i) -> uint32_t { return (i & 2) ? ((i & 1) ? w[3] : w[2]) : ((i & 1) ? w[1] : w[0]); };
 
     // ---- (2) length: words 0, 1 ----------------------------------------------------------------------------------
@@ -208,7 +296,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
     else L = fabsf(fmaf(sp_lsd, z, sp_lm)) * (1.f / 12.f);
     const float blocked_w = L * sp_wr;
 
-    int loc = P.start_node;
+    int loc = start_node;
     bool alive = active;
     int best_rank = 255;
     bool ent_surv = false;
@@ -220,9 +308,14 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
       if (mv.need & NEED_TRIVIAL) {
         // one a-priori node, survival 1.0, at most one successor, no 'U' in its name: every live fish is here,
         // survives (stryke.py:3210 with rate 1.0) and moves to the only successor (or stays, stryke.py:1849-1855)
-        const uint32_t pc = __popc(__ballot_sync(0xffffffffu, alive));
+        if constexpr (PK) {
+          const LevelTally LT = TP::tally(k);           // one field for a whole run of trivial levels
+          if (LT.kind == 1) W[LT.wc] += alive ? (1u << LT.bc) : 0u;
+        } else {
+          const uint32_t pc = __popc(__ballot_sync(0xffffffffu, alive));
 #pragma unroll
-        for (int r = 0; r < PR; ++r) add_if_lane(acc_cnt[r], acc_suc[r], mv.level_begin, lane_r[r], pc, pc);
+          for (int r = 0; r < PR; ++r) add_if_lane(acc_cnt[r], acc_suc[r], mv.level_begin, lane_r[r], pc, pc);
+        }
         if (k < n_moves - 1) loc = alive ? (int)s_dst[(int)mv.pad * stride] : loc;
         continue;
       }
@@ -233,7 +326,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
       float rate = alive ? __uint_as_float(nd.x) : 0.f;
       if (mv.need & (NEED_CAUSE | NEED_DICE)) {          // refill site A (uniform): this level owns a fresh block,
         cur_b = mv.slot_base >> 2;                       // rR, depth, cause, dice at fixed positions 0..3
-        Philox::block((uint32_t)fish, cid_lo, cid_hi, (uint32_t)cur_b, P.seed_lo, P.seed_hi, w);
+        Philox::block_ks((uint32_t)fish, cid_lo, cid_hi, (uint32_t)cur_b, P.ks, w);
       }
       if (mv.need & NEED_CAUSE) {                        // this level has turbine nodes (uniform)
         const float u_rr = u_co<float>(w[0]);
@@ -260,7 +353,8 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         }
         const float a2 = imp * strike, a3 = a2 * baro;
         rate = turb ? a3 : rate;
-        const uint32_t code = u_cau >= imp ? 1u : u_cau >= a2 ? (1u << 8) : u_cau >= a3 ? (1u << 16) : 0u;
+        constexpr int CB = PK ? 10 : 8;                                      // width of the per-lane cause counters
+        const uint32_t code = u_cau >= imp ? 1u : u_cau >= a2 ? (1u << CB) : u_cau >= a3 ? (1u << (2 * CB)) : 0u;
         cz += turb ? code : 0u;
       }
       bool surv;
@@ -268,14 +362,34 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
       else surv = alive && rate >= 1.0f;
 
       // ---- (6) State_Daily: lane p owns pair p ---------------------------------------------------------------------
-      const int key_c = prev_alive ? loc : 0x1ff, key_s = surv ? loc : 0x1ff;
-#pragma unroll(TP::UNROLL_P)
-      for (int p = mv.level_begin; p < mv.level_end; ++p) {                  // uniform bounds
-        const int node = TP::pair_node(FT, p);
-        const uint32_t pc = __popc(__ballot_sync(0xffffffffu, key_c == node));
-        const uint32_t ps = __popc(__ballot_sync(0xffffffffu, key_s == node));
+      if constexpr (PK) {
+        const LevelTally LT = TP::tally(k);
+        if (LT.kind == 2) {
+          W[LT.wc] += prev_alive ? (1u << LT.bc) : 0u;
+          W[LT.ws] += surv ? (1u << LT.bs) : 0u;
+        } else if (LT.kind == 3) {
+          const uint32_t i6 = pk >> 27;                                      // 6 * local index of this lane's node
+          W[LT.wc] += prev_alive ? ((1u << LT.bc) << i6) : 0u;
+          W[LT.ws] += surv ? ((1u << LT.bs) << i6) : 0u;
+        } else {
+          const uint32_t one = 1u << (pk >> 27);
+          const int wi = (int)((pk >> 24) & 7u);
 #pragma unroll
-        for (int r = 0; r < PR; ++r) add_if_lane(acc_cnt[r], acc_suc[r], p, lane_r[r], pc, ps);
+          for (int j = 0; j < LT.nwl; ++j) {
+            W[LT.wc + j] += (prev_alive && wi == j) ? one : 0u;
+            W[LT.ws + j] += (surv && wi == j) ? one : 0u;
+          }
+        }
+      } else {
+        const int key_c = prev_alive ? loc : 0x1ff, key_s = surv ? loc : 0x1ff;
+#pragma unroll(TP::UNROLL_P)
+        for (int p = mv.level_begin; p < mv.level_end; ++p) {                // uniform bounds
+          const int node = TP::pair_node(FT, p);
+          const uint32_t pc = __popc(__ballot_sync(0xffffffffu, key_c == node));
+          const uint32_t ps = __popc(__ballot_sync(0xffffffffu, key_s == node));
+#pragma unroll
+          for (int r = 0; r < PR; ++r) add_if_lane(acc_cnt[r], acc_suc[r], p, lane_r[r], pc, ps);
+        }
       }
       const bool newU = ((pk >> 3) & 1u) && active && (int)mv.lex < best_rank;
       best_rank = newU ? (int)mv.lex : best_rank;
@@ -283,35 +397,46 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
 
       // ---- (3) movement --------------------------------------------------------------------------------------------
       if (k < n_moves - 1) {
-        const int row = loc * stride;
         int j = 0;
         if (mv.need & NEED_ROUTE) {
           const int sr = mv.slot_route;
           if ((sr >> 2) != cur_b) {                                          // refill site B (uniform)
             cur_b = sr >> 2;
-            Philox::block((uint32_t)fish, cid_lo, cid_hi, (uint32_t)cur_b, P.seed_lo, P.seed_hi, w);
+            Philox::block_ks((uint32_t)fish, cid_lo, cid_hi, (uint32_t)cur_b, P.ks, w);
           }
           const float u = u_co<float>(word(sr & 3));
-          const int md = mv.max_deg;
+          // searchsorted(cdf, u, 'right') = number of thresholds <= u; rows are whole float4s padded with 2.0
+          const float4* rowq = reinterpret_cast<const float4*>(s_cdf) + loc * (crow >> 2);
+          const int groups = ((int)mv.max_deg - 1 + 3) >> 2;
 #pragma unroll(TP::UNROLL_P)
-          for (int e = 0; e < md - 1; ++e) j += (s_cdf[row + e] <= u) ? 1 : 0;   // searchsorted(cdf, u, 'right')
+          for (int g = 0; g < groups; ++g) {
+            const float4 q = rowq[g];
+            j -= le_mask(q.x, u) + le_mask(q.y, u) + le_mask(q.z, u) + le_mask(q.w, u);
+          }
         }
-        loc = surv ? (int)s_dst[row + j] : loc;
+        loc = surv ? (int)s_dst[loc * stride + j] : loc;
       }
       alive = surv;
     }
     const bool ent = active && best_rank < 255;
-    const uint32_t b_ent = __ballot_sync(0xffffffffu, ent);
-    const uint32_t b_sur = __ballot_sync(0xffffffffu, ent && ent_surv);
-    uint32_t r_imp = 0, r_bld = 0, r_bar = 0;
-    if (__ballot_sync(0xffffffffu, cz != 0)) {
-      r_imp = __reduce_add_sync(0xffffffffu, cz & 0xffu);
-      r_bld = __reduce_add_sync(0xffffffffu, (cz >> 8) & 0xffu);
-      r_bar = __reduce_add_sync(0xffffffffu, (cz >> 16) & 0xffu);
+    if constexpr (PK) {
+      W[TP::W_ES] += ent ? (ent_surv ? (0x41u << TP::B_ES) : (1u << TP::B_ES)) : 0u;
+      W[TP::W_CAUSE] += cz;
+      if (++held == TP::HOLD) drain();
+    } else {
+      const uint32_t n_ent = __popc(__ballot_sync(0xffffffffu, ent));
+      const uint32_t n_sur = __popc(__ballot_sync(0xffffffffu, ent && ent_surv));
+      add_if_lane1(acc_daily, 0, lane, n_ent);
+      add_if_lane1(acc_daily, 1, lane, n_sur);
+      if (__ballot_sync(0xffffffffu, cz != 0)) {
+        add_if_lane1(acc_daily, 2, lane, __reduce_add_sync(0xffffffffu, cz & 0xffu));
+        add_if_lane1(acc_daily, 3, lane, __reduce_add_sync(0xffffffffu, (cz >> 8) & 0xffu));
+        add_if_lane1(acc_daily, 4, lane, __reduce_add_sync(0xffffffffu, (cz >> 16) & 0xffu));
+      }
     }
-    acc_daily += lane == 0 ? __popc(b_ent) : lane == 1 ? __popc(b_sur) : lane == 2 ? r_imp : lane == 3 ? r_bld : lane == 4 ? r_bar : 0u;
   }
   }
+  if (PK && held) drain();
   if (cur_cell >= 0) flush(cur_cell);
 }
 
