@@ -28,8 +28,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-# Algorithmic lane-ops per fish-passage (derivation: DESIGN.md §4 "Roofline").
-ALGO_LANE_OPS = {"c2": 350.0, "c3": 350.0, "c5": 1250.0}
+# Algorithmic lane-ops per fish-passage = instructions of the best known schedule of the algorithm (DESIGN.md §4
+# "Roofline"): what the specialised kernel executes per fish (ncu, profiles/r01_inst_per_fish.json).  SURVEY.md §8d
+# estimated 500 (C2) / 1900 (C5) assuming 4 Philox blocks and atan/sin/cos per fish; the kernels need 2 blocks and no
+# trigonometry, so the survey figure would put the fraction above 1.
+ALGO_LANE_OPS = {"c2": 243.0, "c3": 243.0, "c5": 942.0}
 
 
 def workload_project(name, n_fish, iterations, days):
@@ -269,20 +272,18 @@ def main():
     achieved = per_gpu_rate * algo
     traffic = None
     prof = os.path.join(ROOT, "profiles", "r01_passage_metrics.json")
-    inst_per_fish = None
     if os.path.isfile(prof):
         with open(prof) as fh:
-            pj = json.load(fh)
-        traffic = pj.get("dram_bytes_per_launch")
-        inst_per_fish = pj.get("thread_inst_per_fish")
+            traffic = json.load(fh).get("dram_bytes_per_launch")
     roofline = {"bound": "issue", "achieved": achieved / 1e12, "peak": peak_ops / 1e12, "unit": "Tlane-op/s",
                 "frac": achieved / peak_ops, "traffic": traffic,
-                "note": "neither HBM nor tensor binds this path (SURVEY.md §8d): bound = SM instruction issue (INT32 Philox + FP32/MUFU). "
-                        f"achieved = {algo:.0f} algorithmic lane-ops per fish-passage (DESIGN.md §4) x fish-passages/s per GPU; peak = lane-ops/s of "
+                "note": "neither HBM nor tensor binds this path (SURVEY.md §8d): bound = SM instruction issue (INT32 Philox on the "
+                        "half-rate ALU pipe + FP32/MUFU). "
+                        f"achieved = {algo:.0f} algorithmic lane-ops per fish-passage (DESIGN.md §4: the instruction count of the best known "
+                        "schedule, = what the specialised kernel executes per fish under ncu) x fish-passages/s per GPU over the step's "
+                        "CUDA-event time (the passage kernel is > 99.9 % of the step, profiles/r01_launch_shares.md); peak = lane-ops/s of "
                         "16 independent FFMA chains per thread at full occupancy (1 warp instruction per scheduler per cycle) measured live by "
                         "stryke_b200_calibrate_issue on this GPU; traffic = DRAM bytes per launch (ncu)",
-                "executed_thread_inst_per_fish_ncu": inst_per_fish,
-                "issue_utilisation_executed": (per_gpu_rate * inst_per_fish / peak_ops) if inst_per_fish and args.workload == "c2" else None,
                 "hbm": {"achieved_GBps": (plan.n_cells * (4 + 20 + plan.n_pairs * 8) * 2) / (ms_total / args.steps * 1e-3) / 1e9,
                         "peak_GBps": _measured_peak()}}
 
