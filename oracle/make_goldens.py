@@ -28,6 +28,10 @@ CASES = {
     "c3_population": ("c3_population", dict(n_species=4, iterations=2, days=8), 6,
                       {"Ambloplites": "Centrarchidae", "Micropterus": "Centrarchidae", "Lepomis": "Centrarchidae"}),
     "c2_low_flow": ("c2_facility", dict(n_fish=120, iterations=1, days=3, curr_Q=600.0), 7, {}),
+    # the reference's own complex-network example workbook (tables extracted by oracle/extract_example.py)
+    "cabot_station": ("cabot_station", dict(iterations=2, days=24, seed=0), 8, {"Micropterus": "Centrarchidae"}),
+    "cabot_station_fish": ("cabot_station", dict(iterations=1, days=4, seed=3, median_Q=7000.0, fish=300.0), 9,
+                           {"Micropterus": "Centrarchidae"}),
 }
 
 

@@ -75,7 +75,9 @@ def _normalize_facility_flow_columns(df):
     """stryke.py:197-209."""
     if df is None or df.empty:
         return df
-    ren = {s: d for s, d in {"Min Op Flow": "Min_Op_Flow", "Env Flow": "Env_Flow", "Bypass Flow": "Bypass_Flow"}.items()
+    # 'Exc_Rack_Spacing' is how the reference's example workbooks label the column stryke.py:447 reads as 'Rack Spacing'
+    ren = {s: d for s, d in {"Min Op Flow": "Min_Op_Flow", "Env Flow": "Env_Flow", "Bypass Flow": "Bypass_Flow",
+                             "Exc_Rack_Spacing": "Rack Spacing"}.items()
            if s in df.columns and d not in df.columns}
     return df.rename(columns=ren) if ren else df
 
@@ -110,20 +112,20 @@ class simulation:
         from . import xlsx
         self.wks_dir = os.path.join(proj_dir, wks)
         book = xlsx.Workbook(self.wks_dir)
-        self.nodes = book.frame("Nodes", "B:D", skiprows=9)
-        self.edges = book.frame("Edges", "B:D", skiprows=9)
+        self.nodes = book.frame("Nodes", "B:D", skiprows=9, expect=("Location", "Surv_Fun"))
+        self.edges = book.frame("Edges", "B:D", skiprows=9, expect=("_from", "_to"))
         self.surv_fun_df = self.nodes[["Location", "Surv_Fun"]].set_index("Location")
         self.surv_fun_dict = self.surv_fun_df.to_dict("index")
         if len(self.nodes) > 1:
             self.max_river_node = self._max_river_node(self.nodes.Location.values)
-        self.unit_params = book.frame("Unit Params", "B:Y", skiprows=4)
+        self.unit_params = book.frame("Unit Params", "B:Y", skiprows=4, expect=("Facility", "Unit"))
         # the reference indexes by 'Unit' and then reads row['Unit'] (stryke.py:389 vs :2724);
         # keep the column so run() works for spreadsheet projects
         self.unit_params.set_index("Unit", inplace=True, drop=False)
-        self.facility_params = _normalize_facility_flow_columns(book.frame("Facilities", "B:I", skiprows=3))
+        self.facility_params = _normalize_facility_flow_columns(book.frame("Facilities", "B:I", skiprows=3, expect=("Facility", "Scenario")))
         self.facility_params.set_index("Facility", inplace=True)
         self.flow_cap = self.unit_params.groupby("Facility")["Qcap"].sum()
-        self.flow_scenarios_df = book.frame("Flow Scenarios", "B:I", skiprows=5, dtype={"Gage": str})
+        self.flow_scenarios_df = book.frame("Flow Scenarios", "B:I", skiprows=5, dtype={"Gage": str}, expect=("Scenario", "Flow"))
         self.input_hydrograph_df = book.frame("Hydrology", "B:C", skiprows=3, dtype={"Date": str, "Discharge": float})
         meta = book.frame("Background and Metadata", None, skiprows=0)
         self.output_units = meta.iat[13, 1]
@@ -139,13 +141,13 @@ class simulation:
             self.facility_params["Rack Spacing"] = self.facility_params["Rack Spacing"] * 0.0328084
         else:
             self.facility_params["Rack Spacing"] = self.facility_params["Rack Spacing"] / 12.0
-        self.operating_scenarios_df = book.frame("Operating Scenarios", "B:I", skiprows=8)
+        self.operating_scenarios_df = book.frame("Operating Scenarios", "B:I", skiprows=8, expect=("Scenario", "Facility", "Unit"))
         self.operating_scenarios_df["OpScenario"] = (self.operating_scenarios_df.Scenario.astype(str) + " "
                                                      + self.operating_scenarios_df.Unit.astype(str))
         self.ops_scens = None
         self.flow_scenarios = self.flow_scenarios_df["Scenario"].unique()
         self.op_scenarios = self.operating_scenarios_df["Scenario"].unique()
-        self.pop = book.frame("Population", "B:V", skiprows=11)
+        self.pop = book.frame("Population", "B:V", skiprows=11, expect=("Species", "Scenario"))
         self.proj_dir, self.output_name = proj_dir, output_name
         self.hdf_path = os.path.join(self.proj_dir, "%s.h5" % self.output_name)
         with open_store(self.hdf_path, mode="w") as hdf:
@@ -602,6 +604,31 @@ class simulation:
     # ----------------------------------------------------------------------------------------------------------
     # hydrograph (stryke.py:2154-2307; USGS download is out of scope — no network)
     # ----------------------------------------------------------------------------------------------------------
+    def get_USGS_hydrograph(self, gage, prorate, flow_year):
+        """Daily mean flow of a USGS gage for one year (stryke.py:2094-2152): columns datetimeUTC, DAvgFlow,
+        DAvgFlow_prorate, year, month.  The reference downloads it (hydrofunctions NWIS 'dv' service); this build has no
+        network client, so the series comes from ``<gage>_<year>.csv`` (columns ``datetimeUTC, DAvgFlow``) in the
+        directory named by ``self.usgs_cache_dir`` / ``$STRYKE_USGS_CACHE``, or from ``self.usgs_provider(gage, year)``."""
+        df = None
+        provider = getattr(self, "usgs_provider", None)
+        if provider is not None:
+            df = provider(str(gage), int(flow_year))
+        else:
+            cache = getattr(self, "usgs_cache_dir", None) or os.environ.get("STRYKE_USGS_CACHE")
+            path = os.path.join(cache, f"{gage}_{int(flow_year)}.csv") if cache else None
+            if path and os.path.isfile(path):
+                df = pd.read_csv(path)
+        if df is None:
+            raise RuntimeError(f"USGS gage download ({gage}, {flow_year}) needs network access; supply the hydrograph in "
+                               "the Hydrology sheet / hydrograph_file, or a <gage>_<year>.csv under $STRYKE_USGS_CACHE.")
+        df = df[["datetimeUTC", "DAvgFlow"]].copy()
+        df["DAvgFlow_prorate"] = df.DAvgFlow * prorate
+        df["datetimeUTC"] = pd.to_datetime(df.datetimeUTC)
+        df["year"] = pd.DatetimeIndex(df["datetimeUTC"]).year
+        df = df[df.year == flow_year].copy()
+        df["month"] = pd.DatetimeIndex(df["datetimeUTC"]).month
+        return df
+
     def create_hydrograph(self, discharge_type, scen, scen_months, flow_scenarios_df, fixed_discharge=None):
         flow_df = pd.DataFrame()
         scen_df = flow_scenarios_df[flow_scenarios_df.Scenario == scen]
@@ -611,8 +638,13 @@ class simulation:
             prorate = scen_df.at[scen_df.index[0], "Prorate"]
             flow_year = scen_df.at[scen_df.index[0], "FlowYear"]
             if sum(ch.isdigit() for ch in gage) > 1:
-                raise RuntimeError(f"USGS gage download ({gage}) needs network access; supply the hydrograph in the "
-                                   "Hydrology sheet / hydrograph_file instead.")
+                df = self.get_USGS_hydrograph(gage, prorate, flow_year)
+                for m in scen_months:
+                    flow_df = pd.concat([flow_df, df[df.month == m]])
+                if flow_df.empty:
+                    raise ValueError(f"ERROR: Hydrograph is empty after filtering for scenario '{scen}'.\n"
+                                     f"Requested months: {scen_months}, year: {flow_year}")
+                return flow_df
             df = self.input_hydrograph_df.copy()
             if "Discharge" in df.columns and "Date" in df.columns:
                 df["DAvgFlow_prorate"] = df["Discharge"] * prorate

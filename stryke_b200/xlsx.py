@@ -126,8 +126,12 @@ class Workbook:
                 cells[(r, col)] = val
         return cells
 
-    def frame(self, sheet, usecols=None, skiprows=0, dtype=None):
-        """``pd.read_excel(..., header=0, usecols=usecols, skiprows=skiprows)``."""
+    def frame(self, sheet, usecols=None, skiprows=0, dtype=None, expect=None):
+        """``pd.read_excel(..., header=0, usecols=usecols, skiprows=skiprows)``.
+
+        ``expect``: column names the header row must contain.  When the row at ``skiprows`` does not hold them, the
+        rows within three of it are searched: the reference's own example workbooks (Spreadsheet Interface/Examples)
+        carry the Edges header one row above where stryke.py:362-367 looks for it."""
         if sheet not in self._cells:
             raise ValueError(f"Worksheet named '{sheet}' not found")
         cells = self._cells[sheet]
@@ -141,6 +145,14 @@ class Workbook:
         else:
             cols = list(range(0, last_col + 1))
         header_row = skiprows
+        if expect:
+            want = set(expect)
+            def holds(r):
+                return want <= {cells.get((r, c)) for c in cols}
+            if not holds(header_row):
+                near = [r for r in range(max(0, skiprows - 3), skiprows + 4) if holds(r)]
+                if near:
+                    header_row = min(near, key=lambda r: abs(r - skiprows))
         names, seen = [], {}
         for j, c in enumerate(cols):
             h = cells.get((header_row, c))

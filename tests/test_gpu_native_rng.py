@@ -31,7 +31,8 @@ def oracle_cells(prj, n_cells, seed=3):
 @pytest.mark.parametrize("fixture,kw", [("c2_facility", dict(n_fish=400000, iterations=2, days=2)),
                                         ("c2_facility", dict(n_fish=300000, iterations=1, days=2, baro=True)),
                                         ("c5_cascade", dict(n_fish=150000, iterations=1, days=2)),
-                                        ("c4_barotrauma", dict(n_fish=200000, iterations=1, days=2))])
+                                        ("c4_barotrauma", dict(n_fish=200000, iterations=1, days=2)),
+                                        ("cabot_station", dict(iterations=1, days=2, seed=3, median_Q=7000.0, fish=200000.0))])
 def test_route_and_survival_counts_match_oracle_distribution(fixture, kw, precision):
     prj = getattr(fixtures, fixture)(**kw)
     sim, plan = G.make_plan(prj, fixture)
@@ -172,7 +173,10 @@ def test_full_size_conservation_properties(fixture, kw):
                                         ("c5_cascade", dict(n_fish=100000, iterations=2, days=2)),
                                         ("c4_barotrauma", dict(n_fish=100000, iterations=2, days=2, habitat="Benthic")),
                                         ("c1_single_unit", dict(iterations=50, days=40, fish=3000.0)),
-                                        ("c3_population", dict(n_species=4, iterations=60, days=10))])
+                                        ("c3_population", dict(n_species=4, iterations=60, days=10)),
+                                        # 13 nodes in one level: the multi-word packed tallies of the specialised kernel
+                                        ("cabot_station", dict(iterations=2, days=6, seed=3, median_Q=7000.0, fish=120000.0)),
+                                        ("cabot_station", dict(iterations=40, days=30, seed=1))])
 def test_fast_kernel_equals_general_kernel(fixture, kw):
     """passage_fast_kernel (throughput variant) vs passage_kernel<float, native> (the template that is validated
     bit-for-bit against the reference in injected mode): same Philox words, same fp32 formulas -> identical tallies."""

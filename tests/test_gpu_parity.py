@@ -59,7 +59,8 @@ def test_fp64_injected_replay_matches_reference_bit_exact(case):
     assert n_checked > 0
 
 
-@pytest.mark.parametrize("case", ["c2_kaplan_francis", "c2_barotrauma", "c4_propeller_baro", "c5_cascade", "c1_single_unit"])
+@pytest.mark.parametrize("case", ["c2_kaplan_francis", "c2_barotrauma", "c4_propeller_baro", "c5_cascade", "c1_single_unit",
+                                  "cabot_station_fish"])
 @pytest.mark.parametrize("precision,tol", [(64, 1e-6), (32, 1e-4)])
 def test_per_fish_probabilities_within_tolerance(case, precision, tol):
     """Strike and barotrauma survival AND mortality probabilities of every evaluated (fish, move)."""
@@ -89,7 +90,7 @@ def test_per_fish_probabilities_within_tolerance(case, precision, tol):
     assert seen > 0
 
 
-@pytest.mark.parametrize("case", ["c2_kaplan_francis", "c2_barotrauma", "c5_cascade"])
+@pytest.mark.parametrize("case", ["c2_kaplan_francis", "c2_barotrauma", "c5_cascade", "cabot_station_fish"])
 def test_fp32_injected_tallies_statistically_identical(case):
     """fp32 arithmetic with the reference's uniforms: a survival flag can only flip when a dice lands within one
     fp32 ulp of the rate, so tallies agree up to a handful of fish."""

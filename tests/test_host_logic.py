@@ -166,3 +166,36 @@ def test_hydrograph_sheet_filter_and_errors():
         sim.create_hydrograph("hydrograph", "S", [9], fs)
     with pytest.raises(RuntimeError, match="network"):
         sim.create_hydrograph("hydrograph", "S", [3], pd.DataFrame([{"Scenario": "S", "Gage": "01170500", "Prorate": 1.0, "FlowYear": 2023}]))
+
+
+# ---- the host table builder against the reference's own routing decisions ----------------------------------------------
+from golden_util import CASES as _GOLDEN_CASES, Golden as _Golden
+
+
+@pytest.mark.parametrize("case", _GOLDEN_CASES)
+def test_day_tables_reproduce_the_reference_routing_probabilities(case):
+    """tables.build_days (what the kernels read) vs the (successors, p) pairs captured at the reference's
+    ``np.random.choice`` call sites (stryke.py:2058) while the goldens were recorded: same successor order, the
+    normalised cumulative probabilities np.random.choice would search, bit for bit."""
+    import gpu_util as G
+    g = _Golden(case)
+    sim, plan = G.make_plan(g.prj, case)
+    fac, days = plan.fac, plan.days
+    names = list(plan.node_names) if hasattr(plan, "node_names") else list(g.model.nodes)
+    idx = {nm: i for i, nm in enumerate(names)}
+    ref_idx = G.reference_cell_index(plan)
+    engine_of = {int(r): c for c, r in enumerate(ref_idx)}
+    checked = 0
+    for rec in g.meta["routing"]:
+        c = engine_of[rec["cell"]]
+        d = int(plan.cell_day[c])
+        v = idx[rec["location"]]
+        e0, e1 = int(fac.edge_off[v]), int(fac.edge_off[v + 1])
+        assert [names[int(x)] for x in fac.edge_dst[e0:e1]] == rec["locs"]
+        assert not days.node_stay[d, v]
+        p = np.array(rec["probs"], dtype=np.float64)
+        want = np.cumsum(p)
+        want = want / want[-1]
+        assert np.array_equal(days.edge_cdf[d, e0:e1], want), (rec["location"], days.edge_cdf[d, e0:e1], want)
+        checked += 1
+    assert checked == len(g.meta["routing"])
