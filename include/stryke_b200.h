@@ -187,8 +187,12 @@ int stryke_b200_baro_survival(int64_t n, const double* fish_depth_ft, double tai
 /* Philox4x32-10 block function evaluated on the device (for known-answer tests). */
 int stryke_b200_philox(int64_t n, const uint32_t* ctr4, const uint32_t* key2, int device, uint32_t* out4);
 
-/* Issue-rate calibration micro-kernel: lane-ops/s of an independent IMAD/LOP3 stream at full occupancy. */
+/* Issue-rate calibration micro-kernel: lane-ops/s of 16 independent FFMA chains per thread at full occupancy. */
 int stryke_b200_calibrate_issue(int device, void* stream, double* lane_ops_per_s, double* ms);
+
+/* Means of n_boot resamples (with replacement, len n) of data[n]: the loop of bootstrap_mean_ci (Stryke/stryke.py:155-159)
+ * that summary() (stryke.py:3520-4101) runs a few hundred times.  Host pointers; indices from Philox4x32-10 keyed by seed. */
+int stryke_b200_bootstrap_means(const double* data, int64_t n, int32_t n_boot, uint64_t seed, int32_t device, double* means);
 
 #ifdef __cplusplus
 }

@@ -112,7 +112,7 @@ def lib():
 EXPORTS = ["stryke_b200_last_error", "stryke_b200_abi_version", "stryke_b200_device_count", "stryke_b200_launch_count",
            "stryke_b200_run", "stryke_b200_plan_create", "stryke_b200_plan_launch", "stryke_b200_plan_kernel", "stryke_b200_set_source_dir", "stryke_b200_jit_selftest", "stryke_b200_plan_set_seed", "stryke_b200_plan_status",
            "stryke_b200_plan_fetch_trace", "stryke_b200_plan_destroy", "stryke_b200_strike_survival",
-           "stryke_b200_baro_survival", "stryke_b200_philox", "stryke_b200_calibrate_issue"]
+           "stryke_b200_baro_survival", "stryke_b200_philox", "stryke_b200_calibrate_issue", "stryke_b200_bootstrap_means"]
 
 
 def check(rc):

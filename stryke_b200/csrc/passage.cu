@@ -1592,3 +1592,5 @@ int stryke_b200_calibrate_issue(int device, void* stream, double* lane_ops_per_s
 }
 
 }  // extern "C"
+
+#include "bootstrap.cuh"

@@ -223,5 +223,17 @@ def calibrate_issue(device=0, stream=0):
     return ops.value, ms.value
 
 
+def bootstrap_means(data, n_boot, seed=0, device=0):
+    """Means of ``n_boot`` resamples (with replacement) of ``data``, computed on the device (bootstrap_mean_ci's loop,
+    stryke.py:155-159)."""
+    a = np.ascontiguousarray(data, dtype=np.float64)
+    out = np.empty(int(n_boot), np.float64)
+    lib = _abi.lib()
+    lib.stryke_b200_bootstrap_means.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_int32, C.c_void_p]
+    _abi.check(lib.stryke_b200_bootstrap_means(_abi.ptr(a), a.size, int(n_boot), C.c_uint64(int(seed) & (2 ** 64 - 1)), int(device),
+                                               _abi.ptr(out)))
+    return out
+
+
 def launch_count():
     return int(_abi.lib().stryke_b200_launch_count())

@@ -32,16 +32,41 @@ def summarize_ci(series):
                       "upper_95_CI": np.percentile(series, 97.5)})
 
 
-def bootstrap_mean_ci(data, n_bootstrap=10000, ci=95, chunk_elems=1 << 24):
-    """Mean and bootstrap interval of ``data`` (stryke.py:143-162), resamples drawn ``chunk`` rows at a time."""
+#: CUDA ordinal the large bootstraps run on (set by summarize(); None = NumPy only)
+_DEVICE = None
+#: resampled values (len(data) * n_bootstrap) from which the device kernel is used.  Below it NumPy is faster than an
+#: upload + launch + download and reproduces the reference's MT19937 stream draw for draw.
+DEVICE_BOOTSTRAP_MIN = 1 << 23
+
+
+def _device_for(n, n_bootstrap):
+    return _DEVICE if (_DEVICE is not None and n * n_bootstrap >= DEVICE_BOOTSTRAP_MIN) else None
+
+
+def bootstrap_mean_ci(data, n_bootstrap=10000, ci=95, chunk_elems=1 << 24, result_used=True):
+    """Mean and bootstrap interval of ``data`` (stryke.py:143-162).
+
+    Small problems: NumPy, resamples drawn ``chunk`` rows at a time from the global MT19937 stream exactly as the
+    reference's loop consumes it.  Large problems (>= DEVICE_BOOTSTRAP_MIN resampled values, a GPU present): the
+    resampled means come from ``stryke_b200_bootstrap_means`` (Philox indices, seeded from ``np.random`` so that
+    ``np.random.seed`` still makes a run reproducible); a call whose result the caller discards
+    (``result_used=False``: the two draws at stryke.py:3832-3833) is then skipped altogether."""
     data = np.array(data)
     n = len(data)
-    means = np.empty(n_bootstrap)
-    rows = max(1, int(chunk_elems // max(n, 1)))
-    for lo in range(0, n_bootstrap, rows):
-        hi = min(n_bootstrap, lo + rows)
-        idx = np.random.randint(0, n, size=(hi - lo, n))
-        means[lo:hi] = data[idx].mean(axis=1)
+    dev = _device_for(n, n_bootstrap)
+    if dev is not None:
+        if not result_used:
+            return np.mean(data), np.nan, np.nan
+        from . import engine
+        seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 32)
+        means = engine.bootstrap_means(data.astype(np.float64), n_bootstrap, seed=seed, device=dev)
+    else:
+        means = np.empty(n_bootstrap)
+        rows = max(1, int(chunk_elems // max(n, 1)))
+        for lo in range(0, n_bootstrap, rows):
+            hi = min(n_bootstrap, lo + rows)
+            idx = np.random.randint(0, n, size=(hi - lo, n))
+            means[lo:hi] = data[idx].mean(axis=1)
     lower = np.percentile(means, (100 - ci) / 2)
     upper = np.percentile(means, 100 - (100 - ci) / 2)
     return np.mean(data), lower, upper
@@ -56,7 +81,27 @@ def _mean_std_ci(prob_values, n_bootstrap=2000):
     return mean, std, lcl, ucl
 
 
+def _gpu_ordinal(sim):
+    """The simulation's CUDA device when the library is built and a GPU is visible, else None."""
+    try:
+        from . import _abi
+        if _abi.lib().stryke_b200_device_count() > 0:
+            return int(getattr(sim, "device", 0))
+    except Exception:      # summary() of an existing store also works on a machine without the library / a GPU
+        pass
+    return None
+
+
 def summarize(sim):
+    global _DEVICE
+    _DEVICE = _gpu_ordinal(sim)
+    try:
+        return _summarize(sim)
+    finally:
+        _DEVICE = None
+
+
+def _summarize(sim):
     if not hasattr(sim, "wks_dir"):
         sim.wks_dir = None
     hdf_path = os.path.join(sim.proj_dir, "%s.h5" % sim.output_name)
@@ -179,8 +224,10 @@ def yearly_summary(daily):
             per_it = df.groupby("iteration")[["pop_size", "num_entrained"]].sum()
             probs = np.where(per_it["pop_size"] > 0, per_it["num_entrained"] / per_it["pop_size"].where(per_it["pop_size"] > 0, 1.0), 0.0)
             out["prob_entrainment"].append(float(np.mean(probs)) if len(probs) else 0.0)
-            bootstrap_mean_ci(df["num_entrained"])      # drawn by the reference (:3832-3833); results unused there too
-            bootstrap_mean_ci(df["num_mortalities"])
+            # drawn by the reference (:3832-3833) although nothing reads the results: kept for stream identity on the
+            # NumPy path, skipped on the device path
+            bootstrap_mean_ci(df["num_entrained"], result_used=False)
+            bootstrap_mean_ci(df["num_mortalities"], result_used=False)
             q = {T: 1 - 1 / T for T in (10, 100, 1000)}
             year = df.groupby(["iteration"])[["num_entrained", "num_mortalities"]].sum().apply(summarize_ci)
             for what, col in (("entrainment", "num_entrained"), ("mortality", "num_mortalities")):
