@@ -47,9 +47,7 @@ def run_sharded(plan_host, rank, world, device, *, precision=32, seed=0, max_dai
     lo, hi = shard_bounds(plan_host.n_cells, rank, world)
     dev = torch.device("cuda", device)
     C, P = plan_host.n_cells, plan_host.fac.n_pairs
-    full_n = torch.zeros(C, dtype=torch.int32, device=dev)
-    full_d = torch.zeros((C, _abi.DAILY_W), dtype=torch.int32, device=dev)
-    full_s = torch.zeros((C, P, 2), dtype=torch.int32, device=dev)
+    full_n, full_d, full_s, base = engine.tally_tensors(C, P, device, with_base=True)     # views of one flat buffer
     if hi > lo:
         plan = engine.Plan(plan_host.fac, plan_host.days, plan_host.species_table, plan_host.cell_day[lo:hi],
                            plan_host.cell_species[lo:hi], plan_host.cell_id[lo:hi], device=device, precision=precision,
@@ -58,5 +56,5 @@ def run_sharded(plan_host, rank, world, device, *, precision=32, seed=0, max_dai
         plan.launch(full_n[lo:hi], full_d[lo:hi], full_s[lo:hi])
         plan.status()
         plan.close()
-    allreduce_tallies([full_n, full_d, full_s], group)
+    allreduce_tallies([base], group)          # ONE collective for the three tensors
     return full_n, full_d, full_s

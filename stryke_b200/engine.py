@@ -72,6 +72,15 @@ class TraceBuffers:
         return t
 
 
+def tally_tensors(n_cells, n_pairs, device, with_base=False):
+    """(cell_n[C], daily[C,5], state_daily[C,P,2]) int32 views of one zeroed flat device buffer."""
+    import torch
+    C_, W, P = int(n_cells), _abi.DAILY_W, int(n_pairs)
+    base = torch.zeros(C_ * (1 + W + 2 * P), dtype=torch.int32, device=torch.device("cuda", device))
+    out = (base[:C_], base[C_:C_ * (1 + W)].view(C_, W), base[C_ * (1 + W):].view(C_, P, 2))
+    return (*out, base) if with_base else out
+
+
 @dataclass
 class CellResult:
     cell_n: np.ndarray        # (C,) int32 pop_size
@@ -146,13 +155,11 @@ class Plan:
         _abi.check(_abi.lib().stryke_b200_plan_create(C.byref(f), C.byref(d), C.byref(st), C.byref(cl), C.byref(o),
                                                       C.byref(self._h)))
 
-    def allocate(self):
-        """Tally tensors on the plan's device (torch is plumbing: device memory + streams + NCCL)."""
-        import torch
-        dev = torch.device("cuda", self.device)
-        return (torch.zeros(self.n_cells, dtype=torch.int32, device=dev),
-                torch.zeros((self.n_cells, _abi.DAILY_W), dtype=torch.int32, device=dev),
-                torch.zeros((self.n_cells, self.n_pairs, 2), dtype=torch.int32, device=dev))
+    def allocate(self, with_base=False):
+        """Tally tensors on the plan's device (torch is plumbing: device memory + streams + NCCL).  The three tensors
+        are views of ONE flat int32 buffer (``with_base=True`` also returns it), so a multi-GPU step finishes with a
+        single collective."""
+        return tally_tensors(self.n_cells, self.n_pairs, self.device, with_base)
 
     def launch(self, cell_n, daily, state_daily, stream=None):
         """Enqueue count -> scan -> passage on ``stream`` (int handle; default: torch's current stream)."""
