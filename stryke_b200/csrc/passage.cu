@@ -1231,7 +1231,17 @@ static std::string generate(const std::vector<MoveRec>& moves, const std::vector
                             const TallyPlan& T, const Dims& D) {
   std::ostringstream o;
   const int M = (int)moves.size(), P = (int)pairs.size();
-  o << "#define STRYKE_NVRTC 1\n#include \"passage_fast.cuh\"\nnamespace stryke {\nstruct SpecJit {\n"
+  o << "#define STRYKE_NVRTC 1\n";
+  if (const char* defs = getenv("STRYKE_B200_JIT_DEFINES")) {      // experiment switches: "A=1,B" -> #define A 1 / #define B
+    std::string d(defs), tok;
+    std::stringstream ss(d);
+    while (std::getline(ss, tok, ',')) {
+      if (tok.empty()) continue;
+      const size_t eq = tok.find('=');
+      o << "#define " << (eq == std::string::npos ? tok : tok.substr(0, eq) + " " + tok.substr(eq + 1)) << "\n";
+    }
+  }
+  o << "#include \"passage_fast.cuh\"\nnamespace stryke {\nstruct SpecJit {\n"
     << "  static constexpr bool kStatic = true;\n"
     << "  static constexpr int M = " << M << ", STRIDE = " << stride << ", UNROLL_K = " << (M <= 32 ? M : 1) << ", UNROLL_P = 8;\n"
     << "  static constexpr int N_NODES = " << D.n_nodes << ", N_UNITS = " << D.n_units << ", N_PAIRS = " << P

@@ -151,8 +151,9 @@ __device__ __forceinline__ float exp_approx(float x) { return ex2_approx(x * 1.4
 template <typename Real> __device__ __forceinline__ Real u_co(uint32_t x);   // [0,1)
 template <typename Real> __device__ __forceinline__ Real u_oc(uint32_t x);   // (0,1]
 // 23 random mantissa bits under exponent 0: v in [1, 2); one ALU op + one FADD, no integer->float conversion (XU pipe)
-template <> __device__ __forceinline__ float u_co<float>(uint32_t x) { return __uint_as_float((x >> 9) | 0x3f800000u) - 1.0f; }
-template <> __device__ __forceinline__ float u_oc<float>(uint32_t x) { return 2.0f - __uint_as_float((x >> 9) | 0x3f800000u); }
+__device__ __forceinline__ float mantissa_float(uint32_t x) { return __uint_as_float((x >> 9) | 0x3f800000u); }
+template <> __device__ __forceinline__ float u_co<float>(uint32_t x) { return mantissa_float(x) - 1.0f; }
+template <> __device__ __forceinline__ float u_oc<float>(uint32_t x) { return 2.0f - mantissa_float(x); }
 template <> __device__ __forceinline__ double u_co<double>(uint32_t x) { return (double)x * 2.3283064365386963e-10; }
 template <> __device__ __forceinline__ double u_oc<double>(uint32_t x) { return ((double)x + 1.0) * 2.3283064365386963e-10; }
 
