@@ -1288,6 +1288,14 @@ static const std::vector<char>* compile(const std::string& src, std::string* err
   Api& a = api();
   if (!a.ok) { *err = "libnvrtc not available"; return nullptr; }
   std::string fast, common;
+  if (g_source_dir.empty()) {      // default: csrc/ next to the shared library this code was loaded from
+    Dl_info info;
+    if (dladdr((const void*)&stryke_b200_abi_version, &info) && info.dli_fname) {
+      std::string so(info.dli_fname);
+      const size_t slash = so.rfind('/');
+      g_source_dir = (slash == std::string::npos ? std::string(".") : so.substr(0, slash)) + "/csrc";
+    }
+  }
   if (g_source_dir.empty() || !read_file(g_source_dir + "/passage_fast.cuh", &fast) || !read_file(g_source_dir + "/passage_common.cuh", &common)) {
     *err = "kernel sources not found (stryke_b200_set_source_dir)";
     return nullptr;
