@@ -1001,6 +1001,8 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
       const NodeRec& n0 = nodes[pnode[m.level_begin]];
       m.pad = pnode[m.level_begin];
       if (m.need == 0 && m.level_end - m.level_begin == 1 && !n0.hasU) m.need |= NEED_TRIVIAL;
+      for (int p = m.level_begin; p < m.level_end; ++p)
+        if (nodes[pnode[p]].hasU) m.need |= NEED_UCHECK;
       pl->fast.moves[k] = m;
     }
     for (int p = 0; p < f->n_pairs; ++p) pl->fast.pair_node[p] = pnode[p];
@@ -1169,36 +1171,42 @@ static TallyPlan plan_tally(const std::vector<MoveRec>& moves, const std::vector
   };
   int n_cause = 0;
   T.lv.assign((size_t)M, LevelTally{});
+  // passive level: nobody can die there (no dice <=> all nodes a-priori with survival >= 1), survivors = arrivals.
+  // Consecutive passive ONE-node levels form a run: the same fish are counted at each of them, one field serves all.
+  auto passive1 = [&](int k) { return !(moves[k].need & NEED_DICE) && moves[k].level_end - moves[k].level_begin == 1; };
   for (int k = 0; k < M; ++k) {
     const MoveRec& m = moves[k];
     const int n = m.level_end - m.level_begin;
+    const bool same = !(m.need & NEED_DICE);
     if (m.need & NEED_CAUSE) ++n_cause;
-    if (m.need & NEED_TRIVIAL) {
-      if (k > 0 && (moves[k - 1].need & NEED_TRIVIAL)) continue;          // inside a run: alive cannot change
+    if (passive1(k)) {
+      if (k > 0 && passive1(k - 1)) continue;                             // inside a run (kind 0)
       int run = 1;
-      while (k + run < M && (moves[k + run].need & NEED_TRIVIAL)) ++run;   // one pair per trivial level, consecutive
+      while (k + run < M && passive1(k + run)) ++run;                      // one pair per level, consecutive pair ids
       const auto a = alloc(1);
-      T.lv[k] = LevelTally{1, (uint8_t)a.first, (uint8_t)a.second, 0, 0, 1};
+      T.lv[k] = LevelTally{1, (uint8_t)a.first, (uint8_t)a.second, 0, 0, 1, 1};
       field(a.first, a.second, 6, 2, m.level_begin, run);
     } else if (n <= 5) {
-      const auto a = alloc(n), b = alloc(n);
-      T.lv[k] = LevelTally{(uint8_t)(n == 1 ? 2 : 3), (uint8_t)a.first, (uint8_t)a.second, (uint8_t)b.first, (uint8_t)b.second, 1};
+      const auto a = alloc(n);
+      const auto b = same ? a : alloc(n);
+      T.lv[k] = LevelTally{(uint8_t)(n == 1 ? 2 : 3), (uint8_t)a.first, (uint8_t)a.second, (uint8_t)b.first, (uint8_t)b.second, 1,
+                           (uint8_t)same};
       for (int i = 0; i < n; ++i) {
-        field(a.first, a.second + 6 * i, 6, 0, m.level_begin + i, 1);
-        field(b.first, b.second + 6 * i, 6, 1, m.level_begin + i, 1);
+        field(a.first, a.second + 6 * i, 6, same ? 2 : 0, m.level_begin + i, 1);
+        if (!same) field(b.first, b.second + 6 * i, 6, 1, m.level_begin + i, 1);
       }
     } else {
       if (n > 40) return TallyPlan{};
       const int nwl = (n + 4) / 5;
       const int wc = (int)fill.size();
-      for (int j = 0; j < 2 * nwl; ++j) fill.push_back(5);
-      T.lv[k] = LevelTally{4, (uint8_t)wc, 0, (uint8_t)(wc + nwl), 0, (uint8_t)nwl};
+      for (int j = 0; j < (same ? 1 : 2) * nwl; ++j) fill.push_back(5);
+      T.lv[k] = LevelTally{4, (uint8_t)wc, 0, (uint8_t)(wc + (same ? 0 : nwl)), 0, (uint8_t)nwl, (uint8_t)same};
       for (int i = 0; i < n; ++i) {
-        field(wc + i / 5, 6 * (i % 5), 6, 0, m.level_begin + i, 1);
-        field(wc + nwl + i / 5, 6 * (i % 5), 6, 1, m.level_begin + i, 1);
+        field(wc + i / 5, 6 * (i % 5), 6, same ? 2 : 0, m.level_begin + i, 1);
+        if (!same) field(wc + nwl + i / 5, 6 * (i % 5), 6, 1, m.level_begin + i, 1);
       }
     }
-    if (!(m.need & NEED_TRIVIAL) && n > 1)
+    if (n > 1)
       for (int i = 0; i < n; ++i) {
         const int v = pairs[m.level_begin + i];
         if (v >= (int)T.node_local.size()) T.node_local.resize((size_t)v + 1, -1);
@@ -1261,7 +1269,8 @@ static std::string generate(const std::vector<MoveRec>& moves, const std::vector
     o << "  static __device__ constexpr LevelTally tally(int k) {\n    constexpr LevelTally T[" << M << "] = {";
     for (int k = 0; k < M; ++k) {
       const LevelTally& l = T.lv[k];
-      o << (k ? ", " : "") << "{" << (int)l.kind << ", " << (int)l.wc << ", " << (int)l.bc << ", " << (int)l.ws << ", " << (int)l.bs << ", " << (int)l.nwl << "}";
+      o << (k ? ", " : "") << "{" << (int)l.kind << ", " << (int)l.wc << ", " << (int)l.bc << ", " << (int)l.ws << ", " << (int)l.bs << ", "
+        << (int)l.nwl << ", " << (int)l.same << "}";
     }
     o << "};\n    return T[k];\n  }\n  static __device__ constexpr FieldRec field(int f) {\n    constexpr FieldRec T[" << T.fields.size() << "] = {";
     for (size_t f = 0; f < T.fields.size(); ++f) {
@@ -1416,7 +1425,7 @@ const char* stryke_b200_plan_kernel(const StrykePlan* pl) { return pl ? pl->kern
 
 // Compile (not load) the specialised kernel for a small built-in facility shape: needs libnvrtc, no GPU.
 int stryke_b200_jit_selftest(void) {
-  std::vector<MoveRec> mv = {{0, 32, 0, 0, 1, 0, 1, 0}, {1, 16, 0, 1, 2, 2, 5, 1}, {2, 11, 4, 2, 7, 0, 1, 2},
+  std::vector<MoveRec> mv = {{0, 32, 0, 0, 1, 0, 1, 0}, {1, 16, 0, 1, 2, 2, 5, 1}, {2, 75, 4, 2, 7, 0, 1, 2},
                              {3, 32, 0, 7, 8, 0, 1, 7}, {4, 32, 0, 8, 9, 0, 1, 8}, {5, 32, 0, 9, 10, 0, 0, 8}};
   std::vector<uint8_t> pairs = {0, 1, 2, 3, 4, 5, 6, 7, 8, 8};
   for (int baro = 0; baro < 2; ++baro) {

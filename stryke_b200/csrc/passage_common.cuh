@@ -91,7 +91,8 @@ struct __align__(4) NodeRec {   // 12 bytes
   uint16_t pad;
 };
 
-enum : uint8_t { NEED_DICE = 1, NEED_RR = 2, NEED_DEPTH = 4, NEED_CAUSE = 8, NEED_ROUTE = 16, NEED_TRIVIAL = 32 };
+enum : uint8_t { NEED_DICE = 1, NEED_RR = 2, NEED_DEPTH = 4, NEED_CAUSE = 8, NEED_ROUTE = 16, NEED_TRIVIAL = 32, NEED_UCHECK = 64 };
+// NEED_UCHECK (throughput kernels): some node of the level has a 'U' in its name, i.e. the level can decide entrainment
 // NEED_TRIVIAL (throughput kernel only): the level is one a-priori node with survival 1.0, <= 1 successor, no 'U'
 
 struct __align__(4) MoveRec {   // 12 bytes

@@ -88,7 +88,7 @@ __device__ __forceinline__ void add_if_lane1(uint32_t& acc, int p, int lane_id, 
 // level, stryke.py:1545-1560).  A tile adds at most 1 to a 6-bit field, so the words are only reduced across the warp
 // (one REDUX per field, added to the lane that owns the pair) every HOLD tiles or when the cell changes — instead of
 // two ballots + two popcounts + predicated adds per pair and tile.
-struct LevelTally { uint8_t kind, wc, bc, ws, bs, nwl; };     // kind: 0 nothing (inside a trivial run), 1 head of a trivial
+struct LevelTally { uint8_t kind, wc, bc, ws, bs, nwl, same; };  // kind: 0 nothing (inside a passive run), 1 head of a passive
                                                               // run (field wc/bc), 2 one node, 3 <= 5 nodes (field base +
                                                               // 6 * local index, from the node record), 4 > 5 nodes
 struct FieldRec { uint8_t w, sh, bits, target, p0, len; };    // target: 0 arrivals of pair p0, 1 survivors of pair p0,
@@ -359,25 +359,27 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
       }
       bool surv;
       if (mv.need & NEED_DICE) surv = alive && (u_oc<float>(w[3]) <= rate);
-      else surv = alive && rate >= 1.0f;
+      else surv = alive;      // no dice <=> every node of the level is a-priori with survival >= 1 (host rule): u <= rate always
 
       // ---- (6) State_Daily: lane p owns pair p ---------------------------------------------------------------------
       if constexpr (PK) {
-        const LevelTally LT = TP::tally(k);
-        if (LT.kind == 2) {
+        const LevelTally LT = TP::tally(k);          // LT.same: nobody can die here, the survivors are the arrivals
+        if (LT.kind == 1) {                          // head of a run of passive one-node levels
+          W[LT.wc] += prev_alive ? (1u << LT.bc) : 0u;
+        } else if (LT.kind == 2) {
           W[LT.wc] += prev_alive ? (1u << LT.bc) : 0u;
           W[LT.ws] += surv ? (1u << LT.bs) : 0u;
         } else if (LT.kind == 3) {
           const uint32_t i6 = pk >> 27;                                      // 6 * local index of this lane's node
           W[LT.wc] += prev_alive ? ((1u << LT.bc) << i6) : 0u;
-          W[LT.ws] += surv ? ((1u << LT.bs) << i6) : 0u;
-        } else {
+          if (!LT.same) W[LT.ws] += surv ? ((1u << LT.bs) << i6) : 0u;
+        } else if (LT.kind == 4) {
           const uint32_t one = 1u << (pk >> 27);
           const int wi = (int)((pk >> 24) & 7u);
 #pragma unroll
           for (int j = 0; j < LT.nwl; ++j) {
             W[LT.wc + j] += (prev_alive && wi == j) ? one : 0u;
-            W[LT.ws + j] += (surv && wi == j) ? one : 0u;
+            if (!LT.same) W[LT.ws + j] += (surv && wi == j) ? one : 0u;
           }
         }
       } else {
@@ -391,9 +393,11 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
           for (int r = 0; r < PR; ++r) add_if_lane(acc_cnt[r], acc_suc[r], p, lane_r[r], pc, ps);
         }
       }
-      const bool newU = ((pk >> 3) & 1u) && active && (int)mv.lex < best_rank;
-      best_rank = newU ? (int)mv.lex : best_rank;
-      ent_surv = newU ? surv : ent_surv;
+      if (mv.need & NEED_UCHECK) {                       // first 'U' state in lexicographic column order (Appendix E5)
+        const bool newU = ((pk >> 3) & 1u) && active && (int)mv.lex < best_rank;
+        best_rank = newU ? (int)mv.lex : best_rank;
+        ent_surv = newU ? surv : ent_surv;
+      }
 
       // ---- (3) movement --------------------------------------------------------------------------------------------
       if (k < n_moves - 1) {
