@@ -319,7 +319,10 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         if (k < n_moves - 1) loc = alive ? (int)s_dst[(int)mv.pad * stride] : loc;
         continue;
       }
-      const uint2 nd = s_nodes[loc];
+      // a level with ONE reachable node: every live fish is there, so its index is a compile-time constant in the
+      // specialised instantiation (table offsets fold to immediates; dead lanes read a valid record they never use)
+      const int at = (TP::kStatic && mv.level_end - mv.level_begin == 1) ? TP::pair_node(FT, mv.level_begin) : loc;
+      const uint2 nd = s_nodes[at];
       const uint32_t pk = nd.y;
       const int kind = pk & 7;
       const bool prev_alive = alive;
@@ -410,7 +413,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
           }
           const float u = u_co<float>(word(sr & 3));
           // searchsorted(cdf, u, 'right') = number of thresholds <= u; rows are whole float4s padded with 2.0
-          const float4* rowq = reinterpret_cast<const float4*>(s_cdf) + loc * (crow >> 2);
+          const float4* rowq = reinterpret_cast<const float4*>(s_cdf) + at * (crow >> 2);
           const int groups = ((int)mv.max_deg - 1 + 3) >> 2;
 #pragma unroll(TP::UNROLL_P)
           for (int g = 0; g < groups; ++g) {
@@ -418,7 +421,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
             j -= le_mask(q.x, u) + le_mask(q.y, u) + le_mask(q.z, u) + le_mask(q.w, u);
           }
         }
-        loc = surv ? (int)s_dst[loc * stride + j] : loc;
+        loc = surv ? (int)s_dst[at * stride + j] : loc;
       }
       alive = surv;
     }
