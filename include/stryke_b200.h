@@ -128,6 +128,9 @@ typedef struct StrykeTrace {
   uint8_t*  survival;      /* [n_moves][n_fish]  survival_k                          */
   double*   strike;        /* [n_moves][n_fish]  blade-strike survival where evaluated, NaN elsewhere */
   double*   baro;          /* [n_moves][n_fish]  barotrauma survival where evaluated, NaN elsewhere   */
+  int64_t   n_fish;        /* capacity of the arrays.  0: the engine derives the fish count itself, which needs injected
+                            * draws or fixed counts with occur_prob = 1.  > 0 (population mode): the caller learnt the
+                            * count from an earlier run with the same seed; a different count is an error              */
 } StrykeTrace;
 
 typedef struct StrykeOpts {

@@ -49,7 +49,7 @@ class Injected(C.Structure):
 
 class Trace(C.Structure):
     _fields_ = [("length_ft", _p), ("length_ft64", _p), ("state", _p), ("rate", _p), ("survival", _p),
-                ("strike", _p), ("baro", _p)]
+                ("strike", _p), ("baro", _p), ("n_fish", C.c_int64)]
 
 
 class Opts(C.Structure):

@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
       if (sp_mode == 0) L = (Real)(fminf(fabsf(fmaf(exp_approx((float)sp_ls * (float)z), (float)sp_lsc, (float)sp_ll)), 150.f) * 0.0328084f);
       else L = (Real)(fabsf(fmaf((float)sp_lsd, (float)z, (float)sp_lm)) * (1.f / 12.f));
     }
-    if (P.trace.length_ft64 && active) { P.trace.length_ft64[gi] = (double)L; if (P.trace.length_ft) P.trace.length_ft[gi] = (float)L; }
+    if (P.trace.length_ft64 && active && gi < NF) { P.trace.length_ft64[gi] = (double)L; if (P.trace.length_ft) P.trace.length_ft[gi] = (float)L; }
 
     int loc = P.start_node;
     bool alive = active;
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
       } else {
         surv = alive && rate32 >= 1.0f;    // every node of this level has survival 1.0: no draw needed
       }
-      if (P.trace.state && active) {
+      if (P.trace.state && active && gi < NF) {     // gi >= NF: caller-supplied capacity too small (plan_status reports it)
         const int64_t o = (int64_t)k * NF + gi;
         P.trace.state[o] = (uint8_t)loc; P.trace.survival[o] = surv ? 1 : 0; P.trace.rate[o] = rate32;
         if (P.trace.strike) { P.trace.strike[o] = (double)strike_t; P.trace.baro[o] = (double)baro_t; }
@@ -954,7 +954,9 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
   // ---- optional per-fish trace -------------------------------------------------------------------------------------
   if (o->trace) {
     int64_t n_tr = NF;
-    if (!o->injected) {   // fish offsets must be known up front: only fixed-count (anadromous) cells
+    if (!o->injected && o->trace->n_fish > 0) {
+      n_tr = o->trace->n_fish;      // population mode: count known from an earlier run with the same seed (checked in plan_status)
+    } else if (!o->injected) {   // fish offsets must be known up front: only fixed-count (anadromous) cells
       n_tr = 0;
       for (int64_t i = 0; i < c->n_cells; ++i) {
         const double* sp = s->params + (size_t)c->cell_species[i] * STRYKE_SPECIES_W;

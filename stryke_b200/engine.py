@@ -69,6 +69,7 @@ class TraceBuffers:
         t = _abi.Trace()
         for k in ("length_ft", "length_ft64", "state", "rate", "survival", "strike", "baro"):
             setattr(t, k, _abi.ptr(getattr(self, k)))
+        t.n_fish = int(getattr(self, "n_fish", 0))      # > 0: capacity known from an earlier run (population mode)
         return t
 
 

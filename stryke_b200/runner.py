@@ -238,7 +238,22 @@ def run_simulation(sim, injected=None, trace=None):
         raise
     sim._last_plan, sim._last_result = plan, res
     frames = assemble_frames(sim, plan, res)
+    # ---- optional per-fish table (STRYKE_STORE_SIM_TABLE, stryke.py:116, :3243-3249) ---------------------------------
+    fish_tables = {}
+    if _flag("STRYKE_STORE_SIM_TABLE"):
+        tr = trace
+        if tr is None:      # second pass with the general kernel: same seed, same fish, now with the per-fish columns
+            n_total = int(res.cell_n.astype(np.int64).sum())
+            tr = engine.TraceBuffers.allocate(plan.fac.n_moves, n_total, probs=False)
+            tr.n_fish = n_total
+            again = engine.run_cells(plan.fac, plan.days, plan.species_table, plan.cell_day, plan.cell_species, plan.cell_id,
+                                     device=sim.device, precision=sim.precision, seed=sim.seed, max_daily_fish=cap, trace=tr)
+            if not (np.array_equal(again.cell_n, res.cell_n) and np.array_equal(again.daily, res.daily)):
+                raise RuntimeError("per-fish pass disagrees with the tally pass")       # same Philox words: cannot happen
+        fish_tables = assemble_fish_tables(sim, plan, res, tr, rates=_flag("STRYKE_STORE_AGENT_TRACES"))
     with open_store(sim.hdf_path, mode="a") as hdf:
+        for key, df in fish_tables.items():
+            hdf.append(key, df, min_itemsize=256)
         for key, df in frames.items():
             if df is not None and len(df):
                 kw = {}
@@ -252,6 +267,46 @@ def run_simulation(sim, injected=None, trace=None):
     print("[INFO] ✅ All scenarios complete! Finalizing results...", flush=True)
     print("[INFO] 💾 Simulation data saved successfully", flush=True)
     return None
+
+
+def assemble_fish_tables(sim, plan: RunPlan, res: engine.CellResult, tr, rates=False):
+    """The reference's per-fish ``fishes`` table (stryke.py:3105-3127, :3230-3236), one frame per
+    ``simulations/{scenario}/{species}`` key, rows in the reference's order (iteration -> day -> fish).  ``draw_k`` of
+    STRYKE_STORE_AGENT_TRACES is not kept (the dice are Philox words consumed in registers); ``rates_k`` is."""
+    fac = plan.fac
+    M = fac.n_moves
+    names = np.array([str(x) for x in fac.node_names], dtype=object)
+    dates = np.array(plan.day_dates, dtype="datetime64[ns]")
+    n_all = res.cell_n.astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(n_all)])
+    out = {}
+    for g in plan.groups:
+        D, I = g.n_active_days, g.iterations
+        if D == 0 or I == 0:
+            continue
+        # engine cell of (iteration i, active day d) = cell0 + d * I + i; the reference loops i outer, d inner
+        cells = (g.cell0 + np.arange(D)[None, :] * I + np.arange(I)[:, None]).ravel()
+        n = n_all[cells]
+        total = int(n.sum())
+        if total == 0:
+            continue
+        first = np.repeat(off[cells], n)
+        within = np.arange(total) - np.repeat(np.cumsum(n) - n, n)
+        fish = first + within                                   # index into the trace arrays
+        day_rows = g.day0 + g.active_days
+        it_col = np.repeat(np.repeat(np.arange(I, dtype=np.int64), D), n)
+        d_idx = np.repeat(np.tile(day_rows, I), n)
+        cols = {"scenario_num": np.repeat(g.scen_num, total), "species": np.repeat(g.species, total),
+                "flow_scenario": np.repeat(g.scenario, total), "season": np.repeat(g.season, total),
+                "iteration": it_col, "day": dates[d_idx], "flow": plan.days.curr_Q[d_idx].astype(np.float64),
+                "population": tr.length_ft[fish].astype(np.float32)}
+        for k in range(M):
+            cols[f"state_{k}"] = names[tr.state[k, fish]].astype(str)
+            if rates:
+                cols[f"rates_{k}"] = tr.rate[k, fish].astype(np.float32)
+            cols[f"survival_{k}"] = tr.survival[k, fish].astype(np.float32)
+        out[f"simulations/{g.scenario}/{g.species}"] = pd.DataFrame(cols)
+    return out
 
 
 def assemble_frames(sim, plan: RunPlan, res: engine.CellResult):

@@ -11,10 +11,10 @@ import numpy as np
 import pandas as pd
 import pytest
 
-from oracle import fixtures
+from oracle import fixtures, stryke_oracle as O
 from golden_util import Golden
 import gpu_util as G
-from stryke_b200 import runner, simulation
+from stryke_b200 import engine, runner, simulation
 from stryke_b200.runner import RunPlan
 from stryke_b200.store import open_store
 
@@ -145,3 +145,68 @@ def test_peaking_plant_hours_gate_and_unit_hours(tmp_path):
     assert (daily["pop_size"] == 500).all()
     idle_u1 = (uh[uh.route == "U1"]["hours"] == 0).mean()
     assert abs(idle_u1 - 0.35) < 0.13
+
+
+@pytest.mark.parametrize("case", ["c2_kaplan_francis", "c5_cascade", "c3_population", "cabot_station_fish"])
+def test_per_fish_table_matches_the_reference_table(case, tmp_path, monkeypatch):
+    """STRYKE_STORE_SIM_TABLE=1 (stryke.py:116, :3243): ``simulations/{scenario}/{species}`` holds the reference's
+    ``fishes`` rows — same fish order, lengths (fp32 ``population``), states and survival flags — when run() replays the
+    reference's recorded draws."""
+    monkeypatch.setenv("STRYKE_STORE_SIM_TABLE", "1")
+    monkeypatch.setenv("STRYKE_STORE_AGENT_TRACES", "1")
+    g = Golden(case)
+    sim = fresh_sim(g.prj, tmp_path, case)
+    sim.precision = 64
+    with contextlib.redirect_stdout(io.StringIO()):
+        plan = RunPlan(sim)
+    inj, off, ref_idx = G.golden_injected(g, plan)
+    tr = engine.TraceBuffers.allocate(plan.fac.n_moves, int(off[-1]), probs=False)
+    with contextlib.redirect_stdout(io.StringIO()):
+        runner.run_simulation(sim, injected=inj, trace=tr)
+    M = g.meta["moves"]
+    with open_store(sim.hdf_path, mode="r") as st:
+        keys = [k for k in st.keys() if "simulations" in k]
+        tabs = {k.strip("/"): st[k] for k in keys}
+    assert tabs
+    seen = {k: 0 for k in tabs}
+    for ci, cm in enumerate(g.cells):
+        if cm["n"] == 0:
+            continue
+        key = f"simulations/{cm['scenario']}/{cm['species']}"
+        df = tabs[key]
+        rows = df.iloc[seen[key]:seen[key] + cm["n"]]
+        seen[key] += cm["n"]
+        assert (rows["iteration"] == cm["iteration"]).all() and (pd.to_datetime(rows["day"]) == pd.Timestamp(cm["day"])).all()
+        assert (rows["flow"] == cm["curr_Q"]).all()
+        want_states, want_surv, want_rates = g.ref(ci, "states"), g.ref(ci, "survival"), g.ref(ci, "rates")
+        for k in range(M):
+            assert list(rows[f"state_{k}"]) == [g.model.nodes[int(s)] for s in want_states[k]]
+            assert np.array_equal(rows[f"survival_{k}"].to_numpy(), want_surv[k].astype(np.float32))
+            close = np.isclose(rows[f"rates_{k}"].to_numpy(), want_rates[k], rtol=2e-7, atol=0)
+            assert close.all()
+        assert np.allclose(rows["population"].to_numpy(), g.ref(ci, "lengths_ft").astype(np.float32), rtol=3e-7)
+    assert all(seen[k] == len(tabs[k]) for k in tabs)
+
+
+def test_per_fish_table_in_population_mode_uses_a_second_pass(tmp_path, monkeypatch):
+    """Native RNG, entrainment counts drawn on the device: the fish count is only known after the tally pass, the
+    per-fish pass repeats the run with the same Philox key and must reproduce every tally."""
+    monkeypatch.setenv("STRYKE_STORE_SIM_TABLE", "1")
+    prj = fixtures.c3_population(n_species=3, iterations=3, days=6)
+    sim = fresh_sim(prj, tmp_path, "fish_tab")
+    with contextlib.redirect_stdout(io.StringIO()):
+        sim.run()
+    with open_store(sim.hdf_path, mode="r") as st:
+        daily = st["Daily"]
+        tabs = {k.strip("/"): st[k] for k in st.keys() if "simulations" in k}
+    assert sum(len(t) for t in tabs.values()) == int(daily["pop_size"].sum()) > 0
+    for key, t in tabs.items():
+        _, scen, spc = key.split("/")
+        d = daily[(daily.species.str.strip() == spc) & (daily.scenario.str.strip() == scen)]
+        per_cell = t.groupby(["iteration", "day"]).size()
+        want = d[d.pop_size > 0].set_index(["iteration", "day"])["pop_size"]
+        assert per_cell.sort_index().to_dict() == want.sort_index().to_dict()
+        # entrained fish = fish whose path contains a node with 'U' in its name; they sum to Daily.num_entrained
+        states = t[[c for c in t.columns if c.startswith("state_")]].to_numpy(dtype=str)
+        ent = (np.char.find(states, "U") >= 0).any(axis=1)
+        assert int(ent.sum()) == int(d["num_entrained"].sum())
