@@ -4,7 +4,9 @@
 The per-fish work exists only as sm_100a CUDA behind the C ABI in include/stryke_b200.h; importing the package
 does not need a GPU, running a simulation does (there is no CPU fallback).
 """
+from .epri import epri  # noqa: F401
 from .simulation import simulation  # noqa: F401
+from .summary import bootstrap_mean_ci, summarize_ci  # noqa: F401  (module-level helpers of stryke.py:136-162)
 
-__all__ = ["simulation"]
+__all__ = ["simulation", "epri", "bootstrap_mean_ci", "summarize_ci"]
 __version__ = "0.1.0"
