@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
     // ---- (2) length draw ---------------------------------------------------------------------------------------
     Real z;
     if (INJECT) z = active ? (Real)P.inj.length_z[gi] : (Real)0;
-    else { const uint32_t a = rng.word(0), b = rng.word(1); z = std_normal(u_oc<Real>(a), u_co<Real>(b)); }
+    else { const uint32_t a = rng.word(0); z = std_normal(u16hi_oc<Real>(a), u16lo_co<Real>(a)); }
     Real L;
     if (sizeof(Real) == 8) {
       if (sp_mode == 0) {   // |Z-lognormal| cm, cap 150, -> ft  (scipy: exp(s*Z)*scale + loc; stryke.py:3070-3077)
@@ -450,14 +450,13 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
       const NodeRec nd = s_nodes[loc];
       const bool prev_alive = alive;
       float rate32 = 0.f;
-      // a level with per-node draws owns one Philox block: rR, depth, cause, dice at fixed positions 0..3
-      const int s_rr = mv.slot_base, s_dep = mv.slot_base + 1, s_cau = mv.slot_base + 2, s_dice = mv.slot_base + 3;
+      // word slots of this move (MoveRec): r/R + cause share one word, depth, dice, route one each
+      const int s_dep = mv.slot_depth, s_dice = mv.slot_dice;
       const int s_rt = mv.slot_route;
-      uint32_t w_rr = 0, w_dep = 0, w_cau = 0;
+      uint32_t w_rc = 0, w_dep = 0;
       if (!INJECT) {   // warp-uniform draws for this move (refill points are identical for every lane)
-        if (mv.need & NEED_RR) w_rr = rng.word(s_rr);
+        if (mv.need & (NEED_RR | NEED_CAUSE)) w_rc = rng.word(mv.slot_rc);
         if (mv.need & NEED_DEPTH) w_dep = rng.word(s_dep);
-        if (mv.need & NEED_CAUSE) w_cau = rng.word(s_cau);
       }
       Real strike_t = (Real)NAN, baro_t = (Real)NAN;
       if (alive) {
@@ -474,8 +473,8 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
             Real rR = (Real)0.75;
             if (nd.kind == STRYKE_KIND_KAPLAN) {
               if (INJECT) rR = (Real)add_(0.3, mul_(sub_(1.0, 0.3), P.inj.rR[(int64_t)k * NF + gi]));
-              else if (sizeof(Real) == 8) rR = (Real)(0.3 + 0.7 * (double)u_co<Real>(w_rr));
-              else rR = (Real)fmaf(0.7f, (float)u_co<Real>(w_rr), 0.3f);
+              else if (sizeof(Real) == 8) rR = (Real)(0.3 + 0.7 * (double)u16hi_co<Real>(w_rc));
+              else rR = (Real)fmaf(0.7f, (float)u16hi_co<Real>(w_rc), 0.3f);
             }
             if (sizeof(Real) == 8) strike = (Real)strike_surv64(nd.kind, (const double*)uc, (double)L, (double)rR);
             else strike = (Real)strike_surv32(nd.kind, (const float*)uc, (float)L, (float)rR);
@@ -505,7 +504,7 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
           } else {
             // one uniform splits [0,1) into the same three probabilities the reference's sequential rolls have:
             // P(imp) = 1-imp, P(blade) = imp (1-strike), P(baro) = imp strike (1-baro)
-            const Real u = u_co<Real>(w_cau);
+            const Real u = u16lo_co<Real>(w_rc);
             const Real a1 = imp, a2 = imp * strike, a3 = a2 * baro;
             if (u >= a1) cz += 1u;
             else if (u >= a2) cz += 1u << 8;
@@ -843,8 +842,7 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
   // Philox word layout (shared by both passage kernels): block 0 words 0,1 = length draw.  Every level with per-node
   // draws owns a fresh block (rR, depth, cause, dice at positions 0..3).  A routing word takes a free position of the
   // block that is current at that point of the move loop, else opens a new block.
-  int next_block = 1, cur_block = 0;
-  std::vector<int> free_pos = {2, 3};
+  int next_slot = 1;
   for (int k = 0; k < f->n_moves; ++k) {
     MoveRec& m = moves[k];
     m.lex = f->move_lex_rank[k];
@@ -863,22 +861,12 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
       if (k < f->n_moves - 1 && r.deg > 1) need |= NEED_ROUTE;
     }
     m.need = need;
-    m.slot_base = 0;
-    m.slot_route = 0;
-    if (need & (NEED_RR | NEED_DEPTH | NEED_CAUSE | NEED_DICE)) {
-      cur_block = next_block++;
-      m.slot_base = (uint16_t)(4 * cur_block);
-      free_pos.clear();
-      if (!(need & NEED_RR)) free_pos.push_back(0);
-      if (!(need & NEED_DEPTH)) free_pos.push_back(1);
-      if (!(need & NEED_CAUSE)) free_pos.push_back(2);
-      if (!(need & NEED_DICE)) free_pos.push_back(3);
-    }
-    if (need & NEED_ROUTE) {
-      if (free_pos.empty()) { cur_block = next_block++; free_pos = {0, 1, 2, 3}; }
-      m.slot_route = (uint16_t)(4 * cur_block + free_pos.front());
-      free_pos.erase(free_pos.begin());
-    }
+    // dense word slots in consumption order (slot 0 is the length word)
+    m.slot_rc = m.slot_depth = m.slot_dice = m.slot_route = 0;
+    if (need & (NEED_RR | NEED_CAUSE)) m.slot_rc = (uint16_t)next_slot++;
+    if (need & NEED_DEPTH) m.slot_depth = (uint16_t)next_slot++;
+    if (need & NEED_DICE) m.slot_dice = (uint16_t)next_slot++;
+    if (need & NEED_ROUTE) m.slot_route = (uint16_t)next_slot++;
     int md = 0;
     for (int p = m.level_begin; p < m.level_end; ++p) md = std::max(md, (int)nodes[pnode[p]].deg);
     m.max_deg = (uint8_t)md;
@@ -1261,8 +1249,9 @@ static std::string generate(const std::vector<MoveRec>& moves, const std::vector
     << "  static __device__ constexpr MoveRec move(const FastTables&, int k) {\n    constexpr MoveRec T[" << M << "] = {";
   for (int k = 0; k < M; ++k) {
     const MoveRec& m = moves[k];
-    o << (k ? ", " : "") << "{" << (int)m.lex << ", " << (int)m.need << ", " << m.slot_base << ", " << m.level_begin << ", "
-      << m.level_end << ", " << m.slot_route << ", " << (int)m.max_deg << ", " << (int)m.pad << "}";
+    o << (k ? ", " : "") << "{" << (int)m.lex << ", " << (int)m.need << ", " << m.slot_rc << ", " << m.level_begin << ", "
+      << m.level_end << ", " << m.slot_route << ", " << (int)m.max_deg << ", " << (int)m.pad << ", " << m.slot_depth << ", "
+      << m.slot_dice << "}";
   }
   o << "};\n    return T[k];\n  }\n  static __device__ constexpr int pair_node(const FastTables&, int p) {\n    constexpr uint8_t N[" << P << "] = {";
   for (int p = 0; p < P; ++p) o << (p ? ", " : "") << (int)pairs[p];
@@ -1427,8 +1416,8 @@ const char* stryke_b200_plan_kernel(const StrykePlan* pl) { return pl ? pl->kern
 
 // Compile (not load) the specialised kernel for a small built-in facility shape: needs libnvrtc, no GPU.
 int stryke_b200_jit_selftest(void) {
-  std::vector<MoveRec> mv = {{0, 32, 0, 0, 1, 0, 1, 0}, {1, 16, 0, 1, 2, 2, 5, 1}, {2, 75, 4, 2, 7, 0, 1, 2},
-                             {3, 32, 0, 7, 8, 0, 1, 7}, {4, 32, 0, 8, 9, 0, 1, 8}, {5, 32, 0, 9, 10, 0, 0, 8}};
+  std::vector<MoveRec> mv = {{0, 32, 0, 0, 1, 0, 1, 0, 0, 0}, {1, 16, 0, 1, 2, 1, 5, 1, 0, 0}, {2, 75, 2, 2, 7, 0, 1, 2, 0, 3},
+                             {3, 32, 0, 7, 8, 0, 1, 7, 0, 0}, {4, 32, 0, 8, 9, 0, 1, 8, 0, 0}, {5, 32, 0, 9, 10, 0, 0, 8, 0, 0}};
   std::vector<uint8_t> pairs = {0, 1, 2, 3, 4, 5, 6, 7, 8, 8};
   for (int baro = 0; baro < 2; ++baro) {
     std::string err;

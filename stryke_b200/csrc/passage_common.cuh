@@ -95,14 +95,21 @@ enum : uint8_t { NEED_DICE = 1, NEED_RR = 2, NEED_DEPTH = 4, NEED_CAUSE = 8, NEE
 // NEED_UCHECK (throughput kernels): some node of the level has a 'U' in its name, i.e. the level can decide entrainment
 // NEED_TRIVIAL (throughput kernel only): the level is one a-priori node with survival 1.0, <= 1 successor, no 'U'
 
-struct __align__(4) MoveRec {   // 12 bytes
+// Native-RNG word budget.  A fish consumes Philox words in a fixed order — word 0: length (Box-Muller radius from the high
+// 16 bits, angle from the low 16 bits); then per move, only where the level can need them (NEED_*): one word for the
+// runner position r/R (high 16 bits) and the mortality-cause roll (low 16 bits), one for the barotrauma depth, one for
+// the survival dice, one for the routing draw (23 bits each).  Word slot s lives in Philox block s >> 2 at position
+// s & 3; the slots are assigned densely by the host, so the C2 facility needs 4 words = ONE block per fish.
+struct __align__(4) MoveRec {   // 16 bytes
   uint8_t lex;                  // rank of "state_k" in lexicographic column order (stryke.py:3272)
   uint8_t need;                 // NEED_* : which draws this move can consume (static facility property)
-  uint16_t slot_base;           // Philox word slot of this move's block of per-node words: rR, depth, cause, dice
+  uint16_t slot_rc;             // word slot of the r/R + cause word
   uint16_t level_begin, level_end;  // reachable pairs of this move in pair_node[]
-  uint16_t slot_route;          // Philox word slot of the routing draw
+  uint16_t slot_route;          // word slot of the routing draw
   uint8_t max_deg;              // largest out-degree among the nodes of this level
   uint8_t pad;                  // throughput kernel: node of the level's first pair
+  uint16_t slot_depth;          // word slot of the barotrauma depth draw
+  uint16_t slot_dice;           // word slot of the survival dice
 };
 
 struct InjectedDev {
@@ -157,6 +164,18 @@ template <> __device__ __forceinline__ float u_co<float>(uint32_t x) { return ma
 template <> __device__ __forceinline__ float u_oc<float>(uint32_t x) { return 2.0f - mantissa_float(x); }
 template <> __device__ __forceinline__ double u_co<double>(uint32_t x) { return (double)x * 2.3283064365386963e-10; }
 template <> __device__ __forceinline__ double u_oc<double>(uint32_t x) { return ((double)x + 1.0) * 2.3283064365386963e-10; }
+
+// 16-bit uniforms from the high / low half of a word (disjoint bits), multiples of 2^-16: exact in fp32 and fp64, so
+// every kernel sees the same value.  hi_co, lo_co in [0, 1): k / 65536;  hi_oc in (0, 1]: 1 - k / 65536.
+template <typename Real> __device__ __forceinline__ Real u16hi_co(uint32_t w);
+template <typename Real> __device__ __forceinline__ Real u16hi_oc(uint32_t w);
+template <typename Real> __device__ __forceinline__ Real u16lo_co(uint32_t w);
+template <> __device__ __forceinline__ float u16hi_co<float>(uint32_t w) { return mantissa_float(w & 0xffff0000u) - 1.0f; }
+template <> __device__ __forceinline__ float u16hi_oc<float>(uint32_t w) { return 2.0f - mantissa_float(w & 0xffff0000u); }
+template <> __device__ __forceinline__ float u16lo_co<float>(uint32_t w) { return mantissa_float(w << 16) - 1.0f; }
+template <> __device__ __forceinline__ double u16hi_co<double>(uint32_t w) { return (double)(w >> 16) * (1.0 / 65536.0); }
+template <> __device__ __forceinline__ double u16hi_oc<double>(uint32_t w) { return 1.0 - (double)(w >> 16) * (1.0 / 65536.0); }
+template <> __device__ __forceinline__ double u16lo_co<double>(uint32_t w) { return (double)(w & 0xffffu) * (1.0 / 65536.0); }
 
 __device__ __forceinline__ float std_normal(float u1_oc, float u2_co) {   // Box-Muller: MUFU lg2, sqrt, cos
   return sqrt_approx(-1.3862943611f * lg2_approx(u1_oc)) * cos_2pi(u2_co);   // -2 ln u = -2 ln2 lg2 u

@@ -287,10 +287,19 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
     uint32_t w[4];
     int cur_b = 0;
     Philox::block_ks((uint32_t)fish, cid_lo, cid_hi, 0u, P.ks, w);
-    auto word = [&](int i) -> uint32_t { return (i & 2) ? ((i & 1) ? w[3] : w[2]) : ((i & 1) ? w[1] : w[0]); };
+    // word slot s -> block s >> 2 (generated when first needed: the slots are consumed in increasing order and the
+    // test is warp-uniform, compile-time in the specialised instantiation), position s & 3
+    auto word = [&](int s) -> uint32_t {
+      if ((s >> 2) != cur_b) {
+        cur_b = s >> 2;
+        Philox::block_ks((uint32_t)fish, cid_lo, cid_hi, (uint32_t)cur_b, P.ks, w);
+      }
+      const int i = s & 3;
+      return (i & 2) ? ((i & 1) ? w[3] : w[2]) : ((i & 1) ? w[1] : w[0]);
+    };
 
-    // ---- (2) length: words 0, 1 ----------------------------------------------------------------------------------
-    const float z = std_normal(u_oc<float>(w[0]), u_co<float>(w[1]));
+    // ---- (2) length: word 0, radius from the high half, angle from the low half --------------------------------------
+    const float z = std_normal(u16hi_oc<float>(w[0]), u16lo_co<float>(w[0]));
     float L;
     if (sp_mode == 0) L = fminf(fabsf(fmaf(exp_approx(sp_ls * z), sp_lsc, sp_ll)), 150.f) * 0.0328084f;
     else L = fabsf(fmaf(sp_lsd, z, sp_lm)) * (1.f / 12.f);
@@ -327,14 +336,11 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
       const int kind = pk & 7;
       const bool prev_alive = alive;
       float rate = alive ? __uint_as_float(nd.x) : 0.f;
-      if (mv.need & (NEED_CAUSE | NEED_DICE)) {          // refill site A (uniform): this level owns a fresh block,
-        cur_b = mv.slot_base >> 2;                       // rR, depth, cause, dice at fixed positions 0..3
-        Philox::block_ks((uint32_t)fish, cid_lo, cid_hi, (uint32_t)cur_b, P.ks, w);
-      }
       if (mv.need & NEED_CAUSE) {                        // this level has turbine nodes (uniform)
-        const float u_rr = u_co<float>(w[0]);
-        const float u_dep = BARO ? u_co<float>(w[1]) : 0.f;
-        const float u_cau = u_co<float>(w[2]);
+        const uint32_t w_rc = word(mv.slot_rc);          // r/R in the high half, cause roll in the low half
+        const float u_rr = u16hi_co<float>(w_rc);
+        const float u_cau = u16lo_co<float>(w_rc);
+        const float u_dep = BARO ? u_co<float>(word(mv.slot_depth)) : 0.f;
         const bool turb = alive && kind != STRYKE_KIND_APRIORI;
         const int unit = turb ? (int)((pk >> 4) & 0x7f) : 0;
         const float4 us = s_ustatic[unit];
@@ -361,7 +367,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         cz += turb ? code : 0u;
       }
       bool surv;
-      if (mv.need & NEED_DICE) surv = alive && (u_oc<float>(w[3]) <= rate);
+      if (mv.need & NEED_DICE) surv = alive && (u_oc<float>(word(mv.slot_dice)) <= rate);
       else surv = alive;      // no dice <=> every node of the level is a-priori with survival >= 1 (host rule): u <= rate always
 
       // ---- (6) State_Daily: lane p owns pair p ---------------------------------------------------------------------
@@ -406,12 +412,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
       if (k < n_moves - 1) {
         int j = 0;
         if (mv.need & NEED_ROUTE) {
-          const int sr = mv.slot_route;
-          if ((sr >> 2) != cur_b) {                                          // refill site B (uniform)
-            cur_b = sr >> 2;
-            Philox::block_ks((uint32_t)fish, cid_lo, cid_hi, (uint32_t)cur_b, P.ks, w);
-          }
-          const float u = u_co<float>(word(sr & 3));
+          const float u = u_co<float>(word(mv.slot_route));
           // searchsorted(cdf, u, 'right') = number of thresholds <= u; rows are whole float4s padded with 2.0
           const float4* rowq = reinterpret_cast<const float4*>(s_cdf) + at * (crow >> 2);
           const int groups = ((int)mv.max_deg - 1 + 3) >> 2;

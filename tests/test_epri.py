@@ -1,13 +1,14 @@
 """stryke_b200.epri against the reference's own ``epri`` class (Stryke/stryke.py:4322-5084): tests/golden/epri_fits.json
 holds, for twelve queries, what the unmodified class computed on its database (oracle/make_epri_goldens.py) and the
 filtered entrainment rates it fitted."""
+import importlib
 import json
 import os
 
 import numpy as np
 import pytest
 
-from stryke_b200 import epri as E
+E = importlib.import_module("stryke_b200.epri")     # the package attribute `epri` is the class, as in the reference
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 with open(os.path.join(HERE, "golden", "epri_fits.json")) as fh:
