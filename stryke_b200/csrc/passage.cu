@@ -904,7 +904,7 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
   Philox::key_schedule(o->seed, K.ks);
   K.n_fish_total = 0;
   K.work_counter = pl->err.as<unsigned long long>() + 1;
-  K.chunk_tiles = 64;
+  K.chunk_tiles = 128;
   if (const char* e = getenv("STRYKE_B200_CHUNK_TILES")) K.chunk_tiles = std::max(1, atoi(e));
 
   // ---- injected draws ----------------------------------------------------------------------------------------------
