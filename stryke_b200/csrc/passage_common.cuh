@@ -170,9 +170,15 @@ template <> __device__ __forceinline__ double u_oc<double>(uint32_t x) { return 
 template <typename Real> __device__ __forceinline__ Real u16hi_co(uint32_t w);
 template <typename Real> __device__ __forceinline__ Real u16hi_oc(uint32_t w);
 template <typename Real> __device__ __forceinline__ Real u16lo_co(uint32_t w);
-template <> __device__ __forceinline__ float u16hi_co<float>(uint32_t w) { return mantissa_float(w & 0xffff0000u) - 1.0f; }
-template <> __device__ __forceinline__ float u16hi_oc<float>(uint32_t w) { return 2.0f - mantissa_float(w & 0xffff0000u); }
-template <> __device__ __forceinline__ float u16lo_co<float>(uint32_t w) { return mantissa_float(w << 16) - 1.0f; }
+// piece already moved to mantissa bits [22:7]: ((x & 0x007fff80) | 0x3f800000) as ONE three-input logic op
+__device__ __forceinline__ float mantissa16(uint32_t x) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "r"(0x007fff80u), "r"(0x3f800000u));
+  return __uint_as_float(r);
+}
+template <> __device__ __forceinline__ float u16hi_co<float>(uint32_t w) { return mantissa16(w >> 9) - 1.0f; }
+template <> __device__ __forceinline__ float u16hi_oc<float>(uint32_t w) { return 2.0f - mantissa16(w >> 9); }
+template <> __device__ __forceinline__ float u16lo_co<float>(uint32_t w) { return mantissa16(w << 7) - 1.0f; }
 template <> __device__ __forceinline__ double u16hi_co<double>(uint32_t w) { return (double)(w >> 16) * (1.0 / 65536.0); }
 template <> __device__ __forceinline__ double u16hi_oc<double>(uint32_t w) { return 1.0 - (double)(w >> 16) * (1.0 / 65536.0); }
 template <> __device__ __forceinline__ double u16lo_co<double>(uint32_t w) { return (double)(w & 0xffffu) * (1.0 / 65536.0); }

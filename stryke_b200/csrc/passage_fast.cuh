@@ -57,7 +57,7 @@ __host__ __device__ constexpr FastSmem fast_smem(int n_nodes, int n_units, int s
   int w = 0;
   L.cdf = w; w = (w + n_nodes * cdf_row(stride) * 4 + 15) & ~15;
   L.ucoef = w; w = (w + n_units * 16 + 15) & ~15;
-  L.dst = w; w = (w + n_nodes * stride + 15) & ~15;
+  L.dst = w; w = (w + n_nodes * stride * 4 + 15) & ~15;     // int32 entries: no sub-word register packing in the hot loop
   L.warp_stride = w;
   L.total = o + w * WARPS;
   return L;
@@ -127,7 +127,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   unsigned char* wbase = smem + SL.warp0 + wid * SL.warp_stride;
   float* s_cdf = reinterpret_cast<float*>(wbase + SL.cdf);              // [n_nodes][cdf_row(stride)], padded with 2.0
   float4* s_ucoef = reinterpret_cast<float4*>(wbase + SL.ucoef);        // fa, fb, fc, has_flow
-  uint8_t* s_dst = wbase + SL.dst;                                      // [n_nodes][stride], padded with the node itself
+  int* s_dst = reinterpret_cast<int*>(wbase + SL.dst);                  // [n_nodes][stride], padded with the node itself
 
   for (int i = threadIdx.x; i < n_nodes; i += BLOCK) s_nodes[i] = g_nodes[i];
   for (int u = threadIdx.x; u < n_units; u += BLOCK) {
@@ -266,7 +266,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         for (int i = lane; i < n_nodes * stride; i += 32) {
           const int v = i / stride, e = i - v * stride;
           const NodeRec nr = P.nodes[v];
-          s_dst[i] = (e < (int)nr.deg && !st[v]) ? P.edge_dst[nr.edge_off + e] : (uint8_t)v;
+          s_dst[i] = (e < (int)nr.deg && !st[v]) ? (int)P.edge_dst[nr.edge_off + e] : v;
         }
         const double* uc = P.unit_coef + (size_t)d * n_units * STRYKE_UNIT_COEF_W;
         for (int u = lane; u < n_units; u += 32) {
@@ -325,7 +325,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
 #pragma unroll
           for (int r = 0; r < PR; ++r) add_if_lane(acc_cnt[r], acc_suc[r], mv.level_begin, lane_r[r], pc, pc);
         }
-        if (k < n_moves - 1) loc = alive ? (int)s_dst[(int)mv.pad * stride] : loc;
+        if (k < n_moves - 1) loc = alive ? s_dst[(int)mv.pad * stride] : loc;
         continue;
       }
       // a level with ONE reachable node: every live fish is there, so its index is a compile-time constant in the
@@ -422,7 +422,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
             j -= le_mask(q.x, u) + le_mask(q.y, u) + le_mask(q.z, u) + le_mask(q.w, u);
           }
         }
-        loc = surv ? (int)s_dst[at * stride + j] : loc;
+        loc = surv ? s_dst[at * stride + j] : loc;
       }
       alive = surv;
     }
