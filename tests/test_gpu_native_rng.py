@@ -32,18 +32,10 @@ def oracle_cells(prj, n_cells, seed=3):
     return out
 
 
-@pytest.mark.parametrize("precision", [32, 64])
-@pytest.mark.parametrize("fixture,kw", [("c2_facility", dict(n_fish=400000, iterations=2, days=2)),
-                                        ("c2_facility", dict(n_fish=300000, iterations=1, days=2, baro=True)),
-                                        ("c5_cascade", dict(n_fish=150000, iterations=1, days=2)),
-                                        ("c4_barotrauma", dict(n_fish=200000, iterations=1, days=2)),
-                                        ("cabot_station", dict(iterations=1, days=2, seed=3, median_Q=7000.0, fish=200000.0))])
-def test_route_and_survival_counts_match_oracle_distribution(fixture, kw, precision):
-    prj = getattr(fixtures, fixture)(**kw)
-    sim, plan = G.make_plan(prj, fixture)
-    res = native(plan, precision=precision)
-    ref = oracle_cells(prj, plan.n_cells)
-    ref_idx = G.reference_cell_index(plan)
+def compare_cells(plan, res, ref, ref_idx):
+    """Two-sample tests between the device tallies and reference-side tallies of the same cells: homogeneity of the
+    per-node arrival counts at every multi-node level (routing), two-proportion tests of the per-(move, node) survival
+    and of the Daily columns; Bonferroni over all tests of the case."""
     tests = []
     for c, r in enumerate(ref_idx):
         got = G.state_daily_dict(plan, res.state_daily[c])
@@ -52,7 +44,7 @@ def test_route_and_survival_counts_match_oracle_distribution(fixture, kw, precis
         moves = sorted({k for k, _ in got})
         for k in moves:
             nodes = sorted(nd for kk, nd in got if kk == k)
-            if len(nodes) > 1:      # routing: homogeneity of the count vectors (GPU vs oracle)
+            if len(nodes) > 1:      # routing: homogeneity of the count vectors (GPU vs reference side)
                 tab = np.array([[got[(k, nd)][1] for nd in nodes], [want[(k, nd)][1] for nd in nodes]])
                 tab = tab[:, tab.sum(axis=0) > 0]
                 tests.append(("route", c, k, stats.chi2_contingency(tab)[1]))
@@ -72,6 +64,42 @@ def test_route_and_survival_counts_match_oracle_distribution(fixture, kw, precis
     assert len(tests) > 5
     worst = min(tests, key=lambda t: t[-1])
     assert worst[-1] > ALPHA / len(tests), (worst, len(tests))
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+@pytest.mark.parametrize("fixture,kw", [("c2_facility", dict(n_fish=400000, iterations=2, days=2)),
+                                        ("c2_facility", dict(n_fish=300000, iterations=1, days=2, baro=True)),
+                                        ("c5_cascade", dict(n_fish=150000, iterations=1, days=2)),
+                                        ("c4_barotrauma", dict(n_fish=200000, iterations=1, days=2)),
+                                        ("cabot_station", dict(iterations=1, days=2, seed=3, median_Q=7000.0, fish=200000.0))])
+def test_route_and_survival_counts_match_oracle_distribution(fixture, kw, precision):
+    prj = getattr(fixtures, fixture)(**kw)
+    sim, plan = G.make_plan(prj, fixture)
+    res = native(plan, precision=precision)
+    ref = oracle_cells(prj, plan.n_cells)
+    compare_cells(plan, res, ref, G.reference_cell_index(plan))
+
+
+def _reference_samples():
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_samples.json")
+    return json.load(open(path)) if os.path.isfile(path) else {}
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+@pytest.mark.parametrize("case", sorted(_reference_samples()))
+def test_route_and_survival_counts_match_the_reference_itself(case, precision):
+    """Same tests against tallies of the UNMODIFIED reference (tests/golden/reference_samples.json, written by
+    oracle/make_reference_samples.py: tens of thousands of fish per cell through the reference's own run())."""
+    rec = _reference_samples()[case]
+    prj = getattr(fixtures, rec["fixture"])(**rec["kwargs"])
+    sim, plan = G.make_plan(prj, case)
+    res = native(plan, precision=precision, seed=2024)
+    ref = [dict(daily=np.array(c["daily"], dtype=np.int64),
+                state_daily={(int(m), str(st)): (int(su), int(cn)) for m, st, su, cn in c["state_daily"]}) for c in rec["cells"]]
+    assert len(ref) == plan.n_cells
+    compare_cells(plan, res, ref, G.reference_cell_index(plan))
 
 
 @pytest.mark.parametrize("precision", [32, 64])
