@@ -231,6 +231,63 @@ def c5_cascade(n_fish=1000, iterations=1, days=1, curr_Q=9000.0, dams=5):
     )
 
 
+def random_facility(seed=0, n_fish=1000, iterations=1, days=4, baro=False):
+    """Randomised cascade for fuzzing the device path against the oracle: 1-3 dams in series, 1-7 units per dam with
+    random runner types, capacities, operating orders and minimum flows, optional environmental-flow nodes, random
+    a-priori survivals, and a hydrograph that spans from (nearly) no flow — nothing runs, fish may stay put — to far
+    above the station capacities (everything spills)."""
+    rng = np.random.default_rng(seed)
+    dams = int(rng.integers(1, 4))
+    nodes, edges, units, facs, ops = [], [], [], [], []
+    runners = (KAPLAN, FRANCIS, PROPELLER)
+    total_cap = 0.0
+    for i in range(dams):
+        fac = f"Dam{i + 1}"
+        rn, fb, tr = f"river_node_{i}", f"forebay_{i}", f"tailrace_{i}"
+        n_units = int(rng.integers(1, 8))
+        names = [f"D{i + 1}U{j + 1}" for j in range(n_units)]
+        order = rng.permutation(n_units) + 1
+        mid = list(names)
+        nodes += [(rn, "a priori", 1.0), (fb, "a priori", float(rng.choice([1.0, 1.0, 0.995])))]
+        cap = 0.0
+        for j, nm in enumerate(names):
+            r = dict(runners[int(rng.integers(0, 3))])
+            scale = float(rng.uniform(0.3, 1.6))
+            r.update(Qcap=round(r["Qcap"] * scale, 1), Qopt=round(r["Qopt"] * scale, 1), H=float(rng.uniform(15, 70)))
+            cap += r["Qcap"]
+            nodes.append((nm, r["Runner Type"], 0.0))
+            units.append(_unit_row(fac, j + 1, nm, int(order[j]), r, baro))
+            ops.append(dict(Scenario="Spring", Facility=fac, Unit=j + 1, Hours=24.0, Prob_Not_Op=NAN, shape=NAN,
+                            location=NAN, scale=NAN))
+        has_env, has_byp = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        if has_env:
+            nodes.append((f"env_{i}", "a priori", float(rng.uniform(0.95, 1.0)))); mid.append(f"env_{i}")
+        if has_byp:
+            nodes.append((f"bypass_{i}", "a priori", float(rng.choice([1.0, 0.98])))); mid.append(f"bypass_{i}")
+        nodes += [(f"spill_{i}", "a priori", float(rng.uniform(0.9, 1.0))), (tr, "a priori", float(rng.choice([1.0, 0.99])))]
+        mid.append(f"spill_{i}")
+        edges += [(rn, fb, 1.0)] + [(fb, x, 1.0) for x in mid] + [(x, tr, 1.0) for x in mid] + [(tr, f"river_node_{i + 1}", 1.0)]
+        facs.append(dict(Facility=fac, Scenario="Spring", Operations="run-of-river",
+                         **{"Rack Spacing": float(rng.choice([1.0, 2.0, 0.35])) / 12.0},
+                         Min_Op_Flow=float(rng.uniform(100, 900)), Env_Flow=float(rng.uniform(50, 400)) if has_env else 0.0,
+                         Bypass_Flow=float(rng.uniform(20, 200)) if has_byp else 0.0, Spillway=f"spill_{i}"))
+        total_cap = max(total_cap, cap)
+    nodes.append((f"river_node_{dams}", "a priori", 1.0))
+    import datetime as _dt
+    d0 = _dt.date(2023, 3, 1)
+    levels = np.concatenate([[float(rng.choice([0.0, 30.0, 150.0]))], rng.uniform(0.05, 2.5, max(days - 1, 0)) * total_cap])
+    flows = levels[rng.permutation(days)]
+    return dict(
+        name=f"random{seed}", output_units="imperial", max_river_node=dams,
+        nodes=[dict(Location=a, Surv_Fun=b, Survival=c) for a, b, c in nodes],
+        edges=[dict(_from=a, _to=b, weight=w) for a, b, w in edges],
+        unit_params=units, facility_params=facs, flow_scenarios=_scenario_rows(["Spring"], months=_months_for(days)),
+        operating_scenarios=ops,
+        hydrograph=[dict(Date=(d0 + _dt.timedelta(days=i)).isoformat(), Discharge=float(flows[i])) for i in range(days)],
+        population=[_pop_row(SHAD, "Spring", fish=float(n_fish), iterations=iterations)],
+    )
+
+
 def c1_single_unit(iterations=5, days=92, seed=0, fish=NAN):
     """the v250304 example — one Francis unit node, Micropterus Log Normal entrainment,
     barotrauma on (fb_depth / submergence set), seeded synthetic hydrograph (the USGS gage needs network)."""

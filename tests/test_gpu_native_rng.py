@@ -71,7 +71,9 @@ def compare_cells(plan, res, ref, ref_idx):
                                         ("c2_facility", dict(n_fish=300000, iterations=1, days=2, baro=True)),
                                         ("c5_cascade", dict(n_fish=150000, iterations=1, days=2)),
                                         ("c4_barotrauma", dict(n_fish=200000, iterations=1, days=2)),
-                                        ("cabot_station", dict(iterations=1, days=2, seed=3, median_Q=7000.0, fish=200000.0))])
+                                        ("cabot_station", dict(iterations=1, days=2, seed=3, median_Q=7000.0, fish=200000.0)),
+                                        ("random_facility", dict(seed=3, n_fish=150000, days=3)),
+                                        ("random_facility", dict(seed=6, n_fish=150000, days=3, baro=True))])
 def test_route_and_survival_counts_match_oracle_distribution(fixture, kw, precision):
     prj = getattr(fixtures, fixture)(**kw)
     sim, plan = G.make_plan(prj, fixture)
@@ -209,7 +211,8 @@ def test_full_size_conservation_properties(fixture, kw):
                                         ("c3_population", dict(n_species=4, iterations=60, days=10)),
                                         # 13 nodes in one level: the multi-word packed tallies of the specialised kernel
                                         ("cabot_station", dict(iterations=2, days=6, seed=3, median_Q=7000.0, fish=120000.0)),
-                                        ("cabot_station", dict(iterations=40, days=30, seed=1))])
+                                        ("cabot_station", dict(iterations=40, days=30, seed=1))]
+                         + [("random_facility", dict(seed=s, n_fish=40000, iterations=2, days=4, baro=bool(s % 2))) for s in range(10)])
 def test_fast_kernel_equals_general_kernel(fixture, kw):
     """passage_fast_kernel (throughput variant) vs passage_kernel<float, native> (the template that is validated
     bit-for-bit against the reference in injected mode): same Philox words, same fp32 formulas -> identical tallies."""

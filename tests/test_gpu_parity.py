@@ -110,7 +110,8 @@ def test_fp32_injected_tallies_statistically_identical(case):
     ("c2_facility", dict(n_fish=100000, iterations=1, days=2, baro=True)),
     ("c5_cascade", dict(n_fish=60000, iterations=1, days=2)),
     ("c4_barotrauma", dict(n_fish=50000, iterations=2, days=1, habitat="Benthic")),
-])
+    ("cabot_station", dict(iterations=1, days=3, seed=5, median_Q=6000.0, fish=30000.0)),
+] + [("random_facility", dict(seed=s, n_fish=15000, days=4, baro=bool(s % 2))) for s in range(10)])
 def test_large_cells_oracle_draws_bit_exact(fixture, kw):
     """Sizes the reference cannot reach in test time: the oracle generates the slot-tagged draws, the GPU (fp64,
     injected) must return identical tallies, states and survival flags."""
@@ -121,7 +122,7 @@ def test_large_cells_oracle_draws_bit_exact(fixture, kw):
     rng = np.random.default_rng(1234)
     M = len(model.moves)
     prow = prj["population"][0]
-    sp = O.species_record(model, prow, None)
+    sp = O.species_record(model, prow, {"Micropterus": "Centrarchidae"}.get(prow["Species"]))
     n = int(prow["Fish"])
     n_ref = plan.n_cells
     draws, results = [], []
