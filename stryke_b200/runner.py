@@ -120,13 +120,63 @@ class RunPlan:
         fp = sim.facility_params
         ops = fp["Operations"].astype(str).values if "Operations" in fp.columns else []
         self.peaking = any(o != "run-of-river" for o in ops)
-        cache = {}
+        cache, ror = {}, {}
         for d, (scenario, q) in enumerate(self.day_rows):
             key = (scenario, q)
-            if self.peaking or key not in cache:
-                th, _, hd, _ = sim.daily_hours(self.ctx.q_dict(q, scenario), scenario)
-                cache[key] = (float(np.sum(th)), dict(hd))
+            if key not in cache or self.peaking:
+                if self.peaking:
+                    th, _, hd, _ = sim.daily_hours(self.ctx.q_dict(q, scenario), scenario)
+                    cache[key] = (float(np.sum(th)), dict(hd))
+                else:
+                    if scenario not in ror:
+                        ror[scenario] = self._run_of_river_units(scenario)
+                    cache[key] = self._run_of_river_hours(ror[scenario], q)
             self.tot_hours[d], self.hours[d] = cache[key]
+
+    # Run-of-river plants (stryke.py:2432-2470): which units get an hours entry depends on the day's flow only through
+    # the point where the cumulative capacity passes min(production flow, station capacity).  The unit order, keys and
+    # hours come from ONE call of the API mirror per scenario; the per-day part is then a walk over a few floats
+    # (identical results: tests/test_host_logic.py compares with simulation.daily_hours day by day).
+    def _run_of_river_units(self, scenario):
+        sim = self.sim
+        probe = self.ctx.q_dict(1.0e30, scenario)          # flow above every capacity: every unit gets its entry
+        _, _, hours_dict, _ = sim.daily_hours(probe, scenario)
+        ops_df = sim.operating_scenarios_df[sim.operating_scenarios_df.Scenario == scenario]
+        order = list(hours_dict.keys())                      # facility by facility, units by op_order
+        key_col = sim.unit_params.index.name or "index"
+        per_fac = []
+        for facility in ops_df.Facility.unique():
+            fac_units = sim.unit_params[sim.unit_params.Facility == facility]
+            if not fac_units.index.equals(pd.RangeIndex(len(fac_units))):
+                fac_units = fac_units.reset_index(drop=fac_units.index.name in fac_units.columns)
+            fac_units = fac_units.sort_values(by="op_order")
+            units = []
+            for i, row in fac_units.iterrows():
+                if ops_df[ops_df.Unit == row["Unit"]].empty:
+                    continue
+                key = row.get(key_col, None) if key_col in fac_units.columns else None
+                if key is None or (isinstance(key, float) and np.isnan(key)):
+                    key = row.get("Unit", None)
+                if key is None or (isinstance(key, float) and np.isnan(key)):
+                    key = i
+                units.append((str(key), float(row["Qcap"])))
+            per_fac.append((facility, probe["env_Q"][facility], probe["bypass_Q"][facility], probe["sta_cap"][facility], units))
+        return per_fac, {k: hours_dict[k] for k in order}
+
+    @staticmethod
+    def _run_of_river_hours(prepared, q):
+        per_fac, all_hours = prepared
+        hours = {}
+        for facility, env_q, byp_q, sta_cap, units in per_fac:
+            limit = min(q - env_q - byp_q, sta_cap)
+            cum = 0.0
+            for key, cap in units:
+                hours[key] = all_hours[key]
+                if cum + cap <= limit:
+                    cum += cap
+                else:
+                    break
+        return float(sum(hours.values())), hours
 
     # ---- the cell list, engine order: group -> day -> iteration ----------------------------------------------
     def _cells(self):
@@ -382,7 +432,8 @@ def _route_and_hours(plan, g, suc, pair_order, fresh, day_rows, dates, cell_hour
     I, D, P = suc.shape
     movable = fac.pair_move[pair_order] < fac.n_moves - 1
     nodes = fac.pair_node[pair_order]
-    rf_rows, uh_rows = [], []
+    rf = {"iteration": [], "day": [], "route": [], "discharge_cfs": []}       # column pieces, ONE frame per call at the end
+    uh = {"iteration": [], "day": [], "route": [], "hours": [], "discharge_cfs": []}
     unit_pos = {u: j for j, u in enumerate(fac.unit_names)}
     for j, d in enumerate(day_rows):
         its = np.nonzero(fresh[:, j])[0]
@@ -396,10 +447,11 @@ def _route_and_hours(plan, g, suc, pair_order, fresh, day_rows, dates, cell_hour
             names = list((plan.hours[d] or {}).keys())
             H = np.tile(np.array([float(plan.hours[d][k]) for k in names]), (its.size, 1)) if names else None
         if names:
-            uh_rows.append(pd.DataFrame({
-                "scenario": str(g.scenario), "iteration": np.repeat(its, len(names)).astype(int), "day": dates[d],
-                "route": np.tile(np.array(names, dtype=object), its.size).astype(str), "hours": H.ravel(),
-                "discharge_cfs": np.tile(np.array([alloc.get(str(k), np.nan) for k in names]), its.size)}))
+            uh["iteration"].append(np.repeat(its, len(names)).astype(np.int64))
+            uh["day"].append(np.full(its.size * len(names), dates[d]))
+            uh["route"].append(np.tile(np.array([str(k) for k in names], dtype=object), its.size))
+            uh["hours"].append(np.asarray(H, dtype=np.float64).ravel())
+            uh["discharge_cfs"].append(np.tile(np.array([alloc.get(str(k), np.nan) for k in names]), its.size))
         live = (suc[its, j, :] > 0) & movable[None, :]              # a live fish stood at this pair before a move
         masks, inverse = np.unique(live, axis=0, return_inverse=True)
         inverse = np.asarray(inverse).ravel()
@@ -415,8 +467,20 @@ def _route_and_hours(plan, g, suc, pair_order, fresh, day_rows, dates, cell_hour
             if not rec:
                 continue
             who = its[inverse == m]
-            routes = np.array(list(rec.keys()), dtype=object).astype(str)
-            rf_rows.append(pd.DataFrame({"scenario": str(g.scenario), "iteration": np.repeat(who, len(routes)).astype(int),
-                                         "day": dates[d], "route": np.tile(routes, who.size),
-                                         "discharge_cfs": np.tile(np.array(list(rec.values())), who.size)}))
+            routes = np.array([str(k) for k in rec.keys()], dtype=object)
+            rf["iteration"].append(np.repeat(who, len(routes)).astype(np.int64))
+            rf["day"].append(np.full(who.size * len(routes), dates[d]))
+            rf["route"].append(np.tile(routes, who.size))
+            rf["discharge_cfs"].append(np.tile(np.array(list(rec.values()), dtype=np.float64), who.size))
+
+    def frame(cols, order):
+        if not cols["iteration"]:
+            return []
+        data = {"scenario": str(g.scenario)}
+        data.update({k: np.concatenate(cols[k]) for k in order})
+        df = pd.DataFrame(data)
+        df["route"] = df["route"].astype(str)
+        return [df]
+    rf_rows = frame(rf, ("iteration", "day", "route", "discharge_cfs"))
+    uh_rows = frame(uh, ("iteration", "day", "route", "hours", "discharge_cfs"))
     return rf_rows, uh_rows

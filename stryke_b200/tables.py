@@ -129,13 +129,19 @@ class RunContext:
 
     def q_dict(self, curr_Q, scenario):
         """stryke.py:2930-2962."""
-        fp = self.sim.facility_params
-        rows = fp[fp.Scenario == scenario] if "Scenario" in fp.columns else fp
-        Q = {"curr_Q": curr_Q, "min_Q": {}, "env_Q": {}, "bypass_Q": {}, "sta_cap": dict(self.sta_cap)}
-        for fac, row in rows.iterrows():
-            Q["min_Q"][fac] = row["Min_Op_Flow"]
-            Q["env_Q"][fac] = row["Env_Flow"]
-            Q["bypass_Q"][fac] = row["Bypass_Flow"]
+        cache = self.__dict__.setdefault("_q_static", {})
+        if scenario not in cache:          # everything but curr_Q depends on the scenario only
+            fp = self.sim.facility_params
+            rows = fp[fp.Scenario == scenario] if "Scenario" in fp.columns else fp
+            base = {"min_Q": {}, "env_Q": {}, "bypass_Q": {}}
+            for fac, row in rows.iterrows():
+                base["min_Q"][fac] = row["Min_Op_Flow"]
+                base["env_Q"][fac] = row["Env_Flow"]
+                base["bypass_Q"][fac] = row["Bypass_Flow"]
+            cache[scenario] = base
+        base = cache[scenario]
+        Q = {"curr_Q": curr_Q, "min_Q": dict(base["min_Q"]), "env_Q": dict(base["env_Q"]), "bypass_Q": dict(base["bypass_Q"]),
+             "sta_cap": dict(self.sta_cap)}
         for u in self.units:
             Q[u] = self.q_cap[u]
         return Q

@@ -199,3 +199,22 @@ def test_day_tables_reproduce_the_reference_routing_probabilities(case):
         assert np.array_equal(days.edge_cdf[d, e0:e1], want), (rec["location"], days.edge_cdf[d, e0:e1], want)
         checked += 1
     assert checked == len(g.meta["routing"])
+
+
+@pytest.mark.parametrize("fixture,kw", [("c2_facility", dict(n_fish=10, iterations=1, days=12, curr_Q=3000.0)),
+                                        ("c5_cascade", dict(n_fish=10, iterations=1, days=9, curr_Q=1500.0)),
+                                        ("cabot_station", dict(iterations=1, days=20, seed=2, median_Q=4000.0)),
+                                        ("random_facility", dict(seed=4, n_fish=10, days=9)),
+                                        ("random_facility", dict(seed=11, n_fish=10, days=9))])
+def test_run_plan_hours_equal_the_daily_hours_method(fixture, kw):
+    """RunPlan's per-day walk for run-of-river plants vs the API mirror ``simulation.daily_hours`` (stryke.py:2309-2503)
+    called day by day: same total hours, same per-unit dict (keys, order, values)."""
+    import gpu_util as G
+    from oracle import fixtures
+    prj = getattr(fixtures, fixture)(**kw)
+    sim, plan = G.make_plan(prj, "hours")
+    assert not plan.peaking
+    for d, (scenario, q) in enumerate(plan.day_rows):
+        th, _, hd, _ = sim.daily_hours(plan.ctx.q_dict(q, scenario), scenario)
+        assert float(np.sum(th)) == plan.tot_hours[d]
+        assert list(hd.items()) == list(plan.hours[d].items())
