@@ -22,6 +22,17 @@ logger = logging.getLogger(__name__)
 CFS_TO_CMS = 0.02831683199881    # stryke.py:3253
 
 
+def _dist_rank_world():
+    """(rank, world size) of an initialised torch.distributed job, else (0, 1)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
 def _flag(name, default="0"):
     return str(os.environ.get(name, default)).strip().lower() in ("1", "true", "yes", "on")
 
@@ -277,16 +288,27 @@ def run_simulation(sim, injected=None, trace=None):
     plan.check_fixed_counts()
     max_fish, max_rows, M = plan.fish_cap()
     cap = min(max_fish, max_rows // M)
+    rank, world = _dist_rank_world()
     try:
-        res = engine.run_cells(plan.fac, plan.days, plan.species_table, plan.cell_day, plan.cell_species, plan.cell_id,
-                               device=sim.device, precision=sim.precision, seed=sim.seed, max_daily_fish=cap,
-                               injected=injected, trace=trace)
+        if world > 1 and injected is None and trace is None:
+            # one process per GPU (torchrun): every rank simulates its block of cells, ONE all-reduce gives every rank the
+            # full tallies; rank 0 writes the frames (Philox is keyed by the cell, so the result does not depend on world)
+            from .distributed import run_sharded
+            n_t, d_t, s_t = run_sharded(plan, rank, world, device=sim.device, precision=sim.precision, seed=sim.seed,
+                                        max_daily_fish=cap)
+            res = engine.CellResult(n_t.cpu().numpy(), d_t.cpu().numpy().view(np.uint32), s_t.cpu().numpy().view(np.uint32), None)
+        else:
+            res = engine.run_cells(plan.fac, plan.days, plan.species_table, plan.cell_day, plan.cell_species, plan.cell_id,
+                                   device=sim.device, precision=sim.precision, seed=sim.seed, max_daily_fish=cap,
+                                   injected=injected, trace=trace)
     except _abi.StrykeError as exc:
         if exc.code == _abi.E_MAX_FISH:
             raise ValueError(f"{exc}. Adjust entrainment inputs or raise STRYKE_MAX_DAILY_FISH / "
                              "STRYKE_MAX_DAILY_STATE_ROWS deliberately.") from exc
         raise
     sim._last_plan, sim._last_result = plan, res
+    if rank != 0:          # the frames are written once
+        return None
     frames = assemble_frames(sim, plan, res)
     # ---- optional per-fish table (STRYKE_STORE_SIM_TABLE, stryke.py:116, :3243-3249) ---------------------------------
     fish_tables = {}

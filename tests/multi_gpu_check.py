@@ -41,6 +41,34 @@ def main():
         dist.all_reduce(flag)
         if int(flag.item()):
             raise SystemExit(f"{name}: sharded result differs on {int(flag.item())} rank(s)")
+    # the class API: sim.run() under torchrun shards by itself; rank 0 writes the frames a single GPU would write
+    import shutil
+    import tempfile
+    import pandas as pd
+    from stryke_b200 import runner
+    from stryke_b200.store import open_store
+    prj = fixtures.c3_population(n_species=4, iterations=12, days=15)
+    tmp = tempfile.mkdtemp(prefix=f"mg_run_{rank}_")
+    sim = G.make_sim(prj, "sharded", proj_dir=tmp)
+    sim.device = local
+    with contextlib.redirect_stdout(io.StringIO()):
+        sim.run()
+    ok = 1
+    if rank == 0:
+        single = G.make_sim(prj, "single", proj_dir=tmp)
+        single.device = local
+        plan1 = runner.RunPlan(single)
+        res1 = engine.run_cells(plan1.fac, plan1.days, plan1.species_table, plan1.cell_day, plan1.cell_species, plan1.cell_id,
+                                device=local, precision=single.precision, seed=single.seed, max_daily_fish=10 ** 7)
+        want = runner.assemble_frames(single, plan1, res1)
+        with open_store(sim.hdf_path, mode="r") as st:
+            ok = int(all(st[k].reset_index(drop=True).equals(want[k].reset_index(drop=True)) for k in ("Daily", "State_Daily", "Unit_Hours")))
+        print(f"rank 0: sim.run() under torchrun wrote the single-GPU frames: {bool(ok)} ({len(want['Daily'])} Daily rows)", flush=True)
+    flag = torch.tensor([0 if ok else 1], device=f"cuda:{local}")
+    dist.all_reduce(flag)
+    shutil.rmtree(tmp, ignore_errors=True)
+    if int(flag.item()):
+        raise SystemExit("sim.run() under torchrun differs from the single-GPU frames")
     dist.destroy_process_group()
 
 
