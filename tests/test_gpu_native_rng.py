@@ -211,7 +211,10 @@ def test_full_size_conservation_properties(fixture, kw):
                                         ("c3_population", dict(n_species=4, iterations=60, days=10)),
                                         # 13 nodes in one level: the multi-word packed tallies of the specialised kernel
                                         ("cabot_station", dict(iterations=2, days=6, seed=3, median_Q=7000.0, fish=120000.0)),
-                                        ("cabot_station", dict(iterations=40, days=30, seed=1))]
+                                        ("cabot_station", dict(iterations=40, days=30, seed=1)),
+                                        # 38 moves / 73 pairs: move loop not unrolled, ballot tallies, 3 pair rows per lane
+                                        ("c5_cascade", dict(n_fish=30000, iterations=2, days=2, dams=9)),
+                                        ("c5_cascade", dict(n_fish=30000, iterations=2, days=2, dams=7))]
                          + [("random_facility", dict(seed=s, n_fish=40000, iterations=2, days=4, baro=bool(s % 2))) for s in range(10)])
 def test_fast_kernel_equals_general_kernel(fixture, kw):
     """passage_fast_kernel (throughput variant) vs passage_kernel<float, native> (the template that is validated

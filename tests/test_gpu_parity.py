@@ -111,6 +111,7 @@ def test_fp32_injected_tallies_statistically_identical(case):
     ("c5_cascade", dict(n_fish=60000, iterations=1, days=2)),
     ("c4_barotrauma", dict(n_fish=50000, iterations=2, days=1, habitat="Benthic")),
     ("cabot_station", dict(iterations=1, days=3, seed=5, median_Q=6000.0, fish=30000.0)),
+    ("c5_cascade", dict(n_fish=8000, iterations=1, days=2, dams=9)),
 ] + [("random_facility", dict(seed=s, n_fish=15000, days=4, baro=bool(s % 2))) for s in range(10)])
 def test_large_cells_oracle_draws_bit_exact(fixture, kw):
     """Sizes the reference cannot reach in test time: the oracle generates the slot-tagged draws, the GPU (fp64,
