@@ -233,3 +233,36 @@ def test_world_size_2_sharding_and_allreduce_over_gloo(tmp_path):
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29653", WORLD_SIZE="2")
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r))) for r in range(2)]
     assert [p.wait(timeout=240) for p in procs] == [0, 0]
+
+
+C_CLIENT = r'''
+#include <stdio.h>
+#include <string.h>
+#include "stryke_b200.h"
+/* what a C (or cgo / JNI) caller of the boundary does: link the shared library, call through the header */
+int main(void) {
+  if (stryke_b200_abi_version() != STRYKE_B200_ABI_VERSION) return 2;
+  int n_dev = stryke_b200_device_count();
+  StrykeFacility fac; StrykeDayTables days; StrykeSpeciesTable sp; StrykeCells cells; StrykeOpts opts; StrykeTallies out;
+  memset(&fac, 0, sizeof fac); memset(&days, 0, sizeof days); memset(&sp, 0, sizeof sp); memset(&cells, 0, sizeof cells);
+  memset(&opts, 0, sizeof opts); memset(&out, 0, sizeof out);
+  int rc = stryke_b200_run(&fac, &days, &sp, &cells, &opts, &out);     /* empty tables: must be refused, not crash */
+  printf("%d %d %s\n", n_dev, rc, stryke_b200_last_error());
+  return rc == 0 ? 3 : 0;
+}
+'''
+
+
+def test_a_plain_c_program_links_against_the_boundary(tmp_path):
+    """The boundary is a C ABI: the header compiles as C (gcc -std=c99 -Wall -Werror), a C program links against
+    libstryke_b200.so and gets an error code + message (never a crash) for invalid input."""
+    from stryke_b200 import build as B
+    lib = B.build()
+    exe = str(tmp_path / "c_client")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                    "-L", os.path.dirname(lib), "-lstryke_b200", "-Wl,-rpath," + os.path.dirname(lib)],
+                   input=C_CLIENT.encode(), check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    n_dev, rc, msg = r.stdout.strip().split(" ", 2)
+    assert int(rc) < 0 and msg
