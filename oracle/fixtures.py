@@ -329,7 +329,17 @@ def peaking_facility(n_fish=200, iterations=2, days=3, curr_Q=9000.0):
     return prj
 
 
-def cabot_station(iterations=2, days=6, seed=0, median_Q=9000.0, fish=NAN):
+def example_v250304(iterations=2, days=30, seed=0, median_Q=3000.0, fish=NAN):
+    """BASELINE.json configs[0]: the reference's example project Spreadsheet Interface/Input_Spreadsheet_v250304.xlsx —
+    one node, one Francis unit (U1 Cabot), barotrauma on (fb_depth 10 ft, elevation_head 2 ft), Micropterus with a Log
+    Normal entrainment rate — with the tables exactly as the workbook holds them (tests/golden/
+    example_v250304_project.json, oracle/extract_example.py) and the synthetic hydrograph SURVEY.md §8(d) prescribes in
+    place of the USGS gage (Q = 3000 exp(0.5 N(0,1)), seeded)."""
+    return cabot_station(iterations, days, seed, median_Q, fish, source="example_v250304_project.json", name="example_v250304")
+
+
+def cabot_station(iterations=2, days=6, seed=0, median_Q=9000.0, fish=NAN, source="cabot_station_project.json",
+                  name="cabot_station"):
     """The reference's own complex-network example (Spreadsheet Interface/Examples/
     Run_of_River_Complex_Network_Cabot_Station.xlsx: 20 nodes, 31 edges, 11 Francis units in two facilities that share
     one spillway, a 0.05 / 0.95 edge-weight split at the canal, Micropterus with a Log Normal entrainment rate).  The
@@ -338,7 +348,7 @@ def cabot_station(iterations=2, days=6, seed=0, median_Q=9000.0, fish=NAN):
     import datetime as _dt
     import json
     import os
-    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "cabot_station_project.json")
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", source)
     with open(path) as fh:
         raw = json.load(fh)
     nan = lambda v: NAN if v is None else v
@@ -356,12 +366,15 @@ def cabot_station(iterations=2, days=6, seed=0, median_Q=9000.0, fish=NAN):
     q = median_Q * np.exp(0.5 * np.random.default_rng(seed).standard_normal(days))
     scen = raw["flow_scenarios"][0]
     pop = {k: nan(v) for k, v in raw["population"][0].items() if k not in ("Notes", "N=")}
-    pop.update(Iterations=iterations, vertical_habitat="Benthic", beta_0=NAN, beta_1=NAN)
+    pop.update(Iterations=iterations)
+    pop.setdefault("vertical_habitat", "Benthic")
+    pop.setdefault("beta_0", NAN)
+    pop.setdefault("beta_1", NAN)
     if not (isinstance(fish, float) and math.isnan(fish)):     # fixed count per day instead of the fitted entrainment rate
         pop.update(Fish=float(fish), shape=NAN, location=NAN, scale=NAN, dist=NAN, max_ent_rate=NAN, occur_prob=1.0)
-    max_rn = max(int(n["Location"].split("_")[2]) for n in raw["nodes"] if n["Location"].startswith("river_node_"))
+    max_rn = max([int(n["Location"].split("_")[2]) for n in raw["nodes"] if n["Location"].startswith("river_node_")] + [0])
     return dict(
-        name="cabot_station", output_units=raw["output_units"], max_river_node=max_rn,
+        name=name, output_units=raw["output_units"], max_river_node=max_rn,
         nodes=[dict(n) for n in raw["nodes"]],
         edges=[dict(e) for e in raw["edges"]],
         unit_params=units,

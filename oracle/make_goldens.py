@@ -30,6 +30,8 @@ CASES = {
     "c2_low_flow": ("c2_facility", dict(n_fish=120, iterations=1, days=3, curr_Q=600.0), 7, {}),
     # the reference's own complex-network example workbook (tables extracted by oracle/extract_example.py)
     "cabot_station": ("cabot_station", dict(iterations=2, days=24, seed=0), 8, {"Micropterus": "Centrarchidae"}),
+    # BASELINE.json configs[0]: the example project workbook itself (one Francis unit, barotrauma on)
+    "example_v250304": ("example_v250304", dict(iterations=2, days=45, seed=0), 10, {"Micropterus": "Centrarchidae"}),
     "cabot_station_fish": ("cabot_station", dict(iterations=1, days=4, seed=3, median_Q=7000.0, fish=300.0), 9,
                            {"Micropterus": "Centrarchidae"}),
 }

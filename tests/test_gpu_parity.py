@@ -60,7 +60,7 @@ def test_fp64_injected_replay_matches_reference_bit_exact(case):
 
 
 @pytest.mark.parametrize("case", ["c2_kaplan_francis", "c2_barotrauma", "c4_propeller_baro", "c5_cascade", "c1_single_unit",
-                                  "cabot_station_fish"])
+                                  "cabot_station_fish", "example_v250304"])
 @pytest.mark.parametrize("precision,tol", [(64, 1e-6), (32, 1e-4)])
 def test_per_fish_probabilities_within_tolerance(case, precision, tol):
     """Strike and barotrauma survival AND mortality probabilities of every evaluated (fish, move)."""
