@@ -1212,7 +1212,8 @@ static TallyPlan plan_tally(const std::vector<MoveRec>& moves, const std::vector
   fill.push_back(5);
   for (int j = 0; j < 3; ++j) field(T.W_CAUSE, 10 * j, 10, 3, 2 + j, 1);
   T.HOLD = std::min(63, 1023 / std::max(1, n_cause));
-  if ((int)fill.size() > 24 || T.fields.size() > 250 || T.HOLD < 4) return TallyPlan{};
+  // n_cause <= 31: the single-tile drain sums whole words, 32 lanes x n_cause must fit the 10-bit cause fields
+  if ((int)fill.size() > 24 || T.fields.size() > 250 || T.HOLD < 4 || n_cause > 31) return TallyPlan{};
   T.NW = (int)fill.size();
   return T;
 }
@@ -1269,9 +1270,30 @@ static std::string generate(const std::vector<MoveRec>& moves, const std::vector
       o << (f ? ", " : "") << "{" << (int)r.w << ", " << (int)r.sh << ", " << (int)r.bits << ", " << (int)r.target << ", " << (int)r.p0 << ", " << (int)r.len << "}";
     }
     o << "};\n    return T[f];\n  }\n";
+    // per-lane views of the same layout for the single-tile drain
+    const int n_lane = 32 * pr;
+    std::vector<uint32_t> lcfg((size_t)n_lane, 0u), dcfg(32, 0u);
+    for (const FieldRec& r : T.fields) {
+      if (r.target == 3) {
+        if (r.p0 < 32) dcfg[r.p0] = (uint32_t)r.w | ((uint32_t)r.sh << 5) | ((r.bits == 10 ? 1u : 0u) << 10) | (1u << 11);
+        continue;
+      }
+      for (int p2 = r.p0; p2 < r.p0 + r.len && p2 < n_lane; ++p2) {
+        if (r.target != 1) lcfg[p2] = (lcfg[p2] & ~0x3ffu) | (uint32_t)r.w | ((uint32_t)r.sh << 5);
+        if (r.target != 0) lcfg[p2] = (lcfg[p2] & ~(0x3ffu << 10)) | ((uint32_t)r.w << 10) | ((uint32_t)r.sh << 15);
+        lcfg[p2] |= 1u << 20;
+      }
+    }
+    o << "  static __device__ uint32_t lane_cfg(int i) {\n    constexpr uint32_t T[" << n_lane << "] = {";
+    for (int i = 0; i < n_lane; ++i) o << (i ? ", " : "") << lcfg[i] << "u";
+    o << "};\n    return T[i];\n  }\n  static __device__ uint32_t daily_cfg(int i) {\n    constexpr uint32_t T[32] = {";
+    for (int i = 0; i < 32; ++i) o << (i ? ", " : "") << dcfg[i] << "u";
+    o << "};\n    return T[i];\n  }\n";
   } else {
     o << "  static __device__ constexpr LevelTally tally(int) { return LevelTally{}; }\n"
-      << "  static __device__ constexpr FieldRec field(int) { return FieldRec{}; }\n";
+      << "  static __device__ constexpr FieldRec field(int) { return FieldRec{}; }\n"
+      << "  static __device__ constexpr uint32_t lane_cfg(int) { return 0u; }\n"
+      << "  static __device__ constexpr uint32_t daily_cfg(int) { return 0u; }\n";
   }
   o << "};\n}  // namespace stryke\n"
     << "extern \"C\" __global__ void __launch_bounds__(256, " << spec_min_blocks() << ") passage_spec(const stryke::KParams P, const stryke::FastTables FT,\n"

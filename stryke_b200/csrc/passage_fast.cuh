@@ -104,6 +104,8 @@ struct RuntimeTables {
   static __device__ __forceinline__ int pair_node(const FastTables& FT, int p) { return (int)FT.pair_node[p]; }
   static __device__ __forceinline__ LevelTally tally(int) { return LevelTally{}; }
   static __device__ __forceinline__ FieldRec field(int) { return FieldRec{}; }
+  static __device__ __forceinline__ uint32_t lane_cfg(int) { return 0u; }
+  static __device__ __forceinline__ uint32_t daily_cfg(int) { return 0u; }
 };
 
 template <class TP, int PR, bool BARO>
@@ -147,7 +149,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   const int64_t G = (int64_t)gridDim.x * WARPS, CH = P.chunk_tiles;
   int64_t chunk = (int64_t)blockIdx.x * WARPS + wid;
   int64_t c = -1, c_begin = 0, c_end = 0;             // current cell and its tile range [c_begin, c_end)
-  int cur_day = -1;
+  int cur_day = -1, cur_species = -1;
   int64_t cur_cell = -1;
   float sp_ls = 0, sp_ll = 0, sp_lsc = 0, sp_lm = 0, sp_lsd = 0, sp_wr = 0, sp_uc = 0, sp_d1 = 0, sp_dd = 0, sp_b0 = 0, sp_b1 = 0;
   int sp_mode = 0, n_c = 0;
@@ -179,6 +181,44 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
             if (F.target != 0) acc_suc[r] += mine ? v : 0u;
           }
         }
+      }
+#pragma unroll
+      for (int j = 0; j < TP::NW; ++j) W[j] = 0;
+      held = 0;
+    }
+  };
+
+  // Single-tile drain (most cells of a population-mode run hold fewer than 32 fish): after ONE tile every field of a lane
+  // is at most its per-tile maximum, so whole words can be summed (one REDUX per word instead of one per field) and
+  // every lane picks the fields of its own pairs.  lane_cfg: arrivals word [0:5) shift [5:10), survivors word [10:15)
+  // shift [15:20), pair exists [20]; daily_cfg: word [0:5) shift [5:10), 10-bit field [10], column exists [11].
+  uint32_t lcfg[PR], dcfg = 0;
+#pragma unroll
+  for (int r = 0; r < PR; ++r) lcfg[r] = PK ? TP::lane_cfg(lane + 32 * r) : 0u;
+  if (PK) dcfg = TP::daily_cfg(lane);
+  auto drain_one_tile = [&]() {
+    if constexpr (PK) {
+      uint32_t S[TP::NW];
+#pragma unroll
+      for (int j = 0; j < TP::NW; ++j) S[j] = __reduce_add_sync(0xffffffffu, W[j]);
+#pragma unroll
+      for (int r = 0; r < PR; ++r) {
+        const uint32_t cf = lcfg[r];
+        const uint32_t cw = cf & 31u, sw = (cf >> 10) & 31u;
+        uint32_t vc = S[0], vs = S[0];
+#pragma unroll
+        for (int j = 1; j < TP::NW; ++j) { vc = cw == (uint32_t)j ? S[j] : vc; vs = sw == (uint32_t)j ? S[j] : vs; }
+        const uint32_t m = (cf >> 20) & 1u ? 63u : 0u;
+        acc_cnt[r] += (vc >> ((cf >> 5) & 31u)) & m;
+        acc_suc[r] += (vs >> ((cf >> 15) & 31u)) & m;
+      }
+      {
+        const uint32_t dw = dcfg & 31u;
+        uint32_t vd = S[0];
+#pragma unroll
+        for (int j = 1; j < TP::NW; ++j) vd = dw == (uint32_t)j ? S[j] : vd;
+        const uint32_t m = (dcfg >> 11) & 1u ? ((dcfg >> 10) & 1u ? 1023u : 63u) : 0u;
+        acc_daily += (vd >> ((dcfg >> 5) & 31u)) & m;
       }
 #pragma unroll
       for (int j = 0; j < TP::NW; ++j) W[j] = 0;
@@ -234,7 +274,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
     if (fresh) {
       fresh = false;
       if (cur_cell >= 0) {
-        if (PK && held) drain();
+        if (PK && held) { if (held == 1) drain_one_tile(); else drain(); }
         flush(cur_cell);
       }
       cur_cell = c;
@@ -242,11 +282,15 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
       const uint64_t cid = P.cell_id[c];
       cid_lo = (uint32_t)cid; cid_hi = (uint32_t)(cid >> 32);
       const int s = P.cell_species[c];
-      if (s < n_sp) {
+      if (s == cur_species) {
+        // cells are ordered group by group: the neighbours of a cell almost always belong to the same species
+      } else if (s < n_sp) {
+        cur_species = s;
         const float* q = s_species + s * SPW;
         sp_ls = q[0]; sp_ll = q[1]; sp_lsc = q[2]; sp_lm = q[3]; sp_lsd = q[4]; sp_mode = (int)q[5];
         sp_wr = q[6]; sp_uc = q[7]; sp_d1 = q[8]; sp_dd = q[9] - q[8]; sp_b0 = q[10] * 1.44269504f; sp_b1 = q[11];
       } else {
+        cur_species = s;
         const double* q = P.species + (int64_t)s * STRYKE_SPECIES_W;
         sp_ls = (float)q[0]; sp_ll = (float)q[1]; sp_lsc = (float)q[2]; sp_lm = (float)q[3]; sp_lsd = (float)q[4];
         sp_mode = (int)q[5]; sp_wr = (float)q[6]; sp_uc = (float)q[7]; sp_d1 = (float)q[8];
@@ -444,7 +488,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
     }
   }
   }
-  if (PK && held) drain();
+  if (PK && held) { if (held == 1) drain_one_tile(); else drain(); }
   if (cur_cell >= 0) flush(cur_cell);
 }
 
