@@ -1,0 +1,65 @@
+"""Edge cases of the device path: empty inputs, cells without fish, one-fish cells, one huge cell, many tiny cells."""
+import numpy as np
+import pytest
+
+from oracle import fixtures
+import gpu_util as G
+from stryke_b200 import engine
+
+pytestmark = pytest.mark.gpu
+
+
+def run(plan, variant=0, cells=slice(None), seed=9, cap=2_000_000_000):
+    return engine.run_cells(plan.fac, plan.days, plan.species_table, plan.cell_day[cells], plan.cell_species[cells],
+                            plan.cell_id[cells], precision=32, seed=seed, max_daily_fish=cap, kernel_variant=variant)
+
+
+def test_no_cells_is_not_an_error():
+    sim, plan = G.make_plan(fixtures.c2_facility(n_fish=10, iterations=1, days=1), "empty")
+    res = run(plan, cells=slice(0, 0))
+    assert res.cell_n.shape == (0,) and res.daily.shape == (0, 5) and res.state_daily.shape[0] == 0
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_species_never_present_gives_zero_rows(variant):
+    prj = fixtures.c3_population(n_species=3, iterations=20, days=5)
+    for row in prj["population"]:
+        row["occur_prob"] = 0.0
+    sim, plan = G.make_plan(prj, "absent")
+    res = run(plan, variant)
+    assert (res.cell_n == 0).all() and not res.daily.any() and not res.state_daily.any()
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_one_fish_cells(variant):
+    sim, plan = G.make_plan(fixtures.c2_facility(n_fish=1, iterations=300, days=3), "one")
+    res = run(plan, variant)
+    assert (res.cell_n == 1).all()
+    sd = res.state_daily.astype(np.int64)
+    assert (sd[:, 0, 1] == 1).all() and (sd[..., 1].sum(axis=1) <= plan.fac.n_moves).all() and (sd[..., 0] <= sd[..., 1]).all()
+    assert np.array_equal(res.daily, run(plan, 1).daily)
+
+
+def test_one_cell_of_three_hundred_million_fish():
+    """A single cell far beyond any tile / chunk / 16-bit boundary: counters, fish indices and the tile walk in 64 bits."""
+    n = 300_000_000
+    sim, plan = G.make_plan(fixtures.c2_facility(n_fish=n, iterations=1, days=1), "huge")
+    res = run(plan, 3)
+    sd = res.state_daily.astype(np.int64)[0]
+    fac = plan.fac
+    assert res.cell_n[0] == n and sd[0, 1] == n
+    for k in range(1, fac.n_moves):
+        now, prev = slice(fac.level_off[k], fac.level_off[k + 1]), slice(fac.level_off[k - 1], fac.level_off[k])
+        assert sd[now, 1].sum() == sd[prev, 0].sum()
+    again = run(plan, 2)
+    assert np.array_equal(again.state_daily, res.state_daily) and np.array_equal(again.daily, res.daily)
+
+
+def test_many_tiny_cells_population_mode_all_variants_agree():
+    prj = fixtures.c3_population(n_species=6, iterations=400, days=12)
+    sim, plan = G.make_plan(prj, "tiny")
+    a, b, c = (run(plan, v, cap=10 ** 7) for v in (1, 2, 3))
+    assert a.cell_n.sum() > 0 and (a.cell_n > 0).mean() < 0.9
+    for other in (b, c):
+        assert np.array_equal(a.cell_n, other.cell_n) and np.array_equal(a.daily, other.daily)
+        assert np.array_equal(a.state_daily, other.state_daily)
