@@ -130,8 +130,16 @@ def c2_facility(n_fish=1000, iterations=1, days=1, curr_Q=9000.0, baro=False, sc
     )
 
 
-def c3_population(n_species=4, iterations=2, days=5, curr_Q=9000.0, scenarios=("Spring",), baro=False):
-    """C2's facility in population mode: daily counts drawn from EPRI-fitted Pareto / Log Normal / Weibull."""
+# A generalised-extreme-value entrainment rate (population_sim's 'Extreme' branch, stryke.py:2560; the web app's species
+# library holds no such entry, epri.ExtremeFit produces them)
+EXTREME_SPECIES = dict(Species="Perca", **{"Common Name": "Yellow Perch"}, dist="Extreme", shape=-0.35, location=0.004,
+                       scale=0.006, max_ent_rate=1.4, occur_prob=0.58, vertical_habitat="Benthic", beta_0=-4.657,
+                       beta_1=3.41, U_crit=1.3, **{"length shape": 0.45, "length location": 0.0, "length scale": 11.0})
+
+
+def c3_population(n_species=4, iterations=2, days=5, curr_Q=9000.0, scenarios=("Spring",), baro=False, extreme=False):
+    """C2's facility in population mode: daily counts drawn from EPRI-fitted Pareto / Log Normal / Weibull
+    (``extreme=True`` appends a species with a generalised-extreme-value rate)."""
     prj = c2_facility(1, iterations, days, curr_Q, baro=baro, scenario=scenarios[0])
     prj["name"] = "c3"
     pop = []
@@ -144,6 +152,11 @@ def c3_population(n_species=4, iterations=2, days=5, curr_Q=9000.0, scenarios=("
             pop.append(_pop_row(sp, scen, fish=NAN, iterations=iterations, occur_prob=sp["occur_prob"],
                                 shape=sp["shape"], location=sp["location"], scale=sp["scale"], dist=sp["dist"],
                                 max_ent_rate=sp["max_ent_rate"]))
+    if extreme:
+        for scen in scenarios:
+            sp = EXTREME_SPECIES
+            pop.append(_pop_row(sp, scen, fish=NAN, iterations=iterations, occur_prob=sp["occur_prob"], shape=sp["shape"],
+                                location=sp["location"], scale=sp["scale"], dist=sp["dist"], max_ent_rate=sp["max_ent_rate"]))
     prj["population"] = pop
     start = "2023-03-01"
     if days > 300:   # a full synthetic year: lognormal-ish seasonal hydrograph around curr_Q

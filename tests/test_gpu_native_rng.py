@@ -23,7 +23,7 @@ def native(plan, precision=32, seed=11, trace=None, cells=None, blocks_per_sm=0,
 
 # family of the genera in the fixtures (Data/fish_class.csv of the reference; the product resolves them itself from
 # stryke_b200/data/fish_family.json): sets the body-width ratio that decides who is blocked by the trash rack
-FAMILIES = {"Ambloplites": "Centrarchidae", "Micropterus": "Centrarchidae", "Lepomis": "Centrarchidae"}
+FAMILIES = {"Ambloplites": "Centrarchidae", "Micropterus": "Centrarchidae", "Lepomis": "Centrarchidae", "Perca": "Percidae"}
 
 
 def oracle_cells(prj, n_cells, seed=3):
@@ -120,7 +120,7 @@ def test_length_distribution_ks(precision):
 def test_daily_entrainment_count_distribution_ks():
     """Population mode (step 1): per-cell n for Pareto / Log Normal / Weibull species vs the oracle's draws, and the
     presence frequency vs occur_prob."""
-    prj = fixtures.c3_population(n_species=4, iterations=1500, days=4)
+    prj = fixtures.c3_population(n_species=4, iterations=1500, days=4, extreme=True)     # + a generalised-extreme-value species
     sim, plan = G.make_plan(prj, "count")
     res = native(plan, precision=32, cap=10 ** 7)
     rng = np.random.default_rng(9)
@@ -209,6 +209,7 @@ def test_full_size_conservation_properties(fixture, kw):
                                         ("c4_barotrauma", dict(n_fish=100000, iterations=2, days=2, habitat="Benthic")),
                                         ("c1_single_unit", dict(iterations=50, days=40, fish=3000.0)),
                                         ("c3_population", dict(n_species=4, iterations=60, days=10)),
+                                        ("c3_population", dict(n_species=2, iterations=80, days=8, extreme=True)),
                                         # 13 nodes in one level: the multi-word packed tallies of the specialised kernel
                                         ("cabot_station", dict(iterations=2, days=6, seed=3, median_Q=7000.0, fish=120000.0)),
                                         ("cabot_station", dict(iterations=40, days=30, seed=1)),
