@@ -103,7 +103,7 @@ def _hydrograph(days, lo, hi, start="2023-03-01"):
 
 
 def c2_facility(n_fish=1000, iterations=1, days=1, curr_Q=9000.0, baro=False, scenario="Spring",
-                species=SHAD, occur_prob=1.0):
+                species=SHAD, occur_prob=1.0, length_normal=None):
     """SURVEY.md §8(d) C2: river_node_0 -> forebay -> {U1 Kaplan, U2 Kaplan, U3 Francis, bypass_flow, spillway}
     -> tailrace -> river_node_1.  Anadromous mode (Fish = n)."""
     nodes = [("river_node_0", "a priori", 1.0), ("forebay", "a priori", 1.0), ("U1", "Kaplan", 0.0),
@@ -126,7 +126,10 @@ def c2_facility(n_fish=1000, iterations=1, days=1, curr_Q=9000.0, baro=False, sc
         operating_scenarios=[dict(Scenario=scenario, Facility="FacA", Unit=u, Hours=24.0, Prob_Not_Op=NAN,
                                   shape=NAN, location=NAN, scale=NAN) for u in (1, 2, 3)],
         hydrograph=_hydrograph(days, curr_Q * 0.6, curr_Q * 1.4),
-        population=[_pop_row(species, scenario, fish=float(n_fish), iterations=iterations, occur_prob=occur_prob)],
+        population=[_pop_row(species, scenario, fish=float(n_fish), iterations=iterations, occur_prob=occur_prob,
+                             **({} if length_normal is None else {   # lengths ~ |N(mean, sd)| inches (stryke.py:3090)
+                                 "Length_mean": float(length_normal[0]), "Length_sd": float(length_normal[1]),
+                                 "length shape": NAN, "length location": NAN, "length scale": NAN}))],
     )
 
 

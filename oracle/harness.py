@@ -150,7 +150,15 @@ class Recorder:
     # ---- wrappers ---------------------------------------------------------------------------------------------
     def install(self):
         S, sim, rec = self.S, self.sim, self
-        self._orig = dict(uniform=np.random.uniform, random=np.random.random, choice=np.random.choice)
+        self._orig = dict(uniform=np.random.uniform, random=np.random.random, choice=np.random.choice, normal=np.random.normal)
+        o_normal = np.random.normal
+
+        def normal(loc=0.0, scale=1.0, size=None):
+            # fish lengths from Length_mean / Length_sd (stryke.py:3090): the legacy global stream, not the PCG64 one
+            v = o_normal(loc, scale, size)
+            if rec.cur is not None and size is not None and np.size(v) > 1:
+                rec.cur["legacy_normal"] = (float(loc), float(scale), np.array(v, dtype=float).ravel().copy())
+            return v
         o_uniform, o_random = np.random.uniform, np.random.random
         o_sample = np.random.random_sample
 
@@ -200,7 +208,7 @@ class Recorder:
                 rec.routing[(len(rec.cells) - 1, rec._ctx[2])] = (list(map(str, a)), p.copy())
             return np.asarray(a)[idx]
 
-        np.random.uniform, np.random.random, np.random.choice = uniform, random, choice
+        np.random.uniform, np.random.random, np.random.choice, np.random.normal = uniform, random, choice, normal
 
         cls = type(sim)
         o_surv, o_move, o_hours = cls.node_surv_rate, cls.movement, cls.daily_hours
@@ -237,7 +245,8 @@ class Recorder:
         sim.node_surv_rate, sim.movement, sim.daily_hours = node_surv_rate, movement, daily_hours
 
     def uninstall(self):
-        np.random.uniform, np.random.random, np.random.choice = (self._orig[k] for k in ("uniform", "random", "choice"))
+        np.random.uniform, np.random.random, np.random.choice, np.random.normal = (
+            self._orig[k] for k in ("uniform", "random", "choice", "normal"))
         for k in ("node_surv_rate", "movement", "daily_hours"):
             self.sim.__dict__.pop(k, None)
 

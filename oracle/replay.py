@@ -9,24 +9,30 @@ from . import stryke_oracle as O
 
 def cell_normals(cell):
     """Standard normals behind the fish lengths: the last PCG64 ``standard_normal`` batch (stryke.py:3070)."""
-    normals = [p for p in cell["pcg"] if p[0] == "standard_normal"]
     if not cell["moves"]:
         return np.zeros(0)
     n = cell["moves"][0]["n"]
-    z = normals[-1][-1]
+    if "legacy_normal" in cell:      # Length_mean / Length_sd mode: np.random.normal(mean, sd, n), stryke.py:3090
+        loc, scale, x = cell["legacy_normal"]
+        z = (x - loc) / scale
+    else:
+        normals = [p for p in cell["pcg"] if p[0] == "standard_normal"]
+        z = normals[-1][-1]
     assert z.shape[0] == n, (z.shape, n)
     return z
 
 
 def cell_lengths(cell, pop_row):
     """Fish lengths (ft) of a recorded cell."""
+    if "legacy_normal" in cell:
+        return np.abs(cell["legacy_normal"][2]) / 12.0
     return O.lengths_from_normals(cell_normals(cell), pop_row["length shape"], pop_row["length location"],
                                   pop_row["length scale"])
 
 
 def cell_count_draw(cell):
     """The PCG64 draw ``population_sim`` consumed (None in anadromous mode)."""
-    pre = cell["pcg"][:-1] if cell["moves"] else cell["pcg"]
+    pre = cell["pcg"][:-1] if (cell["moves"] and "legacy_normal" not in cell) else cell["pcg"]
     if not pre:
         return None
     return float(pre[0][-1][0])

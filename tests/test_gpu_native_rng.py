@@ -72,6 +72,7 @@ def compare_cells(plan, res, ref, ref_idx):
                                         ("c5_cascade", dict(n_fish=150000, iterations=1, days=2)),
                                         ("c4_barotrauma", dict(n_fish=200000, iterations=1, days=2)),
                                         ("cabot_station", dict(iterations=1, days=2, seed=3, median_Q=7000.0, fish=200000.0)),
+                                        ("c2_facility", dict(n_fish=300000, iterations=1, days=2, length_normal=(40.0, 9.0))),
                                         ("random_facility", dict(seed=3, n_fish=150000, days=3)),
                                         ("random_facility", dict(seed=6, n_fish=150000, days=3, baro=True))])
 def test_route_and_survival_counts_match_oracle_distribution(fixture, kw, precision):
@@ -210,6 +211,7 @@ def test_full_size_conservation_properties(fixture, kw):
                                         ("c1_single_unit", dict(iterations=50, days=40, fish=3000.0)),
                                         ("c3_population", dict(n_species=4, iterations=60, days=10)),
                                         ("c3_population", dict(n_species=2, iterations=80, days=8, extreme=True)),
+                                        ("c2_facility", dict(n_fish=150000, iterations=2, days=2, length_normal=(11.0, 3.5))),
                                         # 13 nodes in one level: the multi-word packed tallies of the specialised kernel
                                         ("cabot_station", dict(iterations=2, days=6, seed=3, median_Q=7000.0, fish=120000.0)),
                                         ("cabot_station", dict(iterations=40, days=30, seed=1)),
