@@ -103,7 +103,7 @@ def _hydrograph(days, lo, hi, start="2023-03-01"):
 
 
 def c2_facility(n_fish=1000, iterations=1, days=1, curr_Q=9000.0, baro=False, scenario="Spring",
-                species=SHAD, occur_prob=1.0, length_normal=None):
+                species=SHAD, occur_prob=1.0, length_normal=None, penstock=False, flows=None):
     """SURVEY.md §8(d) C2: river_node_0 -> forebay -> {U1 Kaplan, U2 Kaplan, U3 Francis, bypass_flow, spillway}
     -> tailrace -> river_node_1.  Anadromous mode (Fish = n)."""
     nodes = [("river_node_0", "a priori", 1.0), ("forebay", "a priori", 1.0), ("U1", "Kaplan", 0.0),
@@ -114,6 +114,10 @@ def c2_facility(n_fish=1000, iterations=1, days=1, curr_Q=9000.0, baro=False, sc
              + [(x, "tailrace", 1.0) for x in mid] + [("tailrace", "river_node_1", 1.0)])
     units = [_unit_row("FacA", 1, "U1", 1, KAPLAN, baro), _unit_row("FacA", 2, "U2", 2, KAPLAN, baro),
              _unit_row("FacA", 3, "U3", 3, FRANCIS, baro)]
+    if penstock:       # U1 and U2 share a penstock that carries less than their capacities (stryke.py:2722-2794, :1700-1790)
+        units[0].update(Penstock_ID="P1", Penstock_Qcap=4200.0)
+        units[1].update(Penstock_ID="P1", Penstock_Qcap=4200.0)
+        units[2].update(Penstock_ID="P2", Penstock_Qcap=NAN)
     return dict(
         name="c2", output_units="imperial", max_river_node=1,
         nodes=[dict(Location=a, Surv_Fun=b, Survival=c) for a, b, c in nodes],
@@ -125,7 +129,8 @@ def c2_facility(n_fish=1000, iterations=1, days=1, curr_Q=9000.0, baro=False, sc
         flow_scenarios=_scenario_rows([scenario], months=_months_for(days)),
         operating_scenarios=[dict(Scenario=scenario, Facility="FacA", Unit=u, Hours=24.0, Prob_Not_Op=NAN,
                                   shape=NAN, location=NAN, scale=NAN) for u in (1, 2, 3)],
-        hydrograph=_hydrograph(days, curr_Q * 0.6, curr_Q * 1.4),
+        hydrograph=(_hydrograph(days, curr_Q * 0.6, curr_Q * 1.4) if flows is None else
+                    [dict(h, Discharge=float(q)) for h, q in zip(_hydrograph(len(flows), 1.0, 1.0), flows)]),
         population=[_pop_row(species, scenario, fish=float(n_fish), iterations=iterations, occur_prob=occur_prob,
                              **({} if length_normal is None else {   # lengths ~ |N(mean, sd)| inches (stryke.py:3090)
                                  "Length_mean": float(length_normal[0]), "Length_sd": float(length_normal[1]),

@@ -30,6 +30,8 @@ CASES = {
     "c3_extreme": ("c3_population", dict(n_species=1, iterations=3, days=10, extreme=True), 11,
                    {"Ambloplites": "Centrarchidae", "Perca": "Percidae"}),
     "c2_normal_lengths": ("c2_facility", dict(n_fish=200, iterations=1, days=2, length_normal=(11.0, 3.5)), 12, {}),
+    "c2_penstock": ("c2_facility", dict(n_fish=200, iterations=1, days=3, curr_Q=6500.0, penstock=True), 13, {}),
+    "c2_zero_flow": ("c2_facility", dict(n_fish=80, iterations=1, days=4, flows=[0.0, 250.0, 9000.0, 0.0]), 14, {}),
     "c2_low_flow": ("c2_facility", dict(n_fish=120, iterations=1, days=3, curr_Q=600.0), 7, {}),
     # the reference's own complex-network example workbook (tables extracted by oracle/extract_example.py)
     "cabot_station": ("cabot_station", dict(iterations=2, days=24, seed=0), 8, {"Micropterus": "Centrarchidae"}),

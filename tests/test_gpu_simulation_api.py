@@ -39,7 +39,7 @@ def fresh_sim(prj, tmp_path, name):
 
 
 @pytest.mark.parametrize("case", ["c2_kaplan_francis", "c2_barotrauma", "c5_cascade", "c3_population", "c1_single_unit",
-                                  "c2_low_flow", "c4_propeller_baro", "cabot_station", "cabot_station_fish", "example_v250304", "c3_extreme", "c2_normal_lengths"])
+                                  "c2_low_flow", "c4_propeller_baro", "cabot_station", "cabot_station_fish", "example_v250304", "c3_extreme", "c2_normal_lengths", "c2_penstock", "c2_zero_flow"])
 def test_run_with_injected_uniforms_writes_the_reference_frames(case, tmp_path):
     g = Golden(case)
     sim = fresh_sim(g.prj, tmp_path, case)
