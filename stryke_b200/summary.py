@@ -128,7 +128,12 @@ def _summarize(sim):
             state_daily["state"] = state_daily["state"].astype(str)
         moves = [int(m) for m in sim.moves]
         final_move = max(moves) if moves else 0
-        for spc in species:
+        for si, spc in enumerate(species):
+            if si > 0:
+                # the reference rebuilds the yearly summary inside its species loop (stryke.py:3770-3862 sit under
+                # `for i in species`): the table of the last pass is the one that is kept, but every pass draws its
+                # bootstraps from the global stream — replayed here so that a seeded run stays draw-for-draw identical
+                yearly_summary(sim.daily_summary, draws_only=True)
             for scen in scens:
                 if state_daily is None:
                     logger.warning("Missing simulation data for key 'simulations/%s/%s'", scen, spc)
@@ -201,17 +206,21 @@ def _summarize(sim):
     return None
 
 
-def yearly_summary(daily):
+def yearly_summary(daily, draws_only=False):
     """Per (species, scenario): entrainment probability, yearly totals with 95 % percentiles over iterations, bootstrap
-    means and 1-in-10/100/1000-day quantiles of daily entrainment and mortality (stryke.py:3770-3862)."""
+    means and 1-in-10/100/1000-day quantiles of daily entrainment and mortality (stryke.py:3770-3862).
+    ``draws_only``: consume the random draws of one pass and return nothing (see summarize)."""
     cols = ["species", "scenario", "prob_entrainment", "mean_yearly_entrainment", "lcl_yearly_entrainment",
             "ucl_yearly_entrainment", "1_in_10_day_entrainment", "1_in_100_day_entrainment", "1_in_1000_day_entrainment",
             "mean_yearly_mortality", "lcl_yearly_mortality", "ucl_yearly_mortality", "1_in_10_day_mortality",
             "1_in_100_day_mortality", "1_in_1000_day_mortality"]
     out = {c: [] for c in cols}
+    sizes = daily.groupby(["species", "scenario"], sort=False).size() if draws_only else None
     groups = daily.groupby(["species", "scenario", "iteration"])[["pop_size", "num_survived", "num_entrained"]].sum().reset_index()
     for fishy in groups.species.unique():
         for scen in groups.scenario.unique():
+            if draws_only and _device_for(int(sizes.get((fishy, scen), 0)), 10000) is not None:
+                continue                      # large group on the device path: its discarded bootstraps draw nothing
             out["species"].append(fishy)
             out["scenario"].append(scen)
             day_dat = daily[(daily.species == fishy) & (daily.scenario == scen)]
@@ -221,6 +230,10 @@ def yearly_summary(daily):
                 continue
             df = day_dat[["day", "iteration", "num_entrained", "num_survived", "pop_size"]].copy()
             df["num_mortalities"] = df["num_entrained"] - df["num_survived"]
+            if draws_only:
+                bootstrap_mean_ci(df["num_entrained"], result_used=False)
+                bootstrap_mean_ci(df["num_mortalities"], result_used=False)
+                continue
             per_it = df.groupby("iteration")[["pop_size", "num_entrained"]].sum()
             probs = np.where(per_it["pop_size"] > 0, per_it["num_entrained"] / per_it["pop_size"].where(per_it["pop_size"] > 0, 1.0), 0.0)
             out["prob_entrainment"].append(float(np.mean(probs)) if len(probs) else 0.0)
@@ -236,7 +249,7 @@ def yearly_summary(daily):
                 out[f"ucl_yearly_{what}"].append(year.at["upper_95_CI", col])
                 for T, level in q.items():
                     out[f"1_in_{T}_day_{what}"].append(df[col].quantile(level))
-    return pd.DataFrame.from_dict(out, orient="columns")
+    return None if draws_only else pd.DataFrame.from_dict(out, orient="columns")
 
 
 def driver_diagnostics(unit_params, route_flows, unit_hours, beta_units):
