@@ -128,12 +128,13 @@ def _summarize(sim):
             state_daily["state"] = state_daily["state"].astype(str)
         moves = [int(m) for m in sim.moves]
         final_move = max(moves) if moves else 0
+        group_sizes = sim.daily_summary.groupby(["species", "scenario"], sort=False).size() if len(species) > 1 else None
         for si, spc in enumerate(species):
             if si > 0:
                 # the reference rebuilds the yearly summary inside its species loop (stryke.py:3770-3862 sit under
                 # `for i in species`): the table of the last pass is the one that is kept, but every pass draws its
                 # bootstraps from the global stream — replayed here so that a seeded run stays draw-for-draw identical
-                yearly_summary(sim.daily_summary, draws_only=True)
+                yearly_summary(sim.daily_summary, draws_only=True, sizes=group_sizes)
             for scen in scens:
                 if state_daily is None:
                     logger.warning("Missing simulation data for key 'simulations/%s/%s'", scen, spc)
@@ -206,7 +207,7 @@ def _summarize(sim):
     return None
 
 
-def yearly_summary(daily, draws_only=False):
+def yearly_summary(daily, draws_only=False, sizes=None):
     """Per (species, scenario): entrainment probability, yearly totals with 95 % percentiles over iterations, bootstrap
     means and 1-in-10/100/1000-day quantiles of daily entrainment and mortality (stryke.py:3770-3862).
     ``draws_only``: consume the random draws of one pass and return nothing (see summarize)."""
@@ -215,10 +216,16 @@ def yearly_summary(daily, draws_only=False):
             "mean_yearly_mortality", "lcl_yearly_mortality", "ucl_yearly_mortality", "1_in_10_day_mortality",
             "1_in_100_day_mortality", "1_in_1000_day_mortality"]
     out = {c: [] for c in cols}
-    sizes = daily.groupby(["species", "scenario"], sort=False).size() if draws_only else None
-    groups = daily.groupby(["species", "scenario", "iteration"])[["pop_size", "num_survived", "num_entrained"]].sum().reset_index()
-    for fishy in groups.species.unique():
-        for scen in groups.scenario.unique():
+    if draws_only and sizes is None:
+        sizes = daily.groupby(["species", "scenario"], sort=False).size()
+    if draws_only:      # same group order as below (groupby sorts its keys) without the sums
+        species_order = sorted({k[0] for k in sizes.index})
+        scenario_order = sorted({k[1] for k in sizes.index})
+    else:
+        groups = daily.groupby(["species", "scenario", "iteration"])[["pop_size", "num_survived", "num_entrained"]].sum().reset_index()
+        species_order, scenario_order = groups.species.unique(), groups.scenario.unique()
+    for fishy in species_order:
+        for scen in scenario_order:
             if draws_only and _device_for(int(sizes.get((fishy, scen), 0)), 10000) is not None:
                 continue                      # large group on the device path: its discarded bootstraps draw nothing
             out["species"].append(fishy)
