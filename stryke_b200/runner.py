@@ -24,6 +24,9 @@ CFS_TO_CMS = 0.02831683199881    # stryke.py:3253
 
 def _dist_rank_world():
     """(rank, world size) of an initialised torch.distributed job, else (0, 1)."""
+    import sys
+    if "torch" not in sys.modules:       # a job that initialised a process group has imported torch; do not pay for the
+        return 0, 1                      # import (seconds) in single-process runs
     try:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
