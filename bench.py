@@ -231,7 +231,7 @@ def main():
 
     for i in range(args.warmup):
         step(1000 + i)
-        flush_buf.fill_(i)
+        flush_buf.fill_(i & 0xff)
     torch.cuda.synchronize()
     fish_per_step = plan.status()
     if world > 1:
@@ -247,7 +247,7 @@ def main():
         step(2000 + i)
         e1.record(stream)
         evs.append((e0, e1))
-        flush_buf.fill_(i + 1)     # L2 flush between timed steps (256 MiB > 126 MB L2), outside the event pairs
+        flush_buf.fill_((i + 1) & 0xff)     # L2 flush between timed steps (256 MiB > 126 MB L2), outside the event pairs
     torch.cuda.synchronize()
     launches = engine.launch_count() - launches0
     if world > 1:
