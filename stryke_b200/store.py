@@ -143,3 +143,45 @@ def open_store(path, mode="a"):
             os.remove(path)
         return _HDF(path, mode)
     return FrameStore(path, mode)
+
+
+def export(path, target, fmt=None):
+    """Copy a fallback store (``<name>.h5.store/``) into a container other tools read: ``fmt='hdf'`` writes a real
+    ``pandas.HDFStore`` file with the reference's keys (needs PyTables — run it where the web app runs), ``'parquet'``
+    one ``.parquet`` per key (pyarrow), ``'csv'`` one ``.csv`` per key.  ``path`` is the ``.h5`` path the project used."""
+    fmt = fmt or ("hdf" if str(target).endswith((".h5", ".hdf", ".hdf5")) else "parquet")
+    src = FrameStore(path, mode="r")
+    keys = src.keys()
+    if fmt == "hdf":
+        if not pytables_available():
+            raise RuntimeError("writing HDF5 needs PyTables (pip install tables); use fmt='parquet' or 'csv' here")
+        with pd.HDFStore(target, mode="w") as out:
+            for k in keys:
+                df = src[k]
+                table = k.strip("/") in ("Daily", "State_Daily", "Route_Flows", "Unit_Hours", "Daily_Summary", "Beta_Distributions",
+                                         "Beta_Distributions_Units", "Yearly_Summary", "Driver_Diagnostics") or "simulations" in k
+                out.put(k, df, format="table" if table else "fixed", **({"data_columns": True} if table else {}))
+        return [target]
+    os.makedirs(target, exist_ok=True)
+    written = []
+    for k in keys:
+        name = k.strip("/").replace("/", "__").replace(" ", "_")
+        df = src[k]
+        if fmt == "parquet":
+            p = os.path.join(target, name + ".parquet")
+            df.to_parquet(p)
+        elif fmt == "csv":
+            p = os.path.join(target, name + ".csv")
+            df.to_csv(p)
+        else:
+            raise ValueError(f"unknown format {fmt!r}")
+        written.append(p)
+    return written
+
+
+if __name__ == "__main__":      # python -m stryke_b200.store <project>.h5 <target> [hdf|parquet|csv]
+    import sys
+    if len(sys.argv) < 3:
+        raise SystemExit("usage: python -m stryke_b200.store <project>.h5 <target.h5 | target_dir> [hdf|parquet|csv]")
+    for f in export(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None):
+        print(f)

@@ -266,3 +266,26 @@ def test_a_plain_c_program_links_against_the_boundary(tmp_path):
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     n_dev, rc, msg = r.stdout.strip().split(" ", 2)
     assert int(rc) < 0 and msg
+
+
+def test_fallback_store_exports_to_parquet_and_csv(tmp_path):
+    """The directory store that stands in for the .h5 where PyTables is missing can be handed on as parquet / csv
+    (and as a real HDF5 file where PyTables exists): same keys, same frames."""
+    import pandas as pd
+    from stryke_b200 import store
+    path = str(tmp_path / "proj.h5")
+    daily = pd.DataFrame({"species": ["a", "b"], "iteration": [0, 1], "day": pd.to_datetime(["2023-03-01", "2023-03-02"]),
+                          "pop_size": [3, 4]})
+    with store.FrameStore(path, mode="w") as st:
+        st["Population"] = pd.DataFrame({"Species": ["a"], "Fish": [3.0]})
+        st.append("Daily", daily)
+        st.append("simulations/Spring/a", daily)
+    out = store.export(path, str(tmp_path / "pq"), "parquet")
+    assert sorted(os.path.basename(f) for f in out) == ["Daily.parquet", "Population.parquet", "simulations__Spring__a.parquet"]
+    assert pd.read_parquet(os.path.join(str(tmp_path / "pq"), "Daily.parquet")).equals(daily)
+    out = store.export(path, str(tmp_path / "csv"), "csv")
+    assert len(out) == 3 and pd.read_csv(out[0]).shape[0] == 2
+    if not store.pytables_available():
+        import pytest
+        with pytest.raises(RuntimeError, match="PyTables"):
+            store.export(path, str(tmp_path / "x.h5"))
