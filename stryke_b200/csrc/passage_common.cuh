@@ -162,8 +162,10 @@ template <typename Real> __device__ __forceinline__ Real u_oc(uint32_t x);   // 
 __device__ __forceinline__ float mantissa_float(uint32_t x) { return __uint_as_float((x >> 9) | 0x3f800000u); }
 template <> __device__ __forceinline__ float u_co<float>(uint32_t x) { return mantissa_float(x) - 1.0f; }
 template <> __device__ __forceinline__ float u_oc<float>(uint32_t x) { return 2.0f - mantissa_float(x); }
-template <> __device__ __forceinline__ double u_co<double>(uint32_t x) { return (double)x * 2.3283064365386963e-10; }
-template <> __device__ __forceinline__ double u_oc<double>(uint32_t x) { return ((double)x + 1.0) * 2.3283064365386963e-10; }
+// fp64 kernels see the SAME uniforms as the fp32 ones (23 bits of the word): a native-RNG run then differs between the
+// precisions only where the arithmetic rounds across a threshold (tests compare the two fish population by population)
+template <> __device__ __forceinline__ double u_co<double>(uint32_t x) { return (double)(x >> 9) * 1.1920928955078125e-07; }
+template <> __device__ __forceinline__ double u_oc<double>(uint32_t x) { return 1.0 - (double)(x >> 9) * 1.1920928955078125e-07; }
 
 // 16-bit uniforms from the high / low half of a word (disjoint bits), multiples of 2^-16: exact in fp32 and fp64, so
 // every kernel sees the same value.  hi_co, lo_co in [0, 1): k / 65536;  hi_oc in (0, 1]: 1 - k / 65536.
