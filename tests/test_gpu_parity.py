@@ -205,3 +205,41 @@ def test_philox4x32_10_known_answers():
     got = engine.philox(ctr, key)
     for i in range(64):
         assert [int(x) for x in got[i]] == _philox_np(ctr[i], key[i])
+
+
+def _function_vectors():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "function_vectors.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("precision,tol", [(64, 1e-6), (32, 1e-4)])
+def test_strike_functions_against_240_reference_parameter_sets(precision, tol):
+    """tests/golden/function_vectors.json: the reference's Kaplan / Propeller / Francis / Pump called on 60 random
+    parameter sets each (oracle/make_function_goldens.py).  Tolerances of BASELINE.json on the survival probability and
+    on its complement (the strike probability), wherever the latter is not clipped."""
+    from stryke_b200 import engine
+    kinds = {"Kaplan": 1, "Propeller": 2, "Francis": 3, "Pump": 4}
+    worst = 0.0
+    for case in _function_vectors()["strike"]:
+        want = np.array(case["survival"])
+        got = engine.strike_survival(kinds[case["kind"]], np.array(case["params"]), np.array(case["length"]),
+                                     np.array(case["rR"]), precision=precision)
+        ok = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got), ok)
+        p_want, p_got = 1.0 - want[ok], 1.0 - got[ok]
+        scale = np.maximum(np.abs(p_want), 1e-3)          # strike probability; survival may be far below 0 (reference does not clip)
+        err = np.abs(p_got - p_want) / scale
+        worst = max(worst, float(err.max()) if err.size else 0.0)
+    assert worst <= tol, worst
+
+
+@pytest.mark.parametrize("precision,tol", [(64, 1e-6), (32, 1e-4)])
+def test_barotrauma_response_against_200_reference_cases(precision, tol):
+    from stryke_b200 import engine
+    worst = 0.0
+    for c in _function_vectors()["baro"]:
+        got = engine.baro_survival([c["depth_ft"]], c["tail_ft"], c["beta_0"], c["beta_1"], precision=precision)[0]
+        worst = max(worst, abs((1.0 - got) - c["injury"]) / max(c["injury"], 1e-3))
+    assert worst <= tol, worst
