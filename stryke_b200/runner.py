@@ -337,7 +337,15 @@ def run_simulation(sim, injected=None, trace=None):
                 elif key in ("Route_Flows", "Unit_Hours"):
                     kw = dict(min_itemsize={"scenario": 128, "route": 256})
                 hdf.append(key, df, **kw)
+    all_iters = _flag("STRYKE_DAY_PROGRESS_ALL_ITERS", "1")
     for g in plan.groups:
+        # the day/iteration progress lines the web UI parses for its progress bar (stryke.py:2922-2923): every
+        # max(1, days // 10)-th day, all iterations unless STRYKE_DAY_PROGRESS_ALL_ITERS=0 (then the first three)
+        step = max(1, int(g.n_days / 10))
+        days = [d for d in range(1, g.n_days + 1) if d % step == 0]
+        its = range(1, g.iterations + 1) if all_iters else range(1, min(g.iterations, 3) + 1)
+        if days:
+            print("\n".join(f"[INFO] Day {d} of {g.n_days} (Iteration {i})" for i in its for d in days), flush=True)
         print(f"[INFO] ✅ Completed scenario '{g.scenario}' for species {g.species}", flush=True)
     print("[INFO] ✅ All scenarios complete! Finalizing results...", flush=True)
     print("[INFO] 💾 Simulation data saved successfully", flush=True)

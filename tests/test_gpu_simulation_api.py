@@ -52,6 +52,8 @@ def test_run_with_injected_uniforms_writes_the_reference_frames(case, tmp_path):
     with contextlib.redirect_stdout(out):
         runner.run_simulation(sim, injected=inj)
     assert "will simulate" in out.getvalue()
+    import re
+    assert re.search(r"\[INFO\] Day \d+ of \d+ \(Iteration \d+\)", out.getvalue())      # the web UI's progress regex
     with open_store(sim.hdf_path, mode="r") as st:
         daily, sd = st["Daily"], st["State_Daily"] if "State_Daily" in st else None
         rf = st["Route_Flows"] if "Route_Flows" in st else None
