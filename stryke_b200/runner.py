@@ -310,6 +310,11 @@ def run_simulation(sim, injected=None, trace=None):
                              "STRYKE_MAX_DAILY_STATE_ROWS deliberately.") from exc
         raise
     sim._last_plan, sim._last_result = plan, res
+    warn = int(os.environ.get("STRYKE_WARN_DAILY_FISH", "50000"))        # stryke.py:3041-3051 warns cell by cell
+    n_big = int((res.cell_n >= warn).sum())
+    if n_big:
+        logger.warning("Large daily fish population: %d cell(s) with n >= %d (largest n=%d; STRYKE_WARN_DAILY_FISH)",
+                       n_big, warn, int(res.cell_n.max()))
     if rank != 0:          # the frames are written once
         return None
     frames = assemble_frames(sim, plan, res)
