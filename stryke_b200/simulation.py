@@ -159,8 +159,20 @@ class simulation:
             hdf["Unit_Parameters"] = self.unit_params
 
     def existing_import(self, proj_dir, wks, output_name):
-        """Re-open a project (stryke.py:304-346); the reference's version is broken at HEAD (Appendix §5)."""
-        self.worksheet_import(proj_dir, wks, output_name)
+        """Re-open a project whose results already exist, e.g. to call summary() again (stryke.py:304-346): reads the
+        network sheets only and leaves the result store untouched.  (The reference's version stops at
+        ``create_route(self.wks_dir)`` — a one-argument call of a zero-argument method; the intent is kept.)"""
+        from . import xlsx
+        self.wks_dir = os.path.join(proj_dir, wks)
+        self.proj_dir, self.output_name = proj_dir, output_name
+        self.hdf_path = os.path.join(self.proj_dir, "%s.h5" % self.output_name)
+        book = xlsx.Workbook(self.wks_dir)
+        self.nodes = book.frame("Nodes", "B:D", skiprows=9, expect=("Location", "Surv_Fun"))
+        self.edges = book.frame("Edges", "B:D", skiprows=9, expect=("_from", "_to"))
+        self.surv_fun_df = self.nodes[["Location", "Surv_Fun"]].set_index("Location")
+        self.surv_fun_dict = self.surv_fun_df.to_dict("index")
+        if len(self.nodes) > 1:
+            self.max_river_node = self._max_river_node(self.nodes.Location.values)
         self.create_route()
 
     @staticmethod

@@ -148,3 +148,23 @@ def test_webapp_project_runs_like_the_attribute_built_project(tmp_path):
     assert sd[["move", "state", "successes", "count"]].reset_index(drop=True).equals(
         want_sd[["move", "state", "successes", "count"]].reset_index(drop=True))
     assert set(sim.driver_diagnostics["route"]) == {"FacA - Unit 1", "FacA - Unit 2", "FacA - Unit 3"}
+
+
+def test_reopening_an_existing_project_keeps_its_results(tmp_path):
+    """simulation(proj_dir, name, wks=..., existing=True) (stryke.py:298-346): network sheets only, results untouched,
+    summary() runs on what the earlier run wrote."""
+    prj = fixtures.c2_facility(n_fish=2000, iterations=3, days=4)
+    write_workbook(prj, str(tmp_path / "project.xlsx"))
+    with quiet():
+        sim = simulation(str(tmp_path), "again", wks="project.xlsx")
+        sim.run()
+    with open_store(sim.hdf_path, "r") as st:
+        daily = st["Daily"]
+    with quiet():
+        re = simulation(str(tmp_path), "again", wks="project.xlsx", existing=True)
+        assert list(re.moves) == list(sim.moves) and sorted(re.graph.edges) == sorted(sim.graph.edges)
+        np.random.seed(1)
+        re.summary()
+    with open_store(re.hdf_path, "r") as st:
+        assert st["Daily"].equals(daily)
+        assert "/Beta_Distributions" in st.keys() and len(st["Yearly_Summary"]) == 1
