@@ -616,6 +616,35 @@ class simulation:
     # ----------------------------------------------------------------------------------------------------------
     # hydrograph (stryke.py:2154-2307; USGS download is out of scope — no network)
     # ----------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def speed(L, A, M):
+        """Swimming speed after Sambilay 1990 (stryke.py:2067-2092): L fish length (ft), A caudal fin aspect ratio,
+        M swimming mode (0 sustained, 1 burst); result in ft/s."""
+        sa = 10 ** (-0.828 + 0.6196 * np.log10(np.asarray(L, dtype=float) * 30.48) + 0.3478 * np.log10(A) + 0.7621 * np.asarray(M))
+        return sa * 0.911344
+
+    def create_graph_from_app(self, model_setup, session):
+        """Graph of a web-app project (stryke.py:798-843): one unit node for the single-unit setups, otherwise the
+        node-link graph the editor stored under ``graph_data``."""
+        import networkx as nx
+        if model_setup in ("single_unit_survival_only", "single_unit_simulated_entrainment"):
+            G = nx.DiGraph()
+            up = getattr(self, "unit_params", None)
+            if up is not None and not up.empty:
+                row = up.iloc[0]
+                number = row["Unit"] if "Unit" in row else row.name
+                G.add_node(f"unit_{number}", label=str(number), type="unit", **row.to_dict())
+            else:
+                print("Warning: No unit parameters available for single unit model.")
+            return G
+        graph_json = session.get("graph_data")
+        if graph_json:
+            from networkx.readwrite import json_graph
+            edges_key = "links" if "links" in graph_json else "edges"
+            return json_graph.node_link_graph(graph_json, edges=edges_key)
+        print("No graph data found in session; returning an empty graph.")
+        return nx.DiGraph()
+
     def get_USGS_hydrograph(self, gage, prorate, flow_year):
         """Daily mean flow of a USGS gage for one year (stryke.py:2094-2152): columns datetimeUTC, DAvgFlow,
         DAvgFlow_prorate, year, month.  The reference downloads it (hydrofunctions NWIS 'dv' service); this build has no

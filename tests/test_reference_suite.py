@@ -174,3 +174,23 @@ def test_first_non_river_state_is_the_passage_route():
     states = [c for c in df.columns if c.startswith("state_")]
     first = df[states].apply(lambda r: next(s for s in r if "river_node" not in s.lower()), axis=1)
     assert first.value_counts().to_dict() == {"Unit A": 2, "Unit B": 1}
+
+
+# ---- remaining public helpers of the class (stryke.py:798-843, :2067-2092) ---------------------------------------------
+def test_swimming_speed_formula():
+    # Sambilay 1990 as the reference writes it: 10^(-0.828 + 0.6196 log10(L*30.48) + 0.3478 log10(A) + 0.7621 M) * 0.911344
+    want = 10 ** (-0.828 + 0.6196 * np.log10(1.5 * 30.48) + 0.3478 * np.log10(2.2) + 0.7621 * 1) * 0.911344
+    assert simulation.speed(1.5, 2.2, 1) == pytest.approx(want, rel=1e-15)
+    assert simulation.speed(np.array([1.5, 1.5]), 2.2, np.array([0, 1]))[1] == pytest.approx(want, rel=1e-15)
+
+
+def test_graph_from_the_web_app_session():
+    sim = bare_sim(pd.DataFrame([{"Facility": "F", "Unit": 3, "Qcap": 10.0}], index=pd.Index(["F - Unit 3"], name="Unit_Name")))
+    G = sim.create_graph_from_app("single_unit_survival_only", {})
+    assert list(G.nodes) == ["unit_3"] and G.nodes["unit_3"]["type"] == "unit" and G.nodes["unit_3"]["Qcap"] == 10.0
+    from networkx.readwrite import json_graph
+    H = nx.DiGraph()
+    H.add_edge("river_node_0", "spill", weight=1.0)
+    G2 = sim.create_graph_from_app("multiple_powerhouses_simulated_entrainment_routing", {"graph_data": json_graph.node_link_data(H)})
+    assert list(G2.edges(data="weight")) == [("river_node_0", "spill", 1.0)]
+    assert len(sim.create_graph_from_app("multiple_powerhouses_simulated_entrainment_routing", {})) == 0
