@@ -8,7 +8,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "passage.cu")
 DEPS = [SRC, os.path.join(HERE, "csrc", "passage_common.cuh"), os.path.join(HERE, "csrc", "passage_fast.cuh"),
-        os.path.join(HERE, "csrc", "bootstrap.cuh"),
+        os.path.join(HERE, "csrc", "bootstrap.cuh"), os.path.join(HERE, "csrc", "specialise.inl"),
+        os.path.join(HERE, "csrc", "passage_kernels.cuh"),
         os.path.join(os.path.dirname(HERE), "include", "stryke_b200.h")]
 OUT = os.path.join(HERE, "libstryke_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",

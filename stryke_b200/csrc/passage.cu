@@ -44,627 +44,7 @@
 
 namespace stryke {
 
-// fp64: the reference's operation order with every rounding kept (no FMA contraction)
-__device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ double sub_(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double div_(double a, double b) { return __ddiv_rn(a, b); }
-
-template <typename Real> struct UCW;
-template <> struct UCW<float> { static constexpr int W = 4; };    // folded: fa, fb, fc|fl, has_flow
-template <> struct UCW<double> { static constexpr int W = 8; };   // raw unit_coef row
-
-// ---- blade strike + barotrauma, fp64 validation flavour (operation order of stryke.py:907-922, :1492-1510) --------
-__device__ __forceinline__ double strike_surv64(int kind, const double* uc, double L, double rR) {
-  const double lam = uc[0], N = uc[1], D = uc[2];
-  double x;
-  if (kind == STRYKE_KIND_KAPLAN) {
-    const double a = atan(div_(uc[3], mul_(uc[4], rR)));
-    x = add_(div_(cos(a), uc[5]), div_(sin(a), mul_(M_PI, rR)));
-  } else {
-    x = uc[3];
-  }
-  const double p = mul_(mul_(lam, div_(mul_(N, L), D)), x);
-  return fmin(fmax(sub_(1.0, p), 0.0), 1.0);
-}
-__device__ __forceinline__ double baro_surv64(double depth_ft, double tail_ft, double b0, double b1) {
-  const double p1 = add_(P_ATM, mul_(mul_(RHO, G_SI), mul_(depth_ft, FT2M)));
-  const double p2 = add_(P_ATM, mul_(mul_(RHO, G_SI), mul_(tail_ft, FT2M)));
-  const double e = exp(add_(b0, mul_(b1, log(div_(p1, p2)))));
-  return sub_(1.0, div_(e, add_(1.0, e)));
-}
-// ---- fp32 throughput flavour: folded per-(day, unit) coefficients, MUFU intrinsics ---------------------------------
-//   Kaplan: tan a = fa / rR  =>  cos a = rR * rsqrt(rR^2 + fa^2), sin a = fa * rsqrt(rR^2 + fa^2)
-//           p = fc * L * rsqrt(rR^2 + fa^2) * (rR * fb + fa / (pi rR))
-__device__ __forceinline__ float strike_surv32(int kind, const float* uc, float L, float rR) {
-  float p;
-  if (kind == STRYKE_KIND_KAPLAN) {
-    const float fa = uc[0], fb = uc[1];
-    const float inv = rsqrt_approx(fmaf(rR, rR, fa * fa));
-    p = uc[2] * L * inv * fmaf(rR, fb, fa * 0.318309886f * rcp_approx(rR));
-  } else {
-    p = uc[2] * L;
-  }
-  p = uc[3] > 0.f ? p : INFINITY;   // no flow through the unit: p_strike = inf in the reference (Appendix E10)
-  return __saturatef(1.f - p);
-}
-__device__ __forceinline__ float baro_surv32(float depth_ft, float c0, float c1, float b0l2e, float b1) {
-  const float ratio = fmaf(c1, depth_ft, c0);                 // P1/P2
-  const float e = ex2_approx(fmaf(b1, lg2_approx(ratio), b0l2e));   // exp(b0 + b1 ln ratio)
-  return rcp_approx(1.f + e);                                       // 1 - e/(1+e)
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// native RNG: word slot -> Philox block, warp-uniform refill points
-// ------------------------------------------------------------------------------------------------------------------
-struct FishRng {
-  uint32_t c0, c1, c2, k0, k1;
-  uint32_t w[4];
-  int cur;
-  __device__ __forceinline__ void init(uint32_t fish, uint64_t cell_id, uint32_t seed_lo, uint32_t seed_hi) {
-    c0 = fish; c1 = (uint32_t)cell_id; c2 = (uint32_t)(cell_id >> 32); k0 = seed_lo; k1 = seed_hi; cur = -1;
-  }
-  __device__ __forceinline__ uint32_t word(int slot) {   // slot is warp-uniform
-    const int b = slot >> 2;
-    if (b != cur) { Philox::block(c0, c1, c2, (uint32_t)b, k0, k1, w); cur = b; }
-    const int s = slot & 3;
-    return (s & 2) ? ((s & 1) ? w[3] : w[2]) : ((s & 1) ? w[1] : w[0]);
-  }
-};
-__device__ __forceinline__ double std_normal(double u1_oc, double u2_co) {
-  return sqrt(-2.0 * log(u1_oc)) * cospi(2.0 * u2_co);
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// (1) presence roll + daily entrainment count, one thread per cell
-// ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {   // numpy-style 53-bit double in [0,1)
-  return (double)((((uint64_t)hi >> 5) << 26) | ((uint64_t)lo >> 6)) * (1.0 / 9007199254740992.0);
-}
-
-template <bool INJECT>
-__global__ void count_kernel(KParams P, const double* __restrict__ day_Q, int32_t* __restrict__ cell_n,
-                             int max_daily_fish, unsigned long long* __restrict__ err) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= P.n_cells) return;
-  const double* sp = P.species + (int64_t)P.cell_species[c] * STRYKE_SPECIES_W;
-  const int kind = (int)sp[12];
-  const double shape = sp[13], loc = sp[14], scale = sp[15], max_rate = sp[16], occur = sp[17];
-  uint32_t w[4], v[4];
-  double presence;
-  if (INJECT) {
-    presence = P.inj.presence[c];
-  } else {
-    const uint64_t id = P.cell_id[c];
-    Philox::block(0xFFFFFFFFu, (uint32_t)id, (uint32_t)(id >> 32), 0u, P.seed_lo, P.seed_hi, w);
-    Philox::block(0xFFFFFFFFu, (uint32_t)id, (uint32_t)(id >> 32), 1u, P.seed_lo, P.seed_hi, v);
-    presence = u53(w[0], w[1]);
-  }
-  int64_t n = 0;
-  if (occur >= presence) {                                       // stryke.py:3027
-    if (kind == STRYKE_ENT_FIXED) {
-      n = (int64_t)sp[18];                                       // stryke.py:3029
-    } else {
-      const bool capped = isfinite(max_rate) && max_rate > 0.0;
-      double rate;
-      if (kind == STRYKE_ENT_PARETO) {                           // truncated_rvs, stryke.py:75-106, :2550-2559
-        const double upper = capped ? max_rate * 10.0 : loc + fmax(1.0, scale * 1000.0);
-        const double yu = (upper - loc) / scale;
-        const double f_low = 0.0, f_high = yu >= 1.0 ? 1.0 - pow(yu, -shape) : 0.0;
-        if (!isfinite(f_high) || f_high - f_low < 1e-12) {
-          rate = upper;
-        } else {
-          const double q = INJECT ? P.inj.count_draw[c] : f_low + (f_high - f_low) * u53(w[2], w[3]);
-          rate = loc + scale * pow(1.0 - q, -1.0 / shape);       // scipy pareto._ppf
-        }
-      } else if (kind == STRYKE_ENT_LOGNORMAL) {                 // scipy lognorm._rvs = exp(s*Z), stryke.py:2563
-        double z;
-        if (INJECT) z = P.inj.count_draw[c];
-        else z = sqrt(-2.0 * log(1.0 - u53(w[2], w[3]))) * cospi(2.0 * u53(v[0], v[1]));
-        rate = exp(shape * z) * scale + loc;
-      } else {
-        const double q = INJECT ? P.inj.count_draw[c] : u53(w[2], w[3]);
-        if (kind == STRYKE_ENT_WEIBULL) {                        // weibull_min._ppf, stryke.py:2565
-          rate = pow(-log1p(-q), 1.0 / shape) * scale + loc;
-        } else {                                                 // genextreme._ppf, stryke.py:2561
-          const double x = -log(-log(q));
-          rate = (shape == 0.0 ? x : -expm1(-shape * x) / shape) * scale + loc;
-        }
-      }
-      rate = fabs(rate);                                         // stryke.py:2567
-      if (capped && rate > max_rate * 10.0) rate = max_rate * 10.0;   // stryke.py:2578-2582
-      const double Mft3 = (60.0 * 60.0 * 24.0 * day_Q[P.cell_day[c]]) / 1000000.0;   // stryke.py:2585
-      const double nf = rint(Mft3 * rate);                       // np.round: half to even
-      if (!isfinite(nf) || nf < 0.0) { atomicMax(err, 0x8000000000000000ull | (unsigned long long)c); n = 0; }
-      else n = (int64_t)nf;
-    }
-    if (n == 0) n = 1;                                           // stryke.py:3032-3033
-    if (max_daily_fish > 0 && kind != STRYKE_ENT_FIXED && n > max_daily_fish) {    // stryke.py:2610-2616
-      atomicMax(err, ((unsigned long long)n << 32) | (unsigned long long)(c & 0xFFFFFFFFll));
-      n = 0;
-    }
-    if (n > 0x7FFFFFFFll) { atomicMax(err, 0x8000000000000000ull | (unsigned long long)c); n = 0; }
-  }
-  cell_n[c] = (int32_t)n;
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// exclusive scans of tiles-per-cell and fish-per-cell (three small kernels; int64 offsets)
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int SCAN_T = 1024, SCAN_PER = 4, SCAN_CH = SCAN_T * SCAN_PER;
-
-__device__ __forceinline__ void block_scan2(int64_t& a, int64_t& b, int64_t* sh) {   // inclusive, 1024 threads
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int64_t ta = __shfl_up_sync(0xffffffffu, a, o), tb = __shfl_up_sync(0xffffffffu, b, o);
-    if (lane >= o) { a += ta; b += tb; }
-  }
-  if (lane == 31) { sh[wid] = a; sh[32 + wid] = b; }
-  __syncthreads();
-  if (wid == 0) {
-    int64_t sa = sh[lane], sb = sh[32 + lane];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int64_t ta = __shfl_up_sync(0xffffffffu, sa, o), tb = __shfl_up_sync(0xffffffffu, sb, o);
-      if (lane >= o) { sa += ta; sb += tb; }
-    }
-    sh[lane] = sa; sh[32 + lane] = sb;
-  }
-  __syncthreads();
-  if (wid > 0) { a += sh[wid - 1]; b += sh[32 + wid - 1]; }
-  __syncthreads();
-}
-
-__global__ void __launch_bounds__(SCAN_T) scan_partial(const int32_t* __restrict__ cell_n, int64_t n_cells,
-                                                       int64_t* __restrict__ part) {
-  __shared__ int64_t sh[64];
-  const int64_t base = (int64_t)blockIdx.x * SCAN_CH + threadIdx.x * SCAN_PER;
-  int64_t t = 0, f = 0;
-#pragma unroll
-  for (int i = 0; i < SCAN_PER; ++i)
-    if (base + i < n_cells) { const int32_t n = cell_n[base + i]; f += n; t += (n + 31) >> 5; }
-  block_scan2(t, f, sh);
-  if (threadIdx.x == SCAN_T - 1) { part[2 * blockIdx.x] = t; part[2 * blockIdx.x + 1] = f; }
-}
-__global__ void __launch_bounds__(SCAN_T) scan_blocks(int64_t* __restrict__ part, int nb) {   // exclusive, in place
-  __shared__ int64_t sh[64];
-  const int per = (nb + SCAN_T - 1) / SCAN_T;
-  const int lo = threadIdx.x * per, hi = min(nb, lo + per);
-  int64_t t = 0, f = 0;
-  for (int i = lo; i < hi; ++i) { t += part[2 * i]; f += part[2 * i + 1]; }
-  int64_t it = t, jf = f;
-  block_scan2(it, jf, sh);
-  int64_t et = it - t, ef = jf - f;
-  for (int i = lo; i < hi; ++i) {
-    const int64_t a = part[2 * i], b = part[2 * i + 1];
-    part[2 * i] = et; part[2 * i + 1] = ef; et += a; ef += b;
-  }
-}
-__global__ void __launch_bounds__(SCAN_T) scan_final(const int32_t* __restrict__ cell_n, int64_t n_cells,
-                                                     const int64_t* __restrict__ part, int64_t* __restrict__ tile_off,
-                                                     int64_t* __restrict__ fish_off) {
-  __shared__ int64_t sh[64];
-  const int64_t base = (int64_t)blockIdx.x * SCAN_CH + threadIdx.x * SCAN_PER;
-  int32_t nn[SCAN_PER];
-  int64_t t = 0, f = 0;
-#pragma unroll
-  for (int i = 0; i < SCAN_PER; ++i) {
-    nn[i] = base + i < n_cells ? cell_n[base + i] : 0;
-    f += nn[i]; t += (nn[i] + 31) >> 5;
-  }
-  int64_t it = t, jf = f;
-  block_scan2(it, jf, sh);
-  int64_t et = it - t + part[2 * blockIdx.x], ef = jf - f + part[2 * blockIdx.x + 1];
-#pragma unroll
-  for (int i = 0; i < SCAN_PER; ++i) {
-    if (base + i < n_cells) { tile_off[base + i] = et; fish_off[base + i] = ef; }
-    et += (nn[i] + 31) >> 5; ef += nn[i];
-    if (base + i == n_cells - 1) { tile_off[n_cells] = et; fish_off[n_cells] = ef; }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// (2)-(6) the passage kernel
-// ------------------------------------------------------------------------------------------------------------------
-
-struct SmemLayout {   // byte offsets into dynamic shared memory (all 16-byte aligned)
-  int nodes, edge_dst, moves, pair_node, ustatic, species, warp0, warp_stride, cdf, stay, ucoef, total;
-};
-
-template <typename Real>
-__host__ __device__ inline SmemLayout smem_layout(int n_nodes, int n_units, int n_moves, int n_edges, int n_pairs,
-                                                  int n_species_staged) {
-  auto al = [](int x) { return (x + 15) & ~15; };
-  SmemLayout L;
-  int o = 0;
-  L.nodes = o; o = al(o + n_nodes * (int)sizeof(NodeRec));
-  L.edge_dst = o; o = al(o + n_edges);
-  L.moves = o; o = al(o + n_moves * (int)sizeof(MoveRec));
-  L.pair_node = o; o = al(o + n_pairs);
-  L.ustatic = o; o = al(o + n_units * USW * (int)sizeof(Real));
-  L.species = o; o = al(o + n_species_staged * SPW * (int)sizeof(Real));
-  L.warp0 = o;
-  int w = 0;
-  L.cdf = w; w = al(w + n_edges * (int)sizeof(Real));
-  L.ucoef = w; w = al(w + n_units * UCW<Real>::W * (int)sizeof(Real));
-  L.stay = w; w = al(w + n_nodes);
-  L.warp_stride = w;
-  L.total = o + w * WARPS;
-  return L;
-}
-
-template <typename Real, bool INJECT, int PR>
-__global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const int n_species_staged) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const SmemLayout SL = smem_layout<Real>(P.n_nodes, P.n_units, P.n_moves, P.n_edges, P.n_pairs, n_species_staged);
-  NodeRec* s_nodes = reinterpret_cast<NodeRec*>(smem + SL.nodes);
-  uint8_t* s_edge_dst = smem + SL.edge_dst;
-  MoveRec* s_moves = reinterpret_cast<MoveRec*>(smem + SL.moves);
-  uint8_t* s_pair = smem + SL.pair_node;
-  Real* s_ustatic = reinterpret_cast<Real*>(smem + SL.ustatic);
-  Real* s_species = reinterpret_cast<Real*>(smem + SL.species);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  unsigned char* wbase = smem + SL.warp0 + wid * SL.warp_stride;
-  Real* s_cdf = reinterpret_cast<Real*>(wbase + SL.cdf);
-  Real* s_ucoef = reinterpret_cast<Real*>(wbase + SL.ucoef);
-  uint8_t* s_stay = wbase + SL.stay;
-
-  // ---- block-level staging of the static facility tables ---------------------------------------------------------
-  for (int i = threadIdx.x; i < P.n_nodes; i += BLOCK) s_nodes[i] = P.nodes[i];
-  for (int i = threadIdx.x; i < P.n_edges; i += BLOCK) s_edge_dst[i] = P.edge_dst[i];
-  for (int i = threadIdx.x; i < P.n_moves; i += BLOCK) s_moves[i] = P.moves[i];
-  for (int i = threadIdx.x; i < P.n_pairs; i += BLOCK) s_pair[i] = P.pair_node[i];
-  for (int u = threadIdx.x; u < P.n_units; u += BLOCK) {
-    const double* us = P.unit_static + u * STRYKE_UNIT_STATIC_W;
-    const double p2 = P_ATM + RHO * G_SI * (us[3] * FT2M);
-    s_ustatic[u * USW + 0] = (Real)us[0]; s_ustatic[u * USW + 1] = (Real)us[1];
-    s_ustatic[u * USW + 2] = (Real)us[2]; s_ustatic[u * USW + 3] = (Real)us[3];
-    s_ustatic[u * USW + 4] = (Real)(P_ATM / p2); s_ustatic[u * USW + 5] = (Real)(RHO * G_SI * FT2M / p2);
-  }
-  for (int i = threadIdx.x; i < n_species_staged * SPW; i += BLOCK)
-    s_species[i] = (Real)P.species[(i / SPW) * STRYKE_SPECIES_W + (i % SPW)];
-  __syncthreads();
-
-  // ---- this warp's contiguous tile range -------------------------------------------------------------------------
-  const int64_t T = P.tile_off[P.n_cells];
-  const int64_t G = (int64_t)gridDim.x * WARPS, gw = (int64_t)blockIdx.x * WARPS + wid;
-  const int64_t t0 = (T / G) * gw + min(gw, T % G), t1 = t0 + T / G + (gw < T % G ? 1 : 0);
-  if (t0 >= t1) return;
-  int64_t c;
-  {  // last cell with tile_off[c] <= t0
-    int64_t lo = 0, hi = P.n_cells;
-    while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (P.tile_off[mid] <= t0) lo = mid; else hi = mid; }
-    c = lo;
-  }
-  int64_t c_end = P.tile_off[c + 1], c_begin = P.tile_off[c];
-  int cur_day = -1;
-  int64_t cur_cell = -1;
-
-  // per-cell registers
-  Real sp_ls = 0, sp_ll = 0, sp_lsc = 0, sp_lm = 0, sp_lsd = 0, sp_wr = 0, sp_uc = 0, sp_d1 = 0, sp_d2 = 0, sp_b0 = 0, sp_b1 = 0;
-  int sp_mode = 0, n_c = 0;
-  uint64_t cid = 0;
-  int64_t fo = 0;
-  uint32_t acc_suc[PR], acc_cnt[PR], acc_daily = 0;
-#pragma unroll
-  for (int r = 0; r < PR; ++r) { acc_suc[r] = 0; acc_cnt[r] = 0; }
-
-  auto flush = [&](int64_t cell) {
-#pragma unroll
-    for (int r = 0; r < PR; ++r) {
-      const int p = r * 32 + lane;
-      if (p < P.n_pairs && acc_cnt[r]) {
-        uint32_t* dst = P.state_daily + ((size_t)cell * P.n_pairs + p) * 2;
-        if (acc_suc[r]) atomicAdd(dst, acc_suc[r]);
-        atomicAdd(dst + 1, acc_cnt[r]);
-      }
-      acc_suc[r] = 0; acc_cnt[r] = 0;
-    }
-    if (lane < STRYKE_DAILY_W && acc_daily) atomicAdd(P.daily + (size_t)cell * STRYKE_DAILY_W + lane, acc_daily);
-    acc_daily = 0;
-  };
-
-  for (int64_t t = t0; t < t1; ++t) {
-    while (t >= c_end) { ++c; c_begin = c_end; c_end = P.tile_off[c + 1]; }
-    if (c != cur_cell) {
-      if (cur_cell >= 0) flush(cur_cell);
-      cur_cell = c;
-      n_c = P.cell_n[c];
-      cid = P.cell_id[c];
-      if (INJECT || P.trace.state || P.trace.length_ft64) fo = P.fish_off[c];
-      const int s = P.cell_species[c];
-      if (s < n_species_staged) {
-        const Real* q = s_species + s * SPW;
-        sp_ls = q[0]; sp_ll = q[1]; sp_lsc = q[2]; sp_lm = q[3]; sp_lsd = q[4]; sp_mode = (int)q[5];
-        sp_wr = q[6]; sp_uc = q[7]; sp_d1 = q[8]; sp_d2 = q[9]; sp_b0 = q[10]; sp_b1 = q[11];
-      } else {
-        const double* q = P.species + (int64_t)s * STRYKE_SPECIES_W;
-        sp_ls = (Real)q[0]; sp_ll = (Real)q[1]; sp_lsc = (Real)q[2]; sp_lm = (Real)q[3]; sp_lsd = (Real)q[4];
-        sp_mode = (int)q[5]; sp_wr = (Real)q[6]; sp_uc = (Real)q[7]; sp_d1 = (Real)q[8]; sp_d2 = (Real)q[9];
-        sp_b0 = (Real)q[10]; sp_b1 = (Real)q[11];
-      }
-      const int d = P.cell_day[c];
-      if (d != cur_day) {   // stage the day's routing CDF, stay flags and unit coefficients in this warp's slot
-        cur_day = d;
-        __syncwarp();
-        const double* cdf = P.edge_cdf + (size_t)d * P.n_edges;
-        for (int i = lane; i < P.n_edges; i += 32) s_cdf[i] = (Real)cdf[i];
-        const uint8_t* st = P.node_stay + (size_t)d * P.n_nodes;
-        for (int i = lane; i < P.n_nodes; i += 32) s_stay[i] = st[i];
-        const double* uc = P.unit_coef + (size_t)d * P.n_units * STRYKE_UNIT_COEF_W;
-        if (sizeof(Real) == 8) {
-          for (int i = lane; i < P.n_units * STRYKE_UNIT_COEF_W; i += 32) s_ucoef[i] = (Real)uc[i];
-        } else {
-          for (int u = lane; u < P.n_units; u += 32) {
-            const double* r = uc + u * STRYKE_UNIT_COEF_W;
-            const double lnd = r[0] * r[1] / r[2];
-            // a Kaplan row keeps pi*ada*Ewd, 2*Qwd, 8*Qwd; other runners keep X in slot 3 (slot 4 is 0)
-            const bool kap = r[4] != 0.0 || r[5] != 0.0;
-            s_ucoef[u * 4 + 0] = kap ? (Real)(r[3] / r[4]) : (Real)0;
-            s_ucoef[u * 4 + 1] = kap ? (Real)(1.0 / r[5]) : (Real)0;
-            s_ucoef[u * 4 + 2] = kap ? (Real)lnd : (Real)(lnd * r[3]);
-            s_ucoef[u * 4 + 3] = (Real)r[6];
-          }
-        }
-        __syncwarp();
-      }
-    }
-    const int64_t tile_in_cell = t - c_begin;
-    const int fish = (int)(tile_in_cell * 32 + lane);
-    const bool active = fish < n_c;
-    const int64_t gi = fo + fish;                 // global fish index (injected / trace arrays)
-    const int64_t NF = P.n_fish_total;
-
-    FishRng rng;
-    if (!INJECT) rng.init((uint32_t)fish, cid, P.seed_lo, P.seed_hi);
-
-    // ---- (2) length draw ---------------------------------------------------------------------------------------
-    Real z;
-    if (INJECT) z = active ? (Real)P.inj.length_z[gi] : (Real)0;
-    else { const uint32_t a = rng.word(0); z = std_normal(u16hi_oc<Real>(a), u16lo_co<Real>(a)); }
-    Real L;
-    if (sizeof(Real) == 8) {
-      if (sp_mode == 0) {   // |Z-lognormal| cm, cap 150, -> ft  (scipy: exp(s*Z)*scale + loc; stryke.py:3070-3077)
-        double v = fabs(add_(mul_(exp(mul_((double)sp_ls, (double)z)), (double)sp_lsc), (double)sp_ll));
-        v = v > 150.0 ? 150.0 : v;
-        L = (Real)mul_(v, CM2FT);
-      } else {              // |N(mean, sd)| inches -> ft  (stryke.py:3090)
-        L = (Real)div_(fabs(add_((double)sp_lm, mul_((double)sp_lsd, (double)z))), 12.0);
-      }
-    } else {
-      if (sp_mode == 0) L = (Real)(fminf(fabsf(fmaf(exp_approx((float)sp_ls * (float)z), (float)sp_lsc, (float)sp_ll)), 150.f) * 0.0328084f);
-      else L = (Real)(fabsf(fmaf((float)sp_lsd, (float)z, (float)sp_lm)) * (1.f / 12.f));
-    }
-    if (P.trace.length_ft64 && active && gi < NF) { P.trace.length_ft64[gi] = (double)L; if (P.trace.length_ft) P.trace.length_ft[gi] = (float)L; }
-
-    int loc = P.start_node;
-    bool alive = active;
-    int best_rank = 255;
-    bool ent_surv = false;
-    uint32_t cz = 0;   // cause counters packed: imp | blade << 8 | baro << 16 (one fish visits <= 64 moves)
-    const Real blocked_w = L * sp_wr;    // stryke.py:1418
-
-    for (int k = 0; k < P.n_moves; ++k) {
-      const MoveRec mv = s_moves[k];
-      const NodeRec nd = s_nodes[loc];
-      const bool prev_alive = alive;
-      float rate32 = 0.f;
-      // word slots of this move (MoveRec): r/R + cause share one word, depth, dice, route one each
-      const int s_dep = mv.slot_depth, s_dice = mv.slot_dice;
-      const int s_rt = mv.slot_route;
-      uint32_t w_rc = 0, w_dep = 0;
-      if (!INJECT) {   // warp-uniform draws for this move (refill points are identical for every lane)
-        if (mv.need & (NEED_RR | NEED_CAUSE)) w_rc = rng.word(mv.slot_rc);
-        if (mv.need & NEED_DEPTH) w_dep = rng.word(s_dep);
-      }
-      Real strike_t = (Real)NAN, baro_t = (Real)NAN;
-      if (alive) {
-        if (nd.kind == STRYKE_KIND_APRIORI) {
-          rate32 = nd.apriori32;
-        } else {
-          // ---- (4) impingement, blade strike, barotrauma (node_surv_rate, stryke.py:1410-1572) --------------------
-          const Real* us = s_ustatic + nd.unit * USW;
-          const Real* uc = s_ucoef + nd.unit * UCW<Real>::W;
-          const bool blocked = blocked_w > us[0];
-          const Real imp = (blocked && sp_uc < us[1]) ? (Real)0 : (Real)1;
-          Real strike = (Real)1, baro = (Real)1;
-          if (!blocked) {
-            Real rR = (Real)0.75;
-            if (nd.kind == STRYKE_KIND_KAPLAN) {
-              if (INJECT) rR = (Real)add_(0.3, mul_(sub_(1.0, 0.3), P.inj.rR[(int64_t)k * NF + gi]));
-              else if (sizeof(Real) == 8) rR = (Real)(0.3 + 0.7 * (double)u16hi_co<Real>(w_rc));
-              else rR = (Real)fmaf(0.7f, (float)u16hi_co<Real>(w_rc), 0.3f);
-            }
-            if (sizeof(Real) == 8) strike = (Real)strike_surv64(nd.kind, (const double*)uc, (double)L, (double)rR);
-            else strike = (Real)strike_surv32(nd.kind, (const float*)uc, (float)L, (float)rR);
-            strike_t = strike;
-            if (P.barotrauma) {
-              if (sizeof(Real) == 8) {
-                const double fb = (double)us[2], lo = mul_(fb, (double)sp_d1), hi = mul_(fb, (double)sp_d2);
-                const double ud = INJECT ? P.inj.depth[(int64_t)k * NF + gi] : (double)u_co<Real>(w_dep);
-                baro = (Real)baro_surv64(add_(lo, mul_(sub_(hi, lo), ud)), (double)us[3], (double)sp_b0, (double)sp_b1);
-              } else {
-                const float ud = INJECT ? (float)P.inj.depth[(int64_t)k * NF + gi] : (float)u_co<Real>(w_dep);
-                const float depth = (float)us[2] * fmaf((float)sp_d2 - (float)sp_d1, ud, (float)sp_d1);
-                baro = (Real)baro_surv32(depth, (float)us[4], (float)us[5], (float)sp_b0 * 1.44269504f, (float)sp_b1);
-              }
-              baro_t = baro;
-            }
-          }
-          const Real prob = (sizeof(Real) == 8) ? (Real)mul_(mul_((double)imp, (double)strike), (double)baro)
-                                                : imp * strike * baro;
-          rate32 = (float)prob;                         // np.float32(prob), stryke.py:1575
-          // mortality-cause rolls, independent of the survival dice (stryke.py:1545-1560, Appendix E4)
-          if (INJECT) {
-            const double* cu = P.inj.cause + ((int64_t)k * 4) * NF + gi;
-            if (cu[0] > (double)imp) cz += 1u;
-            else if (cu[NF] > (double)strike) cz += 1u << 8;
-            else if (cu[2 * NF] > (double)baro) cz += 1u << 16;
-          } else {
-            // one uniform splits [0,1) into the same three probabilities the reference's sequential rolls have:
-            // P(imp) = 1-imp, P(blade) = imp (1-strike), P(baro) = imp strike (1-baro)
-            const Real u = u16lo_co<Real>(w_rc);
-            const Real a1 = imp, a2 = imp * strike, a3 = a2 * baro;
-            if (u >= a1) cz += 1u;
-            else if (u >= a2) cz += 1u << 8;
-            else if (u >= a3) cz += 1u << 16;
-          }
-        }
-      }
-      // np.vectorize's probe call: fish 0 is evaluated once more with its own draws; only the cause counters keep
-      // the side effect (stryke.py:3197)
-      if (INJECT && P.inj.ghost_cause && fish == 0 && active && prev_alive && nd.kind != STRYKE_KIND_APRIORI) {
-        const Real* us = s_ustatic + nd.unit * USW;
-        const Real* uc = s_ucoef + nd.unit * UCW<Real>::W;
-        const bool blocked = blocked_w > us[0];
-        const double imp = (blocked && sp_uc < us[1]) ? 0.0 : 1.0;
-        double strike = 1.0, baro = 1.0;
-        const int64_t gk = (int64_t)k * P.n_cells + c;
-        if (!blocked) {
-          double rR = 0.75;
-          if (nd.kind == STRYKE_KIND_KAPLAN) rR = add_(0.3, mul_(sub_(1.0, 0.3), P.inj.ghost_rR[gk]));
-          if (sizeof(Real) == 8) strike = strike_surv64(nd.kind, (const double*)uc, (double)L, rR);
-          else strike = (double)strike_surv32(nd.kind, (const float*)uc, (float)L, (float)rR);
-          if (P.barotrauma) {
-            const double fb = (double)us[2], lo = mul_(fb, (double)sp_d1), hi = mul_(fb, (double)sp_d2);
-            baro = baro_surv64(add_(lo, mul_(sub_(hi, lo), P.inj.ghost_depth[gk])), (double)us[3], (double)sp_b0, (double)sp_b1);
-          }
-        }
-        const double* cu = P.inj.ghost_cause + ((int64_t)k * 4) * P.n_cells + c;
-        if (cu[0] > imp) cz += 1u;
-        else if (cu[P.n_cells] > strike) cz += 1u << 8;
-        else if (cu[2 * P.n_cells] > baro) cz += 1u << 16;
-      }
-
-      // ---- (5) Bernoulli survival roll: dice <= float64(float32(prob)) (stryke.py:3210) ----------------------------
-      bool surv;
-      if (INJECT) {
-        surv = active && (P.inj.dice[(int64_t)k * NF + gi] <= (double)rate32);
-      } else if (mv.need & NEED_DICE) {
-        const uint32_t wd = rng.word(s_dice);
-        surv = alive && (u_oc<Real>(wd) <= (Real)rate32);
-      } else {
-        surv = alive && rate32 >= 1.0f;    // every node of this level has survival 1.0: no draw needed
-      }
-      if (P.trace.state && active && gi < NF) {     // gi >= NF: caller-supplied capacity too small (plan_status reports it)
-        const int64_t o = (int64_t)k * NF + gi;
-        P.trace.state[o] = (uint8_t)loc; P.trace.survival[o] = surv ? 1 : 0; P.trace.rate[o] = rate32;
-        if (P.trace.strike) { P.trace.strike[o] = (double)strike_t; P.trace.baro[o] = (double)baro_t; }
-      }
-
-      // ---- (6) State_Daily: among fish alive after move k-1, per node: successes and count (stryke.py:3302-3351) --
-      for (int p = mv.level_begin; p < mv.level_end; ++p) {
-        const int node = s_pair[p];
-        const bool here = loc == node;
-        const uint32_t bc = __ballot_sync(0xffffffffu, prev_alive && here);
-        const uint32_t bs = __ballot_sync(0xffffffffu, prev_alive && surv && here);
-#pragma unroll
-        for (int r = 0; r < PR; ++r)
-          if ((p >> 5) == r && (p & 31) == lane) { acc_cnt[r] += __popc(bc); acc_suc[r] += __popc(bs); }
-      }
-      // entrainment bookkeeping: first 'U' state in lexicographic column order (stryke.py:3272-3292)
-      if (nd.hasU && active && (int)mv.lex < best_rank) { best_rank = mv.lex; ent_surv = surv; }
-
-      // ---- (3) movement: searchsorted(cdf, u, side='right') over the node's successors (stryke.py:2058) -----------
-      if (k < P.n_moves - 1) {
-        Real u = (Real)0;
-        if (!INJECT && (mv.need & NEED_ROUTE)) u = u_co<Real>(rng.word(s_rt));
-        if (surv && nd.deg > 0 && !s_stay[loc]) {
-          if (INJECT) u = (Real)P.inj.route[(int64_t)k * NF + gi];
-          int j = 0;
-          if (INJECT && sizeof(Real) == 4) {
-            const double* cdf64 = P.edge_cdf + (size_t)cur_day * P.n_edges + nd.edge_off;
-            const double ud = P.inj.route[(int64_t)k * NF + gi];
-            for (int e = 0; e < nd.deg - 1; ++e) j += (cdf64[e] <= ud) ? 1 : 0;
-          } else {
-            const Real* cdf = s_cdf + nd.edge_off;
-            for (int e = 0; e < nd.deg - 1; ++e) j += (cdf[e] <= u) ? 1 : 0;
-          }
-          loc = s_edge_dst[nd.edge_off + j];
-        }
-      }
-      alive = surv;
-    }
-
-    // ---- Daily tallies of this tile (stryke.py:3281-3298, :3353-3366) ----------------------------------------------
-    const bool ent = active && best_rank < 255;
-    const uint32_t b_ent = __ballot_sync(0xffffffffu, ent);
-    const uint32_t b_sur = __ballot_sync(0xffffffffu, ent && ent_surv);
-    const uint32_t any_cz = __ballot_sync(0xffffffffu, cz != 0);
-    uint32_t r_imp = 0, r_bld = 0, r_bar = 0;
-    if (any_cz) {
-      r_imp = __reduce_add_sync(0xffffffffu, cz & 0xffu);
-      r_bld = __reduce_add_sync(0xffffffffu, (cz >> 8) & 0xffu);
-      r_bar = __reduce_add_sync(0xffffffffu, (cz >> 16) & 0xffu);
-    }
-    acc_daily += lane == 0 ? __popc(b_ent) : lane == 1 ? __popc(b_sur) : lane == 2 ? r_imp : lane == 3 ? r_bld : lane == 4 ? r_bar : 0u;
-  }
-  if (cur_cell >= 0) flush(cur_cell);
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// small utility kernels: per-fish probability functions, Philox KAT, issue-rate calibration
-// ------------------------------------------------------------------------------------------------------------------
-template <typename Real>
-__global__ void strike_kernel(int kind, const double* __restrict__ uc8, int64_t n, const double* __restrict__ L,
-                              const double* __restrict__ rR, double* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double r = (kind == STRYKE_KIND_KAPLAN) ? rR[i] : 0.75;
-  if (sizeof(Real) == 8) {
-    out[i] = strike_surv64(kind, uc8, L[i], r);
-  } else {
-    const double lnd = uc8[0] * uc8[1] / uc8[2];
-    const bool kap = kind == STRYKE_KIND_KAPLAN;
-    float f[4] = {kap ? (float)(uc8[3] / uc8[4]) : 0.f, kap ? (float)(1.0 / uc8[5]) : 0.f,
-                  kap ? (float)lnd : (float)(lnd * uc8[3]), (float)uc8[6]};
-    out[i] = (double)strike_surv32(kind, f, (float)L[i], (float)r);
-  }
-}
-template <typename Real>
-__global__ void baro_kernel(int64_t n, const double* __restrict__ depth, double tail, double b0, double b1,
-                            double* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (sizeof(Real) == 8) {
-    out[i] = baro_surv64(depth[i], tail, b0, b1);
-  } else {
-    const double p2 = P_ATM + RHO * G_SI * (tail * FT2M);
-    out[i] = (double)baro_surv32((float)depth[i], (float)(P_ATM / p2), (float)(RHO * G_SI * FT2M / p2),
-                                 (float)b0 * 1.44269504f, (float)b1);
-  }
-}
-__global__ void philox_kernel(int64_t n, const uint32_t* __restrict__ ctr, const uint32_t* __restrict__ key,
-                              uint32_t* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t w[4];
-  Philox::block(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1], w);
-  out[4 * i] = w[0]; out[4 * i + 1] = w[1]; out[4 * i + 2] = w[2]; out[4 * i + 3] = w[3];
-}
-// Issue-rate calibration: 16 independent FFMA chains per thread, 128 FFMA per loop iteration (PTX, so the count is
-// exact).  FFMA issues at one warp instruction per scheduler per cycle (both FP32 datapaths of an SM sub-partition),
-// so the achieved FFMA lane-ops/s is the measured instruction-issue ceiling the passage kernel is compared with.
-constexpr int CAL_ITERS = 1024, CAL_OPS = 128;
-__global__ void __launch_bounds__(256) calibrate_kernel(uint32_t* out, uint32_t seed) {
-  float x[16];
-  const float m = 1.0f + 1e-7f * (float)(seed & 7), c = 1e-9f * (float)(threadIdx.x & 3);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) x[i] = (float)(threadIdx.x + i);
-#pragma unroll 1
-  for (int it = 0; it < CAL_ITERS; ++it) {
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(x[i]) : "f"(m), "f"(c));
-    }
-  }
-  uint32_t s = 0;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) s += __float_as_uint(x[i]);
-  if (s == 0x12345678u) out[0] = s;   // never true in practice; keeps the chains live
-}
+#include "passage_kernels.cuh"     // device code of the general path, count / scan, probability and calibration kernels
 
 // ------------------------------------------------------------------------------------------------------------------
 // host side
@@ -1086,303 +466,7 @@ static int launch_fast_minb(StrykePlan* pl, cudaStream_t st) {
     default: return b ? launch_fast<4, true, MINB>(pl, st) : launch_fast<4, false, MINB>(pl, st);
   }
 }
-// ------------------------------------------------------------------------------------------------------------------
-// Run-time specialisation of the throughput kernel (NVRTC).  The hand-written body passage_fast_body<> is compiled
-// once per facility shape with a table provider whose per-move records, pair list and row stride are compile-time
-// constants generated from the plan: the move loop unrolls, every "does this level need a draw" test, Philox slot and
-// pair index folds to an immediate.  libnvrtc is loaded lazily with dlopen; when it is not available the plan simply
-// keeps the ahead-of-time generic instantiation (same results, tested).
-// ------------------------------------------------------------------------------------------------------------------
-namespace jit {
-typedef struct _nvrtcProgram* nvrtcProgram;
-struct Api {
-  int (*create)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
-  int (*compile)(nvrtcProgram, int, const char* const*) = nullptr;
-  int (*log_size)(nvrtcProgram, size_t*) = nullptr;
-  int (*log)(nvrtcProgram, char*) = nullptr;
-  int (*cubin_size)(nvrtcProgram, size_t*) = nullptr;
-  int (*cubin)(nvrtcProgram, char*) = nullptr;
-  int (*destroy)(nvrtcProgram*) = nullptr;
-  bool ok = false;
-};
-static Api& api() {
-  static Api a = [] {
-    Api x;
-    void* h = nullptr;
-    for (const char* name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"}) {
-      h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
-      if (h) break;
-    }
-    if (!h) return x;
-    x.create = (decltype(x.create))dlsym(h, "nvrtcCreateProgram");
-    x.compile = (decltype(x.compile))dlsym(h, "nvrtcCompileProgram");
-    x.log_size = (decltype(x.log_size))dlsym(h, "nvrtcGetProgramLogSize");
-    x.log = (decltype(x.log))dlsym(h, "nvrtcGetProgramLog");
-    x.cubin_size = (decltype(x.cubin_size))dlsym(h, "nvrtcGetCUBINSize");
-    x.cubin = (decltype(x.cubin))dlsym(h, "nvrtcGetCUBIN");
-    x.destroy = (decltype(x.destroy))dlsym(h, "nvrtcDestroyProgram");
-    x.ok = x.create && x.compile && x.log_size && x.log && x.cubin_size && x.cubin && x.destroy;
-    return x;
-  }();
-  return a;
-}
-static std::string g_source_dir;
-static std::mutex g_mu;
-static std::map<std::string, std::vector<char>> g_cubins;        // generated source -> cubin
-struct Loaded { cudaLibrary_t lib; cudaKernel_t kern; };
-static std::map<std::pair<int, std::string>, Loaded> g_loaded;   // (device, source) -> loaded kernel
-
-static bool read_file(const std::string& path, std::string* out) {
-  std::ifstream f(path);
-  if (!f) return false;
-  std::stringstream ss;
-  ss << f.rdbuf();
-  *out = ss.str();
-  return true;
-}
-
-
-// NW stays 0 (ballot tallies) when the facility does not fit the scheme: move loop not unrolled (> 32 moves), too many
-// words for the register file, a node whose local index differs between two levels, > 40 nodes in one level.
-static TallyPlan plan_tally(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int n_nodes) {
-  TallyPlan T;
-  const int M = (int)moves.size();
-  T.node_local.assign((size_t)std::max(n_nodes, 1), -1);
-  if (M > 32) return T;
-  std::vector<int> fill;             // 6-bit fields used in every word (5 per word)
-  auto alloc = [&](int n) {          // n <= 5 contiguous fields inside one word -> (word, first bit)
-    for (size_t w = 0; w < fill.size(); ++w)
-      if (fill[w] + n <= 5) { const int b = 6 * fill[w]; fill[w] += n; return std::make_pair((int)w, b); }
-    fill.push_back(n);
-    return std::make_pair((int)fill.size() - 1, 0);
-  };
-  auto field = [&](int w, int sh, int bits, int target, int p0, int len) {
-    T.fields.push_back(FieldRec{(uint8_t)w, (uint8_t)sh, (uint8_t)bits, (uint8_t)target, (uint8_t)p0, (uint8_t)len});
-  };
-  int n_cause = 0;
-  T.lv.assign((size_t)M, LevelTally{});
-  // passive level: nobody can die there (no dice <=> all nodes a-priori with survival >= 1), survivors = arrivals.
-  // Consecutive passive ONE-node levels form a run: the same fish are counted at each of them, one field serves all.
-  auto passive1 = [&](int k) { return !(moves[k].need & NEED_DICE) && moves[k].level_end - moves[k].level_begin == 1; };
-  for (int k = 0; k < M; ++k) {
-    const MoveRec& m = moves[k];
-    const int n = m.level_end - m.level_begin;
-    const bool same = !(m.need & NEED_DICE);
-    if (m.need & NEED_CAUSE) ++n_cause;
-    if (passive1(k)) {
-      if (k > 0 && passive1(k - 1)) continue;                             // inside a run (kind 0)
-      int run = 1;
-      while (k + run < M && passive1(k + run)) ++run;                      // one pair per level, consecutive pair ids
-      const auto a = alloc(1);
-      T.lv[k] = LevelTally{1, (uint8_t)a.first, (uint8_t)a.second, 0, 0, 1, 1};
-      field(a.first, a.second, 6, 2, m.level_begin, run);
-    } else if (n <= 5) {
-      const auto a = alloc(n);
-      const auto b = same ? a : alloc(n);
-      T.lv[k] = LevelTally{(uint8_t)(n == 1 ? 2 : 3), (uint8_t)a.first, (uint8_t)a.second, (uint8_t)b.first, (uint8_t)b.second, 1,
-                           (uint8_t)same};
-      for (int i = 0; i < n; ++i) {
-        field(a.first, a.second + 6 * i, 6, same ? 2 : 0, m.level_begin + i, 1);
-        if (!same) field(b.first, b.second + 6 * i, 6, 1, m.level_begin + i, 1);
-      }
-    } else {
-      if (n > 40) return TallyPlan{};
-      const int nwl = (n + 4) / 5;
-      const int wc = (int)fill.size();
-      for (int j = 0; j < (same ? 1 : 2) * nwl; ++j) fill.push_back(5);
-      T.lv[k] = LevelTally{4, (uint8_t)wc, 0, (uint8_t)(wc + (same ? 0 : nwl)), 0, (uint8_t)nwl, (uint8_t)same};
-      for (int i = 0; i < n; ++i) {
-        field(wc + i / 5, 6 * (i % 5), 6, same ? 2 : 0, m.level_begin + i, 1);
-        if (!same) field(wc + nwl + i / 5, 6 * (i % 5), 6, 1, m.level_begin + i, 1);
-      }
-    }
-    if (n > 1)
-      for (int i = 0; i < n; ++i) {
-        const int v = pairs[m.level_begin + i];
-        if (v >= (int)T.node_local.size()) T.node_local.resize((size_t)v + 1, -1);
-        if (T.node_local[v] >= 0 && T.node_local[v] != i) return TallyPlan{};
-        T.node_local[v] = i;
-      }
-  }
-  const auto es = alloc(2);
-  T.W_ES = es.first; T.B_ES = es.second;
-  field(es.first, es.second, 6, 3, 0, 1);
-  field(es.first, es.second + 6, 6, 3, 1, 1);
-  T.W_CAUSE = (int)fill.size();
-  fill.push_back(5);
-  for (int j = 0; j < 3; ++j) field(T.W_CAUSE, 10 * j, 10, 3, 2 + j, 1);
-  T.HOLD = std::min(63, 1023 / std::max(1, n_cause));
-  // n_cause <= 31: the single-tile drain sums whole words, 32 lanes x n_cause must fit the 10-bit cause fields
-  if ((int)fill.size() > 24 || T.fields.size() > 250 || T.HOLD < 4 || n_cause > 31) return TallyPlan{};
-  T.NW = (int)fill.size();
-  return T;
-}
-
-// resident 256-thread blocks per SM the specialised kernel is compiled for (register budget: 4 -> 64, 3 -> 80, 2 -> 128)
-static int spec_min_blocks() {
-  const char* e = getenv("STRYKE_B200_SPEC_MINB");
-  const int v = e ? atoi(e) : 3;      // measured on B200: 3 (80 registers) beats 4 (64, rematerialises) and 2
-  return v >= 1 && v <= 8 ? v : 3;
-}
-
-// The table provider + kernel entry for one plan.
-static std::string generate(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int stride, int pr, bool baro,
-                            const TallyPlan& T, const Dims& D) {
-  std::ostringstream o;
-  const int M = (int)moves.size(), P = (int)pairs.size();
-  o << "#define STRYKE_NVRTC 1\n";
-  if (const char* defs = getenv("STRYKE_B200_JIT_DEFINES")) {      // experiment switches: "A=1,B" -> #define A 1 / #define B
-    std::string d(defs), tok;
-    std::stringstream ss(d);
-    while (std::getline(ss, tok, ',')) {
-      if (tok.empty()) continue;
-      const size_t eq = tok.find('=');
-      o << "#define " << (eq == std::string::npos ? tok : tok.substr(0, eq) + " " + tok.substr(eq + 1)) << "\n";
-    }
-  }
-  o << "#include \"passage_fast.cuh\"\nnamespace stryke {\nstruct SpecJit {\n"
-    << "  static constexpr bool kStatic = true;\n"
-    << "  static constexpr int M = " << M << ", STRIDE = " << stride << ", UNROLL_K = " << (M <= 32 ? M : 1) << ", UNROLL_P = 8;\n"
-    << "  static constexpr int N_NODES = " << D.n_nodes << ", N_UNITS = " << D.n_units << ", N_PAIRS = " << P
-    << ", N_SPECIES_STAGED = " << D.n_species_staged << ", START_NODE = " << D.start_node << ";\n"
-    << "  static constexpr int NW = " << T.NW << ", NF = " << (T.NW ? (int)T.fields.size() : 0) << ", HOLD = " << T.HOLD
-    << ", W_ES = " << T.W_ES << ", B_ES = " << T.B_ES << ", W_CAUSE = " << T.W_CAUSE << ";\n"
-    << "  static __device__ constexpr MoveRec move(const FastTables&, int k) {\n    constexpr MoveRec T[" << M << "] = {";
-  for (int k = 0; k < M; ++k) {
-    const MoveRec& m = moves[k];
-    o << (k ? ", " : "") << "{" << (int)m.lex << ", " << (int)m.need << ", " << m.slot_rc << ", " << m.level_begin << ", "
-      << m.level_end << ", " << m.slot_route << ", " << (int)m.max_deg << ", " << (int)m.pad << ", " << m.slot_depth << ", "
-      << m.slot_dice << "}";
-  }
-  o << "};\n    return T[k];\n  }\n  static __device__ constexpr int pair_node(const FastTables&, int p) {\n    constexpr uint8_t N[" << P << "] = {";
-  for (int p = 0; p < P; ++p) o << (p ? ", " : "") << (int)pairs[p];
-  o << "};\n    return (int)N[p];\n  }\n";
-  if (T.NW) {
-    o << "  static __device__ constexpr LevelTally tally(int k) {\n    constexpr LevelTally T[" << M << "] = {";
-    for (int k = 0; k < M; ++k) {
-      const LevelTally& l = T.lv[k];
-      o << (k ? ", " : "") << "{" << (int)l.kind << ", " << (int)l.wc << ", " << (int)l.bc << ", " << (int)l.ws << ", " << (int)l.bs << ", "
-        << (int)l.nwl << ", " << (int)l.same << "}";
-    }
-    o << "};\n    return T[k];\n  }\n  static __device__ constexpr FieldRec field(int f) {\n    constexpr FieldRec T[" << T.fields.size() << "] = {";
-    for (size_t f = 0; f < T.fields.size(); ++f) {
-      const FieldRec& r = T.fields[f];
-      o << (f ? ", " : "") << "{" << (int)r.w << ", " << (int)r.sh << ", " << (int)r.bits << ", " << (int)r.target << ", " << (int)r.p0 << ", " << (int)r.len << "}";
-    }
-    o << "};\n    return T[f];\n  }\n";
-    // per-lane views of the same layout for the single-tile drain
-    const int n_lane = 32 * pr;
-    std::vector<uint32_t> lcfg((size_t)n_lane, 0u), dcfg(32, 0u);
-    for (const FieldRec& r : T.fields) {
-      if (r.target == 3) {
-        if (r.p0 < 32) dcfg[r.p0] = (uint32_t)r.w | ((uint32_t)r.sh << 5) | ((r.bits == 10 ? 1u : 0u) << 10) | (1u << 11);
-        continue;
-      }
-      for (int p2 = r.p0; p2 < r.p0 + r.len && p2 < n_lane; ++p2) {
-        if (r.target != 1) lcfg[p2] = (lcfg[p2] & ~0x3ffu) | (uint32_t)r.w | ((uint32_t)r.sh << 5);
-        if (r.target != 0) lcfg[p2] = (lcfg[p2] & ~(0x3ffu << 10)) | ((uint32_t)r.w << 10) | ((uint32_t)r.sh << 15);
-        lcfg[p2] |= 1u << 20;
-      }
-    }
-    o << "  static __device__ uint32_t lane_cfg(int i) {\n    constexpr uint32_t T[" << n_lane << "] = {";
-    for (int i = 0; i < n_lane; ++i) o << (i ? ", " : "") << lcfg[i] << "u";
-    o << "};\n    return T[i];\n  }\n  static __device__ uint32_t daily_cfg(int i) {\n    constexpr uint32_t T[32] = {";
-    for (int i = 0; i < 32; ++i) o << (i ? ", " : "") << dcfg[i] << "u";
-    o << "};\n    return T[i];\n  }\n";
-  } else {
-    o << "  static __device__ constexpr LevelTally tally(int) { return LevelTally{}; }\n"
-      << "  static __device__ constexpr FieldRec field(int) { return FieldRec{}; }\n"
-      << "  static __device__ constexpr uint32_t lane_cfg(int) { return 0u; }\n"
-      << "  static __device__ constexpr uint32_t daily_cfg(int) { return 0u; }\n";
-  }
-  o << "};\n}  // namespace stryke\n"
-    << "extern \"C\" __global__ void __launch_bounds__(256, " << spec_min_blocks() << ") passage_spec(const stryke::KParams P, const stryke::FastTables FT,\n"
-    << "    const uint2* __restrict__ g_nodes, const int stride, const int n_species_staged) {\n"
-    << "  stryke::passage_fast_body<stryke::SpecJit, " << pr << ", " << (baro ? "true" : "false") << ">(P, FT, g_nodes, stride, n_species_staged);\n}\n";
-  return o.str();
-}
-
-// nullptr + message on failure
-static const std::vector<char>* compile(const std::string& src, std::string* err, bool fresh) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  auto it = g_cubins.find(src);
-  if (it != g_cubins.end() && !fresh) return &it->second;
-  Api& a = api();
-  if (!a.ok) { *err = "libnvrtc not available"; return nullptr; }
-  std::string fast, common;
-  if (g_source_dir.empty()) {      // default: csrc/ next to the shared library this code was loaded from
-    Dl_info info;
-    if (dladdr((const void*)&stryke_b200_abi_version, &info) && info.dli_fname) {
-      std::string so(info.dli_fname);
-      const size_t slash = so.rfind('/');
-      g_source_dir = (slash == std::string::npos ? std::string(".") : so.substr(0, slash)) + "/csrc";
-    }
-  }
-  if (g_source_dir.empty() || !read_file(g_source_dir + "/passage_fast.cuh", &fast) || !read_file(g_source_dir + "/passage_common.cuh", &common)) {
-    *err = "kernel sources not found (stryke_b200_set_source_dir)";
-    return nullptr;
-  }
-  // on-disk cache of compiled specialisations: key = FNV-1a of (generated source, both headers, target)
-  uint64_t h = 1469598103934665603ull;
-  const std::string* parts[3] = {&src, &fast, &common};
-  for (const std::string* part : parts)
-    for (unsigned char ch : *part) { h ^= ch; h *= 1099511628211ull; }
-  std::string dir;
-  if (const char* e = getenv("STRYKE_B200_CACHE_DIR")) dir = e;
-  else dir = g_source_dir + "/../.jit_cache";      // inside the package directory
-  char name[64];
-  snprintf(name, sizeof name, "/sm_100a_%016llx.cubin", (unsigned long long)h);
-  const std::string path = dir + name;
-  if (!fresh) {
-    std::ifstream f(path, std::ios::binary);
-    if (f) {
-      std::vector<char> bin((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-      if (bin.size() > 1024) return &(g_cubins[src] = std::move(bin));
-    }
-  }
-  const char* headers[2] = {fast.c_str(), common.c_str()};
-  const char* names[2] = {"passage_fast.cuh", "passage_common.cuh"};
-  nvrtcProgram prog = nullptr;
-  if (a.create(&prog, src.c_str(), "passage_spec.cu", 2, headers, names) != 0) { *err = "nvrtcCreateProgram failed"; return nullptr; }
-  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
-  const int rc = a.compile(prog, 3, opts);
-  if (rc != 0) {
-    size_t n = 0;
-    a.log_size(prog, &n);
-    std::string log(n, '\0');
-    if (n) a.log(prog, &log[0]);
-    a.destroy(&prog);
-    *err = "NVRTC compile failed: " + log.substr(0, 2000);
-    return nullptr;
-  }
-  size_t n = 0;
-  a.cubin_size(prog, &n);
-  std::vector<char> bin(n);
-  a.cubin(prog, bin.data());
-  a.destroy(&prog);
-  if (system(("mkdir -p '" + dir + "' 2>/dev/null").c_str()) == 0) {      // best effort; a read-only home is fine
-    const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
-    std::ofstream f(tmp, std::ios::binary);
-    if (f && f.write(bin.data(), (std::streamsize)bin.size())) { f.close(); rename(tmp.c_str(), path.c_str()); }
-  }
-  return &(g_cubins[src] = std::move(bin));
-}
-
-static int load(int device, const std::string& src, const std::vector<char>& bin, cudaKernel_t* kern, std::string* err) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  auto key = std::make_pair(device, src);
-  auto it = g_loaded.find(key);
-  if (it == g_loaded.end()) {
-    Loaded l{};
-    cudaError_t e = cudaLibraryLoadData(&l.lib, bin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-    if (e == cudaSuccess) e = cudaLibraryGetKernel(&l.kern, l.lib, "passage_spec");
-    if (e != cudaSuccess) { *err = std::string("loading the specialised kernel failed: ") + cudaGetErrorString(e); cudaGetLastError(); return 1; }
-    it = g_loaded.emplace(key, l).first;
-  }
-  *kern = it->second.kern;
-  return 0;
-}
-}  // namespace jit
+#include "specialise.inl"      // namespace jit: tally layout, source generation, NVRTC compile + cubin cache, load
 
 static int launch_jit(StrykePlan* pl, cudaStream_t st) {
   const void* fn = (const void*)pl->jit_kernel;

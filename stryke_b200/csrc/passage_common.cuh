@@ -1,5 +1,5 @@
 // passage_common.cuh — device-side definitions shared by the ahead-of-time build (nvcc, passage.cu) and the run-time
-// specialisation of the throughput kernel (NVRTC, see jit_specialise() in passage.cu).  No host headers in here when
+// specialisation of the throughput kernel (NVRTC, see specialise.inl).  No host headers in here when
 // STRYKE_NVRTC is defined: NVRTC has no libc, so the fixed-width integer types and the few ABI constants the kernels
 // need are defined locally.  The struct layouts below are the launch ABI between the host code and BOTH compilations.
 #pragma once

@@ -19,7 +19,7 @@
 //
 // The body is a template over a *table provider*.  RuntimeTables (ahead-of-time build) reads the per-move records from
 // the constant bank.  At plan creation the host can also generate a provider whose tables are compile-time constants of
-// the plan's facility and compile this same body with NVRTC (jit_specialise() in passage.cu): the move loop then unrolls
+// the plan's facility and compile this same body with NVRTC (specialise.inl): the move loop then unrolls
 // completely and every need test, word slot and pair index folds away — measured 347 executed instructions per tile of
 // 32 fish on the C2 facility against 660 for the generic instantiation.
 // tests/test_gpu_native_rng.py requires identical tallies from the general kernel, the generic and the specialised
@@ -82,7 +82,7 @@ __device__ __forceinline__ void add_if_lane1(uint32_t& acc, int p, int lane_id, 
 }
 
 // Packed per-lane tallies (specialised instantiation only; the layout is generated per facility by the host,
-// jit::plan_tally in passage.cu).  Every lane counts ITS OWN fish in 6-bit fields of a few registers ("tally words"):
+// jit::plan_tally in specialise.inl).  Every lane counts ITS OWN fish in 6-bit fields of a few registers ("tally words"):
 // one field per (move, node) pair for arrivals and one for survivors, one per run of trivial levels, two for the
 // Daily entrained / survived flags; the three mortality causes use 10-bit fields (a fish rolls a cause at every turbine
 // level, stryke.py:1545-1560).  A tile adds at most 1 to a 6-bit field, so the words are only reduced across the warp

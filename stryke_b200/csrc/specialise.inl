@@ -1,0 +1,299 @@
+// specialise.inl — run-time specialisation of the throughput kernel with NVRTC (part of passage.cu: included there, uses
+// its StrykePlan / fail / MoveRec definitions).  Host code only.
+// ------------------------------------------------------------------------------------------------------------------
+// Run-time specialisation of the throughput kernel (NVRTC).  The hand-written body passage_fast_body<> is compiled
+// once per facility shape with a table provider whose per-move records, pair list and row stride are compile-time
+// constants generated from the plan: the move loop unrolls, every "does this level need a draw" test, Philox slot and
+// pair index folds to an immediate.  libnvrtc is loaded lazily with dlopen; when it is not available the plan simply
+// keeps the ahead-of-time generic instantiation (same results, tested).
+// ------------------------------------------------------------------------------------------------------------------
+namespace jit {
+typedef struct _nvrtcProgram* nvrtcProgram;
+struct Api {
+  int (*create)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  int (*compile)(nvrtcProgram, int, const char* const*) = nullptr;
+  int (*log_size)(nvrtcProgram, size_t*) = nullptr;
+  int (*log)(nvrtcProgram, char*) = nullptr;
+  int (*cubin_size)(nvrtcProgram, size_t*) = nullptr;
+  int (*cubin)(nvrtcProgram, char*) = nullptr;
+  int (*destroy)(nvrtcProgram*) = nullptr;
+  bool ok = false;
+};
+static Api& api() {
+  static Api a = [] {
+    Api x;
+    void* h = nullptr;
+    for (const char* name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"}) {
+      h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (h) break;
+    }
+    if (!h) return x;
+    x.create = (decltype(x.create))dlsym(h, "nvrtcCreateProgram");
+    x.compile = (decltype(x.compile))dlsym(h, "nvrtcCompileProgram");
+    x.log_size = (decltype(x.log_size))dlsym(h, "nvrtcGetProgramLogSize");
+    x.log = (decltype(x.log))dlsym(h, "nvrtcGetProgramLog");
+    x.cubin_size = (decltype(x.cubin_size))dlsym(h, "nvrtcGetCUBINSize");
+    x.cubin = (decltype(x.cubin))dlsym(h, "nvrtcGetCUBIN");
+    x.destroy = (decltype(x.destroy))dlsym(h, "nvrtcDestroyProgram");
+    x.ok = x.create && x.compile && x.log_size && x.log && x.cubin_size && x.cubin && x.destroy;
+    return x;
+  }();
+  return a;
+}
+static std::string g_source_dir;
+static std::mutex g_mu;
+static std::map<std::string, std::vector<char>> g_cubins;        // generated source -> cubin
+struct Loaded { cudaLibrary_t lib; cudaKernel_t kern; };
+static std::map<std::pair<int, std::string>, Loaded> g_loaded;   // (device, source) -> loaded kernel
+
+static bool read_file(const std::string& path, std::string* out) {
+  std::ifstream f(path);
+  if (!f) return false;
+  std::stringstream ss;
+  ss << f.rdbuf();
+  *out = ss.str();
+  return true;
+}
+
+
+// NW stays 0 (ballot tallies) when the facility does not fit the scheme: move loop not unrolled (> 32 moves), too many
+// words for the register file, a node whose local index differs between two levels, > 40 nodes in one level.
+static TallyPlan plan_tally(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int n_nodes) {
+  TallyPlan T;
+  const int M = (int)moves.size();
+  T.node_local.assign((size_t)std::max(n_nodes, 1), -1);
+  if (M > 32) return T;
+  std::vector<int> fill;             // 6-bit fields used in every word (5 per word)
+  auto alloc = [&](int n) {          // n <= 5 contiguous fields inside one word -> (word, first bit)
+    for (size_t w = 0; w < fill.size(); ++w)
+      if (fill[w] + n <= 5) { const int b = 6 * fill[w]; fill[w] += n; return std::make_pair((int)w, b); }
+    fill.push_back(n);
+    return std::make_pair((int)fill.size() - 1, 0);
+  };
+  auto field = [&](int w, int sh, int bits, int target, int p0, int len) {
+    T.fields.push_back(FieldRec{(uint8_t)w, (uint8_t)sh, (uint8_t)bits, (uint8_t)target, (uint8_t)p0, (uint8_t)len});
+  };
+  int n_cause = 0;
+  T.lv.assign((size_t)M, LevelTally{});
+  // passive level: nobody can die there (no dice <=> all nodes a-priori with survival >= 1), survivors = arrivals.
+  // Consecutive passive ONE-node levels form a run: the same fish are counted at each of them, one field serves all.
+  auto passive1 = [&](int k) { return !(moves[k].need & NEED_DICE) && moves[k].level_end - moves[k].level_begin == 1; };
+  for (int k = 0; k < M; ++k) {
+    const MoveRec& m = moves[k];
+    const int n = m.level_end - m.level_begin;
+    const bool same = !(m.need & NEED_DICE);
+    if (m.need & NEED_CAUSE) ++n_cause;
+    if (passive1(k)) {
+      if (k > 0 && passive1(k - 1)) continue;                             // inside a run (kind 0)
+      int run = 1;
+      while (k + run < M && passive1(k + run)) ++run;                      // one pair per level, consecutive pair ids
+      const auto a = alloc(1);
+      T.lv[k] = LevelTally{1, (uint8_t)a.first, (uint8_t)a.second, 0, 0, 1, 1};
+      field(a.first, a.second, 6, 2, m.level_begin, run);
+    } else if (n <= 5) {
+      const auto a = alloc(n);
+      const auto b = same ? a : alloc(n);
+      T.lv[k] = LevelTally{(uint8_t)(n == 1 ? 2 : 3), (uint8_t)a.first, (uint8_t)a.second, (uint8_t)b.first, (uint8_t)b.second, 1,
+                           (uint8_t)same};
+      for (int i = 0; i < n; ++i) {
+        field(a.first, a.second + 6 * i, 6, same ? 2 : 0, m.level_begin + i, 1);
+        if (!same) field(b.first, b.second + 6 * i, 6, 1, m.level_begin + i, 1);
+      }
+    } else {
+      if (n > 40) return TallyPlan{};
+      const int nwl = (n + 4) / 5;
+      const int wc = (int)fill.size();
+      for (int j = 0; j < (same ? 1 : 2) * nwl; ++j) fill.push_back(5);
+      T.lv[k] = LevelTally{4, (uint8_t)wc, 0, (uint8_t)(wc + (same ? 0 : nwl)), 0, (uint8_t)nwl, (uint8_t)same};
+      for (int i = 0; i < n; ++i) {
+        field(wc + i / 5, 6 * (i % 5), 6, same ? 2 : 0, m.level_begin + i, 1);
+        if (!same) field(wc + nwl + i / 5, 6 * (i % 5), 6, 1, m.level_begin + i, 1);
+      }
+    }
+    if (n > 1)
+      for (int i = 0; i < n; ++i) {
+        const int v = pairs[m.level_begin + i];
+        if (v >= (int)T.node_local.size()) T.node_local.resize((size_t)v + 1, -1);
+        if (T.node_local[v] >= 0 && T.node_local[v] != i) return TallyPlan{};
+        T.node_local[v] = i;
+      }
+  }
+  const auto es = alloc(2);
+  T.W_ES = es.first; T.B_ES = es.second;
+  field(es.first, es.second, 6, 3, 0, 1);
+  field(es.first, es.second + 6, 6, 3, 1, 1);
+  T.W_CAUSE = (int)fill.size();
+  fill.push_back(5);
+  for (int j = 0; j < 3; ++j) field(T.W_CAUSE, 10 * j, 10, 3, 2 + j, 1);
+  T.HOLD = std::min(63, 1023 / std::max(1, n_cause));
+  // n_cause <= 31: the single-tile drain sums whole words, 32 lanes x n_cause must fit the 10-bit cause fields
+  if ((int)fill.size() > 24 || T.fields.size() > 250 || T.HOLD < 4 || n_cause > 31) return TallyPlan{};
+  T.NW = (int)fill.size();
+  return T;
+}
+
+// resident 256-thread blocks per SM the specialised kernel is compiled for (register budget: 4 -> 64, 3 -> 80, 2 -> 128)
+static int spec_min_blocks() {
+  const char* e = getenv("STRYKE_B200_SPEC_MINB");
+  const int v = e ? atoi(e) : 3;      // measured on B200: 3 (80 registers) beats 4 (64, rematerialises) and 2
+  return v >= 1 && v <= 8 ? v : 3;
+}
+
+// The table provider + kernel entry for one plan.
+static std::string generate(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int stride, int pr, bool baro,
+                            const TallyPlan& T, const Dims& D) {
+  std::ostringstream o;
+  const int M = (int)moves.size(), P = (int)pairs.size();
+  o << "#define STRYKE_NVRTC 1\n";
+  if (const char* defs = getenv("STRYKE_B200_JIT_DEFINES")) {      // experiment switches: "A=1,B" -> #define A 1 / #define B
+    std::string d(defs), tok;
+    std::stringstream ss(d);
+    while (std::getline(ss, tok, ',')) {
+      if (tok.empty()) continue;
+      const size_t eq = tok.find('=');
+      o << "#define " << (eq == std::string::npos ? tok : tok.substr(0, eq) + " " + tok.substr(eq + 1)) << "\n";
+    }
+  }
+  o << "#include \"passage_fast.cuh\"\nnamespace stryke {\nstruct SpecJit {\n"
+    << "  static constexpr bool kStatic = true;\n"
+    << "  static constexpr int M = " << M << ", STRIDE = " << stride << ", UNROLL_K = " << (M <= 32 ? M : 1) << ", UNROLL_P = 8;\n"
+    << "  static constexpr int N_NODES = " << D.n_nodes << ", N_UNITS = " << D.n_units << ", N_PAIRS = " << P
+    << ", N_SPECIES_STAGED = " << D.n_species_staged << ", START_NODE = " << D.start_node << ";\n"
+    << "  static constexpr int NW = " << T.NW << ", NF = " << (T.NW ? (int)T.fields.size() : 0) << ", HOLD = " << T.HOLD
+    << ", W_ES = " << T.W_ES << ", B_ES = " << T.B_ES << ", W_CAUSE = " << T.W_CAUSE << ";\n"
+    << "  static __device__ constexpr MoveRec move(const FastTables&, int k) {\n    constexpr MoveRec T[" << M << "] = {";
+  for (int k = 0; k < M; ++k) {
+    const MoveRec& m = moves[k];
+    o << (k ? ", " : "") << "{" << (int)m.lex << ", " << (int)m.need << ", " << m.slot_rc << ", " << m.level_begin << ", "
+      << m.level_end << ", " << m.slot_route << ", " << (int)m.max_deg << ", " << (int)m.pad << ", " << m.slot_depth << ", "
+      << m.slot_dice << "}";
+  }
+  o << "};\n    return T[k];\n  }\n  static __device__ constexpr int pair_node(const FastTables&, int p) {\n    constexpr uint8_t N[" << P << "] = {";
+  for (int p = 0; p < P; ++p) o << (p ? ", " : "") << (int)pairs[p];
+  o << "};\n    return (int)N[p];\n  }\n";
+  if (T.NW) {
+    o << "  static __device__ constexpr LevelTally tally(int k) {\n    constexpr LevelTally T[" << M << "] = {";
+    for (int k = 0; k < M; ++k) {
+      const LevelTally& l = T.lv[k];
+      o << (k ? ", " : "") << "{" << (int)l.kind << ", " << (int)l.wc << ", " << (int)l.bc << ", " << (int)l.ws << ", " << (int)l.bs << ", "
+        << (int)l.nwl << ", " << (int)l.same << "}";
+    }
+    o << "};\n    return T[k];\n  }\n  static __device__ constexpr FieldRec field(int f) {\n    constexpr FieldRec T[" << T.fields.size() << "] = {";
+    for (size_t f = 0; f < T.fields.size(); ++f) {
+      const FieldRec& r = T.fields[f];
+      o << (f ? ", " : "") << "{" << (int)r.w << ", " << (int)r.sh << ", " << (int)r.bits << ", " << (int)r.target << ", " << (int)r.p0 << ", " << (int)r.len << "}";
+    }
+    o << "};\n    return T[f];\n  }\n";
+    // per-lane views of the same layout for the single-tile drain
+    const int n_lane = 32 * pr;
+    std::vector<uint32_t> lcfg((size_t)n_lane, 0u), dcfg(32, 0u);
+    for (const FieldRec& r : T.fields) {
+      if (r.target == 3) {
+        if (r.p0 < 32) dcfg[r.p0] = (uint32_t)r.w | ((uint32_t)r.sh << 5) | ((r.bits == 10 ? 1u : 0u) << 10) | (1u << 11);
+        continue;
+      }
+      for (int p2 = r.p0; p2 < r.p0 + r.len && p2 < n_lane; ++p2) {
+        if (r.target != 1) lcfg[p2] = (lcfg[p2] & ~0x3ffu) | (uint32_t)r.w | ((uint32_t)r.sh << 5);
+        if (r.target != 0) lcfg[p2] = (lcfg[p2] & ~(0x3ffu << 10)) | ((uint32_t)r.w << 10) | ((uint32_t)r.sh << 15);
+        lcfg[p2] |= 1u << 20;
+      }
+    }
+    o << "  static __device__ uint32_t lane_cfg(int i) {\n    constexpr uint32_t T[" << n_lane << "] = {";
+    for (int i = 0; i < n_lane; ++i) o << (i ? ", " : "") << lcfg[i] << "u";
+    o << "};\n    return T[i];\n  }\n  static __device__ uint32_t daily_cfg(int i) {\n    constexpr uint32_t T[32] = {";
+    for (int i = 0; i < 32; ++i) o << (i ? ", " : "") << dcfg[i] << "u";
+    o << "};\n    return T[i];\n  }\n";
+  } else {
+    o << "  static __device__ constexpr LevelTally tally(int) { return LevelTally{}; }\n"
+      << "  static __device__ constexpr FieldRec field(int) { return FieldRec{}; }\n"
+      << "  static __device__ constexpr uint32_t lane_cfg(int) { return 0u; }\n"
+      << "  static __device__ constexpr uint32_t daily_cfg(int) { return 0u; }\n";
+  }
+  o << "};\n}  // namespace stryke\n"
+    << "extern \"C\" __global__ void __launch_bounds__(256, " << spec_min_blocks() << ") passage_spec(const stryke::KParams P, const stryke::FastTables FT,\n"
+    << "    const uint2* __restrict__ g_nodes, const int stride, const int n_species_staged) {\n"
+    << "  stryke::passage_fast_body<stryke::SpecJit, " << pr << ", " << (baro ? "true" : "false") << ">(P, FT, g_nodes, stride, n_species_staged);\n}\n";
+  return o.str();
+}
+
+// nullptr + message on failure
+static const std::vector<char>* compile(const std::string& src, std::string* err, bool fresh) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  auto it = g_cubins.find(src);
+  if (it != g_cubins.end() && !fresh) return &it->second;
+  Api& a = api();
+  if (!a.ok) { *err = "libnvrtc not available"; return nullptr; }
+  std::string fast, common;
+  if (g_source_dir.empty()) {      // default: csrc/ next to the shared library this code was loaded from
+    Dl_info info;
+    if (dladdr((const void*)&stryke_b200_abi_version, &info) && info.dli_fname) {
+      std::string so(info.dli_fname);
+      const size_t slash = so.rfind('/');
+      g_source_dir = (slash == std::string::npos ? std::string(".") : so.substr(0, slash)) + "/csrc";
+    }
+  }
+  if (g_source_dir.empty() || !read_file(g_source_dir + "/passage_fast.cuh", &fast) || !read_file(g_source_dir + "/passage_common.cuh", &common)) {
+    *err = "kernel sources not found (stryke_b200_set_source_dir)";
+    return nullptr;
+  }
+  // on-disk cache of compiled specialisations: key = FNV-1a of (generated source, both headers, target)
+  uint64_t h = 1469598103934665603ull;
+  const std::string* parts[3] = {&src, &fast, &common};
+  for (const std::string* part : parts)
+    for (unsigned char ch : *part) { h ^= ch; h *= 1099511628211ull; }
+  std::string dir;
+  if (const char* e = getenv("STRYKE_B200_CACHE_DIR")) dir = e;
+  else dir = g_source_dir + "/../.jit_cache";      // inside the package directory
+  char name[64];
+  snprintf(name, sizeof name, "/sm_100a_%016llx.cubin", (unsigned long long)h);
+  const std::string path = dir + name;
+  if (!fresh) {
+    std::ifstream f(path, std::ios::binary);
+    if (f) {
+      std::vector<char> bin((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+      if (bin.size() > 1024) return &(g_cubins[src] = std::move(bin));
+    }
+  }
+  const char* headers[2] = {fast.c_str(), common.c_str()};
+  const char* names[2] = {"passage_fast.cuh", "passage_common.cuh"};
+  nvrtcProgram prog = nullptr;
+  if (a.create(&prog, src.c_str(), "passage_spec.cu", 2, headers, names) != 0) { *err = "nvrtcCreateProgram failed"; return nullptr; }
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo"};
+  const int rc = a.compile(prog, 3, opts);
+  if (rc != 0) {
+    size_t n = 0;
+    a.log_size(prog, &n);
+    std::string log(n, '\0');
+    if (n) a.log(prog, &log[0]);
+    a.destroy(&prog);
+    *err = "NVRTC compile failed: " + log.substr(0, 2000);
+    return nullptr;
+  }
+  size_t n = 0;
+  a.cubin_size(prog, &n);
+  std::vector<char> bin(n);
+  a.cubin(prog, bin.data());
+  a.destroy(&prog);
+  if (system(("mkdir -p '" + dir + "' 2>/dev/null").c_str()) == 0) {      // best effort; a read-only home is fine
+    const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+    std::ofstream f(tmp, std::ios::binary);
+    if (f && f.write(bin.data(), (std::streamsize)bin.size())) { f.close(); rename(tmp.c_str(), path.c_str()); }
+  }
+  return &(g_cubins[src] = std::move(bin));
+}
+
+static int load(int device, const std::string& src, const std::vector<char>& bin, cudaKernel_t* kern, std::string* err) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  auto key = std::make_pair(device, src);
+  auto it = g_loaded.find(key);
+  if (it == g_loaded.end()) {
+    Loaded l{};
+    cudaError_t e = cudaLibraryLoadData(&l.lib, bin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&l.kern, l.lib, "passage_spec");
+    if (e != cudaSuccess) { *err = std::string("loading the specialised kernel failed: ") + cudaGetErrorString(e); cudaGetLastError(); return 1; }
+    it = g_loaded.emplace(key, l).first;
+  }
+  *kern = it->second.kern;
+  return 0;
+}
+}  // namespace jit
