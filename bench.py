@@ -32,7 +32,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 # "Roofline"): what the specialised kernel executes per fish (ncu, profiles/r01_inst_per_fish.json).  SURVEY.md §8d
 # estimated 500 (C2) / 1900 (C5) assuming 4 Philox blocks and atan/sin/cos per fish; the kernels need fewer blocks and no
 # trigonometry (C2: ONE block), so the survey figure would put the fraction above 1.
-ALGO_LANE_OPS = {"c2": 187.0, "c3": 187.0, "c5": 777.0}
+ALGO_LANE_OPS = {"c2": 187.0, "c3": 187.0, "c5": 777.0, "c4": 264.0}
 
 
 def workload_project(name, n_fish, iterations, days):
@@ -43,6 +43,8 @@ def workload_project(name, n_fish, iterations, days):
         return fixtures.c5_cascade(n_fish=n_fish, iterations=iterations, days=days, curr_Q=9000.0)
     if name == "c3":
         return fixtures.c3_population(n_species=20, iterations=iterations, days=days, curr_Q=9000.0)
+    if name == "c4":
+        return fixtures.c4_barotrauma(n_fish=n_fish, iterations=iterations, days=days, curr_Q=9000.0)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -119,6 +121,7 @@ class ClockSampler(threading.Thread):
 
 
 CPU_SAMPLE = {"c2": dict(n_fish=200_000, iterations=24, days=1), "c5": dict(n_fish=100_000, iterations=12, days=1),
+              "c4": dict(n_fish=200_000, iterations=24, days=1),
               "c3": dict(n_fish=0, iterations=2, days=40)}    # per worker process and per step
 
 
@@ -155,7 +158,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--fish", type=int, default=None, help="fish per cell (fixed-count workloads)")
     ap.add_argument("--iterations", type=int, default=None)
     ap.add_argument("--days", type=int, default=None)
@@ -168,7 +171,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    defaults = {"c2": (1_000_000, 1000, 1), "c5": (250_000, 400, 1), "c3": (0, 1000, 365)}[args.workload]
+    defaults = {"c2": (1_000_000, 1000, 1), "c5": (250_000, 400, 1), "c3": (0, 1000, 365), "c4": (1_000_000, 500, 1)}[args.workload]
     n_fish = args.fish if args.fish is not None else defaults[0]
     iterations = args.iterations if args.iterations is not None else defaults[1]
     days = args.days if args.days is not None else defaults[2]
@@ -176,6 +179,8 @@ def main():
     workload_desc = {"c2": f"C2: 3-unit Kaplan+Kaplan+Francis facility, bypass+spill, 9 nodes, 6 moves; {n_fish} fish/iteration x "
                            f"{iterations} iterations x {days} day(s) per GPU",
                      "c5": f"C5: 5-dam cascade, 40 nodes, 22 moves; {n_fish} fish x {iterations} iterations x {days} day(s) per GPU",
+                     "c4": f"C4: 6-unit propeller / Francis station with the Pflugrath barotrauma response, 11 nodes, 6 moves; {n_fish} "
+                           f"fish x {iterations} iterations x {days} day(s) per GPU",
                      "c3": f"C3: population mode, 20 species x {days} days x {iterations} iterations per GPU, EPRI-fitted entrainment"}[args.workload]
 
     # ---------------------------------------------------------------------------------------------------------
