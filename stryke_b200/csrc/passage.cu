@@ -244,7 +244,6 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
     // dense word slots in consumption order (slot 0 is the length word)
     m.slot_rc = m.slot_depth = m.slot_dice = m.slot_route = 0;
     if (need & (NEED_RR | NEED_CAUSE)) m.slot_rc = (uint16_t)next_slot++;
-    if (need & NEED_DEPTH) m.slot_depth = (uint16_t)next_slot++;
     if (need & NEED_DICE) m.slot_dice = (uint16_t)next_slot++;
     if (need & NEED_ROUTE) m.slot_route = (uint16_t)next_slot++;
     int md = 0;

@@ -97,8 +97,8 @@ enum : uint8_t { NEED_DICE = 1, NEED_RR = 2, NEED_DEPTH = 4, NEED_CAUSE = 8, NEE
 
 // Native-RNG word budget.  A fish consumes Philox words in a fixed order — word 0: length (Box-Muller radius from the high
 // 16 bits, angle from the low 16 bits); then per move, only where the level can need them (NEED_*): one word for the
-// runner position r/R (high 16 bits) and the mortality-cause roll (low 16 bits), one for the barotrauma depth, one for
-// the survival dice, one for the routing draw (23 bits each).  Word slot s lives in Philox block s >> 2 at position
+// runner position r/R (high 16 bits) and the mortality-cause roll (low 16 bits), one for the survival dice, one for the
+// routing draw (23 bits each); the barotrauma depth draw is made of spare bits of the first two (u13_depth below).  Word slot s lives in Philox block s >> 2 at position
 // s & 3; the slots are assigned densely by the host, so the C2 facility needs 4 words = ONE block per fish.
 struct __align__(4) MoveRec {   // 16 bytes
   uint8_t lex;                  // rank of "state_k" in lexicographic column order (stryke.py:3272)
@@ -108,7 +108,7 @@ struct __align__(4) MoveRec {   // 16 bytes
   uint16_t slot_route;          // word slot of the routing draw
   uint8_t max_deg;              // largest out-degree among the nodes of this level
   uint8_t pad;                  // throughput kernel: node of the level's first pair
-  uint16_t slot_depth;          // word slot of the barotrauma depth draw
+  uint16_t slot_depth;          // unused (the depth draw takes spare bits of the r/R + cause and dice words)
   uint16_t slot_dice;           // word slot of the survival dice
 };
 
@@ -184,6 +184,25 @@ template <> __device__ __forceinline__ float u16lo_co<float>(uint32_t w) { retur
 template <> __device__ __forceinline__ double u16hi_co<double>(uint32_t w) { return (double)(w >> 16) * (1.0 / 65536.0); }
 template <> __device__ __forceinline__ double u16hi_oc<double>(uint32_t w) { return 1.0 - (double)(w >> 16) * (1.0 / 65536.0); }
 template <> __device__ __forceinline__ double u16lo_co<double>(uint32_t w) { return (double)(w & 0xffffu) * (1.0 / 65536.0); }
+
+// Barotrauma levels take no word of their own for the depth draw: r/R then uses the top 12 bits of the r/R + cause word,
+// and the depth uniform is built from 13 otherwise unused bits — bits [19:16] of that word and the 9 low bits of the dice
+// word (the dice uniform reads bits [31:9]).  Multiples of 2^-12 / 2^-13: identical in fp32 and fp64.
+template <typename Real> __device__ __forceinline__ Real u12hi_co(uint32_t w);
+template <typename Real> __device__ __forceinline__ Real u13_depth(uint32_t w_rc, uint32_t w_dice);
+template <> __device__ __forceinline__ float u12hi_co<float>(uint32_t w) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(w >> 9), "r"(0x007ff800u), "r"(0x3f800000u));
+  return __uint_as_float(r) - 1.0f;
+}
+template <> __device__ __forceinline__ double u12hi_co<double>(uint32_t w) { return (double)(w >> 20) * (1.0 / 4096.0); }
+__device__ __forceinline__ uint32_t depth_bits(uint32_t w_rc, uint32_t w_dice) { return ((w_rc >> 7) & 0x1e00u) | (w_dice & 0x1ffu); }
+template <> __device__ __forceinline__ float u13_depth<float>(uint32_t w_rc, uint32_t w_dice) {
+  return __uint_as_float((depth_bits(w_rc, w_dice) << 10) | 0x3f800000u) - 1.0f;
+}
+template <> __device__ __forceinline__ double u13_depth<double>(uint32_t w_rc, uint32_t w_dice) {
+  return (double)depth_bits(w_rc, w_dice) * (1.0 / 8192.0);
+}
 
 __device__ __forceinline__ float std_normal(float u1_oc, float u2_co) {   // Box-Muller: MUFU lg2, sqrt, cos
   return sqrt_approx(-1.3862943611f * lg2_approx(u1_oc)) * cos_2pi(u2_co);   // -2 ln u = -2 ln2 lg2 u

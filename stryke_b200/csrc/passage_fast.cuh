@@ -380,11 +380,14 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
       const int kind = pk & 7;
       const bool prev_alive = alive;
       float rate = alive ? __uint_as_float(nd.x) : 0.f;
+      uint32_t w_dice = 0;
       if (mv.need & NEED_CAUSE) {                        // this level has turbine nodes (uniform)
         const uint32_t w_rc = word(mv.slot_rc);          // r/R in the high half, cause roll in the low half
-        const float u_rr = u16hi_co<float>(w_rc);
         const float u_cau = u16lo_co<float>(w_rc);
-        const float u_dep = BARO ? u_co<float>(word(mv.slot_depth)) : 0.f;
+        // barotrauma: 12-bit r/R, depth draw from spare bits of this word and of the dice word (passage_common.cuh)
+        const float u_rr = BARO ? u12hi_co<float>(w_rc) : u16hi_co<float>(w_rc);
+        if (BARO) w_dice = word(mv.slot_dice);
+        const float u_dep = BARO ? u13_depth<float>(w_rc, w_dice) : 0.f;
         const bool turb = alive && kind != STRYKE_KIND_APRIORI;
         const int unit = turb ? (int)((pk >> 4) & 0x7f) : 0;
         const float4 us = s_ustatic[unit];
@@ -411,7 +414,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         cz += turb ? code : 0u;
       }
       bool surv;
-      if (mv.need & NEED_DICE) surv = alive && (u_oc<float>(word(mv.slot_dice)) <= rate);
+      if (mv.need & NEED_DICE) surv = alive && (u_oc<float>((BARO && (mv.need & NEED_CAUSE)) ? w_dice : word(mv.slot_dice)) <= rate);
       else surv = alive;      // no dice <=> every node of the level is a-priori with survival >= 1 (host rule): u <= rate always
 
       // ---- (6) State_Daily: lane p owns pair p ---------------------------------------------------------------------

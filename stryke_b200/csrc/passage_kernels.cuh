@@ -411,13 +411,14 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
       const bool prev_alive = alive;
       float rate32 = 0.f;
       // word slots of this move (MoveRec): r/R + cause share one word, depth, dice, route one each
-      const int s_dep = mv.slot_depth, s_dice = mv.slot_dice;
+      const int s_dice = mv.slot_dice;
       const int s_rt = mv.slot_route;
-      uint32_t w_rc = 0, w_dep = 0;
+      uint32_t w_rc = 0, w_dice = 0;
       if (!INJECT) {   // warp-uniform draws for this move (refill points are identical for every lane)
         if (mv.need & (NEED_RR | NEED_CAUSE)) w_rc = rng.word(mv.slot_rc);
-        if (mv.need & NEED_DEPTH) w_dep = rng.word(s_dep);
+        if (mv.need & NEED_DICE) w_dice = rng.word(s_dice);
       }
+      const bool with_depth = (mv.need & NEED_DEPTH) != 0;     // barotrauma level: 12-bit r/R, depth from spare bits
       Real strike_t = (Real)NAN, baro_t = (Real)NAN;
       if (alive) {
         if (nd.kind == STRYKE_KIND_APRIORI) {
@@ -433,8 +434,8 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
             Real rR = (Real)0.75;
             if (nd.kind == STRYKE_KIND_KAPLAN) {
               if (INJECT) rR = (Real)add_(0.3, mul_(sub_(1.0, 0.3), P.inj.rR[(int64_t)k * NF + gi]));
-              else if (sizeof(Real) == 8) rR = (Real)(0.3 + 0.7 * (double)u16hi_co<Real>(w_rc));
-              else rR = (Real)fmaf(0.7f, (float)u16hi_co<Real>(w_rc), 0.3f);
+              else if (sizeof(Real) == 8) rR = (Real)(0.3 + 0.7 * (double)(with_depth ? u12hi_co<Real>(w_rc) : u16hi_co<Real>(w_rc)));
+              else rR = (Real)fmaf(0.7f, (float)(with_depth ? u12hi_co<Real>(w_rc) : u16hi_co<Real>(w_rc)), 0.3f);
             }
             if (sizeof(Real) == 8) strike = (Real)strike_surv64(nd.kind, (const double*)uc, (double)L, (double)rR);
             else strike = (Real)strike_surv32(nd.kind, (const float*)uc, (float)L, (float)rR);
@@ -442,10 +443,10 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
             if (P.barotrauma) {
               if (sizeof(Real) == 8) {
                 const double fb = (double)us[2], lo = mul_(fb, (double)sp_d1), hi = mul_(fb, (double)sp_d2);
-                const double ud = INJECT ? P.inj.depth[(int64_t)k * NF + gi] : (double)u_co<Real>(w_dep);
+                const double ud = INJECT ? P.inj.depth[(int64_t)k * NF + gi] : (double)u13_depth<Real>(w_rc, w_dice);
                 baro = (Real)baro_surv64(add_(lo, mul_(sub_(hi, lo), ud)), (double)us[3], (double)sp_b0, (double)sp_b1);
               } else {
-                const float ud = INJECT ? (float)P.inj.depth[(int64_t)k * NF + gi] : (float)u_co<Real>(w_dep);
+                const float ud = INJECT ? (float)P.inj.depth[(int64_t)k * NF + gi] : (float)u13_depth<Real>(w_rc, w_dice);
                 const float depth = (float)us[2] * fmaf((float)sp_d2 - (float)sp_d1, ud, (float)sp_d1);
                 baro = (Real)baro_surv32(depth, (float)us[4], (float)us[5], (float)sp_b0 * 1.44269504f, (float)sp_b1);
               }
@@ -502,8 +503,7 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
       if (INJECT) {
         surv = active && (P.inj.dice[(int64_t)k * NF + gi] <= (double)rate32);
       } else if (mv.need & NEED_DICE) {
-        const uint32_t wd = rng.word(s_dice);
-        surv = alive && (u_oc<Real>(wd) <= (Real)rate32);
+        surv = alive && (u_oc<Real>(w_dice) <= (Real)rate32);
       } else {
         surv = alive && rate32 >= 1.0f;    // every node of this level has survival 1.0: no draw needed
       }
