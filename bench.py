@@ -32,7 +32,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 # "Roofline"): what the specialised kernel executes per fish (ncu, profiles/r01_inst_per_fish.json).  SURVEY.md §8d
 # estimated 500 (C2) / 1900 (C5) assuming 4 Philox blocks and atan/sin/cos per fish; the kernels need fewer blocks and no
 # trigonometry (C2: ONE block), so the survey figure would put the fraction above 1.
-ALGO_LANE_OPS = {"c2": 187.0, "c3": 187.0, "c5": 777.0, "c4": 264.0}
+ALGO_LANE_OPS = {"c2": 187.0, "c3": 187.0, "c5": 777.0, "c4": 225.0}
 
 
 def workload_project(name, n_fish, iterations, days):
