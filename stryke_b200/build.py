@@ -24,7 +24,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", OUT, SRC] + (["-Xptxas", "-v"] if verbose else [])
+    extra = ["-DSTRYKE_BOUNDS_CHECK"] if os.environ.get("STRYKE_B200_BOUNDS_CHECK") == "1" else []   # debug build: checked table indices
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", OUT, SRC] + (["-Xptxas", "-v"] if verbose else [])
     subprocess.run(cmd, check=True)
     return OUT
 

@@ -550,6 +550,8 @@ int stryke_b200_plan_status(StrykePlan* pl, void* stream, int64_t* n_fish_total)
   if (pl->n_cells > 0) CK(cudaMemcpyAsync(&nf, pl->fish_off.as<int64_t>() + pl->n_cells, sizeof(nf), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   if (n_fish_total) *n_fish_total = nf;
+  if ((err >> 62) == 3ull)      // only the bounds-check build (STRYKE_BOUNDS_CHECK) sets both top bits
+    return fail(STRYKE_E_CUDA, "internal bounds check failed in a passage kernel (site " + std::to_string((err >> 48) & 0x3fff) + ")");
   if (err & 0x8000000000000000ull)
     return fail(STRYKE_E_ARG, "Computed non-finite or negative population size in cell " + std::to_string(err & 0x7FFFFFFFFFFFFFFFull));
   if (err)

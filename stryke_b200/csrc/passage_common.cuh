@@ -138,6 +138,18 @@ struct KParams {
   int chunk_tiles;                    // tiles per chunk
 };
 
+// Self-made bounds checks (compute-sanitizer is not available on the test pool): with -DSTRYKE_BOUNDS_CHECK every index
+// into the staged tables is verified before use; a violation ORs bits 63+62 and a site code into the plan's error word
+// (KParams::work_counter[-1]), which plan_status turns into an error.  Compiled out otherwise.
+#ifdef STRYKE_BOUNDS_CHECK
+#define STRYKE_BCHK(P, cond, site)                                                                              \
+  do {                                                                                                          \
+    if (!(cond)) atomicOr((P).work_counter - 1, (3ull << 62) | ((unsigned long long)(site) << 48));             \
+  } while (0)
+#else
+#define STRYKE_BCHK(P, cond, site) do { } while (0)
+#endif
+
 constexpr double P_ATM = 101325.0;    // scipy.constants.atm (stryke.py:1472)
 constexpr double G_SI = 9.80665;      // scipy.constants.g   (stryke.py:1471)
 constexpr double RHO = 998.2;         // stryke.py:1473

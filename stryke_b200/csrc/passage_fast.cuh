@@ -278,6 +278,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         flush(cur_cell);
       }
       cur_cell = c;
+      STRYKE_BCHK(P, c >= 0 && c < P.n_cells, 6);
       n_c = P.cell_n[c];
       const uint64_t cid = P.cell_id[c];
       cid_lo = (uint32_t)cid; cid_hi = (uint32_t)(cid >> 32);
@@ -325,6 +326,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
       }
     }
     const int fish = fish_base + lane;
+    STRYKE_BCHK(P, fish_base >= 0 && (lane != 0 || fish < n_c), 7);     // a tile always holds at least one fish of its cell
     const bool active = fish < n_c;
 
     // ---- Philox: counter (fish, cell id, block), key = seed (constant bank) -------------------------------------
@@ -369,12 +371,14 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
 #pragma unroll
           for (int r = 0; r < PR; ++r) add_if_lane(acc_cnt[r], acc_suc[r], mv.level_begin, lane_r[r], pc, pc);
         }
+        STRYKE_BCHK(P, (int)mv.pad < n_nodes, 1);
         if (k < n_moves - 1) loc = alive ? s_dst[(int)mv.pad * stride] : loc;
         continue;
       }
       // a level with ONE reachable node: every live fish is there, so its index is a compile-time constant in the
       // specialised instantiation (table offsets fold to immediates; dead lanes read a valid record they never use)
       const int at = (TP::kStatic && mv.level_end - mv.level_begin == 1) ? TP::pair_node(FT, mv.level_begin) : loc;
+      STRYKE_BCHK(P, at >= 0 && at < n_nodes, 2);
       const uint2 nd = s_nodes[at];
       const uint32_t pk = nd.y;
       const int kind = pk & 7;
@@ -390,6 +394,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         const float u_dep = BARO ? u13_depth<float>(w_rc, w_dice) : 0.f;
         const bool turb = alive && kind != STRYKE_KIND_APRIORI;
         const int unit = turb ? (int)((pk >> 4) & 0x7f) : 0;
+        STRYKE_BCHK(P, unit >= 0 && unit < (n_units > 0 ? n_units : 1), 3);
         const float4 us = s_ustatic[unit];
         const float4 uc = s_ucoef[unit];
         const bool blocked = blocked_w > us.x;                               // stryke.py:1419
@@ -469,7 +474,9 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
             j -= le_mask(q.x, u) + le_mask(q.y, u) + le_mask(q.z, u) + le_mask(q.w, u);
           }
         }
+        STRYKE_BCHK(P, j >= 0 && j < stride, 4);
         loc = surv ? s_dst[at * stride + j] : loc;
+        STRYKE_BCHK(P, loc >= 0 && loc < n_nodes, 5);
       }
       alive = surv;
     }

@@ -407,6 +407,7 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
 
     for (int k = 0; k < P.n_moves; ++k) {
       const MoveRec mv = s_moves[k];
+      STRYKE_BCHK(P, loc >= 0 && loc < P.n_nodes, 11);
       const NodeRec nd = s_nodes[loc];
       const bool prev_alive = alive;
       float rate32 = 0.f;
@@ -541,6 +542,7 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
             const Real* cdf = s_cdf + nd.edge_off;
             for (int e = 0; e < nd.deg - 1; ++e) j += (cdf[e] <= u) ? 1 : 0;
           }
+          STRYKE_BCHK(P, j >= 0 && j < (int)nd.deg && nd.edge_off + j < P.n_edges, 12);
           loc = s_edge_dst[nd.edge_off + j];
         }
       }

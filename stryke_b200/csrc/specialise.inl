@@ -145,6 +145,9 @@ static std::string generate(const std::vector<MoveRec>& moves, const std::vector
   std::ostringstream o;
   const int M = (int)moves.size(), P = (int)pairs.size();
   o << "#define STRYKE_NVRTC 1\n";
+#ifdef STRYKE_BOUNDS_CHECK
+  o << "#define STRYKE_BOUNDS_CHECK 1\n";
+#endif
   if (const char* defs = getenv("STRYKE_B200_JIT_DEFINES")) {      // experiment switches: "A=1,B" -> #define A 1 / #define B
     std::string d(defs), tok;
     std::stringstream ss(d);
