@@ -130,9 +130,11 @@ def run_cells(fac, days, species, cell_day, cell_species, cell_id, *, device=0, 
     n = int(cl.n_cells)
     if out is not None:      # caller-owned (e.g. pinned) host buffers
         out_n, out_d, out_s = out
-        assert out_n.dtype == np.int32 and out_n.shape == (n,) and out_n.flags["C_CONTIGUOUS"]
-        assert out_d.dtype == np.uint32 and out_d.shape == (n, _abi.DAILY_W) and out_d.flags["C_CONTIGUOUS"]
-        assert out_s.dtype == np.uint32 and out_s.shape == (n, fac.n_pairs, 2) and out_s.flags["C_CONTIGUOUS"]
+        for name, a, dt, shape in (("cell_n", out_n, np.int32, (n,)), ("daily", out_d, np.uint32, (n, _abi.DAILY_W)),
+                                   ("state_daily", out_s, np.uint32, (n, fac.n_pairs, 2))):
+            if a.dtype != dt or a.shape != shape or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"out buffer {name}: need C-contiguous {np.dtype(dt).name}{list(shape)}, "
+                                 f"got {a.dtype.name}{list(a.shape)}")
     else:
         out_n = np.zeros(n, np.int32)
         out_d = np.zeros((n, _abi.DAILY_W), np.uint32)
