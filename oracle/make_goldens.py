@@ -44,8 +44,13 @@ CASES = {
 }
 
 
+PEAKING = {   # written to tests/golden/peaking/ (own test: the hours of every cell are injected too)
+    "peaking_c2": ("peaking_facility", dict(n_fish=150, iterations=3, days=5), 31, {}),
+}
+
+
 def build_case(name):
-    fn, kw, seed, fam = CASES[name]
+    fn, kw, seed, fam = (CASES.get(name) or PEAKING[name])
     prj = getattr(fixtures, fn)(**kw)
     sim, store, rec = harness.run_reference(prj, seed=seed)
     model = O.Model.from_project(prj)
@@ -57,9 +62,19 @@ def build_case(name):
     M = len(model.moves)
     out = {}
     cells_meta = []
-    assert len(rec.cells) == len(daily)
+    # peaking plants: a (species, iteration, day) whose units all sat idle is skipped before anything is written
+    # (stryke.py:3025): the cell is kept in the list (its hours are part of the recording) but has no Daily row
+    idle = [c["tot_hours"] == 0 and not c["moves"] and c["presence"] is None for c in rec.cells]
+    assert len(rec.cells) - sum(idle) == len(daily)
+    di = -1
+    last = None
     for ci, cell in enumerate(rec.cells):
-        drow = daily.iloc[ci]
+        if idle[ci]:
+            cells_meta.append(dict(last or {}, idle=True, curr_Q=cell["curr_Q"], presence=None, tot_hours=0.0, hours=cell["hours"],
+                                   count_draw=None, n=0, iteration=None, day=None))
+            continue
+        di += 1
+        drow = daily.iloc[di]
         spc, scen = drow["species"].strip(), drow["scenario"].strip()
         prow = pops[(spc, scen)]
         p = f"c{ci}_"
@@ -67,6 +82,7 @@ def build_case(name):
                   curr_Q=cell["curr_Q"], presence=cell["presence"], tot_hours=cell["tot_hours"], hours=cell["hours"],
                   count_draw=replay.cell_count_draw(cell), n=(cell["moves"][0]["n"] if cell["moves"] else 0))
         cells_meta.append(cm)
+        last = dict(scenario=scen, species=spc)
         out[p + "daily"] = drow.iloc[6:].to_numpy(dtype=float).astype(np.int64)
         if not cell["moves"]:
             continue
@@ -93,8 +109,9 @@ def build_case(name):
                 route_flows=frame("Route_Flows"), unit_hours=frame("Unit_Hours"), nodes=model.nodes, moves=M,
                 numpy=np.__version__, reference="knebiolo/stryke @ /root/reference (unmodified, oracle/harness.py)")
     out["meta"] = np.array(json.dumps(meta))
-    os.makedirs(GOLDEN_DIR, exist_ok=True)
-    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    out_dir = os.path.join(GOLDEN_DIR, "peaking") if name in PEAKING else GOLDEN_DIR
+    os.makedirs(out_dir, exist_ok=True)
+    path = os.path.join(out_dir, name + ".npz")
     np.savez_compressed(path, **out)
     return path, len(rec.cells)
 

@@ -231,7 +231,12 @@ class RunPlan:
         not the reference's draw order)."""
         from scipy.stats import lognorm
         sim = self.sim
+        given = getattr(sim, "_injected_hours", None)      # replay of a recorded run: {(scenario, species): (keys, H[I, D, units])}
         for gi, g in enumerate(self.groups):
+            if given is not None:
+                keys, H = given[(str(g.scenario), str(g.species))]
+                self.cell_hours[gi] = (list(keys), np.ascontiguousarray(np.transpose(np.asarray(H, dtype=float), (1, 0, 2))))
+                continue
             ops = sim.operating_scenarios_df[sim.operating_scenarios_df.Scenario == g.scenario].reset_index(drop=True)
             keys, cols = [], []
             D, I = g.n_active_days, g.iterations

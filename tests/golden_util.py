@@ -11,8 +11,8 @@ CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
 
 
 class Golden:
-    def __init__(self, name):
-        self.z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    def __init__(self, name, subdir=""):
+        self.z = np.load(os.path.join(GOLDEN_DIR, subdir, name + ".npz"))
         self.meta = json.loads(str(self.z["meta"]))
         self.prj = getattr(fixtures, self.meta["fixture"])(**self.meta["kwargs"])
         self.model = O.Model.from_project(self.prj)

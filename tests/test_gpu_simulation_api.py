@@ -212,3 +212,44 @@ def test_per_fish_table_in_population_mode_uses_a_second_pass(tmp_path, monkeypa
         states = t[[c for c in t.columns if c.startswith("state_")]].to_numpy(dtype=str)
         ent = (np.char.find(states, "U") >= 0).any(axis=1)
         assert int(ent.sum()) == int(d["num_entrained"].sum())
+
+
+def test_peaking_plant_replays_the_reference_run(tmp_path):
+    """A peaking / pumped-storage style plant (per-unit not-operating coin + lognormal hours, stryke.py:2405-2431) recorded
+    from the reference: with the recorded hours and uniforms injected, run() writes the reference's Daily, State_Daily
+    and Unit_Hours rows — cells whose units all sat idle produce no rows at all (stryke.py:3025)."""
+    g = Golden("peaking_c2", subdir="peaking")
+    sim = fresh_sim(g.prj, tmp_path, "peaking")
+    sim.precision = 64
+    live = [c for c in g.cells if not c.get("idle")]
+    assert len(live) < len(g.cells)                     # the recording does contain idle cells
+    prow = g.prj["population"][0]
+    I, D = int(prow["Iterations"]), len(g.prj["hydrograph"])
+    keys = list(g.cells[0]["hours"].keys())
+    H = np.array([[c["hours"][k] for k in keys] for c in g.cells]).reshape(I, D, len(keys))      # reference order: iteration, day
+    sim._injected_hours = {(prow["Scenario"], prow["Species"]): (keys, H)}
+    with contextlib.redirect_stdout(io.StringIO()):
+        plan = RunPlan(sim)
+    inj, off, ref_idx = G.golden_injected(g, plan)
+    sim.graph = None
+    with contextlib.redirect_stdout(io.StringIO()):
+        runner.run_simulation(sim, injected=inj)
+    with open_store(sim.hdf_path, mode="r") as st:
+        daily, sd, uh = st["Daily"], st["State_Daily"], st["Unit_Hours"]
+    assert len(daily) == len(live)
+    want = np.stack([g.ref(ci, "daily") for ci, c in enumerate(g.cells) if not c.get("idle")])
+    assert np.array_equal(daily[DAILY_COLS].to_numpy(dtype=np.int64), want)
+    assert list(daily["iteration"]) == [c["iteration"] for c in live] and [str(d) for d in daily["day"]] == [c["day"] for c in live]
+    want_rows = []
+    for ci, cm in enumerate(g.cells):
+        if cm.get("idle") or cm["n"] == 0:
+            continue
+        for m, s, v in zip(g.ref(ci, "sd_move"), g.ref(ci, "sd_state"), g.ref(ci, "sd_vals")):
+            want_rows.append((cm["iteration"], cm["day"], int(m), g.model.nodes[int(s)], float(v[0]), float(v[1])))
+    got_rows = [(int(r.iteration), str(r.day), int(r.move), r.state, float(r.successes), float(r["count"])) for _, r in sd.iterrows()]
+    assert got_rows == want_rows
+    key = lambda d: (int(d["iteration"]), str(pd.to_datetime(d["day"])), d["route"])
+    want_uh = {key(d): (d["hours"], d["discharge_cfs"]) for d in g.meta["unit_hours"]}
+    got_uh = {key(d): (d["hours"], d["discharge_cfs"]) for d in uh.to_dict("records")}
+    assert set(got_uh) == set(want_uh)
+    assert all(np.allclose(got_uh[k], want_uh[k], rtol=1e-9, atol=1e-9) for k in want_uh)
