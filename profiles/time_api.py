@@ -31,3 +31,5 @@ with contextlib.redirect_stdout(io.StringIO()):
 pr.disable()
 print("summary() %.2f s" % (time.perf_counter() - t1))
 pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
+import resource
+print("peak RSS %.2f GB" % (resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1048576.0))

@@ -107,7 +107,7 @@ struct StrykePlan {
   int64_t n_cells = 0;
   int nb_scan = 0;
   DevBuf nodes, edge_dst, moves, pair_node, ustatic, edge_cdf, node_stay, unit_coef, day_Q, species, cell_day,
-      cell_species, cell_id, tile_off, fish_off, part, err;
+      cell_species, cell_id, tile_off, fish_off, part, err, blk_S;
   DevBuf i_fish_off, i_presence, i_count, i_z, i_dice, i_rR, i_depth, i_cause, i_route, i_grR, i_gdepth, i_gcause;
   DevBuf t_len32, t_len64, t_state, t_rate, t_surv, t_strike, t_baro;
   DevBuf fast_nodes;
@@ -115,6 +115,7 @@ struct StrykePlan {
   size_t fast_smem_bytes = 0;
   int fast_stride = 1;
   bool use_fast = false;
+  bool pool = false;          // remainders of the cells pooled into shared tiles (pool_kernel; specialised kernel only)
   cudaKernel_t jit_kernel = nullptr;
   std::string kernel_name = "passage_kernel (general)";
   int64_t trace_fish = 0;
@@ -132,7 +133,7 @@ struct TallyPlan {
 static TallyPlan plan_tally(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int n_nodes);
 struct Dims { int n_nodes, n_units, n_species_staged, start_node; };
 static std::string generate(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int stride, int pr, bool baro,
-                            const TallyPlan& T, const Dims& D);
+                            const TallyPlan& T, const Dims& D, bool pool);
 static const std::vector<char>* compile(const std::string& src, std::string* err, bool fresh = false);
 static int load(int device, const std::string& src, const std::vector<char>& bin, cudaKernel_t* kern, std::string* err);
 }  // namespace jit
@@ -385,23 +386,35 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
     pl->kernel_name = "passage_fast_kernel (generic tables, ahead-of-time)";
     // ---- specialise for this facility when the run is large enough to amortise a ~1-3 s compile ---------------------
     double fish_hint = 0.0;
+    bool small_cells = false;      // cells that may leave a large share of a tile idle: drawn counts, or small fixed ones
     for (int64_t i = 0; i < c->n_cells; ++i) {
       const double* sp = s->params + (size_t)c->cell_species[i] * STRYKE_SPECIES_W;
-      fish_hint += (int)sp[12] == STRYKE_ENT_FIXED ? sp[18] : 50.0;
+      const bool fixed = (int)sp[12] == STRYKE_ENT_FIXED;
+      fish_hint += fixed ? sp[18] : 50.0;
+      small_cells = small_cells || !fixed || (sp[18] < 4096.0 && ((int64_t)sp[18] & 31) != 0);
     }
+    const char* pool_env = getenv("STRYKE_B200_POOL");
+    const bool pool = tally.NW > 0 && c->n_cells >= 32 && (pool_env ? pool_env[0] == '1' : small_cells);
     const char* env = getenv("STRYKE_B200_JIT");
     const bool want = o->kernel_variant == 3 || (o->kernel_variant == 0 && !(env && env[0] == '0') &&
                                                  ((env && env[0] == '1') || fish_hint >= 2.0e7));
     if (want) {
       std::vector<MoveRec> mv(pl->fast.moves, pl->fast.moves + f->n_moves);
       const std::string src = jit::generate(mv, pnode, pl->fast_stride, pl->pr, f->barotrauma != 0, tally,
-                                                jit::Dims{f->n_nodes, f->n_units, pl->n_species_staged, f->start_node});
+                                                jit::Dims{f->n_nodes, f->n_units, pl->n_species_staged, f->start_node}, pool);
       std::string err;
       const std::vector<char>* bin = jit::compile(src, &err);
       cudaKernel_t k = nullptr;
       if (bin && jit::load(o->device, src, *bin, &k, &err) == 0) {
         pl->jit_kernel = k;
         pl->kernel_name = "passage_spec (tables specialised with NVRTC)";
+        if (pool) {
+          pl->pool = true;
+          pl->kernel_name = "passage_spec (tables specialised with NVRTC, pooled remainders)";
+          pl->fast_smem_bytes = (size_t)fast_smem(f->n_nodes, f->n_units, pl->fast_stride, pl->n_species_staged, tally.NW, f->n_pairs).total;
+          CK(pl->blk_S.alloc((size_t)((c->n_cells + 31) / 32) * sizeof(uint32_t)));
+          K.blk_S = pl->blk_S.as<uint32_t>();
+        }
       } else if (o->kernel_variant == 3) {
         return fail(STRYKE_E_CUDA, "kernel specialisation failed: " + err);
       }
@@ -500,9 +513,15 @@ int stryke_b200_plan_launch(StrykePlan* pl, int32_t* d_cell_n, uint32_t* d_daily
   const int cb = (int)((pl->n_cells + 255) / 256);
   if (pl->inject) count_kernel<true><<<cb, 256, 0, st>>>(K, pl->day_Q.as<double>(), d_cell_n, pl->max_daily_fish, pl->err.as<unsigned long long>());
   else count_kernel<false><<<cb, 256, 0, st>>>(K, pl->day_Q.as<double>(), d_cell_n, pl->max_daily_fish, pl->err.as<unsigned long long>());
-  scan_partial<<<pl->nb_scan, SCAN_T, 0, st>>>(d_cell_n, pl->n_cells, pl->part.as<int64_t>());
+  const uint32_t* blk_S = pl->pool ? pl->blk_S.as<uint32_t>() : nullptr;
+  if (pl->pool) {
+    const int64_t nb = (pl->n_cells + 31) / 32;
+    pool_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, st>>>(d_cell_n, K.cell_species, K.cell_day, pl->n_cells, pl->blk_S.as<uint32_t>());
+    g_launches++;
+  }
+  scan_partial<<<pl->nb_scan, SCAN_T, 0, st>>>(d_cell_n, pl->n_cells, pl->part.as<int64_t>(), blk_S);
   scan_blocks<<<1, SCAN_T, 0, st>>>(pl->part.as<int64_t>(), pl->nb_scan);
-  scan_final<<<pl->nb_scan, SCAN_T, 0, st>>>(d_cell_n, pl->n_cells, pl->part.as<int64_t>(), pl->tile_off.as<int64_t>(), pl->fish_off.as<int64_t>());
+  scan_final<<<pl->nb_scan, SCAN_T, 0, st>>>(d_cell_n, pl->n_cells, pl->part.as<int64_t>(), pl->tile_off.as<int64_t>(), pl->fish_off.as<int64_t>(), blk_S);
   g_launches += 4;
   CK(cudaGetLastError());
   if (pl->use_fast) return launch_fast_any(pl, st);
@@ -528,7 +547,8 @@ int stryke_b200_jit_selftest(void) {
     std::string err;
     const jit::TallyPlan T = jit::plan_tally(mv, pairs, 9);
     if (!T.NW) return fail(STRYKE_E_CUDA, "packed tally layout failed for the self-test facility");
-    if (!jit::compile(jit::generate(mv, pairs, 5, 1, baro != 0, T, jit::Dims{9, 3, 1, 0}), &err, /*fresh=*/true)) return fail(STRYKE_E_CUDA, err);
+    for (int pool = 0; pool < 2; ++pool)
+      if (!jit::compile(jit::generate(mv, pairs, 5, 1, baro != 0, T, jit::Dims{9, 3, 1, 0}, pool != 0), &err, /*fresh=*/true)) return fail(STRYKE_E_CUDA, err);
   }
   return STRYKE_OK;
 }

@@ -136,6 +136,7 @@ struct KParams {
   uint32_t ks[20];                    // Philox key schedule of (seed_lo, seed_hi), throughput kernels
   unsigned long long* work_counter;   // throughput kernels: next chunk of tiles to hand out (zeroed before every launch)
   int chunk_tiles;                    // tiles per chunk
+  const uint32_t* blk_S;              // pooled remainders (passage_fast.cuh): per block of 32 cells, shared tiles [0:31) | mixed [31]
 };
 
 // Self-made bounds checks (compute-sanitizer is not available on the test pool): with -DSTRYKE_BOUNDS_CHECK every index

@@ -43,21 +43,31 @@ __host__ __device__ inline uint32_t pack_node(int kind, int hasU, int unit, int 
 
 struct FastSmem {
   int nodes, ustatic, uc1, species, warp0, warp_stride, cdf, dst, ucoef, total;
+  int pool_blk, pool_ef, pool_rank, pool_seg;      // per-warp scratch of the pooled-remainder path (pool_nw > 0)
+  int pool_field;                                  // per block: where every (pair, arrivals | survivors) / Daily counter sits
 };
 // floats per row of the staged routing cdf: the stride-1 thresholds a draw is compared with, padded to whole float4s
 __host__ __device__ constexpr int cdf_row(int stride) { return stride <= 5 ? 4 : ((stride - 1 + 3) & ~3); }
-__host__ __device__ constexpr FastSmem fast_smem(int n_nodes, int n_units, int stride, int n_species_staged) {
+__host__ __device__ constexpr FastSmem fast_smem(int n_nodes, int n_units, int stride, int n_species_staged, int pool_nw = 0,
+                                                 int n_pairs = 0) {
   FastSmem L{};
   int o = 0;
   L.nodes = o; o = (o + n_nodes * 8 + 15) & ~15;
   L.ustatic = o; o = (o + n_units * 16 + 15) & ~15;
   L.uc1 = o; o = (o + n_units * 4 + 15) & ~15;
   L.species = o; o = (o + n_species_staged * SPW * 4 + 15) & ~15;
+  if (pool_nw > 0) { L.pool_field = o; o = (o + (2 * n_pairs + STRYKE_DAILY_W) * 4 + 15) & ~15; }
   L.warp0 = o;
   int w = 0;
   L.cdf = w; w = (w + n_nodes * cdf_row(stride) * 4 + 15) & ~15;
   L.ucoef = w; w = (w + n_units * 16 + 15) & ~15;
   L.dst = w; w = (w + n_nodes * stride * 4 + 15) & ~15;     // int32 entries: no sub-word register packing in the hot loop
+  if (pool_nw > 0) {
+    L.pool_blk = w; w += 32 * 16;                            // uint4 per cell of the block: n, cell id (lo, hi), remainder offset
+    L.pool_ef = w; w += 32 * 8;                              // int64 per cell: full tiles of the block before this cell
+    L.pool_rank = w; w += 32 * 4;                            // lane of the rho-th cell that has a remainder
+    L.pool_seg = w; w = (w + 32 * pool_nw * 4 + 15) & ~15;         // per cell of the block: accumulated tally words
+  }
   L.warp_stride = w;
   L.total = o + w * WARPS;
   return L;
@@ -100,6 +110,7 @@ struct RuntimeTables {
   static constexpr int M = 1, STRIDE = 1, UNROLL_K = 1, UNROLL_P = 1;
   static constexpr int N_NODES = 0, N_UNITS = 0, N_PAIRS = 0, N_SPECIES_STAGED = 0, START_NODE = 0;   // run-time (KParams)
   static constexpr int NW = 0, NF = 0, HOLD = 1, W_ES = 0, B_ES = 0, W_CAUSE = 0;   // no packed tallies: ballots per pair
+  static constexpr bool POOL = false;                 // pooled remainders need the packed tallies
   static __device__ __forceinline__ MoveRec move(const FastTables& FT, int k) { return FT.moves[k]; }
   static __device__ __forceinline__ int pair_node(const FastTables& FT, int p) { return (int)FT.pair_node[p]; }
   static __device__ __forceinline__ LevelTally tally(int) { return LevelTally{}; }
@@ -119,7 +130,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   const int n_sp = TP::kStatic ? TP::N_SPECIES_STAGED : n_species_staged;
   const int crow = cdf_row(stride);
   extern __shared__ __align__(16) unsigned char smem[];
-  const FastSmem SL = fast_smem(n_nodes, n_units, stride, n_sp);
+  const FastSmem SL = fast_smem(n_nodes, n_units, stride, n_sp, TP::POOL ? TP::NW : 0, n_pairs);
   uint2* s_nodes = reinterpret_cast<uint2*>(smem + SL.nodes);
   float4* s_ustatic = reinterpret_cast<float4*>(smem + SL.ustatic);     // rack, intake_vel, fb_depth, c0
   float* s_uc1 = reinterpret_cast<float*>(smem + SL.uc1);               // c1
@@ -145,15 +156,9 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   // Work distribution: chunks of P.chunk_tiles consecutive tiles handed out through one global counter (the first
   // chunk of every warp is its own global index, later ones come from the counter).  The SM's warp arbiter does not
   // share issue slots evenly, so equal static ranges finish unevenly and leave the SM short of warps at the end.
-  const int64_t T = P.tile_off[P.n_cells];
-  const int64_t G = (int64_t)gridDim.x * WARPS, CH = P.chunk_tiles;
-  int64_t chunk = (int64_t)blockIdx.x * WARPS + wid;
-  int64_t c = -1, c_begin = 0, c_end = 0;             // current cell and its tile range [c_begin, c_end)
   int cur_day = -1, cur_species = -1;
-  int64_t cur_cell = -1;
   float sp_ls = 0, sp_ll = 0, sp_lsc = 0, sp_lm = 0, sp_lsd = 0, sp_wr = 0, sp_uc = 0, sp_d1 = 0, sp_dd = 0, sp_b0 = 0, sp_b1 = 0;
-  int sp_mode = 0, n_c = 0;
-  uint32_t cid_lo = 0, cid_hi = 0;
+  int sp_mode = 0;
   uint32_t acc_suc[PR], acc_cnt[PR], acc_daily = 0;
   int lane_r[PR];
 #pragma unroll
@@ -242,93 +247,55 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   };
 
   const int n_moves = TP::kStatic ? TP::M : P.n_moves;
-  for (;;) {
-  const int64_t t0 = chunk * CH;
-  if (t0 >= T) break;
-  const int64_t t1 = t0 + CH < T ? t0 + CH : T;
-  {   // fetch the next chunk index now, use it after this chunk
-    unsigned long long nx = 0;
-    if (lane == 0) nx = atomicAdd(P.work_counter, 1ull);
-    chunk = G + (int64_t)__shfl_sync(0xffffffffu, nx, 0);
-  }
-  bool fresh = false;       // the tile about to be simulated is the first one this warp sees of cell c
-  if (t0 >= c_end) {        // not a continuation: last cell with tile_off[c] <= t0 (cells without fish have empty ranges)
-    int64_t lo = c < 0 ? 0 : c, hi = P.n_cells;
-    while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (P.tile_off[mid] <= t0) lo = mid; else hi = mid; }
-    c = lo; c_begin = P.tile_off[c]; c_end = P.tile_off[c + 1];
-    fresh = true;
-  }
-  // 32-bit bookkeeping inside the chunk: tiles left in the current cell, index of the tile's first fish
-  const int64_t room = c_end - t0;
-  int left = room < (int64_t)(1 << 30) ? (int)room : (1 << 30);
-  int fish_base = (int)(t0 - c_begin) * 32;
-  const int nt = (int)(t1 - t0);
-  for (int it = 0; it < nt; ++it, --left, fish_base += 32) {
-    if (left == 0) {
-      do { ++c; c_begin = c_end; c_end = P.tile_off[c + 1]; } while (c_end == c_begin);
-      const int64_t rm = c_end - c_begin;
-      left = rm < (int64_t)(1 << 30) ? (int)rm : (1 << 30);
-      fish_base = 0;
-      fresh = true;
-    }
-    if (fresh) {
-      fresh = false;
-      if (cur_cell >= 0) {
-        if (PK && held) { if (held == 1) drain_one_tile(); else drain(); }
-        flush(cur_cell);
-      }
-      cur_cell = c;
-      STRYKE_BCHK(P, c >= 0 && c < P.n_cells, 6);
-      n_c = P.cell_n[c];
-      const uint64_t cid = P.cell_id[c];
-      cid_lo = (uint32_t)cid; cid_hi = (uint32_t)(cid >> 32);
-      const int s = P.cell_species[c];
-      if (s == cur_species) {
-        // cells are ordered group by group: the neighbours of a cell almost always belong to the same species
-      } else if (s < n_sp) {
-        cur_species = s;
-        const float* q = s_species + s * SPW;
-        sp_ls = q[0]; sp_ll = q[1]; sp_lsc = q[2]; sp_lm = q[3]; sp_lsd = q[4]; sp_mode = (int)q[5];
-        sp_wr = q[6]; sp_uc = q[7]; sp_d1 = q[8]; sp_dd = q[9] - q[8]; sp_b0 = q[10] * 1.44269504f; sp_b1 = q[11];
-      } else {
-        cur_species = s;
-        const double* q = P.species + (int64_t)s * STRYKE_SPECIES_W;
-        sp_ls = (float)q[0]; sp_ll = (float)q[1]; sp_lsc = (float)q[2]; sp_lm = (float)q[3]; sp_lsd = (float)q[4];
-        sp_mode = (int)q[5]; sp_wr = (float)q[6]; sp_uc = (float)q[7]; sp_d1 = (float)q[8];
-        sp_dd = (float)q[9] - (float)q[8]; sp_b0 = (float)q[10] * 1.44269504f; sp_b1 = (float)q[11];
-      }
-      const int d = P.cell_day[c];
-      if (d != cur_day) {   // stage the day's routing rows and unit coefficients in this warp's slot
-        cur_day = d;
-        __syncwarp();
-        const double* cdf = P.edge_cdf + (size_t)d * P.n_edges;
-        const uint8_t* st = P.node_stay + (size_t)d * n_nodes;
-        for (int i = lane; i < n_nodes * crow; i += 32) {
-          const int v = i / crow, e = i - v * crow;
-          const NodeRec nr = P.nodes[v];
-          s_cdf[i] = (e < (int)nr.deg && !st[v]) ? (float)cdf[nr.edge_off + e] : 2.0f;
-        }
-        for (int i = lane; i < n_nodes * stride; i += 32) {
-          const int v = i / stride, e = i - v * stride;
-          const NodeRec nr = P.nodes[v];
-          s_dst[i] = (e < (int)nr.deg && !st[v]) ? (int)P.edge_dst[nr.edge_off + e] : v;
-        }
-        const double* uc = P.unit_coef + (size_t)d * n_units * STRYKE_UNIT_COEF_W;
-        for (int u = lane; u < n_units; u += 32) {
-          const double* r = uc + u * STRYKE_UNIT_COEF_W;
-          const double lnd = r[0] * r[1] / r[2];
-          const bool kap = r[4] != 0.0 || r[5] != 0.0;
-          // linear runners use the Kaplan formula with fa = 0, fb = 1, rR = 1, inv = 1:  p = fc * L
-          s_ucoef[u] = make_float4(kap ? (float)(r[3] / r[4]) : 0.f, kap ? (float)(1.0 / r[5]) : 1.f,
-                                   kap ? (float)lnd : (float)(lnd * r[3]), (float)r[6]);
-        }
-        __syncwarp();
-      }
-    }
-    const int fish = fish_base + lane;
-    STRYKE_BCHK(P, fish_base >= 0 && (lane != 0 || fish < n_c), 7);     // a tile always holds at least one fish of its cell
-    const bool active = fish < n_c;
 
+  // species parameters and the day's tables of cell c (both kept across cells: neighbours share them)
+  auto load_params = [&](int64_t c) {
+    const int s = P.cell_species[c];
+    if (s == cur_species) {
+      // cells are ordered group by group: the neighbours of a cell almost always belong to the same species
+    } else if (s < n_sp) {
+      cur_species = s;
+      const float* q = s_species + s * SPW;
+      sp_ls = q[0]; sp_ll = q[1]; sp_lsc = q[2]; sp_lm = q[3]; sp_lsd = q[4]; sp_mode = (int)q[5];
+      sp_wr = q[6]; sp_uc = q[7]; sp_d1 = q[8]; sp_dd = q[9] - q[8]; sp_b0 = q[10] * 1.44269504f; sp_b1 = q[11];
+    } else {
+      cur_species = s;
+      const double* q = P.species + (int64_t)s * STRYKE_SPECIES_W;
+      sp_ls = (float)q[0]; sp_ll = (float)q[1]; sp_lsc = (float)q[2]; sp_lm = (float)q[3]; sp_lsd = (float)q[4];
+      sp_mode = (int)q[5]; sp_wr = (float)q[6]; sp_uc = (float)q[7]; sp_d1 = (float)q[8];
+      sp_dd = (float)q[9] - (float)q[8]; sp_b0 = (float)q[10] * 1.44269504f; sp_b1 = (float)q[11];
+    }
+    const int d = P.cell_day[c];
+    if (d != cur_day) {   // stage the day's routing rows and unit coefficients in this warp's slot
+      cur_day = d;
+      __syncwarp();
+      const double* cdf = P.edge_cdf + (size_t)d * P.n_edges;
+      const uint8_t* st = P.node_stay + (size_t)d * n_nodes;
+      for (int i = lane; i < n_nodes * crow; i += 32) {
+        const int v = i / crow, e = i - v * crow;
+        const NodeRec nr = P.nodes[v];
+        s_cdf[i] = (e < (int)nr.deg && !st[v]) ? (float)cdf[nr.edge_off + e] : 2.0f;
+      }
+      for (int i = lane; i < n_nodes * stride; i += 32) {
+        const int v = i / stride, e = i - v * stride;
+        const NodeRec nr = P.nodes[v];
+        s_dst[i] = (e < (int)nr.deg && !st[v]) ? (int)P.edge_dst[nr.edge_off + e] : v;
+      }
+      const double* uc = P.unit_coef + (size_t)d * n_units * STRYKE_UNIT_COEF_W;
+      for (int u = lane; u < n_units; u += 32) {
+        const double* r = uc + u * STRYKE_UNIT_COEF_W;
+        const double lnd = r[0] * r[1] / r[2];
+        const bool kap = r[4] != 0.0 || r[5] != 0.0;
+        // linear runners use the Kaplan formula with fa = 0, fb = 1, rR = 1, inv = 1:  p = fc * L
+        s_ucoef[u] = make_float4(kap ? (float)(r[3] / r[4]) : 0.f, kap ? (float)(1.0 / r[5]) : 1.f,
+                                 kap ? (float)lnd : (float)(lnd * r[3]), (float)r[6]);
+      }
+      __syncwarp();
+    }
+  };
+
+  // one tile: lane simulates fish `fish` of the cell with id (cid_lo, cid_hi); tallies go to W (packed) or acc_*
+  auto simulate = [&](const int fish, const bool active, const uint32_t cid_lo, const uint32_t cid_hi) {
     // ---- Philox: counter (fish, cell id, block), key = seed (constant bank) -------------------------------------
     uint32_t w[4];
     int cur_b = 0;
@@ -496,10 +463,244 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         add_if_lane1(acc_daily, 4, lane, __reduce_add_sync(0xffffffffu, (cz >> 16) & 0xffu));
       }
     }
+  };
+
+  const int64_t T = P.tile_off[P.n_cells];
+  const int64_t G = (int64_t)gridDim.x * WARPS, CH = P.chunk_tiles;
+  int64_t chunk = (int64_t)blockIdx.x * WARPS + wid;
+  int64_t cur_cell = -1;
+  auto leave_cell = [&]() {                           // packed counters -> owners -> global tallies of the current cell
+    if (cur_cell >= 0) {
+      if (PK && held) { if (held == 1) drain_one_tile(); else drain(); }
+      flush(cur_cell);
+      cur_cell = -1;
+    }
+  };
+
+  if constexpr (!TP::POOL) {
+  int64_t c = -1, c_begin = 0, c_end = 0;             // current cell and its tile range [c_begin, c_end)
+  int n_c = 0;
+  uint32_t cid_lo = 0, cid_hi = 0;
+  for (;;) {
+  const int64_t t0 = chunk * CH;
+  if (t0 >= T) break;
+  const int64_t t1 = t0 + CH < T ? t0 + CH : T;
+  {   // fetch the next chunk index now, use it after this chunk
+    unsigned long long nx = 0;
+    if (lane == 0) nx = atomicAdd(P.work_counter, 1ull);
+    chunk = G + (int64_t)__shfl_sync(0xffffffffu, nx, 0);
+  }
+  bool fresh = false;       // the tile about to be simulated is the first one this warp sees of cell c
+  if (t0 >= c_end) {        // not a continuation: last cell with tile_off[c] <= t0 (cells without fish have empty ranges)
+    int64_t lo = c < 0 ? 0 : c, hi = P.n_cells;
+    while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (P.tile_off[mid] <= t0) lo = mid; else hi = mid; }
+    c = lo; c_begin = P.tile_off[c]; c_end = P.tile_off[c + 1];
+    fresh = true;
+  }
+  // 32-bit bookkeeping inside the chunk: tiles left in the current cell, index of the tile's first fish
+  const int64_t room = c_end - t0;
+  int left = room < (int64_t)(1 << 30) ? (int)room : (1 << 30);
+  int fish_base = (int)(t0 - c_begin) * 32;
+  const int nt = (int)(t1 - t0);
+  for (int it = 0; it < nt; ++it, --left, fish_base += 32) {
+    if (left == 0) {
+      do { ++c; c_begin = c_end; c_end = P.tile_off[c + 1]; } while (c_end == c_begin);
+      const int64_t rm = c_end - c_begin;
+      left = rm < (int64_t)(1 << 30) ? (int)rm : (1 << 30);
+      fish_base = 0;
+      fresh = true;
+    }
+    if (fresh) {
+      fresh = false;
+      leave_cell();
+      cur_cell = c;
+      STRYKE_BCHK(P, c >= 0 && c < P.n_cells, 6);
+      n_c = P.cell_n[c];
+      const uint64_t cid = P.cell_id[c];
+      cid_lo = (uint32_t)cid; cid_hi = (uint32_t)(cid >> 32);
+      load_params(c);
+    }
+    const int fish = fish_base + lane;
+    STRYKE_BCHK(P, fish_base >= 0 && (lane != 0 || fish < n_c), 7);     // a tile always holds at least one fish of its cell
+    simulate(fish, fish < n_c, cid_lo, cid_hi);
   }
   }
-  if (PK && held) { if (held == 1) drain_one_tile(); else drain(); }
-  if (cur_cell >= 0) flush(cur_cell);
+  } else {
+  // ---- pooled remainders (see pool_kernel): blocks of 32 cells; the tiles of block b are its shared tiles, then the
+  // full tiles of its cells in order.  tile_off[32 b] is the block's first tile.  A shared tile's per-lane counters are
+  // added to per-cell accumulator words in shared memory (whole words: a cell has at most 31 pooled fish, no field can
+  // carry); when the warp leaves the block the accumulators go to global memory, one lane per (cell, counter).
+  uint4* s_blk = reinterpret_cast<uint4*>(wbase + SL.pool_blk);
+  long long* s_ef = reinterpret_cast<long long*>(wbase + SL.pool_ef);
+  int* s_rank = reinterpret_cast<int*>(wbase + SL.pool_rank);
+  uint32_t* s_acc = reinterpret_cast<uint32_t*>(wbase + SL.pool_seg);        // [32 cells][NW]
+  uint32_t* s_field = reinterpret_cast<uint32_t*>(smem + SL.pool_field);     // [2 n_pairs + 5]: word [0:5) shift [5:10) 10-bit [10] exists [11]
+  const int NI = 2 * n_pairs + STRYKE_DAILY_W;
+  if (wid == 0) {
+#pragma unroll
+    for (int r = 0; r < PR; ++r) {
+      const int p = r * 32 + lane;
+      if (p < n_pairs) {
+        const uint32_t ex = ((lcfg[r] >> 20) & 1u) << 11;
+        s_field[2 * p] = ((lcfg[r] >> 10) & 0x3ffu) | ex;                   // survivors
+        s_field[2 * p + 1] = (lcfg[r] & 0x3ffu) | ex;                       // arrivals
+      }
+    }
+    if (lane < STRYKE_DAILY_W) s_field[2 * n_pairs + lane] = dcfg & 0xfffu;
+  }
+#pragma unroll
+  for (int q = 0; q < TP::NW; ++q) s_acc[lane * TP::NW + q] = 0u;
+  __syncthreads();
+  const int64_t NB = (P.n_cells + 31) >> 5;
+  auto blk_off = [&](int64_t b) -> int64_t { const int64_t c = b << 5; return P.tile_off[c < P.n_cells ? c : P.n_cells]; };
+  const uint32_t below = (2u << lane) - 1u;           // bits 0 .. lane
+  int64_t b = -1, b_begin = 0, b_end = 0;             // current block and its tile range
+  int S_b = 0, nrem = 0;                              // its shared tiles, its cells with a remainder
+  bool pool_dirty = false;
+  auto pool_flush = [&]() {                           // accumulators of block b -> global tallies
+    if (pool_dirty) {
+      pool_dirty = false;
+      __syncwarp();
+      for (int i0 = 0; i0 < NI; i0 += 32) {           // lane <-> counter i0 + lane, loop over the cells with a remainder
+        const int i = i0 + lane;
+        const uint32_t cf = i < NI ? s_field[i] : 0u;
+        const int wq = (int)(cf & 31u);
+        const uint32_t sh = (cf >> 5) & 31u;
+        const uint32_t mask = ((cf >> 11) & 1u) ? (((cf >> 10) & 1u) ? 1023u : 63u) : 0u;
+        const bool state = i < 2 * n_pairs;
+        uint32_t* base = state ? P.state_daily + i : P.daily + (i - 2 * n_pairs);
+        const uint32_t per_cell = state ? (uint32_t)(2 * n_pairs) : (uint32_t)STRYKE_DAILY_W;
+        base += (size_t)(b << 5) * per_cell;
+        for (int rho = 0; rho < nrem; ++rho) {
+          const int jl = s_rank[rho];
+          const uint32_t v = (s_acc[jl * TP::NW + wq] >> sh) & mask;
+          STRYKE_BCHK(P, (b << 5) + jl < P.n_cells, 12);
+          if (v) atomicAdd(base + (uint32_t)jl * per_cell, v);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < TP::NW; ++q) s_acc[lane * TP::NW + q] = 0u;
+      __syncwarp();
+    }
+  };
+  auto clamp30 = [](long long x) -> int { return x < (long long)(1 << 30) ? (int)x : (1 << 30); };
+  for (;;) {
+  const int64_t t0 = chunk * CH;
+  if (t0 >= T) break;
+  const int64_t t1 = t0 + CH < T ? t0 + CH : T;
+  {
+    unsigned long long nx = 0;
+    if (lane == 0) nx = atomicAdd(P.work_counter, 1ull);
+    chunk = G + (int64_t)__shfl_sync(0xffffffffu, nx, 0);
+  }
+  bool new_block = false;
+  if (t0 < b_begin || t0 >= b_end) {                  // last block with blk_off <= t0 (blocks without fish have empty ranges)
+    pool_flush();
+    int64_t lo = 0, hi = NB;
+    while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (blk_off(mid) <= t0) lo = mid; else hi = mid; }
+    b = lo; b_begin = blk_off(b); b_end = blk_off(b + 1);
+    new_block = true;
+  }
+  // `run` tiles from here on are full tiles of one cell (fish_base: first fish of the next one): nothing to decide
+  // between them.  run == 0: find out what the next tile is (next block? shared tile? which cell?).
+  const int nt = (int)(t1 - t0);
+  int run = 0, fish_base = 0, jl = 0;
+  bool shared = false;
+  uint32_t cid_lo = 0, cid_hi = 0;
+  for (int it = 0; it < nt; ++it, --run, fish_base += 32) {
+    int fish = fish_base + lane;
+    bool active = true;
+    if (run == 0) {
+      leave_cell();
+      const int64_t t = t0 + it;
+      if (t >= b_end) {
+        pool_flush();
+        do { ++b; b_begin = b_end; b_end = blk_off(b + 1); } while (b_end == b_begin);
+        new_block = true;
+      }
+      if (new_block) {
+        new_block = false;
+        STRYKE_BCHK(P, b >= 0 && b < NB, 8);
+        const int64_t ci = (b << 5) + lane;
+        const bool in = ci < P.n_cells;
+        const int n = in ? P.cell_n[ci] : 0;
+        const uint64_t id = in ? P.cell_id[ci] : 0ull;
+        const uint32_t info = P.blk_S[b];
+        S_b = (int)(info & 0x7fffffffu);
+        const int r = n & 31, f = n >> 5;
+        const int pr = (info >> 31) ? (r ? 32 : 0) : r;   // mixed block: every remainder is padded to a tile of its own
+        int sr = pr;
+        long long sf = f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int tr = __shfl_up_sync(0xffffffffu, sr, o);
+          const long long tf = __shfl_up_sync(0xffffffffu, sf, o);
+          if (lane >= o) { sr += tr; sf += tf; }
+        }
+        const uint32_t rmask = __ballot_sync(0xffffffffu, r > 0);
+        nrem = __popc(rmask);
+        __syncwarp();
+        s_blk[lane] = make_uint4((uint32_t)n, (uint32_t)id, (uint32_t)(id >> 32), (uint32_t)(sr - pr));
+        s_ef[lane] = sf - f;
+        if (r > 0) s_rank[__popc(rmask & (below >> 1))] = lane;
+        __syncwarp();
+      }
+      const int64_t j = t - b_begin;
+      shared = j < (int64_t)S_b;
+      if (shared) {
+        // shared tile j: positions [base, base + 32) of the block's concatenated remainders.  M: cells whose remainder
+        // starts in this tile (bit = lane of its first fish); jl: lane (within the block) of the cell of this lane's fish
+        run = 1;
+        const int base = (int)j << 5;
+        const uint4 mine = s_blk[lane];
+        const int rel = (int)mine.w - base;
+        const bool has_r = (mine.x & 31u) != 0u;
+        const uint32_t M = __reduce_or_sync(0xffffffffu, (has_r && (unsigned)rel < 32u) ? (1u << rel) : 0u);
+        const int K0 = __popc(__ballot_sync(0xffffffffu, has_r && rel < 0));     // remainders that start before the tile
+        const int rank = K0 + __popc(M & below) - 1;
+        STRYKE_BCHK(P, rank >= 0 && rank < nrem, 9);
+        jl = s_rank[rank];
+        STRYKE_BCHK(P, jl >= 0 && jl < 32, 10);
+        const uint4 cellrec = s_blk[jl];
+        const int n = (int)cellrec.x;
+        fish = (n & ~31) + (base + lane - (int)cellrec.w);
+        active = fish < n;
+        STRYKE_BCHK(P, fish >= (n & ~31) && (lane != 0 || active), 11);
+        cid_lo = cellrec.y; cid_hi = cellrec.z;
+        load_params((b << 5) + __shfl_sync(0xffffffffu, jl, 0));
+      } else {                                          // full tile jj of the block: which cell?
+        const long long jj = j - S_b;
+        const long long ef = s_ef[lane];
+        const int f = (int)(s_blk[lane].x >> 5);
+        const int sel = __ffs(__ballot_sync(0xffffffffu, f > 0 && jj >= ef && jj < ef + f)) - 1;
+        STRYKE_BCHK(P, sel >= 0 && sel < 32, 13);
+        const long long ef_s = s_ef[sel];
+        const uint4 cellrec = s_blk[sel];
+        run = __shfl_sync(0xffffffffu, clamp30(ef_s + (long long)(cellrec.x >> 5) - jj), 0);
+        fish_base = __shfl_sync(0xffffffffu, (int)(jj - ef_s) * 32, 0);
+        fish = fish_base + lane;
+        cur_cell = (b << 5) + sel;
+        cid_lo = cellrec.y; cid_hi = cellrec.z;
+        load_params(cur_cell);
+      }
+    }
+    simulate(fish, active, cid_lo, cid_hi);
+    if (shared) {
+      uint32_t* row = s_acc + jl * TP::NW;
+#pragma unroll
+      for (int q = 0; q < TP::NW; ++q) {
+        if (W[q]) atomicAdd(row + q, W[q]);
+        W[q] = 0;
+      }
+      held = 0;
+      pool_dirty = true;
+    }
+  }
+  }
+  pool_flush();
+  }
+  leave_cell();
 }
 
 #ifndef STRYKE_NVRTC

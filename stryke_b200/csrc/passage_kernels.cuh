@@ -153,6 +153,32 @@ __global__ void count_kernel(KParams P, const double* __restrict__ day_Q, int32_
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int SCAN_T = 1024, SCAN_PER = 4, SCAN_CH = SCAN_T * SCAN_PER;
 
+// Pooled remainders (throughput kernel, population mode: most present cells hold fewer than 32 fish).  Cells are taken
+// in aligned blocks of 32; a cell of n fish keeps n >> 5 full tiles of its own, the n & 31 fish left over are laid end to
+// end with those of the other cells of its block and cut into shared tiles.  A block whose cells differ in species or
+// day ("mixed") keeps one tile per remainder instead (the day tables and species parameters are warp-uniform).  One warp
+// per block writes the block's number of shared tiles; the scans below then charge them to the first cell of the block.
+__global__ void __launch_bounds__(256) pool_kernel(const int32_t* __restrict__ cell_n, const int32_t* __restrict__ cell_species,
+                                                   const int32_t* __restrict__ cell_day, int64_t n_cells, uint32_t* __restrict__ blk_S) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b * 32 >= n_cells) return;                              // whole warps leave together
+  const int64_t c = b * 32 + lane;
+  const bool in = c < n_cells;
+  const int n = in ? cell_n[c] : 0;
+  const int sp = in ? cell_species[c] : 0, dy = in ? cell_day[c] : 0;
+  const int sp0 = __shfl_sync(0xffffffffu, sp, 0), dy0 = __shfl_sync(0xffffffffu, dy, 0);
+  const bool mixed = __ballot_sync(0xffffffffu, in && (sp != sp0 || dy != dy0)) != 0u;
+  const int r = n & 31;
+  const uint32_t tot = mixed ? 32u * (uint32_t)__popc(__ballot_sync(0xffffffffu, r > 0)) : __reduce_add_sync(0xffffffffu, (uint32_t)r);
+  if (lane == 0) blk_S[b] = ((tot + 31u) >> 5) | (mixed ? 0x80000000u : 0u);
+}
+// tiles charged to cell c of n fish: blk_S == nullptr -> one tile per started 32 fish
+__device__ __forceinline__ int64_t cell_tiles(const uint32_t* __restrict__ blk_S, int64_t c, int32_t n) {
+  if (!blk_S) return (n + 31) >> 5;
+  return (int64_t)(n >> 5) + ((c & 31) == 0 ? (int64_t)(blk_S[c >> 5] & 0x7fffffffu) : 0);
+}
+
 __device__ __forceinline__ void block_scan2(int64_t& a, int64_t& b, int64_t* sh) {   // inclusive, 1024 threads
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -177,13 +203,13 @@ __device__ __forceinline__ void block_scan2(int64_t& a, int64_t& b, int64_t* sh)
 }
 
 __global__ void __launch_bounds__(SCAN_T) scan_partial(const int32_t* __restrict__ cell_n, int64_t n_cells,
-                                                       int64_t* __restrict__ part) {
+                                                       int64_t* __restrict__ part, const uint32_t* __restrict__ blk_S) {
   __shared__ int64_t sh[64];
   const int64_t base = (int64_t)blockIdx.x * SCAN_CH + threadIdx.x * SCAN_PER;
   int64_t t = 0, f = 0;
 #pragma unroll
   for (int i = 0; i < SCAN_PER; ++i)
-    if (base + i < n_cells) { const int32_t n = cell_n[base + i]; f += n; t += (n + 31) >> 5; }
+    if (base + i < n_cells) { const int32_t n = cell_n[base + i]; f += n; t += cell_tiles(blk_S, base + i, n); }
   block_scan2(t, f, sh);
   if (threadIdx.x == SCAN_T - 1) { part[2 * blockIdx.x] = t; part[2 * blockIdx.x + 1] = f; }
 }
@@ -203,7 +229,7 @@ __global__ void __launch_bounds__(SCAN_T) scan_blocks(int64_t* __restrict__ part
 }
 __global__ void __launch_bounds__(SCAN_T) scan_final(const int32_t* __restrict__ cell_n, int64_t n_cells,
                                                      const int64_t* __restrict__ part, int64_t* __restrict__ tile_off,
-                                                     int64_t* __restrict__ fish_off) {
+                                                     int64_t* __restrict__ fish_off, const uint32_t* __restrict__ blk_S) {
   __shared__ int64_t sh[64];
   const int64_t base = (int64_t)blockIdx.x * SCAN_CH + threadIdx.x * SCAN_PER;
   int32_t nn[SCAN_PER];
@@ -211,7 +237,7 @@ __global__ void __launch_bounds__(SCAN_T) scan_final(const int32_t* __restrict__
 #pragma unroll
   for (int i = 0; i < SCAN_PER; ++i) {
     nn[i] = base + i < n_cells ? cell_n[base + i] : 0;
-    f += nn[i]; t += (nn[i] + 31) >> 5;
+    f += nn[i]; t += base + i < n_cells ? cell_tiles(blk_S, base + i, nn[i]) : 0;
   }
   int64_t it = t, jf = f;
   block_scan2(it, jf, sh);
@@ -219,7 +245,7 @@ __global__ void __launch_bounds__(SCAN_T) scan_final(const int32_t* __restrict__
 #pragma unroll
   for (int i = 0; i < SCAN_PER; ++i) {
     if (base + i < n_cells) { tile_off[base + i] = et; fish_off[base + i] = ef; }
-    et += (nn[i] + 31) >> 5; ef += nn[i];
+    et += base + i < n_cells ? cell_tiles(blk_S, base + i, nn[i]) : 0; ef += nn[i];
     if (base + i == n_cells - 1) { tile_off[n_cells] = et; fish_off[n_cells] = ef; }
   }
 }

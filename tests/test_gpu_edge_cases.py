@@ -63,3 +63,60 @@ def test_many_tiny_cells_population_mode_all_variants_agree():
     for other in (b, c):
         assert np.array_equal(a.cell_n, other.cell_n) and np.array_equal(a.daily, other.daily)
         assert np.array_equal(a.state_daily, other.state_daily)
+
+
+def _same(a, b):
+    return (np.array_equal(a.cell_n, b.cell_n) and np.array_equal(a.daily, b.daily)
+            and np.array_equal(a.state_daily, b.state_daily))
+
+
+@pytest.mark.parametrize("order", ["engine", "shuffled", "ragged"])
+def test_pooled_remainders_equal_one_tile_per_remainder(order, monkeypatch):
+    """The specialised kernel packs the n mod 32 left-over fish of the cells of a 32-cell block into shared tiles
+    (pool_kernel, passage_fast.cuh).  Same Philox counters (fish index, cell id) -> the tallies must not change, whether
+    the blocks are uniform (engine order), mixed in species and day (shuffled cells: one tile per remainder) or the cell
+    list is not a multiple of 32 long."""
+    prj = fixtures.c3_population(n_species=5, iterations=90, days=7)
+    sim, plan = G.make_plan(prj, "pool")
+    cells = np.arange(plan.n_cells)
+    if order == "shuffled":
+        cells = np.random.default_rng(5).permutation(plan.n_cells)
+    elif order == "ragged":
+        cells = cells[3:-18]
+    assert order != "ragged" or len(cells) % 32 != 0
+    ref = run(plan, 1, cells=cells, cap=10 ** 7)
+    monkeypatch.setenv("STRYKE_B200_POOL", "1")
+    pooled = run(plan, 3, cells=cells, cap=10 ** 7)
+    monkeypatch.setenv("STRYKE_B200_POOL", "0")
+    plain = run(plan, 3, cells=cells, cap=10 ** 7)
+    assert ref.cell_n.sum() > 0 and ((ref.cell_n & 31) != 0).any() and (ref.cell_n >= 32).any()
+    assert _same(ref, pooled) and _same(ref, plain)
+
+
+@pytest.mark.parametrize("n_fish", [1, 31, 32, 33, 63, 64, 95, 1000, 4097])
+def test_pooled_remainders_fixed_counts_around_the_tile_size(n_fish, monkeypatch):
+    """Fixed counts at and around multiples of the tile: no remainder at all, only remainders, both."""
+    sim, plan = G.make_plan(fixtures.c2_facility(n_fish=n_fish, iterations=45, days=3), "poolfix")
+    ref = run(plan, 1)
+    monkeypatch.setenv("STRYKE_B200_POOL", "1")
+    pooled = run(plan, 3)
+    assert (ref.cell_n == n_fish).all() and _same(ref, pooled)
+
+
+def test_pooled_remainders_next_to_a_huge_cell(monkeypatch):
+    """One block holds a cell of 70 million fish (its full tiles span many chunks) between cells of a few fish."""
+    prj = fixtures.c3_population(n_species=2, iterations=40, days=4)
+    sim, plan = G.make_plan(prj, "poolhuge")
+    table = np.array(plan.species_table, dtype=np.float64).reshape(-1, plan.species_table.shape[-1])
+    big = table[0].copy()
+    big[12], big[17], big[18] = 0.0, 1.0, 70_000_013.0      # STRYKE_ENT_FIXED, always present, n
+    table = np.vstack([table, big[None, :]])
+    species = plan.cell_species.copy()
+    species[37] = len(table) - 1
+    args = (plan.fac, plan.days, table, plan.cell_day, species, plan.cell_id)
+    monkeypatch.setenv("STRYKE_B200_POOL", "1")
+    a = engine.run_cells(*args, precision=32, seed=4, max_daily_fish=10 ** 7, kernel_variant=3)
+    monkeypatch.setenv("STRYKE_B200_POOL", "0")
+    b = engine.run_cells(*args, precision=32, seed=4, max_daily_fish=10 ** 7, kernel_variant=3)
+    assert a.cell_n[37] == 70_000_013 and _same(a, b)
+    assert int(a.state_daily[37, 0, 1]) == 70_000_013
