@@ -285,7 +285,10 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
   K.n_fish_total = 0;
   K.work_counter = pl->err.as<unsigned long long>() + 1;
   K.chunk_tiles = 128;
+  K.chunk_min = 16;
   if (const char* e = getenv("STRYKE_B200_CHUNK_TILES")) K.chunk_tiles = std::max(1, atoi(e));
+  if (const char* e = getenv("STRYKE_B200_CHUNK_MIN")) K.chunk_min = std::max(1, atoi(e));
+  K.chunk_min = std::min(K.chunk_min, K.chunk_tiles);
 
   // ---- injected draws ----------------------------------------------------------------------------------------------
   int64_t NF = 0;

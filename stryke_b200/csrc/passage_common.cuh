@@ -135,7 +135,7 @@ struct KParams {
   InjectedDev inj; TraceDev trace;
   uint32_t ks[20];                    // Philox key schedule of (seed_lo, seed_hi), throughput kernels
   unsigned long long* work_counter;   // throughput kernels: next chunk of tiles to hand out (zeroed before every launch)
-  int chunk_tiles;                    // tiles per chunk
+  int chunk_tiles, chunk_min;         // largest and smallest chunk (tiles) of the guided schedule
   const uint32_t* blk_S;              // pooled remainders (passage_fast.cuh): per block of 32 cells, shared tiles [0:31) | mixed [31]
 };
 

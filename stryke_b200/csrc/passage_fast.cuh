@@ -466,8 +466,26 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   };
 
   const int64_t T = P.tile_off[P.n_cells];
-  const int64_t G = (int64_t)gridDim.x * WARPS, CH = P.chunk_tiles;
-  int64_t chunk = (int64_t)blockIdx.x * WARPS + wid;
+  // Guided self-scheduling: a warp takes (tiles not yet handed out) / (2 x warps of the grid) consecutive tiles from one
+  // global counter, at most P.chunk_tiles and at least P.chunk_min: long chunks while there is plenty of work (one cell
+  // search per chunk), short ones at the end so that all warps finish together.  The next chunk is fetched while the
+  // current one is being simulated.
+  const int64_t G = (int64_t)gridDim.x * WARPS;
+  int64_t nx0 = 0, nx1 = 0;                           // the chunk fetched ahead: tiles [nx0, nx1)
+  auto fetch_chunk = [&]() {
+    unsigned long long start = 0, size = 0;
+    if (lane == 0) {
+      const long long seen = (long long)*reinterpret_cast<volatile unsigned long long*>(P.work_counter);
+      long long sz = (T - seen) / (2 * G);
+      sz = sz > (long long)P.chunk_tiles ? (long long)P.chunk_tiles : sz;
+      sz = sz < (long long)P.chunk_min ? (long long)P.chunk_min : sz;
+      size = (unsigned long long)sz;
+      start = atomicAdd(P.work_counter, size);
+    }
+    nx0 = (int64_t)__shfl_sync(0xffffffffu, start, 0);
+    nx1 = nx0 + (int64_t)__shfl_sync(0xffffffffu, size, 0);
+  };
+  fetch_chunk();
   int64_t cur_cell = -1;
   auto leave_cell = [&]() {                           // packed counters -> owners -> global tallies of the current cell
     if (cur_cell >= 0) {
@@ -482,14 +500,10 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   int n_c = 0;
   uint32_t cid_lo = 0, cid_hi = 0;
   for (;;) {
-  const int64_t t0 = chunk * CH;
+  const int64_t t0 = nx0;
   if (t0 >= T) break;
-  const int64_t t1 = t0 + CH < T ? t0 + CH : T;
-  {   // fetch the next chunk index now, use it after this chunk
-    unsigned long long nx = 0;
-    if (lane == 0) nx = atomicAdd(P.work_counter, 1ull);
-    chunk = G + (int64_t)__shfl_sync(0xffffffffu, nx, 0);
-  }
+  const int64_t t1 = nx1 < T ? nx1 : T;
+  fetch_chunk();            // the one after this
   bool fresh = false;       // the tile about to be simulated is the first one this warp sees of cell c
   if (t0 >= c_end) {        // not a continuation: last cell with tile_off[c] <= t0 (cells without fish have empty ranges)
     int64_t lo = c < 0 ? 0 : c, hi = P.n_cells;
@@ -586,14 +600,10 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   };
   auto clamp30 = [](long long x) -> int { return x < (long long)(1 << 30) ? (int)x : (1 << 30); };
   for (;;) {
-  const int64_t t0 = chunk * CH;
+  const int64_t t0 = nx0;
   if (t0 >= T) break;
-  const int64_t t1 = t0 + CH < T ? t0 + CH : T;
-  {
-    unsigned long long nx = 0;
-    if (lane == 0) nx = atomicAdd(P.work_counter, 1ull);
-    chunk = G + (int64_t)__shfl_sync(0xffffffffu, nx, 0);
-  }
+  const int64_t t1 = nx1 < T ? nx1 : T;
+  fetch_chunk();            // the one after this
   bool new_block = false;
   if (t0 < b_begin || t0 >= b_end) {                  // last block with blk_off <= t0 (blocks without fish have empty ranges)
     pool_flush();
@@ -603,17 +613,29 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
     new_block = true;
   }
   // `run` tiles from here on are full tiles of one cell (fish_base: first fish of the next one): nothing to decide
-  // between them.  run == 0: find out what the next tile is (next block? shared tile? which cell?).
-  const int nt = (int)(t1 - t0);
+  // between them.  run == 0: find out what the next tile is (end of the chunk? next block? shared tile? which cell?).
+  int chunk_left = (int)(t1 - t0);                    // tiles of the chunk not yet handed to a run
+  int64_t t = t0;                                     // first tile after the current run
   int run = 0, fish_base = 0, jl = 0;
-  bool shared = false;
+  bool shared = false;                                // the tile just simulated was a shared one: its counters are still in W
   uint32_t cid_lo = 0, cid_hi = 0;
-  for (int it = 0; it < nt; ++it, --run, fish_base += 32) {
+  for (;; --run, fish_base += 32) {
     int fish = fish_base + lane;
     bool active = true;
     if (run == 0) {
+      if (shared) {
+        shared = false;
+        uint32_t* row = s_acc + jl * TP::NW;
+#pragma unroll
+        for (int q = 0; q < TP::NW; ++q) {
+          if (W[q]) atomicAdd(row + q, W[q]);
+          W[q] = 0;
+        }
+        held = 0;
+        pool_dirty = true;
+      }
+      if (chunk_left == 0) break;
       leave_cell();
-      const int64_t t = t0 + it;
       if (t >= b_end) {
         pool_flush();
         do { ++b; b_begin = b_end; b_end = blk_off(b + 1); } while (b_end == b_begin);
@@ -678,24 +700,17 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         const long long ef_s = s_ef[sel];
         const uint4 cellrec = s_blk[sel];
         run = __shfl_sync(0xffffffffu, clamp30(ef_s + (long long)(cellrec.x >> 5) - jj), 0);
+        run = run < chunk_left ? run : chunk_left;
         fish_base = __shfl_sync(0xffffffffu, (int)(jj - ef_s) * 32, 0);
         fish = fish_base + lane;
         cur_cell = (b << 5) + sel;
         cid_lo = cellrec.y; cid_hi = cellrec.z;
         load_params(cur_cell);
       }
+      chunk_left -= run;
+      t += run;
     }
     simulate(fish, active, cid_lo, cid_hi);
-    if (shared) {
-      uint32_t* row = s_acc + jl * TP::NW;
-#pragma unroll
-      for (int q = 0; q < TP::NW; ++q) {
-        if (W[q]) atomicAdd(row + q, W[q]);
-        W[q] = 0;
-      }
-      held = 0;
-      pool_dirty = true;
-    }
   }
   }
   pool_flush();
