@@ -244,6 +244,7 @@ def main():
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    plan.time_kernel(True)       # CUDA events around the passage kernel of every timed launch, on the launch stream
     launches0 = engine.launch_count()
     evs = []
     for i in range(args.steps):
@@ -260,6 +261,8 @@ def main():
     torch.cuda.synchronize()
     sampler.stop_flag = True
     ms = sum(a.elapsed_time(b) for a, b in evs)
+    kernel_ms, kernel_n = plan.kernel_ms()
+    plan.time_kernel(False)
     plan.status()
     t_ms = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     t_fish = torch.tensor([float(fish_per_step)], dtype=torch.float64, device=f"cuda:{local_rank}")
@@ -273,19 +276,23 @@ def main():
     peak_ops, cal_ms = engine.calibrate_issue(local_rank, stream.cuda_stream)
     algo = ALGO_LANE_OPS[args.workload]
     per_gpu_rate = fish_per_step * args.steps / (ms_total * 1e-3)
-    achieved = per_gpu_rate * algo
+    achieved = fish_per_step * kernel_n / (kernel_ms * 1e-3) * algo      # this rank's passage kernel alone
     traffic = None
-    prof = os.path.join(ROOT, "profiles", "r01_passage_metrics.json")
+    prof = os.path.join(ROOT, "profiles", "r01_c3_passage_metrics.json" if args.workload == "c3" else "r01_passage_metrics.json")
     if os.path.isfile(prof):
         with open(prof) as fh:
             traffic = json.load(fh).get("dram_bytes_per_launch")
     roofline = {"bound": "issue", "achieved": achieved / 1e12, "peak": peak_ops / 1e12, "unit": "Tlane-op/s",
                 "frac": achieved / peak_ops, "traffic": traffic,
+                "kernel_ms_per_launch": kernel_ms / max(kernel_n, 1), "kernel_share_of_step": kernel_ms / ms,
+                "frac_of_whole_step": per_gpu_rate * algo / peak_ops,
                 "note": "neither HBM nor tensor binds this path (SURVEY.md §8d): bound = SM instruction issue (INT32 Philox on the "
                         "half-rate ALU pipe + FP32/MUFU). "
                         f"achieved = {algo:.0f} algorithmic lane-ops per fish-passage (DESIGN.md §4: the instruction count of the best known "
-                        "schedule, = what the specialised kernel executes per fish under ncu) x fish-passages/s per GPU over the step's "
-                        "CUDA-event time (the passage kernel is > 99.9 % of the step, profiles/r01_launch_shares.md); peak = lane-ops/s of "
+                        "schedule, = what the specialised kernel executes per fish under ncu) x fish-passages per launch / the passage "
+                        "kernel's own launch duration (CUDA events recorded around it on the launch stream inside the timed region, "
+                        "stryke_b200_plan_time_kernel; kernel_share_of_step = its share of the step's CUDA-event time, the count / scan "
+                        "kernels and the tally memsets are the rest; frac_of_whole_step uses the step time instead); peak = lane-ops/s of "
                         "16 independent FFMA chains per thread at full occupancy (1 warp instruction per scheduler per cycle) measured live by "
                         "stryke_b200_calibrate_issue on this GPU; traffic = DRAM bytes per launch (ncu)",
                 "hbm": {"achieved_GBps": (plan.n_cells * (4 + 20 + plan.n_pairs * 8) * 2) / (ms_total / args.steps * 1e-3) / 1e9,

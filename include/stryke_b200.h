@@ -174,6 +174,11 @@ int stryke_b200_plan_launch(StrykePlan* plan, int32_t* d_cell_n, uint32_t* d_dai
 const char* stryke_b200_plan_kernel(const StrykePlan* plan);      /* which passage kernel the plan will launch */
 int stryke_b200_set_source_dir(const char* dir);                 /* directory holding passage_fast.cuh / passage_common.cuh (run-time specialisation) */
 int stryke_b200_jit_selftest(void);                              /* compiles a specialised kernel with NVRTC; needs no GPU */
+/* Measurement support (no reference counterpart): with enable != 0 every later plan_launch brackets its passage kernel
+ * (not the count / scan kernels before it) with CUDA events on the launch stream; plan_kernel_ms waits for them, returns
+ * the summed kernel time and the number of launches since the last call, and forgets them. */
+int stryke_b200_plan_time_kernel(StrykePlan* plan, int enable);
+int stryke_b200_plan_kernel_ms(StrykePlan* plan, double* total_ms, int32_t* n_launches);
 int stryke_b200_plan_set_seed(StrykePlan* plan, uint64_t seed);   /* Philox key of the next launches */
 int stryke_b200_plan_status(StrykePlan* plan, void* stream, int64_t* n_fish_total);   /* syncs the stream; reports STRYKE_E_MAX_FISH etc. */
 int stryke_b200_plan_fetch_trace(StrykePlan* plan, const StrykeTrace* host_trace, void* stream);

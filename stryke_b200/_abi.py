@@ -95,6 +95,8 @@ def lib():
     L.stryke_b200_set_source_dir.restype = C.c_int
     L.stryke_b200_jit_selftest.restype = C.c_int
     L.stryke_b200_plan_status.argtypes = [_p, _p, P(C.c_int64)]
+    L.stryke_b200_plan_time_kernel.argtypes = [_p, C.c_int]
+    L.stryke_b200_plan_kernel_ms.argtypes = [_p, P(C.c_double), P(C.c_int32)]
     L.stryke_b200_plan_fetch_trace.argtypes = [_p, P(Trace), _p]
     L.stryke_b200_plan_destroy.argtypes = [_p]
     L.stryke_b200_strike_survival.argtypes = [C.c_int, _p, C.c_int64, _p, _p, C.c_int, C.c_int, _p]
@@ -102,6 +104,7 @@ def lib():
     L.stryke_b200_philox.argtypes = [C.c_int64, _p, _p, C.c_int, _p]
     L.stryke_b200_calibrate_issue.argtypes = [C.c_int, _p, P(C.c_double), P(C.c_double)]
     for name in ("run", "plan_create", "plan_launch", "plan_set_seed", "plan_status", "plan_fetch_trace", "plan_destroy",
+                 "plan_time_kernel", "plan_kernel_ms",
                  "strike_survival", "baro_survival", "philox", "calibrate_issue"):
         getattr(L, "stryke_b200_" + name).restype = C.c_int
     L.stryke_b200_set_source_dir(os.path.join(_HERE, "csrc").encode())
@@ -111,7 +114,7 @@ def lib():
 
 EXPORTS = ["stryke_b200_last_error", "stryke_b200_abi_version", "stryke_b200_device_count", "stryke_b200_launch_count",
            "stryke_b200_run", "stryke_b200_plan_create", "stryke_b200_plan_launch", "stryke_b200_plan_kernel", "stryke_b200_set_source_dir", "stryke_b200_jit_selftest", "stryke_b200_plan_set_seed", "stryke_b200_plan_status",
-           "stryke_b200_plan_fetch_trace", "stryke_b200_plan_destroy", "stryke_b200_strike_survival",
+           "stryke_b200_plan_fetch_trace", "stryke_b200_plan_destroy", "stryke_b200_plan_time_kernel", "stryke_b200_plan_kernel_ms", "stryke_b200_strike_survival",
            "stryke_b200_baro_survival", "stryke_b200_philox", "stryke_b200_calibrate_issue", "stryke_b200_bootstrap_means"]
 
 

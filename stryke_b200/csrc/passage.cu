@@ -115,11 +115,15 @@ struct StrykePlan {
   size_t fast_smem_bytes = 0;
   int fast_stride = 1;
   bool use_fast = false;
-  bool pool = false;          // remainders of the cells pooled into shared tiles (pool_kernel; specialised kernel only)
+  bool pool = false;          // remainders of the cells pooled into shared tiles (pool_block; specialised kernel only)
   cudaKernel_t jit_kernel = nullptr;
   std::string kernel_name = "passage_kernel (general)";
   int64_t trace_fish = 0;
   bool has_trace = false, trace_probs = false;
+  // optional: CUDA events around every launch of the passage kernel (stryke_b200_plan_time_kernel)
+  bool time_kernel = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_events;
+  ~StrykePlan() { for (auto& e : kernel_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } }
 };
 
 namespace jit {
@@ -514,22 +518,49 @@ int stryke_b200_plan_launch(StrykePlan* pl, int32_t* d_cell_n, uint32_t* d_daily
   CK(cudaMemsetAsync(d_state_daily, 0, (size_t)pl->n_cells * K.n_pairs * 2 * 4, st));
   CK(cudaMemsetAsync(pl->err.p, 0, 2 * sizeof(unsigned long long), st));
   const int cb = (int)((pl->n_cells + 255) / 256);
-  if (pl->inject) count_kernel<true><<<cb, 256, 0, st>>>(K, pl->day_Q.as<double>(), d_cell_n, pl->max_daily_fish, pl->err.as<unsigned long long>());
-  else count_kernel<false><<<cb, 256, 0, st>>>(K, pl->day_Q.as<double>(), d_cell_n, pl->max_daily_fish, pl->err.as<unsigned long long>());
-  const uint32_t* blk_S = pl->pool ? pl->blk_S.as<uint32_t>() : nullptr;
-  if (pl->pool) {
-    const int64_t nb = (pl->n_cells + 31) / 32;
-    pool_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, st>>>(d_cell_n, K.cell_species, K.cell_day, pl->n_cells, pl->blk_S.as<uint32_t>());
-    g_launches++;
-  }
+  uint32_t* blk_S = pl->pool ? pl->blk_S.as<uint32_t>() : nullptr;      // pooled remainders: shared tiles per block of 32 cells
+  if (pl->inject) count_kernel<true><<<cb, 256, 0, st>>>(K, pl->day_Q.as<double>(), d_cell_n, pl->max_daily_fish, pl->err.as<unsigned long long>(), blk_S);
+  else count_kernel<false><<<cb, 256, 0, st>>>(K, pl->day_Q.as<double>(), d_cell_n, pl->max_daily_fish, pl->err.as<unsigned long long>(), blk_S);
   scan_partial<<<pl->nb_scan, SCAN_T, 0, st>>>(d_cell_n, pl->n_cells, pl->part.as<int64_t>(), blk_S);
   scan_blocks<<<1, SCAN_T, 0, st>>>(pl->part.as<int64_t>(), pl->nb_scan);
   scan_final<<<pl->nb_scan, SCAN_T, 0, st>>>(d_cell_n, pl->n_cells, pl->part.as<int64_t>(), pl->tile_off.as<int64_t>(), pl->fish_off.as<int64_t>(), blk_S);
   g_launches += 4;
   CK(cudaGetLastError());
-  if (pl->use_fast) return launch_fast_any(pl, st);
-  if (pl->precision == 64) return pl->inject ? launch_passage_pr<double, true>(pl, st) : launch_passage_pr<double, false>(pl, st);
-  return pl->inject ? launch_passage_pr<float, true>(pl, st) : launch_passage_pr<float, false>(pl, st);
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (pl->time_kernel) {
+    CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+    pl->kernel_events.emplace_back(ev0, ev1);
+    CK(cudaEventRecord(ev0, st));
+  }
+  int rc;
+  if (pl->use_fast) rc = launch_fast_any(pl, st);
+  else if (pl->precision == 64) rc = pl->inject ? launch_passage_pr<double, true>(pl, st) : launch_passage_pr<double, false>(pl, st);
+  else rc = pl->inject ? launch_passage_pr<float, true>(pl, st) : launch_passage_pr<float, false>(pl, st);
+  if (ev1) CK(cudaEventRecord(ev1, st));
+  return rc;
+}
+
+int stryke_b200_plan_time_kernel(StrykePlan* pl, int enable) {
+  if (!pl) return fail(STRYKE_E_ARG, "null plan");
+  pl->time_kernel = enable != 0;
+  return STRYKE_OK;
+}
+
+int stryke_b200_plan_kernel_ms(StrykePlan* pl, double* total_ms, int32_t* n_launches) {
+  if (!pl || !total_ms || !n_launches) return fail(STRYKE_E_ARG, "null argument");
+  CK(cudaSetDevice(pl->device));
+  double ms = 0.0;
+  for (auto& e : pl->kernel_events) {
+    float t = 0.f;
+    CK(cudaEventSynchronize(e.second));
+    CK(cudaEventElapsedTime(&t, e.first, e.second));
+    ms += t;
+  }
+  *total_ms = ms;
+  *n_launches = (int32_t)pl->kernel_events.size();
+  for (auto& e : pl->kernel_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  pl->kernel_events.clear();
+  return STRYKE_OK;
 }
 
 int stryke_b200_set_source_dir(const char* dir) {

@@ -540,7 +540,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   }
   }
   } else {
-  // ---- pooled remainders (see pool_kernel): blocks of 32 cells; the tiles of block b are its shared tiles, then the
+  // ---- pooled remainders (see pool_block): blocks of 32 cells; the tiles of block b are its shared tiles, then the
   // full tiles of its cells in order.  tile_off[32 b] is the block's first tile.  A shared tile's per-lane counters are
   // added to per-cell accumulator words in shared memory (whole words: a cell has at most 31 pooled fish, no field can
   // carry); when the warp leaves the block the accumulators go to global memory, one lane per (cell, counter).

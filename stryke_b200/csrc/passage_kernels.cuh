@@ -82,12 +82,30 @@ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {   // numpy-sty
   return (double)((((uint64_t)hi >> 5) << 26) | ((uint64_t)lo >> 6)) * (1.0 / 9007199254740992.0);
 }
 
+// Pooled remainders (throughput kernel, population mode: most present cells hold fewer than 32 fish).  Cells are taken
+// in aligned blocks of 32; a cell of n fish keeps n >> 5 full tiles of its own, the n & 31 fish left over are laid end to
+// end with those of the other cells of its block and cut into shared tiles.  A block whose cells differ in species or
+// day ("mixed") keeps one tile per remainder instead (the day tables and species parameters are warp-uniform).  The warp
+// of count_kernel that drew the 32 counts writes the block's number of shared tiles (bit 31: mixed); the scans then
+// charge them to the first cell of the block.  Called by all 32 lanes; lanes past the last cell pass in = false, n = 0.
+__device__ __forceinline__ void pool_block(uint32_t* __restrict__ blk_S, int64_t c, bool in, int n, int sp, int dy) {
+  const int lane = threadIdx.x & 31;
+  const int sp0 = __shfl_sync(0xffffffffu, sp, 0), dy0 = __shfl_sync(0xffffffffu, dy, 0);
+  const bool mixed = __ballot_sync(0xffffffffu, in && (sp != sp0 || dy != dy0)) != 0u;
+  const int r = n & 31;
+  const uint32_t tot = mixed ? 32u * (uint32_t)__popc(__ballot_sync(0xffffffffu, r > 0)) : __reduce_add_sync(0xffffffffu, (uint32_t)r);
+  if (lane == 0) blk_S[c >> 5] = ((tot + 31u) >> 5) | (mixed ? 0x80000000u : 0u);
+}
+
 template <bool INJECT>
 __global__ void count_kernel(KParams P, const double* __restrict__ day_Q, int32_t* __restrict__ cell_n,
-                             int max_daily_fish, unsigned long long* __restrict__ err) {
+                             int max_daily_fish, unsigned long long* __restrict__ err, uint32_t* __restrict__ blk_S) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= P.n_cells) return;
-  const double* sp = P.species + (int64_t)P.cell_species[c] * STRYKE_SPECIES_W;
+  const bool in = c < P.n_cells;
+  int species_c = 0, n_c = 0;
+  if (in) {
+  species_c = P.cell_species[c];
+  const double* sp = P.species + (int64_t)species_c * STRYKE_SPECIES_W;
   const int kind = (int)sp[12];
   const double shape = sp[13], loc = sp[14], scale = sp[15], max_rate = sp[16], occur = sp[17];
   uint32_t w[4], v[4];
@@ -146,6 +164,10 @@ __global__ void count_kernel(KParams P, const double* __restrict__ day_Q, int32_
     if (n > 0x7FFFFFFFll) { atomicMax(err, 0x8000000000000000ull | (unsigned long long)c); n = 0; }
   }
   cell_n[c] = (int32_t)n;
+  n_c = (int)n;
+  }
+  // (blockDim.x is a multiple of 32: a warp holds one aligned block of 32 cells; all its lanes arrive here together)
+  if (blk_S && (c & ~31ll) < P.n_cells) pool_block(blk_S, c, in, n_c, species_c, in ? P.cell_day[c] : 0);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -153,26 +175,6 @@ __global__ void count_kernel(KParams P, const double* __restrict__ day_Q, int32_
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int SCAN_T = 1024, SCAN_PER = 4, SCAN_CH = SCAN_T * SCAN_PER;
 
-// Pooled remainders (throughput kernel, population mode: most present cells hold fewer than 32 fish).  Cells are taken
-// in aligned blocks of 32; a cell of n fish keeps n >> 5 full tiles of its own, the n & 31 fish left over are laid end to
-// end with those of the other cells of its block and cut into shared tiles.  A block whose cells differ in species or
-// day ("mixed") keeps one tile per remainder instead (the day tables and species parameters are warp-uniform).  One warp
-// per block writes the block's number of shared tiles; the scans below then charge them to the first cell of the block.
-__global__ void __launch_bounds__(256) pool_kernel(const int32_t* __restrict__ cell_n, const int32_t* __restrict__ cell_species,
-                                                   const int32_t* __restrict__ cell_day, int64_t n_cells, uint32_t* __restrict__ blk_S) {
-  const int lane = threadIdx.x & 31;
-  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (b * 32 >= n_cells) return;                              // whole warps leave together
-  const int64_t c = b * 32 + lane;
-  const bool in = c < n_cells;
-  const int n = in ? cell_n[c] : 0;
-  const int sp = in ? cell_species[c] : 0, dy = in ? cell_day[c] : 0;
-  const int sp0 = __shfl_sync(0xffffffffu, sp, 0), dy0 = __shfl_sync(0xffffffffu, dy, 0);
-  const bool mixed = __ballot_sync(0xffffffffu, in && (sp != sp0 || dy != dy0)) != 0u;
-  const int r = n & 31;
-  const uint32_t tot = mixed ? 32u * (uint32_t)__popc(__ballot_sync(0xffffffffu, r > 0)) : __reduce_add_sync(0xffffffffu, (uint32_t)r);
-  if (lane == 0) blk_S[b] = ((tot + 31u) >> 5) | (mixed ? 0x80000000u : 0u);
-}
 // tiles charged to cell c of n fish: blk_S == nullptr -> one tile per started 32 fish
 __device__ __forceinline__ int64_t cell_tiles(const uint32_t* __restrict__ blk_S, int64_t c, int32_t n) {
   if (!blk_S) return (n + 31) >> 5;

@@ -176,6 +176,16 @@ class Plan:
         """Name of the passage kernel this plan launches (general / generic throughput / NVRTC-specialised)."""
         return _abi.lib().stryke_b200_plan_kernel(self._h).decode()
 
+    def time_kernel(self, enable=True):
+        """Bracket the passage kernel of every later launch with CUDA events (measurement support)."""
+        _abi.check(_abi.lib().stryke_b200_plan_time_kernel(self._h, C.c_int(1 if enable else 0)))
+
+    def kernel_ms(self):
+        """(summed passage-kernel milliseconds, launches) since the last call; waits for those launches."""
+        ms, n = C.c_double(0.0), C.c_int32(0)
+        _abi.check(_abi.lib().stryke_b200_plan_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
     def set_seed(self, seed):
         _abi.check(_abi.lib().stryke_b200_plan_set_seed(self._h, C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF)))
 

@@ -73,7 +73,7 @@ def _same(a, b):
 @pytest.mark.parametrize("order", ["engine", "shuffled", "ragged"])
 def test_pooled_remainders_equal_one_tile_per_remainder(order, monkeypatch):
     """The specialised kernel packs the n mod 32 left-over fish of the cells of a 32-cell block into shared tiles
-    (pool_kernel, passage_fast.cuh).  Same Philox counters (fish index, cell id) -> the tallies must not change, whether
+    (pool_block, passage_fast.cuh).  Same Philox counters (fish index, cell id) -> the tallies must not change, whether
     the blocks are uniform (engine order), mixed in species and day (shuffled cells: one tile per remainder) or the cell
     list is not a multiple of 32 long."""
     prj = fixtures.c3_population(n_species=5, iterations=90, days=7)
@@ -120,3 +120,28 @@ def test_pooled_remainders_next_to_a_huge_cell(monkeypatch):
     b = engine.run_cells(*args, precision=32, seed=4, max_daily_fish=10 ** 7, kernel_variant=3)
     assert a.cell_n[37] == 70_000_013 and _same(a, b)
     assert int(a.state_daily[37, 0, 1]) == 70_000_013
+
+
+def test_kernel_timing_events_cover_every_launch():
+    """stryke_b200_plan_time_kernel / plan_kernel_ms: the measurement hook bench.py's roofline uses."""
+    import torch
+    sim, plan_h = G.make_plan(fixtures.c2_facility(n_fish=200_000, iterations=4, days=2), "ktime")
+    plan = engine.Plan(plan_h.fac, plan_h.days, plan_h.species_table, plan_h.cell_day, plan_h.cell_species, plan_h.cell_id,
+                       device=0, precision=32, seed=3, max_daily_fish=10 ** 7)
+    n, d, sd = plan.allocate()
+    plan.launch(n, d, sd)                      # not timed
+    assert plan.kernel_ms() == (0.0, 0)
+    plan.time_kernel(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        plan.launch(n, d, sd)
+    e1.record()
+    ms, launches = plan.kernel_ms()
+    torch.cuda.synchronize()
+    assert launches == 3 and 0.0 < ms <= e0.elapsed_time(e1)
+    assert plan.kernel_ms() == (0.0, 0)        # forgotten after the read
+    plan.time_kernel(False)
+    plan.launch(n, d, sd)
+    assert plan.kernel_ms()[1] == 0
+    assert plan.status() == 200_000 * 8
