@@ -123,7 +123,15 @@ struct StrykePlan {
   // optional: CUDA events around every launch of the passage kernel (stryke_b200_plan_time_kernel)
   bool time_kernel = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_events;
-  ~StrykePlan() { for (auto& e : kernel_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } }
+  // large tally buffers are zeroed on a side stream while the count / scan kernels run (fork / join with two events)
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  ~StrykePlan() {
+    for (auto& e : kernel_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (aux) cudaStreamDestroy(aux);
+  }
 };
 
 namespace jit {
@@ -514,8 +522,23 @@ int stryke_b200_plan_launch(StrykePlan* pl, int32_t* d_cell_n, uint32_t* d_daily
   KParams& K = pl->K;
   K.cell_n = d_cell_n; K.daily = d_daily; K.state_daily = d_state_daily;
   if (pl->n_cells == 0) return STRYKE_OK;
-  CK(cudaMemsetAsync(d_daily, 0, (size_t)pl->n_cells * STRYKE_DAILY_W * 4, st));
-  CK(cudaMemsetAsync(d_state_daily, 0, (size_t)pl->n_cells * K.n_pairs * 2 * 4, st));
+  const size_t daily_bytes = (size_t)pl->n_cells * STRYKE_DAILY_W * 4, state_bytes = (size_t)pl->n_cells * K.n_pairs * 2 * 4;
+  const bool side = daily_bytes + state_bytes >= ((size_t)32 << 20);
+  if (side) {
+    if (!pl->aux) {
+      CK(cudaStreamCreateWithFlags(&pl->aux, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(pl->ev_fork, st));                  // after everything already queued on the caller's stream
+    CK(cudaStreamWaitEvent(pl->aux, pl->ev_fork, 0));
+    CK(cudaMemsetAsync(d_daily, 0, daily_bytes, pl->aux));
+    CK(cudaMemsetAsync(d_state_daily, 0, state_bytes, pl->aux));
+    CK(cudaEventRecord(pl->ev_join, pl->aux));
+  } else {
+    CK(cudaMemsetAsync(d_daily, 0, daily_bytes, st));
+    CK(cudaMemsetAsync(d_state_daily, 0, state_bytes, st));
+  }
   CK(cudaMemsetAsync(pl->err.p, 0, 2 * sizeof(unsigned long long), st));
   const int cb = (int)((pl->n_cells + 255) / 256);
   uint32_t* blk_S = pl->pool ? pl->blk_S.as<uint32_t>() : nullptr;      // pooled remainders: shared tiles per block of 32 cells
@@ -526,6 +549,7 @@ int stryke_b200_plan_launch(StrykePlan* pl, int32_t* d_cell_n, uint32_t* d_daily
   scan_final<<<pl->nb_scan, SCAN_T, 0, st>>>(d_cell_n, pl->n_cells, pl->part.as<int64_t>(), pl->tile_off.as<int64_t>(), pl->fish_off.as<int64_t>(), blk_S);
   g_launches += 4;
   CK(cudaGetLastError());
+  if (side) CK(cudaStreamWaitEvent(st, pl->ev_join, 0));    // the passage kernel adds into the zeroed tallies
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (pl->time_kernel) {
     CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
