@@ -107,7 +107,7 @@ struct StrykePlan {
   int64_t n_cells = 0;
   int nb_scan = 0;
   DevBuf nodes, edge_dst, moves, pair_node, ustatic, edge_cdf, node_stay, unit_coef, day_Q, species, cell_day,
-      cell_species, cell_id, tile_off, fish_off, part, err, blk_S;
+      cell_species, cell_id, tile_off, fish_off, part, err, blk_S, pareto;
   DevBuf i_fish_off, i_presence, i_count, i_z, i_dice, i_rR, i_depth, i_cause, i_route, i_grR, i_gdepth, i_gcause;
   DevBuf t_len32, t_len64, t_state, t_rate, t_surv, t_strike, t_baro;
   DevBuf fast_nodes;
@@ -274,6 +274,11 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
   CK(upload(pl->unit_coef, d->unit_coef, (size_t)d->n_days * f->n_units * STRYKE_UNIT_COEF_W));
   CK(upload(pl->day_Q, d->curr_Q, (size_t)d->n_days));
   CK(upload(pl->species, s->params, (size_t)s->n_species * STRYKE_SPECIES_W));
+  CK(pl->pareto.alloc((size_t)std::max(s->n_species, 1) * STRYKE_PARETO_W * sizeof(double)));
+  if (s->n_species > 0) {
+    pareto_constants_kernel<<<(s->n_species + 127) / 128, 128>>>(pl->species.as<double>(), s->n_species, pl->pareto.as<double>());
+    CK(cudaGetLastError());
+  }
   CK(upload(pl->cell_day, c->cell_day, (size_t)c->n_cells));
   CK(upload(pl->cell_species, c->cell_species, (size_t)c->n_cells));
   CK(upload(pl->cell_id, c->cell_id, (size_t)c->n_cells));
@@ -542,8 +547,8 @@ int stryke_b200_plan_launch(StrykePlan* pl, int32_t* d_cell_n, uint32_t* d_daily
   CK(cudaMemsetAsync(pl->err.p, 0, 2 * sizeof(unsigned long long), st));
   const int cb = (int)((pl->n_cells + 255) / 256);
   uint32_t* blk_S = pl->pool ? pl->blk_S.as<uint32_t>() : nullptr;      // pooled remainders: shared tiles per block of 32 cells
-  if (pl->inject) count_kernel<true><<<cb, 256, 0, st>>>(K, pl->day_Q.as<double>(), d_cell_n, pl->max_daily_fish, pl->err.as<unsigned long long>(), blk_S);
-  else count_kernel<false><<<cb, 256, 0, st>>>(K, pl->day_Q.as<double>(), d_cell_n, pl->max_daily_fish, pl->err.as<unsigned long long>(), blk_S);
+  if (pl->inject) count_kernel<true><<<cb, 256, 0, st>>>(K, pl->day_Q.as<double>(), d_cell_n, pl->max_daily_fish, pl->err.as<unsigned long long>(), blk_S, pl->pareto.as<double>());
+  else count_kernel<false><<<cb, 256, 0, st>>>(K, pl->day_Q.as<double>(), d_cell_n, pl->max_daily_fish, pl->err.as<unsigned long long>(), blk_S, pl->pareto.as<double>());
   scan_partial<<<pl->nb_scan, SCAN_T, 0, st>>>(d_cell_n, pl->n_cells, pl->part.as<int64_t>(), blk_S);
   scan_blocks<<<1, SCAN_T, 0, st>>>(pl->part.as<int64_t>(), pl->nb_scan);
   scan_final<<<pl->nb_scan, SCAN_T, 0, st>>>(d_cell_n, pl->n_cells, pl->part.as<int64_t>(), pl->tile_off.as<int64_t>(), pl->fish_off.as<int64_t>(), blk_S);

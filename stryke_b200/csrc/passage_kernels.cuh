@@ -97,9 +97,28 @@ __device__ __forceinline__ void pool_block(uint32_t* __restrict__ blk_S, int64_t
   if (lane == 0) blk_S[c >> 5] = ((tot + 31u) >> 5) | (mixed ? 0x80000000u : 0u);
 }
 
+// Per-species constants of the truncated Pareto draw (truncated_rvs, stryke.py:75-106): the upper truncation point, the
+// CDF there and the exponent of the inverse CDF depend on the Population row only.  Computed once per plan, on the
+// device (the same operations count_kernel would run per cell, so the counts do not change).
+constexpr int STRYKE_PARETO_W = 4;      // -1/shape, upper, F(upper), 0
+__global__ void pareto_constants_kernel(const double* __restrict__ species, int n_species, double* __restrict__ out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_species) return;
+  const double* sp = species + (int64_t)s * STRYKE_SPECIES_W;
+  const double shape = sp[13], loc = sp[14], scale = sp[15], max_rate = sp[16];
+  const bool capped = isfinite(max_rate) && max_rate > 0.0;
+  const double upper = capped ? max_rate * 10.0 : loc + fmax(1.0, scale * 1000.0);
+  const double yu = (upper - loc) / scale;
+  out[s * STRYKE_PARETO_W + 0] = -1.0 / shape;
+  out[s * STRYKE_PARETO_W + 1] = upper;
+  out[s * STRYKE_PARETO_W + 2] = yu >= 1.0 ? 1.0 - pow(yu, -shape) : 0.0;
+  out[s * STRYKE_PARETO_W + 3] = 0.0;
+}
+
 template <bool INJECT>
 __global__ void count_kernel(KParams P, const double* __restrict__ day_Q, int32_t* __restrict__ cell_n,
-                             int max_daily_fish, unsigned long long* __restrict__ err, uint32_t* __restrict__ blk_S) {
+                             int max_daily_fish, unsigned long long* __restrict__ err, uint32_t* __restrict__ blk_S,
+                             const double* __restrict__ pareto) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool in = c < P.n_cells;
   int species_c = 0, n_c = 0;
@@ -108,14 +127,14 @@ __global__ void count_kernel(KParams P, const double* __restrict__ day_Q, int32_
   const double* sp = P.species + (int64_t)species_c * STRYKE_SPECIES_W;
   const int kind = (int)sp[12];
   const double shape = sp[13], loc = sp[14], scale = sp[15], max_rate = sp[16], occur = sp[17];
-  uint32_t w[4], v[4];
+  uint32_t w[4], v[4] = {0u, 0u, 0u, 0u};
   double presence;
   if (INJECT) {
     presence = P.inj.presence[c];
   } else {
     const uint64_t id = P.cell_id[c];
     Philox::block(0xFFFFFFFFu, (uint32_t)id, (uint32_t)(id >> 32), 0u, P.seed_lo, P.seed_hi, w);
-    Philox::block(0xFFFFFFFFu, (uint32_t)id, (uint32_t)(id >> 32), 1u, P.seed_lo, P.seed_hi, v);
+    if (kind == STRYKE_ENT_LOGNORMAL) Philox::block(0xFFFFFFFFu, (uint32_t)id, (uint32_t)(id >> 32), 1u, P.seed_lo, P.seed_hi, v);
     presence = u53(w[0], w[1]);
   }
   int64_t n = 0;
@@ -126,14 +145,14 @@ __global__ void count_kernel(KParams P, const double* __restrict__ day_Q, int32_
       const bool capped = isfinite(max_rate) && max_rate > 0.0;
       double rate;
       if (kind == STRYKE_ENT_PARETO) {                           // truncated_rvs, stryke.py:75-106, :2550-2559
-        const double upper = capped ? max_rate * 10.0 : loc + fmax(1.0, scale * 1000.0);
-        const double yu = (upper - loc) / scale;
-        const double f_low = 0.0, f_high = yu >= 1.0 ? 1.0 - pow(yu, -shape) : 0.0;
+        const double* pc = pareto + species_c * STRYKE_PARETO_W;
+        const double upper = pc[1];
+        const double f_low = 0.0, f_high = pc[2];
         if (!isfinite(f_high) || f_high - f_low < 1e-12) {
           rate = upper;
         } else {
           const double q = INJECT ? P.inj.count_draw[c] : f_low + (f_high - f_low) * u53(w[2], w[3]);
-          rate = loc + scale * pow(1.0 - q, -1.0 / shape);       // scipy pareto._ppf
+          rate = loc + scale * pow(1.0 - q, pc[0]);              // scipy pareto._ppf
         }
       } else if (kind == STRYKE_ENT_LOGNORMAL) {                 // scipy lognorm._rvs = exp(s*Z), stryke.py:2563
         double z;
