@@ -145,3 +145,23 @@ def test_kernel_timing_events_cover_every_launch():
     plan.launch(n, d, sd)
     assert plan.kernel_ms()[1] == 0
     assert plan.status() == 200_000 * 8
+
+
+@pytest.mark.parametrize("fixture,kw", [("c5_cascade", dict(n_fish=1037, iterations=40, days=2)),            # 41 pairs: two pair rows per lane
+                                        ("c5_cascade", dict(n_fish=333, iterations=50, days=2, dams=7)),
+                                        ("c4_barotrauma", dict(n_fish=777, iterations=50, days=2)),          # barotrauma words
+                                        ("cabot_station", dict(iterations=40, days=3, seed=2, fish=555.0)),  # 13 nodes in one level
+                                        ("c1_single_unit", dict(iterations=60, days=20, fish=45.0))])
+def test_pooled_remainders_on_other_facilities(fixture, kw, monkeypatch):
+    """Pooling with more than 32 (move, node) pairs (several counters per lane in the accumulator flush), multi-word
+    levels and barotrauma levels: identical to the general kernel."""
+    sim, plan = G.make_plan(getattr(fixtures, fixture)(**kw), "poolfac")
+    ref = run(plan, 1)
+    monkeypatch.setenv("STRYKE_B200_POOL", "1")
+    monkeypatch.setenv("STRYKE_B200_JIT", "1")
+    pooled = run(plan, 3)
+    assert ref.cell_n.sum() > 0 and _same(ref, pooled)
+    if fixture == "c5_cascade" and "dams" not in kw:
+        p = engine.Plan(plan.fac, plan.days, plan.species_table, plan.cell_day, plan.cell_species, plan.cell_id, device=0,
+                        precision=32, seed=9, max_daily_fish=2_000_000_000, kernel_variant=3)
+        assert "pooled" in p.kernel() and plan.fac.n_pairs > 32
