@@ -239,13 +239,19 @@ def main():
         flush_buf.fill_(i & 0xff)
     torch.cuda.synchronize()
     fish_per_step = plan.status()
+    sampler = ClockSampler(local_rank)      # NVML set-up takes a few ms and differs from process to process: before the barrier
+    sampler.start()
+    plan.time_kernel(True)       # CUDA events around the passage kernel of every timed launch, on the launch stream
+    align = torch.zeros(1, device=f"cuda:{local_rank}")
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    plan.time_kernel(True)       # CUDA events around the passage kernel of every timed launch, on the launch stream
+    sampler.sm.clear()           # keep only the samples taken during the timed region
     launches0 = engine.launch_count()
+    if world > 1:
+        # device-side start line (untimed): the ranks' host threads leave the barrier a few ms apart; without this the
+        # earliest rank's first step would contain that host skew as time spent waiting in the first all-reduce
+        dist.all_reduce(align)
     evs = []
     for i in range(args.steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -337,6 +343,24 @@ def main():
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "how": "stryke_b200_run through ctypes: host tables in, count+scan+passage kernels, host tallies out; wall clock"}
 
+    # ---- every rank's own figures (a straggling GPU shows up here; the headline uses the max over ranks) -----------
+    clocks = sampler.summary()
+    per_rank = None
+    if world > 1:
+        names = ClockSampler.NAMES
+        mine = torch.tensor([ms / args.steps, kernel_ms / max(kernel_n, 1), clocks["sm_mhz"] or 0.0,
+                             float(sum(1 << i for i, nm in enumerate(names) if nm in clocks["reasons"]))],
+                            dtype=torch.float64, device=f"cuda:{local_rank}")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rows = [[float(x) for x in t.tolist()] for t in allr]
+        per_rank = {"step_ms": [r[0] for r in rows], "kernel_ms": [r[1] for r in rows], "sm_mhz": [r[2] for r in rows]}
+        bits = 0
+        for r in rows:
+            bits |= int(r[3])
+        clocks = dict(clocks, sm_mhz=min(r[2] for r in rows), reasons=[nm for i, nm in enumerate(names) if bits >> i & 1],
+                      note="sm_mhz = lowest per-rank median, reasons = union over ranks")
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         rate, done, dt, desc = cpu_port_rate(args.workload, nproc, seed=5, scale=2)
@@ -353,7 +377,9 @@ def main():
                            "fish_passages_per_step": fish_all, "cells_per_gpu": plan.n_cells, "kernel": plan.kernel(),
                            "collective": "one NCCL all_reduce(sum) of the flat tally buffer (cell_n + Daily + State_Daily) per step" if world > 1 else "none"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": sampler.summary()}
+                "clocks": clocks}
+        if per_rank:
+            line["per_rank"] = per_rank
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
