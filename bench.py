@@ -282,6 +282,8 @@ def main():
     peak_ops, cal_ms = engine.calibrate_issue(local_rank, stream.cuda_stream)
     algo = ALGO_LANE_OPS[args.workload]
     per_gpu_rate = fish_per_step * args.steps / (ms_total * 1e-3)
+    if kernel_n <= 0 or kernel_ms <= 0.0:      # (cannot happen with the in-tree library; keeps the line printable)
+        kernel_ms, kernel_n = ms, args.steps
     achieved = fish_per_step * kernel_n / (kernel_ms * 1e-3) * algo      # this rank's passage kernel alone
     traffic = None
     prof = os.path.join(ROOT, "profiles", "r01_c3_passage_metrics.json" if args.workload == "c3" else "r01_passage_metrics.json")
