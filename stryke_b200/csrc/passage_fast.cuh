@@ -153,10 +153,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
     s_species[i] = (float)P.species[(i / SPW) * STRYKE_SPECIES_W + (i % SPW)];
   __syncthreads();
 
-  // Work distribution: chunks of P.chunk_tiles consecutive tiles handed out through one global counter (the first
-  // chunk of every warp is its own global index, later ones come from the counter).  The SM's warp arbiter does not
-  // share issue slots evenly, so equal static ranges finish unevenly and leave the SM short of warps at the end.
-  int cur_day = -1, cur_species = -1;
+  int cur_day = -1, cur_species = -1;                 // what the staged day tables / the species registers hold
   float sp_ls = 0, sp_ll = 0, sp_lsc = 0, sp_lm = 0, sp_lsd = 0, sp_wr = 0, sp_uc = 0, sp_d1 = 0, sp_dd = 0, sp_b0 = 0, sp_b1 = 0;
   int sp_mode = 0;
   uint32_t acc_suc[PR], acc_cnt[PR], acc_daily = 0;
@@ -466,6 +463,8 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   };
 
   const int64_t T = P.tile_off[P.n_cells];
+  // Work distribution.  The SM's warp arbiter does not share issue slots evenly, so equal static ranges finish unevenly and
+  // leave the SM short of warps at the end; tiles are therefore handed out dynamically.
   // Guided self-scheduling: a warp takes (tiles not yet handed out) / (2 x warps of the grid) consecutive tiles from one
   // global counter, at most P.chunk_tiles and at least P.chunk_min: long chunks while there is plenty of work (one cell
   // search per chunk), short ones at the end so that all warps finish together.  The next chunk is fetched while the
