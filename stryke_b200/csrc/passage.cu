@@ -30,6 +30,9 @@
 #include <vector>
 
 #include <dlfcn.h>
+#include <errno.h>
+#include <sys/stat.h>
+#include <sys/types.h>
 #include <unistd.h>
 
 #include <fstream>

@@ -220,6 +220,18 @@ static std::string generate(const std::vector<MoveRec>& moves, const std::vector
   return o.str();
 }
 
+// mkdir -p (no shell): true when the directory exists afterwards
+static bool make_dirs(const std::string& dir) {
+  for (size_t i = 1; i <= dir.size(); ++i) {
+    if (i == dir.size() || dir[i] == '/') {
+      const std::string part = dir.substr(0, i);
+      if (mkdir(part.c_str(), 0755) != 0 && errno != EEXIST) return false;
+    }
+  }
+  struct stat st;
+  return stat(dir.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+
 // nullptr + message on failure
 static const std::vector<char>* compile(const std::string& src, std::string* err, bool fresh) {
   std::lock_guard<std::mutex> lock(g_mu);
@@ -278,7 +290,7 @@ static const std::vector<char>* compile(const std::string& src, std::string* err
   std::vector<char> bin(n);
   a.cubin(prog, bin.data());
   a.destroy(&prog);
-  if (system(("mkdir -p '" + dir + "' 2>/dev/null").c_str()) == 0) {      // best effort; a read-only home is fine
+  if (make_dirs(dir)) {      // best effort; a read-only home is fine
     const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
     std::ofstream f(tmp, std::ios::binary);
     if (f && f.write(bin.data(), (std::streamsize)bin.size())) { f.close(); rename(tmp.c_str(), path.c_str()); }
