@@ -145,9 +145,13 @@ EXTREME_SPECIES = dict(Species="Perca", **{"Common Name": "Yellow Perch"}, dist=
                        beta_1=3.41, U_crit=1.3, **{"length shape": 0.45, "length location": 0.0, "length scale": 11.0})
 
 
-def c3_population(n_species=4, iterations=2, days=5, curr_Q=9000.0, scenarios=("Spring",), baro=False, extreme=False):
+def c3_population(n_species=4, iterations=2, days=5, curr_Q=9000.0, scenarios=("Spring",), baro=False, extreme=False,
+                  facility_scenario_column=True):
     """C2's facility in population mode: daily counts drawn from EPRI-fitted Pareto / Log Normal / Weibull
-    (``extreme=True`` appends a species with a generalised-extreme-value rate)."""
+    (``extreme=True`` appends a species with a generalised-extreme-value rate).  Several ``scenarios`` share one
+    hydrograph scaled through ``Prorate``; with ``facility_scenario_column=False`` the Facilities table has ONE row per
+    facility and no ``Scenario`` column — the only layout with which the reference itself runs more than one flow
+    scenario (it takes the ``else`` branches at stryke.py:2359 and :2941; with one row per scenario it stops at :2759)."""
     prj = c2_facility(1, iterations, days, curr_Q, baro=baro, scenario=scenarios[0])
     prj["name"] = "c3"
     pop = []
@@ -178,7 +182,10 @@ def c3_population(n_species=4, iterations=2, days=5, curr_Q=9000.0, scenarios=("
     if len(scenarios) > 1:   # one hydrograph, scaled per scenario through Prorate (x0.5 .. x2)
         for r, k in zip(prj["flow_scenarios"], np.linspace(0.5, 2.0, len(scenarios))):
             r["Prorate"] = float(k)
-    prj["facility_params"] = [dict(prj["facility_params"][0], Scenario=s) for s in scenarios]
+    if facility_scenario_column:
+        prj["facility_params"] = [dict(prj["facility_params"][0], Scenario=s) for s in scenarios]
+    else:
+        prj["facility_params"] = [{k: v for k, v in prj["facility_params"][0].items() if k != "Scenario"}]
     prj["operating_scenarios"] = [dict(r, Scenario=s) for s in scenarios for r in prj["operating_scenarios"][:3]]
     return prj
 

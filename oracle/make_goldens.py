@@ -32,8 +32,12 @@ CASES = {
     "c2_normal_lengths": ("c2_facility", dict(n_fish=200, iterations=1, days=2, length_normal=(11.0, 3.5)), 12, {}),
     "c2_penstock": ("c2_facility", dict(n_fish=200, iterations=1, days=3, curr_Q=6500.0, penstock=True), 13, {}),
     "c2_zero_flow": ("c2_facility", dict(n_fish=80, iterations=1, days=4, flows=[0.0, 250.0, 9000.0, 0.0]), 14, {}),
-    # (no multi-scenario case: with one Facilities row per scenario — the layout of the reference's own Bad Creek example —
-    #  the reference stops at stryke.py:2759 with "float() argument must be ... not 'Series'")
+    # several flow scenarios (BASELINE.json configs[2] "x 5 flow scenarios"): the Facilities table has no Scenario column, the
+    # layout with which the reference runs them (else-branches stryke.py:2359, :2941; close() neutralised, Appendix E1).  With
+    # one Facilities row per scenario — the layout of its own Bad Creek example — it stops at stryke.py:2759 (float(Series)).
+    "c3_multi_scenario": ("c3_population", dict(n_species=3, iterations=2, days=5, scenarios=["Spring", "Summer", "Fall"],
+                                                facility_scenario_column=False), 21,
+                          {"Ambloplites": "Centrarchidae", "Micropterus": "Centrarchidae"}),
     "c2_low_flow": ("c2_facility", dict(n_fish=120, iterations=1, days=3, curr_Q=600.0), 7, {}),
     # the reference's own complex-network example workbook (tables extracted by oracle/extract_example.py)
     "cabot_station": ("cabot_station", dict(iterations=2, days=24, seed=0), 8, {"Micropterus": "Centrarchidae"}),

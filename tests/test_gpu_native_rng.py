@@ -148,6 +148,63 @@ def test_daily_entrainment_count_distribution_ks():
     assert worst[-1] > ALPHA / len(tests), worst
 
 
+def test_five_flow_scenarios_match_the_oracle_distribution():
+    """BASELINE.json configs[2] runs 5 flow scenarios (one hydrograph x 0.5 .. 2 through Prorate): per (scenario, species,
+    day) the tallies summed over the iterations, device (native Philox) against the oracle's own NumPy stream — presence
+    frequency, total fish, routing at the forebay, survival per (move, node) and the Daily columns."""
+    names = ["S050", "S075", "S100", "S150", "S200"]
+    prj = fixtures.c3_population(n_species=3, iterations=300, days=3, scenarios=names, facility_scenario_column=False)
+    sim, plan = G.make_plan(prj, "five_scen")
+    assert len(plan.groups) == 15 and len({g.scen_index for g in plan.groups}) == 5
+    res = native(plan, precision=32, cap=10 ** 7)
+    ref = oracle_cells(prj, None)
+    ref_idx = G.reference_cell_index(plan)
+    assert len(ref) == plan.n_cells
+    P = plan.fac.n_pairs
+    key_of = lambda r: (r["scenario"], r["species"], r["day"])
+    agg_ref, agg_dev = {}, {}
+    for c, r in enumerate(ref_idx):
+        k = key_of(ref[r])
+        a = agg_ref.setdefault(k, dict(present=0, cells=0, daily=np.zeros(7, np.int64), sd={}))
+        a["cells"] += 1
+        a["present"] += int(ref[r]["daily"][0] > 0)
+        a["daily"] += ref[r]["daily"]
+        for kk, (su, cn) in ref[r]["state_daily"].items():
+            x = a["sd"].setdefault(kk, [0, 0]); x[0] += su; x[1] += cn
+        b = agg_dev.setdefault(k, dict(present=0, cells=0, daily=np.zeros(7, np.int64), sd={}))
+        b["cells"] += 1
+        b["present"] += int(res.cell_n[c] > 0)
+        b["daily"] += G.full_daily(res.cell_n[c], res.daily[c])
+        for kk, (su, cn) in G.state_daily_dict(plan, res.state_daily[c]).items():
+            x = b["sd"].setdefault(kk, [0, 0]); x[0] += su; x[1] += cn
+    # the scenarios really differ: the discharge of scenario j is the hydrograph x Prorate
+    q_by_scen = {g.scenario: plan.days.curr_Q[g.day0] for g in plan.groups}
+    assert len(set(np.round(list(q_by_scen.values()), 6))) == 5
+    tests = []
+    occur = {p["Species"]: p["occur_prob"] for p in prj["population"]}
+    for k, a in agg_ref.items():
+        b = agg_dev[k]
+        tests.append(("presence", k, stats.binomtest(b["present"], b["cells"], occur[k[1]]).pvalue))
+        for kk in set(a["sd"]) | set(b["sd"]):
+            (s1, n1), (s2, n2) = b["sd"].get(kk, (0, 0)), a["sd"].get(kk, (0, 0))
+            if n1 + n2 >= 200 and 0 < s1 + s2 < n1 + n2 and n1 > 0 and n2 > 0:
+                tests.append(("surv", k, kk, stats.chi2_contingency(np.array([[s1, n1 - s1], [s2, n2 - s2]]), correction=False)[1]))
+        nodes = sorted({nd for (mv, nd) in set(a["sd"]) | set(b["sd"]) if mv == 2})
+        tab = np.array([[b["sd"].get((2, nd), (0, 0))[1] for nd in nodes], [a["sd"].get((2, nd), (0, 0))[1] for nd in nodes]])
+        tab = tab[:, tab.sum(axis=0) >= 10]
+        if tab.shape[1] > 1 and tab.sum(axis=1).min() > 0:
+            tests.append(("route", k, stats.chi2_contingency(tab)[1]))
+        g7, w7 = b["daily"], a["daily"]
+        for j in (1, 2, 5):
+            if g7[0] > 0 and w7[0] > 0 and 0 < g7[j] + w7[j] < g7[0] + w7[0]:
+                tests.append(("daily", k, j, stats.chi2_contingency(np.array([[g7[j], g7[0] - g7[j]], [w7[j], w7[0] - w7[j]]]), correction=False)[1]))
+    # total fish per (scenario, species): KS of the per-cell counts pooled over days is covered by
+    # test_daily_entrainment_count_distribution_ks; here the scenario's discharge must scale the counts (stryke.py:2585)
+    assert len(tests) > 60
+    worst = min(tests, key=lambda t: t[-1])
+    assert worst[-1] > ALPHA / len(tests), (worst, len(tests))
+
+
 def test_results_do_not_depend_on_partition_or_grid():
     """Philox is keyed by (seed, cell id, fish, slot): any subset of cells, in any launch geometry, gives the same
     tallies — the property the multi-GPU sharding relies on."""

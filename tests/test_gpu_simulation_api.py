@@ -39,7 +39,8 @@ def fresh_sim(prj, tmp_path, name):
 
 
 @pytest.mark.parametrize("case", ["c2_kaplan_francis", "c2_barotrauma", "c5_cascade", "c3_population", "c1_single_unit",
-                                  "c2_low_flow", "c4_propeller_baro", "cabot_station", "cabot_station_fish", "example_v250304", "c3_extreme", "c2_normal_lengths", "c2_penstock", "c2_zero_flow"])
+                                  "c2_low_flow", "c4_propeller_baro", "cabot_station", "cabot_station_fish", "example_v250304", "c3_extreme", "c2_normal_lengths", "c2_penstock", "c2_zero_flow",
+                                  "c3_multi_scenario"])
 def test_run_with_injected_uniforms_writes_the_reference_frames(case, tmp_path):
     g = Golden(case)
     sim = fresh_sim(g.prj, tmp_path, case)
@@ -62,6 +63,7 @@ def test_run_with_injected_uniforms_writes_the_reference_frames(case, tmp_path):
     ref_daily = np.stack([g.ref(ci, "daily") for ci in range(len(g.cells))])
     assert np.array_equal(daily[DAILY_COLS].to_numpy(dtype=np.int64), ref_daily)
     assert [s.strip() for s in daily["species"]] == [cm["species"] for cm in g.cells]
+    assert [s.strip() for s in daily["scenario"]] == [cm["scenario"] for cm in g.cells]
     assert list(daily["iteration"]) == [cm["iteration"] for cm in g.cells]
     assert [str(d) for d in daily["day"]] == [cm["day"] for cm in g.cells]
     assert np.allclose(daily["flow"].to_numpy(), [cm["curr_Q"] for cm in g.cells], rtol=0, atol=0)
