@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define STRYKE_B200_ABI_VERSION 1
+#define STRYKE_B200_ABI_VERSION 2
 
 /* error codes */
 #define STRYKE_OK            0
@@ -93,12 +93,29 @@ typedef struct StrykeSpeciesTable {
   const double* params;      /* [n_species][STRYKE_SPECIES_W] */
 } StrykeSpeciesTable;
 
-/* The cells to simulate: one entry per (scenario, species, iteration, day) with tot_hours > 0. */
+/* One (scenario, species) group of an implicit cell list: the reference's loops `for i in range(iterations)` x
+ * `for day in flow_df` (stryke.py:2897-2902) for one Population row.  Cell cell0 + d * iterations + i is iteration i on the
+ * group's d-th day with tot_hours > 0; that day is row day0 + active_days[active_off + d] of StrykeDayTables and the
+ * cell's Philox id is (id_base + i) * id_days + active_days[active_off + d] + id_add. */
+typedef struct StrykeCellGroup {
+  int64_t  cell0;
+  int32_t  iterations, n_active_days, day0, species, active_off, reserved;
+  uint64_t id_base;
+} StrykeCellGroup;
+
+/* The cells to simulate: one entry per (scenario, species, iteration, day) with tot_hours > 0 — either three explicit
+ * arrays, or (cell_day == NULL) the group table above: a year of 1000 iterations x 20 species x 5 scenarios is then a few
+ * KB instead of 16 bytes per cell crossing PCIe on every call. */
 typedef struct StrykeCells {
   int64_t n_cells;
   const int32_t*  cell_day;      /* [n_cells] index into StrykeDayTables                                   */
   const int32_t*  cell_species;  /* [n_cells] index into StrykeSpeciesTable                                */
   const uint64_t* cell_id;       /* [n_cells] logical id mixed into the Philox counter (partition-independent) */
+  int32_t n_groups;              /* implicit list: groups ordered by cell0, covering [0, n_cells)           */
+  int32_t n_active;              /* length of active_days                                                   */
+  const StrykeCellGroup* groups;
+  const int32_t* active_days;
+  uint64_t id_days, id_add;
 } StrykeCells;
 
 /* Injected draws (bit-exact replay of the reference's numpy uniforms).  All pointers are
@@ -144,7 +161,14 @@ typedef struct StrykeOpts {
   int32_t  kernel_variant;      /* 0 = auto; 1 = general passage_kernel; 2 = throughput kernel, generic tables (ahead-of-time);
                                    3 = throughput kernel specialised for the facility with NVRTC (error if unavailable).
                                    auto: fp32 + native RNG + no trace -> throughput kernel, specialised when the run is large */
+  int32_t  rng_mode;            /* native stream: 0 = compact word budget (16/23-bit centred uniforms, one cause uniform; all kernels);
+                                   1 = wide: every draw a 53-bit uniform of its own, Box-Muller from two of them, the reference's
+                                   sequential cause rolls (stryke.py:1545-1560) — fp64 general kernel only; the arbiter the
+                                   throughput kernels are checked against at 1e10 fish (tests/test_gpu_high_power.py) */
+  uint32_t flags;               /* STRYKE_FLAG_* */
 } StrykeOpts;
+
+#define STRYKE_FLAG_NO_PROMOTE 1u   /* keep a drawn count of 0 (population_sim itself, stryke.py:2596-2618; run() promotes it to 1, :3032) */
 
 /* Host-side result buffers, caller-allocated. */
 typedef struct StrykeTallies {
@@ -152,6 +176,32 @@ typedef struct StrykeTallies {
   uint32_t* daily;         /* [n_cells][STRYKE_DAILY_W]                                                     */
   uint32_t* state_daily;   /* [n_cells][n_pairs][2] successes, count (stryke.py:3302-3351)                   */
 } StrykeTallies;
+
+/* Compact tallies: one row per cell that holds fish (nothing for a species absent that day, stryke.py:3392-3426), 16-bit
+ * counters wherever the cell's population allows.  A slot is row_w = n_pairs + 3 uint32 words.
+ *   narrow cell (pop_size <= narrow_max), ONE slot:  w0 = pop_size | mortality_barotrauma << 16,
+ *       w1 = num_entrained | num_survived << 16,  w2 = mortality_impingement | mortality_blade_strike << 16,
+ *       w[3 + p] = successes_p | count_p << 16   (State_Daily of reachable pair p, stryke.py:3302-3351)
+ *   wide cell, TWO slots:  w0 = pop_size, w1..w5 = num_entrained, num_survived, mortality_impingement, _blade_strike,
+ *       _barotrauma, w[6 + 2p] = successes_p, w[7 + 2p] = count_p
+ * Cells are taken in aligned blocks of 32: blk_row[b] = slot of the block's first present cell, bit j of blk_mask[b] =
+ * cell 32 b + j holds fish, bit j of blk_wide[b] = it uses the wide layout.  The slot of cell 32 b + j is
+ * blk_row[b] + popcount(blk_mask[b] & ((1 << j) - 1)) + popcount(blk_wide[b] & ((1 << j) - 1)).
+ * HOST buffers for stryke_b200_run_compact (pinned memory lets the copies overlap the kernels). */
+typedef struct StrykeCompact {
+  int64_t   n_blocks;       /* (n_cells + 31) / 32                                                            */
+  uint32_t* blk_row;        /* [n_blocks]                                                                     */
+  uint32_t* blk_mask;       /* [n_blocks]                                                                     */
+  uint32_t* blk_wide;       /* [n_blocks]                                                                     */
+  uint32_t* rows;           /* [rows_cap][row_w]                                                              */
+  int64_t   rows_cap;       /* slots the caller allocated                                                     */
+  int64_t   n_slots;        /* out: slots used (if > rows_cap the call fails with STRYKE_E_ARG and says so)  */
+  int64_t   n_fish;         /* out: fish simulated                                                            */
+  int32_t   row_w;          /* out: n_pairs + 3                                                               */
+  int32_t   narrow_max;     /* out: largest pop_size kept in the narrow layout                                */
+  int32_t   n_slabs;        /* in: cut the cell list into this many launches so that the device->host copy of one slab's
+                               rows runs under the next slab's kernels (0 = choose)                           */
+} StrykeCompact;
 
 typedef struct StrykePlan StrykePlan;
 
@@ -165,12 +215,30 @@ uint64_t stryke_b200_launch_count(void);     /* kernels launched by this library
 int stryke_b200_run(const StrykeFacility* fac, const StrykeDayTables* days, const StrykeSpeciesTable* species,
                     const StrykeCells* cells, const StrykeOpts* opts, StrykeTallies* out);
 
+/* One-shot with compact host results: the production form of stryke_b200_run for population-mode projects (millions of
+ * cells of a few dozen fish).  out->cell_n of `tallies` is not needed: pop_size rides in the rows. */
+int stryke_b200_run_compact(const StrykeFacility* fac, const StrykeDayTables* days, const StrykeSpeciesTable* species,
+                            const StrykeCells* cells, const StrykeOpts* opts, StrykeCompact* out);
+
 /* Plan API: tables stay resident in HBM; tallies live in caller-owned DEVICE buffers (e.g. torch tensors that are
  * then all-reduced with NCCL); launches are asynchronous on `stream` (a cudaStream_t, 0 = legacy default). */
 int stryke_b200_plan_create(const StrykeFacility* fac, const StrykeDayTables* days, const StrykeSpeciesTable* species,
                             const StrykeCells* cells, const StrykeOpts* opts, StrykePlan** plan);
 int stryke_b200_plan_launch(StrykePlan* plan, int32_t* d_cell_n, uint32_t* d_daily, uint32_t* d_state_daily,
                             void* stream);
+/* Same hot path with compact rows (see StrykeCompact), for cells [cell_lo, cell_hi) of the plan (cell_lo a multiple of
+ * 256; cell_hi = -1: to the end).  d_rows holds rows_cap slots; the per-block tables live in the plan
+ * (stryke_b200_plan_compact_tables).  Slots continue from the previous range when first_slot < 0, else start at first_slot.
+ * d_slots_after (device, may be NULL) receives the slot count after this range — what a caller that overlaps the copy of one
+ * range with the kernels of the next needs to know.  Ranges of one pass go to ONE stream, in order.
+ * Rows are zeroed by the launch itself: no memset, no read-modify-write of untouched cells. */
+int stryke_b200_plan_launch_compact(StrykePlan* plan, int64_t cell_lo, int64_t cell_hi, int32_t* d_cell_n, uint32_t* d_rows,
+                                    int64_t rows_cap, int64_t first_slot, uint64_t* d_slots_after, void* stream);
+/* DEVICE pointers of the plan's per-block tables [n_blocks] and the row geometry. */
+int stryke_b200_plan_compact_tables(StrykePlan* plan, uint32_t** d_blk_row, uint32_t** d_blk_mask, uint32_t** d_blk_wide,
+                                    int32_t* row_w, int32_t* narrow_max);
+/* Slots and fish counted so far by the launches on `stream` (syncs the stream). */
+int stryke_b200_plan_compact_totals(StrykePlan* plan, void* stream, int64_t* n_slots, int64_t* n_fish);
 const char* stryke_b200_plan_kernel(const StrykePlan* plan);      /* which passage kernel the plan will launch */
 int stryke_b200_set_source_dir(const char* dir);                 /* directory holding passage_fast.cuh / passage_common.cuh (run-time specialisation) */
 int stryke_b200_jit_selftest(void);                              /* compiles a specialised kernel with NVRTC; needs no GPU */

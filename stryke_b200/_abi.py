@@ -18,6 +18,8 @@ ENT = {"fixed": 0, "Pareto": 1, "Log Normal": 2, "Weibull": 3, "Extreme": 4}
 UNIT_STATIC_W, UNIT_COEF_W, SPECIES_W, DAILY_W = 4, 8, 20, 5
 MAX_NODES, MAX_UNITS, MAX_EDGES, MAX_MOVES, MAX_PAIRS = 255, 64, 1024, 64, 128
 E_MAX_FISH, E_NOGPU = -4, -5
+FLAG_NO_PROMOTE = 1
+ABI_VERSION = 2
 
 _p = C.c_void_p
 
@@ -37,8 +39,26 @@ class SpeciesTable(C.Structure):
     _fields_ = [("n_species", C.c_int32), ("params", _p)]
 
 
+class CellGroup(C.Structure):
+    _fields_ = [("cell0", C.c_int64), ("iterations", C.c_int32), ("n_active_days", C.c_int32), ("day0", C.c_int32),
+                ("species", C.c_int32), ("active_off", C.c_int32), ("reserved", C.c_int32), ("id_base", C.c_uint64)]
+
+
+GROUP_DTYPE = np.dtype([("cell0", np.int64), ("iterations", np.int32), ("n_active_days", np.int32), ("day0", np.int32),
+                        ("species", np.int32), ("active_off", np.int32), ("reserved", np.int32), ("id_base", np.uint64)])
+assert GROUP_DTYPE.itemsize == C.sizeof(CellGroup) == 40
+
+
 class Cells(C.Structure):
-    _fields_ = [("n_cells", C.c_int64), ("cell_day", _p), ("cell_species", _p), ("cell_id", _p)]
+    _fields_ = [("n_cells", C.c_int64), ("cell_day", _p), ("cell_species", _p), ("cell_id", _p),
+                ("n_groups", C.c_int32), ("n_active", C.c_int32), ("groups", _p), ("active_days", _p),
+                ("id_days", C.c_uint64), ("id_add", C.c_uint64)]
+
+
+class Compact(C.Structure):
+    _fields_ = [("n_blocks", C.c_int64), ("blk_row", _p), ("blk_mask", _p), ("blk_wide", _p), ("rows", _p),
+                ("rows_cap", C.c_int64), ("n_slots", C.c_int64), ("n_fish", C.c_int64), ("row_w", C.c_int32),
+                ("narrow_max", C.c_int32), ("n_slabs", C.c_int32)]
 
 
 class Injected(C.Structure):
@@ -55,7 +75,7 @@ class Trace(C.Structure):
 class Opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("precision", C.c_int32), ("seed", C.c_uint64), ("max_daily_fish", C.c_int32),
                 ("blocks_per_sm", C.c_int32), ("injected", C.POINTER(Injected)), ("trace", C.POINTER(Trace)),
-                ("kernel_variant", C.c_int32)]
+                ("kernel_variant", C.c_int32), ("rng_mode", C.c_int32), ("flags", C.c_uint32)]
 
 
 class Tallies(C.Structure):
@@ -88,6 +108,10 @@ def lib():
     L.stryke_b200_run.argtypes = [P(Facility), P(DayTables), P(SpeciesTable), P(Cells), P(Opts), P(Tallies)]
     L.stryke_b200_plan_create.argtypes = [P(Facility), P(DayTables), P(SpeciesTable), P(Cells), P(Opts), P(_p)]
     L.stryke_b200_plan_launch.argtypes = [_p, _p, _p, _p, _p]
+    L.stryke_b200_run_compact.argtypes = [P(Facility), P(DayTables), P(SpeciesTable), P(Cells), P(Opts), P(Compact)]
+    L.stryke_b200_plan_launch_compact.argtypes = [_p, C.c_int64, C.c_int64, _p, _p, C.c_int64, C.c_int64, _p, _p]
+    L.stryke_b200_plan_compact_tables.argtypes = [_p, P(_p), P(_p), P(_p), P(C.c_int32), P(C.c_int32)]
+    L.stryke_b200_plan_compact_totals.argtypes = [_p, _p, P(C.c_int64), P(C.c_int64)]
     L.stryke_b200_plan_set_seed.argtypes = [_p, C.c_uint64]
     L.stryke_b200_plan_kernel.argtypes = [_p]
     L.stryke_b200_plan_kernel.restype = C.c_char_p
@@ -103,7 +127,7 @@ def lib():
     L.stryke_b200_baro_survival.argtypes = [C.c_int64, _p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, _p]
     L.stryke_b200_philox.argtypes = [C.c_int64, _p, _p, C.c_int, _p]
     L.stryke_b200_calibrate_issue.argtypes = [C.c_int, _p, P(C.c_double), P(C.c_double)]
-    for name in ("run", "plan_create", "plan_launch", "plan_set_seed", "plan_status", "plan_fetch_trace", "plan_destroy",
+    for name in ("run_compact", "plan_launch_compact", "plan_compact_tables", "plan_compact_totals", "run", "plan_create", "plan_launch", "plan_set_seed", "plan_status", "plan_fetch_trace", "plan_destroy",
                  "plan_time_kernel", "plan_kernel_ms",
                  "strike_survival", "baro_survival", "philox", "calibrate_issue"):
         getattr(L, "stryke_b200_" + name).restype = C.c_int
@@ -112,7 +136,8 @@ def lib():
     return L
 
 
-EXPORTS = ["stryke_b200_last_error", "stryke_b200_abi_version", "stryke_b200_device_count", "stryke_b200_launch_count",
+EXPORTS = ["stryke_b200_run_compact", "stryke_b200_plan_launch_compact", "stryke_b200_plan_compact_tables",
+           "stryke_b200_plan_compact_totals", "stryke_b200_last_error", "stryke_b200_abi_version", "stryke_b200_device_count", "stryke_b200_launch_count",
            "stryke_b200_run", "stryke_b200_plan_create", "stryke_b200_plan_launch", "stryke_b200_plan_kernel", "stryke_b200_set_source_dir", "stryke_b200_jit_selftest", "stryke_b200_plan_set_seed", "stryke_b200_plan_status",
            "stryke_b200_plan_fetch_trace", "stryke_b200_plan_destroy", "stryke_b200_plan_time_kernel", "stryke_b200_plan_kernel_ms", "stryke_b200_strike_survival",
            "stryke_b200_baro_survival", "stryke_b200_philox", "stryke_b200_calibrate_issue", "stryke_b200_bootstrap_means"]

@@ -108,9 +108,13 @@ struct StrykePlan {
   int n_species_staged = 0, pr = 1;
   size_t smem = 0;
   int64_t n_cells = 0;
-  int nb_scan = 0;
   DevBuf nodes, edge_dst, moves, pair_node, ustatic, edge_cdf, node_stay, unit_coef, day_Q, species, cell_day,
-      cell_species, cell_id, tile_off, fish_off, part, err, blk_S, pareto;
+      cell_species, cell_id, tile_off, fish_off, err, blk_S, pareto;
+  DevBuf groups, active_days, blk_tile, blk_row, blk_mask, blk_wide, scan_flag, scan_agg, scan_incl;
+  unsigned int epoch = 0;     // launch number: tags the look-back flags of count_kernel
+  int n_days = 0, n_species = 0, row_w = 0, narrow_max = 0;
+  int64_t last_rows_cap = -1;  // capacity of the last compact launch (-1: dense)
+  bool attr_set = false;      // cudaFuncAttributeMaxDynamicSharedMemorySize applied to this plan's passage kernel
   DevBuf i_fish_off, i_presence, i_count, i_z, i_dice, i_rR, i_depth, i_cause, i_route, i_grR, i_gdepth, i_gcause;
   DevBuf t_len32, t_len64, t_state, t_rate, t_surv, t_strike, t_baro;
   DevBuf fast_nodes;
@@ -164,6 +168,8 @@ static int validate(const StrykeFacility* f, const StrykeDayTables* d, const Str
   if (f->start_node < 0 || f->start_node >= f->n_nodes) return fail(STRYKE_E_ARG, "start_node out of range");
   if (d->n_days < 1 || s->n_species < 1 || c->n_cells < 0) return fail(STRYKE_E_ARG, "empty day/species/cell tables");
   if (o->precision != 32 && o->precision != 64) return fail(STRYKE_E_ARG, "precision must be 32 or 64");
+  if (o->rng_mode != 0 && o->rng_mode != 1) return fail(STRYKE_E_ARG, "rng_mode must be 0 or 1");
+  if (o->rng_mode == 1 && (o->precision != 64 || o->injected)) return fail(STRYKE_E_ARG, "rng_mode 1 (wide stream) needs precision 64 and no injected draws");
   for (int i = 0; i < f->n_nodes; ++i) {
     if (f->node_kind[i] > STRYKE_KIND_PUMP) return fail(STRYKE_E_ARG, "unknown node kind");
     if (f->node_kind[i] != STRYKE_KIND_APRIORI && (f->node_unit[i] < 0 || f->node_unit[i] >= f->n_units))
@@ -176,11 +182,45 @@ static int validate(const StrykeFacility* f, const StrykeDayTables* d, const Str
   for (int p = 0; p < f->n_pairs; ++p)
     if (f->pair_node[p] < 0 || f->pair_node[p] >= f->n_nodes) return fail(STRYKE_E_ARG, "pair_node out of range");
   if (f->level_off[0] != 0 || f->level_off[f->n_moves] != f->n_pairs) return fail(STRYKE_E_ARG, "bad level_off");
-  for (int64_t i = 0; i < c->n_cells; ++i) {
-    if (c->cell_day[i] < 0 || c->cell_day[i] >= d->n_days) return fail(STRYKE_E_ARG, "cell_day out of range");
-    if (c->cell_species[i] < 0 || c->cell_species[i] >= s->n_species) return fail(STRYKE_E_ARG, "cell_species out of range");
+  for (int k = 0; k < f->n_moves; ++k)      // every move has at least one reachable node
+    if (f->level_off[k] >= f->level_off[k + 1] || f->level_off[k + 1] > f->n_pairs) return fail(STRYKE_E_ARG, "level_off must increase strictly");
+  // cell lists: the explicit arrays are range-checked on the device (count_kernel); the group table here
+  if (c->cell_day == nullptr && c->n_cells > 0) {
+    if (!c->groups || c->n_groups < 1 || !c->active_days) return fail(STRYKE_E_ARG, "cells: neither explicit arrays nor a group table");
+    if (c->cell_species || c->cell_id) return fail(STRYKE_E_ARG, "cells: explicit arrays and a group table are exclusive");
+    int64_t next = 0;
+    for (int g = 0; g < c->n_groups; ++g) {
+      const StrykeCellGroup& G = c->groups[g];
+      if (G.cell0 != next || G.iterations < 1 || G.n_active_days < 1) return fail(STRYKE_E_ARG, "cell groups must be non-empty and contiguous");
+      if (G.species < 0 || G.species >= s->n_species) return fail(STRYKE_E_ARG, "cell group: species out of range");
+      if (G.active_off < 0 || (int64_t)G.active_off + G.n_active_days > c->n_active) return fail(STRYKE_E_ARG, "cell group: active_days out of range");
+      for (int j = 0; j < G.n_active_days; ++j) {
+        const int64_t row = (int64_t)G.day0 + c->active_days[G.active_off + j];
+        if (c->active_days[G.active_off + j] < 0 || row < 0 || row >= d->n_days) return fail(STRYKE_E_ARG, "cell group: day out of range");
+      }
+      next += (int64_t)G.iterations * G.n_active_days;
+    }
+    if (next != c->n_cells) return fail(STRYKE_E_ARG, "cell groups do not cover n_cells");
+  } else if (c->n_cells > 0 && (!c->cell_species || !c->cell_id)) {
+    return fail(STRYKE_E_ARG, "cells: cell_species / cell_id missing");
   }
   return STRYKE_OK;
+}
+
+// fn(species row, number of cells) over the plan's cells (runs of equal species for explicit lists)
+template <class F>
+static void for_each_species_run(const StrykeCells* c, F fn) {
+  if (c->cell_day == nullptr) {
+    for (int g = 0; g < c->n_groups; ++g) fn(c->groups[g].species, (int64_t)c->groups[g].iterations * c->groups[g].n_active_days);
+    return;
+  }
+  int64_t i = 0;
+  while (i < c->n_cells) {
+    int64_t j = i + 1;
+    while (j < c->n_cells && c->cell_species[j] == c->cell_species[i]) ++j;
+    fn(c->cell_species[i], j - i);
+    i = j;
+  }
 }
 
 extern "C" {
@@ -217,7 +257,11 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
   pl->device = o->device; pl->precision = o->precision; pl->max_daily_fish = o->max_daily_fish;
   pl->inject = o->injected != nullptr;
   pl->n_cells = c->n_cells;
+  pl->n_days = d->n_days; pl->n_species = s->n_species;
   if (device_sm_count(o->device, &pl->n_sm)) return fail(STRYKE_E_CUDA, "cannot query the SM count");
+  bool species_ok = true;
+  for_each_species_run(c, [&](int sp, int64_t) { species_ok = species_ok && sp >= 0 && sp < s->n_species; });
+  if (!species_ok) return fail(STRYKE_E_ARG, "cell_species out of range");
 
   // ---- static facility records -----------------------------------------------------------------------------------
   std::vector<NodeRec> nodes(f->n_nodes);
@@ -282,14 +326,25 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
     pareto_constants_kernel<<<(s->n_species + 127) / 128, 128>>>(pl->species.as<double>(), s->n_species, pl->pareto.as<double>());
     CK(cudaGetLastError());
   }
-  CK(upload(pl->cell_day, c->cell_day, (size_t)c->n_cells));
-  CK(upload(pl->cell_species, c->cell_species, (size_t)c->n_cells));
-  CK(upload(pl->cell_id, c->cell_id, (size_t)c->n_cells));
-  CK(pl->tile_off.alloc((size_t)(c->n_cells + 1) * sizeof(int64_t)));
-  CK(pl->fish_off.alloc((size_t)(c->n_cells + 1) * sizeof(int64_t)));
-  pl->nb_scan = (int)((c->n_cells + SCAN_CH - 1) / SCAN_CH);
-  CK(pl->part.alloc((size_t)(pl->nb_scan > 0 ? pl->nb_scan : 1) * 2 * sizeof(int64_t)));
-  CK(pl->err.alloc(2 * sizeof(unsigned long long)));    // [0] error word of count_kernel, [1] chunk counter of the throughput kernels
+  const bool implicit = c->cell_day == nullptr && c->n_cells > 0;
+  if (implicit) {
+    CK(upload(pl->groups, c->groups, (size_t)c->n_groups));
+    CK(upload(pl->active_days, c->active_days, (size_t)c->n_active));
+  } else {
+    CK(upload(pl->cell_day, c->cell_day, (size_t)c->n_cells));
+    CK(upload(pl->cell_species, c->cell_species, (size_t)c->n_cells));
+    CK(upload(pl->cell_id, c->cell_id, (size_t)c->n_cells));
+  }
+  const size_t NB = (size_t)((c->n_cells + 31) / 32), NCB = (size_t)((c->n_cells + COUNT_T - 1) / COUNT_T);
+  CK(pl->blk_row.alloc((NB + 1) * sizeof(uint32_t)));
+  CK(pl->blk_mask.alloc((NB + 1) * sizeof(uint32_t)));
+  CK(pl->blk_wide.alloc((NB + 1) * sizeof(uint32_t)));
+  CK(pl->scan_flag.alloc((NCB + 1) * sizeof(unsigned int)));
+  CK(cudaMemsetAsync(pl->scan_flag.p, 0, (NCB + 1) * sizeof(unsigned int), 0));
+  CK(pl->scan_agg.alloc((NCB + 1) * 3 * sizeof(long long)));
+  CK(pl->scan_incl.alloc((NCB + 1) * 3 * sizeof(long long)));
+  CK(pl->err.alloc(ERR_N * sizeof(unsigned long long)));    // status words (ERR_*): error word, chunk counter, totals
+  CK(cudaMemsetAsync(pl->err.p, 0, ERR_N * sizeof(unsigned long long), 0));
 
   KParams& K = pl->K;
   K.nodes = pl->nodes.as<NodeRec>(); K.edge_dst = pl->edge_dst.as<uint8_t>(); K.moves = pl->moves.as<MoveRec>();
@@ -299,11 +354,20 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
   K.edge_cdf = pl->edge_cdf.as<double>(); K.node_stay = pl->node_stay.as<uint8_t>(); K.unit_coef = pl->unit_coef.as<double>();
   K.species = pl->species.as<double>(); K.n_species = s->n_species;
   K.cell_day = pl->cell_day.as<int32_t>(); K.cell_species = pl->cell_species.as<int32_t>(); K.cell_id = pl->cell_id.as<uint64_t>();
-  K.tile_off = pl->tile_off.as<int64_t>(); K.fish_off = pl->fish_off.as<int64_t>(); K.n_cells = c->n_cells;
+  if (implicit) {
+    K.cell_day = nullptr; K.cell_species = nullptr; K.cell_id = nullptr;
+    K.groups = pl->groups.as<StrykeCellGroup>(); K.n_groups = c->n_groups; K.active_days = pl->active_days.as<int32_t>();
+    K.id_days = c->id_days; K.id_add = c->id_add;
+  }
+  K.n_cells = c->n_cells;
+  K.rng_wide = o->rng_mode == 1 ? 1 : 0;
+  K.flags = o->flags;
+  K.out.rows = nullptr; K.out.blk_row = pl->blk_row.as<uint32_t>(); K.out.blk_mask = pl->blk_mask.as<uint32_t>();
+  K.out.blk_wide = pl->blk_wide.as<uint32_t>();
   K.seed_lo = (uint32_t)o->seed; K.seed_hi = (uint32_t)(o->seed >> 32);
   Philox::key_schedule(o->seed, K.ks);
   K.n_fish_total = 0;
-  K.work_counter = pl->err.as<unsigned long long>() + 1;
+  K.work_counter = pl->err.as<unsigned long long>() + ERR_WORK;      // (the error word sits right below it: STRYKE_BCHK)
   K.chunk_tiles = 128;
   K.chunk_min = 16;
   if (const char* e = getenv("STRYKE_B200_CHUNK_TILES")) K.chunk_tiles = std::max(1, atoi(e));
@@ -349,13 +413,14 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
       n_tr = o->trace->n_fish;      // population mode: count known from an earlier run with the same seed (checked in plan_status)
     } else if (!o->injected) {   // fish offsets must be known up front: only fixed-count (anadromous) cells
       n_tr = 0;
-      for (int64_t i = 0; i < c->n_cells; ++i) {
-        const double* sp = s->params + (size_t)c->cell_species[i] * STRYKE_SPECIES_W;
-        if ((int)sp[12] != STRYKE_ENT_FIXED || !(sp[17] >= 1.0))
-          return fail(STRYKE_E_ARG, "per-fish trace needs injected draws or fixed counts with occur_prob = 1");
-        int64_t n = (int64_t)sp[18];
-        n_tr += n == 0 ? 1 : n;
-      }
+      bool ok = true;
+      for_each_species_run(c, [&](int spi, int64_t cnt) {
+        const double* sp = s->params + (size_t)spi * STRYKE_SPECIES_W;
+        if ((int)sp[12] != STRYKE_ENT_FIXED || !(sp[17] >= 1.0)) ok = false;
+        const int64_t n = (int64_t)sp[18];
+        n_tr += cnt * (n == 0 ? 1 : n);
+      });
+      if (!ok) return fail(STRYKE_E_ARG, "per-fish trace needs injected draws or fixed counts with occur_prob = 1");
     }
     const size_t M = (size_t)f->n_moves;
     pl->has_trace = true; pl->trace_fish = n_tr; pl->trace_probs = o->trace->strike != nullptr;
@@ -381,6 +446,14 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
   pl->blocks_per_sm = o->blocks_per_sm;
   // ---- throughput variant: fp32, native Philox, tallies only ---------------------------------------------------------
   pl->use_fast = pl->precision == 32 && !pl->inject && !pl->has_trace && o->kernel_variant != 1;
+  {   // compact rows: a cell stays in the narrow (16-bit) layout while no counter can pass 65 535 — a fish rolls a
+      // mortality cause at every turbine level it reaches alive (stryke.py:1545-1560; + the probe call in injected mode)
+    int n_cause = 0;
+    for (int k = 0; k < f->n_moves; ++k) n_cause += (moves[k].need & NEED_CAUSE) ? 1 : 0;
+    pl->narrow_max = (65535 - n_cause) / std::max(1, n_cause);
+    pl->row_w = f->n_pairs + 3;
+    K.out.row_w = pl->row_w; K.out.narrow_max = pl->narrow_max; K.out.cap = 0;
+  }
   if (pl->use_fast) {
     int stride = 1;
     for (int i = 0; i < f->n_nodes; ++i) stride = std::max(stride, (int)nodes[i].deg);
@@ -410,12 +483,12 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
     // ---- specialise for this facility when the run is large enough to amortise a ~1-3 s compile ---------------------
     double fish_hint = 0.0;
     bool small_cells = false;      // cells that may leave a large share of a tile idle: drawn counts, or small fixed ones
-    for (int64_t i = 0; i < c->n_cells; ++i) {
-      const double* sp = s->params + (size_t)c->cell_species[i] * STRYKE_SPECIES_W;
+    for_each_species_run(c, [&](int spi, int64_t cnt) {
+      const double* sp = s->params + (size_t)spi * STRYKE_SPECIES_W;
       const bool fixed = (int)sp[12] == STRYKE_ENT_FIXED;
-      fish_hint += fixed ? sp[18] : 50.0;
+      fish_hint += (double)cnt * (fixed ? sp[18] : 50.0);
       small_cells = small_cells || !fixed || (sp[18] < 4096.0 && ((int64_t)sp[18] & 31) != 0);
-    }
+    });
     const char* pool_env = getenv("STRYKE_B200_POOL");
     const bool pool = tally.NW > 0 && c->n_cells >= 32 && (pool_env ? pool_env[0] == '1' : small_cells);
     const char* env = getenv("STRYKE_B200_JIT");
@@ -435,8 +508,9 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
           pl->pool = true;
           pl->kernel_name = "passage_spec (tables specialised with NVRTC, pooled remainders)";
           pl->fast_smem_bytes = (size_t)fast_smem(f->n_nodes, f->n_units, pl->fast_stride, pl->n_species_staged, tally.NW, f->n_pairs).total;
-          CK(pl->blk_S.alloc((size_t)((c->n_cells + 31) / 32) * sizeof(uint32_t)));
-          K.blk_S = pl->blk_S.as<uint32_t>();
+          CK(pl->blk_S.alloc((NB + 1) * sizeof(uint32_t)));
+          CK(pl->blk_tile.alloc((NB + 1) * sizeof(int64_t)));
+          K.blk_S = pl->blk_S.as<uint32_t>(); K.blk_tile = pl->blk_tile.as<int64_t>();
         }
       } else if (o->kernel_variant == 3) {
         return fail(STRYKE_E_CUDA, "kernel specialisation failed: " + err);
@@ -446,6 +520,14 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
     pl->kernel_name = "passage_kernel (general)";
   }
   if (o->kernel_variant == 3 && !pl->jit_kernel) return fail(STRYKE_E_ARG, "kernel_variant 3 needs fp32, native RNG, no trace");
+  if (!pl->pool) {             // per-cell tile offsets (pooled plans walk blocks: blk_tile)
+    CK(pl->tile_off.alloc((size_t)(c->n_cells + 1) * sizeof(int64_t)));
+    K.tile_off = pl->tile_off.as<int64_t>();
+  }
+  if (pl->inject || pl->has_trace) {      // the only readers of per-cell fish offsets
+    CK(pl->fish_off.alloc((size_t)(c->n_cells + 1) * sizeof(int64_t)));
+    K.fish_off = pl->fish_off.as<int64_t>();
+  }
   CK(cudaStreamSynchronize(0));      // uploads done: the caller may release its host tables
   guard.p = nullptr;
   *out = pl;
@@ -455,121 +537,194 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
 }  // extern "C"
 
 template <typename Real, bool INJECT, int PR>
-static int launch_passage(StrykePlan* pl, cudaStream_t st) {
+static int launch_passage(StrykePlan* pl, const KParams& K, cudaStream_t st) {
   auto kern = passage_kernel<Real, INJECT, PR>;
-  if (pl->smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+  if (pl->smem > 48 * 1024 && !pl->attr_set) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    pl->attr_set = true;
+  }
   int bps = pl->blocks_per_sm;
   if (bps <= 0) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, BLOCK, pl->smem));
     if (bps < 1) bps = 1;
+    pl->blocks_per_sm = bps;
   }
-  kern<<<pl->n_sm * bps, BLOCK, pl->smem, st>>>(pl->K, pl->n_species_staged);
+  kern<<<pl->n_sm * bps, BLOCK, pl->smem, st>>>(K, pl->n_species_staged);
   g_launches++;
   CK(cudaGetLastError());
   return STRYKE_OK;
 }
 template <typename Real, bool INJECT>
-static int launch_passage_pr(StrykePlan* pl, cudaStream_t st) {
+static int launch_passage_pr(StrykePlan* pl, const KParams& K, cudaStream_t st) {
   switch (pl->pr) {
-    case 1: return launch_passage<Real, INJECT, 1>(pl, st);
-    case 2: return launch_passage<Real, INJECT, 2>(pl, st);
-    default: return launch_passage<Real, INJECT, 4>(pl, st);
+    case 1: return launch_passage<Real, INJECT, 1>(pl, K, st);
+    case 2: return launch_passage<Real, INJECT, 2>(pl, K, st);
+    default: return launch_passage<Real, INJECT, 4>(pl, K, st);
   }
 }
 
 template <int PR, bool BARO, int MINB>
-static int launch_fast(StrykePlan* pl, cudaStream_t st) {
+static int launch_fast(StrykePlan* pl, const KParams& K, cudaStream_t st) {
   auto kern = passage_fast_kernel<PR, BARO, MINB>;
-  if (pl->fast_smem_bytes > 48 * 1024)
+  if (pl->fast_smem_bytes > 48 * 1024 && !pl->attr_set) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem_bytes));
+    pl->attr_set = true;
+  }
   int bps = pl->blocks_per_sm;
   if (bps <= 0) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, BLOCK, pl->fast_smem_bytes));
     if (bps < 1) bps = 1;
+    pl->blocks_per_sm = bps;
   }
-  kern<<<pl->n_sm * bps, BLOCK, pl->fast_smem_bytes, st>>>(pl->K, pl->fast, pl->fast_nodes.as<uint2>(), pl->fast_stride, pl->n_species_staged);
+  kern<<<pl->n_sm * bps, BLOCK, pl->fast_smem_bytes, st>>>(K, pl->fast, pl->fast_nodes.as<uint2>(), pl->fast_stride, pl->n_species_staged);
   g_launches++;
   CK(cudaGetLastError());
   return STRYKE_OK;
 }
 template <int MINB>
-static int launch_fast_minb(StrykePlan* pl, cudaStream_t st) {
-  const bool b = pl->K.barotrauma != 0;
+static int launch_fast_minb(StrykePlan* pl, const KParams& K, cudaStream_t st) {
+  const bool b = K.barotrauma != 0;
   switch (pl->pr) {
-    case 1: return b ? launch_fast<1, true, MINB>(pl, st) : launch_fast<1, false, MINB>(pl, st);
-    case 2: return b ? launch_fast<2, true, MINB>(pl, st) : launch_fast<2, false, MINB>(pl, st);
-    default: return b ? launch_fast<4, true, MINB>(pl, st) : launch_fast<4, false, MINB>(pl, st);
+    case 1: return b ? launch_fast<1, true, MINB>(pl, K, st) : launch_fast<1, false, MINB>(pl, K, st);
+    case 2: return b ? launch_fast<2, true, MINB>(pl, K, st) : launch_fast<2, false, MINB>(pl, K, st);
+    default: return b ? launch_fast<4, true, MINB>(pl, K, st) : launch_fast<4, false, MINB>(pl, K, st);
   }
 }
 #include "specialise.inl"      // namespace jit: tally layout, source generation, NVRTC compile + cubin cache, load
 
-static int launch_jit(StrykePlan* pl, cudaStream_t st) {
+static int launch_jit(StrykePlan* pl, const KParams& K, cudaStream_t st) {
   const void* fn = (const void*)pl->jit_kernel;
-  if (pl->fast_smem_bytes > 48 * 1024)
+  if (pl->fast_smem_bytes > 48 * 1024 && !pl->attr_set) {
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fast_smem_bytes));
+    pl->attr_set = true;
+  }
   int bps = pl->blocks_per_sm;
   if (bps <= 0) bps = std::max(1, std::min(jit::spec_min_blocks(), (int)((200 * 1024) / std::max<size_t>(pl->fast_smem_bytes, 1))));
   const uint2* nodes = pl->fast_nodes.as<uint2>();
-  void* args[] = {(void*)&pl->K, (void*)&pl->fast, (void*)&nodes, (void*)&pl->fast_stride, (void*)&pl->n_species_staged};
+  void* args[] = {(void*)&K, (void*)&pl->fast, (void*)&nodes, (void*)&pl->fast_stride, (void*)&pl->n_species_staged};
   CK(cudaLaunchKernel(fn, dim3(pl->n_sm * bps), dim3(BLOCK), args, pl->fast_smem_bytes, st));
   g_launches++;
   return STRYKE_OK;
 }
 
-static int launch_fast_any(StrykePlan* pl, cudaStream_t st) {
-  if (pl->jit_kernel) return launch_jit(pl, st);
-  return launch_fast_minb<4>(pl, st);
+static int launch_fast_any(StrykePlan* pl, const KParams& K, cudaStream_t st) {
+  if (pl->jit_kernel) return launch_jit(pl, K, st);
+  return launch_fast_minb<4>(pl, K, st);
 }
 
-extern "C" {
-
-int stryke_b200_plan_launch(StrykePlan* pl, int32_t* d_cell_n, uint32_t* d_daily, uint32_t* d_state_daily, void* stream) {
-  if (!pl || !d_cell_n || !d_daily || !d_state_daily) return fail(STRYKE_E_ARG, "null argument");
-  cudaStream_t st = (cudaStream_t)stream;
+// count (+ scan) kernel and passage kernel for cells [c_lo, c_hi) of the plan.  Dense output: d_daily / d_state (zeroed
+// here); compact output: d_rows (zeroed row by row by count_kernel).  first_slot < 0: slots continue after the previous range.
+static int launch_cells(StrykePlan* pl, int64_t c_lo, int64_t c_hi, int32_t* d_cell_n, uint32_t* d_daily, uint32_t* d_state_daily,
+                        uint32_t* d_rows, int64_t rows_cap, int64_t first_slot, cudaStream_t st,
+                        unsigned long long* d_slots_after = nullptr) {
   CK(cudaSetDevice(pl->device));
-  KParams& K = pl->K;
-  K.cell_n = d_cell_n; K.daily = d_daily; K.state_daily = d_state_daily;
-  if (pl->n_cells == 0) return STRYKE_OK;
-  const size_t daily_bytes = (size_t)pl->n_cells * STRYKE_DAILY_W * 4, state_bytes = (size_t)pl->n_cells * K.n_pairs * 2 * 4;
-  const bool side = daily_bytes + state_bytes >= ((size_t)32 << 20);
-  if (side) {
-    if (!pl->aux) {
-      CK(cudaStreamCreateWithFlags(&pl->aux, cudaStreamNonBlocking));
-      CK(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
-    }
-    CK(cudaEventRecord(pl->ev_fork, st));                  // after everything already queued on the caller's stream
-    CK(cudaStreamWaitEvent(pl->aux, pl->ev_fork, 0));
-    CK(cudaMemsetAsync(d_daily, 0, daily_bytes, pl->aux));
-    CK(cudaMemsetAsync(d_state_daily, 0, state_bytes, pl->aux));
-    CK(cudaEventRecord(pl->ev_join, pl->aux));
+  KParams K = pl->K;                 // this launch's view of the plan
+  const int64_t nC = c_hi - c_lo;
+  if (nC <= 0) return STRYKE_OK;
+  K.n_cells = nC;
+  K.cell_base = c_lo;
+  if (K.groups == nullptr) { K.cell_day += c_lo; K.cell_species += c_lo; K.cell_id += c_lo; }
+  K.cell_n = d_cell_n + c_lo;
+  K.out.blk_row += c_lo >> 5; K.out.blk_mask += c_lo >> 5; K.out.blk_wide += c_lo >> 5;
+  const bool compact = d_rows != nullptr;
+  const bool fresh = !compact || first_slot >= 0;
+  pl->last_rows_cap = compact ? rows_cap : -1;
+  unsigned long long* err = pl->err.as<unsigned long long>();
+  if (fresh) CK(cudaMemsetAsync(err, 0, ERR_N * sizeof(unsigned long long), st));
+  else CK(cudaMemsetAsync(err + ERR_WORK, 0, 2 * sizeof(unsigned long long), st));      // chunk counter and ticket
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool side = false;
+  if (compact) {
+    K.daily = nullptr; K.state_daily = nullptr;
+    K.out.rows = d_rows; K.out.cap = (unsigned int)std::min<int64_t>(rows_cap, 0xFFFFFFFFll);
   } else {
-    CK(cudaMemsetAsync(d_daily, 0, daily_bytes, st));
-    CK(cudaMemsetAsync(d_state_daily, 0, state_bytes, st));
+    K.daily = d_daily + (size_t)c_lo * STRYKE_DAILY_W; K.state_daily = d_state_daily + (size_t)c_lo * K.n_pairs * 2;
+    K.out.rows = nullptr;
+    const size_t daily_bytes = (size_t)nC * STRYKE_DAILY_W * 4, state_bytes = (size_t)nC * K.n_pairs * 2 * 4;
+    side = daily_bytes + state_bytes >= ((size_t)32 << 20);
+    if (side) {
+      if (!pl->aux) {
+        CK(cudaStreamCreateWithFlags(&pl->aux, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
+      }
+      CK(cudaEventRecord(pl->ev_fork, st));                  // after everything already queued on the caller's stream
+      CK(cudaStreamWaitEvent(pl->aux, pl->ev_fork, 0));
+      CK(cudaMemsetAsync(K.daily, 0, daily_bytes, pl->aux));
+      CK(cudaMemsetAsync(K.state_daily, 0, state_bytes, pl->aux));
+      CK(cudaEventRecord(pl->ev_join, pl->aux));
+    } else {
+      CK(cudaMemsetAsync(K.daily, 0, daily_bytes, st));
+      CK(cudaMemsetAsync(K.state_daily, 0, state_bytes, st));
+    }
   }
-  CK(cudaMemsetAsync(pl->err.p, 0, 2 * sizeof(unsigned long long), st));
-  const int cb = (int)((pl->n_cells + 255) / 256);
-  uint32_t* blk_S = pl->pool ? pl->blk_S.as<uint32_t>() : nullptr;      // pooled remainders: shared tiles per block of 32 cells
-  if (pl->inject) count_kernel<true><<<cb, 256, 0, st>>>(K, pl->day_Q.as<double>(), d_cell_n, pl->max_daily_fish, pl->err.as<unsigned long long>(), blk_S, pl->pareto.as<double>());
-  else count_kernel<false><<<cb, 256, 0, st>>>(K, pl->day_Q.as<double>(), d_cell_n, pl->max_daily_fish, pl->err.as<unsigned long long>(), blk_S, pl->pareto.as<double>());
-  scan_partial<<<pl->nb_scan, SCAN_T, 0, st>>>(d_cell_n, pl->n_cells, pl->part.as<int64_t>(), blk_S);
-  scan_blocks<<<1, SCAN_T, 0, st>>>(pl->part.as<int64_t>(), pl->nb_scan);
-  scan_final<<<pl->nb_scan, SCAN_T, 0, st>>>(d_cell_n, pl->n_cells, pl->part.as<int64_t>(), pl->tile_off.as<int64_t>(), pl->fish_off.as<int64_t>(), blk_S);
-  g_launches += 4;
+  CountOut O{};
+  O.cell_n = d_cell_n + c_lo; O.tile_off = pl->tile_off.as<int64_t>(); O.fish_off = pl->fish_off.as<int64_t>();
+  O.blk_tile = pl->pool ? pl->blk_tile.as<int64_t>() : nullptr;
+  O.blk_S = pl->pool ? pl->blk_S.as<uint32_t>() : nullptr;
+  O.err = err;
+  O.slot0 = compact && first_slot >= 0 ? (long long)first_slot : -1ll;
+  O.slots_after = d_slots_after;
+  ScanDev S{pl->scan_flag.as<unsigned int>(), pl->scan_agg.as<long long>(), pl->scan_incl.as<long long>(), ++pl->epoch};
+  const int cb = (int)((nC + COUNT_T - 1) / COUNT_T);
+  if (pl->inject) count_kernel<true><<<cb, COUNT_T, 0, st>>>(K, pl->day_Q.as<double>(), O, pl->max_daily_fish, pl->pareto.as<double>(), S, pl->n_days, pl->n_species);
+  else count_kernel<false><<<cb, COUNT_T, 0, st>>>(K, pl->day_Q.as<double>(), O, pl->max_daily_fish, pl->pareto.as<double>(), S, pl->n_days, pl->n_species);
+  g_launches += 1;
   CK(cudaGetLastError());
   if (side) CK(cudaStreamWaitEvent(st, pl->ev_join, 0));    // the passage kernel adds into the zeroed tallies
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (pl->time_kernel) {
     CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
     pl->kernel_events.emplace_back(ev0, ev1);
     CK(cudaEventRecord(ev0, st));
   }
   int rc;
-  if (pl->use_fast) rc = launch_fast_any(pl, st);
-  else if (pl->precision == 64) rc = pl->inject ? launch_passage_pr<double, true>(pl, st) : launch_passage_pr<double, false>(pl, st);
-  else rc = pl->inject ? launch_passage_pr<float, true>(pl, st) : launch_passage_pr<float, false>(pl, st);
+  if (pl->use_fast) rc = launch_fast_any(pl, K, st);
+  else if (pl->precision == 64) rc = pl->inject ? launch_passage_pr<double, true>(pl, K, st) : launch_passage_pr<double, false>(pl, K, st);
+  else rc = pl->inject ? launch_passage_pr<float, true>(pl, K, st) : launch_passage_pr<float, false>(pl, K, st);
   if (ev1) CK(cudaEventRecord(ev1, st));
   return rc;
+}
+
+extern "C" {
+
+int stryke_b200_plan_launch(StrykePlan* pl, int32_t* d_cell_n, uint32_t* d_daily, uint32_t* d_state_daily, void* stream) {
+  if (!pl || !d_cell_n || !d_daily || !d_state_daily) return fail(STRYKE_E_ARG, "null argument");
+  return launch_cells(pl, 0, pl->n_cells, d_cell_n, d_daily, d_state_daily, nullptr, 0, 0, (cudaStream_t)stream);
+}
+
+int stryke_b200_plan_launch_compact(StrykePlan* pl, int64_t cell_lo, int64_t cell_hi, int32_t* d_cell_n, uint32_t* d_rows,
+                                    int64_t rows_cap, int64_t first_slot, uint64_t* d_slots_after, void* stream) {
+  if (!pl || !d_cell_n || !d_rows) return fail(STRYKE_E_ARG, "null argument");
+  if (cell_hi < 0) cell_hi = pl->n_cells;
+  if (cell_lo < 0 || cell_lo > cell_hi || cell_hi > pl->n_cells || (cell_lo % COUNT_T) != 0)
+    return fail(STRYKE_E_ARG, "cell range must lie inside the plan and start at a multiple of 256");
+  if (pl->inject || pl->has_trace) return fail(STRYKE_E_ARG, "compact rows are for native-RNG tally runs (no injected draws, no trace)");
+  if (rows_cap < 0) return fail(STRYKE_E_ARG, "negative rows_cap");
+  return launch_cells(pl, cell_lo, cell_hi, d_cell_n, nullptr, nullptr, d_rows, rows_cap, first_slot, (cudaStream_t)stream,
+                      (unsigned long long*)d_slots_after);
+}
+
+int stryke_b200_plan_compact_tables(StrykePlan* pl, uint32_t** d_blk_row, uint32_t** d_blk_mask, uint32_t** d_blk_wide,
+                                    int32_t* row_w, int32_t* narrow_max) {
+  if (!pl) return fail(STRYKE_E_ARG, "null plan");
+  if (d_blk_row) *d_blk_row = pl->blk_row.as<uint32_t>();
+  if (d_blk_mask) *d_blk_mask = pl->blk_mask.as<uint32_t>();
+  if (d_blk_wide) *d_blk_wide = pl->blk_wide.as<uint32_t>();
+  if (row_w) *row_w = pl->row_w;
+  if (narrow_max) *narrow_max = pl->narrow_max;
+  return STRYKE_OK;
+}
+
+int stryke_b200_plan_compact_totals(StrykePlan* pl, void* stream, int64_t* n_slots, int64_t* n_fish) {
+  if (!pl) return fail(STRYKE_E_ARG, "null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(pl->device));
+  unsigned long long h[ERR_N] = {0};
+  CK(cudaMemcpyAsync(h, pl->err.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (n_slots) *n_slots = (int64_t)h[ERR_SLOTS];
+  if (n_fish) *n_fish = (int64_t)h[ERR_FISH_CUM];
+  return STRYKE_OK;
 }
 
 int stryke_b200_plan_time_kernel(StrykePlan* pl, int enable) {
@@ -630,22 +785,27 @@ int stryke_b200_plan_status(StrykePlan* pl, void* stream, int64_t* n_fish_total)
   if (!pl) return fail(STRYKE_E_ARG, "null plan");
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaSetDevice(pl->device));
-  unsigned long long err = 0;
-  int64_t nf = 0;
-  CK(cudaMemcpyAsync(&err, pl->err.p, sizeof(err), cudaMemcpyDeviceToHost, st));
-  if (pl->n_cells > 0) CK(cudaMemcpyAsync(&nf, pl->fish_off.as<int64_t>() + pl->n_cells, sizeof(nf), cudaMemcpyDeviceToHost, st));
+  unsigned long long h[ERR_N] = {0};
+  CK(cudaMemcpyAsync(h, pl->err.p, sizeof(h), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  const unsigned long long err = h[ERR_WORD];
+  const int64_t nf = (int64_t)h[ERR_FISH_CUM];
   if (n_fish_total) *n_fish_total = nf;
   if ((err >> 62) == 3ull)      // only the bounds-check build (STRYKE_BOUNDS_CHECK) sets both top bits
     return fail(STRYKE_E_CUDA, "internal bounds check failed in a passage kernel (site " + std::to_string((err >> 48) & 0x3fff) + ")");
-  if (err & 0x8000000000000000ull)
-    return fail(STRYKE_E_ARG, "Computed non-finite or negative population size in cell " + std::to_string(err & 0x7FFFFFFFFFFFFFFFull));
+  if ((err >> 61) == 5ull)
+    return fail(STRYKE_E_ARG, "cell_day / cell_species out of range in cell " + std::to_string(err & 0xFFFFFFFFull));
+  if (err & ERRBIT_NONFINITE)
+    return fail(STRYKE_E_ARG, "Computed non-finite or negative population size in cell " + std::to_string(err & 0xFFFFFFFFull));
   if (err)
     return fail(STRYKE_E_MAX_FISH, "Computed population size n=" + std::to_string(err >> 32) + " exceeds STRYKE_MAX_DAILY_FISH=" +
                                        std::to_string(pl->max_daily_fish) + " (cell " + std::to_string(err & 0xFFFFFFFFull) + ")");
   if ((pl->inject || pl->has_trace) && nf != pl->K.n_fish_total)
     return fail(STRYKE_E_ARG, "fish count computed on the device (" + std::to_string(nf) + ") != injected/trace fish count (" +
                                   std::to_string(pl->K.n_fish_total) + ")");
+  if (h[ERR_SLOTS] > (unsigned long long)pl->last_rows_cap && pl->last_rows_cap >= 0)
+    return fail(STRYKE_E_ARG, "compact rows buffer too small: " + std::to_string(h[ERR_SLOTS]) + " slots needed, " +
+                                  std::to_string(pl->last_rows_cap) + " given");
   return STRYKE_OK;
 }
 
@@ -684,6 +844,80 @@ int stryke_b200_run(const StrykeFacility* f, const StrykeDayTables* d, const Str
   if (rc) return rc;
   if (o->trace) return stryke_b200_plan_fetch_trace(pl, o->trace, nullptr);
   return STRYKE_OK;
+}
+
+// One-shot run with compact host results.  The cell list is cut into slabs (multiples of 256 cells); the rows of slab k
+// travel to the host on a copy stream while slab k + 1 is being simulated, so the call costs about
+// max(kernel time, PCIe time) instead of their sum.
+int stryke_b200_run_compact(const StrykeFacility* f, const StrykeDayTables* d, const StrykeSpeciesTable* s, const StrykeCells* c,
+                            const StrykeOpts* o, StrykeCompact* out) {
+  if (!out || !out->blk_row || !out->blk_mask || !out->blk_wide || !out->rows) return fail(STRYKE_E_ARG, "null compact buffers");
+  if (!c) return fail(STRYKE_E_ARG, "null argument");
+  const int64_t C = c->n_cells, NB = (C + 31) / 32;
+  if (out->n_blocks < NB) return fail(STRYKE_E_ARG, "compact: n_blocks < (n_cells + 31) / 32");
+  if (o && (o->injected || o->trace)) return fail(STRYKE_E_ARG, "compact rows are for native-RNG tally runs (no injected draws, no trace)");
+  StrykePlan* pl = nullptr;
+  int rc = stryke_b200_plan_create(f, d, s, c, o, &pl);
+  if (rc) return rc;
+  struct Guard { StrykePlan* p; ~Guard() { stryke_b200_plan_destroy(p); } } guard{pl};
+  out->row_w = pl->row_w; out->narrow_max = pl->narrow_max; out->n_slots = 0; out->n_fish = 0;
+  if (C == 0) return STRYKE_OK;
+  const size_t row_bytes = (size_t)pl->row_w * 4;
+  DevBuf dn, dr, tot;
+  CK(dn.alloc((size_t)C * 4));
+  CK(dr.alloc((size_t)std::max<int64_t>(out->rows_cap, 1) * row_bytes));
+  int n_slabs = out->n_slabs > 0 ? out->n_slabs : (C >= (1 << 20) ? 8 : C >= (1 << 16) ? 2 : 1);
+  int64_t per = ((C + n_slabs - 1) / n_slabs + COUNT_T - 1) / COUNT_T * COUNT_T;
+  if (per < COUNT_T) per = COUNT_T;
+  n_slabs = (int)((C + per - 1) / per);
+  cudaStream_t comp = nullptr, copy = nullptr;
+  CK(cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+  struct Streams { cudaStream_t a, b; std::vector<cudaEvent_t> ev; unsigned long long* pin = nullptr;
+                   ~Streams() { for (auto e : ev) cudaEventDestroy(e); if (pin) cudaFreeHost(pin); cudaStreamDestroy(a); cudaStreamDestroy(b); } } S{comp, copy};
+  CK(cudaMallocHost((void**)&S.pin, (size_t)n_slabs * sizeof(unsigned long long)));
+  CK(tot.alloc((size_t)n_slabs * sizeof(unsigned long long)));
+  CK(cudaStreamSynchronize(0));      // (the buffers come from the default stream's pool)
+  std::vector<cudaEvent_t> ev_cnt((size_t)n_slabs), ev_done((size_t)n_slabs);
+  for (int k = 0; k < n_slabs; ++k) {
+    CK(cudaEventCreateWithFlags(&ev_cnt[k], cudaEventDisableTiming)); S.ev.push_back(ev_cnt[k]);
+    CK(cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming)); S.ev.push_back(ev_done[k]);
+  }
+  // the plan was built on the legacy default stream and is complete (plan_create synchronised); queue every slab
+  for (int k = 0; k < n_slabs; ++k) {
+    const int64_t lo = (int64_t)k * per, hi = std::min<int64_t>(C, lo + per);
+    rc = launch_cells(pl, lo, hi, dn.as<int32_t>(), nullptr, nullptr, dr.as<uint32_t>(), out->rows_cap, k == 0 ? 0 : -1, comp,
+                      tot.as<unsigned long long>() + k);
+    if (rc) return rc;
+    CK(cudaEventRecord(ev_done[k], comp));
+  }
+  // slab by slab: wait for its kernels, read its slot total (8 bytes), then queue the copy of its rows and block tables —
+  // which runs on the copy engine under the kernels of the slabs that follow
+  int64_t done_slots = 0;
+  for (int k = 0; k < n_slabs; ++k) {
+    const int64_t lo = (int64_t)k * per, hi = std::min<int64_t>(C, lo + per);
+    CK(cudaStreamWaitEvent(copy, ev_done[k], 0));
+    CK(cudaMemcpyAsync(&S.pin[k], tot.as<unsigned long long>() + k, sizeof(unsigned long long), cudaMemcpyDeviceToHost, copy));
+    const int64_t b0 = lo >> 5, b1 = (hi + 31) >> 5;
+    CK(cudaMemcpyAsync(out->blk_row + b0, pl->blk_row.as<uint32_t>() + b0, (size_t)(b1 - b0) * 4, cudaMemcpyDeviceToHost, copy));
+    CK(cudaMemcpyAsync(out->blk_mask + b0, pl->blk_mask.as<uint32_t>() + b0, (size_t)(b1 - b0) * 4, cudaMemcpyDeviceToHost, copy));
+    CK(cudaMemcpyAsync(out->blk_wide + b0, pl->blk_wide.as<uint32_t>() + b0, (size_t)(b1 - b0) * 4, cudaMemcpyDeviceToHost, copy));
+    CK(cudaEventRecord(ev_cnt[k], copy));
+    CK(cudaEventSynchronize(ev_cnt[k]));
+    const int64_t lim = std::min<int64_t>((int64_t)S.pin[k], out->rows_cap);
+    if (lim > done_slots) {
+      CK(cudaMemcpyAsync(out->rows + (size_t)done_slots * pl->row_w, dr.as<uint32_t>() + (size_t)done_slots * pl->row_w,
+                         (size_t)(lim - done_slots) * row_bytes, cudaMemcpyDeviceToHost, copy));
+      done_slots = lim;
+    }
+  }
+  CK(cudaStreamSynchronize(copy));
+  int64_t nf = 0;
+  rc = stryke_b200_plan_status(pl, comp, &nf);
+  int64_t ns = 0;
+  stryke_b200_plan_compact_totals(pl, comp, &ns, nullptr);
+  out->n_slots = ns; out->n_fish = nf;
+  return rc;
 }
 
 static int params15_to_coef(int kind, const double* p, double* uc) {

@@ -22,6 +22,12 @@ typedef unsigned long size_t;
 #define STRYKE_UNIT_COEF_W 8
 #define STRYKE_SPECIES_W 20
 #define STRYKE_DAILY_W 5
+#define STRYKE_FLAG_NO_PROMOTE 1u
+typedef struct StrykeCellGroup {
+  int64_t cell0;
+  int32_t iterations, n_active_days, day0, species, active_off, reserved;
+  uint64_t id_base;
+} StrykeCellGroup;
 #else
 #include <stdint.h>
 #include "../../include/stryke_b200.h"
@@ -121,6 +127,21 @@ struct TraceDev {
   float* length_ft; double* length_ft64; uint8_t* state; float* rate; uint8_t* survival; double* strike; double* baro;
 };
 
+// Compact tally rows (plan_launch_compact): ONE row per cell that holds fish, nothing for the others.  A row is a slot of
+// row_w = n_pairs + 3 words.  Narrow layout (n <= narrow_max, so that no counter can pass 65 535): 16-bit counters in pairs,
+//   w0 = pop_size | mortality_barotrauma << 16,  w1 = num_entrained | num_survived << 16,
+//   w2 = mortality_impingement | mortality_blade_strike << 16,  w[3 + p] = successes_p | count_p << 16.
+// Wide layout (larger cells; TWO consecutive slots = 2 n_pairs + 6 words): 32-bit counters,
+//   w0 = pop_size, w1..w5 = the five Daily columns, w[6 + 2p] = successes_p, w[7 + 2p] = count_p.
+// Per aligned block of 32 cells: blk_row = slot of its first present cell, blk_mask = cells with fish, blk_wide = cells in
+// the wide layout.  count_kernel zeroes the rows and writes pop_size; the passage kernels add with red.global.
+struct RowsDev {
+  uint32_t* rows;               // nullptr = dense output (KParams::daily / state_daily)
+  uint32_t* blk_row; uint32_t* blk_mask; uint32_t* blk_wide;
+  int row_w, narrow_max;
+  unsigned int cap;             // slots the rows buffer holds
+};
+
 struct KParams {
   const NodeRec* nodes; const uint8_t* edge_dst; const MoveRec* moves; const uint8_t* pair_node;
   const double* unit_static;
@@ -136,6 +157,13 @@ struct KParams {
   uint32_t ks[20];                    // Philox key schedule of (seed_lo, seed_hi), throughput kernels
   unsigned long long* work_counter;   // throughput kernels: next chunk of tiles to hand out (zeroed before every launch)
   int chunk_tiles, chunk_min;         // largest and smallest chunk (tiles) of the guided schedule
+  int rng_wide;                       // general fp64 kernel: wide native stream (53-bit uniforms, sequential cause rolls)
+  uint32_t flags;                     // STRYKE_FLAG_*
+  // implicit cell list (StrykeCells.groups): cell c of group g = cell0 + d * iterations + i  ->  day row, species, Philox id
+  const StrykeCellGroup* groups; int n_groups; const int32_t* active_days; uint64_t id_days, id_add;
+  int64_t cell_base;                  // index of this launch's first cell in the plan's cell list (launches over a range)
+  RowsDev out;                        // compact tally rows
+  const int64_t* blk_tile;            // pooled remainders: first tile of every aligned block of 32 cells [n_blocks + 1]
   const uint32_t* blk_S;              // pooled remainders (passage_fast.cuh): per block of 32 cells, shared tiles [0:31) | mixed [31]
 };
 
@@ -150,6 +178,81 @@ struct KParams {
 #else
 #define STRYKE_BCHK(P, cond, site) do { } while (0)
 #endif
+
+// (day row, species row, Philox cell id) of cell c of the launch — from the explicit arrays or from the group table
+struct CellInfo { int day, species; uint64_t id; };
+__device__ __forceinline__ CellInfo cell_info(const KParams& P, int64_t c) {
+  CellInfo ci;
+  if (P.groups == nullptr) {
+    ci.day = P.cell_day[c]; ci.species = P.cell_species[c]; ci.id = P.cell_id[c];
+    return ci;
+  }
+  const int64_t gc = c + P.cell_base;
+  int lo = 0, hi = P.n_groups;                      // last group with cell0 <= gc
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (P.groups[mid].cell0 <= gc) lo = mid; else hi = mid; }
+  const StrykeCellGroup g = P.groups[lo];
+  const int64_t local = gc - g.cell0;
+  const int dd = (int)(local / g.iterations);
+  const int it = (int)(local - (int64_t)dd * g.iterations);
+  const int rel = P.active_days[g.active_off + dd];
+  ci.day = g.day0 + rel; ci.species = g.species;
+  ci.id = (g.id_base + (uint64_t)it) * P.id_days + (uint64_t)rel + P.id_add;
+  return ci;
+}
+
+// Lane-held accumulators of one cell (lane p + 32 r owns pair p + 32 r, lanes 0..4 the Daily columns) -> global tallies.
+// Dense output: red.global into daily[cell][5] / state_daily[cell][pair][2].  Compact output: into the cell's row.
+// Called by all 32 lanes.
+template <int PR>
+__device__ __forceinline__ void tally_flush(const KParams& P, int64_t cell, int lane, int n_pairs, uint32_t (&acc_suc)[PR],
+                                            uint32_t (&acc_cnt)[PR], uint32_t& acc_daily) {
+  if (P.out.rows == nullptr) {
+#pragma unroll
+    for (int r = 0; r < PR; ++r) {
+      const int p = r * 32 + lane;
+      if (p < n_pairs && acc_cnt[r]) {
+        uint32_t* dst = P.state_daily + ((size_t)cell * n_pairs + p) * 2;
+        if (acc_suc[r]) atomicAdd(dst, acc_suc[r]);
+        atomicAdd(dst + 1, acc_cnt[r]);
+      }
+    }
+    if (lane < STRYKE_DAILY_W && acc_daily) atomicAdd(P.daily + (size_t)cell * STRYKE_DAILY_W + lane, acc_daily);
+  } else {
+    const int64_t b = cell >> 5;
+    const int lc = (int)(cell & 31);
+    const uint32_t m = P.out.blk_mask[b], wm = P.out.blk_wide[b], below = (1u << lc) - 1u;
+    const unsigned int slot = P.out.blk_row[b] + __popc(m & below) + __popc(wm & below);
+    const bool wide = (wm >> lc) & 1u;
+    const uint32_t up = __shfl_down_sync(0xffffffffu, acc_daily, 1);
+    if (slot + (wide ? 2u : 1u) <= P.out.cap) {
+      uint32_t* row = P.out.rows + (size_t)slot * P.out.row_w;
+      if (wide) {
+#pragma unroll
+        for (int r = 0; r < PR; ++r) {
+          const int p = r * 32 + lane;
+          if (p < n_pairs && acc_cnt[r]) {
+            if (acc_suc[r]) atomicAdd(row + 6 + 2 * p, acc_suc[r]);
+            atomicAdd(row + 7 + 2 * p, acc_cnt[r]);
+          }
+        }
+        if (lane < STRYKE_DAILY_W && acc_daily) atomicAdd(row + 1 + lane, acc_daily);
+      } else {
+#pragma unroll
+        for (int r = 0; r < PR; ++r) {
+          const int p = r * 32 + lane;
+          if (p < n_pairs && acc_cnt[r]) atomicAdd(row + 3 + p, acc_suc[r] | (acc_cnt[r] << 16));
+        }
+        const uint32_t w = acc_daily | (up << 16);
+        if (lane == 0 && w) atomicAdd(row + 1, w);                       // num_entrained | num_survived << 16
+        if (lane == 2 && w) atomicAdd(row + 2, w);                       // impingement | blade strike << 16
+        if (lane == 4 && acc_daily) atomicAdd(row, acc_daily << 16);     // pop_size | barotrauma << 16
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < PR; ++r) { acc_suc[r] = 0; acc_cnt[r] = 0; }
+  acc_daily = 0;
+}
 
 constexpr double P_ATM = 101325.0;    // scipy.constants.atm (stryke.py:1472)
 constexpr double G_SI = 9.80665;      // scipy.constants.g   (stryke.py:1471)
@@ -169,56 +272,59 @@ __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.
 __device__ __forceinline__ float cos_2pi(float turns) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(turns * 6.283185307f)); return y; }
 __device__ __forceinline__ float exp_approx(float x) { return ex2_approx(x * 1.44269504f); }
 
-template <typename Real> __device__ __forceinline__ Real u_co(uint32_t x);   // [0,1)
-template <typename Real> __device__ __forceinline__ Real u_oc(uint32_t x);   // (0,1]
+// Uniforms of the native stream.  Every uniform is the CENTRE of its grid cell: (k + 1/2) / 2^b for the b random bits k,
+// i.e. strictly inside (0, 1) and symmetric.  A floor grid k / 2^b would make P(u >= a) low by 2^-(b+1) on average — at
+// 16 bits 7.6e-6, measurable on the mortality-cause counters at 1e9-1e10 fish — and put a point mass at 0; with the
+// centred grid the error of P(u >= a) is zero-mean over thresholds a that vary from fish to fish (strike and barotrauma
+// probabilities depend on the fish's length) and at most 2^-24 = 6e-8 for the fixed thresholds (a-priori survival,
+// routing cdf), which the 23-bit uniforms serve.  Cost: none — the constant of the FADD changes from 1 to 1 - 2^-(b+1).
+// All values are exact in fp32 AND fp64, so the fp64 kernels see the SAME uniforms as the fp32 ones: a native-RNG run
+// differs between the precisions only where the arithmetic rounds across a threshold (tests compare them fish by fish).
+template <typename Real> __device__ __forceinline__ Real u23(uint32_t x);    // bits [31:9]: dice, routing
+template <typename Real> __device__ __forceinline__ Real u16hi(uint32_t w);  // bits [31:16]: r/R, Box-Muller radius
+template <typename Real> __device__ __forceinline__ Real u16lo(uint32_t w);  // bits [15:0]: cause roll, Box-Muller angle
 // 23 random mantissa bits under exponent 0: v in [1, 2); one ALU op + one FADD, no integer->float conversion (XU pipe)
 __device__ __forceinline__ float mantissa_float(uint32_t x) { return __uint_as_float((x >> 9) | 0x3f800000u); }
-template <> __device__ __forceinline__ float u_co<float>(uint32_t x) { return mantissa_float(x) - 1.0f; }
-template <> __device__ __forceinline__ float u_oc<float>(uint32_t x) { return 2.0f - mantissa_float(x); }
-// fp64 kernels see the SAME uniforms as the fp32 ones (23 bits of the word): a native-RNG run then differs between the
-// precisions only where the arithmetic rounds across a threshold (tests compare the two fish population by population)
-template <> __device__ __forceinline__ double u_co<double>(uint32_t x) { return (double)(x >> 9) * 1.1920928955078125e-07; }
-template <> __device__ __forceinline__ double u_oc<double>(uint32_t x) { return 1.0 - (double)(x >> 9) * 1.1920928955078125e-07; }
-
-// 16-bit uniforms from the high / low half of a word (disjoint bits), multiples of 2^-16: exact in fp32 and fp64, so
-// every kernel sees the same value.  hi_co, lo_co in [0, 1): k / 65536;  hi_oc in (0, 1]: 1 - k / 65536.
-template <typename Real> __device__ __forceinline__ Real u16hi_co(uint32_t w);
-template <typename Real> __device__ __forceinline__ Real u16hi_oc(uint32_t w);
-template <typename Real> __device__ __forceinline__ Real u16lo_co(uint32_t w);
+template <> __device__ __forceinline__ float u23<float>(uint32_t x) { return mantissa_float(x) - 0.99999994039535522461f; }   // 1 - 2^-24
+template <> __device__ __forceinline__ double u23<double>(uint32_t x) { return ((double)(x >> 9) + 0.5) * 1.1920928955078125e-07; }
 // piece already moved to mantissa bits [22:7]: ((x & 0x007fff80) | 0x3f800000) as ONE three-input logic op
 __device__ __forceinline__ float mantissa16(uint32_t x) {
   uint32_t r;
   asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(x), "r"(0x007fff80u), "r"(0x3f800000u));
   return __uint_as_float(r);
 }
-template <> __device__ __forceinline__ float u16hi_co<float>(uint32_t w) { return mantissa16(w >> 9) - 1.0f; }
-template <> __device__ __forceinline__ float u16hi_oc<float>(uint32_t w) { return 2.0f - mantissa16(w >> 9); }
-template <> __device__ __forceinline__ float u16lo_co<float>(uint32_t w) { return mantissa16(w << 7) - 1.0f; }
-template <> __device__ __forceinline__ double u16hi_co<double>(uint32_t w) { return (double)(w >> 16) * (1.0 / 65536.0); }
-template <> __device__ __forceinline__ double u16hi_oc<double>(uint32_t w) { return 1.0 - (double)(w >> 16) * (1.0 / 65536.0); }
-template <> __device__ __forceinline__ double u16lo_co<double>(uint32_t w) { return (double)(w & 0xffffu) * (1.0 / 65536.0); }
+#define STRYKE_C16 0.99999237060546875f        /* 1 - 2^-17 */
+template <> __device__ __forceinline__ float u16hi<float>(uint32_t w) { return mantissa16(w >> 9) - STRYKE_C16; }
+template <> __device__ __forceinline__ float u16lo<float>(uint32_t w) { return mantissa16(w << 7) - STRYKE_C16; }
+template <> __device__ __forceinline__ double u16hi<double>(uint32_t w) { return ((double)(w >> 16) + 0.5) * (1.0 / 65536.0); }
+template <> __device__ __forceinline__ double u16lo<double>(uint32_t w) { return ((double)(w & 0xffffu) + 0.5) * (1.0 / 65536.0); }
 
 // Barotrauma levels take no word of their own for the depth draw: r/R then uses the top 12 bits of the r/R + cause word,
 // and the depth uniform is built from 13 otherwise unused bits — bits [19:16] of that word and the 9 low bits of the dice
-// word (the dice uniform reads bits [31:9]).  Multiples of 2^-12 / 2^-13: identical in fp32 and fp64.
-template <typename Real> __device__ __forceinline__ Real u12hi_co(uint32_t w);
+// word (the dice uniform reads bits [31:9]).  Centred like the others: (k + 1/2) / 2^12, (k + 1/2) / 2^13.
+template <typename Real> __device__ __forceinline__ Real u12hi(uint32_t w);
 template <typename Real> __device__ __forceinline__ Real u13_depth(uint32_t w_rc, uint32_t w_dice);
-template <> __device__ __forceinline__ float u12hi_co<float>(uint32_t w) {
+template <> __device__ __forceinline__ float u12hi<float>(uint32_t w) {
   uint32_t r;
   asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(w >> 9), "r"(0x007ff800u), "r"(0x3f800000u));
-  return __uint_as_float(r) - 1.0f;
+  return __uint_as_float(r) - 0.9998779296875f;            // 1 - 2^-13
 }
-template <> __device__ __forceinline__ double u12hi_co<double>(uint32_t w) { return (double)(w >> 20) * (1.0 / 4096.0); }
+template <> __device__ __forceinline__ double u12hi<double>(uint32_t w) { return ((double)(w >> 20) + 0.5) * (1.0 / 4096.0); }
 __device__ __forceinline__ uint32_t depth_bits(uint32_t w_rc, uint32_t w_dice) { return ((w_rc >> 7) & 0x1e00u) | (w_dice & 0x1ffu); }
 template <> __device__ __forceinline__ float u13_depth<float>(uint32_t w_rc, uint32_t w_dice) {
-  return __uint_as_float((depth_bits(w_rc, w_dice) << 10) | 0x3f800000u) - 1.0f;
+  return __uint_as_float((depth_bits(w_rc, w_dice) << 10) | 0x3f800000u) - 0.99993896484375f;   // 1 - 2^-14
 }
 template <> __device__ __forceinline__ double u13_depth<double>(uint32_t w_rc, uint32_t w_dice) {
-  return (double)depth_bits(w_rc, w_dice) * (1.0 / 8192.0);
+  return ((double)depth_bits(w_rc, w_dice) + 0.5) * (1.0 / 8192.0);
 }
 
-__device__ __forceinline__ float std_normal(float u1_oc, float u2_co) {   // Box-Muller: MUFU lg2, sqrt, cos
-  return sqrt_approx(-1.3862943611f * lg2_approx(u1_oc)) * cos_2pi(u2_co);   // -2 ln u = -2 ln2 lg2 u
+// Length draw: Box-Muller from ONE word — radius from the high half, angle from the low half (65 536 radii x 65 536
+// angles; |z| <= sqrt(-2 ln 2^-17) = 4.85, i.e. 1.2e-6 of the normal mass is folded inwards.  Lengths are capped at 150 cm
+// (stryke.py:3076) which is z = 3.8 for the reference's example species, and a strike probability is linear in the
+// length, so the truncation moves no tally by more than 1e-8 relative; tests/test_gpu_high_power.py compares 1e10 fish
+// against the fp64 kernel's wide stream (two 53-bit uniforms, |z| <= 8.6) and tests/test_gpu_native_rng.py the tail mass).
+__device__ __forceinline__ float std_normal(float u1, float u2) {   // Box-Muller: MUFU lg2, sqrt, cos; u1, u2 in (0, 1)
+  return sqrt_approx(-1.3862943611f * lg2_approx(u1)) * cos_2pi(u2);   // -2 ln u = -2 ln2 lg2 u
 }
 
 }  // namespace stryke

@@ -43,7 +43,7 @@ __host__ __device__ inline uint32_t pack_node(int kind, int hasU, int unit, int 
 
 struct FastSmem {
   int nodes, ustatic, uc1, species, warp0, warp_stride, cdf, dst, ucoef, total;
-  int pool_blk, pool_ef, pool_rank, pool_seg;      // per-warp scratch of the pooled-remainder path (pool_nw > 0)
+  int pool_blk, pool_ef, pool_rank, pool_seg, pool_sd;   // per-warp scratch of the pooled-remainder path (pool_nw > 0)
   int pool_field;                                  // per block: where every (pair, arrivals | survivors) / Daily counter sits
 };
 // floats per row of the staged routing cdf: the stride-1 thresholds a draw is compared with, padded to whole float4s
@@ -66,6 +66,7 @@ __host__ __device__ constexpr FastSmem fast_smem(int n_nodes, int n_units, int s
     L.pool_blk = w; w += 32 * 16;                            // uint4 per cell of the block: n, cell id (lo, hi), remainder offset
     L.pool_ef = w; w += 32 * 8;                              // int64 per cell: full tiles of the block before this cell
     L.pool_rank = w; w += 32 * 4;                            // lane of the rho-th cell that has a remainder
+    L.pool_sd = w; w += 32 * 8;                              // int2 per cell: species row, day row
     L.pool_seg = w; w = (w + 32 * pool_nw * 4 + 15) & ~15;         // per cell of the block: accumulated tally words
   }
   L.warp_stride = w;
@@ -228,26 +229,12 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
     }
   };
 
-  auto flush = [&](int64_t cell) {
-#pragma unroll
-    for (int r = 0; r < PR; ++r) {
-      const int p = r * 32 + lane;
-      if (p < n_pairs && acc_cnt[r]) {
-        uint32_t* dst = P.state_daily + ((size_t)cell * n_pairs + p) * 2;
-        if (acc_suc[r]) atomicAdd(dst, acc_suc[r]);
-        atomicAdd(dst + 1, acc_cnt[r]);
-      }
-      acc_suc[r] = 0; acc_cnt[r] = 0;
-    }
-    if (lane < STRYKE_DAILY_W && acc_daily) atomicAdd(P.daily + (size_t)cell * STRYKE_DAILY_W + lane, acc_daily);
-    acc_daily = 0;
-  };
+  auto flush = [&](int64_t cell) { tally_flush<PR>(P, cell, lane, n_pairs, acc_suc, acc_cnt, acc_daily); };
 
   const int n_moves = TP::kStatic ? TP::M : P.n_moves;
 
   // species parameters and the day's tables of cell c (both kept across cells: neighbours share them)
-  auto load_params = [&](int64_t c) {
-    const int s = P.cell_species[c];
+  auto load_params = [&](const int s, const int d) {
     if (s == cur_species) {
       // cells are ordered group by group: the neighbours of a cell almost always belong to the same species
     } else if (s < n_sp) {
@@ -262,7 +249,6 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
       sp_mode = (int)q[5]; sp_wr = (float)q[6]; sp_uc = (float)q[7]; sp_d1 = (float)q[8];
       sp_dd = (float)q[9] - (float)q[8]; sp_b0 = (float)q[10] * 1.44269504f; sp_b1 = (float)q[11];
     }
-    const int d = P.cell_day[c];
     if (d != cur_day) {   // stage the day's routing rows and unit coefficients in this warp's slot
       cur_day = d;
       __syncwarp();
@@ -309,7 +295,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
     };
 
     // ---- (2) length: word 0, radius from the high half, angle from the low half --------------------------------------
-    const float z = std_normal(u16hi_oc<float>(w[0]), u16lo_co<float>(w[0]));
+    const float z = std_normal(u16hi<float>(w[0]), u16lo<float>(w[0]));
     float L;
     if (sp_mode == 0) L = fminf(fabsf(fmaf(exp_approx(sp_ls * z), sp_lsc, sp_ll)), 150.f) * 0.0328084f;
     else L = fabsf(fmaf(sp_lsd, z, sp_lm)) * (1.f / 12.f);
@@ -351,9 +337,9 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
       uint32_t w_dice = 0;
       if (mv.need & NEED_CAUSE) {                        // this level has turbine nodes (uniform)
         const uint32_t w_rc = word(mv.slot_rc);          // r/R in the high half, cause roll in the low half
-        const float u_cau = u16lo_co<float>(w_rc);
+        const float u_cau = u16lo<float>(w_rc);
         // barotrauma: 12-bit r/R, depth draw from spare bits of this word and of the dice word (passage_common.cuh)
-        const float u_rr = BARO ? u12hi_co<float>(w_rc) : u16hi_co<float>(w_rc);
+        const float u_rr = BARO ? u12hi<float>(w_rc) : u16hi<float>(w_rc);
         if (BARO) w_dice = word(mv.slot_dice);
         const float u_dep = BARO ? u13_depth<float>(w_rc, w_dice) : 0.f;
         const bool turb = alive && kind != STRYKE_KIND_APRIORI;
@@ -383,7 +369,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         cz += turb ? code : 0u;
       }
       bool surv;
-      if (mv.need & NEED_DICE) surv = alive && (u_oc<float>((BARO && (mv.need & NEED_CAUSE)) ? w_dice : word(mv.slot_dice)) <= rate);
+      if (mv.need & NEED_DICE) surv = alive && (u23<float>((BARO && (mv.need & NEED_CAUSE)) ? w_dice : word(mv.slot_dice)) <= rate);
       else surv = alive;      // no dice <=> every node of the level is a-priori with survival >= 1 (host rule): u <= rate always
 
       // ---- (6) State_Daily: lane p owns pair p ---------------------------------------------------------------------
@@ -428,7 +414,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
       if (k < n_moves - 1) {
         int j = 0;
         if (mv.need & NEED_ROUTE) {
-          const float u = u_co<float>(word(mv.slot_route));
+          const float u = u23<float>(word(mv.slot_route));
           // searchsorted(cdf, u, 'right') = number of thresholds <= u; rows are whole float4s padded with 2.0
           const float4* rowq = reinterpret_cast<const float4*>(s_cdf) + at * (crow >> 2);
           const int groups = ((int)mv.max_deg - 1 + 3) >> 2;
@@ -462,7 +448,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
     }
   };
 
-  const int64_t T = P.tile_off[P.n_cells];
+  const int64_t T = TP::POOL ? P.blk_tile[(P.n_cells + 31) >> 5] : P.tile_off[P.n_cells];
   // Work distribution.  The SM's warp arbiter does not share issue slots evenly, so equal static ranges finish unevenly and
   // leave the SM short of warps at the end; tiles are therefore handed out dynamically.
   // Guided self-scheduling: a warp takes (tiles not yet handed out) / (2 x warps of the grid) consecutive tiles from one
@@ -529,9 +515,9 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
       cur_cell = c;
       STRYKE_BCHK(P, c >= 0 && c < P.n_cells, 6);
       n_c = P.cell_n[c];
-      const uint64_t cid = P.cell_id[c];
-      cid_lo = (uint32_t)cid; cid_hi = (uint32_t)(cid >> 32);
-      load_params(c);
+      const CellInfo ci = cell_info(P, c);
+      cid_lo = (uint32_t)ci.id; cid_hi = (uint32_t)(ci.id >> 32);
+      load_params(ci.species, ci.day);
     }
     const int fish = fish_base + lane;
     STRYKE_BCHK(P, fish_base >= 0 && (lane != 0 || fish < n_c), 7);     // a tile always holds at least one fish of its cell
@@ -540,12 +526,13 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   }
   } else {
   // ---- pooled remainders (see pool_block): blocks of 32 cells; the tiles of block b are its shared tiles, then the
-  // full tiles of its cells in order.  tile_off[32 b] is the block's first tile.  A shared tile's per-lane counters are
+  // full tiles of its cells in order.  blk_tile[b] is the block's first tile.  A shared tile's per-lane counters are
   // added to per-cell accumulator words in shared memory (whole words: a cell has at most 31 pooled fish, no field can
   // carry); when the warp leaves the block the accumulators go to global memory, one lane per (cell, counter).
   uint4* s_blk = reinterpret_cast<uint4*>(wbase + SL.pool_blk);
   long long* s_ef = reinterpret_cast<long long*>(wbase + SL.pool_ef);
   int* s_rank = reinterpret_cast<int*>(wbase + SL.pool_rank);
+  int2* s_sd = reinterpret_cast<int2*>(wbase + SL.pool_sd);
   uint32_t* s_acc = reinterpret_cast<uint32_t*>(wbase + SL.pool_seg);        // [32 cells][NW]
   uint32_t* s_field = reinterpret_cast<uint32_t*>(smem + SL.pool_field);     // [2 n_pairs + 5]: word [0:5) shift [5:10) 10-bit [10] exists [11]
   const int NI = 2 * n_pairs + STRYKE_DAILY_W;
@@ -565,7 +552,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   for (int q = 0; q < TP::NW; ++q) s_acc[lane * TP::NW + q] = 0u;
   __syncthreads();
   const int64_t NB = (P.n_cells + 31) >> 5;
-  auto blk_off = [&](int64_t b) -> int64_t { const int64_t c = b << 5; return P.tile_off[c < P.n_cells ? c : P.n_cells]; };
+  auto blk_off = [&](int64_t b) -> int64_t { return P.blk_tile[b]; };
   const uint32_t below = (2u << lane) - 1u;           // bits 0 .. lane
   int64_t b = -1, b_begin = 0, b_end = 0;             // current block and its tile range
   int S_b = 0, nrem = 0;                              // its shared tiles, its cells with a remainder
@@ -574,6 +561,10 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
     if (pool_dirty) {
       pool_dirty = false;
       __syncwarp();
+      const bool compact = P.out.rows != nullptr;
+      uint32_t bm = 0, bw = 0;
+      unsigned int slot0 = 0;
+      if (compact) { bm = P.out.blk_mask[b]; bw = P.out.blk_wide[b]; slot0 = P.out.blk_row[b]; }
       for (int i0 = 0; i0 < NI; i0 += 32) {           // lane <-> counter i0 + lane, loop over the cells with a remainder
         const int i = i0 + lane;
         const uint32_t cf = i < NI ? s_field[i] : 0u;
@@ -581,14 +572,38 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         const uint32_t sh = (cf >> 5) & 31u;
         const uint32_t mask = ((cf >> 11) & 1u) ? (((cf >> 10) & 1u) ? 1023u : 63u) : 0u;
         const bool state = i < 2 * n_pairs;
-        uint32_t* base = state ? P.state_daily + i : P.daily + (i - 2 * n_pairs);
-        const uint32_t per_cell = state ? (uint32_t)(2 * n_pairs) : (uint32_t)STRYKE_DAILY_W;
-        base += (size_t)(b << 5) * per_cell;
-        for (int rho = 0; rho < nrem; ++rho) {
-          const int jl = s_rank[rho];
-          const uint32_t v = (s_acc[jl * TP::NW + wq] >> sh) & mask;
-          STRYKE_BCHK(P, (b << 5) + jl < P.n_cells, 12);
-          if (v) atomicAdd(base + (uint32_t)jl * per_cell, v);
+        if (!compact) {
+          uint32_t* base = state ? P.state_daily + i : P.daily + (i - 2 * n_pairs);
+          const uint32_t per_cell = state ? (uint32_t)(2 * n_pairs) : (uint32_t)STRYKE_DAILY_W;
+          base += (size_t)(b << 5) * per_cell;
+          for (int rho = 0; rho < nrem; ++rho) {
+            const int jl = s_rank[rho];
+            const uint32_t v = (s_acc[jl * TP::NW + wq] >> sh) & mask;
+            STRYKE_BCHK(P, (b << 5) + jl < P.n_cells, 12);
+            if (v) atomicAdd(base + (uint32_t)jl * per_cell, v);
+          }
+        } else {
+          // compact rows: counters 2p (successes) / 2p + 1 (count) of a narrow cell share one word, as do the Daily columns
+          const int dj = i - 2 * n_pairs;
+          const int wide_idx = state ? 6 + i : 1 + dj;
+          const int narrow_idx = state ? 3 + (i >> 1) : (dj == 0 ? 1 : dj == 2 ? 2 : 0);
+          for (int rho = 0; rho < nrem; ++rho) {
+            const int jl = s_rank[rho];
+            const uint32_t v = (s_acc[jl * TP::NW + wq] >> sh) & mask;
+            const uint32_t up = __shfl_down_sync(0xffffffffu, v, 1);
+            const uint32_t bl = (1u << jl) - 1u;
+            const unsigned int slot = slot0 + __popc(bm & bl) + __popc(bw & bl);
+            const bool wide = (bw >> jl) & 1u;
+            uint32_t* row = P.out.rows + (size_t)slot * P.out.row_w;
+            if (slot + (wide ? 2u : 1u) <= P.out.cap && i < NI) {
+              if (wide) {
+                if (v) atomicAdd(row + wide_idx, v);
+              } else if (!(i & 1)) {
+                const uint32_t w2 = (!state && dj == 4) ? (v << 16) : (v | (up << 16));
+                if (w2) atomicAdd(row + narrow_idx, w2);
+              }
+            }
+          }
         }
       }
       __syncwarp();
@@ -646,7 +661,9 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         const int64_t ci = (b << 5) + lane;
         const bool in = ci < P.n_cells;
         const int n = in ? P.cell_n[ci] : 0;
-        const uint64_t id = in ? P.cell_id[ci] : 0ull;
+        CellInfo cinf{0, 0, 0ull};
+        if (in) cinf = cell_info(P, ci);
+        const uint64_t id = cinf.id;
         const uint32_t info = P.blk_S[b];
         S_b = (int)(info & 0x7fffffffu);
         const int r = n & 31, f = n >> 5;
@@ -664,6 +681,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         __syncwarp();
         s_blk[lane] = make_uint4((uint32_t)n, (uint32_t)id, (uint32_t)(id >> 32), (uint32_t)(sr - pr));
         s_ef[lane] = sf - f;
+        s_sd[lane] = make_int2(cinf.species, cinf.day);
         if (r > 0) s_rank[__popc(rmask & (below >> 1))] = lane;
         __syncwarp();
       }
@@ -689,7 +707,8 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         active = fish < n;
         STRYKE_BCHK(P, fish >= (n & ~31) && (lane != 0 || active), 11);
         cid_lo = cellrec.y; cid_hi = cellrec.z;
-        load_params((b << 5) + __shfl_sync(0xffffffffu, jl, 0));
+        const int2 sd = s_sd[__shfl_sync(0xffffffffu, jl, 0)];
+        load_params(sd.x, sd.y);
       } else {                                          // full tile jj of the block: which cell?
         const long long jj = j - S_b;
         const long long ef = s_ef[lane];
@@ -704,7 +723,8 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         fish = fish_base + lane;
         cur_cell = (b << 5) + sel;
         cid_lo = cellrec.y; cid_hi = cellrec.z;
-        load_params(cur_cell);
+        const int2 sd = s_sd[sel];
+        load_params(sd.x, sd.y);
       }
       chunk_left -= run;
       t += run;

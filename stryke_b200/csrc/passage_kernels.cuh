@@ -57,6 +57,9 @@ __device__ __forceinline__ float baro_surv32(float depth_ft, float c0, float c1,
 // ------------------------------------------------------------------------------------------------------------------
 // native RNG: word slot -> Philox block, warp-uniform refill points
 // ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {   // numpy-style 53-bit double in [0,1)
+  return (double)((((uint64_t)hi >> 5) << 26) | ((uint64_t)lo >> 6)) * (1.0 / 9007199254740992.0);
+}
 struct FishRng {
   uint32_t c0, c1, c2, k0, k1;
   uint32_t w[4];
@@ -70,7 +73,13 @@ struct FishRng {
     const int s = slot & 3;
     return (s & 2) ? ((s & 1) ? w[3] : w[2]) : ((s & 1) ? w[1] : w[0]);
   }
+  // wide stream (StrykeOpts.rng_mode = 1): one draw = two words (even slot) = a 53-bit uniform in [0, 1) like numpy's
+  __device__ __forceinline__ double wide(int slot) { const uint32_t hi = word(slot), lo = word(slot + 1); return u53(hi, lo); }
 };
+// Wide stream layout: block 0 = the two uniforms of the length draw; move k owns blocks 1 + 4k .. 4 + 4k, draw j of the
+// move sits at word slot 4 + 16 k + 2 j:  j = 0 r/R, 1 depth, 2..4 the reference's sequential cause rolls (stryke.py:1545-1560),
+// 5 survival dice, 6 routing.
+__device__ __forceinline__ int wide_slot(int k, int j) { return 4 + 16 * k + 2 * j; }
 __device__ __forceinline__ double std_normal(double u1_oc, double u2_co) {
   return sqrt(-2.0 * log(u1_oc)) * cospi(2.0 * u2_co);
 }
@@ -78,23 +87,18 @@ __device__ __forceinline__ double std_normal(double u1_oc, double u2_co) {
 // ------------------------------------------------------------------------------------------------------------------
 // (1) presence roll + daily entrainment count, one thread per cell
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {   // numpy-style 53-bit double in [0,1)
-  return (double)((((uint64_t)hi >> 5) << 26) | ((uint64_t)lo >> 6)) * (1.0 / 9007199254740992.0);
-}
 
 // Pooled remainders (throughput kernel, population mode: most present cells hold fewer than 32 fish).  Cells are taken
 // in aligned blocks of 32; a cell of n fish keeps n >> 5 full tiles of its own, the n & 31 fish left over are laid end to
 // end with those of the other cells of its block and cut into shared tiles.  A block whose cells differ in species or
-// day ("mixed") keeps one tile per remainder instead (the day tables and species parameters are warp-uniform).  The warp
-// of count_kernel that drew the 32 counts writes the block's number of shared tiles (bit 31: mixed); the scans then
-// charge them to the first cell of the block.  Called by all 32 lanes; lanes past the last cell pass in = false, n = 0.
-__device__ __forceinline__ void pool_block(uint32_t* __restrict__ blk_S, int64_t c, bool in, int n, int sp, int dy) {
-  const int lane = threadIdx.x & 31;
+// day ("mixed") keeps one tile per remainder instead (the day tables and species parameters are warp-uniform).  Returns
+// the block's number of shared tiles (bit 31: mixed).  Called by all 32 lanes; lanes past the last cell pass in = false.
+__device__ __forceinline__ uint32_t pool_block(bool in, int n, int sp, int dy) {
   const int sp0 = __shfl_sync(0xffffffffu, sp, 0), dy0 = __shfl_sync(0xffffffffu, dy, 0);
   const bool mixed = __ballot_sync(0xffffffffu, in && (sp != sp0 || dy != dy0)) != 0u;
   const int r = n & 31;
   const uint32_t tot = mixed ? 32u * (uint32_t)__popc(__ballot_sync(0xffffffffu, r > 0)) : __reduce_add_sync(0xffffffffu, (uint32_t)r);
-  if (lane == 0) blk_S[c >> 5] = ((tot + 31u) >> 5) | (mixed ? 0x80000000u : 0u);
+  return ((tot + 31u) >> 5) | (mixed ? 0x80000000u : 0u);
 }
 
 // Per-species constants of the truncated Pareto draw (truncated_rvs, stryke.py:75-106): the upper truncation point, the
@@ -115,15 +119,57 @@ __global__ void pareto_constants_kernel(const double* __restrict__ species, int 
   out[s * STRYKE_PARETO_W + 3] = 0.0;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// (1) count_kernel: presence roll + daily entrainment count, one thread per cell — and, in the same pass, everything the
+// passage kernel needs to find its work: the exclusive prefix sums of tiles, fish and row slots over the cells (a
+// single-pass scan with decoupled look-back over the thread blocks), the per-block tables of the pooled remainders and of
+// the compact rows, and the zeroed rows themselves.  One launch instead of count + three scan kernels + memsets.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int COUNT_T = 256;
+// plan status words.  ERR_WORD: 0 = fine; top bits 11 = bounds check (debug build), 101 = cell_day / cell_species out of
+// range, 100 = non-finite or negative count (low 32 bits: cell); else count << 32 | cell of a cell above max_daily_fish.
+// ERR_WORK (chunk counter of the throughput kernels) and ERR_TICKET are cleared before every launch; ERR_SLOTS carries the
+// slot count from one range of cells to the next, ERR_FISH_CUM the fish.
+enum : int { ERR_WORD = 0, ERR_WORK = 1, ERR_TICKET = 2, ERR_FISH = 3, ERR_FISH_CUM = 4, ERR_SLOTS = 5, ERR_TILES = 6, ERR_N = 8 };
+constexpr unsigned long long ERRBIT_RANGE = 0xA000000000000000ull, ERRBIT_NONFINITE = 0x8000000000000000ull;
+struct ScanDev {                  // decoupled look-back state, one entry per thread block of count_kernel
+  unsigned int* flag;             // 4 * epoch + 1: aggregate published, 4 * epoch + 2: inclusive prefix published
+  long long* agg;                 // [n_blocks][3] tiles, fish, slots of the block
+  long long* incl;                // [n_blocks][3] inclusive prefix
+  unsigned int epoch;             // changes with every launch: the flags need no clearing
+};
+struct CountOut {
+  int32_t* cell_n;
+  int64_t* tile_off;              // [n_cells + 1] or nullptr (pooled plans use blk_tile)
+  int64_t* fish_off;              // [n_cells + 1] or nullptr (only the injected / trace paths read it)
+  int64_t* blk_tile;              // [n_blocks + 1] or nullptr
+  uint32_t* blk_S;                // [n_blocks] or nullptr: shared tiles of the block | mixed << 31
+  unsigned long long* err;        // ERR_* words
+  long long slot0;                // compact rows: first slot of this launch, < 0 = continue after the previous launch
+  unsigned long long* slots_after;    // optional: receives the slot count after this launch's cells
+};
+
 template <bool INJECT>
-__global__ void count_kernel(KParams P, const double* __restrict__ day_Q, int32_t* __restrict__ cell_n,
-                             int max_daily_fish, unsigned long long* __restrict__ err, uint32_t* __restrict__ blk_S,
-                             const double* __restrict__ pareto) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(COUNT_T) count_kernel(const KParams P, const double* __restrict__ day_Q, const CountOut O,
+                                                        const int max_daily_fish, const double* __restrict__ pareto,
+                                                        const ScanDev S, const int n_days, const int n_species) {
+  __shared__ unsigned int s_bid;
+  __shared__ long long s_w[COUNT_T / 32][3];
+  __shared__ long long s_pre[3];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_bid = atomicAdd(reinterpret_cast<unsigned int*>(O.err + ERR_TICKET), 1u);
+  __syncthreads();
+  const unsigned int bid = s_bid;      // thread blocks take their cells in ticket order: a block only ever waits for started ones
+  const int64_t c = (int64_t)bid * COUNT_T + threadIdx.x;
   const bool in = c < P.n_cells;
-  int species_c = 0, n_c = 0;
+  int species_c = 0, day_c = 0, n_c = 0;
   if (in) {
-  species_c = P.cell_species[c];
+  const CellInfo ci = cell_info(P, c);
+  species_c = ci.species; day_c = ci.day;
+  if (species_c < 0 || species_c >= n_species || day_c < 0 || day_c >= n_days) {      // (validated here, not on the host)
+    atomicMax(O.err, ERRBIT_RANGE | (unsigned long long)(c & 0xFFFFFFFFll));
+    species_c = 0; day_c = 0;
+  } else {
   const double* sp = P.species + (int64_t)species_c * STRYKE_SPECIES_W;
   const int kind = (int)sp[12];
   const double shape = sp[13], loc = sp[14], scale = sp[15], max_rate = sp[16], occur = sp[17];
@@ -132,7 +178,7 @@ __global__ void count_kernel(KParams P, const double* __restrict__ day_Q, int32_
   if (INJECT) {
     presence = P.inj.presence[c];
   } else {
-    const uint64_t id = P.cell_id[c];
+    const uint64_t id = ci.id;
     Philox::block(0xFFFFFFFFu, (uint32_t)id, (uint32_t)(id >> 32), 0u, P.seed_lo, P.seed_hi, w);
     if (kind == STRYKE_ENT_LOGNORMAL) Philox::block(0xFFFFFFFFu, (uint32_t)id, (uint32_t)(id >> 32), 1u, P.seed_lo, P.seed_hi, v);
     presence = u53(w[0], w[1]);
@@ -170,104 +216,130 @@ __global__ void count_kernel(KParams P, const double* __restrict__ day_Q, int32_
       }
       rate = fabs(rate);                                         // stryke.py:2567
       if (capped && rate > max_rate * 10.0) rate = max_rate * 10.0;   // stryke.py:2578-2582
-      const double Mft3 = (60.0 * 60.0 * 24.0 * day_Q[P.cell_day[c]]) / 1000000.0;   // stryke.py:2585
+      const double Mft3 = (60.0 * 60.0 * 24.0 * day_Q[day_c]) / 1000000.0;   // stryke.py:2585
       const double nf = rint(Mft3 * rate);                       // np.round: half to even
-      if (!isfinite(nf) || nf < 0.0) { atomicMax(err, 0x8000000000000000ull | (unsigned long long)c); n = 0; }
+      if (!isfinite(nf) || nf < 0.0 || nf > 2147483647.0) { atomicMax(O.err, ERRBIT_NONFINITE | (unsigned long long)(c & 0xFFFFFFFFll)); n = 0; }
       else n = (int64_t)nf;
     }
-    if (n == 0) n = 1;                                           // stryke.py:3032-3033
-    if (max_daily_fish > 0 && kind != STRYKE_ENT_FIXED && n > max_daily_fish) {    // stryke.py:2610-2616
-      atomicMax(err, ((unsigned long long)n << 32) | (unsigned long long)(c & 0xFFFFFFFFll));
+    if (n == 0 && !(P.flags & STRYKE_FLAG_NO_PROMOTE)) n = 1;    // stryke.py:3032-3033 (run(), not population_sim)
+    if (n < 0 || n > 0x7FFFFFFFll) { atomicMax(O.err, ERRBIT_NONFINITE | (unsigned long long)(c & 0xFFFFFFFFll)); n = 0; }
+    if (max_daily_fish > 0 && n > max_daily_fish) {              // stryke.py:2610-2616 (drawn counts), :3052 (fixed counts)
+      atomicMax(O.err, ((unsigned long long)(n & 0x7FFFFFFFll) << 32) | (unsigned long long)(c & 0xFFFFFFFFll));
       n = 0;
     }
-    if (n > 0x7FFFFFFFll) { atomicMax(err, 0x8000000000000000ull | (unsigned long long)c); n = 0; }
   }
-  cell_n[c] = (int32_t)n;
   n_c = (int)n;
   }
-  // (blockDim.x is a multiple of 32: a warp holds one aligned block of 32 cells; all its lanes arrive here together)
-  if (blk_S && (c & ~31ll) < P.n_cells) pool_block(blk_S, c, in, n_c, species_c, in ? P.cell_day[c] : 0);
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// exclusive scans of tiles-per-cell and fish-per-cell (three small kernels; int64 offsets)
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int SCAN_T = 1024, SCAN_PER = 4, SCAN_CH = SCAN_T * SCAN_PER;
-
-// tiles charged to cell c of n fish: blk_S == nullptr -> one tile per started 32 fish
-__device__ __forceinline__ int64_t cell_tiles(const uint32_t* __restrict__ blk_S, int64_t c, int32_t n) {
-  if (!blk_S) return (n + 31) >> 5;
-  return (int64_t)(n >> 5) + ((c & 31) == 0 ? (int64_t)(blk_S[c >> 5] & 0x7fffffffu) : 0);
-}
-
-__device__ __forceinline__ void block_scan2(int64_t& a, int64_t& b, int64_t* sh) {   // inclusive, 1024 threads
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  O.cell_n[c] = (int32_t)n_c;
+  }
+  // ---- per aligned block of 32 cells (= this warp): pooled-remainder tiles, row slots, prefix sums over the lanes -------
+  const uint32_t below = (1u << lane) - 1u;
+  const uint32_t mask = __ballot_sync(0xffffffffu, n_c > 0);
+  const uint32_t wmask = P.out.rows ? __ballot_sync(0xffffffffu, n_c > P.out.narrow_max) : 0u;
+  const int slots_w = P.out.rows ? __popc(mask) + __popc(wmask) : 0;
+  uint32_t info = 0;
+  if (O.blk_S) info = pool_block(in, n_c, species_c, day_c);
+  long long t = O.blk_S ? (long long)(n_c >> 5) + (lane == 0 ? (long long)(info & 0x7fffffffu) : 0ll) : (long long)((n_c + 31) >> 5);
+  long long f = n_c;
+  const long long t_own = t, f_own = f;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const int64_t ta = __shfl_up_sync(0xffffffffu, a, o), tb = __shfl_up_sync(0xffffffffu, b, o);
-    if (lane >= o) { a += ta; b += tb; }
+    const long long ta = __shfl_up_sync(0xffffffffu, t, o), fa = __shfl_up_sync(0xffffffffu, f, o);
+    if (lane >= o) { t += ta; f += fa; }
   }
-  if (lane == 31) { sh[wid] = a; sh[32 + wid] = b; }
+  if (lane == 31) { s_w[wid][0] = t; s_w[wid][1] = f; s_w[wid][2] = slots_w; }
   __syncthreads();
+  // ---- decoupled look-back over the thread blocks (warp 0) -----------------------------------------------------------
   if (wid == 0) {
-    int64_t sa = sh[lane], sb = sh[32 + lane];
+    long long a[3] = {0, 0, 0};
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int64_t ta = __shfl_up_sync(0xffffffffu, sa, o), tb = __shfl_up_sync(0xffffffffu, sb, o);
-      if (lane >= o) { sa += ta; sb += tb; }
+    for (int q = 0; q < COUNT_T / 32; ++q) { a[0] += s_w[q][0]; a[1] += s_w[q][1]; a[2] += s_w[q][2]; }
+    const unsigned int E = S.epoch * 4u;
+    volatile unsigned int* flag = S.flag;
+    volatile long long* agg = S.agg;
+    volatile long long* incl = S.incl;
+    long long run[3] = {0, 0, 0};
+    if (bid == 0) {
+      run[2] = O.slot0 >= 0 ? O.slot0 : (long long)O.err[ERR_SLOTS];      // slots continue after the previous range of cells
+      if (lane == 0) {
+        incl[0] = a[0]; incl[1] = a[1]; incl[2] = a[2] + run[2];
+        __threadfence();
+        flag[0] = E + 2u;
+      }
+    } else {
+      if (lane == 0) {
+        agg[3 * (size_t)bid] = a[0]; agg[3 * (size_t)bid + 1] = a[1]; agg[3 * (size_t)bid + 2] = a[2];
+        __threadfence();
+        flag[bid] = E + 1u;
+      }
+      long long look = (long long)bid - 1;
+      for (;;) {
+        const long long idx = look - lane;
+        unsigned int fl = E + 2u;                                // before the first block: an inclusive prefix of zero
+        if (idx >= 0) { do { fl = flag[idx]; } while (fl != E + 1u && fl != E + 2u); }
+        __threadfence();
+        const uint32_t im = __ballot_sync(0xffffffffu, fl == E + 2u);
+        const int first = __ffs(im) - 1;                         // nearest block that already knows its inclusive prefix
+        long long v[3] = {0, 0, 0};
+        if (idx >= 0 && (first < 0 || lane <= first)) {
+          volatile long long* src = (first >= 0 && lane == first) ? incl : agg;
+          v[0] = src[3 * (size_t)idx]; v[1] = src[3 * (size_t)idx + 1]; v[2] = src[3 * (size_t)idx + 2];
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+          run[q] += v[q];
+        }
+        if (first >= 0) break;
+        look -= 32;
+      }
+      if (lane == 0) {
+        incl[3 * (size_t)bid] = run[0] + a[0]; incl[3 * (size_t)bid + 1] = run[1] + a[1]; incl[3 * (size_t)bid + 2] = run[2] + a[2];
+        __threadfence();
+        flag[bid] = E + 2u;
+      }
     }
-    sh[lane] = sa; sh[32 + lane] = sb;
+    if (lane == 0) {
+      s_pre[0] = run[0]; s_pre[1] = run[1]; s_pre[2] = run[2];
+      if (bid == gridDim.x - 1) {                                // the block of the last cells: totals and end markers
+        O.err[ERR_TILES] = (unsigned long long)(run[0] + a[0]);
+        O.err[ERR_FISH] = (unsigned long long)(run[1] + a[1]);
+        O.err[ERR_FISH_CUM] += (unsigned long long)(run[1] + a[1]);
+        O.err[ERR_SLOTS] = (unsigned long long)(run[2] + a[2]);
+        if (O.slots_after) *O.slots_after = (unsigned long long)(run[2] + a[2]);
+        if (O.tile_off) O.tile_off[P.n_cells] = run[0] + a[0];
+        if (O.fish_off) O.fish_off[P.n_cells] = run[1] + a[1];
+        if (O.blk_tile) O.blk_tile[(P.n_cells + 31) >> 5] = run[0] + a[0];
+      }
+    }
   }
   __syncthreads();
-  if (wid > 0) { a += sh[wid - 1]; b += sh[32 + wid - 1]; }
-  __syncthreads();
-}
-
-__global__ void __launch_bounds__(SCAN_T) scan_partial(const int32_t* __restrict__ cell_n, int64_t n_cells,
-                                                       int64_t* __restrict__ part, const uint32_t* __restrict__ blk_S) {
-  __shared__ int64_t sh[64];
-  const int64_t base = (int64_t)blockIdx.x * SCAN_CH + threadIdx.x * SCAN_PER;
-  int64_t t = 0, f = 0;
-#pragma unroll
-  for (int i = 0; i < SCAN_PER; ++i)
-    if (base + i < n_cells) { const int32_t n = cell_n[base + i]; f += n; t += cell_tiles(blk_S, base + i, n); }
-  block_scan2(t, f, sh);
-  if (threadIdx.x == SCAN_T - 1) { part[2 * blockIdx.x] = t; part[2 * blockIdx.x + 1] = f; }
-}
-__global__ void __launch_bounds__(SCAN_T) scan_blocks(int64_t* __restrict__ part, int nb) {   // exclusive, in place
-  __shared__ int64_t sh[64];
-  const int per = (nb + SCAN_T - 1) / SCAN_T;
-  const int lo = threadIdx.x * per, hi = min(nb, lo + per);
-  int64_t t = 0, f = 0;
-  for (int i = lo; i < hi; ++i) { t += part[2 * i]; f += part[2 * i + 1]; }
-  int64_t it = t, jf = f;
-  block_scan2(it, jf, sh);
-  int64_t et = it - t, ef = jf - f;
-  for (int i = lo; i < hi; ++i) {
-    const int64_t a = part[2 * i], b = part[2 * i + 1];
-    part[2 * i] = et; part[2 * i + 1] = ef; et += a; ef += b;
+  long long bt = s_pre[0], bf = s_pre[1], bs = s_pre[2];
+  for (int q = 0; q < wid; ++q) { bt += s_w[q][0]; bf += s_w[q][1]; bs += s_w[q][2]; }
+  // ---- outputs --------------------------------------------------------------------------------------------------------
+  const int64_t blk = c >> 5;
+  const bool blk_in = (c & ~31ll) < P.n_cells;
+  if (in) {
+    if (O.tile_off) O.tile_off[c] = bt + t - t_own;
+    if (O.fish_off) O.fish_off[c] = bf + f - f_own;
   }
-}
-__global__ void __launch_bounds__(SCAN_T) scan_final(const int32_t* __restrict__ cell_n, int64_t n_cells,
-                                                     const int64_t* __restrict__ part, int64_t* __restrict__ tile_off,
-                                                     int64_t* __restrict__ fish_off, const uint32_t* __restrict__ blk_S) {
-  __shared__ int64_t sh[64];
-  const int64_t base = (int64_t)blockIdx.x * SCAN_CH + threadIdx.x * SCAN_PER;
-  int32_t nn[SCAN_PER];
-  int64_t t = 0, f = 0;
-#pragma unroll
-  for (int i = 0; i < SCAN_PER; ++i) {
-    nn[i] = base + i < n_cells ? cell_n[base + i] : 0;
-    f += nn[i]; t += base + i < n_cells ? cell_tiles(blk_S, base + i, nn[i]) : 0;
+  if (blk_in && lane == 0) {
+    if (O.blk_S) O.blk_S[blk] = info;
+    if (O.blk_tile) O.blk_tile[blk] = bt;
   }
-  int64_t it = t, jf = f;
-  block_scan2(it, jf, sh);
-  int64_t et = it - t + part[2 * blockIdx.x], ef = jf - f + part[2 * blockIdx.x + 1];
-#pragma unroll
-  for (int i = 0; i < SCAN_PER; ++i) {
-    if (base + i < n_cells) { tile_off[base + i] = et; fish_off[base + i] = ef; }
-    et += base + i < n_cells ? cell_tiles(blk_S, base + i, nn[i]) : 0; ef += nn[i];
-    if (base + i == n_cells - 1) { tile_off[n_cells] = et; fish_off[n_cells] = ef; }
+  if (P.out.rows && blk_in) {
+    if (lane == 0) { P.out.blk_row[blk] = (uint32_t)bs; P.out.blk_mask[blk] = mask; P.out.blk_wide[blk] = wmask; }
+    const unsigned long long w0 = (unsigned long long)bs * (unsigned long long)P.out.row_w;
+    const unsigned long long cap_w = (unsigned long long)P.out.cap * (unsigned long long)P.out.row_w;
+    const int nw = slots_w * P.out.row_w;
+    for (int i = lane; i < nw; i += 32)
+      if (w0 + i < cap_w) P.out.rows[w0 + i] = 0u;
+    __syncwarp();
+    if (n_c > 0) {
+      const unsigned long long slot = (unsigned long long)bs + __popc(mask & below) + __popc(wmask & below);
+      if (slot + ((wmask >> lane) & 1u) < (unsigned long long)P.out.cap) P.out.rows[slot * P.out.row_w] = (uint32_t)n_c;
+    }
   }
 }
 
@@ -347,6 +419,7 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
   int64_t c_end = P.tile_off[c + 1], c_begin = P.tile_off[c];
   int cur_day = -1;
   int64_t cur_cell = -1;
+  const bool wide = !INJECT && sizeof(Real) == 8 && P.rng_wide != 0;      // 53-bit uniforms, one draw per two words
 
   // per-cell registers
   Real sp_ls = 0, sp_ll = 0, sp_lsc = 0, sp_lm = 0, sp_lsd = 0, sp_wr = 0, sp_uc = 0, sp_d1 = 0, sp_d2 = 0, sp_b0 = 0, sp_b1 = 0;
@@ -357,20 +430,7 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
 #pragma unroll
   for (int r = 0; r < PR; ++r) { acc_suc[r] = 0; acc_cnt[r] = 0; }
 
-  auto flush = [&](int64_t cell) {
-#pragma unroll
-    for (int r = 0; r < PR; ++r) {
-      const int p = r * 32 + lane;
-      if (p < P.n_pairs && acc_cnt[r]) {
-        uint32_t* dst = P.state_daily + ((size_t)cell * P.n_pairs + p) * 2;
-        if (acc_suc[r]) atomicAdd(dst, acc_suc[r]);
-        atomicAdd(dst + 1, acc_cnt[r]);
-      }
-      acc_suc[r] = 0; acc_cnt[r] = 0;
-    }
-    if (lane < STRYKE_DAILY_W && acc_daily) atomicAdd(P.daily + (size_t)cell * STRYKE_DAILY_W + lane, acc_daily);
-    acc_daily = 0;
-  };
+  auto flush = [&](int64_t cell) { tally_flush<PR>(P, cell, lane, P.n_pairs, acc_suc, acc_cnt, acc_daily); };
 
   for (int64_t t = t0; t < t1; ++t) {
     while (t >= c_end) { ++c; c_begin = c_end; c_end = P.tile_off[c + 1]; }
@@ -378,9 +438,10 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
       if (cur_cell >= 0) flush(cur_cell);
       cur_cell = c;
       n_c = P.cell_n[c];
-      cid = P.cell_id[c];
+      const CellInfo ci = cell_info(P, c);
+      cid = ci.id;
       if (INJECT || P.trace.state || P.trace.length_ft64) fo = P.fish_off[c];
-      const int s = P.cell_species[c];
+      const int s = ci.species;
       if (s < n_species_staged) {
         const Real* q = s_species + s * SPW;
         sp_ls = q[0]; sp_ll = q[1]; sp_lsc = q[2]; sp_lm = q[3]; sp_lsd = q[4]; sp_mode = (int)q[5];
@@ -391,7 +452,7 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
         sp_mode = (int)q[5]; sp_wr = (Real)q[6]; sp_uc = (Real)q[7]; sp_d1 = (Real)q[8]; sp_d2 = (Real)q[9];
         sp_b0 = (Real)q[10]; sp_b1 = (Real)q[11];
       }
-      const int d = P.cell_day[c];
+      const int d = ci.day;
       if (d != cur_day) {   // stage the day's routing CDF, stay flags and unit coefficients in this warp's slot
         cur_day = d;
         __syncwarp();
@@ -429,7 +490,8 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
     // ---- (2) length draw ---------------------------------------------------------------------------------------
     Real z;
     if (INJECT) z = active ? (Real)P.inj.length_z[gi] : (Real)0;
-    else { const uint32_t a = rng.word(0); z = std_normal(u16hi_oc<Real>(a), u16lo_co<Real>(a)); }
+    else if (wide) z = (Real)std_normal(1.0 - rng.wide(0), rng.wide(2));
+    else { const uint32_t a = rng.word(0); z = std_normal(u16hi<Real>(a), u16lo<Real>(a)); }
     Real L;
     if (sizeof(Real) == 8) {
       if (sp_mode == 0) {   // |Z-lognormal| cm, cap 150, -> ft  (scipy: exp(s*Z)*scale + loc; stryke.py:3070-3077)
@@ -462,7 +524,7 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
       const int s_dice = mv.slot_dice;
       const int s_rt = mv.slot_route;
       uint32_t w_rc = 0, w_dice = 0;
-      if (!INJECT) {   // warp-uniform draws for this move (refill points are identical for every lane)
+      if (!INJECT && !wide) {   // warp-uniform draws for this move (refill points are identical for every lane)
         if (mv.need & (NEED_RR | NEED_CAUSE)) w_rc = rng.word(mv.slot_rc);
         if (mv.need & NEED_DICE) w_dice = rng.word(s_dice);
       }
@@ -482,8 +544,9 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
             Real rR = (Real)0.75;
             if (nd.kind == STRYKE_KIND_KAPLAN) {
               if (INJECT) rR = (Real)add_(0.3, mul_(sub_(1.0, 0.3), P.inj.rR[(int64_t)k * NF + gi]));
-              else if (sizeof(Real) == 8) rR = (Real)(0.3 + 0.7 * (double)(with_depth ? u12hi_co<Real>(w_rc) : u16hi_co<Real>(w_rc)));
-              else rR = (Real)fmaf(0.7f, (float)(with_depth ? u12hi_co<Real>(w_rc) : u16hi_co<Real>(w_rc)), 0.3f);
+              else if (wide) rR = (Real)add_(0.3, mul_(sub_(1.0, 0.3), rng.wide(wide_slot(k, 0))));
+              else if (sizeof(Real) == 8) rR = (Real)(0.3 + 0.7 * (double)(with_depth ? u12hi<Real>(w_rc) : u16hi<Real>(w_rc)));
+              else rR = (Real)fmaf(0.7f, (float)(with_depth ? u12hi<Real>(w_rc) : u16hi<Real>(w_rc)), 0.3f);
             }
             if (sizeof(Real) == 8) strike = (Real)strike_surv64(nd.kind, (const double*)uc, (double)L, (double)rR);
             else strike = (Real)strike_surv32(nd.kind, (const float*)uc, (float)L, (float)rR);
@@ -491,7 +554,7 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
             if (P.barotrauma) {
               if (sizeof(Real) == 8) {
                 const double fb = (double)us[2], lo = mul_(fb, (double)sp_d1), hi = mul_(fb, (double)sp_d2);
-                const double ud = INJECT ? P.inj.depth[(int64_t)k * NF + gi] : (double)u13_depth<Real>(w_rc, w_dice);
+                const double ud = INJECT ? P.inj.depth[(int64_t)k * NF + gi] : wide ? rng.wide(wide_slot(k, 1)) : (double)u13_depth<Real>(w_rc, w_dice);
                 baro = (Real)baro_surv64(add_(lo, mul_(sub_(hi, lo), ud)), (double)us[3], (double)sp_b0, (double)sp_b1);
               } else {
                 const float ud = INJECT ? (float)P.inj.depth[(int64_t)k * NF + gi] : (float)u13_depth<Real>(w_rc, w_dice);
@@ -510,10 +573,14 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
             if (cu[0] > (double)imp) cz += 1u;
             else if (cu[NF] > (double)strike) cz += 1u << 8;
             else if (cu[2 * NF] > (double)baro) cz += 1u << 16;
+          } else if (wide) {     // the reference's own sequence of rolls, each with a fresh uniform
+            if (rng.wide(wide_slot(k, 2)) > (double)imp) cz += 1u;
+            else if (rng.wide(wide_slot(k, 3)) > (double)strike) cz += 1u << 8;
+            else if (rng.wide(wide_slot(k, 4)) > (double)baro) cz += 1u << 16;
           } else {
             // one uniform splits [0,1) into the same three probabilities the reference's sequential rolls have:
             // P(imp) = 1-imp, P(blade) = imp (1-strike), P(baro) = imp strike (1-baro)
-            const Real u = u16lo_co<Real>(w_rc);
+            const Real u = u16lo<Real>(w_rc);
             const Real a1 = imp, a2 = imp * strike, a3 = a2 * baro;
             if (u >= a1) cz += 1u;
             else if (u >= a2) cz += 1u << 8;
@@ -550,8 +617,10 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
       bool surv;
       if (INJECT) {
         surv = active && (P.inj.dice[(int64_t)k * NF + gi] <= (double)rate32);
+      } else if (wide) {
+        surv = alive && (rng.wide(wide_slot(k, 5)) <= (double)rate32);
       } else if (mv.need & NEED_DICE) {
-        surv = alive && (u_oc<Real>(w_dice) <= (Real)rate32);
+        surv = alive && (u23<Real>(w_dice) <= (Real)rate32);
       } else {
         surv = alive && rate32 >= 1.0f;    // every node of this level has survival 1.0: no draw needed
       }
@@ -577,7 +646,8 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
       // ---- (3) movement: searchsorted(cdf, u, side='right') over the node's successors (stryke.py:2058) -----------
       if (k < P.n_moves - 1) {
         Real u = (Real)0;
-        if (!INJECT && (mv.need & NEED_ROUTE)) u = u_co<Real>(rng.word(s_rt));
+        if (!INJECT && wide) { if (surv && nd.deg > 1) u = (Real)rng.wide(wide_slot(k, 6)); }
+        else if (!INJECT && (mv.need & NEED_ROUTE)) u = u23<Real>(rng.word(s_rt));
         if (surv && nd.deg > 0 && !s_stay[loc]) {
           if (INJECT) u = (Real)P.inj.route[(int64_t)k * NF + gi];
           int j = 0;

@@ -90,9 +90,9 @@ class CellResult:
     trace: TraceBuffers | None = None
 
 
-def _opts(device, precision, seed, max_daily_fish, blocks_per_sm, injected, trace, keep, kernel_variant=0):
+def _opts(device, precision, seed, max_daily_fish, blocks_per_sm, injected, trace, keep, kernel_variant=0, rng_mode=0, flags=0):
     o = _abi.Opts()
-    o.kernel_variant = int(kernel_variant)
+    o.kernel_variant, o.rng_mode, o.flags = int(kernel_variant), int(rng_mode), int(flags)
     o.device, o.precision, o.seed = int(device), int(precision), int(seed) & 0xFFFFFFFFFFFFFFFF
     o.max_daily_fish, o.blocks_per_sm = int(max_daily_fish), int(blocks_per_sm)
     if injected is not None:
@@ -106,27 +106,194 @@ def _opts(device, precision, seed, max_daily_fish, blocks_per_sm, injected, trac
     return o
 
 
+@dataclass
+class CellGrid:
+    """Implicit cell list (include/stryke_b200.h ``StrykeCellGroup``): the reference's loops over iterations and days
+    (stryke.py:2897-2902) per (scenario, species) group, described by a few numbers per group instead of 16 bytes per cell.
+    Cell ``cell0 + d * iterations + i`` of a group = iteration ``i`` on its ``d``-th day with operating hours."""
+    groups: np.ndarray          # structured, _abi.GROUP_DTYPE, ordered by cell0
+    active_days: np.ndarray     # int32: day offsets (relative to the group's day0) of the days with tot_hours > 0
+    id_days: int                # Philox id = (id_base + iteration) * id_days + day offset + id_add
+    id_add: int = 0
+
+    @property
+    def n_cells(self):
+        g = self.groups
+        return int((g["iterations"].astype(np.int64) * g["n_active_days"]).sum())
+
+    def explicit(self):
+        """The same list as three arrays (cell_day, cell_species, cell_id)."""
+        day, spc, ids = [], [], []
+        for g in self.groups:
+            rel = self.active_days[g["active_off"]:g["active_off"] + g["n_active_days"]].astype(np.int64)
+            I = int(g["iterations"])
+            dd = np.repeat(rel, I)
+            ii = np.tile(np.arange(I, dtype=np.uint64), len(rel))
+            day.append((int(g["day0"]) + dd).astype(np.int32))
+            spc.append(np.full(dd.shape[0], int(g["species"]), np.int32))
+            ids.append((np.uint64(g["id_base"]) + ii) * np.uint64(self.id_days) + dd.astype(np.uint64) + np.uint64(self.id_add))
+        cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
+        return cat(day, np.int32), cat(spc, np.int32), cat(ids, np.uint64)
+
+    def iterations_slice(self, lo_frac, hi_frac):
+        """The sub-grid holding iterations [floor(I * lo_frac), floor(I * hi_frac)) of every group — how the cells are
+        sharded over GPUs (iterations are independent: stryke.py:2897).  Groups left without iterations are dropped."""
+        g = self.groups.copy()
+        lo = np.floor(g["iterations"] * lo_frac + 1e-9).astype(np.int64)
+        hi = np.floor(g["iterations"] * hi_frac + 1e-9).astype(np.int64)
+        g["id_base"] = g["id_base"] + lo.astype(np.uint64)
+        g["iterations"] = (hi - lo).astype(np.int32)
+        its = (hi - lo)
+        keep = its > 0
+        g, its_lo = g[keep], lo[keep]
+        n = g["iterations"].astype(np.int64) * g["n_active_days"]
+        g["cell0"] = np.concatenate([[0], np.cumsum(n)[:-1]]) if len(g) else g["cell0"]
+        out = CellGrid(g, self.active_days, self.id_days, self.id_add)
+        out.iter_lo = its_lo           # first iteration of every kept group (frame assembly maps rows back with it)
+        out.kept = np.nonzero(keep)[0]
+        return out
+
+
 def _tables(fac: FacilityTables, days: DayTables, species: np.ndarray, cell_day, cell_species, cell_id, keep):
+    """C structs of the tables; ``cell_day`` may be a ``CellGrid`` (then the other two are None)."""
     species = _abi.arr(species, np.float64).reshape(-1, _abi.SPECIES_W)
-    cell_day, cell_species = _abi.arr(cell_day, np.int32), _abi.arr(cell_species, np.int32)
-    cell_id = _abi.arr(cell_id, np.uint64)
-    keep += [species, cell_day, cell_species, cell_id]
+    keep.append(species)
     st = _abi.SpeciesTable()
     st.n_species, st.params = species.shape[0], _abi.ptr(species)
     cl = _abi.Cells()
-    cl.n_cells = cell_day.shape[0]
-    cl.cell_day, cl.cell_species, cl.cell_id = _abi.ptr(cell_day), _abi.ptr(cell_species), _abi.ptr(cell_id)
+    if isinstance(cell_day, CellGrid):
+        grid = cell_day
+        groups = np.ascontiguousarray(grid.groups, dtype=_abi.GROUP_DTYPE)
+        act = _abi.arr(grid.active_days, np.int32)
+        keep += [groups, act]
+        cl.n_cells = grid.n_cells
+        cl.n_groups, cl.n_active = len(groups), act.shape[0]
+        cl.groups, cl.active_days = groups.ctypes.data_as(_abi._p), _abi.ptr(act)
+        cl.id_days, cl.id_add = int(grid.id_days), int(grid.id_add) & 0xFFFFFFFFFFFFFFFF
+    else:
+        cell_day, cell_species = _abi.arr(cell_day, np.int32), _abi.arr(cell_species, np.int32)
+        cell_id = _abi.arr(cell_id, np.uint64)
+        keep += [cell_day, cell_species, cell_id]
+        cl.n_cells = cell_day.shape[0]
+        cl.cell_day, cl.cell_species, cl.cell_id = _abi.ptr(cell_day), _abi.ptr(cell_species), _abi.ptr(cell_id)
     return fac.c_struct(), days.c_struct(), st, cl
+
+
+@dataclass
+class CompactResult:
+    """Compact tallies of ``stryke_b200_run_compact`` (layout: include/stryke_b200.h ``StrykeCompact``)."""
+    n_cells: int
+    n_pairs: int
+    row_w: int
+    narrow_max: int
+    n_slots: int
+    n_fish: int
+    blk_row: np.ndarray
+    blk_mask: np.ndarray
+    blk_wide: np.ndarray
+    rows: np.ndarray            # (n_slots, row_w) uint32
+
+    def present(self):
+        """bool[n_cells]: the cell holds fish (its species was present that day)."""
+        return np.unpackbits(np.ascontiguousarray(self.blk_mask).view(np.uint8), bitorder="little")[:self.n_cells].astype(bool)
+
+    def wide(self):
+        return np.unpackbits(np.ascontiguousarray(self.blk_wide).view(np.uint8), bitorder="little")[:self.n_cells].astype(bool)
+
+    def slots(self):
+        """(cells with fish, their slot, wide flag of those cells)."""
+        pres, wide = self.present(), self.wide()
+        per = pres.astype(np.int64) + wide
+        slot = np.cumsum(per) - per + (int(self.blk_row[0]) if len(self.blk_row) else 0)
+        cells = np.flatnonzero(pres)
+        return cells, slot[cells], wide[cells]
+
+    def columns(self):
+        """Per present cell (in cell order): cells, pop_size, daily[., 5] (num_entrained, num_survived, mortality_impingement,
+        _blade_strike, _barotrauma), state[., n_pairs, 2] (successes, count) as int64."""
+        cells, slot, wide = self.slots()
+        P, W = self.n_pairs, self.row_w
+        flat = np.ascontiguousarray(self.rows).reshape(-1)
+        h = flat.view(np.uint16).reshape(-1, 2 * W)          # little-endian halves: low, high
+        r = h[slot]
+        n = r[:, 0].astype(np.int64)
+        daily = np.stack([r[:, 2], r[:, 3], r[:, 4], r[:, 5], r[:, 1]], axis=1).astype(np.int64)
+        state = r[:, 6:6 + 2 * P].reshape(-1, P, 2).astype(np.int64)
+        for j in np.flatnonzero(wide):                       # rare: cells above narrow_max use 32-bit counters over two slots
+            w = flat[slot[j] * W: slot[j] * W + 2 * P + 6].astype(np.int64)
+            n[j], daily[j], state[j] = w[0], w[1:6], w[6:6 + 2 * P].reshape(P, 2)
+        return cells, n, daily, state
+
+    def dense(self) -> "CellResult":
+        """The same tallies in the dense layout of ``run_cells``."""
+        cells, n, daily, state = self.columns()
+        out_n = np.zeros(self.n_cells, np.int32)
+        out_d = np.zeros((self.n_cells, _abi.DAILY_W), np.uint32)
+        out_s = np.zeros((self.n_cells, self.n_pairs, 2), np.uint32)
+        out_n[cells], out_d[cells], out_s[cells] = n, daily, state
+        return CellResult(out_n, out_d, out_s, None)
+
+
+def _pinned(shape, dtype):
+    """Pinned host array when torch is around (copies overlap kernels), else a plain one."""
+    import sys
+    n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+    if "torch" in sys.modules:
+        import torch
+        try:
+            t = torch.empty(max(n, 1) * np.dtype(dtype).itemsize, dtype=torch.uint8).pin_memory()
+            a = t.numpy().view(dtype)[:n].reshape(shape)
+            return a, t
+        except Exception:
+            pass
+    return np.empty(shape, dtype), None
+
+
+def run_compact(fac, days, species, cells, cell_species=None, cell_id=None, *, device=0, precision=32, seed=0,
+                max_daily_fish=100000, blocks_per_sm=0, kernel_variant=0, rows_cap=None, n_slabs=0, buffers=None) -> CompactResult:
+    """One call of ``stryke_b200_run_compact``: the hot path with one tally row per cell that holds fish.  ``cells`` is a
+    ``CellGrid`` or the ``cell_day`` array.  ``rows_cap`` (slots) defaults to two per cell, which always suffices; pass an
+    estimate for population-mode projects (the call fails loudly and names the count it needed when it was too small)."""
+    keep = []
+    f, d, st, cl = _tables(fac, days, species, cells, cell_species, cell_id, keep)
+    o = _opts(device, precision, seed, max_daily_fish, blocks_per_sm, None, None, keep, kernel_variant)
+    C_ = int(cl.n_cells)
+    NB = (C_ + 31) // 32
+    W = fac.n_pairs + 3
+    if rows_cap is None:
+        rows_cap = 2 * C_
+    rows_cap = max(int(rows_cap), 1)
+    if buffers is None:
+        buffers = compact_buffers(C_, fac.n_pairs, rows_cap)
+    blk, rows, _owners = buffers
+    if blk.shape != (3, max(NB, 1)) or rows.shape[0] < rows_cap or rows.shape[1] != W:
+        raise ValueError("compact buffers do not fit this call")
+    c = _abi.Compact()
+    c.n_blocks = NB
+    c.blk_row, c.blk_mask, c.blk_wide = (blk[i].ctypes.data_as(_abi._p) for i in range(3))
+    c.rows, c.rows_cap, c.n_slabs = rows.ctypes.data_as(_abi._p), rows_cap, int(n_slabs)
+    _abi.check(_abi.lib().stryke_b200_run_compact(C.byref(f), C.byref(d), C.byref(st), C.byref(cl), C.byref(o), C.byref(c)))
+    ns = int(c.n_slots)
+    return CompactResult(C_, fac.n_pairs, int(c.row_w), int(c.narrow_max), ns, int(c.n_fish), blk[0, :NB], blk[1, :NB], blk[2, :NB],
+                         rows[:ns])
+
+
+def compact_buffers(n_cells, n_pairs, rows_cap):
+    """Host buffers for ``run_compact`` (pinned when torch is loaded): (block tables [3, n_blocks], rows [rows_cap, row_w])."""
+    NB = max((int(n_cells) + 31) // 32, 1)
+    blk, o1 = _pinned((3, NB), np.uint32)
+    rows, o2 = _pinned((max(int(rows_cap), 1), int(n_pairs) + 3), np.uint32)
+    return blk, rows, (o1, o2)
 
 
 def run_cells(fac, days, species, cell_day, cell_species, cell_id, *, device=0, precision=32, seed=0,
               max_daily_fish=100000, blocks_per_sm=0, injected: Injected | None = None,
-              trace: TraceBuffers | None = None, kernel_variant=0, out=None) -> CellResult:
+              trace: TraceBuffers | None = None, kernel_variant=0, out=None, rng_mode=0, flags=0) -> CellResult:
     """One call of ``stryke_b200_run``: everything between the presence roll and the Daily / State_Daily tallies
     (stryke.py:3025-3366) for the listed cells, on the GPU, host buffers in and out."""
     keep = []
     f, d, st, cl = _tables(fac, days, species, cell_day, cell_species, cell_id, keep)
-    o = _opts(device, precision, seed, max_daily_fish, blocks_per_sm, injected, trace, keep, kernel_variant)
+    o = _opts(device, precision, seed, max_daily_fish, blocks_per_sm, injected, trace, keep, kernel_variant, rng_mode, flags)
     n = int(cl.n_cells)
     if out is not None:      # caller-owned (e.g. pinned) host buffers
         out_n, out_d, out_s = out
@@ -149,10 +316,10 @@ class Plan:
     """Device-resident tables + asynchronous launches into caller-owned device buffers."""
 
     def __init__(self, fac, days, species, cell_day, cell_species, cell_id, *, device=0, precision=32, seed=0,
-                 max_daily_fish=100000, blocks_per_sm=0, injected=None, trace=None, kernel_variant=0):
+                 max_daily_fish=100000, blocks_per_sm=0, injected=None, trace=None, kernel_variant=0, rng_mode=0, flags=0):
         self._keep = []
         f, d, st, cl = _tables(fac, days, species, cell_day, cell_species, cell_id, self._keep)
-        o = _opts(device, precision, seed, max_daily_fish, blocks_per_sm, injected, trace, self._keep, kernel_variant)
+        o = _opts(device, precision, seed, max_daily_fish, blocks_per_sm, injected, trace, self._keep, kernel_variant, rng_mode, flags)
         self.n_cells, self.n_pairs, self.device = int(cl.n_cells), fac.n_pairs, int(device)
         self._h = C.c_void_p()
         _abi.check(_abi.lib().stryke_b200_plan_create(C.byref(f), C.byref(d), C.byref(st), C.byref(cl), C.byref(o),
@@ -171,6 +338,42 @@ class Plan:
             stream = torch.cuda.current_stream(self.device).cuda_stream
         _abi.check(_abi.lib().stryke_b200_plan_launch(self._h, C.c_void_p(cell_n.data_ptr()), C.c_void_p(daily.data_ptr()),
                                                       C.c_void_p(state_daily.data_ptr()), C.c_void_p(stream)))
+
+    def launch_compact(self, cell_n, rows, cell_lo=0, cell_hi=-1, first_slot=0, slots_after=None, stream=None):
+        """Enqueue the hot path for cells [cell_lo, cell_hi) with compact rows (``rows``: uint32/int32 tensor of
+        [rows_cap, n_pairs + 3]; ``cell_n``: int32[n_cells]).  ``first_slot`` < 0 continues after the previous range;
+        ``slots_after``: optional int64 device tensor (1 element) that receives the slot count after this range."""
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        sa = C.c_void_p(slots_after.data_ptr()) if slots_after is not None else None
+        _abi.check(_abi.lib().stryke_b200_plan_launch_compact(self._h, int(cell_lo), int(cell_hi), C.c_void_p(cell_n.data_ptr()),
+                                                              C.c_void_p(rows.data_ptr()), int(rows.shape[0]), int(first_slot), sa,
+                                                              C.c_void_p(stream)))
+
+    def compact_tables(self):
+        """(blk_row, blk_mask, blk_wide) as int32 torch tensors over the plan's device memory, row_w, narrow_max."""
+        import torch
+        ptrs = [C.c_void_p() for _ in range(3)]
+        rw, nm = C.c_int32(0), C.c_int32(0)
+        _abi.check(_abi.lib().stryke_b200_plan_compact_tables(self._h, C.byref(ptrs[0]), C.byref(ptrs[1]), C.byref(ptrs[2]),
+                                                              C.byref(rw), C.byref(nm)))
+        NB = max((self.n_cells + 31) // 32, 1)
+
+        class _Dev:
+            def __init__(self, p):
+                self.__cuda_array_interface__ = {"shape": (NB,), "typestr": "<i4", "data": (int(p.value), False), "version": 2}
+        ts = [torch.as_tensor(_Dev(p), device=torch.device("cuda", self.device)) for p in ptrs]
+        return ts[0], ts[1], ts[2], int(rw.value), int(nm.value)
+
+    def compact_totals(self, stream=None):
+        """(slots, fish) counted by the compact launches so far (waits for the stream)."""
+        if stream is None:
+            import torch
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        ns, nf = C.c_int64(0), C.c_int64(0)
+        _abi.check(_abi.lib().stryke_b200_plan_compact_totals(self._h, C.c_void_p(stream), C.byref(ns), C.byref(nf)))
+        return int(ns.value), int(nf.value)
 
     def kernel(self):
         """Name of the passage kernel this plan launches (general / generic throughput / NVRTC-specialised)."""

@@ -194,35 +194,47 @@ class RunPlan:
 
     # ---- the cell list, engine order: group -> day -> iteration ----------------------------------------------
     def _cells(self):
-        day_idx, sp_idx, ids = [], [], []
-        c0 = 0
+        """Cells are described per (scenario, species) group (``engine.CellGrid``: a few numbers per group); the explicit
+        per-cell arrays are materialised only when something asks for them (injected replays, tests)."""
+        c0, act_off = 0, 0
         max_it = max([g.iterations for g in self.groups] + [1])
         max_days = max([g.n_days for g in self.groups] + [1])
         n_sp = max(len(self.species_params), 1)
-        for g in self.groups:
+        recs = np.zeros(len(self.groups), _abi.GROUP_DTYPE)
+        active = []
+        for j, g in enumerate(self.groups):
             g.cell0 = c0
             if self.peaking:
                 # hours are random per (species, iteration, day) in a peaking plant; drawn on the host like the
                 # reference does (SURVEY.md §8 f-4 "next" row) — every cell keeps its own draw
-                active = np.ones(g.n_days, bool)
+                act = np.ones(g.n_days, bool)
             else:
-                active = self.tot_hours[g.day0:g.day0 + g.n_days] > 0
-            days = np.nonzero(active)[0]
+                act = self.tot_hours[g.day0:g.day0 + g.n_days] > 0
+            days = np.nonzero(act)[0]
             g.active_days = days
             g.n_active_days = len(days)
-            dd = np.repeat(days, g.iterations)
-            ii = np.tile(np.arange(g.iterations), len(days))
-            day_idx.append((g.day0 + dd).astype(np.int32))
-            sp_idx.append(np.full(dd.shape[0], g.species_index, np.int32))
-            ids.append((((np.uint64(g.scen_index) * np.uint64(n_sp) + np.uint64(g.species_index)) * np.uint64(max_it)
-                         + ii.astype(np.uint64)) * np.uint64(max_days) + dd.astype(np.uint64)))
-            c0 += dd.shape[0]
-        cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
-        self.cell_day, self.cell_species, self.cell_id = cat(day_idx, np.int32), cat(sp_idx, np.int32), cat(ids, np.uint64)
+            recs[j] = (c0, g.iterations, len(days), g.day0, g.species_index, act_off, 0,
+                       (g.scen_index * n_sp + g.species_index) * max_it)
+            active.append(days.astype(np.int32))
+            act_off += len(days)
+            c0 += len(days) * g.iterations
+        keep = (recs["n_active_days"] > 0) & (recs["iterations"] > 0)
+        self.grid = engine.CellGrid(recs[keep], np.concatenate(active).astype(np.int32) if active else np.zeros(0, np.int32),
+                                    int(max_days))
         self.n_cells = c0
+        self._explicit = None
         self.cell_hours = {}
         if self.peaking:
             self._peaking_hours()
+
+    def _explicit_cells(self):
+        if self._explicit is None:
+            self._explicit = self.grid.explicit()
+        return self._explicit
+
+    cell_day = property(lambda self: self._explicit_cells()[0])
+    cell_species = property(lambda self: self._explicit_cells()[1])
+    cell_id = property(lambda self: self._explicit_cells()[2])
 
     def _peaking_hours(self):
         """Peaking / pumped-storage plants (stryke.py:2405-2431): per (species, iteration, day) every unit flips a

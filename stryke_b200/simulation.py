@@ -530,7 +530,8 @@ class simulation:
         seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 32)
         try:
             res = engine.run_cells(fac, days, params[None, :], [0], [0], [0], device=self.device, precision=32, seed=seed,
-                                   max_daily_fish=int(os.environ.get("STRYKE_MAX_DAILY_FISH", "100000")))
+                                   max_daily_fish=int(os.environ.get("STRYKE_MAX_DAILY_FISH", "100000")),
+                                   flags=_abi.FLAG_NO_PROMOTE)      # the n == 0 -> 1 promotion belongs to run() (stryke.py:3032)
         except _abi.StrykeError as exc:
             if exc.code == _abi.E_MAX_FISH:
                 raise ValueError(f"{exc} Inputs: curr_Q={curr_Q}. Adjust entrainment inputs or raise "

@@ -26,21 +26,22 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(_abi.EXPORTS) == declared
-    assert lib.stryke_b200_abi_version() == 1
+    assert lib.stryke_b200_abi_version() == _abi.ABI_VERSION == 2
 
 
 def test_abi_struct_layout_matches_header():
     """sizeof() of the ctypes mirrors vs the C compiler's."""
     from stryke_b200 import _abi
     import ctypes as C
-    src = '#include <stdio.h>\n#include "stryke_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+    src = '#include <stdio.h>\n#include "stryke_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
           "sizeof(StrykeFacility),sizeof(StrykeDayTables),sizeof(StrykeSpeciesTable),sizeof(StrykeCells)," \
-          "sizeof(StrykeInjected),sizeof(StrykeTrace),sizeof(StrykeOpts),sizeof(StrykeTallies));return 0;}"
+          "sizeof(StrykeInjected),sizeof(StrykeTrace),sizeof(StrykeOpts),sizeof(StrykeTallies),sizeof(StrykeCellGroup)," \
+          "sizeof(StrykeCompact));return 0;}"
     exe = "/tmp/stryke_b200_sizeof"
     subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src.encode(), check=True)
     got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     want = [C.sizeof(t) for t in (_abi.Facility, _abi.DayTables, _abi.SpeciesTable, _abi.Cells, _abi.Injected, _abi.Trace,
-                                  _abi.Opts, _abi.Tallies)]
+                                  _abi.Opts, _abi.Tallies, _abi.CellGroup, _abi.Compact)]
     assert got == want
 
 

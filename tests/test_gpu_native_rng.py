@@ -14,11 +14,11 @@ pytestmark = pytest.mark.gpu
 ALPHA = 0.01
 
 
-def native(plan, precision=32, seed=11, trace=None, cells=None, blocks_per_sm=0, cap=10 ** 9):
+def native(plan, precision=32, seed=11, trace=None, cells=None, blocks_per_sm=0, cap=10 ** 9, rng_mode=0):
     sel = slice(None) if cells is None else cells
     return engine.run_cells(plan.fac, plan.days, plan.species_table, plan.cell_day[sel], plan.cell_species[sel],
                             plan.cell_id[sel], precision=precision, seed=seed, max_daily_fish=cap, trace=trace,
-                            blocks_per_sm=blocks_per_sm)
+                            blocks_per_sm=blocks_per_sm, rng_mode=rng_mode)
 
 
 # family of the genera in the fixtures (Data/fish_class.csv of the reference; the product resolves them itself from
@@ -81,6 +81,60 @@ def test_route_and_survival_counts_match_oracle_distribution(fixture, kw, precis
     res = native(plan, precision=precision)
     ref = oracle_cells(prj, plan.n_cells)
     compare_cells(plan, res, ref, G.reference_cell_index(plan))
+
+
+@pytest.mark.parametrize("fixture,kw", [("c2_facility", dict(n_fish=300000, iterations=1, days=2, baro=True)),
+                                        ("c5_cascade", dict(n_fish=150000, iterations=1, days=2)),
+                                        ("cabot_station", dict(iterations=1, days=2, seed=3, median_Q=7000.0, fish=200000.0))])
+def test_wide_stream_of_the_fp64_kernel_matches_oracle_distribution(fixture, kw):
+    """rng_mode 1: 53-bit uniforms, one per draw, the reference's sequential cause rolls — the arbiter of
+    tests/test_gpu_high_power.py is itself checked against the oracle here."""
+    prj = getattr(fixtures, fixture)(**kw)
+    sim, plan = G.make_plan(prj, fixture)
+    res = native(plan, precision=64, rng_mode=1)
+    compact_stream = native(plan, precision=64)
+    assert not np.array_equal(res.state_daily, compact_stream.state_daily)      # really another stream
+    ref = oracle_cells(prj, plan.n_cells)
+    compare_cells(plan, res, ref, G.reference_cell_index(plan))
+
+
+def test_wide_stream_needs_the_fp64_kernel():
+    from stryke_b200 import _abi
+    prj = fixtures.c2_facility(n_fish=100, iterations=1, days=1)
+    sim, plan = G.make_plan(prj, "w32")
+    with pytest.raises(_abi.StrykeError, match="rng_mode"):
+        native(plan, precision=32, rng_mode=1)
+
+
+def test_length_normal_tail_mass_and_range():
+    """The one-word Box-Muller (16-bit centred radius and angle): tail masses beyond 2, 3, 4 sigma agree with the normal law
+    (binomial tests on 8e6 fish), no point mass at z = 0, |z| <= sqrt(-2 ln 2^-17) = 4.855; the wide stream reaches further."""
+    n = 4_000_000
+    prj = fixtures.c2_facility(n_fish=n, iterations=2, days=1)
+    sim, plan = G.make_plan(prj, "tail")
+    prow = prj["population"][0]
+    s_, loc, scale = prow["length shape"], prow["length location"], prow["length scale"]
+    out = {}
+    for mode, precision in ((0, 32), (0, 64), (1, 64)):
+        tr = TraceBuffers.allocate(plan.fac.n_moves, 2 * n, probs=False)
+        native(plan, precision=precision, trace=tr, rng_mode=mode)
+        cm = tr.length_ft64 / 0.0328084
+        ok = cm < 149.999                        # lengths are capped at 150 cm (stryke.py:3076): z above 3.8 is not observable
+        z = np.log((cm[ok] - loc) / scale) / s_
+        out[(mode, precision)] = z
+        out[("cm", mode, precision)] = cm
+        tests = []
+        for t in (2.0, 3.0):
+            for sign in (-1, 1):
+                k = int((z * sign > t).sum()) if sign < 0 else int(((z > t) & (z < 3.7)).sum())
+                p = stats.norm.sf(t) if sign < 0 else stats.norm.cdf(3.7) - stats.norm.cdf(t)
+                tests.append(stats.binomtest(k, 2 * n, p).pvalue)
+        tests.append(stats.binomtest(int((z < -4.0).sum()), 2 * n, stats.norm.sf(4.0)).pvalue)
+        assert min(tests) > ALPHA / (3 * len(tests)), (mode, precision, tests)
+        assert (np.abs(z) < 1e-7).sum() <= 2          # no point mass at zero
+    assert out[(0, 32)].min() > -4.87 and out[(0, 64)].min() > -4.86
+    a, b = out[("cm", 0, 32)], out[("cm", 0, 64)]
+    assert np.abs(a / b - 1.0).max() < 1e-4                           # same uniforms in both precisions (tolerance of BASELINE.json)
 
 
 def _reference_samples():
