@@ -229,6 +229,7 @@ int stryke_b200_plan_launch(StrykePlan* plan, int32_t* d_cell_n, uint32_t* d_dai
 /* Same hot path with compact rows (see StrykeCompact), for cells [cell_lo, cell_hi) of the plan (cell_lo a multiple of
  * 256; cell_hi = -1: to the end).  d_rows holds rows_cap slots; the per-block tables live in the plan
  * (stryke_b200_plan_compact_tables).  Slots continue from the previous range when first_slot < 0, else start at first_slot.
+ * A range that starts at cell 0 starts a new pass: the status words (error, fish and slot totals) start over.
  * d_slots_after (device, may be NULL) receives the slot count after this range — what a caller that overlaps the copy of one
  * range with the kernels of the next needs to know.  Ranges of one pass go to ONE stream, in order.
  * Rows are zeroed by the launch itself: no memset, no read-modify-write of untouched cells. */

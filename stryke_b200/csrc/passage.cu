@@ -627,7 +627,7 @@ static int launch_cells(StrykePlan* pl, int64_t c_lo, int64_t c_hi, int32_t* d_c
   K.cell_n = d_cell_n + c_lo;
   K.out.blk_row += c_lo >> 5; K.out.blk_mask += c_lo >> 5; K.out.blk_wide += c_lo >> 5;
   const bool compact = d_rows != nullptr;
-  const bool fresh = !compact || first_slot >= 0;
+  const bool fresh = !compact || c_lo == 0;      // a pass over the cell list starts at its first cell: status words start over
   pl->last_rows_cap = compact ? rows_cap : -1;
   unsigned long long* err = pl->err.as<unsigned long long>();
   if (fresh) CK(cudaMemsetAsync(err, 0, ERR_N * sizeof(unsigned long long), st));

@@ -1,15 +1,25 @@
-"""Multi-GPU layer: one process per GPU, cells sharded over ranks, ONE all-reduce of the tally arrays.
+"""Multi-GPU layer: one process per GPU, cells sharded over ranks, the ranks' compact tally rows gathered at the end.
 
-Scenario x species x iteration x day cells are independent (the reference's loops share nothing but RNG streams and
-the HDF append, Stryke/stryke.py:2806-2902) and the Philox counter is keyed by the logical cell id, so any partition
-of the cell list gives the same tallies (tests/test_gpu_native_rng.py).  Each rank simulates a contiguous block of
-the engine-order cell list, writes its block into zero-initialised full-size tally tensors and the ranks sum them
-with ``torch.distributed.all_reduce`` (NCCL over NVLink/NVSwitch on GPUs, gloo in the CPU tests) — there is no
-exchange inside the simulation, so no fused compute+collective kernel exists or is needed on this path.
+Scenario x species x iteration x day cells are independent (the reference's loops share nothing but RNG streams and the
+HDF append, Stryke/stryke.py:2806-2902) and the Philox counter is keyed by the logical cell id, so any partition of the
+cell list gives the same tallies (tests/test_gpu_native_rng.py).  A rank simulates the iterations [I r / N, I (r + 1) / N) of
+every (scenario, species) group — the loop the reference runs at stryke.py:2897 — into compact rows (one row per cell
+that holds fish, 16-bit counters; include/stryke_b200.h ``StrykeCompact``) inside ONE flat device buffer, and the ranks
+exchange those buffers: every rank ends up with every rank's rows (what the north star calls the tally all-reduce; the
+shards are disjoint, so the sum is a concatenation and nobody ships zeros).
+
+Exchange.  ``push`` (NCCL process groups with CUDA peer access): the cell list of a rank is cut into slabs, every slab owns a
+fixed region of the buffer, and as soon as a slab's kernels are done a copy stream pushes its region straight into every
+peer's gathered buffer over NVLink (``cudaMemcpyPeerAsync`` through torch's symmetric memory — copy engines, no SMs), under
+the kernels of the next slab; one tiny all-reduce at the end is the completion fence.  ``gather`` (anything else, e.g. gloo in
+the CPU tests): one ``all_gather_into_tensor`` of the flat buffers after the last slab.
+There is no exchange inside the simulation, hence no fused compute + collective kernel on this path.
 """
 from __future__ import annotations
 
 import numpy as np
+
+HDR = 16          # int32 words at the head of a rank's flat buffer: [0:2) slots used (int64), [2] status code, [3] n_cells
 
 
 def shard_bounds(n_cells, rank, world):
@@ -28,8 +38,225 @@ def shard_by_weight(weights, world):
     return np.concatenate([[0], cuts, [len(w)]]).astype(np.int64)
 
 
+def expected_slots(grid, species, margin=1.08, extra=4096):
+    """Upper estimate of the rows a grid needs: cells x occur_prob per group (+ margin); two slots per cell for groups
+    whose fixed count may not fit 16-bit counters."""
+    tot = 0.0
+    for g in grid.groups:
+        sp = species[int(g["species"])]
+        cells = float(g["iterations"]) * float(g["n_active_days"])
+        occur = sp[17] if np.isfinite(sp[17]) else 1.0
+        fixed = int(sp[12]) == 0
+        per = 2.0 if (fixed and sp[18] > 13000) else 1.0
+        p = min(max(occur, 0.0), 1.0)
+        tot += per * (cells * p * margin + 6.0 * np.sqrt(max(cells * p * (1 - p), 1.0))) + (0.02 * cells if not fixed else 0.0)
+    return int(tot) + extra
+
+
+class ShardLayout:
+    """Geometry of one rank's flat buffer: header, block tables, slab regions of rows (identical on every rank)."""
+
+    def __init__(self, n_cells_max, n_pairs, slab_cells, slab_cap):
+        self.W = int(n_pairs) + 3
+        self.NB = (int(n_cells_max) + 31) // 32
+        self.slab_cells = int(slab_cells)
+        self.n_slabs = max(1, -(-int(n_cells_max) // self.slab_cells))
+        self.slab_cap = int(slab_cap)
+        self.blk_off = HDR
+        self.rows_off = HDR + 3 * self.NB
+        self.rows_off += (-self.rows_off) % 4                    # rows start 16-byte aligned
+        self.total = self.rows_off + self.n_slabs * self.slab_cap * self.W
+
+    def slab_words(self, k):
+        lo = self.rows_off + k * self.slab_cap * self.W
+        return lo, lo + self.slab_cap * self.W
+
+
+def pack_flat(L, blk, rows, status=0, n_cells=0, slots_used=0):
+    """A rank's flat int32 buffer (numpy) from block tables [3, <= NB] and rows [<= n_slabs * slab_cap, W] — the layout the
+    kernels fill in place on the device; used by the host-side tests of the exchange."""
+    flat = np.zeros(L.total, np.int32)
+    u = flat.view(np.uint32)
+    u[0], u[1] = int(slots_used) & 0xFFFFFFFF, int(slots_used) >> 32
+    flat[2], flat[3] = int(status), int(n_cells)
+    b = np.zeros((3, L.NB), np.uint32)
+    b[:, :blk.shape[1]] = blk
+    u[L.blk_off:L.blk_off + 3 * L.NB] = b.reshape(-1)
+    r = np.ascontiguousarray(rows, dtype=np.uint32).reshape(-1)
+    u[L.rows_off:L.rows_off + r.shape[0]] = r
+    return flat
+
+
+def unpack_flat(L, flat, n_pairs):
+    """(n_cells, status code, engine.CompactResult) of one rank's flat buffer (host int32 array of ``L.total`` words)."""
+    from .engine import CompactResult
+    u = np.ascontiguousarray(flat).view(np.uint32)
+    n_cells, status = int(flat[3]), int(flat[2])
+    NB = (n_cells + 31) // 32
+    blk = u[L.blk_off:L.blk_off + 3 * L.NB].reshape(3, L.NB)
+    rows = u[L.rows_off:L.rows_off + L.n_slabs * L.slab_cap * L.W].reshape(-1, L.W)
+    return n_cells, status, CompactResult(n_cells, int(n_pairs), L.W, 0, rows.shape[0], 0, blk[0, :NB], blk[1, :NB], blk[2, :NB], rows)
+
+
+def gather_flat(local, world, group=None):
+    """ONE ``all_gather_into_tensor`` of the ranks' flat buffers (NCCL on GPUs, gloo in the CPU tests): [world * len(local)]."""
+    import torch
+    import torch.distributed as dist
+    out = torch.empty(world * local.numel(), dtype=local.dtype, device=local.device)
+    if world == 1:
+        out.copy_(local)
+    else:
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return out
+
+
+class ShardedRun:
+    """One rank's share of a run, resident on its GPU: plan, flat result buffer, gathered buffer, streams."""
+
+    def __init__(self, fac, days, species, grid, rank, world, device, *, precision=32, seed=0, max_daily_fish=100000,
+                 kernel_variant=0, slab_cells=None, slab_cap=None, n_cells_max=None, group=None, exchange="auto"):
+        import torch
+        import torch.distributed as dist
+        from . import engine
+        self.torch, self.dist = torch, dist
+        self.rank, self.world, self.device, self.group = int(rank), int(world), int(device), group
+        self.grid, self.fac = grid, fac
+        self.n_cells = grid.n_cells
+        self.dev = torch.device("cuda", device)
+        self.plan = engine.Plan(fac, days, species, grid, None, None, device=device, precision=precision, seed=seed,
+                                max_daily_fish=max_daily_fish, kernel_variant=kernel_variant)
+        n_max = int(n_cells_max if n_cells_max is not None else self.n_cells)
+        if slab_cells is None:           # ~8 slabs on large lists, whole multiples of 256 cells
+            slab_cells = max(256, -(-max(n_max, 1) // 8 // 256) * 256) if n_max >= (1 << 18) else max(256, -(-max(n_max, 1) // 256) * 256)
+        if slab_cap is None:
+            est = expected_slots(grid, np.asarray(species).reshape(-1, 20))
+            slab_cap = max(1024, int(est / max(1, -(-n_max // slab_cells)) * 1.25) + 2048)
+        self.L = ShardLayout(n_max, fac.n_pairs, slab_cells, slab_cap)
+        L = self.L
+        self.mode = "gather"
+        self.symm = None
+        if exchange in ("auto", "push") and world > 1 and dist.is_initialized() and dist.get_backend(group) == "nccl":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self.gathered = symm_mem.empty(world * L.total, dtype=torch.int32, device=self.dev)
+                self.symm = symm_mem.rendezvous(self.gathered, group=group if group is not None else dist.group.WORLD)
+                self.peers = [self.symm.get_buffer(p, (world * L.total,), torch.int32) for p in range(world)]
+                self.mode = "push"
+            except Exception as exc:      # no peer access / API not there: one collective at the end instead
+                if exchange == "push":
+                    raise
+                self.push_error = repr(exc)
+        if self.mode != "push":
+            self.gathered = torch.zeros(world * L.total, dtype=torch.int32, device=self.dev)
+        # this rank's buffer IS its region of the gathered buffer: kernels write the rows in place
+        self.buf = self.gathered[self.rank * L.total:(self.rank + 1) * L.total]
+        self.buf.zero_()
+        self.cell_n = torch.zeros(max(self.n_cells, 1), dtype=torch.int32, device=self.dev)
+        self.rows = self.buf[L.rows_off:L.rows_off + L.n_slabs * L.slab_cap * L.W].view(L.n_slabs * L.slab_cap, L.W)
+        self.blk = self.buf[L.blk_off:L.blk_off + 3 * L.NB].view(3, L.NB)
+        self.slots_after = torch.zeros(L.n_slabs + 1, dtype=torch.int64, device=self.dev)
+        self.compute = torch.cuda.current_stream(self.dev)
+        self.copy = torch.cuda.Stream(self.dev)
+        self.fence = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.t_blk = self.plan.compact_tables()[:3]
+        self.slab_events = [torch.cuda.Event() for _ in range(L.n_slabs)]
+        self.host = None
+
+    # -- one pass over this rank's cells ------------------------------------------------------------------------
+    def launch(self, seed=None, to_host=False):
+        """Enqueue every slab (count + passage kernels) and its export (peer pushes and / or the copy to pinned host memory)."""
+        torch, L = self.torch, self.L
+        if seed is not None:
+            self.plan.set_seed(seed)
+        nC = self.n_cells
+        cs = self.compute.cuda_stream
+        if to_host and self.host is None:
+            self.host = torch.empty(L.total, dtype=torch.int32).pin_memory()
+        self.copy.wait_stream(self.compute)               # the previous pass's exports are ordered before this pass's kernels
+        self.compute.wait_stream(self.copy)
+        for k in range(L.n_slabs):
+            lo, hi = k * L.slab_cells, min(nC, (k + 1) * L.slab_cells)
+            if lo >= hi:
+                break
+            self.plan.launch_compact(self.cell_n, self.rows, lo, hi, first_slot=k * L.slab_cap,
+                                     slots_after=self.slots_after[k:k + 1], stream=cs)
+            b0, b1 = lo >> 5, (hi + 31) >> 5
+            for j in range(3):                             # the plan's block tables of this slab -> the flat buffer
+                self.blk[j, b0:b1].copy_(self.t_blk[j][b0:b1], non_blocking=True)
+            self.slab_events[k].record(self.compute)
+            if self.mode == "push" or to_host:
+                w0, w1 = L.slab_words(k)
+                with torch.cuda.stream(self.copy):
+                    self.copy.wait_event(self.slab_events[k])
+                    if self.mode == "push":
+                        base = self.rank * L.total
+                        for p in range(self.world):
+                            if p != self.rank:
+                                self.peers[p][base + w0:base + w1].copy_(self.buf[w0:w1], non_blocking=True)
+                    if to_host:
+                        self.host[w0:w1].copy_(self.buf[w0:w1], non_blocking=True)
+
+    def exchange(self, status_code=0, to_host=False):
+        """Finish the pass: header + block tables to the peers, completion fence (push) or the one all-gather."""
+        torch, dist, L = self.torch, self.dist, self.L
+        hdr = torch.tensor([0, 0, int(status_code), self.n_cells], dtype=torch.int32)
+        self.buf[2:4].copy_(hdr[2:4].to(self.dev, non_blocking=True), non_blocking=True)
+        self.buf[0:2].copy_(self.slots_after[max(0, min(L.n_slabs, -(-self.n_cells // L.slab_cells)) - 1):][:1].view(torch.int32)[:2],
+                            non_blocking=True)
+        if self.world > 1:
+            if self.mode == "push":
+                self.copy.wait_stream(self.compute)
+                with torch.cuda.stream(self.copy):
+                    base = self.rank * L.total
+                    for p in range(self.world):
+                        if p != self.rank:
+                            self.peers[p][base:base + L.rows_off].copy_(self.buf[:L.rows_off], non_blocking=True)
+                    if to_host:
+                        self.host[:L.rows_off].copy_(self.buf[:L.rows_off], non_blocking=True)
+                    dist.all_reduce(self.fence, group=self.group)      # every rank's pushes are stream-ordered before its fence
+                self.compute.wait_stream(self.copy)
+            else:
+                self.compute.wait_stream(self.copy)
+                if to_host:
+                    with torch.cuda.stream(self.copy):
+                        self.copy.wait_stream(self.compute)
+                        self.host[:L.rows_off].copy_(self.buf[:L.rows_off], non_blocking=True)
+                mine = self.buf.clone() if dist.get_backend(self.group) != "nccl" else self.buf
+                dist.all_gather_into_tensor(self.gathered, mine, group=self.group)
+                self.compute.wait_stream(self.copy)
+        elif to_host:
+            with torch.cuda.stream(self.copy):
+                self.copy.wait_stream(self.compute)
+                self.host[:L.rows_off].copy_(self.buf[:L.rows_off], non_blocking=True)
+            self.compute.wait_stream(self.copy)
+
+    def step(self, seed=None, to_host=False):
+        self.launch(seed, to_host)
+        self.exchange(0, to_host)
+
+    # -- results -----------------------------------------------------------------------------------------------------
+    def results(self):
+        """Per rank: (n_cells, status code, CompactResult) from the gathered buffer (device -> host copy of everything)."""
+        self.torch.cuda.synchronize(self.dev)
+        g = self.gathered.cpu().numpy().reshape(self.world, self.L.total)
+        return [unpack_flat(self.L, g[r], self.fac.n_pairs) for r in range(self.world)]
+
+    def slab_overflow(self):
+        """True when some slab used more slots than its region holds (the caller retries with a larger ``slab_cap``)."""
+        self.torch.cuda.synchronize(self.dev)
+        after = self.slots_after.cpu().numpy()
+        L = self.L
+        for k in range(L.n_slabs):
+            if k * L.slab_cells < self.n_cells and after[k] > (k + 1) * L.slab_cap:
+                return True
+        return False
+
+    def close(self):
+        self.plan.close()
+
+
 def allreduce_tallies(tensors, group=None):
-    """Sum the tally tensors over ranks in place (each rank contributed zeros outside its own block)."""
+    """Sum dense tally tensors over ranks in place (small fixed-count projects; kept for callers of the dense layout)."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return tensors
@@ -38,23 +265,55 @@ def allreduce_tallies(tensors, group=None):
     return tensors
 
 
-def run_sharded(plan_host, rank, world, device, *, precision=32, seed=0, max_daily_fish=100000, group=None):
-    """Simulate this rank's block of ``plan_host`` (a ``runner.RunPlan``) on ``device`` and all-reduce.
-
-    Returns full-size (cell_n, daily, state_daily) torch tensors (int32, summed over ranks) on ``device``."""
+def agree_on_status(code, device=None, group=None):
+    """The largest-magnitude status code over the ranks (0 = every rank succeeded): an error on one rank must stop all of
+    them BEFORE they enter a collective the failing rank will never reach."""
     import torch
-    from . import _abi, engine
-    lo, hi = shard_bounds(plan_host.n_cells, rank, world)
-    dev = torch.device("cuda", device)
-    C, P = plan_host.n_cells, plan_host.fac.n_pairs
-    full_n, full_d, full_s, base = engine.tally_tensors(C, P, device, with_base=True)     # views of one flat buffer
-    if hi > lo:
-        plan = engine.Plan(plan_host.fac, plan_host.days, plan_host.species_table, plan_host.cell_day[lo:hi],
-                           plan_host.cell_species[lo:hi], plan_host.cell_id[lo:hi], device=device, precision=precision,
-                           seed=seed, max_daily_fish=max_daily_fish)
-        # the block is a contiguous slice of the full tensors: the kernels write in place, no copy
-        plan.launch(full_n[lo:hi], full_d[lo:hi], full_s[lo:hi])
-        plan.status()
-        plan.close()
-    allreduce_tallies([base], group)          # ONE collective for the three tensors
-    return full_n, full_d, full_s
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return int(code)
+    t = torch.tensor([-int(code)], dtype=torch.int32, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return -int(t.item())
+
+
+def run_sharded(plan_host, rank, world, device, *, precision=32, seed=0, max_daily_fish=100000, group=None):
+    """Simulate this rank's iterations of ``plan_host`` (a ``runner.RunPlan``) on ``device`` and exchange the rows.
+
+    Returns a list with one (grid slice, CompactResult) per rank, in rank order — on EVERY rank.  An engine error on any
+    rank (population cap, non-finite count) is raised on all ranks with the failing rank's message; nobody hangs in a
+    collective."""
+    from . import _abi
+    grids = [plan_host.grid.iterations_slice(r / world, (r + 1) / world) for r in range(world)]
+    mine = grids[rank]
+    n_max = max(g.n_cells for g in grids)
+    species = plan_host.species_table
+    cap_scale = 1.0
+    while True:
+        est = max(expected_slots(g, species) for g in grids)
+        slab_cells = max(256, -(-max(n_max, 1) // (8 if n_max >= (1 << 18) else 1) // 256) * 256)
+        n_slabs = max(1, -(-n_max // slab_cells))
+        run = ShardedRun(plan_host.fac, plan_host.days, species, mine, rank, world, device, precision=precision, seed=seed,
+                         max_daily_fish=max_daily_fish, slab_cells=slab_cells,
+                         slab_cap=int(cap_scale * (est / n_slabs * 1.25 + 2048)), n_cells_max=n_max, group=group)
+        code, msg = 0, ""
+        try:
+            run.launch(seed)
+            run.plan.status()
+        except _abi.StrykeError as exc:
+            code, msg = exc.code, str(exc)
+        over = 1 if (code == 0 and run.slab_overflow()) else 0
+        worst = agree_on_status(code, run.dev if world > 1 and run.dist.get_backend(group) == "nccl" else None, group)
+        if worst != 0:
+            run.close()
+            if code != 0:
+                raise _abi.StrykeError(code, msg)
+            raise _abi.StrykeError(worst, f"rank {rank}: another rank stopped with status {worst}")
+        if agree_on_status(-over, run.dev if world > 1 and run.dist.get_backend(group) == "nccl" else None, group) != 0:
+            run.close()
+            cap_scale *= 2.0           # some slab region was too small somewhere: every rank retries with room to spare
+            continue
+        run.exchange(0)
+        out = [(grids[r], res) for r, (_, _, res) in enumerate(run.results())]
+        run.close()
+        return out

@@ -201,11 +201,15 @@ class CompactResult:
         return np.unpackbits(np.ascontiguousarray(self.blk_wide).view(np.uint8), bitorder="little")[:self.n_cells].astype(bool)
 
     def slots(self):
-        """(cells with fish, their slot, wide flag of those cells)."""
-        pres, wide = self.present(), self.wide()
+        """(cells with fish, their slot, wide flag of those cells): the slot of cell 32 b + j is blk_row[b] + the slots of
+        the block's present cells before it (launches over ranges of cells may start a range at any slot)."""
+        NB = len(self.blk_row)
+        bits = lambda a: np.unpackbits(np.ascontiguousarray(a).view(np.uint8), bitorder="little")
+        pres, wide = bits(self.blk_mask).astype(bool), bits(self.blk_wide).astype(bool)
         per = pres.astype(np.int64) + wide
-        slot = np.cumsum(per) - per + (int(self.blk_row[0]) if len(self.blk_row) else 0)
-        cells = np.flatnonzero(pres)
+        cs = np.cumsum(per) - per
+        slot = cs - np.repeat(cs[::32], 32) + np.repeat(self.blk_row.astype(np.int64), 32)
+        cells = np.flatnonzero(pres[:self.n_cells])
         return cells, slot[cells], wide[cells]
 
     def columns(self):
@@ -215,13 +219,17 @@ class CompactResult:
         P, W = self.n_pairs, self.row_w
         flat = np.ascontiguousarray(self.rows).reshape(-1)
         h = flat.view(np.uint16).reshape(-1, 2 * W)          # little-endian halves: low, high
-        r = h[slot]
+        contiguous = len(slot) > 0 and not wide.any() and slot[-1] - slot[0] == len(slot) - 1
+        r = h[slot[0]:slot[-1] + 1] if contiguous else h[slot]     # (a run without wide cells and gaps: a view, no gather)
         n = r[:, 0].astype(np.int64)
         daily = np.stack([r[:, 2], r[:, 3], r[:, 4], r[:, 5], r[:, 1]], axis=1).astype(np.int64)
-        state = r[:, 6:6 + 2 * P].reshape(-1, P, 2).astype(np.int64)
-        for j in np.flatnonzero(wide):                       # rare: cells above narrow_max use 32-bit counters over two slots
-            w = flat[slot[j] * W: slot[j] * W + 2 * P + 6].astype(np.int64)
-            n[j], daily[j], state[j] = w[0], w[1:6], w[6:6 + 2 * P].reshape(P, 2)
+        state = r[:, 6:6 + 2 * P].reshape(-1, P, 2)              # uint16 while every cell is narrow
+        wj = np.flatnonzero(wide)
+        if len(wj):                                          # cells above narrow_max use 32-bit counters over two slots
+            state = state.astype(np.uint32)
+            idx = (slot[wj] * W)[:, None] + np.arange(2 * P + 6)[None, :]
+            w = flat[idx].astype(np.int64)
+            n[wj], daily[wj], state[wj] = w[:, 0], w[:, 1:6], w[:, 6:6 + 2 * P].reshape(-1, P, 2)
         return cells, n, daily, state
 
     def dense(self) -> "CellResult":

@@ -219,6 +219,7 @@ class RunPlan:
             act_off += len(days)
             c0 += len(days) * g.iterations
         keep = (recs["n_active_days"] > 0) & (recs["iterations"] > 0)
+        self.grid_group_index = np.nonzero(keep)[0]        # grid group -> index into self.groups
         self.grid = engine.CellGrid(recs[keep], np.concatenate(active).astype(np.int32) if active else np.zeros(0, np.int32),
                                     int(max_days))
         self.n_cells = c0
@@ -309,36 +310,45 @@ def run_simulation(sim, injected=None, trace=None):
     max_fish, max_rows, M = plan.fish_cap()
     cap = min(max_fish, max_rows // M)
     rank, world = _dist_rank_world()
+    if world > 1 and "device" not in sim.__dict__:       # one process per GPU: this process's GPU unless the caller chose one
+        sim.device = int(os.environ.get("LOCAL_RANK", rank))
+    res = None
     try:
-        if world > 1 and injected is None and trace is None:
-            # one process per GPU (torchrun): every rank simulates its block of cells, ONE all-reduce gives every rank the
-            # full tallies; rank 0 writes the frames (Philox is keyed by the cell, so the result does not depend on world)
-            from .distributed import run_sharded
-            n_t, d_t, s_t = run_sharded(plan, rank, world, device=sim.device, precision=sim.precision, seed=sim.seed,
-                                        max_daily_fish=cap)
-            res = engine.CellResult(n_t.cpu().numpy(), d_t.cpu().numpy().view(np.uint32), s_t.cpu().numpy().view(np.uint32), None)
-        else:
+        if injected is not None or trace is not None:
+            # replay of recorded draws / per-fish trace: dense tallies, explicit cell arrays (parity and debugging path)
             res = engine.run_cells(plan.fac, plan.days, plan.species_table, plan.cell_day, plan.cell_species, plan.cell_id,
                                    device=sim.device, precision=sim.precision, seed=sim.seed, max_daily_fish=cap,
                                    injected=injected, trace=trace)
+            pieces = [(plan.grid, res)]
+        elif world > 1:
+            # one process per GPU (torchrun): every rank simulates its iterations of every group, the ranks exchange their
+            # compact rows; rank 0 writes the frames (Philox is keyed by the cell, so the result does not depend on world)
+            from .distributed import run_sharded
+            pieces = run_sharded(plan, rank, world, device=sim.device, precision=sim.precision, seed=sim.seed, max_daily_fish=cap)
+        else:
+            pieces = [(plan.grid, run_compact_retry(plan, sim.device, sim.precision, sim.seed, cap))]
     except _abi.StrykeError as exc:
         if exc.code == _abi.E_MAX_FISH:
             raise ValueError(f"{exc}. Adjust entrainment inputs or raise STRYKE_MAX_DAILY_FISH / "
                              "STRYKE_MAX_DAILY_STATE_ROWS deliberately.") from exc
         raise
-    sim._last_plan, sim._last_result = plan, res
+    tallies = group_tallies(plan, pieces)
+    sim._last_plan, sim._last_result, sim._last_tallies = plan, res, tallies
     warn = int(os.environ.get("STRYKE_WARN_DAILY_FISH", "50000"))        # stryke.py:3041-3051 warns cell by cell
-    n_big = int((res.cell_n >= warn).sum())
-    if n_big:
+    n_max = max([int(t.n.max()) for t in tallies.values() if t.n.size] + [0])
+    if n_max >= warn:
+        n_big = int(sum(int((t.n >= warn).sum()) for t in tallies.values()))
         logger.warning("Large daily fish population: %d cell(s) with n >= %d (largest n=%d; STRYKE_WARN_DAILY_FISH)",
-                       n_big, warn, int(res.cell_n.max()))
+                       n_big, warn, n_max)
     if rank != 0:          # the frames are written once
         return None
-    frames = assemble_frames(sim, plan, res)
+    frames = assemble_frames(sim, plan, tallies)
     # ---- optional per-fish table (STRYKE_STORE_SIM_TABLE, stryke.py:116, :3243-3249) ---------------------------------
     fish_tables = {}
     if _flag("STRYKE_STORE_SIM_TABLE"):
         tr = trace
+        if res is None:
+            res = dense_from_tallies(plan, tallies)
         if tr is None:      # second pass with the general kernel: same seed, same fish, now with the per-fish columns
             n_total = int(res.cell_n.astype(np.int64).sum())
             tr = engine.TraceBuffers.allocate(plan.fac.n_moves, n_total, probs=False)
@@ -414,53 +424,143 @@ def assemble_fish_tables(sim, plan: RunPlan, res: engine.CellResult, tr, rates=F
     return out
 
 
-def assemble_frames(sim, plan: RunPlan, res: engine.CellResult):
-    """Tally arrays -> the reference's result frames, in the reference's row order
-    (scenario -> species -> iteration -> day; stryke.py:3256-3383, :3433-3502)."""
+def run_compact_retry(plan, device, precision, seed, cap):
+    """``engine.run_compact`` on the plan's cell grid with an estimated row capacity, once more with the exact need when the
+    estimate was too small (the engine names it)."""
+    import re
+    from .distributed import expected_slots
+    rows_cap = min(2 * plan.n_cells, expected_slots(plan.grid, plan.species_table)) if plan.n_cells > 4096 else 2 * plan.n_cells
+    try:
+        return engine.run_compact(plan.fac, plan.days, plan.species_table, plan.grid, device=device, precision=precision, seed=seed,
+                                  max_daily_fish=cap, rows_cap=rows_cap)
+    except _abi.StrykeError as exc:
+        m = re.search(r"rows buffer too small: (\d+) slots needed", str(exc))
+        if not m:
+            raise
+        return engine.run_compact(plan.fac, plan.days, plan.species_table, plan.grid, device=device, precision=precision, seed=seed,
+                                  max_daily_fish=cap, rows_cap=int(m.group(1)))
+
+
+@dataclass
+class GroupTallies:
+    """Tallies of one (scenario, species) group in the reference's order (iteration-major, day-minor)."""
+    n: np.ndarray          # int64[I, D]  pop_size (0 = species absent that day)
+    daily: np.ndarray      # int64[I, D, 5]
+    it: np.ndarray         # present cells, sorted by (iteration, day): iteration
+    dd: np.ndarray         #                                            index of the active day
+    state: np.ndarray      # [len(it), n_pairs, 2] successes, count
+
+
+def group_tallies(plan, pieces):
+    """{index into plan.groups: GroupTallies} from the device results: ``pieces`` = [(engine.CellGrid, engine.CompactResult
+    or dense engine.CellResult)], one per rank (iterations of a group may be spread over the pieces, in rank order)."""
+    P = plan.fac.n_pairs
+    parts = {}
+    for grid_p, r in pieces:
+        kept, ilo = getattr(grid_p, "kept", None), getattr(grid_p, "iter_lo", None)
+        if isinstance(r, engine.CompactResult):
+            cells, n, daily, state = r.columns()
+        else:
+            cells = np.flatnonzero(r.cell_n > 0)
+            n, daily, state = r.cell_n[cells].astype(np.int64), r.daily[cells].astype(np.int64), r.state_daily[cells]
+        for j, g in enumerate(grid_p.groups):
+            gi = int(plan.grid_group_index[kept[j] if kept is not None else j])
+            Ip, D, c0 = int(g["iterations"]), int(g["n_active_days"]), int(g["cell0"])
+            a, b = np.searchsorted(cells, [c0, c0 + Ip * D])
+            loc = cells[a:b] - c0
+            parts.setdefault(gi, []).append((int(ilo[j]) if ilo is not None else 0, loc % Ip, loc // Ip, n[a:b], daily[a:b], state[a:b]))
+    out = {}
+    for gi, g in enumerate(plan.groups):
+        I, D = g.iterations, g.n_active_days
+        N, DL = np.zeros((I, D), np.int64), np.zeros((I, D, _abi.DAILY_W), np.int64)
+        its, dds, sts = [], [], []
+        for i_lo, ii, dd, n, daily, state in parts.get(gi, []):
+            N[i_lo + ii, dd] = n
+            DL[i_lo + ii, dd] = daily
+            its.append(i_lo + ii); dds.append(dd); sts.append(state)
+        it = np.concatenate(its) if its else np.zeros(0, np.int64)
+        dd = np.concatenate(dds) if dds else np.zeros(0, np.int64)
+        st = np.concatenate(sts) if sts else np.zeros((0, P, 2), np.uint16)
+        order = np.argsort(it * max(D, 1) + dd, kind="stable")
+        out[gi] = GroupTallies(N, DL, it[order], dd[order], st[order])
+    return out
+
+
+def dense_from_tallies(plan, tallies):
+    """Engine-order dense ``CellResult`` (day-major, iteration-minor per group) from the grouped tallies."""
+    P = plan.fac.n_pairs
+    out_n = np.zeros(plan.n_cells, np.int32)
+    out_d = np.zeros((plan.n_cells, _abi.DAILY_W), np.uint32)
+    out_s = np.zeros((plan.n_cells, P, 2), np.uint32)
+    for gi, g in enumerate(plan.groups):
+        t = tallies[gi]
+        I, D = g.iterations, g.n_active_days
+        if I == 0 or D == 0:
+            continue
+        sl = slice(g.cell0, g.cell0 + I * D)
+        out_n[sl] = t.n.T.ravel()
+        out_d[sl] = t.daily.transpose(1, 0, 2).reshape(I * D, -1)
+        out_s[g.cell0 + t.dd * I + t.it] = t.state
+    return engine.CellResult(out_n, out_d, out_s, None)
+
+
+def assemble_frames(sim, plan: RunPlan, tallies):
+    """Grouped tallies -> the reference's result frames, in the reference's row order
+    (scenario -> species -> iteration -> day; stryke.py:3256-3383, :3433-3502).  Columns are gathered as arrays over all
+    groups and every frame is built once; the label columns (species, scenario, season, state) take their strings from a
+    small table by code — object columns like the reference's for ordinary projects, categoricals above
+    STRYKE_B200_CATEGORICAL_ROWS rows (default 2e6), where one Python string per row would cost more than the simulation."""
     fac = plan.fac
     P = fac.n_pairs
     metric = sim.output_units == "metric"
     dates = np.array(plan.day_dates, dtype="datetime64[ns]")
-    pair_name = np.array([fac.node_names[v] for v in fac.pair_node], dtype=object)
+    pair_name = np.array([str(fac.node_names[v]) for v in fac.pair_node], dtype=object)
     # State_Daily rows of one cell come out of a groupby per move: moves ascending, states alphabetical (:3319-3324)
     pair_order = np.array(sorted(range(P), key=lambda p: (int(fac.pair_move[p]), str(pair_name[p]))), dtype=np.int64)
-    daily_parts, sd_parts, rf_parts, uh_parts = [], [], [], []
+    move_of, name_of = fac.pair_move[pair_order].astype(np.int64), pair_name[pair_order]
+    dcols = {k: [] for k in ("grp", "iteration", "day", "flow", "pop_size", "num_entrained", "num_survived", "num_mortality",
+                             "mortality_impingement", "mortality_blade_strike", "mortality_barotrauma")}
+    scols = {k: [] for k in ("grp", "iteration", "day", "move", "state", "successes", "count")}
+    rf_parts, uh_parts = [], []
     logged = {}     # scenario -> bool[iteration, day row]: Route_Flows / Unit_Hours already written (stryke.py:3437)
     for gi, g in enumerate(plan.groups):
         D, I = g.n_active_days, g.iterations
         if D == 0 or I == 0:
             continue
-        sl = slice(g.cell0, g.cell0 + D * I)
-        keep = np.ones((I, D), bool)          # peaking plants: cells whose units all sat idle produce no rows (:3025)
+        t = tallies[gi]
+        keep = None                           # peaking plants: cells whose units all sat idle produce no rows (:3025)
         if gi in plan.cell_hours:
-            keep = (plan.cell_hours[gi][1].sum(axis=-1) > 0).T
-        # engine order (day, iteration) -> reference order (iteration, day)
-        n = res.cell_n[sl].reshape(D, I).T.astype(np.int64)
-        dl = res.daily[sl].reshape(D, I, _abi.DAILY_W).transpose(1, 0, 2).astype(np.int64)
-        sd = res.state_daily[sl].reshape(D, I, P, 2).transpose(1, 0, 2, 3)
+            k2 = (plan.cell_hours[gi][1].sum(axis=-1) > 0).T
+            keep = None if k2.all() else k2
+        dl = t.daily
         day_rows = g.day0 + g.active_days
         flow = plan.days.curr_Q[day_rows] * (CFS_TO_CMS if metric else 1.0)
-        it_col = np.repeat(np.arange(I, dtype=np.int64), D)
-        day_col = np.tile(dates[day_rows], I)
-        ent, sur = dl[..., 0].ravel(), dl[..., 1].ravel()
+        sel = slice(None) if keep is None else keep.ravel()
+        ent, sur = dl[..., 0].ravel()[sel], dl[..., 1].ravel()[sel]
         gate = ent > 0                                              # stryke.py:3359
-        daily = pd.DataFrame({
-            "species": "{:50}".format(g.species), "scenario": "{:50}".format(g.scenario), "season": "{:50}".format(g.season),
-            "iteration": it_col, "day": day_col, "flow": np.tile(flow.astype(np.float64), I),
-            "pop_size": n.ravel(), "num_entrained": ent, "num_survived": sur, "num_mortality": ent - sur,
-            "mortality_impingement": np.where(gate, dl[..., 2].ravel(), 0),
-            "mortality_blade_strike": np.where(gate, dl[..., 3].ravel(), 0),
-            "mortality_barotrauma": np.where(gate, dl[..., 4].ravel(), 0)})
-        daily_parts.append(daily if keep.all() else daily[keep.ravel()])
-        cnt = sd[..., 1].reshape(I * D, P)[:, pair_order] * keep.reshape(I * D, 1)
-        suc = sd[..., 0].reshape(I * D, P)[:, pair_order] * keep.reshape(I * D, 1)
+        dcols["grp"].append(np.full(ent.shape[0], gi, np.int32))
+        dcols["iteration"].append(np.repeat(np.arange(I, dtype=np.int64), D)[sel])
+        dcols["day"].append(np.tile(dates[day_rows], I)[sel])
+        dcols["flow"].append(np.tile(flow.astype(np.float64), I)[sel])
+        dcols["pop_size"].append(t.n.ravel()[sel])
+        dcols["num_entrained"].append(ent)
+        dcols["num_survived"].append(sur)
+        dcols["num_mortality"].append(ent - sur)
+        for j, nm in ((2, "mortality_impingement"), (3, "mortality_blade_strike"), (4, "mortality_barotrauma")):
+            dcols[nm].append(np.where(gate, dl[..., j].ravel()[sel], 0))
+        kp = None if keep is None else keep[t.it, t.dd]
+        st = t.state if kp is None else t.state[kp]
+        s_it, s_dd = (t.it, t.dd) if kp is None else (t.it[kp], t.dd[kp])
+        cnt = st[:, pair_order, 1]
         ci, pi = np.nonzero(cnt)
         if ci.size:
-            sd_parts.append(pd.DataFrame({
-                "scenario": str(g.scenario), "species": str(g.species), "iteration": it_col[ci].astype(int),
-                "day": day_col[ci], "move": fac.pair_move[pair_order][pi].astype(int),
-                "state": pair_name[pair_order][pi].astype(str), "successes": suc[ci, pi].astype(float),
-                "count": cnt[ci, pi].astype(float)}))
+            scols["grp"].append(np.full(ci.size, gi, np.int32))
+            scols["iteration"].append(s_it[ci].astype(np.int64))
+            scols["day"].append(dates[day_rows][s_dd[ci]])
+            scols["move"].append(move_of[pi])
+            scols["state"].append(pi.astype(np.int32))
+            scols["successes"].append(st[ci, pair_order[pi], 0].astype(np.float64))
+            scols["count"].append(cnt[ci, pi].astype(np.float64))
         # Route_Flows / Unit_Hours: once per (scenario, iteration, day), by the first species that gets there (:3437)
         n_rows = len(plan.day_rows)
         done = logged.setdefault(g.scenario, np.zeros((0, n_rows), bool))
@@ -469,13 +569,41 @@ def assemble_frames(sim, plan: RunPlan, res: engine.CellResult):
         fresh = ~done[:I][:, day_rows]
         if fresh.any():
             hours = plan.cell_hours.get(gi)
-            rf, uh = _route_and_hours(plan, g, suc.reshape(I, D, P), pair_order, fresh, day_rows, dates, hours)
+            suc = np.zeros((I, D, P), np.int64)                    # successes of the group's cells (only its first species per scenario gets here)
+            suc[s_it, s_dd] = st[:, pair_order, 0]
+            rf, uh = _route_and_hours(plan, g, suc, pair_order, fresh, day_rows, dates, hours)
             rf_parts += rf
             uh_parts += uh
         done[:I, day_rows] = True
         logged[g.scenario] = done
     cat = lambda parts: pd.concat(parts, ignore_index=True) if parts else None
-    return {"Daily": cat(daily_parts), "State_Daily": cat(sd_parts), "Route_Flows": cat(rf_parts), "Unit_Hours": cat(uh_parts)}
+    join = lambda xs: np.concatenate(xs) if xs else np.zeros(0)
+    daily = sd = None
+    if dcols["grp"]:
+        grp = join(dcols["grp"])
+        daily = pd.DataFrame({
+            "species": _labels(["{:50}".format(g.species) for g in plan.groups], grp),
+            "scenario": _labels(["{:50}".format(g.scenario) for g in plan.groups], grp),
+            "season": _labels(["{:50}".format(g.season) for g in plan.groups], grp),
+            **{k: join(v) for k, v in dcols.items() if k != "grp"}}, copy=False)
+    if scols["grp"]:
+        grp = join(scols["grp"])
+        sd = pd.DataFrame({
+            "scenario": _labels([str(g.scenario) for g in plan.groups], grp), "species": _labels([str(g.species) for g in plan.groups], grp),
+            "iteration": join(scols["iteration"]), "day": join(scols["day"]), "move": join(scols["move"]),
+            "state": _labels([str(x) for x in name_of], join(scols["state"])), "successes": join(scols["successes"]),
+            "count": join(scols["count"])}, copy=False)
+    return {"Daily": daily, "State_Daily": sd, "Route_Flows": cat(rf_parts), "Unit_Hours": cat(uh_parts)}
+
+
+def _labels(labels, codes):
+    """Label column: ``labels[codes]`` as an object Series (what the reference writes) or, for very long frames, a
+    categorical with the same values."""
+    codes = np.asarray(codes)
+    if codes.shape[0] > int(os.environ.get("STRYKE_B200_CATEGORICAL_ROWS", "2000000")):
+        cats, inv = np.unique(np.asarray(labels, dtype=object).astype(str), return_inverse=True)
+        return pd.Categorical.from_codes(np.asarray(inv)[codes], categories=list(cats))
+    return pd.Series(np.asarray(labels, dtype=object)[codes], dtype=object)
 
 
 def _route_and_hours(plan, g, suc, pair_order, fresh, day_rows, dates, cell_hours):

@@ -10,6 +10,8 @@ file:line citations are relative to /root/reference.
 """
 from __future__ import annotations
 
+import contextlib
+
 import json
 import logging
 import math
@@ -23,6 +25,12 @@ from networkx.readwrite import json_graph
 
 from . import _abi, engine, routing, tables
 from .store import open_store
+
+
+def _is_writer():
+    """Only rank 0 of a torch.distributed job creates / writes the project's result store (every rank runs the ingest)."""
+    from .runner import _dist_rank_world
+    return _dist_rank_world()[0] == 0
 
 logger = logging.getLogger(__name__)
 
@@ -95,7 +103,7 @@ class simulation:
     precision = 32
     #: Philox4x32-10 key of the native RNG
     seed = 0x5EED
-    #: CUDA ordinal
+    #: CUDA ordinal; inside a torch.distributed job (one process per GPU) the default is the process's LOCAL_RANK
     device = 0
 
     def __init__(self, proj_dir, output_name, wks=None, existing=False):
@@ -150,7 +158,7 @@ class simulation:
         self.pop = book.frame("Population", "B:V", skiprows=11, expect=("Species", "Scenario"))
         self.proj_dir, self.output_name = proj_dir, output_name
         self.hdf_path = os.path.join(self.proj_dir, "%s.h5" % self.output_name)
-        with open_store(self.hdf_path, mode="w") as hdf:
+        with (open_store(self.hdf_path, mode="w") if _is_writer() else contextlib.nullcontext({})) as hdf:
             hdf["Flow Scenarios"] = self.flow_scenarios_df
             hdf["Operating Scenarios"] = self.operating_scenarios_df
             hdf["Population"] = self.pop
@@ -282,7 +290,7 @@ class simulation:
                 raise ValueError(f"Hydrograph contains invalid {src[0]}/{src[1]} values: invalid_dates={bad_d}, "
                                  f"invalid_flows={bad_q}. Fix or remove malformed rows in hydrograph.csv.")
             self.input_hydrograph_df = df
-        with open_store(hdf_path, mode="w") as hdf:
+        with (open_store(hdf_path, mode="w") if _is_writer() else contextlib.nullcontext({})) as hdf:
             for key, df in (("Flow Scenarios", getattr(self, "flow_scenarios_df", None)),
                             ("Operating Scenarios", getattr(self, "operating_scenarios_df", None)),
                             ("Population", getattr(self, "pop", None)), ("Nodes", self.nodes), ("Edges", self.edges),

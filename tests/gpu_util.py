@@ -11,17 +11,7 @@ from stryke_b200.engine import Injected, TraceBuffers, run_cells
 from stryke_b200.runner import RunPlan
 
 
-def make_sim(prj, name="case", proj_dir="/tmp/stryke_b200_tests"):
-    sim = simulation.__new__(simulation)
-    fixtures.apply_to(sim, prj, proj_dir=proj_dir, output_name=name)
-    return sim
-
-
-def make_plan(prj, name="case"):
-    sim = make_sim(prj, name)
-    with contextlib.redirect_stdout(io.StringIO()):
-        plan = RunPlan(sim)
-    return sim, plan
+from stryke_b200.workloads import make_plan, make_sim  # noqa: E402,F401
 
 
 def reference_cell_index(plan):

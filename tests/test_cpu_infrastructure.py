@@ -206,31 +206,48 @@ def test_shard_bounds_cover_everything():
 GLOO_WORKER = textwrap.dedent("""
     import os, sys
     import numpy as np, torch, torch.distributed as dist
-    sys.path.insert(0, %r)
-    from stryke_b200.distributed import shard_bounds, allreduce_tallies
+    sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+    from golden_util import Golden
+    import gpu_util as G
+    from test_frames_cpu import encode_compact, golden_dense, check_frames
+    from stryke_b200 import runner
+    from stryke_b200.engine import CellResult
+    from stryke_b200.distributed import ShardLayout, pack_flat, unpack_flat, gather_flat, agree_on_status
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    C, P = 1001, 10
-    lo, hi = shard_bounds(C, rank, world)
-    cells = torch.arange(C, dtype=torch.int32)
-    n = torch.zeros(C, dtype=torch.int32); d = torch.zeros((C, 5), dtype=torch.int32); s = torch.zeros((C, P, 2), dtype=torch.int32)
-    # every rank fills ONLY its block with a function of the global cell index (what the kernels do with the Philox
-    # stream keyed by the cell id), zeros elsewhere
-    n[lo:hi] = cells[lo:hi] * 3 + 1
-    d[lo:hi] = (cells[lo:hi, None] * 5 + torch.arange(5, dtype=torch.int32)[None, :])
-    s[lo:hi] = (cells[lo:hi, None, None] + torch.arange(P, dtype=torch.int32)[None, :, None] * 2 + torch.arange(2, dtype=torch.int32)[None, None, :])
-    allreduce_tallies([n, d, s])
-    ok = bool((n == cells * 3 + 1).all()) and bool((d == cells[:, None] * 5 + torch.arange(5, dtype=torch.int32)[None, :]).all())
-    ok = ok and bool((s == cells[:, None, None] + torch.arange(P, dtype=torch.int32)[None, :, None] * 2 + torch.arange(2, dtype=torch.int32)[None, None, :]).all())
+    # the reference's own tallies of a multi-scenario population-mode run (tests/golden), split by iteration over the ranks:
+    # every rank packs ITS iterations as compact rows into its flat buffer, ONE all-gather, every rank assembles the frames
+    g = Golden("c3_multi_scenario")
+    sim, plan = G.make_plan(g.prj, "gloo")
+    res, _ = golden_dense(g, plan)
+    day, spc, ids = plan.grid.explicit()
+    pos = {int(i): k for k, i in enumerate(ids)}
+    grids = [plan.grid.iterations_slice(r / world, (r + 1) / world) for r in range(world)]
+    mine = grids[rank]
+    sel = np.array([pos[int(i)] for i in mine.explicit()[2]], dtype=np.int64)
+    part = encode_compact(CellResult(res.cell_n[sel], res.daily[sel], res.state_daily[sel], None), narrow_max=65534)
+    n_max = max(x.n_cells for x in grids)
+    L = ShardLayout(n_max, plan.fac.n_pairs, slab_cells=256 * ((n_max + 255) // 256), slab_cap=2 * n_max + 8)
+    flat = torch.from_numpy(pack_flat(L, np.stack([part.blk_row, part.blk_mask, part.blk_wide]), part.rows, 0, mine.n_cells, part.n_slots))
+    gathered = gather_flat(flat, world).numpy().reshape(world, L.total)
+    pieces = []
+    for r in range(world):
+        n_cells, status, c = unpack_flat(L, gathered[r], plan.fac.n_pairs)
+        assert n_cells == grids[r].n_cells and status == 0
+        pieces.append((grids[r], c))
+    check_frames(g, plan, sim, runner.group_tallies(plan, pieces))
+    # an error on one rank reaches all of them before any further collective
+    code = agree_on_status(-4 if rank == 1 else 0)
+    ok = code == -4 and agree_on_status(0) == 0
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 3)
 """)
 
 
-def test_world_size_2_sharding_and_allreduce_over_gloo(tmp_path):
+def test_world_size_2_sharding_and_gather_over_gloo(tmp_path):
     script = tmp_path / "worker.py"
-    script.write_text(GLOO_WORKER % ROOT)
+    script.write_text(GLOO_WORKER % (ROOT, ROOT))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29653", WORLD_SIZE="2")
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r))) for r in range(2)]
     assert [p.wait(timeout=240) for p in procs] == [0, 0]

@@ -4,7 +4,7 @@ import pytest
 
 from oracle import fixtures
 import gpu_util as G
-from stryke_b200 import engine
+from stryke_b200 import _abi, engine
 
 pytestmark = pytest.mark.gpu
 
@@ -115,10 +115,13 @@ def test_pooled_remainders_next_to_a_huge_cell(monkeypatch):
     species[37] = len(table) - 1
     args = (plan.fac, plan.days, table, plan.cell_day, species, plan.cell_id)
     monkeypatch.setenv("STRYKE_B200_POOL", "1")
-    a = engine.run_cells(*args, precision=32, seed=4, max_daily_fish=10 ** 7, kernel_variant=3)
+    a = engine.run_cells(*args, precision=32, seed=4, max_daily_fish=10 ** 8, kernel_variant=3)
     monkeypatch.setenv("STRYKE_B200_POOL", "0")
-    b = engine.run_cells(*args, precision=32, seed=4, max_daily_fish=10 ** 7, kernel_variant=3)
+    b = engine.run_cells(*args, precision=32, seed=4, max_daily_fish=10 ** 8, kernel_variant=3)
     assert a.cell_n[37] == 70_000_013 and _same(a, b)
+    # the population cap holds for fixed counts too (stryke.py:3052), as for drawn ones (:2610)
+    with pytest.raises(_abi.StrykeError, match="exceeds STRYKE_MAX_DAILY_FISH"):
+        engine.run_cells(*args, precision=32, seed=4, max_daily_fish=10 ** 7, kernel_variant=3)
     assert int(a.state_daily[37, 0, 1]) == 70_000_013
 
 

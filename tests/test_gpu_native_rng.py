@@ -110,7 +110,8 @@ def test_length_normal_tail_mass_and_range():
     """The one-word Box-Muller (16-bit centred radius and angle): tail masses beyond 2, 3, 4 sigma agree with the normal law
     (binomial tests on 8e6 fish), no point mass at z = 0, |z| <= sqrt(-2 ln 2^-17) = 4.855; the wide stream reaches further."""
     n = 4_000_000
-    prj = fixtures.c2_facility(n_fish=n, iterations=2, days=1)
+    # (a length location of 0: with the example species' negative location the lower tail folds at |.|, stryke.py:3071)
+    prj = fixtures.c2_facility(n_fish=n, iterations=2, days=1, species=dict(fixtures.SHAD, **{"length location": 0.0}))
     sim, plan = G.make_plan(prj, "tail")
     prow = prj["population"][0]
     s_, loc, scale = prow["length shape"], prow["length location"], prow["length scale"]
