@@ -110,8 +110,7 @@ struct StrykePlan {
   int64_t n_cells = 0;
   DevBuf nodes, edge_dst, moves, pair_node, ustatic, edge_cdf, node_stay, unit_coef, day_Q, species, cell_day,
       cell_species, cell_id, tile_off, fish_off, err, blk_S, pareto;
-  DevBuf groups, active_days, blk_tile, blk_row, blk_mask, blk_wide, scan_flag, scan_agg, scan_incl;
-  unsigned int epoch = 0;     // launch number: tags the look-back flags of count_kernel
+  DevBuf groups, active_days, blk_tile, blk_row, blk_mask, blk_wide, scan_status;
   int n_days = 0, n_species = 0, row_w = 0, narrow_max = 0;
   int64_t last_rows_cap = -1;  // capacity of the last compact launch (-1: dense)
   bool attr_set = false;      // cudaFuncAttributeMaxDynamicSharedMemorySize applied to this plan's passage kernel
@@ -339,10 +338,7 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
   CK(pl->blk_row.alloc((NB + 1) * sizeof(uint32_t)));
   CK(pl->blk_mask.alloc((NB + 1) * sizeof(uint32_t)));
   CK(pl->blk_wide.alloc((NB + 1) * sizeof(uint32_t)));
-  CK(pl->scan_flag.alloc((NCB + 1) * sizeof(unsigned int)));
-  CK(cudaMemsetAsync(pl->scan_flag.p, 0, (NCB + 1) * sizeof(unsigned int), 0));
-  CK(pl->scan_agg.alloc((NCB + 1) * 3 * sizeof(long long)));
-  CK(pl->scan_incl.alloc((NCB + 1) * 3 * sizeof(long long)));
+  CK(pl->scan_status.alloc((NCB + 1) * sizeof(uint4)));
   CK(pl->err.alloc(ERR_N * sizeof(unsigned long long)));    // status words (ERR_*): error word, chunk counter, totals
   CK(cudaMemsetAsync(pl->err.p, 0, ERR_N * sizeof(unsigned long long), 0));
 
@@ -451,6 +447,8 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
     int n_cause = 0;
     for (int k = 0; k < f->n_moves; ++k) n_cause += (moves[k].need & NEED_CAUSE) ? 1 : 0;
     pl->narrow_max = (65535 - n_cause) / std::max(1, n_cause);
+    // pooled remainders: 63 fish of one cell fit the packed fields when 63 * (turbine levels) <= 1023 (10-bit cause fields)
+    K.pool_all = (n_cause <= 16 && !(getenv("STRYKE_B200_POOL_ALL") && atoi(getenv("STRYKE_B200_POOL_ALL")) == 32)) ? 64 : 32;
     pl->row_w = f->n_pairs + 3;
     K.out.row_w = pl->row_w; K.out.narrow_max = pl->narrow_max; K.out.cap = 0;
   }
@@ -665,8 +663,9 @@ static int launch_cells(StrykePlan* pl, int64_t c_lo, int64_t c_hi, int32_t* d_c
   O.err = err;
   O.slot0 = compact && first_slot >= 0 ? (long long)first_slot : -1ll;
   O.slots_after = d_slots_after;
-  ScanDev S{pl->scan_flag.as<unsigned int>(), pl->scan_agg.as<long long>(), pl->scan_incl.as<long long>(), ++pl->epoch};
   const int cb = (int)((nC + COUNT_T - 1) / COUNT_T);
+  ScanDev S{pl->scan_status.as<uint4>()};
+  CK(cudaMemsetAsync(S.status, 0, (size_t)cb * sizeof(uint4), st));      // look-back states: empty
   if (pl->inject) count_kernel<true><<<cb, COUNT_T, 0, st>>>(K, pl->day_Q.as<double>(), O, pl->max_daily_fish, pl->pareto.as<double>(), S, pl->n_days, pl->n_species);
   else count_kernel<false><<<cb, COUNT_T, 0, st>>>(K, pl->day_Q.as<double>(), O, pl->max_daily_fish, pl->pareto.as<double>(), S, pl->n_days, pl->n_species);
   g_launches += 1;

@@ -163,6 +163,7 @@ struct KParams {
   const StrykeCellGroup* groups; int n_groups; const int32_t* active_days; uint64_t id_days, id_add;
   int64_t cell_base;                  // index of this launch's first cell in the plan's cell list (launches over a range)
   RowsDev out;                        // compact tally rows
+  int pool_all;                       // pooled remainders: cells below this many fish (32 or 64) are pooled entirely
   const int64_t* blk_tile;            // pooled remainders: first tile of every aligned block of 32 cells [n_blocks + 1]
   const uint32_t* blk_S;              // pooled remainders (passage_fast.cuh): per block of 32 cells, shared tiles [0:31) | mixed [31]
 };
@@ -179,25 +180,50 @@ struct KParams {
 #define STRYKE_BCHK(P, cond, site) do { } while (0)
 #endif
 
-// (day row, species row, Philox cell id) of cell c of the launch — from the explicit arrays or from the group table
+// (day row, species row, Philox cell id) of cell c of the launch — from the explicit arrays or from the group table.
+// With a group table the lookup is split: group_cursor finds the group of a BASE cell (a binary search and one 64-bit
+// division, done once per thread block of count_kernel / per block of 32 cells of the passage kernel, with warp-uniform
+// operands), cell_at then places the cells that follow it with 32-bit arithmetic.
 struct CellInfo { int day, species; uint64_t id; };
-__device__ __forceinline__ CellInfo cell_info(const KParams& P, int64_t c) {
-  CellInfo ci;
-  if (P.groups == nullptr) {
-    ci.day = P.cell_day[c]; ci.species = P.cell_species[c]; ci.id = P.cell_id[c];
-    return ci;
-  }
+struct GroupCursor {
+  int64_t base, end;            // launch-relative cells [base, end) lie in this group from `base` on
+  int iterations, day0, species, act_off, dd0, rem0;
+  uint64_t id_base;
+};
+__device__ __forceinline__ GroupCursor group_cursor(const KParams& P, int64_t c) {
+  GroupCursor G;
   const int64_t gc = c + P.cell_base;
   int lo = 0, hi = P.n_groups;                      // last group with cell0 <= gc
   while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (P.groups[mid].cell0 <= gc) lo = mid; else hi = mid; }
   const StrykeCellGroup g = P.groups[lo];
   const int64_t local = gc - g.cell0;
-  const int dd = (int)(local / g.iterations);
-  const int it = (int)(local - (int64_t)dd * g.iterations);
-  const int rel = P.active_days[g.active_off + dd];
-  ci.day = g.day0 + rel; ci.species = g.species;
-  ci.id = (g.id_base + (uint64_t)it) * P.id_days + (uint64_t)rel + P.id_add;
+  G.base = c;
+  G.end = c + ((int64_t)g.iterations * g.n_active_days - local);
+  G.iterations = g.iterations; G.day0 = g.day0; G.species = g.species; G.act_off = g.active_off; G.id_base = g.id_base;
+  const int64_t dd = local / g.iterations;
+  G.dd0 = (int)dd; G.rem0 = (int)(local - dd * g.iterations);
+  return G;
+}
+__device__ __forceinline__ CellInfo cell_at(const KParams& P, const GroupCursor& G, int64_t c) {
+  CellInfo ci;
+  if (P.groups == nullptr) {
+    ci.day = P.cell_day[c]; ci.species = P.cell_species[c]; ci.id = P.cell_id[c];
+    return ci;
+  }
+  GroupCursor H = G;
+  if (c < G.base || c >= G.end || c - G.base > 0x3fffffffll) H = group_cursor(P, c);      // (rare: the cell lies in a later group)
+  const unsigned int r = (unsigned int)H.rem0 + (unsigned int)(c - H.base);
+  const unsigned int q = r / (unsigned int)H.iterations;
+  const int it = (int)(r - q * (unsigned int)H.iterations);
+  const int rel = P.active_days[H.act_off + H.dd0 + (int)q];
+  ci.day = H.day0 + rel; ci.species = H.species;
+  ci.id = (H.id_base + (uint64_t)it) * P.id_days + (uint64_t)rel + P.id_add;
   return ci;
+}
+__device__ __forceinline__ CellInfo cell_info(const KParams& P, int64_t c) {
+  GroupCursor G{};
+  if (P.groups != nullptr) G = group_cursor(P, c);
+  return cell_at(P, G, c);
 }
 
 // Lane-held accumulators of one cell (lane p + 32 r owns pair p + 32 r, lanes 0..4 the Daily columns) -> global tallies.
@@ -253,6 +279,12 @@ __device__ __forceinline__ void tally_flush(const KParams& P, int64_t cell, int 
   for (int r = 0; r < PR; ++r) { acc_suc[r] = 0; acc_cnt[r] = 0; }
   acc_daily = 0;
 }
+
+// Pooled remainders: a cell of n fish keeps pool_full(n) tiles of its own and sends pool_rem(n) fish to the shared tiles of
+// its block.  Cells below pool_all fish (64 when the packed 6-/10-bit tally fields can hold 63 fish of one cell, else 32) are
+// pooled entirely: entering and leaving a cell costs more than simulating its one or two tiles.
+__host__ __device__ __forceinline__ int pool_rem(int n, int pool_all) { return n < pool_all ? n : (n & 31); }
+__host__ __device__ __forceinline__ int pool_full(int n, int pool_all) { return n < pool_all ? 0 : (n >> 5); }
 
 constexpr double P_ATM = 101325.0;    // scipy.constants.atm (stryke.py:1472)
 constexpr double G_SI = 9.80665;      // scipy.constants.g   (stryke.py:1471)

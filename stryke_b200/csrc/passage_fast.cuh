@@ -43,7 +43,7 @@ __host__ __device__ inline uint32_t pack_node(int kind, int hasU, int unit, int 
 
 struct FastSmem {
   int nodes, ustatic, uc1, species, warp0, warp_stride, cdf, dst, ucoef, total;
-  int pool_blk, pool_ef, pool_rank, pool_seg, pool_sd;   // per-warp scratch of the pooled-remainder path (pool_nw > 0)
+  int pool_blk, pool_ef, pool_rank, pool_seg, pool_sd, pool_full;   // per-warp scratch of the pooled-remainder path (pool_nw > 0)
   int pool_field;                                  // per block: where every (pair, arrivals | survivors) / Daily counter sits
 };
 // floats per row of the staged routing cdf: the stride-1 thresholds a draw is compared with, padded to whole float4s
@@ -67,6 +67,7 @@ __host__ __device__ constexpr FastSmem fast_smem(int n_nodes, int n_units, int s
     L.pool_ef = w; w += 32 * 8;                              // int64 per cell: full tiles of the block before this cell
     L.pool_rank = w; w += 32 * 4;                            // lane of the rho-th cell that has a remainder
     L.pool_sd = w; w += 32 * 8;                              // int2 per cell: species row, day row
+    L.pool_full = w; w += 32 * 4;                            // full tiles of the cell
     L.pool_seg = w; w = (w + 32 * pool_nw * 4 + 15) & ~15;         // per cell of the block: accumulated tally words
   }
   L.warp_stride = w;
@@ -533,6 +534,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   long long* s_ef = reinterpret_cast<long long*>(wbase + SL.pool_ef);
   int* s_rank = reinterpret_cast<int*>(wbase + SL.pool_rank);
   int2* s_sd = reinterpret_cast<int2*>(wbase + SL.pool_sd);
+  int* s_full = reinterpret_cast<int*>(wbase + SL.pool_full);           // full tiles of every cell of the block
   uint32_t* s_acc = reinterpret_cast<uint32_t*>(wbase + SL.pool_seg);        // [32 cells][NW]
   uint32_t* s_field = reinterpret_cast<uint32_t*>(smem + SL.pool_field);     // [2 n_pairs + 5]: word [0:5) shift [5:10) 10-bit [10] exists [11]
   const int NI = 2 * n_pairs + STRYKE_DAILY_W;
@@ -662,12 +664,14 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         const bool in = ci < P.n_cells;
         const int n = in ? P.cell_n[ci] : 0;
         CellInfo cinf{0, 0, 0ull};
-        if (in) cinf = cell_info(P, ci);
+        GroupCursor gcur{};
+        if (P.groups != nullptr) gcur = group_cursor(P, b << 5);      // warp-uniform: one search for the block's first cell
+        if (in) cinf = cell_at(P, gcur, ci);
         const uint64_t id = cinf.id;
         const uint32_t info = P.blk_S[b];
         S_b = (int)(info & 0x7fffffffu);
-        const int r = n & 31, f = n >> 5;
-        const int pr = (info >> 31) ? (r ? 32 : 0) : r;   // mixed block: every remainder is padded to a tile of its own
+        const int r = pool_rem(n, P.pool_all), f = pool_full(n, P.pool_all);
+        const int pr = (info >> 31) ? ((r + 31) & ~31) : r;   // mixed block: every remainder is padded to whole tiles of its own
         int sr = pr;
         long long sf = f;
 #pragma unroll
@@ -676,11 +680,12 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
           const long long tf = __shfl_up_sync(0xffffffffu, sf, o);
           if (lane >= o) { sr += tr; sf += tf; }
         }
-        const uint32_t rmask = __ballot_sync(0xffffffffu, r > 0);
+        const uint32_t rmask = __ballot_sync(0xffffffffu, r > 0);      // cells with pooled fish
         nrem = __popc(rmask);
         __syncwarp();
         s_blk[lane] = make_uint4((uint32_t)n, (uint32_t)id, (uint32_t)(id >> 32), (uint32_t)(sr - pr));
         s_ef[lane] = sf - f;
+        s_full[lane] = f;
         s_sd[lane] = make_int2(cinf.species, cinf.day);
         if (r > 0) s_rank[__popc(rmask & (below >> 1))] = lane;
         __syncwarp();
@@ -694,7 +699,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         const int base = (int)j << 5;
         const uint4 mine = s_blk[lane];
         const int rel = (int)mine.w - base;
-        const bool has_r = (mine.x & 31u) != 0u;
+        const bool has_r = pool_rem((int)mine.x, P.pool_all) != 0;
         const uint32_t M = __reduce_or_sync(0xffffffffu, (has_r && (unsigned)rel < 32u) ? (1u << rel) : 0u);
         const int K0 = __popc(__ballot_sync(0xffffffffu, has_r && rel < 0));     // remainders that start before the tile
         const int rank = K0 + __popc(M & below) - 1;
@@ -703,21 +708,22 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         STRYKE_BCHK(P, jl >= 0 && jl < 32, 10);
         const uint4 cellrec = s_blk[jl];
         const int n = (int)cellrec.x;
-        fish = (n & ~31) + (base + lane - (int)cellrec.w);
+        const int own = pool_full(n, P.pool_all) << 5;      // fish of the cell's own full tiles come first
+        fish = own + (base + lane - (int)cellrec.w);
         active = fish < n;
-        STRYKE_BCHK(P, fish >= (n & ~31) && (lane != 0 || active), 11);
+        STRYKE_BCHK(P, fish >= own && (lane != 0 || active), 11);
         cid_lo = cellrec.y; cid_hi = cellrec.z;
         const int2 sd = s_sd[__shfl_sync(0xffffffffu, jl, 0)];
         load_params(sd.x, sd.y);
       } else {                                          // full tile jj of the block: which cell?
         const long long jj = j - S_b;
         const long long ef = s_ef[lane];
-        const int f = (int)(s_blk[lane].x >> 5);
+        const int f = s_full[lane];
         const int sel = __ffs(__ballot_sync(0xffffffffu, f > 0 && jj >= ef && jj < ef + f)) - 1;
         STRYKE_BCHK(P, sel >= 0 && sel < 32, 13);
         const long long ef_s = s_ef[sel];
         const uint4 cellrec = s_blk[sel];
-        run = __shfl_sync(0xffffffffu, clamp30(ef_s + (long long)(cellrec.x >> 5) - jj), 0);
+        run = __shfl_sync(0xffffffffu, clamp30(ef_s + (long long)s_full[sel] - jj), 0);
         run = run < chunk_left ? run : chunk_left;
         fish_base = __shfl_sync(0xffffffffu, (int)(jj - ef_s) * 32, 0);
         fish = fish_base + lane;

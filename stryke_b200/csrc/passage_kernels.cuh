@@ -93,11 +93,11 @@ __device__ __forceinline__ double std_normal(double u1_oc, double u2_co) {
 // end with those of the other cells of its block and cut into shared tiles.  A block whose cells differ in species or
 // day ("mixed") keeps one tile per remainder instead (the day tables and species parameters are warp-uniform).  Returns
 // the block's number of shared tiles (bit 31: mixed).  Called by all 32 lanes; lanes past the last cell pass in = false.
-__device__ __forceinline__ uint32_t pool_block(bool in, int n, int sp, int dy) {
+__device__ __forceinline__ uint32_t pool_block(bool in, int n, int sp, int dy, int pool_all) {
   const int sp0 = __shfl_sync(0xffffffffu, sp, 0), dy0 = __shfl_sync(0xffffffffu, dy, 0);
   const bool mixed = __ballot_sync(0xffffffffu, in && (sp != sp0 || dy != dy0)) != 0u;
-  const int r = n & 31;
-  const uint32_t tot = mixed ? 32u * (uint32_t)__popc(__ballot_sync(0xffffffffu, r > 0)) : __reduce_add_sync(0xffffffffu, (uint32_t)r);
+  const int r = pool_rem(n, pool_all);
+  const uint32_t tot = __reduce_add_sync(0xffffffffu, mixed ? (uint32_t)((r + 31) & ~31) : (uint32_t)r);
   return ((tot + 31u) >> 5) | (mixed ? 0x80000000u : 0u);
 }
 
@@ -132,12 +132,30 @@ constexpr int COUNT_T = 256;
 // slot count from one range of cells to the next, ERR_FISH_CUM the fish.
 enum : int { ERR_WORD = 0, ERR_WORK = 1, ERR_TICKET = 2, ERR_FISH = 3, ERR_FISH_CUM = 4, ERR_SLOTS = 5, ERR_TILES = 6, ERR_N = 8 };
 constexpr unsigned long long ERRBIT_RANGE = 0xA000000000000000ull, ERRBIT_NONFINITE = 0x8000000000000000ull;
-struct ScanDev {                  // decoupled look-back state, one entry per thread block of count_kernel
-  unsigned int* flag;             // 4 * epoch + 1: aggregate published, 4 * epoch + 2: inclusive prefix published
-  long long* agg;                 // [n_blocks][3] tiles, fish, slots of the block
-  long long* incl;                // [n_blocks][3] inclusive prefix
-  unsigned int epoch;             // changes with every launch: the flags need no clearing
-};
+// Decoupled look-back state: ONE 16-byte word per thread block of count_kernel, cleared before every launch.  State and the
+// three running sums travel together in a single 128-bit store / load (as in CUB's single-pass scan), so no memory fence is
+// needed between "value written" and "flag set":
+//   x = state (0 empty, 1 aggregate of the block, 2 inclusive prefix) | slots << 2   (slots < 2^30)
+//   y = tiles [31:0],  z = tiles [39:32] | fish [55:32] << 8,  w = fish [31:0]
+struct ScanDev { uint4* status; };
+__device__ __forceinline__ uint4 scan_pack(unsigned int state, long long tiles, long long fish, long long slots) {
+  return make_uint4(state | ((unsigned int)slots << 2), (unsigned int)tiles,
+                    ((unsigned int)((unsigned long long)tiles >> 32) & 0xffu) | ((unsigned int)((unsigned long long)fish >> 32) << 8),
+                    (unsigned int)fish);
+}
+__device__ __forceinline__ void scan_unpack(const uint4 v, long long& tiles, long long& fish, long long& slots) {
+  slots = (long long)(v.x >> 2);
+  tiles = (long long)(((unsigned long long)(v.z & 0xffu) << 32) | v.y);
+  fish = (long long)(((unsigned long long)(v.z >> 8) << 32) | v.w);
+}
+__device__ __forceinline__ void scan_store(uint4* p, const uint4 v) {
+  asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 scan_load(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.cv.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
 struct CountOut {
   int32_t* cell_n;
   int64_t* tile_off;              // [n_cells + 1] or nullptr (pooled plans use blk_tile)
@@ -154,17 +172,21 @@ __global__ void __launch_bounds__(COUNT_T) count_kernel(const KParams P, const d
                                                         const int max_daily_fish, const double* __restrict__ pareto,
                                                         const ScanDev S, const int n_days, const int n_species) {
   __shared__ unsigned int s_bid;
+  __shared__ GroupCursor s_cur;
   __shared__ long long s_w[COUNT_T / 32][3];
   __shared__ long long s_pre[3];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_bid = atomicAdd(reinterpret_cast<unsigned int*>(O.err + ERR_TICKET), 1u);
+  if (threadIdx.x == 0) {
+    s_bid = atomicAdd(reinterpret_cast<unsigned int*>(O.err + ERR_TICKET), 1u);
+    if (P.groups != nullptr) s_cur = group_cursor(P, (int64_t)s_bid * COUNT_T);      // the group of the block's first cell
+  }
   __syncthreads();
   const unsigned int bid = s_bid;      // thread blocks take their cells in ticket order: a block only ever waits for started ones
   const int64_t c = (int64_t)bid * COUNT_T + threadIdx.x;
   const bool in = c < P.n_cells;
   int species_c = 0, day_c = 0, n_c = 0;
   if (in) {
-  const CellInfo ci = cell_info(P, c);
+  const CellInfo ci = cell_at(P, s_cur, c);
   species_c = ci.species; day_c = ci.day;
   if (species_c < 0 || species_c >= n_species || day_c < 0 || day_c >= n_days) {      // (validated here, not on the host)
     atomicMax(O.err, ERRBIT_RANGE | (unsigned long long)(c & 0xFFFFFFFFll));
@@ -238,8 +260,8 @@ __global__ void __launch_bounds__(COUNT_T) count_kernel(const KParams P, const d
   const uint32_t wmask = P.out.rows ? __ballot_sync(0xffffffffu, n_c > P.out.narrow_max) : 0u;
   const int slots_w = P.out.rows ? __popc(mask) + __popc(wmask) : 0;
   uint32_t info = 0;
-  if (O.blk_S) info = pool_block(in, n_c, species_c, day_c);
-  long long t = O.blk_S ? (long long)(n_c >> 5) + (lane == 0 ? (long long)(info & 0x7fffffffu) : 0ll) : (long long)((n_c + 31) >> 5);
+  if (O.blk_S) info = pool_block(in, n_c, species_c, day_c, P.pool_all);
+  long long t = O.blk_S ? (long long)pool_full(n_c, P.pool_all) + (lane == 0 ? (long long)(info & 0x7fffffffu) : 0ll) : (long long)((n_c + 31) >> 5);
   long long f = n_c;
   const long long t_own = t, f_own = f;
 #pragma unroll
@@ -254,51 +276,31 @@ __global__ void __launch_bounds__(COUNT_T) count_kernel(const KParams P, const d
     long long a[3] = {0, 0, 0};
 #pragma unroll
     for (int q = 0; q < COUNT_T / 32; ++q) { a[0] += s_w[q][0]; a[1] += s_w[q][1]; a[2] += s_w[q][2]; }
-    const unsigned int E = S.epoch * 4u;
-    volatile unsigned int* flag = S.flag;
-    volatile long long* agg = S.agg;
-    volatile long long* incl = S.incl;
     long long run[3] = {0, 0, 0};
     if (bid == 0) {
       run[2] = O.slot0 >= 0 ? O.slot0 : (long long)O.err[ERR_SLOTS];      // slots continue after the previous range of cells
-      if (lane == 0) {
-        incl[0] = a[0]; incl[1] = a[1]; incl[2] = a[2] + run[2];
-        __threadfence();
-        flag[0] = E + 2u;
-      }
+      if (lane == 0) scan_store(S.status, scan_pack(2u, a[0], a[1], a[2] + run[2]));
     } else {
-      if (lane == 0) {
-        agg[3 * (size_t)bid] = a[0]; agg[3 * (size_t)bid + 1] = a[1]; agg[3 * (size_t)bid + 2] = a[2];
-        __threadfence();
-        flag[bid] = E + 1u;
-      }
+      if (lane == 0) scan_store(S.status + bid, scan_pack(1u, a[0], a[1], a[2]));
       long long look = (long long)bid - 1;
       for (;;) {
         const long long idx = look - lane;
-        unsigned int fl = E + 2u;                                // before the first block: an inclusive prefix of zero
-        if (idx >= 0) { do { fl = flag[idx]; } while (fl != E + 1u && fl != E + 2u); }
-        __threadfence();
-        const uint32_t im = __ballot_sync(0xffffffffu, fl == E + 2u);
+        uint4 v = make_uint4(2u, 0u, 0u, 0u);                   // before the first block: an inclusive prefix of zero
+        if (idx >= 0) { do { v = scan_load(S.status + idx); } while ((v.x & 3u) == 0u); }
+        const uint32_t im = __ballot_sync(0xffffffffu, (v.x & 3u) == 2u);
         const int first = __ffs(im) - 1;                         // nearest block that already knows its inclusive prefix
-        long long v[3] = {0, 0, 0};
-        if (idx >= 0 && (first < 0 || lane <= first)) {
-          volatile long long* src = (first >= 0 && lane == first) ? incl : agg;
-          v[0] = src[3 * (size_t)idx]; v[1] = src[3 * (size_t)idx + 1]; v[2] = src[3 * (size_t)idx + 2];
-        }
+        long long q[3] = {0, 0, 0};
+        if (first < 0 || lane <= first) scan_unpack(v, q[0], q[1], q[2]);
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int j = 0; j < 3; ++j) {
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
-          run[q] += v[q];
+          for (int o = 16; o > 0; o >>= 1) q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
+          run[j] += q[j];
         }
         if (first >= 0) break;
         look -= 32;
       }
-      if (lane == 0) {
-        incl[3 * (size_t)bid] = run[0] + a[0]; incl[3 * (size_t)bid + 1] = run[1] + a[1]; incl[3 * (size_t)bid + 2] = run[2] + a[2];
-        __threadfence();
-        flag[bid] = E + 2u;
-      }
+      if (lane == 0) scan_store(S.status + bid, scan_pack(2u, run[0] + a[0], run[1] + a[1], run[2] + a[2]));
     }
     if (lane == 0) {
       s_pre[0] = run[0]; s_pre[1] = run[1]; s_pre[2] = run[2];

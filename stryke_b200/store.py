@@ -3,16 +3,25 @@
 The reference writes ``<proj_dir>/<output_name>.h5`` through ``pandas.HDFStore`` (PyTables).  When PyTables is
 importable this module uses exactly that (same keys, table format, ``min_itemsize``).  PyTables / libhdf5 are absent
 from this image, so otherwise a same-keys container is written next to where the ``.h5`` would be:
-``<output_name>.h5.store/`` holding one pickled DataFrame per key plus ``manifest.json``.  The API below is the
-subset of ``HDFStore`` that ``run()``, ``summary()`` and downstream readers use (``[]``, ``put``, ``append``,
-``keys``, ``in``, context manager)."""
+``<output_name>.h5.store/`` holding, per key, a directory of Parquet parts (``pyarrow``; one part per ``put`` / ``append``,
+so appending never rewrites what is already there) plus ``manifest.json`` — a non-executable, documented format that
+anything reading Arrow / Parquet opens, and a loud log line says that no ``.h5`` was produced.  Nothing here unpickles:
+opening a project directory somebody else wrote cannot run code.  ``python -m stryke_b200.store <project>.h5 <target.h5>``
+converts such a store to a real ``HDFStore`` file where PyTables exists (the web app's host).  The API below is the subset
+of ``HDFStore`` that ``run()``, ``summary()`` and downstream readers use (``[]``, ``put``, ``append``, ``keys``, ``in``,
+context manager)."""
 from __future__ import annotations
 
 import json
+import logging
 import os
 import shutil
 
+import numpy as np
 import pandas as pd
+
+logger = logging.getLogger(__name__)
+_WARNED = set()
 
 
 def pytables_available():
@@ -23,8 +32,45 @@ def pytables_available():
         return False
 
 
+def _encode_mixed(df):
+    """Object columns that Arrow cannot type (numbers and strings in one column, as in the reference's ``Flow`` column:
+    'hydrograph' or a discharge) are stored cell by cell as JSON text; returns (frame to write, names of such columns)."""
+    import pyarrow as pa
+    mixed = []
+    out = df
+    for c in df.columns:
+        col = df[c]
+        if col.dtype != object:
+            continue
+        try:
+            pa.array(col.to_numpy(), from_pandas=True)
+        except (pa.ArrowInvalid, pa.ArrowTypeError):
+            mixed.append(c)
+    if mixed:
+        out = df.copy()
+        for c in mixed:
+            out[c] = [json.dumps(_plain(v)) for v in df[c]]
+    return out, mixed
+
+
+def _plain(v):
+    if v is None or (isinstance(v, float) and np.isnan(v)):
+        return None
+    if isinstance(v, (np.integer,)):
+        return int(v)
+    if isinstance(v, (np.floating,)):
+        return float(v)
+    if isinstance(v, (np.bool_,)):
+        return bool(v)
+    if isinstance(v, (str, int, float, bool)):
+        return v
+    return str(v)
+
+
 class FrameStore:
-    """Directory-backed stand-in for ``pd.HDFStore`` (keys are stored with a leading '/')."""
+    """Directory-backed stand-in for ``pd.HDFStore`` (keys are stored with a leading '/'): Parquet parts per key."""
+
+    FORMAT = "stryke_b200.framestore/2 (parquet parts)"
 
     def __init__(self, path, mode="a"):
         self.h5_path = str(path)
@@ -36,35 +82,52 @@ class FrameStore:
             raise FileNotFoundError(f"no result store at {self.dir}")
         os.makedirs(self.dir, exist_ok=True)
         self._manifest_path = os.path.join(self.dir, "manifest.json")
-        self._manifest = {}
+        self._manifest = {"format": self.FORMAT, "keys": {}}
         if os.path.isfile(self._manifest_path):
             with open(self._manifest_path) as fh:
-                self._manifest = json.load(fh)
-        self._pending = {}
+                m = json.load(fh)
+            if m.get("format") != self.FORMAT:
+                raise RuntimeError(f"{self.dir}: unknown store format {m.get('format')!r} (written by another version; "
+                                   "stores are never unpickled — re-run the project)")
+            self._manifest = m
+        if mode != "r" and self.h5_path not in _WARNED:
+            _WARNED.add(self.h5_path)
+            logger.warning("PyTables is not installed: results go to %s (Parquet parts per HDF key), NOT to %s; convert with "
+                           "`python -m stryke_b200.store %s <target.h5>` where PyTables exists", self.dir, self.h5_path, self.h5_path)
 
     @staticmethod
     def _norm(key):
         return "/" + str(key).strip("/")
 
-    def _file(self, key):
+    def _dir(self, key):
         safe = self._norm(key).strip("/").replace("/", "__").replace(" ", "_")
-        return os.path.join(self.dir, safe + ".pkl")
+        return os.path.join(self.dir, safe)
 
     def keys(self):
-        return sorted(set(self._manifest) | set(self._pending))
+        return sorted(self._manifest["keys"])
 
     def __contains__(self, key):
-        return self._norm(key) in self._manifest or self._norm(key) in self._pending
+        return self._norm(key) in self._manifest["keys"]
 
     def __getitem__(self, key):
         k = self._norm(key)
-        parts = []
-        if k in self._manifest:
-            parts.append(pd.read_pickle(self._file(k)))
-        parts += self._pending.get(k, [])
-        if not parts:
+        rec = self._manifest["keys"].get(k)
+        if rec is None:
             raise KeyError(f"No object named {key} in the file")
-        return parts[0] if len(parts) == 1 else pd.concat(parts, ignore_index=True)
+        parts = [self._read_part(os.path.join(self._dir(k), f"part-{i:05d}.parquet"), rec) for i in range(rec["parts"])]
+        df = parts[0] if len(parts) == 1 else pd.concat(parts, ignore_index=rec.get("range_index", True))
+        return df
+
+    @staticmethod
+    def _read_part(path, rec):
+        df = pd.read_parquet(path)
+        for c in rec.get("json_columns", []):
+            df[c] = pd.Series([json.loads(v) if v is not None else None for v in df[c]], index=df.index, dtype=object)
+            df[c] = df[c].where(df[c].notna(), np.nan)
+        for c in rec.get("object_columns", []):          # keep what the writer had as plain object columns
+            if c in df.columns and df[c].dtype != object:
+                df[c] = df[c].astype(object)
+        return df
 
     def get(self, key):
         return self[key]
@@ -72,32 +135,44 @@ class FrameStore:
     def __setitem__(self, key, df):
         self.put(key, df)
 
-    def put(self, key, df, **kwargs):
-        k = self._norm(key)
-        self._pending.pop(k, None)
-        df.to_pickle(self._file(k))
-        self._manifest[k] = {"rows": int(len(df)), "columns": [str(c) for c in df.columns]}
+    def _write_part(self, k, df, fresh):
+        d = self._dir(k)
+        if fresh and os.path.isdir(d):
+            shutil.rmtree(d)
+        os.makedirs(d, exist_ok=True)
+        rec = self._manifest["keys"].get(k) if not fresh else None
+        if rec is None:
+            rec = {"parts": 0, "rows": 0, "columns": [str(c) for c in df.columns], "json_columns": [], "object_columns": [],
+                   "range_index": isinstance(df.index, pd.RangeIndex)}
+        out, mixed = _encode_mixed(df)
+        rec["json_columns"] = sorted(set(rec["json_columns"]) | set(str(c) for c in mixed))
+        rec["object_columns"] = sorted(set(rec["object_columns"]) | {str(c) for c in df.columns if df[c].dtype == object and c not in mixed})
+        out.columns = [str(c) for c in out.columns]
+        out.to_parquet(os.path.join(d, f"part-{rec['parts']:05d}.parquet"), engine="pyarrow",
+                       index=None if not isinstance(df.index, pd.RangeIndex) else False)
+        rec["parts"] += 1
+        rec["rows"] += int(len(df))
+        self._manifest["keys"][k] = rec
         self._write_manifest()
+
+    def put(self, key, df, **kwargs):
+        self._write_part(self._norm(key), df, fresh=True)
 
     def append(self, key, df, **kwargs):
-        self._pending.setdefault(self._norm(key), []).append(df)
+        """A new Parquet part; what is already stored is not touched."""
+        self._write_part(self._norm(key), df, fresh=False)
 
     def flush(self, *a, **k):
-        for k_, parts in list(self._pending.items()):
-            base = [pd.read_pickle(self._file(k_))] if k_ in self._manifest else []
-            df = pd.concat(base + parts, ignore_index=True) if (base or len(parts) > 1) else parts[0]
-            df.to_pickle(self._file(k_))
-            self._manifest[k_] = {"rows": int(len(df)), "columns": [str(c) for c in df.columns]}
-        self._pending = {}
-        self._write_manifest()
+        pass
 
     def _write_manifest(self):
-        with open(self._manifest_path, "w") as fh:
+        tmp = self._manifest_path + ".tmp"
+        with open(tmp, "w") as fh:
             json.dump(self._manifest, fh, indent=1)
+        os.replace(tmp, self._manifest_path)
 
     def close(self):
-        if self.mode != "r":
-            self.flush()
+        pass
 
     def __enter__(self):
         return self

@@ -28,7 +28,8 @@ def test_reference_arm_line():
     assert d["value"] > 0 and d["higher_is_better"] is True and d["steps"] == 1 and d["vs_baseline"] is None
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    have_ref = os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "Stryke", "stryke.py"))
+    assert cb["kind"] == ("reference" if have_ref else "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
