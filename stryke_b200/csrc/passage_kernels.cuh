@@ -286,7 +286,11 @@ __global__ void __launch_bounds__(COUNT_T) count_kernel(const KParams P, const d
       for (;;) {
         const long long idx = look - lane;
         uint4 v = make_uint4(2u, 0u, 0u, 0u);                   // before the first block: an inclusive prefix of zero
-        if (idx >= 0) { do { v = scan_load(S.status + idx); } while ((v.x & 3u) == 0u); }
+        if (idx >= 0) {      // spin on the state word (a volatile 32-bit load), then take the whole 16-byte word in one load
+          const volatile unsigned int* st = reinterpret_cast<const volatile unsigned int*>(S.status + idx);
+          while ((*st & 3u) == 0u) { }
+          v = scan_load(S.status + idx);
+        }
         const uint32_t im = __ballot_sync(0xffffffffu, (v.x & 3u) == 2u);
         const int first = __ffs(im) - 1;                         // nearest block that already knows its inclusive prefix
         long long q[3] = {0, 0, 0};
