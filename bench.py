@@ -44,8 +44,8 @@ def workload_project(name, n_fish, iterations, days):
     if name == "c3":
         return W.c3_population(n_species=20, iterations=iterations, days=days, curr_Q=9000.0, scenarios=SCENARIOS5,
                                facility_scenario_column=False)
-    if name == "c4":
-        return W.c4_barotrauma(n_fish=n_fish, iterations=iterations, days=days, curr_Q=9000.0)
+    if name == "c4":      # BASELINE.json configs[3] as named: propeller / pump station, friction-loss pressures
+        return W.c4_barotrauma(n_fish=n_fish, iterations=iterations, days=days, curr_Q=9000.0, pump=True, friction=True)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -58,7 +58,7 @@ def describe(name, n_fish, iterations, days, world):
     return {"c2": f"C2: 3-unit Kaplan+Kaplan+Francis facility, bypass+spill, 9 nodes, 6 moves; {n_fish} fish/iteration x "
                   f"{iterations} iterations x {days} day(s) {per}",
             "c5": f"C5: 5-dam cascade, 40 nodes, 22 moves; {n_fish} fish x {iterations} iterations x {days} day(s) {per}",
-            "c4": f"C4: 6-unit propeller / Francis station with the Pflugrath barotrauma response, 11 nodes, 6 moves; {n_fish} "
+            "c4": f"C4: 6-unit propeller / pump station, Pflugrath barotrauma response with friction-loss pressures, 12 nodes, 6 moves; {n_fish} "
                   f"fish x {iterations} iterations x {days} day(s) {per}",
             "c3": f"C3: population mode, 20 species x {days} days x {iterations} iterations x 5 flow scenarios {per}, "
                   "EPRI-fitted entrainment"}[name]

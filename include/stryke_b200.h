@@ -75,7 +75,10 @@ typedef struct StrykeFacility {
  * unit_coef[d][u][.]: 0 lambda, 1 N, 2 D,
  *    Kaplan:              3 pi*ada*Ewd, 4 2*Qwd, 5 8*Qwd          (strike = lambda*(N*L/D)*(cos a/(8Qwd) + sin a/(pi rR)), a = atan(c3/(c4*rR)))
  *    Propeller/Francis/Pump: 3 X  with p_strike = lambda*(N*L/D)*X (Pump: lambda slot holds gamma, D slot holds 0.707*D2)
- *    6 = 1 if the unit has flow today (Q > 0), 7 reserved                                                          */
+ *    6 = 1 if the unit has flow today (Q > 0)
+ *    7 = barotrauma, friction-loss pressure mode: the day's offset c0 of P1/P2 = c0 + c1 * fish_depth_ft, with
+ *        c1 = rho g 0.3048 / P2 and P2 = atm + rho g 0.3048 * unit_static[3] (Darcy-Weisbach head loss of the unit's discharge,
+ *        Stryke/barotrauma.py:43-137 composed as Stryke/stryke_barotrauma.py:565-601); 0 = hydrostatic pressures (stryke.py:1496-1503) */
 typedef struct StrykeDayTables {
   int32_t n_days;
   const double*  curr_Q;     /* [n_days]                                                                  */

@@ -42,7 +42,7 @@ __host__ __device__ inline uint32_t pack_node(int kind, int hasU, int unit, int 
 }
 
 struct FastSmem {
-  int nodes, ustatic, uc1, species, warp0, warp_stride, cdf, dst, ucoef, total;
+  int nodes, ustatic, uc1, species, warp0, warp_stride, cdf, dst, ucoef, uc0, total;
   int pool_blk, pool_ef, pool_rank, pool_seg, pool_sd, pool_full;   // per-warp scratch of the pooled-remainder path (pool_nw > 0)
   int pool_field;                                  // per block: where every (pair, arrivals | survivors) / Daily counter sits
 };
@@ -61,6 +61,7 @@ __host__ __device__ constexpr FastSmem fast_smem(int n_nodes, int n_units, int s
   int w = 0;
   L.cdf = w; w = (w + n_nodes * cdf_row(stride) * 4 + 15) & ~15;
   L.ucoef = w; w = (w + n_units * 16 + 15) & ~15;
+  L.uc0 = w; w = (w + n_units * 4 + 15) & ~15;                // barotrauma: P1/P2 offset of the day (friction-loss mode) or of the unit
   L.dst = w; w = (w + n_nodes * stride * 4 + 15) & ~15;     // int32 entries: no sub-word register packing in the hot loop
   if (pool_nw > 0) {
     L.pool_blk = w; w += 32 * 16;                            // uint4 per cell of the block: n, cell id (lo, hi), remainder offset
@@ -142,6 +143,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   unsigned char* wbase = smem + SL.warp0 + wid * SL.warp_stride;
   float* s_cdf = reinterpret_cast<float*>(wbase + SL.cdf);              // [n_nodes][cdf_row(stride)], padded with 2.0
   float4* s_ucoef = reinterpret_cast<float4*>(wbase + SL.ucoef);        // fa, fb, fc, has_flow
+  float* s_uc0 = reinterpret_cast<float*>(wbase + SL.uc0);              // c0: P1/P2 = c0 + c1 * depth
   int* s_dst = reinterpret_cast<int*>(wbase + SL.dst);                  // [n_nodes][stride], padded with the node itself
 
   for (int i = threadIdx.x; i < n_nodes; i += BLOCK) s_nodes[i] = g_nodes[i];
@@ -273,6 +275,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         // linear runners use the Kaplan formula with fa = 0, fb = 1, rR = 1, inv = 1:  p = fc * L
         s_ucoef[u] = make_float4(kap ? (float)(r[3] / r[4]) : 0.f, kap ? (float)(1.0 / r[5]) : 1.f,
                                  kap ? (float)lnd : (float)(lnd * r[3]), (float)r[6]);
+        if (BARO) s_uc0[u] = r[7] != 0.0 ? (float)r[7] : s_ustatic[u].w;      // friction-loss mode: the day's offset
       }
       __syncwarp();
     }
@@ -359,7 +362,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         float baro = 1.f;
         if (BARO) {
           const float depth = us.z * fmaf(sp_dd, u_dep, sp_d1);
-          const float ratio = fmaf(s_uc1[unit], depth, us.w);
+          const float ratio = fmaf(s_uc1[unit], depth, s_uc0[unit]);
           const float e = ex2_approx(fmaf(sp_b1, lg2_approx(ratio), sp_b0));
           baro = blocked ? 1.f : rcp_approx(1.f + e);
         }

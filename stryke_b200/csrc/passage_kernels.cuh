@@ -11,7 +11,7 @@ __device__ __forceinline__ double sub_(double a, double b) { return __dsub_rn(a,
 __device__ __forceinline__ double div_(double a, double b) { return __ddiv_rn(a, b); }
 
 template <typename Real> struct UCW;
-template <> struct UCW<float> { static constexpr int W = 4; };    // folded: fa, fb, fc|fl, has_flow
+template <> struct UCW<float> { static constexpr int W = 5; };    // folded: fa, fb, fc|fl, has_flow, c0 of the day (0 = hydrostatic)
 template <> struct UCW<double> { static constexpr int W = 8; };   // raw unit_coef row
 
 // ---- blade strike + barotrauma, fp64 validation flavour (operation order of stryke.py:907-922, :1492-1510) --------
@@ -47,6 +47,12 @@ __device__ __forceinline__ float strike_surv32(int kind, const float* uc, float 
   }
   p = uc[3] > 0.f ? p : INFINITY;   // no flow through the unit: p_strike = inf in the reference (Appendix E10)
   return __saturatef(1.f - p);
+}
+// friction-loss pressure mode (unit_coef slot 7 != 0): P1/P2 = c0 + c1 * depth with the day's c0 from the host (Darcy-Weisbach
+// head loss of the unit's discharge, Stryke/barotrauma.py:43-137) and c1 = rho g 0.3048 / P2 of the unit
+__device__ __forceinline__ double baro_surv64_ratio(double ratio, double b0, double b1) {
+  const double e = exp(add_(b0, mul_(b1, log(ratio))));
+  return sub_(1.0, div_(e, add_(1.0, e)));
 }
 __device__ __forceinline__ float baro_surv32(float depth_ft, float c0, float c1, float b0l2e, float b1) {
   const float ratio = fmaf(c1, depth_ft, c0);                 // P1/P2
@@ -475,10 +481,11 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
             const double lnd = r[0] * r[1] / r[2];
             // a Kaplan row keeps pi*ada*Ewd, 2*Qwd, 8*Qwd; other runners keep X in slot 3 (slot 4 is 0)
             const bool kap = r[4] != 0.0 || r[5] != 0.0;
-            s_ucoef[u * 4 + 0] = kap ? (Real)(r[3] / r[4]) : (Real)0;
-            s_ucoef[u * 4 + 1] = kap ? (Real)(1.0 / r[5]) : (Real)0;
-            s_ucoef[u * 4 + 2] = kap ? (Real)lnd : (Real)(lnd * r[3]);
-            s_ucoef[u * 4 + 3] = (Real)r[6];
+            s_ucoef[u * 5 + 0] = kap ? (Real)(r[3] / r[4]) : (Real)0;
+            s_ucoef[u * 5 + 1] = kap ? (Real)(1.0 / r[5]) : (Real)0;
+            s_ucoef[u * 5 + 2] = kap ? (Real)lnd : (Real)(lnd * r[3]);
+            s_ucoef[u * 5 + 3] = (Real)r[6];
+            s_ucoef[u * 5 + 4] = (Real)r[7];
           }
         }
         __syncwarp();
@@ -561,11 +568,13 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
               if (sizeof(Real) == 8) {
                 const double fb = (double)us[2], lo = mul_(fb, (double)sp_d1), hi = mul_(fb, (double)sp_d2);
                 const double ud = INJECT ? P.inj.depth[(int64_t)k * NF + gi] : wide ? rng.wide(wide_slot(k, 1)) : (double)u13_depth<Real>(w_rc, w_dice);
-                baro = (Real)baro_surv64(add_(lo, mul_(sub_(hi, lo), ud)), (double)us[3], (double)sp_b0, (double)sp_b1);
+                const double dep = add_(lo, mul_(sub_(hi, lo), ud));
+                if ((double)uc[7] != 0.0) baro = (Real)baro_surv64_ratio((double)uc[7] + (double)us[5] * dep, (double)sp_b0, (double)sp_b1);
+                else baro = (Real)baro_surv64(dep, (double)us[3], (double)sp_b0, (double)sp_b1);
               } else {
                 const float ud = INJECT ? (float)P.inj.depth[(int64_t)k * NF + gi] : (float)u13_depth<Real>(w_rc, w_dice);
                 const float depth = (float)us[2] * fmaf((float)sp_d2 - (float)sp_d1, ud, (float)sp_d1);
-                baro = (Real)baro_surv32(depth, (float)us[4], (float)us[5], (float)sp_b0 * 1.44269504f, (float)sp_b1);
+                baro = (Real)baro_surv32(depth, (float)uc[4] != 0.f ? (float)uc[4] : (float)us[4], (float)us[5], (float)sp_b0 * 1.44269504f, (float)sp_b1);
               }
               baro_t = baro;
             }
@@ -610,7 +619,10 @@ __global__ void __launch_bounds__(BLOCK) passage_kernel(const KParams P, const i
           else strike = (double)strike_surv32(nd.kind, (const float*)uc, (float)L, (float)rR);
           if (P.barotrauma) {
             const double fb = (double)us[2], lo = mul_(fb, (double)sp_d1), hi = mul_(fb, (double)sp_d2);
-            baro = baro_surv64(add_(lo, mul_(sub_(hi, lo), P.inj.ghost_depth[gk])), (double)us[3], (double)sp_b0, (double)sp_b1);
+            const double dep = add_(lo, mul_(sub_(hi, lo), P.inj.ghost_depth[gk]));
+            const double c0d = sizeof(Real) == 8 ? (double)uc[7] : (double)uc[4];
+            baro = c0d != 0.0 ? baro_surv64_ratio(c0d + (double)us[5] * dep, (double)sp_b0, (double)sp_b1)
+                              : baro_surv64(dep, (double)us[3], (double)sp_b0, (double)sp_b1);
           }
         }
         const double* cu = P.inj.ghost_cause + ((int64_t)k * 4) * P.n_cells + c;

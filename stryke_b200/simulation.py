@@ -103,6 +103,9 @@ class simulation:
     precision = 32
     #: Philox4x32-10 key of the native RNG
     seed = 0x5EED
+    #: barotrauma pressures: "hydrostatic" (what the reference's run() does, stryke.py:1496-1503) or "friction" (the
+    #: Darcy-Weisbach penstock head loss of Stryke/barotrauma.py composed as in Stryke/stryke_barotrauma.py:565-601; opt-in)
+    barotrauma_pressure = "hydrostatic"
     #: CUDA ordinal; inside a torch.distributed job (one process per GPU) the default is the process's LOCAL_RANK
     device = 0
 

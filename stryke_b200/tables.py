@@ -220,7 +220,8 @@ def build_facility(sim, ctx: RunContext) -> FacilityTables:
             node_unit[i] = unit_idx[n]
     for u in ctx.units:   # stryke.py:2749-2787 builds no param_dict for other runner types (Appendix E8)
         rt = sim.unit_params.at[u, "Runner Type"]
-        if u in idx and kind[idx[u]] and rt not in ("Kaplan", "Propeller", "Francis"):
+        pump_ok = rt == "Pump" and _has(sim.unit_params.loc[u], "Q_p") and _has(sim.unit_params.loc[u], "gamma")      # opt-in, see unit_coefficients
+        if u in idx and kind[idx[u]] and rt not in ("Kaplan", "Propeller", "Francis") and not pump_ok:
             raise KeyError(u)
     has_U = np.array([1 if "U" in n else 0 for n in names], np.uint8)
 
@@ -255,8 +256,8 @@ def build_facility(sim, ctx: RunContext) -> FacilityTables:
         if baro:
             ustat[j, 2] = float(up.at[u, "fb_depth"])
             tail = up.at[u, "elevation_head"] if "elevation_head" in up.columns else None
-            if _isnan(tail) and "submergence_depth" in up.columns:
-                tail = up.at[u, "submergence_depth"]
+            if (_isnan(tail) or getattr(sim, "barotrauma_pressure", "hydrostatic") == "friction") and "submergence_depth" in up.columns:
+                tail = up.at[u, "submergence_depth"]      # (friction-loss mode: P2 = atm + rho g h_D, h_D the draft-tube submergence)
             if _isnan(tail):
                 raise ValueError(f"Barotrauma requires elevation_head or submergence_depth for route {u}.")
             ustat[j, 3] = float(tail)
@@ -297,6 +298,41 @@ def finalize_levels(fac: FacilityTables, days: "DayTables"):
     return fac
 
 
+def _has(row, col):
+    return col in row.index and not _isnan(row[col])
+
+
+RHO, G_SI, P_ATM = 998.2, 9.80665, 101325.0      # stryke.py:1471-1473 (scipy.constants.g, atm)
+
+
+def friction_pressure_offset(row, Q):
+    """Friction-loss pressure mode (opt-in, ``simulation.barotrauma_pressure = "friction"``): the day's offset c0 of
+    P1 / P2 = c0 + c1 * fish_depth_ft for one unit.  Restates the composition of Stryke/stryke_barotrauma.py:565-601 over
+    the helpers of Stryke/barotrauma.py:11-137 (the reference does not wire it into run()): imperial inputs are converted
+    to SI, v = Q / A in the penstock, Darcy-Weisbach head loss with the friction factor of ``calc_friction``,
+    P2 = atm + rho g h_D (h_D = submergence_depth), P1 = P2 + rho g (h_fish - h_2) + rho g h_loss (h_2 = elevation_head,
+    0 when empty; the velocity heads cancel, v_1 = v_2).  So c1 = rho g 0.3048 / P2 and c0 = 1 + rho g (h_loss - h_2) / P2."""
+    for c in ("ps_D", "ps_length", "roughness", "submergence_depth"):
+        if not _has(row, c):
+            raise ValueError(f"Friction-loss barotrauma pressure requires {c} for unit {row.name}.")
+    ps_d = float(row["ps_D"]) * 0.3048
+    ps_l = float(row["ps_length"]) * 0.3048
+    a = np.pi * (float(row["ps_D"]) / 2.0) ** 2 * 0.092903
+    q = float(Q) * 0.02831683199881
+    h_D = float(row["submergence_depth"]) * 0.3048
+    h_2 = (float(row["elevation_head"]) if _has(row, "elevation_head") else 0.0) * 0.3048
+    v = np.float64(q / a)
+    k_v = 0.0010016 / RHO
+    with np.errstate(divide="ignore", invalid="ignore"):
+        Re = np.float64(v * ps_d / k_v)          # (NumPy scalars: a unit without flow gives Re = 0 -> f = 0, no exception)
+        f = 0.25 / (np.log((float(row["roughness"]) / ps_d) / (3.7 * ps_d) + (5.74 / Re ** 0.9))) ** 2
+    h_loss = f * (ps_l / ps_d) * ((v * v) / (2 * G_SI))
+    if not np.isfinite(h_loss):
+        h_loss = 0.0
+    p2 = P_ATM + RHO * G_SI * h_D
+    return 1.0 + RHO * G_SI * (h_loss - h_2) / p2
+
+
 def unit_coefficients(row, Q):
     """Per-(day, unit) coefficient row (layout: include/stryke_b200.h).  The day's flow ``Q`` is the all-units
     allocation (stryke.py:2977); formulas follow Kaplan/Propeller/Francis (stryke.py:907-918, :993-1006, :1078-1091)."""
@@ -328,9 +364,19 @@ def unit_coefficients(row, Q):
                               + (np.pi * 0.707 ** 2) / (2 * Qwd) * (B / D1) * (D2 / D1) ** 2
                               - 4 * 0.707 * np.tan(beta) * (B / D1) * (D1 / D2))
             out[3] = (np.sin(alpha) * (B / D1)) / (2 * Qwd) + np.cos(alpha) / np.pi
+        elif rt == "Pump" and _has(row, "Q_p") and _has(row, "gamma"):
+            # opt-in: the reference's Pump formula (stryke.py:1096-1127) needs Q_p and gamma, which no sheet of the reference
+            # carries — its run() stops with KeyError at a Pump node (:2749-2787, :2977).  With both columns present the node
+            # runs: p = gamma * (N L / (0.707 D2)) * (sin(beta_p) (B / D1) / (2 Qpwd) + cos(beta_p) / pi); the pumped
+            # discharge Q_p, not the day's allocation, enters.
+            B, D1, D2 = float(row["B"]), float(row["D1"]), float(row["D2"])
+            Qpwd = float(row["Q_p"]) / (omega * D ** 3)
+            beta_p = np.arctan((0.707 * np.pi / 8) / (Qpwd * np.power(D1 / D2, 3)))
+            out[0], out[2], out[6] = float(row["gamma"]), 0.707 * D2, 1.0
+            out[3] = ((np.sin(beta_p) * (B / D1)) / (2 * Qpwd)) + (np.cos(beta_p) / np.pi)
         else:
             raise KeyError(rt)
-    if rt != "Kaplan" and not np.isfinite(out[3]):
+    if rt not in ("Kaplan", "Pump") and not np.isfinite(out[3]):
         out[3] = np.inf      # reference: ZeroDivisionError for a fish at a unit with no flow (Appendix E10)
     return out
 
@@ -354,6 +400,9 @@ def build_days(sim, ctx: RunContext, fac: FacilityTables, day_list):
             Q = ctx.q_dict(Qd, scenario)
             alloc = ctx.allocations(Q)
             c_coef = np.stack([unit_coefficients(rows[j], alloc[u]) for j, u in enumerate(fac.unit_names)]) if U else np.zeros((0, _abi.UNIT_COEF_W))
+            if U and fac.barotrauma and getattr(sim, "barotrauma_pressure", "hydrostatic") == "friction":
+                for j, u in enumerate(fac.unit_names):
+                    c_coef[j, 7] = friction_pressure_offset(rows[j], alloc[u])
             c_cdf, c_flow, c_stay = np.ones(E), np.zeros(E), np.zeros(Nn, np.uint8)
             for i, n in enumerate(fac.node_names):
                 lo, hi = fac.edge_off[i], fac.edge_off[i + 1]

@@ -188,24 +188,32 @@ def c3_population(n_species=4, iterations=2, days=5, curr_Q=9000.0, scenarios=("
     return prj
 
 
-def c4_barotrauma(n_fish=1000, iterations=1, days=1, curr_Q=9000.0, habitat="Pelagic"):
-    """6-unit propeller station with barotrauma columns populated (Pump is unreachable
-    from ``run()`` in the reference — SURVEY.md Appendix E8 — so the run-path fixture is all Propeller/Francis)."""
+PUMP = dict(**{"Runner Type": "Pump"}, intake_vel=2.0, H=60.0, RPM=97.3, D=10.76, ada=0.94, N=13, Qopt=2150.72, Qcap=2288.0,
+            B=4.0, iota=1.1, D1=11.22, D2=10.76, Q_p=1800.0, gamma=0.153)
+
+
+def c4_barotrauma(n_fish=1000, iterations=1, days=1, curr_Q=9000.0, habitat="Pelagic", pump=False, friction=False):
+    """6-unit station with barotrauma columns populated.  Default: 4 Propeller + 2 Francis units and
+    hydrostatic pressures — what the reference's ``run()`` can do (a Pump node stops it with KeyError, Appendix E8).
+    ``pump=True``: BASELINE.json's C4 as named, 3 Propeller + 3 Pump units (``Q_p``, ``gamma`` columns: opt-in Pump runner);
+    ``friction=True``: the friction-loss pressure mode (``barotrauma_pressure = "friction"``)."""
     names = [f"U{i}" for i in range(1, 7)]
+    kind_of = (lambda i: "Propeller" if i < 3 else "Pump") if pump else (lambda i: "Propeller" if i < 4 else "Francis")
+    runner_of = (lambda i: PROPELLER if i < 3 else PUMP) if pump else (lambda i: PROPELLER if i < 4 else FRANCIS)
     nodes = ([("river_node_0", "a priori", 1.0), ("forebay", "a priori", 1.0)]
-             + [(u, "Propeller" if i < 4 else "Francis", 0.0) for i, u in enumerate(names)]
+             + [(u, kind_of(i), 0.0) for i, u in enumerate(names)]
              + [("bypass_flow", "a priori", 0.98), ("spillway", "a priori", 0.97), ("tailrace", "a priori", 1.0),
                 ("river_node_1", "a priori", 1.0)])
     mid = names + ["bypass_flow", "spillway"]
     edges = ([("river_node_0", "forebay", 1.0)] + [("forebay", x, 1.0) for x in mid]
              + [(x, "tailrace", 1.0) for x in mid] + [("tailrace", "river_node_1", 1.0)])
-    units = [_unit_row("Sta", i + 1, u, i + 1, PROPELLER if i < 4 else FRANCIS, baro=True,
-                       fb_depth=30.0 + 2 * i, submergence_depth=6.0 if i % 2 == 0 else NAN,
+    units = [_unit_row("Sta", i + 1, u, i + 1, runner_of(i), baro=True,
+                       fb_depth=30.0 + 2 * i, submergence_depth=6.0 if (i % 2 == 0 or friction) else NAN,
                        elevation_head=NAN if i % 2 == 0 else 4.0 + i)
              for i, u in enumerate(names)]
     species = dict(SHAD, vertical_habitat=habitat)
     return dict(
-        name="c4", output_units="imperial", max_river_node=1,
+        name="c4", output_units="imperial", max_river_node=1, barotrauma_pressure="friction" if friction else "hydrostatic",
         nodes=[dict(Location=a, Surv_Fun=b, Survival=c) for a, b, c in nodes],
         edges=[dict(_from=a, _to=b, weight=w) for a, b, w in edges],
         unit_params=units,
@@ -375,6 +383,8 @@ def apply_to(sim, prj, proj_dir="/tmp/stryke_b200_project", output_name="project
     sim.operating_scenarios_df = pd.DataFrame(prj["operating_scenarios"])
     sim.input_hydrograph_df = pd.DataFrame(prj["hydrograph"])
     sim.pop = pd.DataFrame(prj["population"])
+    if prj.get("barotrauma_pressure", "hydrostatic") != "hydrostatic":      # (our class only; the reference has no such switch)
+        sim.barotrauma_pressure = prj["barotrauma_pressure"]
     return sim
 
 

@@ -20,6 +20,7 @@ CASES = {
     "c2": ("c2_facility", dict(n_fish=1_000_000, iterations=1000, days=10)),
     "c2_baro": ("c2_facility", dict(n_fish=1_000_000, iterations=1000, days=10, baro=True)),
     "c4": ("c4_barotrauma", dict(n_fish=1_000_000, iterations=1000, days=10)),
+    "c4_pump_friction": ("c4_barotrauma", dict(n_fish=1_000_000, iterations=1000, days=10, pump=True, friction=True)),
     "c5": ("c5_cascade", dict(n_fish=1_000_000, iterations=1000, days=10)),
 }
 

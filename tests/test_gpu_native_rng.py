@@ -71,6 +71,7 @@ def compare_cells(plan, res, ref, ref_idx):
                                         ("c2_facility", dict(n_fish=300000, iterations=1, days=2, baro=True)),
                                         ("c5_cascade", dict(n_fish=150000, iterations=1, days=2)),
                                         ("c4_barotrauma", dict(n_fish=200000, iterations=1, days=2)),
+                                        ("c4_barotrauma", dict(n_fish=200000, iterations=1, days=3, pump=True, friction=True)),
                                         ("cabot_station", dict(iterations=1, days=2, seed=3, median_Q=7000.0, fish=200000.0)),
                                         ("c2_facility", dict(n_fish=300000, iterations=1, days=2, length_normal=(40.0, 9.0))),
                                         ("random_facility", dict(seed=3, n_fish=150000, days=3)),
@@ -320,6 +321,7 @@ def test_full_size_conservation_properties(fixture, kw):
                                         ("c2_facility", dict(n_fish=50000, iterations=2, days=3, curr_Q=600.0)),
                                         ("c5_cascade", dict(n_fish=100000, iterations=2, days=2)),
                                         ("c4_barotrauma", dict(n_fish=100000, iterations=2, days=2, habitat="Benthic")),
+                                        ("c4_barotrauma", dict(n_fish=100000, iterations=2, days=3, pump=True, friction=True)),
                                         ("c1_single_unit", dict(iterations=50, days=40, fish=3000.0)),
                                         ("c3_population", dict(n_species=4, iterations=60, days=10)),
                                         ("c3_population", dict(n_species=2, iterations=80, days=8, extreme=True)),

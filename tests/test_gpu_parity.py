@@ -110,6 +110,10 @@ def test_fp32_injected_tallies_statistically_identical(case):
     ("c2_facility", dict(n_fish=100000, iterations=1, days=2, baro=True)),
     ("c5_cascade", dict(n_fish=60000, iterations=1, days=2)),
     ("c4_barotrauma", dict(n_fish=50000, iterations=2, days=1, habitat="Benthic")),
+    # BASELINE.json configs[3] as named: 3 Propeller + 3 Pump units (opt-in Pump runner, Q_p / gamma columns) and the
+    # friction-loss pressure mode; the oracle composes Stryke/barotrauma.py's calc_* helpers as stryke_barotrauma.py:565-601
+    ("c4_barotrauma", dict(n_fish=40000, iterations=1, days=3, pump=True, friction=True)),
+    ("c4_barotrauma", dict(n_fish=40000, iterations=1, days=2, pump=True, habitat="Benthic")),
     ("cabot_station", dict(iterations=1, days=3, seed=5, median_Q=6000.0, fish=30000.0)),
     ("c5_cascade", dict(n_fish=8000, iterations=1, days=2, dams=9)),
 ] + [("random_facility", dict(seed=s, n_fish=15000, days=4, baro=bool(s % 2))) for s in range(10)])
@@ -144,6 +148,12 @@ def test_large_cells_oracle_draws_bit_exact(fixture, kw):
         s = slice(off[c], off[c + 1])
         assert np.array_equal(res.trace.state[:, s], ora.states)
         assert np.array_equal(res.trace.survival[:, s], ora.survival)
+        # per-fish probabilities where both sides evaluated them (strike: Kaplan / Propeller / Francis / Pump; barotrauma:
+        # hydrostatic or friction-loss pressures): 1e-6 relative, the fp64 tolerance of BASELINE.json
+        for dev, ref in ((res.trace.strike[:, s], ora.strike), (res.trace.baro[:, s], ora.baro)):
+            both = np.isfinite(dev) & np.isfinite(ref)
+            assert both.sum() == np.isfinite(ref).sum()
+            np.testing.assert_allclose(dev[both], ref[both], rtol=1e-6, atol=1e-12)
 
 
 def test_strike_known_answer_vectors():
