@@ -52,7 +52,8 @@ extern "C" {
 #define STRYKE_UNIT_STATIC_W 4   /* rack_spacing_ft, intake_vel, fb_depth_ft, tail_depth_ft */
 #define STRYKE_UNIT_COEF_W   8   /* see StrykeDayTables.unit_coef */
 #define STRYKE_SPECIES_W    20   /* see StrykeSpeciesTable.params */
-#define STRYKE_DAILY_W       5   /* num_entrained, num_survived, mortality_impingement, _blade_strike, _barotrauma */
+#define STRYKE_DAILY_W       5
+#define STRYKE_RANGE_ALIGN 1024   /* ranges of cells of plan_launch_compact start at multiples of this */   /* num_entrained, num_survived, mortality_impingement, _blade_strike, _barotrauma */
 
 /* Static description of the facility DAG (reference: create_route stryke.py:1581-1655, Nodes/Edges/Unit tables). */
 typedef struct StrykeFacility {
@@ -230,7 +231,7 @@ int stryke_b200_plan_create(const StrykeFacility* fac, const StrykeDayTables* da
 int stryke_b200_plan_launch(StrykePlan* plan, int32_t* d_cell_n, uint32_t* d_daily, uint32_t* d_state_daily,
                             void* stream);
 /* Same hot path with compact rows (see StrykeCompact), for cells [cell_lo, cell_hi) of the plan (cell_lo a multiple of
- * 256; cell_hi = -1: to the end).  d_rows holds rows_cap slots; the per-block tables live in the plan
+ * STRYKE_RANGE_ALIGN; cell_hi = -1: to the end).  d_rows holds rows_cap slots; the per-block tables live in the plan
  * (stryke_b200_plan_compact_tables).  Slots continue from the previous range when first_slot < 0, else start at first_slot.
  * A range that starts at cell 0 starts a new pass: the status words (error, fish and slot totals) start over.
  * d_slots_after (device, may be NULL) receives the slot count after this range — what a caller that overlaps the copy of one

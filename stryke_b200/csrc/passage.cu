@@ -334,7 +334,7 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
     CK(upload(pl->cell_species, c->cell_species, (size_t)c->n_cells));
     CK(upload(pl->cell_id, c->cell_id, (size_t)c->n_cells));
   }
-  const size_t NB = (size_t)((c->n_cells + 31) / 32), NCB = (size_t)((c->n_cells + COUNT_T - 1) / COUNT_T);
+  const size_t NB = (size_t)((c->n_cells + 31) / 32), NCB = (size_t)((c->n_cells + COUNT_CELLS - 1) / COUNT_CELLS);
   CK(pl->blk_row.alloc((NB + 1) * sizeof(uint32_t)));
   CK(pl->blk_mask.alloc((NB + 1) * sizeof(uint32_t)));
   CK(pl->blk_wide.alloc((NB + 1) * sizeof(uint32_t)));
@@ -663,7 +663,7 @@ static int launch_cells(StrykePlan* pl, int64_t c_lo, int64_t c_hi, int32_t* d_c
   O.err = err;
   O.slot0 = compact && first_slot >= 0 ? (long long)first_slot : -1ll;
   O.slots_after = d_slots_after;
-  const int cb = (int)((nC + COUNT_T - 1) / COUNT_T);
+  const int cb = (int)((nC + COUNT_CELLS - 1) / COUNT_CELLS);
   ScanDev S{pl->scan_status.as<uint4>()};
   CK(cudaMemsetAsync(S.status, 0, (size_t)cb * sizeof(uint4), st));      // look-back states: empty
   if (pl->inject) count_kernel<true><<<cb, COUNT_T, 0, st>>>(K, pl->day_Q.as<double>(), O, pl->max_daily_fish, pl->pareto.as<double>(), S, pl->n_days, pl->n_species);
@@ -695,8 +695,8 @@ int stryke_b200_plan_launch_compact(StrykePlan* pl, int64_t cell_lo, int64_t cel
                                     int64_t rows_cap, int64_t first_slot, uint64_t* d_slots_after, void* stream) {
   if (!pl || !d_cell_n || !d_rows) return fail(STRYKE_E_ARG, "null argument");
   if (cell_hi < 0) cell_hi = pl->n_cells;
-  if (cell_lo < 0 || cell_lo > cell_hi || cell_hi > pl->n_cells || (cell_lo % COUNT_T) != 0)
-    return fail(STRYKE_E_ARG, "cell range must lie inside the plan and start at a multiple of 256");
+  if (cell_lo < 0 || cell_lo > cell_hi || cell_hi > pl->n_cells || (cell_lo % COUNT_CELLS) != 0)
+    return fail(STRYKE_E_ARG, "cell range must lie inside the plan and start at a multiple of 1024 (STRYKE_RANGE_ALIGN)");
   if (pl->inject || pl->has_trace) return fail(STRYKE_E_ARG, "compact rows are for native-RNG tally runs (no injected draws, no trace)");
   if (rows_cap < 0) return fail(STRYKE_E_ARG, "negative rows_cap");
   return launch_cells(pl, cell_lo, cell_hi, d_cell_n, nullptr, nullptr, d_rows, rows_cap, first_slot, (cudaStream_t)stream,
@@ -866,8 +866,8 @@ int stryke_b200_run_compact(const StrykeFacility* f, const StrykeDayTables* d, c
   CK(dn.alloc((size_t)C * 4));
   CK(dr.alloc((size_t)std::max<int64_t>(out->rows_cap, 1) * row_bytes));
   int n_slabs = out->n_slabs > 0 ? out->n_slabs : (C >= (1 << 20) ? 8 : C >= (1 << 16) ? 2 : 1);
-  int64_t per = ((C + n_slabs - 1) / n_slabs + COUNT_T - 1) / COUNT_T * COUNT_T;
-  if (per < COUNT_T) per = COUNT_T;
+  int64_t per = ((C + n_slabs - 1) / n_slabs + COUNT_CELLS - 1) / COUNT_CELLS * COUNT_CELLS;
+  if (per < COUNT_CELLS) per = COUNT_CELLS;
   n_slabs = (int)((C + per - 1) / per);
   cudaStream_t comp = nullptr, copy = nullptr;
   CK(cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking));

@@ -561,15 +561,59 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   const uint32_t below = (2u << lane) - 1u;           // bits 0 .. lane
   int64_t b = -1, b_begin = 0, b_end = 0;             // current block and its tile range
   int S_b = 0, nrem = 0;                              // its shared tiles, its cells with a remainder
+  uint32_t cur_rmask = 0;                             // bit j: cell j of the block has pooled fish
   bool pool_dirty = false;
   auto pool_flush = [&]() {                           // accumulators of block b -> global tallies
     if (pool_dirty) {
       pool_dirty = false;
       __syncwarp();
-      const bool compact = P.out.rows != nullptr;
-      uint32_t bm = 0, bw = 0;
-      unsigned int slot0 = 0;
-      if (compact) { bm = P.out.blk_mask[b]; bw = P.out.blk_wide[b]; slot0 = P.out.blk_row[b]; }
+      if (P.out.rows != nullptr) {
+        // compact rows, transposed: lane <-> cell of the block.  Every lane unpacks the packed fields of ITS cell's
+        // accumulator words (word and shift of every pair are compile-time constants of the facility) into the row's 16-bit
+        // pairs and adds them to its own row; cells above narrow_max take the 32-bit layout.
+        const uint32_t bm = P.out.blk_mask[b], bw = P.out.blk_wide[b];
+        const uint32_t lower = (1u << lane) - 1u;
+        const unsigned int slot = P.out.blk_row[b] + __popc(bm & lower) + __popc(bw & lower);
+        const bool wide = (bw >> lane) & 1u;
+        if (((cur_rmask >> lane) & 1u) && slot + (wide ? 2u : 1u) <= P.out.cap) {
+          uint32_t A[TP::NW > 0 ? TP::NW : 1];
+#pragma unroll
+          for (int q = 0; q < TP::NW; ++q) A[q] = s_acc[lane * TP::NW + q];
+          uint32_t* row = P.out.rows + (size_t)slot * P.out.row_w;
+          uint32_t dv[STRYKE_DAILY_W];
+#pragma unroll
+          for (int j = 0; j < STRYKE_DAILY_W; ++j) {
+            const uint32_t cf = TP::daily_cfg(j);
+            dv[j] = ((cf >> 11) & 1u) ? ((A[cf & 31u] >> ((cf >> 5) & 31u)) & (((cf >> 10) & 1u) ? 1023u : 63u)) : 0u;
+          }
+          if (!wide) {
+            const uint32_t w1 = dv[0] | (dv[1] << 16), w2 = dv[2] | (dv[3] << 16);
+            if (w1) atomicAdd(row + 1, w1);
+            if (w2) atomicAdd(row + 2, w2);
+            if (dv[4]) atomicAdd(row, dv[4] << 16);
+#pragma unroll
+            for (int p = 0; p < (TP::kStatic ? TP::N_PAIRS : 0); ++p) {
+              const uint32_t cf = TP::lane_cfg(p);
+              if (!((cf >> 20) & 1u)) continue;
+              const uint32_t cnt = (A[cf & 31u] >> ((cf >> 5) & 31u)) & 63u, suc = (A[(cf >> 10) & 31u] >> ((cf >> 15) & 31u)) & 63u;
+              const uint32_t v = suc | (cnt << 16);
+              if (v) atomicAdd(row + 3 + p, v);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < STRYKE_DAILY_W; ++j)
+              if (dv[j]) atomicAdd(row + 1 + j, dv[j]);
+#pragma unroll
+            for (int p = 0; p < (TP::kStatic ? TP::N_PAIRS : 0); ++p) {
+              const uint32_t cf = TP::lane_cfg(p);
+              if (!((cf >> 20) & 1u)) continue;
+              const uint32_t cnt = (A[cf & 31u] >> ((cf >> 5) & 31u)) & 63u, suc = (A[(cf >> 10) & 31u] >> ((cf >> 15) & 31u)) & 63u;
+              if (suc) atomicAdd(row + 6 + 2 * p, suc);
+              if (cnt) atomicAdd(row + 7 + 2 * p, cnt);
+            }
+          }
+        }
+      } else {
       for (int i0 = 0; i0 < NI; i0 += 32) {           // lane <-> counter i0 + lane, loop over the cells with a remainder
         const int i = i0 + lane;
         const uint32_t cf = i < NI ? s_field[i] : 0u;
@@ -577,39 +621,16 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         const uint32_t sh = (cf >> 5) & 31u;
         const uint32_t mask = ((cf >> 11) & 1u) ? (((cf >> 10) & 1u) ? 1023u : 63u) : 0u;
         const bool state = i < 2 * n_pairs;
-        if (!compact) {
-          uint32_t* base = state ? P.state_daily + i : P.daily + (i - 2 * n_pairs);
-          const uint32_t per_cell = state ? (uint32_t)(2 * n_pairs) : (uint32_t)STRYKE_DAILY_W;
-          base += (size_t)(b << 5) * per_cell;
-          for (int rho = 0; rho < nrem; ++rho) {
-            const int jl = s_rank[rho];
-            const uint32_t v = (s_acc[jl * TP::NW + wq] >> sh) & mask;
-            STRYKE_BCHK(P, (b << 5) + jl < P.n_cells, 12);
-            if (v) atomicAdd(base + (uint32_t)jl * per_cell, v);
-          }
-        } else {
-          // compact rows: counters 2p (successes) / 2p + 1 (count) of a narrow cell share one word, as do the Daily columns
-          const int dj = i - 2 * n_pairs;
-          const int wide_idx = state ? 6 + i : 1 + dj;
-          const int narrow_idx = state ? 3 + (i >> 1) : (dj == 0 ? 1 : dj == 2 ? 2 : 0);
-          for (int rho = 0; rho < nrem; ++rho) {
-            const int jl = s_rank[rho];
-            const uint32_t v = (s_acc[jl * TP::NW + wq] >> sh) & mask;
-            const uint32_t up = __shfl_down_sync(0xffffffffu, v, 1);
-            const uint32_t bl = (1u << jl) - 1u;
-            const unsigned int slot = slot0 + __popc(bm & bl) + __popc(bw & bl);
-            const bool wide = (bw >> jl) & 1u;
-            uint32_t* row = P.out.rows + (size_t)slot * P.out.row_w;
-            if (slot + (wide ? 2u : 1u) <= P.out.cap && i < NI) {
-              if (wide) {
-                if (v) atomicAdd(row + wide_idx, v);
-              } else if (!(i & 1)) {
-                const uint32_t w2 = (!state && dj == 4) ? (v << 16) : (v | (up << 16));
-                if (w2) atomicAdd(row + narrow_idx, w2);
-              }
-            }
-          }
+        uint32_t* base = state ? P.state_daily + i : P.daily + (i - 2 * n_pairs);
+        const uint32_t per_cell = state ? (uint32_t)(2 * n_pairs) : (uint32_t)STRYKE_DAILY_W;
+        base += (size_t)(b << 5) * per_cell;
+        for (int rho = 0; rho < nrem; ++rho) {
+          const int jl = s_rank[rho];
+          const uint32_t v = (s_acc[jl * TP::NW + wq] >> sh) & mask;
+          STRYKE_BCHK(P, (b << 5) + jl < P.n_cells, 12);
+          if (v) atomicAdd(base + (uint32_t)jl * per_cell, v);
         }
+      }
       }
       __syncwarp();
 #pragma unroll
@@ -685,6 +706,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
         }
         const uint32_t rmask = __ballot_sync(0xffffffffu, r > 0);      // cells with pooled fish
         nrem = __popc(rmask);
+        cur_rmask = rmask;
         __syncwarp();
         s_blk[lane] = make_uint4((uint32_t)n, (uint32_t)id, (uint32_t)(id >> 32), (uint32_t)(sr - pr));
         s_ef[lane] = sf - f;

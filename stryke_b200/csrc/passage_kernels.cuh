@@ -131,7 +131,7 @@ __global__ void pareto_constants_kernel(const double* __restrict__ species, int 
 // single-pass scan with decoupled look-back over the thread blocks), the per-block tables of the pooled remainders and of
 // the compact rows, and the zeroed rows themselves.  One launch instead of count + three scan kernels + memsets.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int COUNT_T = 256;
+constexpr int COUNT_T = 256, COUNT_K = 4, COUNT_CELLS = COUNT_T * COUNT_K;      // threads, blocks of 32 cells per warp, cells per thread block
 // plan status words.  ERR_WORD: 0 = fine; top bits 11 = bounds check (debug build), 101 = cell_day / cell_species out of
 // range, 100 = non-finite or negative count (low 32 bits: cell); else count << 32 | cell of a cell above max_daily_fish.
 // ERR_WORK (chunk counter of the throughput kernels) and ERR_TICKET are cleared before every launch; ERR_SLOTS carries the
@@ -173,6 +173,9 @@ struct CountOut {
   unsigned long long* slots_after;    // optional: receives the slot count after this launch's cells
 };
 
+// One thread block = COUNT_CELLS consecutive cells: every warp takes COUNT_K aligned blocks of 32 cells, one after the
+// other (phase 1: draw the counts, add up the warp's tiles / fish / slots), then ONE look-back per thread block, then the
+// outputs that need the prefix (phase 2).  Four blocks per warp amortise the barrier and the look-back latency.
 template <bool INJECT>
 __global__ void __launch_bounds__(COUNT_T) count_kernel(const KParams P, const double* __restrict__ day_Q, const CountOut O,
                                                         const int max_daily_fish, const double* __restrict__ pareto,
@@ -181,14 +184,23 @@ __global__ void __launch_bounds__(COUNT_T) count_kernel(const KParams P, const d
   __shared__ GroupCursor s_cur;
   __shared__ long long s_w[COUNT_T / 32][3];
   __shared__ long long s_pre[3];
+  __shared__ int s_n[COUNT_CELLS];
+  __shared__ uint32_t s_info[COUNT_CELLS / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     s_bid = atomicAdd(reinterpret_cast<unsigned int*>(O.err + ERR_TICKET), 1u);
-    if (P.groups != nullptr) s_cur = group_cursor(P, (int64_t)s_bid * COUNT_T);      // the group of the block's first cell
+    if (P.groups != nullptr) s_cur = group_cursor(P, (int64_t)s_bid * COUNT_CELLS);      // the group of the block's first cell
   }
   __syncthreads();
   const unsigned int bid = s_bid;      // thread blocks take their cells in ticket order: a block only ever waits for started ones
-  const int64_t c = (int64_t)bid * COUNT_T + threadIdx.x;
+  const int64_t cta0 = (int64_t)bid * COUNT_CELLS;
+  const uint32_t below = (1u << lane) - 1u;
+  // ---- phase 1 ---------------------------------------------------------------------------------------------------------
+  long long tw = 0, fw = 0, sw = 0;       // this warp's tiles, fish, row slots
+#pragma unroll 1
+  for (int k = 0; k < COUNT_K; ++k) {
+  const int lc = (wid * COUNT_K + k) * 32 + lane;        // cell within the thread block
+  const int64_t c = cta0 + lc;
   const bool in = c < P.n_cells;
   int species_c = 0, day_c = 0, n_c = 0;
   if (in) {
@@ -260,22 +272,19 @@ __global__ void __launch_bounds__(COUNT_T) count_kernel(const KParams P, const d
   }
   O.cell_n[c] = (int32_t)n_c;
   }
-  // ---- per aligned block of 32 cells (= this warp): pooled-remainder tiles, row slots, prefix sums over the lanes -------
-  const uint32_t below = (1u << lane) - 1u;
+  s_n[lc] = n_c;
   const uint32_t mask = __ballot_sync(0xffffffffu, n_c > 0);
   const uint32_t wmask = P.out.rows ? __ballot_sync(0xffffffffu, n_c > P.out.narrow_max) : 0u;
-  const int slots_w = P.out.rows ? __popc(mask) + __popc(wmask) : 0;
   uint32_t info = 0;
   if (O.blk_S) info = pool_block(in, n_c, species_c, day_c, P.pool_all);
-  long long t = O.blk_S ? (long long)pool_full(n_c, P.pool_all) + (lane == 0 ? (long long)(info & 0x7fffffffu) : 0ll) : (long long)((n_c + 31) >> 5);
+  if (lane == 0) s_info[lc >> 5] = info;
+  long long t = O.blk_S ? (long long)pool_full(n_c, P.pool_all) : (long long)((n_c + 31) >> 5);
   long long f = n_c;
-  const long long t_own = t, f_own = f;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const long long ta = __shfl_up_sync(0xffffffffu, t, o), fa = __shfl_up_sync(0xffffffffu, f, o);
-    if (lane >= o) { t += ta; f += fa; }
+  for (int o = 16; o > 0; o >>= 1) { t += __shfl_xor_sync(0xffffffffu, t, o); f += __shfl_xor_sync(0xffffffffu, f, o); }
+  tw += t + (long long)(info & 0x7fffffffu); fw += f; sw += P.out.rows ? __popc(mask) + __popc(wmask) : 0;
   }
-  if (lane == 31) { s_w[wid][0] = t; s_w[wid][1] = f; s_w[wid][2] = slots_w; }
+  if (lane == 0) { s_w[wid][0] = tw; s_w[wid][1] = fw; s_w[wid][2] = sw; }
   __syncthreads();
   // ---- decoupled look-back over the thread blocks (warp 0) -----------------------------------------------------------
   if (wid == 0) {
@@ -327,31 +336,51 @@ __global__ void __launch_bounds__(COUNT_T) count_kernel(const KParams P, const d
     }
   }
   __syncthreads();
+  // ---- phase 2: outputs ---------------------------------------------------------------------------------------------------
   long long bt = s_pre[0], bf = s_pre[1], bs = s_pre[2];
   for (int q = 0; q < wid; ++q) { bt += s_w[q][0]; bf += s_w[q][1]; bs += s_w[q][2]; }
-  // ---- outputs --------------------------------------------------------------------------------------------------------
-  const int64_t blk = c >> 5;
-  const bool blk_in = (c & ~31ll) < P.n_cells;
-  if (in) {
-    if (O.tile_off) O.tile_off[c] = bt + t - t_own;
-    if (O.fish_off) O.fish_off[c] = bf + f - f_own;
-  }
-  if (blk_in && lane == 0) {
-    if (O.blk_S) O.blk_S[blk] = info;
-    if (O.blk_tile) O.blk_tile[blk] = bt;
-  }
-  if (P.out.rows && blk_in) {
-    if (lane == 0) { P.out.blk_row[blk] = (uint32_t)bs; P.out.blk_mask[blk] = mask; P.out.blk_wide[blk] = wmask; }
-    const unsigned long long w0 = (unsigned long long)bs * (unsigned long long)P.out.row_w;
-    const unsigned long long cap_w = (unsigned long long)P.out.cap * (unsigned long long)P.out.row_w;
-    const int nw = slots_w * P.out.row_w;
-    for (int i = lane; i < nw; i += 32)
-      if (w0 + i < cap_w) P.out.rows[w0 + i] = 0u;
-    __syncwarp();
-    if (n_c > 0) {
-      const unsigned long long slot = (unsigned long long)bs + __popc(mask & below) + __popc(wmask & below);
-      if (slot + ((wmask >> lane) & 1u) < (unsigned long long)P.out.cap) P.out.rows[slot * P.out.row_w] = (uint32_t)n_c;
+#pragma unroll 1
+  for (int k = 0; k < COUNT_K; ++k) {
+    const int lc = (wid * COUNT_K + k) * 32 + lane;
+    const int64_t c = cta0 + lc;
+    const bool in = c < P.n_cells;
+    const bool blk_in = (c & ~31ll) < P.n_cells;
+    const int64_t blk = c >> 5;
+    const int n_c = s_n[lc];
+    const uint32_t info = s_info[lc >> 5];
+    const uint32_t mask = __ballot_sync(0xffffffffu, n_c > 0);
+    const uint32_t wmask = P.out.rows ? __ballot_sync(0xffffffffu, n_c > P.out.narrow_max) : 0u;
+    const int slots_w = P.out.rows ? __popc(mask) + __popc(wmask) : 0;
+    long long t = O.blk_S ? (long long)pool_full(n_c, P.pool_all) + (lane == 0 ? (long long)(info & 0x7fffffffu) : 0ll) : (long long)((n_c + 31) >> 5);
+    long long f = n_c;
+    const long long t_own = t, f_own = f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long ta = __shfl_up_sync(0xffffffffu, t, o), fa = __shfl_up_sync(0xffffffffu, f, o);
+      if (lane >= o) { t += ta; f += fa; }
     }
+    if (in) {
+      if (O.tile_off) O.tile_off[c] = bt + t - t_own;
+      if (O.fish_off) O.fish_off[c] = bf + f - f_own;
+    }
+    if (blk_in && lane == 0) {
+      if (O.blk_S) O.blk_S[blk] = info;
+      if (O.blk_tile) O.blk_tile[blk] = bt;
+    }
+    if (P.out.rows && blk_in) {
+      if (lane == 0) { P.out.blk_row[blk] = (uint32_t)bs; P.out.blk_mask[blk] = mask; P.out.blk_wide[blk] = wmask; }
+      const unsigned long long w0 = (unsigned long long)bs * (unsigned long long)P.out.row_w;
+      const unsigned long long cap_w = (unsigned long long)P.out.cap * (unsigned long long)P.out.row_w;
+      const int nw = slots_w * P.out.row_w;
+      for (int i = lane; i < nw; i += 32)
+        if (w0 + i < cap_w) P.out.rows[w0 + i] = 0u;
+      __syncwarp();
+      if (n_c > 0) {
+        const unsigned long long slot = (unsigned long long)bs + __popc(mask & below) + __popc(wmask & below);
+        if (slot + ((wmask >> lane) & 1u) < (unsigned long long)P.out.cap) P.out.rows[slot * P.out.row_w] = (uint32_t)n_c;
+      }
+    }
+    bt += __shfl_sync(0xffffffffu, t, 31); bf += __shfl_sync(0xffffffffu, f, 31); bs += slots_w;
   }
 }
 

@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import numpy as np
 
+ALIGN = 1024      # ranges of cells start at multiples of this (include/stryke_b200.h STRYKE_RANGE_ALIGN)
 HDR = 16          # int32 words at the head of a rank's flat buffer: [0:2) slots used (int64), [2] status code, [3] n_cells
 
 
@@ -126,8 +127,8 @@ class ShardedRun:
         self.plan = engine.Plan(fac, days, species, grid, None, None, device=device, precision=precision, seed=seed,
                                 max_daily_fish=max_daily_fish, kernel_variant=kernel_variant)
         n_max = int(n_cells_max if n_cells_max is not None else self.n_cells)
-        if slab_cells is None:           # ~8 slabs on large lists, whole multiples of 256 cells
-            slab_cells = max(256, -(-max(n_max, 1) // 8 // 256) * 256) if n_max >= (1 << 18) else max(256, -(-max(n_max, 1) // 256) * 256)
+        if slab_cells is None:           # ~8 slabs on large lists, whole multiples of ALIGN cells
+            slab_cells = max(ALIGN, -(-max(n_max, 1) // 8 // ALIGN) * ALIGN) if n_max >= (1 << 18) else max(ALIGN, -(-max(n_max, 1) // ALIGN) * ALIGN)
         if slab_cap is None:
             est = expected_slots(grid, np.asarray(species).reshape(-1, 20))
             slab_cap = max(1024, int(est / max(1, -(-n_max // slab_cells)) * 1.25) + 2048)
@@ -291,7 +292,7 @@ def run_sharded(plan_host, rank, world, device, *, precision=32, seed=0, max_dai
     cap_scale = 1.0
     while True:
         est = max(expected_slots(g, species) for g in grids)
-        slab_cells = max(256, -(-max(n_max, 1) // (8 if n_max >= (1 << 18) else 1) // 256) * 256)
+        slab_cells = max(ALIGN, -(-max(n_max, 1) // (8 if n_max >= (1 << 18) else 1) // ALIGN) * ALIGN)
         n_slabs = max(1, -(-n_max // slab_cells))
         run = ShardedRun(plan_host.fac, plan_host.days, species, mine, rank, world, device, precision=precision, seed=seed,
                          max_daily_fish=max_daily_fish, slab_cells=slab_cells,

@@ -509,7 +509,8 @@ def assemble_frames(sim, plan: RunPlan, tallies):
     (scenario -> species -> iteration -> day; stryke.py:3256-3383, :3433-3502).  Columns are gathered as arrays over all
     groups and every frame is built once; the label columns (species, scenario, season, state) take their strings from a
     small table by code — object columns like the reference's for ordinary projects, categoricals above
-    STRYKE_B200_CATEGORICAL_ROWS rows (default 2e6), where one Python string per row would cost more than the simulation."""
+    STRYKE_B200_CATEGORICAL_ROWS rows (default 50 000), where one Python string per row would cost more than the simulation
+    (the result store writes them dictionary-encoded and hands them back as plain object columns)."""
     fac = plan.fac
     P = fac.n_pairs
     metric = sim.output_units == "metric"
@@ -600,7 +601,7 @@ def _labels(labels, codes):
     """Label column: ``labels[codes]`` as an object Series (what the reference writes) or, for very long frames, a
     categorical with the same values."""
     codes = np.asarray(codes)
-    if codes.shape[0] > int(os.environ.get("STRYKE_B200_CATEGORICAL_ROWS", "2000000")):
+    if codes.shape[0] > int(os.environ.get("STRYKE_B200_CATEGORICAL_ROWS", "50000")):
         cats, inv = np.unique(np.asarray(labels, dtype=object).astype(str), return_inverse=True)
         return pd.Categorical.from_codes(np.asarray(inv)[codes], categories=list(cats))
     return pd.Series(np.asarray(labels, dtype=object)[codes], dtype=object)

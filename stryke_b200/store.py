@@ -148,6 +148,9 @@ class FrameStore:
         rec["json_columns"] = sorted(set(rec["json_columns"]) | set(str(c) for c in mixed))
         rec["object_columns"] = sorted(set(rec["object_columns"]) | {str(c) for c in df.columns if df[c].dtype == object and c not in mixed})
         out.columns = [str(c) for c in out.columns]
+        # label columns handed over as categoricals (runner._labels on long frames) are dictionary-encoded as they are and
+        # come back as the plain object columns the reference writes
+        rec["object_columns"] = sorted(set(rec["object_columns"]) | {str(c) for c in df.columns if isinstance(df[c].dtype, pd.CategoricalDtype)})
         out.to_parquet(os.path.join(d, f"part-{rec['parts']:05d}.parquet"), engine="pyarrow",
                        index=None if not isinstance(df.index, pd.RangeIndex) else False)
         rec["parts"] += 1

@@ -46,7 +46,7 @@ def main():
               f"sharded == single GPU: {ok}", flush=True)
         all_ok(ok, name)
 
-    # both exchanges give the same gathered buffers, slab by slab (several slabs: 256-cell slabs on a 6 000-cell shard)
+    # both exchanges give the same gathered buffers, slab by slab (several slabs of 1024 cells on a 6 000-cell shard)
     prj = W.c3_population(n_species=4, iterations=300, days=10)
     sim, plan = W.make_plan(prj, f"mg_x_{rank}")
     grids = [plan.grid.iterations_slice(r / world, (r + 1) / world) for r in range(world)]

@@ -227,7 +227,7 @@ GLOO_WORKER = textwrap.dedent("""
     sel = np.array([pos[int(i)] for i in mine.explicit()[2]], dtype=np.int64)
     part = encode_compact(CellResult(res.cell_n[sel], res.daily[sel], res.state_daily[sel], None), narrow_max=65534)
     n_max = max(x.n_cells for x in grids)
-    L = ShardLayout(n_max, plan.fac.n_pairs, slab_cells=256 * ((n_max + 255) // 256), slab_cap=2 * n_max + 8)
+    L = ShardLayout(n_max, plan.fac.n_pairs, slab_cells=1024 * ((n_max + 1023) // 1024), slab_cap=2 * n_max + 8)
     flat = torch.from_numpy(pack_flat(L, np.stack([part.blk_row, part.blk_mask, part.blk_wide]), part.rows, 0, mine.n_cells, part.n_slots))
     gathered = gather_flat(flat, world).numpy().reshape(world, L.total)
     pieces = []

@@ -122,7 +122,7 @@ def test_plan_ranges_on_device_buffers():
     cell_n = torch.zeros(C, dtype=torch.int32, device="cuda")
     rows = torch.full((2 * C, plan.fac.n_pairs + 3), -1, dtype=torch.int32, device="cuda")
     after = torch.zeros(3, dtype=torch.int64, device="cuda")
-    cuts = [0, 256 * 3, 256 * 11, C]
+    cuts = [0, 1024 * 1, 1024 * 5, C]
     for k in range(3):
         p.launch_compact(cell_n, rows, cuts[k], cuts[k + 1], first_slot=0 if k == 0 else -1, slots_after=after[k:k + 1])
     ns, nf = p.compact_totals()
