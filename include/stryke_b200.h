@@ -154,6 +154,18 @@ typedef struct StrykeTrace {
                             * count from an earlier run with the same seed; a different count is an error              */
 } StrykeTrace;
 
+/* Peaking / pumped-storage operations (daily_hours, stryke.py:2405-2431): in every cell each unit flips a not-operating coin
+ * (uniform <= Prob_Not_Op -> 0 hours) and otherwise draws lognormal hours, exp(shape Z) scale + location clipped to
+ * [0, 24]; a cell whose units all sit idle is skipped altogether (no fish, no rows: stryke.py:3025).  Drawn on the device from
+ * the cell's Philox stream (counter word 0 = 0xFFFFFFFE - unit).  params[s][u][.] for species row s (the Operating Scenarios
+ * rows of its scenario) and unit u: 0 Prob_Not_Op, 1 shape, 2 location, 3 scale, 4 fixed hours (used when shape is NaN: a
+ * run-of-river facility next to a peaking one). */
+typedef struct StrykePeaking {
+  int32_t n_units;
+  const double* params;         /* [n_species][n_units][5]                                                          */
+  float* hours;                 /* out, HOST, [n_cells][n_units] hours operated; may be NULL                         */
+} StrykePeaking;
+
 typedef struct StrykeOpts {
   int32_t  device;              /* CUDA ordinal                                                            */
   int32_t  precision;           /* 32 or 64 (bits of the per-fish arithmetic)                               */
@@ -170,6 +182,7 @@ typedef struct StrykeOpts {
                                    sequential cause rolls (stryke.py:1545-1560) — fp64 general kernel only; the arbiter the
                                    throughput kernels are checked against at 1e10 fish (tests/test_gpu_high_power.py) */
   uint32_t flags;               /* STRYKE_FLAG_* */
+  const StrykePeaking* peaking; /* NULL = every listed cell operates (run-of-river: the host lists only days with hours) */
 } StrykeOpts;
 
 #define STRYKE_FLAG_NO_PROMOTE 1u   /* keep a drawn count of 0 (population_sim itself, stryke.py:2596-2618; run() promotes it to 1, :3032) */
@@ -255,6 +268,7 @@ int stryke_b200_plan_kernel_ms(StrykePlan* plan, double* total_ms, int32_t* n_la
 int stryke_b200_plan_set_seed(StrykePlan* plan, uint64_t seed);   /* Philox key of the next launches */
 int stryke_b200_plan_status(StrykePlan* plan, void* stream, int64_t* n_fish_total);   /* syncs the stream; reports STRYKE_E_MAX_FISH etc. */
 int stryke_b200_plan_fetch_trace(StrykePlan* plan, const StrykeTrace* host_trace, void* stream);
+int stryke_b200_plan_fetch_hours(StrykePlan* plan, float* host_hours, void* stream);   /* [n_cells][n_units] of StrykePeaking */
 int stryke_b200_plan_destroy(StrykePlan* plan);
 
 /* Per-fish probability functions on the device (Kaplan/Propeller/Francis/Pump stryke.py:846-1127 and the

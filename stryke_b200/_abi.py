@@ -72,10 +72,14 @@ class Trace(C.Structure):
                 ("strike", _p), ("baro", _p), ("n_fish", C.c_int64)]
 
 
+class Peaking(C.Structure):
+    _fields_ = [("n_units", C.c_int32), ("params", _p), ("hours", _p)]
+
+
 class Opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("precision", C.c_int32), ("seed", C.c_uint64), ("max_daily_fish", C.c_int32),
                 ("blocks_per_sm", C.c_int32), ("injected", C.POINTER(Injected)), ("trace", C.POINTER(Trace)),
-                ("kernel_variant", C.c_int32), ("rng_mode", C.c_int32), ("flags", C.c_uint32)]
+                ("kernel_variant", C.c_int32), ("rng_mode", C.c_int32), ("flags", C.c_uint32), ("peaking", C.POINTER(Peaking))]
 
 
 class Tallies(C.Structure):
@@ -122,6 +126,8 @@ def lib():
     L.stryke_b200_plan_time_kernel.argtypes = [_p, C.c_int]
     L.stryke_b200_plan_kernel_ms.argtypes = [_p, P(C.c_double), P(C.c_int32)]
     L.stryke_b200_plan_fetch_trace.argtypes = [_p, P(Trace), _p]
+    L.stryke_b200_plan_fetch_hours.argtypes = [_p, _p, _p]
+    L.stryke_b200_plan_fetch_hours.restype = C.c_int
     L.stryke_b200_plan_destroy.argtypes = [_p]
     L.stryke_b200_strike_survival.argtypes = [C.c_int, _p, C.c_int64, _p, _p, C.c_int, C.c_int, _p]
     L.stryke_b200_baro_survival.argtypes = [C.c_int64, _p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, _p]
@@ -136,7 +142,7 @@ def lib():
     return L
 
 
-EXPORTS = ["stryke_b200_run_compact", "stryke_b200_plan_launch_compact", "stryke_b200_plan_compact_tables",
+EXPORTS = ["stryke_b200_plan_fetch_hours", "stryke_b200_run_compact", "stryke_b200_plan_launch_compact", "stryke_b200_plan_compact_tables",
            "stryke_b200_plan_compact_totals", "stryke_b200_last_error", "stryke_b200_abi_version", "stryke_b200_device_count", "stryke_b200_launch_count",
            "stryke_b200_run", "stryke_b200_plan_create", "stryke_b200_plan_launch", "stryke_b200_plan_kernel", "stryke_b200_set_source_dir", "stryke_b200_jit_selftest", "stryke_b200_plan_set_seed", "stryke_b200_plan_status",
            "stryke_b200_plan_fetch_trace", "stryke_b200_plan_destroy", "stryke_b200_plan_time_kernel", "stryke_b200_plan_kernel_ms", "stryke_b200_strike_survival",

@@ -110,7 +110,8 @@ struct StrykePlan {
   int64_t n_cells = 0;
   DevBuf nodes, edge_dst, moves, pair_node, ustatic, edge_cdf, node_stay, unit_coef, day_Q, species, cell_day,
       cell_species, cell_id, tile_off, fish_off, err, blk_S, pareto;
-  DevBuf groups, active_days, blk_tile, blk_row, blk_mask, blk_wide, scan_status;
+  DevBuf groups, active_days, blk_tile, blk_row, blk_mask, blk_wide, scan_status, peak_params, peak_hours;
+  int peak_units = 0;
   int n_days = 0, n_species = 0, row_w = 0, narrow_max = 0;
   int64_t last_rows_cap = -1;  // capacity of the last compact launch (-1: dense)
   bool attr_set = false;      // cudaFuncAttributeMaxDynamicSharedMemorySize applied to this plan's passage kernel
@@ -356,6 +357,13 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
     K.id_days = c->id_days; K.id_add = c->id_add;
   }
   K.n_cells = c->n_cells;
+  if (o->peaking && o->peaking->n_units > 0 && !o->injected) {
+    if (!o->peaking->params || o->peaking->n_units > STRYKE_MAX_UNITS) return fail(STRYKE_E_ARG, "peaking: params missing or too many units");
+    pl->peak_units = o->peaking->n_units;
+    CK(upload(pl->peak_params, o->peaking->params, (size_t)s->n_species * pl->peak_units * 5));
+    CK(pl->peak_hours.alloc((size_t)std::max<int64_t>(c->n_cells, 1) * pl->peak_units * sizeof(float)));
+    K.peak_units = pl->peak_units; K.peak_params = pl->peak_params.as<double>(); K.peak_hours = pl->peak_hours.as<float>();
+  }
   K.rng_wide = o->rng_mode == 1 ? 1 : 0;
   K.flags = o->flags;
   K.out.rows = nullptr; K.out.blk_row = pl->blk_row.as<uint32_t>(); K.out.blk_mask = pl->blk_mask.as<uint32_t>();
@@ -808,6 +816,16 @@ int stryke_b200_plan_status(StrykePlan* pl, void* stream, int64_t* n_fish_total)
   return STRYKE_OK;
 }
 
+int stryke_b200_plan_fetch_hours(StrykePlan* pl, float* host_hours, void* stream) {
+  if (!pl || !host_hours) return fail(STRYKE_E_ARG, "null argument");
+  if (pl->peak_units <= 0) return fail(STRYKE_E_ARG, "plan has no peaking operations");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaSetDevice(pl->device));
+  CK(cudaMemcpyAsync(host_hours, pl->peak_hours.p, (size_t)pl->n_cells * pl->peak_units * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return STRYKE_OK;
+}
+
 int stryke_b200_plan_fetch_trace(StrykePlan* pl, const StrykeTrace* h, void* stream) {
   if (!pl || !h || !pl->has_trace) return fail(STRYKE_E_ARG, "plan has no trace");
   cudaStream_t st = (cudaStream_t)stream;
@@ -841,6 +859,7 @@ int stryke_b200_run(const StrykeFacility* f, const StrykeDayTables* d, const Str
   CK(cudaMemcpyAsync(out->state_daily, ds.p, C * P * 2 * 4, cudaMemcpyDeviceToHost, 0));
   rc = stryke_b200_plan_status(pl, nullptr, nullptr);
   if (rc) return rc;
+  if (pl->peak_units > 0 && o->peaking->hours) { rc = stryke_b200_plan_fetch_hours(pl, o->peaking->hours, nullptr); if (rc) return rc; }
   if (o->trace) return stryke_b200_plan_fetch_trace(pl, o->trace, nullptr);
   return STRYKE_OK;
 }
@@ -916,6 +935,7 @@ int stryke_b200_run_compact(const StrykeFacility* f, const StrykeDayTables* d, c
   int64_t ns = 0;
   stryke_b200_plan_compact_totals(pl, comp, &ns, nullptr);
   out->n_slots = ns; out->n_fish = nf;
+  if (!rc && pl->peak_units > 0 && o->peaking->hours) rc = stryke_b200_plan_fetch_hours(pl, o->peaking->hours, comp);
   return rc;
 }
 

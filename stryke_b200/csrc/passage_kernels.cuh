@@ -214,6 +214,30 @@ __global__ void __launch_bounds__(COUNT_T) count_kernel(const KParams P, const d
   const int kind = (int)sp[12];
   const double shape = sp[13], loc = sp[14], scale = sp[15], max_rate = sp[16], occur = sp[17];
   uint32_t w[4], v[4] = {0u, 0u, 0u, 0u};
+  bool idle = false;
+  if (!INJECT && P.peak_units > 0) {      // peaking operations (stryke.py:2405-2431): coin + clipped lognormal hours per unit
+    double tot = 0.0;
+    for (int j = 0; j < P.peak_units; ++j) {
+      const double* pp = P.peak_params + ((int64_t)species_c * P.peak_units + j) * 5;
+      double h;
+      if (isnan(pp[1])) {
+        h = pp[4];
+      } else {
+        Philox::block(0xFFFFFFFEu - (uint32_t)j, (uint32_t)ci.id, (uint32_t)(ci.id >> 32), 0u, P.seed_lo, P.seed_hi, w);
+        const double coin = ((double)w[0] + 0.5) * (1.0 / 4294967296.0);
+        if (coin <= pp[0]) {
+          h = 0.0;
+        } else {
+          const double z = sqrt(-2.0 * log(1.0 - u53(w[1], w[2]))) * cospi(2.0 * ((double)w[3] + 0.5) * (1.0 / 4294967296.0));
+          h = exp(pp[1] * z) * pp[3] + pp[2];               // scipy lognorm._rvs
+          h = h > 24.0 ? 24.0 : h < 0.0 ? 0.0 : h;
+        }
+      }
+      if (P.peak_hours) P.peak_hours[(c + P.cell_base) * P.peak_units + j] = (float)h;
+      tot += h;
+    }
+    idle = !(tot > 0.0);                                    // stryke.py:3025: nothing is drawn or written for the day
+  }
   double presence;
   if (INJECT) {
     presence = P.inj.presence[c];
@@ -224,7 +248,7 @@ __global__ void __launch_bounds__(COUNT_T) count_kernel(const KParams P, const d
     presence = u53(w[0], w[1]);
   }
   int64_t n = 0;
-  if (occur >= presence) {                                       // stryke.py:3027
+  if (!idle && occur >= presence) {                              // stryke.py:3027
     if (kind == STRYKE_ENT_FIXED) {
       n = (int64_t)sp[18];                                       // stryke.py:3029
     } else {

@@ -90,8 +90,19 @@ class CellResult:
     trace: TraceBuffers | None = None
 
 
-def _opts(device, precision, seed, max_daily_fish, blocks_per_sm, injected, trace, keep, kernel_variant=0, rng_mode=0, flags=0):
+def _opts(device, precision, seed, max_daily_fish, blocks_per_sm, injected, trace, keep, kernel_variant=0, rng_mode=0, flags=0,
+          peaking=None, n_cells=0):
+    """``peaking``: array [n_species, n_units, 5] (include/stryke_b200.h ``StrykePeaking``); the hours drawn on the device come
+    back in ``keep[-1]`` ... see ``run_cells`` / ``run_compact`` (attribute ``hours`` of their results)."""
     o = _abi.Opts()
+    if peaking is not None:
+        pk = _abi.arr(peaking, np.float64)
+        hours = np.zeros((int(n_cells), pk.shape[1]), np.float32)
+        st = _abi.Peaking()
+        st.n_units, st.params, st.hours = int(pk.shape[1]), _abi.ptr(pk), _abi.ptr(hours)
+        keep += [pk, hours, st]
+        o.peaking = C.pointer(st)
+        o._hours = hours
     o.kernel_variant, o.rng_mode, o.flags = int(kernel_variant), int(rng_mode), int(flags)
     o.device, o.precision, o.seed = int(device), int(precision), int(seed) & 0xFFFFFFFFFFFFFFFF
     o.max_daily_fish, o.blocks_per_sm = int(max_daily_fish), int(blocks_per_sm)
@@ -258,13 +269,14 @@ def _pinned(shape, dtype):
 
 
 def run_compact(fac, days, species, cells, cell_species=None, cell_id=None, *, device=0, precision=32, seed=0,
-                max_daily_fish=100000, blocks_per_sm=0, kernel_variant=0, rows_cap=None, n_slabs=0, buffers=None) -> CompactResult:
+                max_daily_fish=100000, blocks_per_sm=0, kernel_variant=0, rows_cap=None, n_slabs=0, buffers=None,
+                peaking=None) -> CompactResult:
     """One call of ``stryke_b200_run_compact``: the hot path with one tally row per cell that holds fish.  ``cells`` is a
     ``CellGrid`` or the ``cell_day`` array.  ``rows_cap`` (slots) defaults to two per cell, which always suffices; pass an
     estimate for population-mode projects (the call fails loudly and names the count it needed when it was too small)."""
     keep = []
     f, d, st, cl = _tables(fac, days, species, cells, cell_species, cell_id, keep)
-    o = _opts(device, precision, seed, max_daily_fish, blocks_per_sm, None, None, keep, kernel_variant)
+    o = _opts(device, precision, seed, max_daily_fish, blocks_per_sm, None, None, keep, kernel_variant, 0, 0, peaking, int(cl.n_cells))
     C_ = int(cl.n_cells)
     NB = (C_ + 31) // 32
     W = fac.n_pairs + 3
@@ -282,8 +294,10 @@ def run_compact(fac, days, species, cells, cell_species=None, cell_id=None, *, d
     c.rows, c.rows_cap, c.n_slabs = rows.ctypes.data_as(_abi._p), rows_cap, int(n_slabs)
     _abi.check(_abi.lib().stryke_b200_run_compact(C.byref(f), C.byref(d), C.byref(st), C.byref(cl), C.byref(o), C.byref(c)))
     ns = int(c.n_slots)
-    return CompactResult(C_, fac.n_pairs, int(c.row_w), int(c.narrow_max), ns, int(c.n_fish), blk[0, :NB], blk[1, :NB], blk[2, :NB],
-                         rows[:ns])
+    res = CompactResult(C_, fac.n_pairs, int(c.row_w), int(c.narrow_max), ns, int(c.n_fish), blk[0, :NB], blk[1, :NB], blk[2, :NB],
+                        rows[:ns])
+    res.hours = getattr(o, "_hours", None)
+    return res
 
 
 def compact_buffers(n_cells, n_pairs, rows_cap):
@@ -296,12 +310,13 @@ def compact_buffers(n_cells, n_pairs, rows_cap):
 
 def run_cells(fac, days, species, cell_day, cell_species, cell_id, *, device=0, precision=32, seed=0,
               max_daily_fish=100000, blocks_per_sm=0, injected: Injected | None = None,
-              trace: TraceBuffers | None = None, kernel_variant=0, out=None, rng_mode=0, flags=0) -> CellResult:
+              trace: TraceBuffers | None = None, kernel_variant=0, out=None, rng_mode=0, flags=0, peaking=None) -> CellResult:
     """One call of ``stryke_b200_run``: everything between the presence roll and the Daily / State_Daily tallies
     (stryke.py:3025-3366) for the listed cells, on the GPU, host buffers in and out."""
     keep = []
     f, d, st, cl = _tables(fac, days, species, cell_day, cell_species, cell_id, keep)
-    o = _opts(device, precision, seed, max_daily_fish, blocks_per_sm, injected, trace, keep, kernel_variant, rng_mode, flags)
+    o = _opts(device, precision, seed, max_daily_fish, blocks_per_sm, injected, trace, keep, kernel_variant, rng_mode, flags,
+              peaking, int(cl.n_cells))
     n = int(cl.n_cells)
     if out is not None:      # caller-owned (e.g. pinned) host buffers
         out_n, out_d, out_s = out
@@ -317,7 +332,9 @@ def run_cells(fac, days, species, cell_day, cell_species, cell_id, *, device=0, 
     t = _abi.Tallies()
     t.cell_n, t.daily, t.state_daily = _abi.ptr(out_n), _abi.ptr(out_d), _abi.ptr(out_s)
     _abi.check(_abi.lib().stryke_b200_run(C.byref(f), C.byref(d), C.byref(st), C.byref(cl), C.byref(o), C.byref(t)))
-    return CellResult(out_n, out_d, out_s, trace)
+    res = CellResult(out_n, out_d, out_s, trace)
+    res.hours = getattr(o, "_hours", None)        # peaking operations: hours per (cell, unit) drawn on the device
+    return res
 
 
 class Plan:

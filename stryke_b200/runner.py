@@ -240,37 +240,54 @@ class RunPlan:
     def _peaking_hours(self):
         """Peaking / pumped-storage plants (stryke.py:2405-2431): per (species, iteration, day) every unit flips a
         not-operating coin and draws lognormal hours clipped to [0, 24]; a cell with no operating unit is skipped
-        altogether (stryke.py:3025).  Drawn here with NumPy, vectorised over the group's cells (same distributions,
-        not the reference's draw order)."""
-        from scipy.stats import lognorm
+        altogether (stryke.py:3025).  The draws are made on the device from the cell's Philox stream (count_kernel,
+        include/stryke_b200.h ``StrykePeaking``); here only the per-(scenario, unit) parameter table is built.  A recorded
+        run is replayed by injecting its hours (``sim._injected_hours``)."""
         sim = self.sim
         given = getattr(sim, "_injected_hours", None)      # replay of a recorded run: {(scenario, species): (keys, H[I, D, units])}
+        self.peak_params, self.peak_keys = None, {}
+        tables_ = []
         for gi, g in enumerate(self.groups):
             if given is not None:
                 keys, H = given[(str(g.scenario), str(g.species))]
                 self.cell_hours[gi] = (list(keys), np.ascontiguousarray(np.transpose(np.asarray(H, dtype=float), (1, 0, 2))))
                 continue
             ops = sim.operating_scenarios_df[sim.operating_scenarios_df.Scenario == g.scenario].reset_index(drop=True)
-            keys, cols = [], []
-            D, I = g.n_active_days, g.iterations
+            keys, rows = [], []
             for fac in ops.Facility.unique():
                 fac_type = sim.facility_params.at[fac, "Operations"]
                 if isinstance(fac_type, pd.Series):
                     fac_type = fac_type.iloc[0]
                 fu = sim.unit_params[sim.unit_params.Facility == fac].sort_values(by="op_order")
-                for pos, (uname, row) in enumerate(fu.iterrows()):
+                for uname, row in fu.iterrows():
                     orow = ops[(ops.Facility == fac) & (ops.Unit == row["Unit"])]
                     if orow.empty:
                         continue
                     o = orow.iloc[0]
                     keys.append(str(uname))
                     if fac_type == "run-of-river":
-                        cols.append(np.full((D, I), float(o["Hours"])))
+                        rows.append([0.0, np.nan, 0.0, 0.0, float(o["Hours"])])
                     else:
-                        off = np.random.uniform(0, 1, (D, I)) <= float(o["Prob_Not_Op"])
-                        hrs = np.clip(lognorm.rvs(o["shape"], o["location"], o["scale"], size=(D, I)), 0.0, 24.0)
-                        cols.append(np.where(off, 0.0, hrs))
-            self.cell_hours[gi] = (keys, np.stack(cols, axis=-1) if cols else np.zeros((D, I, 0)))
+                        rows.append([float(o["Prob_Not_Op"]), float(o["shape"]), float(o["location"]), float(o["scale"]), 0.0])
+            self.peak_keys[gi] = keys
+            tables_.append((g.species_index, np.array(rows, dtype=np.float64).reshape(-1, 5)))
+        if tables_:
+            U = max(t.shape[0] for _, t in tables_)
+            pk = np.zeros((len(self.species_params), U, 5))
+            pk[:, :, 1] = np.nan                    # units a scenario does not list: fixed 0 hours
+            for si, t in tables_:
+                pk[si, :t.shape[0]] = t
+            self.peak_params = pk
+
+    def set_device_hours(self, hours):
+        """Hours per (cell, unit) drawn on the device (engine order) -> ``cell_hours`` per group, [days, iterations, units]."""
+        for gi, g in enumerate(self.groups):
+            keys = self.peak_keys.get(gi)
+            if keys is None:
+                continue
+            D, I = g.n_active_days, g.iterations
+            H = np.asarray(hours[g.cell0:g.cell0 + D * I], dtype=np.float64).reshape(D, I, -1)[:, :, :len(keys)]
+            self.cell_hours[gi] = (keys, H)
 
     @property
     def species_table(self):
@@ -320,6 +337,13 @@ def run_simulation(sim, injected=None, trace=None):
                                    device=sim.device, precision=sim.precision, seed=sim.seed, max_daily_fish=cap,
                                    injected=injected, trace=trace)
             pieces = [(plan.grid, res)]
+        elif plan.peaking and plan.peak_params is not None:
+            # peaking plants: hours per (cell, unit) are drawn on the device with the counts (small projects: one GPU, rank 0)
+            if rank != 0:
+                return None
+            cres = run_compact_retry(plan, sim.device, sim.precision, sim.seed, cap, peaking=plan.peak_params)
+            plan.set_device_hours(cres.hours)
+            pieces = [(plan.grid, cres)]
         elif world > 1:
             # one process per GPU (torchrun): every rank simulates its iterations of every group, the ranks exchange their
             # compact rows; rank 0 writes the frames (Philox is keyed by the cell, so the result does not depend on world)
@@ -424,7 +448,7 @@ def assemble_fish_tables(sim, plan: RunPlan, res: engine.CellResult, tr, rates=F
     return out
 
 
-def run_compact_retry(plan, device, precision, seed, cap):
+def run_compact_retry(plan, device, precision, seed, cap, peaking=None):
     """``engine.run_compact`` on the plan's cell grid with an estimated row capacity, once more with the exact need when the
     estimate was too small (the engine names it)."""
     import re
@@ -432,13 +456,13 @@ def run_compact_retry(plan, device, precision, seed, cap):
     rows_cap = min(2 * plan.n_cells, expected_slots(plan.grid, plan.species_table)) if plan.n_cells > 4096 else 2 * plan.n_cells
     try:
         return engine.run_compact(plan.fac, plan.days, plan.species_table, plan.grid, device=device, precision=precision, seed=seed,
-                                  max_daily_fish=cap, rows_cap=rows_cap)
+                                  max_daily_fish=cap, rows_cap=rows_cap, peaking=peaking)
     except _abi.StrykeError as exc:
         m = re.search(r"rows buffer too small: (\d+) slots needed", str(exc))
         if not m:
             raise
         return engine.run_compact(plan.fac, plan.days, plan.species_table, plan.grid, device=device, precision=precision, seed=seed,
-                                  max_daily_fish=cap, rows_cap=int(m.group(1)))
+                                  max_daily_fish=cap, rows_cap=int(m.group(1)), peaking=peaking)
 
 
 @dataclass

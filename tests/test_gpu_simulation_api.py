@@ -255,3 +255,36 @@ def test_peaking_plant_replays_the_reference_run(tmp_path):
     got_uh = {key(d): (d["hours"], d["discharge_cfs"]) for d in uh.to_dict("records")}
     assert set(got_uh) == set(want_uh)
     assert all(np.allclose(got_uh[k], want_uh[k], rtol=1e-9, atol=1e-9) for k in want_uh)
+
+
+def test_device_peaking_hours_match_the_reference_distribution():
+    """f-4: the not-operating coin and the clipped lognormal hours of ``daily_hours`` (stryke.py:2405-2431) are drawn on the
+    device (count_kernel) from the cell's Philox stream.  Against 20 000 calls of the UNMODIFIED reference's daily_hours
+    (tests/golden/peaking/hours_samples.npz, oracle/make_peaking_samples.py): binomial test of every unit's idle frequency,
+    two-sample KS of the hours of operating units, the idle-cell frequency; idle cells hold no fish."""
+    from scipy import stats
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "peaking", "hours_samples.npz"))
+    ref = g["hours"].astype(np.float64)
+    prj = fixtures.peaking_facility(n_fish=40, iterations=6000, days=4)
+    sim, plan = G.make_plan(prj, "pk_stat")
+    assert plan.peaking and plan.peak_params is not None and plan.peak_params.shape[1:] == (3, 5)
+    assert [str(k) for k in g["keys"]] == plan.peak_keys[0]
+    res = engine.run_cells(plan.fac, plan.days, plan.species_table, plan.grid, None, None, precision=32, seed=99,
+                           max_daily_fish=10 ** 6, peaking=plan.peak_params)
+    H = res.hours.astype(np.float64)
+    assert H.shape == (plan.n_cells, 3) and H.min() >= 0 and H.max() <= 24.0
+    tests = []
+    for j in range(3):
+        p_not = float(g["prob_not_op"][j])
+        tests.append(stats.binomtest(int((H[:, j] == 0).sum()), len(H), p_not).pvalue)
+        tests.append(stats.ks_2samp(H[H[:, j] > 0, j], ref[ref[:, j] > 0, j]).pvalue)
+        # and against the law itself: exp(shape Z) scale + location, clipped at 24
+        law = stats.lognorm(float(g["shape"][j]), float(g["location"][j]), float(g["scale"][j]))
+        op = H[(H[:, j] > 0) & (H[:, j] < 24.0), j]
+        tests.append(stats.kstest(op, lambda x: law.cdf(x) / law.cdf(24.0)).pvalue)
+    idle = H.sum(axis=1) == 0
+    p_idle = float(np.prod(g["prob_not_op"]))
+    tests.append(stats.binomtest(int(idle.sum()), len(H), p_idle).pvalue)
+    assert min(tests) > 0.01 / len(tests), tests
+    assert (res.cell_n[idle] == 0).all() and (res.cell_n[~idle] == 40).all()
+    assert res.state_daily[idle].sum() == 0
