@@ -154,6 +154,7 @@ struct Dims { int n_nodes, n_units, n_species_staged, start_node; };
 static std::string generate(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int stride, int pr, bool baro,
                             const TallyPlan& T, const Dims& D, bool pool);
 static const std::vector<char>* compile(const std::string& src, std::string* err, bool fresh = false);
+static void evict(const std::string& src);
 static int load(int device, const std::string& src, const std::vector<char>& bin, cudaKernel_t* kern, std::string* err);
 }  // namespace jit
 
@@ -507,7 +508,13 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
       std::string err;
       const std::vector<char>* bin = jit::compile(src, &err);
       cudaKernel_t k = nullptr;
-      if (bin && jit::load(o->device, src, *bin, &k, &err) == 0) {
+      bool loaded = bin && jit::load(o->device, src, *bin, &k, &err) == 0;
+      if (bin && !loaded) {          // a stale or damaged cache entry: drop it and compile once more
+        jit::evict(src);
+        bin = jit::compile(src, &err, /*fresh=*/true);
+        loaded = bin && jit::load(o->device, src, *bin, &k, &err) == 0;
+      }
+      if (loaded) {
         pl->jit_kernel = k;
         pl->kernel_name = "passage_spec (tables specialised with NVRTC)";
         if (pool) {
@@ -884,7 +891,11 @@ int stryke_b200_run_compact(const StrykeFacility* f, const StrykeDayTables* d, c
   DevBuf dn, dr, tot;
   CK(dn.alloc((size_t)C * 4));
   CK(dr.alloc((size_t)std::max<int64_t>(out->rows_cap, 1) * row_bytes));
+  // slabs: at least 8 on large lists (copies overlap kernels), and enough to keep one slab's rows (about half the capacity the
+  // caller expects to fill) near 64 MB, so that the rows zeroed by count_kernel are still in L2 when the passage kernel adds to them
   int n_slabs = out->n_slabs > 0 ? out->n_slabs : (C >= (1 << 20) ? 8 : C >= (1 << 16) ? 2 : 1);
+  if (out->n_slabs <= 0 && C >= (1 << 20))
+    n_slabs = (int)std::min<int64_t>(64, std::max<int64_t>(8, (int64_t)(((size_t)out->rows_cap * row_bytes) >> 26)));
   int64_t per = ((C + n_slabs - 1) / n_slabs + COUNT_CELLS - 1) / COUNT_CELLS * COUNT_CELLS;
   if (per < COUNT_CELLS) per = COUNT_CELLS;
   n_slabs = (int)((C + per - 1) / per);

@@ -17,6 +17,8 @@ struct Api {
   int (*cubin_size)(nvrtcProgram, size_t*) = nullptr;
   int (*cubin)(nvrtcProgram, char*) = nullptr;
   int (*destroy)(nvrtcProgram*) = nullptr;
+  int (*version)(int*, int*) = nullptr;
+  int ver_major = 0, ver_minor = 0;
   bool ok = false;
 };
 static Api& api() {
@@ -35,6 +37,8 @@ static Api& api() {
     x.cubin_size = (decltype(x.cubin_size))dlsym(h, "nvrtcGetCUBINSize");
     x.cubin = (decltype(x.cubin))dlsym(h, "nvrtcGetCUBIN");
     x.destroy = (decltype(x.destroy))dlsym(h, "nvrtcDestroyProgram");
+    x.version = (decltype(x.version))dlsym(h, "nvrtcVersion");
+    if (x.version) x.version(&x.ver_major, &x.ver_minor);
     x.ok = x.create && x.compile && x.log_size && x.log && x.cubin_size && x.cubin && x.destroy;
     return x;
   }();
@@ -233,13 +237,27 @@ static bool make_dirs(const std::string& dir) {
 }
 
 // nullptr + message on failure
-static const std::vector<char>* compile(const std::string& src, std::string* err, bool fresh) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  auto it = g_cubins.find(src);
-  if (it != g_cubins.end() && !fresh) return &it->second;
+// where compiled specialisations are kept between processes: $STRYKE_B200_CACHE_DIR, else $XDG_CACHE_HOME/stryke_b200, else
+// ~/.cache/stryke_b200 (never the package directory: installs may be read-only or shared between users)
+static std::string cache_dir() {
+  if (const char* e = getenv("STRYKE_B200_CACHE_DIR")) return e;
+  if (const char* x = getenv("XDG_CACHE_HOME")) { if (*x) return std::string(x) + "/stryke_b200"; }
+  if (const char* h = getenv("HOME")) { if (*h) return std::string(h) + "/.cache/stryke_b200"; }
+  return "/tmp/stryke_b200_cache";
+}
+static std::string cache_path(const std::string& src, const std::string& fast, const std::string& common) {
+  // key = FNV-1a of (format tag, NVRTC version, target, generated source, both headers)
+  uint64_t h = 1469598103934665603ull;
   Api& a = api();
-  if (!a.ok) { *err = "libnvrtc not available"; return nullptr; }
-  std::string fast, common;
+  const std::string tag = "stryke_b200.cubin/2 nvrtc " + std::to_string(a.ver_major) + "." + std::to_string(a.ver_minor) + " sm_100a";
+  const std::string* parts[4] = {&tag, &src, &fast, &common};
+  for (const std::string* part : parts)
+    for (unsigned char ch : *part) { h ^= ch; h *= 1099511628211ull; }
+  char name[64];
+  snprintf(name, sizeof name, "/sm_100a_%016llx.cubin", (unsigned long long)h);
+  return cache_dir() + name;
+}
+static bool load_sources(std::string* fast, std::string* common) {
   if (g_source_dir.empty()) {      // default: csrc/ next to the shared library this code was loaded from
     Dl_info info;
     if (dladdr((const void*)&stryke_b200_abi_version, &info) && info.dli_fname) {
@@ -248,26 +266,36 @@ static const std::vector<char>* compile(const std::string& src, std::string* err
       g_source_dir = (slash == std::string::npos ? std::string(".") : so.substr(0, slash)) + "/csrc";
     }
   }
-  if (g_source_dir.empty() || !read_file(g_source_dir + "/passage_fast.cuh", &fast) || !read_file(g_source_dir + "/passage_common.cuh", &common)) {
+  return !g_source_dir.empty() && read_file(g_source_dir + "/passage_fast.cuh", fast) && read_file(g_source_dir + "/passage_common.cuh", common);
+}
+// forget a specialisation that failed to load (stale or damaged cache entry): the next compile() builds it again
+static void evict(const std::string& src) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  g_cubins.erase(src);
+  std::string fast, common;
+  if (load_sources(&fast, &common)) unlink(cache_path(src, fast, common).c_str());
+}
+
+static const std::vector<char>* compile(const std::string& src, std::string* err, bool fresh) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  auto it = g_cubins.find(src);
+  if (it != g_cubins.end() && !fresh) return &it->second;
+  Api& a = api();
+  if (!a.ok) { *err = "libnvrtc not available"; return nullptr; }
+  std::string fast, common;
+  if (!load_sources(&fast, &common)) {
     *err = "kernel sources not found (stryke_b200_set_source_dir)";
     return nullptr;
   }
-  // on-disk cache of compiled specialisations: key = FNV-1a of (generated source, both headers, target)
-  uint64_t h = 1469598103934665603ull;
-  const std::string* parts[3] = {&src, &fast, &common};
-  for (const std::string* part : parts)
-    for (unsigned char ch : *part) { h ^= ch; h *= 1099511628211ull; }
-  std::string dir;
-  if (const char* e = getenv("STRYKE_B200_CACHE_DIR")) dir = e;
-  else dir = g_source_dir + "/../.jit_cache";      // inside the package directory
-  char name[64];
-  snprintf(name, sizeof name, "/sm_100a_%016llx.cubin", (unsigned long long)h);
-  const std::string path = dir + name;
+  const std::string path = cache_path(src, fast, common);
+  const std::string dir = path.substr(0, path.rfind('/'));
   if (!fresh) {
     std::ifstream f(path, std::ios::binary);
     if (f) {
       std::vector<char> bin((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-      if (bin.size() > 1024) return &(g_cubins[src] = std::move(bin));
+      // an ELF image of plausible size; a damaged entry that still passes is evicted when cudaLibraryLoadData refuses it
+      if (bin.size() > 1024 && bin[0] == 0x7f && bin[1] == 'E' && bin[2] == 'L' && bin[3] == 'F') return &(g_cubins[src] = std::move(bin));
+      unlink(path.c_str());
     }
   }
   const char* headers[2] = {fast.c_str(), common.c_str()};

@@ -54,6 +54,20 @@ def expected_slots(grid, species, margin=1.08, extra=4096):
     return int(tot) + extra
 
 
+SLAB_ROW_BYTES = 64 << 20      # rows of one slab: about half of the 126 MB L2
+
+
+def default_slab_cells(n_cells, rows_bytes):
+    """Cells per slab (a multiple of ALIGN).  Large lists are cut into at least 8 slabs (the export of one slab runs under
+    the kernels of the next) and into as many as keep a slab's rows near SLAB_ROW_BYTES: the rows count_kernel zeroes are
+    then still in L2 when the passage kernel adds to them, and DRAM sees them once, on the way out."""
+    n_cells = max(int(n_cells), 1)
+    if n_cells < (1 << 18):
+        return max(ALIGN, -(-n_cells // ALIGN) * ALIGN)
+    n_slabs = min(64, max(8, -(-int(rows_bytes) // SLAB_ROW_BYTES)))
+    return max(ALIGN, -(-n_cells // n_slabs // ALIGN) * ALIGN)
+
+
 class ShardLayout:
     """Geometry of one rank's flat buffer: header, block tables, slab regions of rows (identical on every rank)."""
 
@@ -127,10 +141,10 @@ class ShardedRun:
         self.plan = engine.Plan(fac, days, species, grid, None, None, device=device, precision=precision, seed=seed,
                                 max_daily_fish=max_daily_fish, kernel_variant=kernel_variant)
         n_max = int(n_cells_max if n_cells_max is not None else self.n_cells)
-        if slab_cells is None:           # ~8 slabs on large lists, whole multiples of ALIGN cells
-            slab_cells = max(ALIGN, -(-max(n_max, 1) // 8 // ALIGN) * ALIGN) if n_max >= (1 << 18) else max(ALIGN, -(-max(n_max, 1) // ALIGN) * ALIGN)
+        est = expected_slots(grid, np.asarray(species).reshape(-1, 20))
+        if slab_cells is None:
+            slab_cells = default_slab_cells(n_max, est * (fac.n_pairs + 3) * 4)
         if slab_cap is None:
-            est = expected_slots(grid, np.asarray(species).reshape(-1, 20))
             slab_cap = max(1024, int(est / max(1, -(-n_max // slab_cells)) * 1.25) + 2048)
         self.L = ShardLayout(n_max, fac.n_pairs, slab_cells, slab_cap)
         L = self.L
@@ -158,6 +172,8 @@ class ShardedRun:
         self.slots_after = torch.zeros(L.n_slabs + 1, dtype=torch.int64, device=self.dev)
         self.compute = torch.cuda.current_stream(self.dev)
         self.copy = torch.cuda.Stream(self.dev)
+        # one stream per peer: the pushes of a slab to different GPUs run on different copy engines at the same time
+        self.peer_streams = {p: torch.cuda.Stream(self.dev) for p in range(self.world) if p != self.rank} if self.mode == "push" else {}
         self.fence = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.t_blk = self.plan.compact_tables()[:3]
         self.slab_events = [torch.cuda.Event() for _ in range(L.n_slabs)]
@@ -175,6 +191,8 @@ class ShardedRun:
             self.host = torch.empty(L.total, dtype=torch.int32).pin_memory()
         self.copy.wait_stream(self.compute)               # the previous pass's exports are ordered before this pass's kernels
         self.compute.wait_stream(self.copy)
+        for ps in self.peer_streams.values():
+            self.compute.wait_stream(ps)
         for k in range(L.n_slabs):
             lo, hi = k * L.slab_cells, min(nC, (k + 1) * L.slab_cells)
             if lo >= hi:
@@ -185,17 +203,17 @@ class ShardedRun:
             for j in range(3):                             # the plan's block tables of this slab -> the flat buffer
                 self.blk[j, b0:b1].copy_(self.t_blk[j][b0:b1], non_blocking=True)
             self.slab_events[k].record(self.compute)
-            if self.mode == "push" or to_host:
-                w0, w1 = L.slab_words(k)
+            w0, w1 = L.slab_words(k)
+            if self.mode == "push":
+                base = self.rank * L.total
+                for p, ps in self.peer_streams.items():
+                    with torch.cuda.stream(ps):
+                        ps.wait_event(self.slab_events[k])
+                        self.peers[p][base + w0:base + w1].copy_(self.buf[w0:w1], non_blocking=True)
+            if to_host:
                 with torch.cuda.stream(self.copy):
                     self.copy.wait_event(self.slab_events[k])
-                    if self.mode == "push":
-                        base = self.rank * L.total
-                        for p in range(self.world):
-                            if p != self.rank:
-                                self.peers[p][base + w0:base + w1].copy_(self.buf[w0:w1], non_blocking=True)
-                    if to_host:
-                        self.host[w0:w1].copy_(self.buf[w0:w1], non_blocking=True)
+                    self.host[w0:w1].copy_(self.buf[w0:w1], non_blocking=True)
 
     def exchange(self, status_code=0, to_host=False):
         """Finish the pass: header + block tables to the peers, completion fence (push) or the one all-gather."""
@@ -206,12 +224,15 @@ class ShardedRun:
                             non_blocking=True)
         if self.world > 1:
             if self.mode == "push":
+                base = self.rank * L.total
+                for p, ps in self.peer_streams.items():
+                    with torch.cuda.stream(ps):
+                        ps.wait_stream(self.compute)
+                        self.peers[p][base:base + L.rows_off].copy_(self.buf[:L.rows_off], non_blocking=True)
                 self.copy.wait_stream(self.compute)
                 with torch.cuda.stream(self.copy):
-                    base = self.rank * L.total
-                    for p in range(self.world):
-                        if p != self.rank:
-                            self.peers[p][base:base + L.rows_off].copy_(self.buf[:L.rows_off], non_blocking=True)
+                    for ps in self.peer_streams.values():
+                        self.copy.wait_stream(ps)
                     if to_host:
                         self.host[:L.rows_off].copy_(self.buf[:L.rows_off], non_blocking=True)
                     dist.all_reduce(self.fence, group=self.group)      # every rank's pushes are stream-ordered before its fence
@@ -292,7 +313,7 @@ def run_sharded(plan_host, rank, world, device, *, precision=32, seed=0, max_dai
     cap_scale = 1.0
     while True:
         est = max(expected_slots(g, species) for g in grids)
-        slab_cells = max(ALIGN, -(-max(n_max, 1) // (8 if n_max >= (1 << 18) else 1) // ALIGN) * ALIGN)
+        slab_cells = default_slab_cells(n_max, est * (plan_host.fac.n_pairs + 3) * 4)
         n_slabs = max(1, -(-n_max // slab_cells))
         run = ShardedRun(plan_host.fac, plan_host.days, species, mine, rank, world, device, precision=precision, seed=seed,
                          max_daily_fish=max_daily_fish, slab_cells=slab_cells,
