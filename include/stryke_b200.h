@@ -255,6 +255,9 @@ int stryke_b200_plan_launch_compact(StrykePlan* plan, int64_t cell_lo, int64_t c
 /* DEVICE pointers of the plan's per-block tables [n_blocks] and the row geometry. */
 int stryke_b200_plan_compact_tables(StrykePlan* plan, uint32_t** d_blk_row, uint32_t** d_blk_mask, uint32_t** d_blk_wide,
                                     int32_t* row_w, int32_t* narrow_max);
+/* Let the launches write the per-block tables straight into caller-owned DEVICE arrays of n_blocks words each (e.g. inside the
+ * buffer a rank exchanges with its peers) instead of the plan's own; NULLs switch back. */
+int stryke_b200_plan_set_compact_tables(StrykePlan* plan, uint32_t* d_blk_row, uint32_t* d_blk_mask, uint32_t* d_blk_wide);
 /* Slots and fish counted so far by the launches on `stream` (syncs the stream). */
 int stryke_b200_plan_compact_totals(StrykePlan* plan, void* stream, int64_t* n_slots, int64_t* n_fish);
 const char* stryke_b200_plan_kernel(const StrykePlan* plan);      /* which passage kernel the plan will launch */

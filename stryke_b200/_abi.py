@@ -116,6 +116,8 @@ def lib():
     L.stryke_b200_plan_launch_compact.argtypes = [_p, C.c_int64, C.c_int64, _p, _p, C.c_int64, C.c_int64, _p, _p]
     L.stryke_b200_plan_compact_tables.argtypes = [_p, P(_p), P(_p), P(_p), P(C.c_int32), P(C.c_int32)]
     L.stryke_b200_plan_compact_totals.argtypes = [_p, _p, P(C.c_int64), P(C.c_int64)]
+    L.stryke_b200_plan_set_compact_tables.argtypes = [_p, _p, _p, _p]
+    L.stryke_b200_plan_set_compact_tables.restype = C.c_int
     L.stryke_b200_plan_set_seed.argtypes = [_p, C.c_uint64]
     L.stryke_b200_plan_kernel.argtypes = [_p]
     L.stryke_b200_plan_kernel.restype = C.c_char_p
@@ -142,7 +144,7 @@ def lib():
     return L
 
 
-EXPORTS = ["stryke_b200_plan_fetch_hours", "stryke_b200_run_compact", "stryke_b200_plan_launch_compact", "stryke_b200_plan_compact_tables",
+EXPORTS = ["stryke_b200_plan_set_compact_tables", "stryke_b200_plan_fetch_hours", "stryke_b200_run_compact", "stryke_b200_plan_launch_compact", "stryke_b200_plan_compact_tables",
            "stryke_b200_plan_compact_totals", "stryke_b200_last_error", "stryke_b200_abi_version", "stryke_b200_device_count", "stryke_b200_launch_count",
            "stryke_b200_run", "stryke_b200_plan_create", "stryke_b200_plan_launch", "stryke_b200_plan_kernel", "stryke_b200_set_source_dir", "stryke_b200_jit_selftest", "stryke_b200_plan_set_seed", "stryke_b200_plan_status",
            "stryke_b200_plan_fetch_trace", "stryke_b200_plan_destroy", "stryke_b200_plan_time_kernel", "stryke_b200_plan_kernel_ms", "stryke_b200_strike_survival",

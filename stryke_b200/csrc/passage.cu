@@ -113,6 +113,7 @@ struct StrykePlan {
   DevBuf groups, active_days, blk_tile, blk_row, blk_mask, blk_wide, scan_status, peak_params, peak_hours;
   int peak_units = 0;
   int n_days = 0, n_species = 0, row_w = 0, narrow_max = 0;
+  uint32_t *ext_blk_row = nullptr, *ext_blk_mask = nullptr, *ext_blk_wide = nullptr;      // caller-owned block tables (plan_set_compact_tables)
   int64_t last_rows_cap = -1;  // capacity of the last compact launch (-1: dense)
   bool attr_set = false;      // cudaFuncAttributeMaxDynamicSharedMemorySize applied to this plan's passage kernel
   DevBuf i_fish_off, i_presence, i_count, i_z, i_dice, i_rR, i_depth, i_cause, i_route, i_grR, i_gdepth, i_gcause;
@@ -638,6 +639,7 @@ static int launch_cells(StrykePlan* pl, int64_t c_lo, int64_t c_hi, int32_t* d_c
   K.cell_base = c_lo;
   if (K.groups == nullptr) { K.cell_day += c_lo; K.cell_species += c_lo; K.cell_id += c_lo; }
   K.cell_n = d_cell_n + c_lo;
+  if (pl->ext_blk_row) { K.out.blk_row = pl->ext_blk_row; K.out.blk_mask = pl->ext_blk_mask; K.out.blk_wide = pl->ext_blk_wide; }
   K.out.blk_row += c_lo >> 5; K.out.blk_mask += c_lo >> 5; K.out.blk_wide += c_lo >> 5;
   const bool compact = d_rows != nullptr;
   const bool fresh = !compact || c_lo == 0;      // a pass over the cell list starts at its first cell: status words start over
@@ -721,11 +723,18 @@ int stryke_b200_plan_launch_compact(StrykePlan* pl, int64_t cell_lo, int64_t cel
 int stryke_b200_plan_compact_tables(StrykePlan* pl, uint32_t** d_blk_row, uint32_t** d_blk_mask, uint32_t** d_blk_wide,
                                     int32_t* row_w, int32_t* narrow_max) {
   if (!pl) return fail(STRYKE_E_ARG, "null plan");
-  if (d_blk_row) *d_blk_row = pl->blk_row.as<uint32_t>();
-  if (d_blk_mask) *d_blk_mask = pl->blk_mask.as<uint32_t>();
-  if (d_blk_wide) *d_blk_wide = pl->blk_wide.as<uint32_t>();
+  if (d_blk_row) *d_blk_row = pl->ext_blk_row ? pl->ext_blk_row : pl->blk_row.as<uint32_t>();
+  if (d_blk_mask) *d_blk_mask = pl->ext_blk_mask ? pl->ext_blk_mask : pl->blk_mask.as<uint32_t>();
+  if (d_blk_wide) *d_blk_wide = pl->ext_blk_wide ? pl->ext_blk_wide : pl->blk_wide.as<uint32_t>();
   if (row_w) *row_w = pl->row_w;
   if (narrow_max) *narrow_max = pl->narrow_max;
+  return STRYKE_OK;
+}
+
+int stryke_b200_plan_set_compact_tables(StrykePlan* pl, uint32_t* d_blk_row, uint32_t* d_blk_mask, uint32_t* d_blk_wide) {
+  if (!pl) return fail(STRYKE_E_ARG, "null plan");
+  if ((d_blk_row || d_blk_mask || d_blk_wide) && !(d_blk_row && d_blk_mask && d_blk_wide)) return fail(STRYKE_E_ARG, "all three block tables or none");
+  pl->ext_blk_row = d_blk_row; pl->ext_blk_mask = d_blk_mask; pl->ext_blk_wide = d_blk_wide;
   return STRYKE_OK;
 }
 

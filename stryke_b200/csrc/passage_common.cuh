@@ -281,6 +281,24 @@ __device__ __forceinline__ void tally_flush(const KParams& P, int64_t cell, int 
   acc_daily = 0;
 }
 
+// Last index i in [lo, hi) with off[i] <= t (off is non-decreasing, off[lo] <= t), found by the whole warp: every step the 32
+// lanes probe 32 evenly spaced entries at once, so 3 rounds of loads place a tile among 32 768 offsets (a lane-serial binary
+// search pays 15 dependent memory latencies for the same).  All lanes call it with the same arguments and get the result.
+__device__ __forceinline__ int64_t warp_search_last_le(const int64_t* __restrict__ off, int64_t lo, int64_t hi, int64_t t, int lane) {
+  while (hi - lo > 1) {
+    const int64_t span = hi - lo;
+    const int64_t step = (span + 31) >> 5;                      // probes lo + (lane + 1) * step, clipped
+    const int64_t idx = lo + (int64_t)(lane + 1) * step;
+    const bool le = idx < hi && off[idx] <= t;
+    const int k = __popc(__ballot_sync(0xffffffffu, le));        // probes 1..k hold offsets <= t (monotone)
+    const int64_t nlo = lo + (int64_t)k * step;
+    const int64_t nhi = lo + (int64_t)(k + 1) * step;
+    lo = nlo;
+    hi = nhi < hi ? nhi : hi;
+  }
+  return lo;
+}
+
 // Pooled remainders: a cell of n fish keeps pool_full(n) tiles of its own and sends pool_rem(n) fish to the shared tiles of
 // its block.  Cells below pool_all fish (64 when the packed 6-/10-bit tally fields can hold 63 fish of one cell, else 32) are
 // pooled entirely: entering and leaving a cell costs more than simulating its one or two tiles.

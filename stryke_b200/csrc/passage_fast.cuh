@@ -495,9 +495,8 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   fetch_chunk();            // the one after this
   bool fresh = false;       // the tile about to be simulated is the first one this warp sees of cell c
   if (t0 >= c_end) {        // not a continuation: last cell with tile_off[c] <= t0 (cells without fish have empty ranges)
-    int64_t lo = c < 0 ? 0 : c, hi = P.n_cells;
-    while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (P.tile_off[mid] <= t0) lo = mid; else hi = mid; }
-    c = lo; c_begin = P.tile_off[c]; c_end = P.tile_off[c + 1];
+    c = warp_search_last_le(P.tile_off, c < 0 ? 0 : c, P.n_cells, t0, lane);
+    c_begin = P.tile_off[c]; c_end = P.tile_off[c + 1];
     fresh = true;
   }
   // 32-bit bookkeeping inside the chunk: tiles left in the current cell, index of the tile's first fish
@@ -647,9 +646,8 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   bool new_block = false;
   if (t0 < b_begin || t0 >= b_end) {                  // last block with blk_off <= t0 (blocks without fish have empty ranges)
     pool_flush();
-    int64_t lo = 0, hi = NB;
-    while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (blk_off(mid) <= t0) lo = mid; else hi = mid; }
-    b = lo; b_begin = blk_off(b); b_end = blk_off(b + 1);
+    b = warp_search_last_le(P.blk_tile, (b >= 0 && t0 >= b_end) ? b : 0, NB, t0, lane);      // (chunks are handed out in increasing order)
+    b_begin = blk_off(b); b_end = blk_off(b + 1);
     new_block = true;
   }
   // `run` tiles from here on are full tiles of one cell (fish_base: first fish of the next one): nothing to decide

@@ -61,10 +61,13 @@ def default_slab_cells(n_cells, rows_bytes):
     """Cells per slab (a multiple of ALIGN).  Large lists are cut into at least 8 slabs (the export of one slab runs under
     the kernels of the next) and into as many as keep a slab's rows near SLAB_ROW_BYTES: the rows count_kernel zeroes are
     then still in L2 when the passage kernel adds to them, and DRAM sees them once, on the way out."""
+    import os
     n_cells = max(int(n_cells), 1)
     if n_cells < (1 << 18):
         return max(ALIGN, -(-n_cells // ALIGN) * ALIGN)
     n_slabs = min(64, max(8, -(-int(rows_bytes) // SLAB_ROW_BYTES)))
+    if os.environ.get("STRYKE_B200_SLABS"):
+        n_slabs = max(1, int(os.environ["STRYKE_B200_SLABS"]))
     return max(ALIGN, -(-n_cells // n_slabs // ALIGN) * ALIGN)
 
 
@@ -175,7 +178,7 @@ class ShardedRun:
         # one stream per peer: the pushes of a slab to different GPUs run on different copy engines at the same time
         self.peer_streams = {p: torch.cuda.Stream(self.dev) for p in range(self.world) if p != self.rank} if self.mode == "push" else {}
         self.fence = torch.zeros(1, dtype=torch.int32, device=self.dev)
-        self.t_blk = self.plan.compact_tables()[:3]
+        self.plan.set_compact_tables(self.blk[0], self.blk[1], self.blk[2])      # count_kernel writes them into the flat buffer
         self.slab_events = [torch.cuda.Event() for _ in range(L.n_slabs)]
         self.host = None
 
@@ -199,9 +202,6 @@ class ShardedRun:
                 break
             self.plan.launch_compact(self.cell_n, self.rows, lo, hi, first_slot=k * L.slab_cap,
                                      slots_after=self.slots_after[k:k + 1], stream=cs)
-            b0, b1 = lo >> 5, (hi + 31) >> 5
-            for j in range(3):                             # the plan's block tables of this slab -> the flat buffer
-                self.blk[j, b0:b1].copy_(self.t_blk[j][b0:b1], non_blocking=True)
             self.slab_events[k].record(self.compute)
             w0, w1 = L.slab_words(k)
             if self.mode == "push":

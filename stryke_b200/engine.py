@@ -376,6 +376,11 @@ class Plan:
                                                               C.c_void_p(rows.data_ptr()), int(rows.shape[0]), int(first_slot), sa,
                                                               C.c_void_p(stream)))
 
+    def set_compact_tables(self, blk_row, blk_mask, blk_wide):
+        """The launches write the per-block tables into these int32 device tensors ([n_blocks] each) instead of the plan's own."""
+        _abi.check(_abi.lib().stryke_b200_plan_set_compact_tables(self._h, C.c_void_p(blk_row.data_ptr()), C.c_void_p(blk_mask.data_ptr()),
+                                                                  C.c_void_p(blk_wide.data_ptr())))
+
     def compact_tables(self):
         """(blk_row, blk_mask, blk_wide) as int32 torch tensors over the plan's device memory, row_w, narrow_max."""
         import torch
