@@ -459,6 +459,11 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   // global counter, at most P.chunk_tiles and at least P.chunk_min: long chunks while there is plenty of work (one cell
   // search per chunk), short ones at the end so that all warps finish together.  The next chunk is fetched while the
   // current one is being simulated.
+  // The next chunk is fetched when the current one has PREFETCH_TILES tiles left to hand out: late enough that its size is
+  // decided on the work that is REALLY left (a chunk fetched a whole chunk ahead is one round too large, and the kernel's
+  // tail is as long as the largest chunk: measured 1.0-1.4 chunk durations per launch), early enough that the atomic's
+  // latency hides under the last tiles.
+  constexpr int PREFETCH_TILES = 6;
   const int64_t G = (int64_t)gridDim.x * WARPS;
   int64_t nx0 = 0, nx1 = 0;                           // the chunk fetched ahead: tiles [nx0, nx1)
   auto fetch_chunk = [&]() {
@@ -492,7 +497,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   const int64_t t0 = nx0;
   if (t0 >= T) break;
   const int64_t t1 = nx1 < T ? nx1 : T;
-  fetch_chunk();            // the one after this
+  bool fetched = false;     // the next chunk is fetched near the END of this one (see PREFETCH_TILES)
   bool fresh = false;       // the tile about to be simulated is the first one this warp sees of cell c
   if (t0 >= c_end) {        // not a continuation: last cell with tile_off[c] <= t0 (cells without fish have empty ranges)
     c = warp_search_last_le(P.tile_off, c < 0 ? 0 : c, P.n_cells, t0, lane);
@@ -505,6 +510,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   int fish_base = (int)(t0 - c_begin) * 32;
   const int nt = (int)(t1 - t0);
   for (int it = 0; it < nt; ++it, --left, fish_base += 32) {
+    if (!fetched && nt - it <= PREFETCH_TILES) { fetch_chunk(); fetched = true; }
     if (left == 0) {
       do { ++c; c_begin = c_end; c_end = P.tile_off[c + 1]; } while (c_end == c_begin);
       const int64_t rm = c_end - c_begin;
@@ -526,6 +532,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
     STRYKE_BCHK(P, fish_base >= 0 && (lane != 0 || fish < n_c), 7);     // a tile always holds at least one fish of its cell
     simulate(fish, fish < n_c, cid_lo, cid_hi);
   }
+  if (!fetched) fetch_chunk();
   }
   } else {
   // ---- pooled remainders (see pool_block): blocks of 32 cells; the tiles of block b are its shared tiles, then the
@@ -642,7 +649,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   const int64_t t0 = nx0;
   if (t0 >= T) break;
   const int64_t t1 = nx1 < T ? nx1 : T;
-  fetch_chunk();            // the one after this
+  bool fetched = false;     // the next chunk is fetched near the END of this one (see PREFETCH_TILES)
   bool new_block = false;
   if (t0 < b_begin || t0 >= b_end) {                  // last block with blk_off <= t0 (blocks without fish have empty ranges)
     pool_flush();
@@ -757,9 +764,11 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
       }
       chunk_left -= run;
       t += run;
+      if (!fetched && chunk_left <= PREFETCH_TILES) { fetch_chunk(); fetched = true; }
     }
     simulate(fish, active, cid_lo, cid_hi);
   }
+  if (!fetched) fetch_chunk();
   }
   pool_flush();
   }
