@@ -110,7 +110,8 @@ struct StrykePlan {
   int64_t n_cells = 0;
   DevBuf nodes, edge_dst, moves, pair_node, ustatic, edge_cdf, node_stay, unit_coef, day_Q, species, cell_day,
       cell_species, cell_id, tile_off, fish_off, err, blk_S, pareto;
-  DevBuf groups, active_days, blk_tile, blk_row, blk_mask, blk_wide, scan_status, peak_params, peak_hours;
+  DevBuf groups, active_days, blk_tile, blk_row, blk_mask, blk_wide, scan_status, peak_params, peak_hours, timeline;
+  int timeline_launch = 0;
   int peak_units = 0;
   int n_days = 0, n_species = 0, row_w = 0, narrow_max = 0;
   uint32_t *ext_blk_row = nullptr, *ext_blk_mask = nullptr, *ext_blk_wide = nullptr;      // caller-owned block tables (plan_set_compact_tables)
@@ -693,11 +694,25 @@ static int launch_cells(StrykePlan* pl, int64_t c_lo, int64_t c_hi, int32_t* d_c
     pl->kernel_events.emplace_back(ev0, ev1);
     CK(cudaEventRecord(ev0, st));
   }
+  if (pl->use_fast && getenv("STRYKE_B200_TIMELINE")) {      // debug: per-warp start / end times of one launch -> a text file
+    if (!pl->timeline.p) CK(pl->timeline.alloc((size_t)pl->n_sm * 8 * WARPS * 4 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(pl->timeline.p, 0, pl->timeline.bytes, st));
+    K.timeline = pl->timeline.as<unsigned long long>();
+  }
   int rc;
   if (pl->use_fast) rc = launch_fast_any(pl, K, st);
   else if (pl->precision == 64) rc = pl->inject ? launch_passage_pr<double, true>(pl, K, st) : launch_passage_pr<double, false>(pl, K, st);
   else rc = pl->inject ? launch_passage_pr<float, true>(pl, K, st) : launch_passage_pr<float, false>(pl, K, st);
   if (ev1) CK(cudaEventRecord(ev1, st));
+  if (K.timeline && ++pl->timeline_launch == atoi(getenv("STRYKE_B200_TIMELINE"))) {
+    std::vector<unsigned long long> h(pl->timeline.bytes / 8);
+    CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpy(h.data(), pl->timeline.p, pl->timeline.bytes, cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen("gpurun_out/timeline.txt", "w")) {
+      for (size_t i = 0; i + 3 < h.size(); i += 4) if (h[i]) fprintf(f, "%llu %llu %llu %llu\n", h[i], h[i + 1], h[i + 2], h[i + 3]);
+      fclose(f);
+    }
+  }
   return rc;
 }
 

@@ -164,6 +164,7 @@ struct KParams {
   int64_t cell_base;                  // index of this launch's first cell in the plan's cell list (launches over a range)
   RowsDev out;                        // compact tally rows
   int peak_units; const double* peak_params; float* peak_hours;      // peaking operations (StrykePeaking), hours [plan cells][units]
+  unsigned long long* timeline;       // debug (STRYKE_B200_TIMELINE=1): per warp of the grid: start ns, end ns, chunks, tiles
   int pool_all;                       // pooled remainders: cells below this many fish (32 or 64) are pooled entirely
   const int64_t* blk_tile;            // pooled remainders: first tile of every aligned block of 32 cells [n_blocks + 1]
   const uint32_t* blk_S;              // pooled remainders (passage_fast.cuh): per block of 32 cells, shared tiles [0:31) | mixed [31]

@@ -465,16 +465,31 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   // latency hides under the last tiles.
   constexpr int PREFETCH_TILES = 6;
   const int64_t G = (int64_t)gridDim.x * WARPS;
+  unsigned long long tl_start = 0, tl_chunks = 0, tl_tiles = 0;
+  if (P.timeline) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tl_start));
   int64_t nx0 = 0, nx1 = 0;                           // the chunk fetched ahead: tiles [nx0, nx1)
+  long long my_done = 0;                              // tiles this warp has taken so far
   auto fetch_chunk = [&]() {
     unsigned long long start = 0, size = 0;
     if (lane == 0) {
       const long long seen = (long long)*reinterpret_cast<volatile unsigned long long*>(P.work_counter);
       long long sz = (T - seen) / (2 * G);
-      sz = sz > (long long)P.chunk_tiles ? (long long)P.chunk_tiles : sz;
+      // Warps do not run at one speed: the SM's arbiter favours the older thread blocks, the youngest third of the grid gets
+      // about half the issue slots (measured: 372 .. 2104 tiles per warp in one launch).  A chunk sized for the average
+      // warp keeps a slow one busy long after the queue is empty (the kernel's tail: ~100 us per launch), so the guided
+      // size is scaled by this warp's own share of the work so far, my_done / (seen / G), between 1/4 and 3/2.
+      long long cap = P.chunk_tiles;
+      if (seen > 4 * G) {
+        float r = (float)my_done * (float)G / (float)seen;
+        r = r < 0.25f ? 0.25f : r > 1.5f ? 1.5f : r;
+        sz = (long long)((float)sz * r);
+        if (r < 1.f) cap = (long long)((float)cap * r);      // a starved warp left alone at the end finishes its chunk at single-warp speed
+      }
+      sz = sz > cap ? cap : sz;
       sz = sz < (long long)P.chunk_min ? (long long)P.chunk_min : sz;
       size = (unsigned long long)sz;
       start = atomicAdd(P.work_counter, size);
+      my_done += sz;
     }
     nx0 = (int64_t)__shfl_sync(0xffffffffu, start, 0);
     nx1 = nx0 + (int64_t)__shfl_sync(0xffffffffu, size, 0);
@@ -497,6 +512,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   const int64_t t0 = nx0;
   if (t0 >= T) break;
   const int64_t t1 = nx1 < T ? nx1 : T;
+  tl_chunks += 1; tl_tiles += (unsigned long long)(t1 - t0);
   bool fetched = false;     // the next chunk is fetched near the END of this one (see PREFETCH_TILES)
   bool fresh = false;       // the tile about to be simulated is the first one this warp sees of cell c
   if (t0 >= c_end) {        // not a continuation: last cell with tile_off[c] <= t0 (cells without fish have empty ranges)
@@ -649,6 +665,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   const int64_t t0 = nx0;
   if (t0 >= T) break;
   const int64_t t1 = nx1 < T ? nx1 : T;
+  tl_chunks += 1; tl_tiles += (unsigned long long)(t1 - t0);
   bool fetched = false;     // the next chunk is fetched near the END of this one (see PREFETCH_TILES)
   bool new_block = false;
   if (t0 < b_begin || t0 >= b_end) {                  // last block with blk_off <= t0 (blocks without fish have empty ranges)
@@ -773,6 +790,12 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   pool_flush();
   }
   leave_cell();
+  if (P.timeline && lane == 0) {
+    unsigned long long tl_end;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tl_end));
+    unsigned long long* rec = P.timeline + 4 * ((size_t)blockIdx.x * WARPS + wid);
+    rec[0] = tl_start; rec[1] = tl_end; rec[2] = tl_chunks; rec[3] = tl_tiles;
+  }
 }
 
 #ifndef STRYKE_NVRTC
