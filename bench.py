@@ -459,20 +459,27 @@ def api_timing(device):
         tmp = tempfile.mkdtemp(prefix="bench_api_")
         sim = W.make_sim(prj, "api", proj_dir=tmp)
         sim.device = device
+        inputs = (("Flow Scenarios", sim.flow_scenarios_df), ("Operating Scenarios", sim.operating_scenarios_df),
+                  ("Population", sim.pop), ("Nodes", sim.nodes), ("Edges", sim.edges), ("Unit_Parameters", sim.unit_params),
+                  ("Facilities", sim.facility_params), ("Hydrograph", sim.input_hydrograph_df))
         with open_store(sim.hdf_path, mode="w") as st:
-            for key, df in (("Flow Scenarios", sim.flow_scenarios_df), ("Operating Scenarios", sim.operating_scenarios_df),
-                            ("Population", sim.pop), ("Nodes", sim.nodes), ("Edges", sim.edges), ("Unit_Parameters", sim.unit_params),
-                            ("Facilities", sim.facility_params), ("Hydrograph", sim.input_hydrograph_df)):
+            for key, df in inputs:
                 st[key] = df
         with contextlib.redirect_stdout(io.StringIO()):
+            tw = time.perf_counter()
+            sim.run()                       # first call in the process: includes the NVRTC specialisation for this facility
+            first = time.perf_counter() - tw
+            with open_store(sim.hdf_path, mode="w") as st:      # start over: run() appends
+                for key, df in inputs:
+                    st[key] = df
             t0 = time.perf_counter()
             sim.run()
             t1 = time.perf_counter()
             sim.summary()
             t2 = time.perf_counter()
         fish = int(sum(int(t.n.sum()) for t in sim._last_tallies.values()))
-        out[tag] = {"fish_passages": fish, "run_s": t1 - t0, "summary_s": t2 - t1, "run_fish_passages_per_s": fish / (t1 - t0),
-                    "run_plus_summary_fish_passages_per_s": fish / (t2 - t0)}
+        out[tag] = {"fish_passages": fish, "run_s": t1 - t0, "first_run_s": first, "summary_s": t2 - t1,
+                    "run_fish_passages_per_s": fish / (t1 - t0), "run_plus_summary_fish_passages_per_s": fish / (t2 - t0)}
         import shutil
         shutil.rmtree(tmp, ignore_errors=True)
     return out
