@@ -422,8 +422,8 @@ def measure(name, args, rank, local_rank, world, sampler, main):
                       "tally_rows_per_gpu": int(slots_used), "host_plan_seconds": host_plan_s,
                       "kernel": kernel_name(plan_h, grid, local_rank, args),
                       "collective": ("none" if world == 1 else
-                                     ("rows pushed slab by slab into every peer's buffer over NVLink (copy engines, symmetric memory) under "
-                                      "the next slab's kernels + one 4-byte all-reduce as the fence" if exchange_mode == "push" else
+                                     ("every rank's rows pushed slab by slab into rank 0's buffer over NVLink (peer copies on side streams, torch "
+                                      "symmetric memory) under the next slab's kernels + one 4-byte all-reduce as the fence" if exchange_mode == "push" else
                                       "one NCCL all_gather_into_tensor of the ranks' flat row buffers per step"))},
            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
     if per_rank:

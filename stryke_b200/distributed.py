@@ -132,12 +132,16 @@ class ShardedRun:
     """One rank's share of a run, resident on its GPU: plan, flat result buffer, gathered buffer, streams."""
 
     def __init__(self, fac, days, species, grid, rank, world, device, *, precision=32, seed=0, max_daily_fish=100000,
-                 kernel_variant=0, slab_cells=None, slab_cap=None, n_cells_max=None, group=None, exchange="auto"):
+                 kernel_variant=0, slab_cells=None, slab_cap=None, n_cells_max=None, group=None, exchange="auto", gather_to="root"):
+        """``gather_to``: "root" — every rank's rows end up on rank 0, the one rank that writes the frames (each rank pushes
+        1/(N-1) of what "all" costs it); "all" — on every rank (the all-reduce semantics: any rank can run ``summary()``)."""
         import torch
         import torch.distributed as dist
         from . import engine
         self.torch, self.dist = torch, dist
         self.rank, self.world, self.device, self.group = int(rank), int(world), int(device), group
+        self.gather_to = gather_to
+        self.targets = [p for p in range(int(world)) if p != int(rank)] if gather_to == "all" else ([0] if int(rank) != 0 else [])
         self.grid, self.fac = grid, fac
         self.n_cells = grid.n_cells
         self.dev = torch.device("cuda", device)
@@ -147,8 +151,8 @@ class ShardedRun:
         est = expected_slots(grid, np.asarray(species).reshape(-1, 20))
         if slab_cells is None:
             slab_cells = default_slab_cells(n_max, est * (fac.n_pairs + 3) * 4)
-        if slab_cap is None:
-            slab_cap = max(1024, int(est / max(1, -(-n_max // slab_cells)) * 1.25) + 2048)
+        if slab_cap is None:       # (expected_slots carries the margin; a slab that overflows is reported: slab_overflow -> the caller retries)
+            slab_cap = max(1024, int(est / max(1, -(-n_max // slab_cells)) * 1.04) + 1024)
         self.L = ShardLayout(n_max, fac.n_pairs, slab_cells, slab_cap)
         L = self.L
         self.mode = "gather"
@@ -176,7 +180,7 @@ class ShardedRun:
         self.compute = torch.cuda.current_stream(self.dev)
         self.copy = torch.cuda.Stream(self.dev)
         # one stream per peer: the pushes of a slab to different GPUs run on different copy engines at the same time
-        self.peer_streams = {p: torch.cuda.Stream(self.dev) for p in range(self.world) if p != self.rank} if self.mode == "push" else {}
+        self.peer_streams = {p: torch.cuda.Stream(self.dev) for p in self.targets} if self.mode == "push" else {}
         self.fence = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.plan.set_compact_tables(self.blk[0], self.blk[1], self.blk[2])      # count_kernel writes them into the flat buffer
         self.slab_events = [torch.cuda.Event() for _ in range(L.n_slabs)]
@@ -258,8 +262,11 @@ class ShardedRun:
 
     # -- results -----------------------------------------------------------------------------------------------------
     def results(self):
-        """Per rank: (n_cells, status code, CompactResult) from the gathered buffer (device -> host copy of everything)."""
+        """Per rank: (n_cells, status code, CompactResult) from the gathered buffer (device -> host copy of everything).  With
+        ``gather_to="root"`` only rank 0 holds the other ranks' rows: the other ranks get None."""
         self.torch.cuda.synchronize(self.dev)
+        if self.gather_to == "root" and self.rank != 0 and self.mode == "push":
+            return None
         g = self.gathered.cpu().numpy().reshape(self.world, self.L.total)
         return [unpack_flat(self.L, g[r], self.fac.n_pairs) for r in range(self.world)]
 
@@ -299,12 +306,12 @@ def agree_on_status(code, device=None, group=None):
     return -int(t.item())
 
 
-def run_sharded(plan_host, rank, world, device, *, precision=32, seed=0, max_daily_fish=100000, group=None):
+def run_sharded(plan_host, rank, world, device, *, precision=32, seed=0, max_daily_fish=100000, group=None, gather_to="root"):
     """Simulate this rank's iterations of ``plan_host`` (a ``runner.RunPlan``) on ``device`` and exchange the rows.
 
-    Returns a list with one (grid slice, CompactResult) per rank, in rank order — on EVERY rank.  An engine error on any
-    rank (population cap, non-finite count) is raised on all ranks with the failing rank's message; nobody hangs in a
-    collective."""
+    Returns a list with one (grid slice, CompactResult) per rank, in rank order — on rank 0, or on EVERY rank with
+    ``gather_to="all"`` (the other ranks get None otherwise).  An engine error on any rank (population cap, non-finite count)
+    is raised on all ranks with the failing rank's message; nobody hangs in a collective."""
     from . import _abi
     grids = [plan_host.grid.iterations_slice(r / world, (r + 1) / world) for r in range(world)]
     mine = grids[rank]
@@ -317,7 +324,7 @@ def run_sharded(plan_host, rank, world, device, *, precision=32, seed=0, max_dai
         n_slabs = max(1, -(-n_max // slab_cells))
         run = ShardedRun(plan_host.fac, plan_host.days, species, mine, rank, world, device, precision=precision, seed=seed,
                          max_daily_fish=max_daily_fish, slab_cells=slab_cells,
-                         slab_cap=int(cap_scale * (est / n_slabs * 1.25 + 2048)), n_cells_max=n_max, group=group)
+                         slab_cap=int(cap_scale * (est / n_slabs * 1.04 + 1024)), n_cells_max=n_max, group=group, gather_to=gather_to)
         code, msg = 0, ""
         try:
             run.launch(seed)
@@ -336,6 +343,7 @@ def run_sharded(plan_host, rank, world, device, *, precision=32, seed=0, max_dai
             cap_scale *= 2.0           # some slab region was too small somewhere: every rank retries with room to spare
             continue
         run.exchange(0)
-        out = [(grids[r], res) for r, (_, _, res) in enumerate(run.results())]
+        res = run.results()
+        out = None if res is None else [(grids[r], x[2]) for r, x in enumerate(res)]
         run.close()
         return out

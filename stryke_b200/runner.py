@@ -349,6 +349,8 @@ def run_simulation(sim, injected=None, trace=None):
             # compact rows; rank 0 writes the frames (Philox is keyed by the cell, so the result does not depend on world)
             from .distributed import run_sharded
             pieces = run_sharded(plan, rank, world, device=sim.device, precision=sim.precision, seed=sim.seed, max_daily_fish=cap)
+            if pieces is None:          # the rows went to rank 0, which writes the frames
+                return None
         else:
             pieces = [(plan.grid, run_compact_retry(plan, sim.device, sim.precision, sim.seed, cap))]
     except _abi.StrykeError as exc:

@@ -36,7 +36,7 @@ def main():
     for name, prj in (("c3", W.c3_population(n_species=5, iterations=30, days=20, scenarios=["A", "B"], facility_scenario_column=False)),
                       ("c5", W.c5_cascade(n_fish=40000, iterations=7, days=3))):
         sim, plan = W.make_plan(prj, f"mg_{name}_{rank}")
-        pieces = run_sharded(plan, rank, world, device=local, seed=123, max_daily_fish=10 ** 7)
+        pieces = run_sharded(plan, rank, world, device=local, seed=123, max_daily_fish=10 ** 7, gather_to="all")
         got = runner.dense_from_tallies(plan, runner.group_tallies(plan, pieces))
         whole = engine.run_cells(plan.fac, plan.days, plan.species_table, plan.grid, None, None, device=local, precision=32, seed=123,
                                  max_daily_fish=10 ** 7)
@@ -53,7 +53,7 @@ def main():
     bufs = {}
     for mode in ("push", "gather"):
         run = ShardedRun(plan.fac, plan.days, plan.species_table, grids[rank], rank, world, local, seed=9, max_daily_fish=10 ** 7,
-                         slab_cells=1024, slab_cap=2200, n_cells_max=max(g.n_cells for g in grids), exchange=mode)
+                         slab_cells=1024, slab_cap=2200, n_cells_max=max(g.n_cells for g in grids), exchange=mode, gather_to="all")
         assert run.mode == mode, (run.mode, getattr(run, "push_error", None))
         for seed in (9, 10):                 # twice: a second pass reuses the buffers
             run.step(seed)
@@ -69,6 +69,15 @@ def main():
     ok = ok and np.array_equal(got.cell_n, whole.cell_n) and np.array_equal(got.state_daily, whole.state_daily)
     print(f"rank {rank}: push == gather == single GPU: {ok}", flush=True)
     all_ok(ok, "exchange modes")
+
+    # gather to the root only (what simulation.run() and bench.py use): rank 0 holds everybody's rows, the others only their own
+    root = run_sharded(plan, rank, world, device=local, seed=10, max_daily_fish=10 ** 7, gather_to="root")
+    ok = (root is None) if rank != 0 else True
+    if rank == 0:
+        got = runner.dense_from_tallies(plan, runner.group_tallies(plan, root))
+        ok = np.array_equal(got.cell_n, whole.cell_n) and np.array_equal(got.state_daily, whole.state_daily) and np.array_equal(got.daily, whole.daily)
+    print(f"rank {rank}: gather to root == single GPU: {ok}", flush=True)
+    all_ok(ok, "gather to root")
 
     # an error on ONE rank (population cap exceeded in a cell only that rank owns) is raised on every rank, nobody hangs
     prj = W.c3_population(n_species=2, iterations=8 * world, days=30)
