@@ -479,7 +479,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
       // warp keeps a slow one busy long after the queue is empty (the kernel's tail: ~100 us per launch), so the guided
       // size is scaled by this warp's own share of the work so far, my_done / (seen / G), between 1/4 and 3/2.
       long long cap = P.chunk_tiles;
-      if (seen > 4 * G) {
+      if (seen > 4 * G && T < 8192 * G) {      // (long launches: the tail is noise, keep the chunk starts few)
         float r = (float)my_done * (float)G / (float)seen;
         r = r < 0.25f ? 0.25f : r > 1.5f ? 1.5f : r;
         sz = (long long)((float)sz * r);
