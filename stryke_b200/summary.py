@@ -81,6 +81,30 @@ def _mean_std_ci(prob_values, n_bootstrap=2000):
     return mean, std, lcl, ucl
 
 
+def _label_codes(col):
+    """(codes, labels) of a label column: ``labels[codes]`` reproduces it.  Long frames are compared by these integer codes
+    instead of string by string (3e6-row string compares per (species, scenario) were most of summary()'s time)."""
+    if isinstance(col.dtype, pd.CategoricalDtype):
+        return np.asarray(col.cat.codes), np.array([str(x) for x in col.cat.categories], dtype=object)
+    codes, uniq = pd.factorize(col, sort=False)
+    return np.asarray(codes), np.array([str(x) for x in uniq], dtype=object)
+
+
+def _stripped(col):
+    """``col.astype(str).str.strip()`` computed on the distinct labels only; also returns (codes, stripped labels)."""
+    codes, labels = _label_codes(col)
+    stripped = np.array([x.strip() for x in labels], dtype=object)
+    return pd.Series(stripped[codes], index=col.index, dtype=object), codes, stripped
+
+
+def _code_mask(codes, labels, value):
+    """Rows whose (stripped) label equals ``value``: the labels are few, the rows are compared as integers."""
+    hit = np.flatnonzero(labels == value)
+    if hit.size == 0:
+        return np.zeros(codes.shape[0], bool)
+    return np.isin(codes, hit) if hit.size > 1 else codes == hit[0]
+
+
 def _gpu_ordinal(sim):
     """The simulation's CUDA device when the library is built and a GPU is visible, else None."""
     try:
@@ -112,8 +136,8 @@ def _summarize(sim):
         sim.daily_summary = store["Daily"].copy()
         num_cols = list(sim.daily_summary.columns[6:])
         sim.daily_summary[num_cols] = sim.daily_summary[num_cols].astype(float)      # stryke.py:3564
-        sim.daily_summary["species_norm"] = sim.daily_summary["species"].astype(str).str.strip()
-        sim.daily_summary["scenario_norm"] = sim.daily_summary["scenario"].astype(str).str.strip()
+        sim.daily_summary["species_norm"], d_spc, d_spc_l = _stripped(sim.daily_summary["species"])
+        sim.daily_summary["scenario_norm"], d_scn, d_scn_l = _stripped(sim.daily_summary["scenario"])
         print("\n" + "=" * 60, flush=True)
         print("SIMULATION SUMMARY STATISTICS", flush=True)
         print("=" * 60, flush=True)
@@ -123,9 +147,15 @@ def _summarize(sim):
             state_daily["move"] = pd.to_numeric(state_daily["move"], errors="coerce").fillna(0).astype(int)
             for c in ("successes", "count"):
                 state_daily[c] = pd.to_numeric(state_daily[c], errors="coerce").fillna(0.0)
-            for c in ("scenario", "species"):
-                state_daily[c] = state_daily[c].astype(str).str.strip()
-            state_daily["state"] = state_daily["state"].astype(str)
+            state_daily["scenario"], s_scn, s_scn_l = _stripped(state_daily["scenario"])
+            state_daily["species"], s_spc, s_spc_l = _stripped(state_daily["species"])
+            st_codes, st_labels = _label_codes(state_daily["state"])
+            state_daily["state"] = pd.Series(st_labels[st_codes], index=state_daily.index, dtype=object)
+            # rows of one (scenario, species) made contiguous once (stable: the order inside a group is kept)
+            s_group = s_scn.astype(np.int64) * max(len(s_spc_l), 1) + s_spc
+            s_order = np.argsort(s_group, kind="stable")
+            state_sorted = state_daily.iloc[s_order]
+            s_group_sorted = s_group[s_order]
         moves = [int(m) for m in sim.moves]
         final_move = max(moves) if moves else 0
         group_sizes = sim.daily_summary.groupby(["species", "scenario"], sort=False).size() if len(species) > 1 else None
@@ -139,14 +169,19 @@ def _summarize(sim):
                 if state_daily is None:
                     logger.warning("Missing simulation data for key 'simulations/%s/%s'", scen, spc)
                     continue
-                state_dat = state_daily[(state_daily["scenario"] == str(scen).strip())
-                                        & (state_daily["species"] == str(spc).strip())]
+                hs, hp = np.flatnonzero(s_scn_l == str(scen).strip()), np.flatnonzero(s_spc_l == str(spc).strip())
+                if hs.size == 1 and hp.size == 1:
+                    gkey = int(hs[0]) * max(len(s_spc_l), 1) + int(hp[0])
+                    lo_, hi_ = np.searchsorted(s_group_sorted, [gkey, gkey + 1])
+                    state_dat = state_sorted.iloc[lo_:hi_]
+                else:
+                    state_dat = state_daily[_code_mask(s_scn, s_scn_l, str(scen).strip()) & _code_mask(s_spc, s_spc_l, str(spc).strip())]
                 if state_dat.empty:
                     logger.warning("Missing simulation aggregates for scenario '%s' species '%s'", scen, spc)
                     continue
                 # whole-project survival per (iteration, day): successes at the final move / pop_size (:3616-3637)
-                sub = sim.daily_summary[(sim.daily_summary["species_norm"] == str(spc).strip())
-                                        & (sim.daily_summary["scenario_norm"] == str(scen).strip())][["iteration", "day", "pop_size"]].copy()
+                sub = sim.daily_summary[_code_mask(d_spc, d_spc_l, str(spc).strip())
+                                        & _code_mask(d_scn, d_scn_l, str(scen).strip())][["iteration", "day", "pop_size"]].copy()
                 sub["day"] = pd.to_datetime(sub["day"])
                 sub = sub.groupby(["iteration", "day"], as_index=False)["pop_size"].max()
                 fin = state_dat[state_dat["move"] == final_move]
@@ -163,13 +198,23 @@ def _summarize(sim):
                     raise ValueError(f"No survival probability data for scenario '{scen}' species '{spc}'.")
                 sim.beta_caption = BETA_CAPTION
                 sim.beta_dict["%s_%s_%s" % (scen, spc, "whole")] = [scen, spc, "whole", *_mean_std_ci(probs)]
+                # per (move, state): one pass over the group's rows; keys in the reference's order — moves ascending, the
+                # states of a move in order of first appearance (`for l in moves: for m in rs["state"].unique()`, :3688-3749)
+                cnt_, suc_ = state_dat["count"].to_numpy(dtype=float), state_dat["successes"].to_numpy(dtype=float)
+                prob_ = np.where(cnt_ > 0, suc_ / np.where(cnt_ > 0, cnt_, 1.0), 0.0)
+                mv_ = state_dat["move"].to_numpy()
+                stc_, stl_ = _label_codes(state_dat["state"])
+                key_ = mv_.astype(np.int64) * max(len(stl_), 1) + stc_
+                uk, first, inv = np.unique(key_, return_index=True, return_inverse=True)
+                order_ = np.argsort(np.asarray(inv), kind="stable")
+                bounds = np.concatenate([[0], np.cumsum(np.bincount(np.asarray(inv), minlength=len(uk)))])
+                by_move = {}
+                for j in np.argsort(first, kind="stable"):          # (move, state) keys by first appearance
+                    by_move.setdefault(int(uk[j] // max(len(stl_), 1)), []).append(j)
                 for l in moves:
-                    rs = state_dat[state_dat["move"] == int(l)][["iteration", "day", "state", "successes", "count"]].copy()
-                    if rs.empty:
-                        continue
-                    rs["prob"] = np.where(rs["count"] > 0, rs["successes"] / rs["count"], 0.0)
-                    for m in rs["state"].unique():
-                        pv = rs[rs["state"] == m]["prob"].values
+                    for j in by_move.get(int(l), []):
+                        m = stl_[int(uk[j] % max(len(stl_), 1))]
+                        pv = prob_[order_[bounds[j]:bounds[j + 1]]]
                         if pv.size == 0:
                             continue
                         sim.beta_dict["%s_%s_%s" % (scen, spc, m)] = [scen, spc, m, *_mean_std_ci(pv)]
@@ -224,13 +269,15 @@ def yearly_summary(daily, draws_only=False, sizes=None):
     else:
         groups = daily.groupby(["species", "scenario", "iteration"])[["pop_size", "num_survived", "num_entrained"]].sum().reset_index()
         species_order, scenario_order = groups.species.unique(), groups.scenario.unique()
+    y_spc, y_spc_l = _label_codes(daily["species"])
+    y_scn, y_scn_l = _label_codes(daily["scenario"])
     for fishy in species_order:
         for scen in scenario_order:
             if draws_only and _device_for(int(sizes.get((fishy, scen), 0)), 10000) is not None:
                 continue                      # large group on the device path: its discarded bootstraps draw nothing
             out["species"].append(fishy)
             out["scenario"].append(scen)
-            day_dat = daily[(daily.species == fishy) & (daily.scenario == scen)]
+            day_dat = daily[_code_mask(y_spc, y_spc_l, str(fishy)) & _code_mask(y_scn, y_scn_l, str(scen))]
             if len(day_dat) == 0:
                 for c in cols[2:]:
                     out[c].append(0.0)
