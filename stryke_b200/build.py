@@ -25,6 +25,7 @@ def build(force=False, verbose=False):
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
     extra = ["-DSTRYKE_BOUNDS_CHECK"] if os.environ.get("STRYKE_B200_BOUNDS_CHECK") == "1" else []   # debug build: checked table indices
+    extra += os.environ.get("STRYKE_B200_NVCC_FLAGS", "").split()                                  # experiments: -DSTRYKE_COUNT_MINB=5 ...
     cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", OUT, SRC] + (["-Xptxas", "-v"] if verbose else [])
     subprocess.run(cmd, check=True)
     return OUT

@@ -132,6 +132,10 @@ __global__ void pareto_constants_kernel(const double* __restrict__ species, int 
 // the compact rows, and the zeroed rows themselves.  One launch instead of count + three scan kernels + memsets.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int COUNT_T = 256, COUNT_K = 4, COUNT_CELLS = COUNT_T * COUNT_K;      // threads, blocks of 32 cells per warp, cells per thread block
+#ifndef STRYKE_COUNT_MINB
+#define STRYKE_COUNT_MINB 4
+#endif
+constexpr int COUNT_MINB = STRYKE_COUNT_MINB;      // resident thread blocks per SM the register budget is set for (63 registers, no spills)
 // plan status words.  ERR_WORD: 0 = fine; top bits 11 = bounds check (debug build), 101 = cell_day / cell_species out of
 // range, 100 = non-finite or negative count (low 32 bits: cell); else count << 32 | cell of a cell above max_daily_fish.
 // ERR_WORK (chunk counter of the throughput kernels) and ERR_TICKET are cleared before every launch; ERR_SLOTS carries the
@@ -177,7 +181,7 @@ struct CountOut {
 // other (phase 1: draw the counts, add up the warp's tiles / fish / slots), then ONE look-back per thread block, then the
 // outputs that need the prefix (phase 2).  Four blocks per warp amortise the barrier and the look-back latency.
 template <bool INJECT>
-__global__ void __launch_bounds__(COUNT_T) count_kernel(const KParams P, const double* __restrict__ day_Q, const CountOut O,
+__global__ void __launch_bounds__(COUNT_T, COUNT_MINB) count_kernel(const KParams P, const double* __restrict__ day_Q, const CountOut O,
                                                         const int max_daily_fish, const double* __restrict__ pareto,
                                                         const ScanDev S, const int n_days, const int n_species) {
   __shared__ unsigned int s_bid;
