@@ -11,7 +11,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstryke_b200.so")
+# STRYKE_B200_LIB: file name of another build of the library in this directory (e.g. the bounds-checked debug build made
+# with `STRYKE_B200_BOUNDS_CHECK=1 python -m stryke_b200.build --out libstryke_b200_chk.so`)
+LIB_PATH = os.path.join(_HERE, os.path.basename(os.environ.get("STRYKE_B200_LIB", "") or "libstryke_b200.so"))
 
 KIND = {"a priori": 0, "Kaplan": 1, "Propeller": 2, "Francis": 3, "Pump": 4}
 ENT = {"fixed": 0, "Pareto": 1, "Log Normal": 2, "Weibull": 3, "Extreme": 4}

@@ -20,7 +20,10 @@ def needs_build():
     return not os.path.isfile(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in DEPS)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None):
+    global OUT
+    if out:
+        OUT = os.path.join(HERE, os.path.basename(out))
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
@@ -32,4 +35,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv,
+                out=sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None))

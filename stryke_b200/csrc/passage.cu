@@ -154,7 +154,7 @@ struct TallyPlan {
 static TallyPlan plan_tally(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int n_nodes);
 struct Dims { int n_nodes, n_units, n_species_staged, start_node; };
 static std::string generate(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int stride, int pr, bool baro,
-                            const TallyPlan& T, const Dims& D, bool pool);
+                            const TallyPlan& T, const Dims& D, int pool);
 static const std::vector<char>* compile(const std::string& src, std::string* err, bool fresh = false);
 static void evict(const std::string& src);
 static int load(int device, const std::string& src, const std::vector<char>& bin, cudaKernel_t* kern, std::string* err);
@@ -460,6 +460,7 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
     pl->narrow_max = (65535 - n_cause) / std::max(1, n_cause);
     // pooled remainders: 63 fish of one cell fit the packed fields when 63 * (turbine levels) <= 1023 (10-bit cause fields)
     K.pool_all = (n_cause <= 16 && !(getenv("STRYKE_B200_POOL_ALL") && atoi(getenv("STRYKE_B200_POOL_ALL")) == 32)) ? 64 : 32;
+    K.big_full = -1;               // (set below for pooled plans with owned rows)
     pl->row_w = f->n_pairs + 3;
     K.out.row_w = pl->row_w; K.out.narrow_max = pl->narrow_max; K.out.cap = 0;
   }
@@ -500,13 +501,21 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
     });
     const char* pool_env = getenv("STRYKE_B200_POOL");
     const bool pool = tally.NW > 0 && c->n_cells >= 32 && (pool_env ? pool_env[0] == '1' : small_cells);
+    // owned rows (pool_big): the rows of a block's cells are assembled in shared memory, 32 x (pairs + 3) words per warp
+    const char* own_env = getenv("STRYKE_B200_OWN");
+    const bool own = pool && f->n_pairs <= 32 && !(own_env && own_env[0] == '0');
+    {
+      const char* bf = getenv("STRYKE_B200_BIG_FULL");
+      const int v = bf ? atoi(bf) : 6;      // cells of up to 6 full tiles + a remainder (< 224 fish) are simulated by one warp
+      K.big_full = own ? std::max(0, std::min(v, POOL_BIG_FULL_MAX)) : -1;
+    }
     const char* env = getenv("STRYKE_B200_JIT");
     const bool want = o->kernel_variant == 3 || (o->kernel_variant == 0 && !(env && env[0] == '0') &&
                                                  ((env && env[0] == '1') || fish_hint >= 2.0e7));
     if (want) {
       std::vector<MoveRec> mv(pl->fast.moves, pl->fast.moves + f->n_moves);
       const std::string src = jit::generate(mv, pnode, pl->fast_stride, pl->pr, f->barotrauma != 0, tally,
-                                                jit::Dims{f->n_nodes, f->n_units, pl->n_species_staged, f->start_node}, pool);
+                                                jit::Dims{f->n_nodes, f->n_units, pl->n_species_staged, f->start_node}, pool ? (own ? 2 : 1) : 0);
       std::string err;
       const std::vector<char>* bin = jit::compile(src, &err);
       cudaKernel_t k = nullptr;
@@ -522,7 +531,7 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
         if (pool) {
           pl->pool = true;
           pl->kernel_name = "passage_spec (tables specialised with NVRTC, pooled remainders)";
-          pl->fast_smem_bytes = (size_t)fast_smem(f->n_nodes, f->n_units, pl->fast_stride, pl->n_species_staged, tally.NW, f->n_pairs).total;
+          pl->fast_smem_bytes = (size_t)fast_smem(f->n_nodes, f->n_units, pl->fast_stride, pl->n_species_staged, tally.NW, f->n_pairs, own).total;
           CK(pl->blk_S.alloc((NB + 1) * sizeof(uint32_t)));
           CK(pl->blk_tile.alloc((NB + 1) * sizeof(int64_t)));
           K.blk_S = pl->blk_S.as<uint32_t>(); K.blk_tile = pl->blk_tile.as<int64_t>();
@@ -806,8 +815,8 @@ int stryke_b200_jit_selftest(void) {
     std::string err;
     const jit::TallyPlan T = jit::plan_tally(mv, pairs, 9);
     if (!T.NW) return fail(STRYKE_E_CUDA, "packed tally layout failed for the self-test facility");
-    for (int pool = 0; pool < 2; ++pool)
-      if (!jit::compile(jit::generate(mv, pairs, 5, 1, baro != 0, T, jit::Dims{9, 3, 1, 0}, pool != 0), &err, /*fresh=*/true)) return fail(STRYKE_E_CUDA, err);
+    for (int pool = 0; pool < 3; ++pool)
+      if (!jit::compile(jit::generate(mv, pairs, 5, 1, baro != 0, T, jit::Dims{9, 3, 1, 0}, pool), &err, /*fresh=*/true)) return fail(STRYKE_E_CUDA, err);
   }
   return STRYKE_OK;
 }

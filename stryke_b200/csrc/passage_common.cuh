@@ -167,7 +167,9 @@ struct KParams {
   unsigned long long* timeline;       // debug (STRYKE_B200_TIMELINE=1): per warp of the grid: start ns, end ns, chunks, tiles
   int pool_all;                       // pooled remainders: cells below this many fish (32 or 64) are pooled entirely
   const int64_t* blk_tile;            // pooled remainders: first tile of every aligned block of 32 cells [n_blocks + 1]
-  const uint32_t* blk_S;              // pooled remainders (passage_fast.cuh): per block of 32 cells, shared tiles [0:31) | mixed [31]
+  const uint32_t* blk_S;              // pooled remainders (passage_fast.cuh): per block of 32 cells, shared tiles [0:8) | full tiles of
+                                      // its owned cells [8:24) | mixed [31]
+  int big_full;                       // pooled remainders: cells with more full tiles than this are "big" (pool_big); -1 = every cell
 };
 
 // Self-made bounds checks (compute-sanitizer is not available on the test pool): with -DSTRYKE_BOUNDS_CHECK every index
@@ -305,6 +307,18 @@ __device__ __forceinline__ int64_t warp_search_last_le(const int64_t* __restrict
 // pooled entirely: entering and leaving a cell costs more than simulating its one or two tiles.
 __host__ __device__ __forceinline__ int pool_rem(int n, int pool_all) { return n < pool_all ? n : (n & 31); }
 __host__ __device__ __forceinline__ int pool_full(int n, int pool_all) { return n < pool_all ? 0 : (n >> 5); }
+// Owned and big cells.  The tiles of a block of 32 cells are laid out as [shared tiles][full tiles of its OWNED cells][full
+// tiles of its BIG cells]; the first two parts (the block's "atomic part") are simulated by ONE warp — the one whose chunk
+// holds the block's first tile — so the compact rows of the owned cells are assembled in shared memory and written once,
+// with plain stores, into rows nobody zeroed.  Big cells (more than big_full full tiles, or too many fish for the 16-bit
+// row layout) are the ones whose tiles may be split between warps: their rows are zeroed by count_kernel and receive
+// red.global adds, as every row did before.
+__host__ __device__ __forceinline__ bool pool_big(int n, int pool_all, int big_full, int narrow_max) {
+  return pool_full(n, pool_all) > big_full || n > narrow_max;
+}
+constexpr uint32_t POOL_S_MASK = 0xffu, POOL_OWNED_SHIFT = 8, POOL_OWNED_MASK = 0xffffu, POOL_MIXED = 0x80000000u;
+constexpr int POOL_BIG_FULL_MAX = 255;      // 32 cells x 255 tiles fit POOL_OWNED_MASK
+__host__ __device__ constexpr int pool_rwp(int n_pairs) { return (n_pairs + 3) | 1; }      // padded row (odd: no bank conflicts, lane <-> cell)
 
 constexpr double P_ATM = 101325.0;    // scipy.constants.atm (stryke.py:1472)
 constexpr double G_SI = 9.80665;      // scipy.constants.g   (stryke.py:1471)

@@ -44,12 +44,13 @@ __host__ __device__ inline uint32_t pack_node(int kind, int hasU, int unit, int 
 struct FastSmem {
   int nodes, ustatic, uc1, species, warp0, warp_stride, cdf, dst, ucoef, uc0, total;
   int pool_blk, pool_ef, pool_rank, pool_seg, pool_sd, pool_full;   // per-warp scratch of the pooled-remainder path (pool_nw > 0)
+  int pool_row;                                    // ... and the rows of the block's owned cells being assembled (own)
   int pool_field;                                  // per block: where every (pair, arrivals | survivors) / Daily counter sits
 };
 // floats per row of the staged routing cdf: the stride-1 thresholds a draw is compared with, padded to whole float4s
 __host__ __device__ constexpr int cdf_row(int stride) { return stride <= 5 ? 4 : ((stride - 1 + 3) & ~3); }
 __host__ __device__ constexpr FastSmem fast_smem(int n_nodes, int n_units, int stride, int n_species_staged, int pool_nw = 0,
-                                                 int n_pairs = 0) {
+                                                 int n_pairs = 0, bool own = false) {
   FastSmem L{};
   int o = 0;
   L.nodes = o; o = (o + n_nodes * 8 + 15) & ~15;
@@ -70,6 +71,7 @@ __host__ __device__ constexpr FastSmem fast_smem(int n_nodes, int n_units, int s
     L.pool_sd = w; w += 32 * 8;                              // int2 per cell: species row, day row
     L.pool_full = w; w += 32 * 4;                            // full tiles of the cell
     L.pool_seg = w; w = (w + 32 * pool_nw * 4 + 15) & ~15;         // per cell of the block: accumulated tally words
+    if (own) { L.pool_row = w; w = (w + 32 * pool_rwp(n_pairs) * 4 + 15) & ~15; }      // per cell: its compact row (narrow layout)
   }
   L.warp_stride = w;
   L.total = o + w * WARPS;
@@ -114,6 +116,7 @@ struct RuntimeTables {
   static constexpr int N_NODES = 0, N_UNITS = 0, N_PAIRS = 0, N_SPECIES_STAGED = 0, START_NODE = 0;   // run-time (KParams)
   static constexpr int NW = 0, NF = 0, HOLD = 1, W_ES = 0, B_ES = 0, W_CAUSE = 0;   // no packed tallies: ballots per pair
   static constexpr bool POOL = false;                 // pooled remainders need the packed tallies
+  static constexpr bool OWN = false;                  // owned rows need the pooled remainders
   static __device__ __forceinline__ MoveRec move(const FastTables& FT, int k) { return FT.moves[k]; }
   static __device__ __forceinline__ int pair_node(const FastTables& FT, int p) { return (int)FT.pair_node[p]; }
   static __device__ __forceinline__ LevelTally tally(int) { return LevelTally{}; }
@@ -133,7 +136,7 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   const int n_sp = TP::kStatic ? TP::N_SPECIES_STAGED : n_species_staged;
   const int crow = cdf_row(stride);
   extern __shared__ __align__(16) unsigned char smem[];
-  const FastSmem SL = fast_smem(n_nodes, n_units, stride, n_sp, TP::POOL ? TP::NW : 0, n_pairs);
+  const FastSmem SL = fast_smem(n_nodes, n_units, stride, n_sp, TP::POOL ? TP::NW : 0, n_pairs, TP::OWN);
   uint2* s_nodes = reinterpret_cast<uint2*>(smem + SL.nodes);
   float4* s_ustatic = reinterpret_cast<float4*>(smem + SL.ustatic);     // rack, intake_vel, fb_depth, c0
   float* s_uc1 = reinterpret_cast<float*>(smem + SL.uc1);               // c1
@@ -512,10 +515,31 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   };
   fetch_chunk();
   int64_t cur_cell = -1;
+  bool cur_owned = false;                             // the current cell is an owned one (pool_big): its row is assembled in s_row
+  bool pool_dirty = false;                            // the accumulators of the current block hold something
+  constexpr int RWP = pool_rwp(TP::kStatic ? TP::N_PAIRS : 0);
+  uint32_t* s_row = TP::OWN ? reinterpret_cast<uint32_t*>(wbase + SL.pool_row) : nullptr;      // [32 cells][RWP]
   auto leave_cell = [&]() {                           // packed counters -> owners -> global tallies of the current cell
     if (cur_cell >= 0) {
       if (PK && held) { if (held == 1) drain_one_tile(); else drain(); }
-      flush(cur_cell);
+      if (TP::OWN && cur_owned) {                     // into the cell's row in shared memory (narrow layout, see tally_flush)
+        uint32_t* row = s_row + (int)(cur_cell & 31) * RWP;
+#pragma unroll
+        for (int r = 0; r < PR; ++r) {
+          const int p = r * 32 + lane;
+          if (p < n_pairs) row[3 + p] += acc_suc[r] | (acc_cnt[r] << 16);
+          acc_suc[r] = 0; acc_cnt[r] = 0;
+        }
+        const uint32_t up = __shfl_down_sync(0xffffffffu, acc_daily, 1);
+        const uint32_t w = acc_daily | (up << 16);
+        if (lane == 0) row[1] += w;                     // num_entrained | num_survived << 16
+        if (lane == 2) row[2] += w;                     // impingement | blade strike << 16
+        if (lane == 4) row[0] += acc_daily << 16;       // (pop_size) | barotrauma << 16
+        acc_daily = 0;
+        pool_dirty = true;
+      } else {
+        flush(cur_cell);
+      }
       cur_cell = -1;
     }
   };
@@ -606,21 +630,30 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   const uint32_t below = (2u << lane) - 1u;           // bits 0 .. lane
   int64_t b = -1, b_begin = 0, b_end = 0;             // current block and its tile range
   int S_b = 0, nrem = 0;                              // its shared tiles, its cells with a remainder
-  uint32_t cur_rmask = 0;                             // bit j: cell j of the block has pooled fish
-  bool pool_dirty = false;
-  auto pool_flush = [&]() {                           // accumulators of block b -> global tallies
-    if (pool_dirty) {
+  uint32_t cur_rmask = 0, cur_bigm = 0xffffffffu;     // bit j: cell j of the block has pooled fish / is big
+  int64_t a_end = 0;                                  // end of the block's atomic part
+  bool own = false;                                   // this warp is simulating the atomic part of block b
+  const int nmax_big = P.out.rows != nullptr ? (int)P.out.narrow_max : 0x7fffffff;
+  if constexpr (TP::OWN) {
+    for (int i = lane; i < 32 * RWP; i += 32) s_row[i] = 0u;
+  }
+  auto pool_flush = [&]() {                           // accumulators of block b -> global tallies (after leave_cell: an owned
+    if (pool_dirty) {                                 // cell's last tiles go into its row first)
       pool_dirty = false;
       __syncwarp();
       if (P.out.rows != nullptr) {
         // compact rows, transposed: lane <-> cell of the block.  Every lane unpacks the packed fields of ITS cell's
         // accumulator words (word and shift of every pair are compile-time constants of the facility) into the row's 16-bit
-        // pairs and adds them to its own row; cells above narrow_max take the 32-bit layout.
+        // pairs.  An owned cell's row is complete now (pooled fish here, full tiles in s_row): it is written once, with
+        // plain stores.  A big cell's pooled fish are added to its row (red.global: other warps add its full tiles); cells
+        // above narrow_max take the 32-bit layout.
         const uint32_t bm = P.out.blk_mask[b], bw = P.out.blk_wide[b];
         const uint32_t lower = (1u << lane) - 1u;
         const unsigned int slot = P.out.blk_row[b] + __popc(bm & lower) + __popc(bw & lower);
         const bool wide = (bw >> lane) & 1u;
-        if (((cur_rmask >> lane) & 1u) && slot + (wide ? 2u : 1u) <= P.out.cap) {
+        const bool big = (cur_bigm >> lane) & 1u;
+        const bool owned = TP::OWN && ((bm >> lane) & 1u) && !big;
+        if ((owned || ((cur_rmask >> lane) & 1u)) && slot + (wide ? 2u : 1u) <= P.out.cap) {
           uint32_t A[TP::NW > 0 ? TP::NW : 1];
 #pragma unroll
           for (int q = 0; q < TP::NW; ++q) A[q] = s_acc[lane * TP::NW + q];
@@ -631,7 +664,22 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
             const uint32_t cf = TP::daily_cfg(j);
             dv[j] = ((cf >> 11) & 1u) ? ((A[cf & 31u] >> ((cf >> 5) & 31u)) & (((cf >> 10) & 1u) ? 1023u : 63u)) : 0u;
           }
-          if (!wide) {
+          if (owned) {
+            const uint32_t* sr = s_row + lane * RWP;
+            row[0] = s_blk[lane].x + (dv[4] << 16) + sr[0];
+            row[1] = (dv[0] | (dv[1] << 16)) + sr[1];
+            row[2] = (dv[2] | (dv[3] << 16)) + sr[2];
+#pragma unroll
+            for (int p = 0; p < (TP::kStatic ? TP::N_PAIRS : 0); ++p) {
+              const uint32_t cf = TP::lane_cfg(p);
+              uint32_t v = 0u;
+              if ((cf >> 20) & 1u) {
+                const uint32_t cnt = (A[cf & 31u] >> ((cf >> 5) & 31u)) & 63u, suc = (A[(cf >> 10) & 31u] >> ((cf >> 15) & 31u)) & 63u;
+                v = suc | (cnt << 16);
+              }
+              row[3 + p] = v + sr[3 + p];
+            }
+          } else if (!wide) {
             const uint32_t w1 = dv[0] | (dv[1] << 16), w2 = dv[2] | (dv[3] << 16);
             if (w1) atomicAdd(row + 1, w1);
             if (w2) atomicAdd(row + 2, w2);
@@ -657,6 +705,11 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
               if (cnt) atomicAdd(row + 7 + 2 * p, cnt);
             }
           }
+        }
+        if constexpr (TP::OWN) {
+          __syncwarp();
+#pragma unroll
+          for (int w = 0; w < RWP; ++w) s_row[lane * RWP + w] = 0u;
         }
       } else {
       for (int i0 = 0; i0 < NI; i0 += 32) {           // lane <-> counter i0 + lane, loop over the cells with a remainder
@@ -684,32 +737,45 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
     }
   };
   auto clamp30 = [](long long x) -> int { return x < (long long)(1 << 30) ? (int)x : (1 << 30); };
-  for (;;) {
-  const int64_t t0 = nx0;
-  if (t0 >= T) break;
-  const int64_t t1 = nx1 < T ? nx1 : T;
-  tl_chunks += 1; tl_tiles += (unsigned long long)(t1 - t0);
-  bool fetched = false;     // the next chunk is fetched near the END of this one (see PREFETCH_TILES)
+  // One loop, one decision per run: what is the next tile (a new chunk? next block? a shared tile? full tiles of which
+  // cell?), then `run` tiles with nothing to decide between them.  (One loop rather than chunks x runs so that leave_cell
+  // and pool_flush, with the drains and flushes inlined into them, exist once in the code: the kernel is I-cache bound
+  // outside its inner loop.)  A chunk is [t0, t1) — except that the atomic part of a block (pool_big) goes, whole, to the
+  // warp whose chunk holds the block's first tile: t_lim moves past t1 to the end of an atomic part this warp has started,
+  // and an atomic part that began before t0 is skipped (its owner runs or has run past its own t1).
+  int64_t t = 0, t_lim = 0;                           // next tile; first tile this warp does not simulate
+  bool fetched = true;                                // nx0 / nx1 hold a chunk that has not been taken yet
   bool new_block = false;
-  if (t0 < b_begin || t0 >= b_end) {                  // last block with blk_off <= t0 (blocks without fish have empty ranges)
-    pool_flush();
-    b = warp_search_last_le(P.blk_tile, (b >= 0 && t0 >= b_end) ? b : 0, NB, t0, lane);      // (chunks are handed out in increasing order)
-    b_begin = blk_off(b); b_end = blk_off(b + 1);
-    new_block = true;
-  }
-  // One decision per run: what is the next tile (next block? a shared tile? full tiles of which cell?), then `run` tiles
-  // with nothing to decide between them.
-  int chunk_left = (int)(t1 - t0);                    // tiles of the chunk not yet handed to a run
-  int64_t t = t0;                                     // first tile after the current run
-  while (chunk_left > 0) {
+  for (;;) {
+    bool done = false, search = false;
+    if (t >= t_lim) {                                 // the chunk is finished: take the next one
+      if (!fetched) fetch_chunk();
+      const int64_t t0 = nx0;
+      if (t0 >= T) {
+        done = true;
+      } else {
+        t = t0; t_lim = nx1 < T ? nx1 : T;
+        tl_chunks += 1; tl_tiles += (unsigned long long)(t_lim - t0);
+        fetched = false;                              // its successor is fetched near the END of this one (see PREFETCH_TILES)
+        own = false;
+        search = t0 < b_begin || t0 >= b_end;         // (else: still inside the block where the last chunk ended)
+      }
+    }
     leave_cell();
-    if (t >= b_end) {
+    if (done || search || t >= b_end) {
       pool_flush();
-      do { ++b; b_begin = b_end; b_end = blk_off(b + 1); } while (b_end == b_begin);
+      if (done) break;
+      if (search) {      // last block with blk_off <= t (blocks without fish have empty ranges; chunks are handed out in increasing order)
+        b = warp_search_last_le(P.blk_tile, (b >= 0 && t >= b_end) ? b : 0, NB, t, lane);
+        b_begin = blk_off(b); b_end = blk_off(b + 1);
+      } else {
+        do { ++b; b_begin = b_end; b_end = blk_off(b + 1); } while (b_end == b_begin);
+      }
       new_block = true;
     }
     if (new_block) {
       new_block = false;
+      own = false;
       STRYKE_BCHK(P, b >= 0 && b < NB, 8);
       const int64_t ci = (b << 5) + lane;
       const bool in = ci < P.n_cells;
@@ -720,91 +786,96 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
       if (in) cinf = cell_at(P, gcur, ci);
       const uint64_t id = cinf.id;
       const uint32_t info = P.blk_S[b];
-      S_b = (int)(info & 0x7fffffffu);
+      S_b = (int)(info & POOL_S_MASK);
+      const int owned_full = (int)((info >> POOL_OWNED_SHIFT) & POOL_OWNED_MASK);
+      a_end = b_begin + S_b + owned_full;
       const int r = pool_rem(n, P.pool_all), f = pool_full(n, P.pool_all);
-      const int pr = (info >> 31) ? ((r + 31) & ~31) : r;   // mixed block: every remainder is padded to whole tiles of its own
-      int sr = pr;
-      long long sf = f;
+      const bool big = pool_big(n, P.pool_all, P.big_full, nmax_big);
+      const int pr = (info & POOL_MIXED) ? ((r + 31) & ~31) : r;   // mixed block: every remainder is padded to whole tiles of its own
+      int sr = pr, so = big ? 0 : f;                      // prefix sums: pooled fish, full tiles of the owned cells ...
+      long long sb = big ? f : 0;                         // ... and of the big ones, which come after them
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int tr = __shfl_up_sync(0xffffffffu, sr, o);
-        const long long tf = __shfl_up_sync(0xffffffffu, sf, o);
-        if (lane >= o) { sr += tr; sf += tf; }
+        const int tr = __shfl_up_sync(0xffffffffu, sr, o), to = __shfl_up_sync(0xffffffffu, so, o);
+        const long long tb = __shfl_up_sync(0xffffffffu, sb, o);
+        if (lane >= o) { sr += tr; so += to; sb += tb; }
       }
       const uint32_t rmask = __ballot_sync(0xffffffffu, r > 0);      // cells with pooled fish
       nrem = __popc(rmask);
       cur_rmask = rmask;
+      cur_bigm = __ballot_sync(0xffffffffu, big);
+      STRYKE_BCHK(P, __shfl_sync(0xffffffffu, so, 31) == owned_full, 14);
       __syncwarp();
       s_blk[lane] = make_uint4((uint32_t)n, (uint32_t)id, (uint32_t)(id >> 32), (uint32_t)(sr - pr));
-      s_ef[lane] = sf - f;
+      s_ef[lane] = big ? (long long)owned_full + (sb - f) : (long long)(so - f);      // first full tile of the cell within the block's full tiles
       s_full[lane] = f;
       s_sd[lane] = make_int2(cinf.species, cinf.day);
       if (r > 0) s_rank[__popc(rmask & (below >> 1))] = lane;
       __syncwarp();
     }
-    const int64_t j = t - b_begin;
-    const bool shared = j < (int64_t)S_b;
-    int run, fish, n_lim, jl = 0;
-    uint32_t cid_lo, cid_hi;
-    if (shared) {
-      // shared tile j: positions [base, base + 32) of the block's concatenated remainders.  M: cells whose remainder
-      // starts in this tile (bit = lane of its first fish); jl: lane (within the block) of the cell of this lane's fish
-      run = 1;
-      const int base = (int)j << 5;
-      const uint4 mine = s_blk[lane];
-      const int rel = (int)mine.w - base;
-      const bool has_r = pool_rem((int)mine.x, P.pool_all) != 0;
-      const uint32_t M = __reduce_or_sync(0xffffffffu, (has_r && (unsigned)rel < 32u) ? (1u << rel) : 0u);
-      const int K0 = __popc(__ballot_sync(0xffffffffu, has_r && rel < 0));     // remainders that start before the tile
-      const int rank = K0 + __popc(M & below) - 1;
-      STRYKE_BCHK(P, rank >= 0 && rank < nrem, 9);
-      jl = s_rank[rank];
-      STRYKE_BCHK(P, jl >= 0 && jl < 32, 10);
-      const uint4 cellrec = s_blk[jl];
-      n_lim = (int)cellrec.x;
-      const int own = pool_full(n_lim, P.pool_all) << 5;      // fish of the cell's own full tiles come first
-      fish = own + (base + lane - (int)cellrec.w);
-      STRYKE_BCHK(P, fish >= own && (lane != 0 || fish < n_lim), 11);
-      cid_lo = cellrec.y; cid_hi = cellrec.z;
-      const int2 sd = s_sd[__shfl_sync(0xffffffffu, jl, 0)];
-      load_params(sd.x, sd.y);
-    } else {                                          // full tile jj of the block: which cell?
-      const long long jj = j - S_b;
-      const long long ef = s_ef[lane];
-      const int f = s_full[lane];
-      const int sel = __ffs(__ballot_sync(0xffffffffu, f > 0 && jj >= ef && jj < ef + f)) - 1;
-      STRYKE_BCHK(P, sel >= 0 && sel < 32, 13);
-      const long long ef_s = s_ef[sel];
-      const uint4 cellrec = s_blk[sel];
-      run = __shfl_sync(0xffffffffu, clamp30(ef_s + (long long)s_full[sel] - jj), 0);
-      run = run < chunk_left ? run : chunk_left;
-      fish = __shfl_sync(0xffffffffu, (int)(jj - ef_s) * 32, 0) + lane;
-      n_lim = 0x7fffffff;                             // full tiles: every lane has a fish
-      cur_cell = (b << 5) + sel;
-      cid_lo = cellrec.y; cid_hi = cellrec.z;
-      const int2 sd = s_sd[sel];
-      load_params(sd.x, sd.y);
+    if (t < a_end && !own) {
+      if (t == b_begin) { own = true; t_lim = t_lim > a_end ? t_lim : a_end; }
+      else { t = a_end; continue; }
     }
-    chunk_left -= run;
-    t += run;
-    if (!fetched && chunk_left <= PREFETCH_TILES) { fetch_chunk(); fetched = true; }
-    simulate_run(run, fish, n_lim, cid_lo, cid_hi);
-    if (shared) {                                     // the shared tile's counters: whole words into the per-cell accumulators
-      uint32_t* row = s_acc + jl * TP::NW;
+    if (t == b_begin && S_b > 0) {
+      // The block's shared tiles (this warp owns them: they open the atomic part), all in one go.  Shared tile js holds
+      // positions [32 js, 32 js + 32) of the block's concatenated remainders.  M: cells whose remainder starts in this tile
+      // (bit = lane of its first fish); jl: lane (within the block) of the cell of this lane's fish.  The tile's per-lane
+      // counters go, whole words, into the per-cell accumulators.
+      const uint4 mine = s_blk[lane];
+      int rel = pool_rem((int)mine.x, P.pool_all) != 0 ? (int)mine.w : 0x40000000;   // first pooled fish of MY cell, relative to the tile
+#pragma unroll 1
+      for (int js = 0; js < S_b; ++js, rel -= 32) {
+        const uint32_t M = __reduce_or_sync(0xffffffffu, (unsigned)rel < 32u ? (1u << rel) : 0u);
+        const int K0 = __popc(__ballot_sync(0xffffffffu, rel < 0));            // remainders that start before the tile
+        const int rank = K0 + __popc(M & below) - 1;
+        STRYKE_BCHK(P, rank >= 0 && rank < nrem, 9);
+        const int jl = s_rank[rank];
+        STRYKE_BCHK(P, jl >= 0 && jl < 32, 10);
+        const uint4 cellrec = s_blk[jl];
+        const int n = (int)cellrec.x;
+        const int own_fish = pool_full(n, P.pool_all) << 5;        // fish of the cell's own full tiles come first
+        const int fish = own_fish + ((js << 5) + lane - (int)cellrec.w);
+        STRYKE_BCHK(P, fish >= own_fish && (lane != 0 || fish < n), 11);
+        const int2 sd = s_sd[__shfl_sync(0xffffffffu, jl, 0)];
+        load_params(sd.x, sd.y);
+        simulate(fish, fish < n, cellrec.y, cellrec.z);
+        uint32_t* row = s_acc + jl * TP::NW;
 #pragma unroll
-      for (int q = 0; q < TP::NW; ++q) {
-        if (W[q]) atomicAdd(row + q, W[q]);
-        W[q] = 0;
+        for (int q = 0; q < TP::NW; ++q) {
+          if (W[q]) atomicAdd(row + q, W[q]);
+          W[q] = 0;
+        }
       }
       held = 0;
       pool_dirty = true;
+      t += S_b;
+      if (!fetched && t_lim - t <= PREFETCH_TILES) { fetch_chunk(); fetched = true; }
+      continue;
     }
+    // full tile jj of the block: which cell?  Its tiles up to the end of the cell (or of what this warp may take) are one run.
+    const long long jj = t - b_begin - S_b;
+    const long long ef = s_ef[lane];
+    const int f = s_full[lane];
+    const int sel = __ffs(__ballot_sync(0xffffffffu, f > 0 && jj >= ef && jj < ef + f)) - 1;
+    STRYKE_BCHK(P, sel >= 0 && sel < 32, 13);
+    const long long ef_s = s_ef[sel];
+    const uint4 cellrec = s_blk[sel];
+    int run = __shfl_sync(0xffffffffu, clamp30(ef_s + (long long)s_full[sel] - jj), 0);
+    const int room = clamp30(t_lim - t);
+    run = run < room ? run : room;
+    const int fish = __shfl_sync(0xffffffffu, (int)(jj - ef_s) * 32, 0) + lane;
+    cur_cell = (b << 5) + sel;
+    cur_owned = TP::OWN && P.out.rows != nullptr && !((cur_bigm >> sel) & 1u);
+    STRYKE_BCHK(P, !cur_owned || (own && t + run <= a_end), 15);
+    const int2 sd = s_sd[sel];
+    load_params(sd.x, sd.y);
+    t += run;
+    if (!fetched && t_lim - t <= PREFETCH_TILES) { fetch_chunk(); fetched = true; }
+    simulate_run(run, fish, 0x7fffffff, cellrec.y, cellrec.z);      // (full tiles: every lane has a fish)
   }
-  if (!fetched) fetch_chunk();
   }
-  pool_flush();
-  }
-  leave_cell();
+  if constexpr (!TP::POOL) leave_cell();
   if (P.timeline && lane == 0) {
     unsigned long long tl_end;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tl_end));

@@ -99,12 +99,13 @@ __device__ __forceinline__ double std_normal(double u1_oc, double u2_co) {
 // end with those of the other cells of its block and cut into shared tiles.  A block whose cells differ in species or
 // day ("mixed") keeps one tile per remainder instead (the day tables and species parameters are warp-uniform).  Returns
 // the block's number of shared tiles (bit 31: mixed).  Called by all 32 lanes; lanes past the last cell pass in = false.
-__device__ __forceinline__ uint32_t pool_block(bool in, int n, int sp, int dy, int pool_all) {
+__device__ __forceinline__ uint32_t pool_block(bool in, int n, int sp, int dy, int pool_all, int big_full, int narrow_max) {
   const int sp0 = __shfl_sync(0xffffffffu, sp, 0), dy0 = __shfl_sync(0xffffffffu, dy, 0);
   const bool mixed = __ballot_sync(0xffffffffu, in && (sp != sp0 || dy != dy0)) != 0u;
   const int r = pool_rem(n, pool_all);
   const uint32_t tot = __reduce_add_sync(0xffffffffu, mixed ? (uint32_t)((r + 31) & ~31) : (uint32_t)r);
-  return ((tot + 31u) >> 5) | (mixed ? 0x80000000u : 0u);
+  const uint32_t owned = __reduce_add_sync(0xffffffffu, pool_big(n, pool_all, big_full, narrow_max) ? 0u : (uint32_t)pool_full(n, pool_all));
+  return ((tot + 31u) >> 5) | (owned << POOL_OWNED_SHIFT) | (mixed ? POOL_MIXED : 0u);
 }
 
 // Per-species constants of the truncated Pareto draw (truncated_rvs, stryke.py:75-106): the upper truncation point, the
@@ -304,13 +305,13 @@ __global__ void __launch_bounds__(COUNT_T, COUNT_MINB) count_kernel(const KParam
   const uint32_t mask = __ballot_sync(0xffffffffu, n_c > 0);
   const uint32_t wmask = P.out.rows ? __ballot_sync(0xffffffffu, n_c > P.out.narrow_max) : 0u;
   uint32_t info = 0;
-  if (O.blk_S) info = pool_block(in, n_c, species_c, day_c, P.pool_all);
+  if (O.blk_S) info = pool_block(in, n_c, species_c, day_c, P.pool_all, P.big_full, P.out.rows ? P.out.narrow_max : 0x7fffffff);
   if (lane == 0) s_info[lc >> 5] = info;
   long long t = O.blk_S ? (long long)pool_full(n_c, P.pool_all) : (long long)((n_c + 31) >> 5);
   long long f = n_c;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { t += __shfl_xor_sync(0xffffffffu, t, o); f += __shfl_xor_sync(0xffffffffu, f, o); }
-  tw += t + (long long)(info & 0x7fffffffu); fw += f; sw += P.out.rows ? __popc(mask) + __popc(wmask) : 0;
+  tw += t + (long long)(info & POOL_S_MASK); fw += f; sw += P.out.rows ? __popc(mask) + __popc(wmask) : 0;
   }
   if (lane == 0) { s_w[wid][0] = tw; s_w[wid][1] = fw; s_w[wid][2] = sw; }
   __syncthreads();
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(COUNT_T, COUNT_MINB) count_kernel(const KParam
     const uint32_t mask = __ballot_sync(0xffffffffu, n_c > 0);
     const uint32_t wmask = P.out.rows ? __ballot_sync(0xffffffffu, n_c > P.out.narrow_max) : 0u;
     const int slots_w = P.out.rows ? __popc(mask) + __popc(wmask) : 0;
-    long long t = O.blk_S ? (long long)pool_full(n_c, P.pool_all) + (lane == 0 ? (long long)(info & 0x7fffffffu) : 0ll) : (long long)((n_c + 31) >> 5);
+    long long t = O.blk_S ? (long long)pool_full(n_c, P.pool_all) + (lane == 0 ? (long long)(info & POOL_S_MASK) : 0ll) : (long long)((n_c + 31) >> 5);
     long long f = n_c;
     const long long t_own = t, f_own = f;
 #pragma unroll
@@ -397,16 +398,26 @@ __global__ void __launch_bounds__(COUNT_T, COUNT_MINB) count_kernel(const KParam
     }
     if (P.out.rows && blk_in) {
       if (lane == 0) { P.out.blk_row[blk] = (uint32_t)bs; P.out.blk_mask[blk] = mask; P.out.blk_wide[blk] = wmask; }
-      const unsigned long long w0 = (unsigned long long)bs * (unsigned long long)P.out.row_w;
+      // Rows that receive red.global adds are zeroed here, and their cell's count goes into word 0: every row of a plan
+      // without pooled remainders, the rows of the big cells of a pooled one (the owned cells' rows are written whole, once,
+      // by the warp that simulates the block: passage_fast.cuh).
+      const bool big = n_c > 0 && (!O.blk_S || pool_big(n_c, P.pool_all, P.big_full, P.out.narrow_max));
+      const uint32_t bigm = __ballot_sync(0xffffffffu, big);
       const unsigned long long cap_w = (unsigned long long)P.out.cap * (unsigned long long)P.out.row_w;
-      const int nw = slots_w * P.out.row_w;
-      for (int i = lane; i < nw; i += 32)
-        if (w0 + i < cap_w) P.out.rows[w0 + i] = 0u;
-      __syncwarp();
-      if (n_c > 0) {
-        const unsigned long long slot = (unsigned long long)bs + __popc(mask & below) + __popc(wmask & below);
-        if (slot + ((wmask >> lane) & 1u) < (unsigned long long)P.out.cap) P.out.rows[slot * P.out.row_w] = (uint32_t)n_c;
+      const unsigned long long slot = (unsigned long long)bs + __popc(mask & below) + __popc(wmask & below);
+      if (bigm == mask) {                                    // all of them: one coalesced sweep over the block's rows
+        const unsigned long long w0 = (unsigned long long)bs * (unsigned long long)P.out.row_w;
+        const int nw = slots_w * P.out.row_w;
+        for (int i = lane; i < nw; i += 32)
+          if (w0 + i < cap_w) P.out.rows[w0 + i] = 0u;
+        __syncwarp();
+      } else if (big) {
+        const unsigned long long w0 = slot * (unsigned long long)P.out.row_w;
+        const int nw = (((wmask >> lane) & 1u) ? 2 : 1) * P.out.row_w;
+        for (int i = 1; i < nw; ++i)
+          if (w0 + i < cap_w) P.out.rows[w0 + i] = 0u;
       }
+      if (big && slot + ((wmask >> lane) & 1u) < (unsigned long long)P.out.cap) P.out.rows[slot * P.out.row_w] = (uint32_t)n_c;
     }
     bt += __shfl_sync(0xffffffffu, t, 31); bf += __shfl_sync(0xffffffffu, f, 31); bs += slots_w;
   }

@@ -145,7 +145,7 @@ static int spec_min_blocks() {
 
 // The table provider + kernel entry for one plan.
 static std::string generate(const std::vector<MoveRec>& moves, const std::vector<uint8_t>& pairs, int stride, int pr, bool baro,
-                            const TallyPlan& T, const Dims& D, bool pool) {
+                            const TallyPlan& T, const Dims& D, int pool) {      // pool: 0 no, 1 pooled remainders, 2 + owned rows
   std::ostringstream o;
   const int M = (int)moves.size(), P = (int)pairs.size();
   o << "#define STRYKE_NVRTC 1\n";
@@ -168,7 +168,7 @@ static std::string generate(const std::vector<MoveRec>& moves, const std::vector
     << ", N_SPECIES_STAGED = " << D.n_species_staged << ", START_NODE = " << D.start_node << ";\n"
     << "  static constexpr int NW = " << T.NW << ", NF = " << (T.NW ? (int)T.fields.size() : 0) << ", HOLD = " << T.HOLD
     << ", W_ES = " << T.W_ES << ", B_ES = " << T.B_ES << ", W_CAUSE = " << T.W_CAUSE << ";\n"
-    << "  static constexpr bool POOL = " << (pool && T.NW ? "true" : "false") << ";\n"
+    << "  static constexpr bool POOL = " << (pool && T.NW ? "true" : "false") << ", OWN = " << (pool == 2 && T.NW ? "true" : "false") << ";\n"
     << "  static __device__ constexpr MoveRec move(const FastTables&, int k) {\n    constexpr MoveRec T[" << M << "] = {";
   for (int k = 0; k < M; ++k) {
     const MoveRec& m = moves[k];

@@ -151,3 +151,25 @@ def test_cell_tables_out_of_range_are_reported():
     day[3] = 99
     with pytest.raises(_abi.StrykeError, match="out of range"):
         engine.run_cells(plan.fac, plan.days, plan.species_table, day, plan.cell_species, plan.cell_id, precision=32, seed=1)
+
+
+@pytest.mark.parametrize("big_full,own,chunk", [("0", "1", ("8", "2")), ("1", "1", ("3", "1")), ("6", "1", None), ("255", "1", ("64", "8")),
+                                                ("6", "0", ("16", "4"))])
+def test_owned_rows_equal_the_dense_tallies(monkeypatch, big_full, own, chunk):
+    """Pooled plans write the rows of their 'owned' cells (at most big_full full tiles) once, from the warp that simulates the
+    block's atomic part, and add into zeroed rows only for big cells: whatever the threshold, the chunk sizes (which move the
+    ownership boundaries) and the slabs, the rows must hold the dense tallies."""
+    monkeypatch.setenv("STRYKE_B200_BIG_FULL", big_full)
+    monkeypatch.setenv("STRYKE_B200_OWN", own)
+    if chunk:
+        monkeypatch.setenv("STRYKE_B200_CHUNK_TILES", chunk[0])
+        monkeypatch.setenv("STRYKE_B200_CHUNK_MIN", chunk[1])
+    prj = fixtures.c3_population(n_species=4, iterations=300, days=6, extreme=True)
+    sim, plan = G.make_plan(prj, "own")
+    want = dense(plan, variant=2)                     # generic tables, no pooling
+    got = compact(plan, variant=3)
+    same(got.dense(), want)
+    same(dense(plan, variant=3), want)                # the same kernel writing the dense layout
+    same(compact(plan, variant=3, n_slabs=3).dense(), want)
+    # narrow cap: cells above it take the 32-bit layout and count as big
+    same(compact(plan, variant=3, seed=11).dense(), dense(plan, variant=2, seed=11))
