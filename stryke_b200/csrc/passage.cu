@@ -506,7 +506,7 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
     const bool own = pool && f->n_pairs <= 32 && !(own_env && own_env[0] == '0');
     {
       const char* bf = getenv("STRYKE_B200_BIG_FULL");
-      const int v = bf ? atoi(bf) : 6;      // cells of up to 6 full tiles + a remainder (< 224 fish) are simulated by one warp
+      const int v = bf ? atoi(bf) : 16;     // cells of up to 16 full tiles + a remainder (< 544 fish) are simulated by one warp
       K.big_full = own ? std::max(0, std::min(v, POOL_BIG_FULL_MAX)) : -1;
     }
     const char* env = getenv("STRYKE_B200_JIT");
@@ -535,6 +535,9 @@ int stryke_b200_plan_create(const StrykeFacility* f, const StrykeDayTables* d, c
           CK(pl->blk_S.alloc((NB + 1) * sizeof(uint32_t)));
           CK(pl->blk_tile.alloc((NB + 1) * sizeof(int64_t)));
           K.blk_S = pl->blk_S.as<uint32_t>(); K.blk_tile = pl->blk_tile.as<int64_t>();
+          // chunks end inside blocks of 32 cells, whose set-up is then paid twice: longer chunks than for big cells (measured
+          // on C3, 4 launches per step: 64 tiles 21.1 ms, 128 20.0, 256 19.7, 512 20.1, 1024 21.3 — the tail grows)
+          if (!getenv("STRYKE_B200_CHUNK_TILES")) K.chunk_tiles = 256;
         }
       } else if (o->kernel_variant == 3) {
         return fail(STRYKE_E_CUDA, "kernel specialisation failed: " + err);

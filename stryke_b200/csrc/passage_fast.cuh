@@ -45,6 +45,7 @@ struct FastSmem {
   int nodes, ustatic, uc1, species, warp0, warp_stride, cdf, dst, ucoef, uc0, total;
   int pool_blk, pool_ef, pool_rank, pool_seg, pool_sd, pool_full;   // per-warp scratch of the pooled-remainder path (pool_nw > 0)
   int pool_row;                                    // ... and the rows of the block's owned cells being assembled (own)
+  int pool_gcur;                                   // ... and the group cursor of the last block (cell groups)
   int pool_field;                                  // per block: where every (pair, arrivals | survivors) / Daily counter sits
 };
 // floats per row of the staged routing cdf: the stride-1 thresholds a draw is compared with, padded to whole float4s
@@ -72,6 +73,7 @@ __host__ __device__ constexpr FastSmem fast_smem(int n_nodes, int n_units, int s
     L.pool_full = w; w += 32 * 4;                            // full tiles of the cell
     L.pool_seg = w; w = (w + 32 * pool_nw * 4 + 15) & ~15;         // per cell of the block: accumulated tally words
     if (own) { L.pool_row = w; w = (w + 32 * pool_rwp(n_pairs) * 4 + 15) & ~15; }      // per cell: its compact row (narrow layout)
+    L.pool_gcur = w; w += 64;                                // GroupCursor
   }
   L.warp_stride = w;
   L.total = o + w * WARPS;
@@ -637,6 +639,10 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
   if constexpr (TP::OWN) {
     for (int i = lane; i < 32 * RWP; i += 32) s_row[i] = 0u;
   }
+  static_assert(sizeof(GroupCursor) <= 64, "GroupCursor slot");
+  GroupCursor* s_gcur = reinterpret_cast<GroupCursor*>(wbase + SL.pool_gcur);
+  *s_gcur = GroupCursor{};                            // (base = end = 0: no group yet)
+  __syncwarp();
   auto pool_flush = [&]() {                           // accumulators of block b -> global tallies (after leave_cell: an owned
     if (pool_dirty) {                                 // cell's last tiles go into its row first)
       pool_dirty = false;
@@ -782,7 +788,16 @@ __device__ __forceinline__ void passage_fast_body(const KParams& P, const FastTa
       const int n = in ? P.cell_n[ci] : 0;
       CellInfo cinf{0, 0, 0ull};
       GroupCursor gcur{};
-      if (P.groups != nullptr) gcur = group_cursor(P, b << 5);      // warp-uniform: one search for the block's first cell
+      if (P.groups != nullptr) {      // warp-uniform: the group of the block's first cell — nearly always the last block's group
+        gcur = *s_gcur;
+        const int64_t c0 = b << 5;
+        if (c0 < gcur.base || c0 >= gcur.end || c0 - gcur.base > 0x3fffff00ll) {
+          gcur = group_cursor(P, c0);
+          __syncwarp();
+          *s_gcur = gcur;
+          __syncwarp();
+        }
+      }
       if (in) cinf = cell_at(P, gcur, ci);
       const uint64_t id = cinf.id;
       const uint32_t info = P.blk_S[b];

@@ -54,19 +54,19 @@ def expected_slots(grid, species, margin=1.08, extra=4096):
     return int(tot) + extra
 
 
-SLAB_ROW_BYTES = 64 << 20      # rows of one slab: about half of the 126 MB L2
+N_SLABS = 4
 
 
 def default_slab_cells(n_cells, rows_bytes):
-    """Cells per slab (a multiple of ALIGN).  Large lists are cut into at least 4 slabs (the export of one slab runs under
-    the kernels of the next; every launch costs ~0.1 ms of chunk starts and tail, so not more than needed) and into as many
-    as keep a slab's rows near SLAB_ROW_BYTES: the rows count_kernel zeroes are then still in L2 when the passage kernel
-    adds to them — DRAM never reads them back (measured: 125 MB read per 8th of C3 -> 1 MB per 16th)."""
+    """Cells per slab (a multiple of ALIGN).  Large lists are cut into N_SLABS slabs: the export of one slab runs under the
+    kernels of the next, and every launch costs ~0.1 ms of chunk starts and tail, so not more than that needs.  (Round 2
+    first sized slabs for L2 — 16 on C3 — so that the rows count_kernel zeroed were still cached when the passage kernel
+    added to them; pooled plans now write the rows of their owned cells once and nothing is zeroed for them.)"""
     import os
     n_cells = max(int(n_cells), 1)
     if n_cells < (1 << 18):
         return max(ALIGN, -(-n_cells // ALIGN) * ALIGN)
-    n_slabs = min(64, max(4, -(-int(rows_bytes) // SLAB_ROW_BYTES)))
+    n_slabs = N_SLABS
     if os.environ.get("STRYKE_B200_SLABS"):
         n_slabs = max(1, int(os.environ["STRYKE_B200_SLABS"]))
     return max(ALIGN, -(-n_cells // n_slabs // ALIGN) * ALIGN)
