@@ -232,7 +232,7 @@ def measure(name, args, rank, local_rank, world, sampler, main):
     import torch
     import torch.distributed as dist
     from stryke_b200 import engine, workloads as W
-    from stryke_b200.distributed import ShardedRun
+    from stryke_b200.distributed import SLAB_SHARES, ShardedRun, slab_plan
     n_fish, iterations, days = DEFAULTS[name]
     if main:
         n_fish = args.fish if args.fish is not None else n_fish
@@ -260,8 +260,7 @@ def measure(name, args, rank, local_rank, world, sampler, main):
     while True:
         run = ShardedRun(plan_h.fac, plan_h.days, species, grid, rank, world, local_rank, precision=args.precision, seed=0x5EED,
                          max_daily_fish=2_000_000_000, kernel_variant=args.kernel_variant, n_cells_max=n_max,
-                         slab_cap=None if cap_scale == 1.0 else int(cap_scale * run_cap))
-        run_cap = run.L.slab_cap
+                         slabs=slab_plan(grids, species, n_max, shares=SLAB_SHARES if world > 1 else (0.25,) * 4, scale=cap_scale))
         flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream()
         for i in range(args.warmup):
@@ -329,8 +328,7 @@ def measure(name, args, rank, local_rank, world, sampler, main):
             prof = json.load(fh)
     executed = prof.get("warp_inst_per_fish")      # executed warp instructions per simulated fish under ncu (x 32 lanes)
     rows_bytes = None
-    slots_used = int(run.slots_after.cpu().numpy()[:run.L.n_slabs].astype(np.int64).sum()
-                     - sum(k * run.L.slab_cap for k in range(run.L.n_slabs) if k * run.L.slab_cells < run.n_cells))
+    slots_used = run.slots_used()
     rows_bytes = slots_used * run.L.W * 4
     algo_bytes = run.n_cells * 4 + rows_bytes + ((run.n_cells + 31) // 32) * 12
     roofline = {"bound": "issue", "achieved": achieved / 1e12, "peak": peak_ops / 1e12, "unit": "Tlane-op/s",

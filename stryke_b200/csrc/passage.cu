@@ -927,14 +927,27 @@ int stryke_b200_run_compact(const StrykeFacility* f, const StrykeDayTables* d, c
   DevBuf dn, dr, tot;
   CK(dn.alloc((size_t)C * 4));
   CK(dr.alloc((size_t)std::max<int64_t>(out->rows_cap, 1) * row_bytes));
-  // slabs: at least 8 on large lists (copies overlap kernels), and enough to keep one slab's rows (about half the capacity the
-  // caller expects to fill) near 64 MB, so that the rows zeroed by count_kernel are still in L2 when the passage kernel adds to them
-  int n_slabs = out->n_slabs > 0 ? out->n_slabs : (C >= (1 << 20) ? 8 : C >= (1 << 16) ? 2 : 1);
-  if (out->n_slabs <= 0 && C >= (1 << 20))
-    n_slabs = (int)std::min<int64_t>(64, std::max<int64_t>(8, (int64_t)(((size_t)out->rows_cap * row_bytes) >> 26)));
-  int64_t per = ((C + n_slabs - 1) / n_slabs + COUNT_CELLS - 1) / COUNT_CELLS * COUNT_CELLS;
-  if (per < COUNT_CELLS) per = COUNT_CELLS;
-  n_slabs = (int)((C + per - 1) / per);
+  // Slabs of cells: the copy of one slab's rows to the host runs under the kernels of the slabs that follow; only the last
+  // copy is exposed.  Large lists: seven equal slabs, then three that halve (the last holds 1/63 of the cells); every launch
+  // costs ~0.1 ms of ramp and tail, so not more.  A caller's n_slabs gives equal slabs.
+  std::vector<int64_t> bound;        // slab k = cells [bound[k], bound[k + 1]), multiples of COUNT_CELLS
+  {
+    std::vector<double> w;
+    if (out->n_slabs > 0) w.assign((size_t)out->n_slabs, 1.0);
+    else if (C >= (1 << 20)) w = {1, 1, 1, 1, 1, 1, 1, 0.5, 0.25, 0.125};
+    else w.assign(C >= (1 << 16) ? 2 : 1, 1.0);
+    double tot_w = 0.0, acc = 0.0;
+    for (double x : w) tot_w += x;
+    bound.push_back(0);
+    for (size_t k = 0; k < w.size(); ++k) {
+      acc += w[k];
+      int64_t e = k + 1 == w.size() ? C : (int64_t)((double)C * (acc / tot_w));
+      e = std::min<int64_t>(C, (e + COUNT_CELLS - 1) / COUNT_CELLS * COUNT_CELLS);
+      if (e > bound.back()) bound.push_back(e);
+    }
+    if (bound.back() < C) bound.push_back(C);
+  }
+  const int n_slabs = (int)bound.size() - 1;
   cudaStream_t comp = nullptr, copy = nullptr;
   CK(cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
@@ -950,7 +963,7 @@ int stryke_b200_run_compact(const StrykeFacility* f, const StrykeDayTables* d, c
   }
   // the plan was built on the legacy default stream and is complete (plan_create synchronised); queue every slab
   for (int k = 0; k < n_slabs; ++k) {
-    const int64_t lo = (int64_t)k * per, hi = std::min<int64_t>(C, lo + per);
+    const int64_t lo = bound[(size_t)k], hi = bound[(size_t)k + 1];
     rc = launch_cells(pl, lo, hi, dn.as<int32_t>(), nullptr, nullptr, dr.as<uint32_t>(), out->rows_cap, k == 0 ? 0 : -1, comp,
                       tot.as<unsigned long long>() + k);
     if (rc) return rc;
@@ -960,7 +973,7 @@ int stryke_b200_run_compact(const StrykeFacility* f, const StrykeDayTables* d, c
   // which runs on the copy engine under the kernels of the slabs that follow
   int64_t done_slots = 0;
   for (int k = 0; k < n_slabs; ++k) {
-    const int64_t lo = (int64_t)k * per, hi = std::min<int64_t>(C, lo + per);
+    const int64_t lo = bound[(size_t)k], hi = bound[(size_t)k + 1];
     CK(cudaStreamWaitEvent(copy, ev_done[k], 0));
     CK(cudaMemcpyAsync(&S.pin[k], tot.as<unsigned long long>() + k, sizeof(unsigned long long), cudaMemcpyDeviceToHost, copy));
     const int64_t b0 = lo >> 5, b1 = (hi + 31) >> 5;

@@ -17,6 +17,8 @@ There is no exchange inside the simulation, hence no fused compute + collective 
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 ALIGN = 1024      # ranges of cells start at multiples of this (include/stryke_b200.h STRYKE_RANGE_ALIGN)
@@ -72,27 +74,83 @@ def default_slab_cells(n_cells, rows_bytes):
     return max(ALIGN, -(-n_cells // n_slabs // ALIGN) * ALIGN)
 
 
+SLAB_SHARES = (0.40, 0.30, 0.20, 0.10)      # cells per slab when the rows are exported (peer push): the LAST export is not hidden
+
+
+def group_density(grid, species, margin=1.08):
+    """Per group of ``grid``: (first cell, cells, expected rows per cell with margin, variance of the rows per cell)."""
+    out = []
+    for g in grid.groups:
+        sp = species[int(g["species"])]
+        cells = float(g["iterations"]) * float(g["n_active_days"])
+        occur = sp[17] if np.isfinite(sp[17]) else 1.0
+        fixed = int(sp[12]) == 0
+        per = 2.0 if (fixed and sp[18] > 13000) else 1.0
+        p = min(max(occur, 0.0), 1.0)
+        out.append((float(g["cell0"]), cells, per * p * margin + (0.0 if fixed else 0.02), per * per * p * (1 - p)))
+    return out
+
+
+def slab_plan(grids, species, n_cells_max, shares=SLAB_SHARES, scale=1.0, extra=1024):
+    """(cell_lo, slot_lo): slab k of every rank covers its cells [cell_lo[k], cell_lo[k+1]) (multiples of ALIGN) and owns
+    the slots [slot_lo[k], slot_lo[k+1]) of the rows buffer — sized for the rows the slab is expected to need (cells x
+    occur_prob of the groups it crosses, + 6 sigma + margin), the largest over the ranks' grids, times ``scale``.  The shares
+    decrease: the export of slab k runs under the kernels of slab k+1, only the last one is exposed."""
+    n = max(int(n_cells_max), 1)
+    if n < (1 << 18):
+        shares = (1.0,)
+    elif os.environ.get("STRYKE_B200_SLABS"):
+        k = max(1, int(os.environ["STRYKE_B200_SLABS"]))
+        shares = tuple([1.0 / k] * k)
+    cum = np.cumsum((0.0,) + tuple(shares)) / float(sum(shares))
+    cell_lo = [min(n, int(-(-(c * n) // ALIGN) * ALIGN)) for c in cum]
+    cell_lo[0], cell_lo[-1] = 0, n
+    cell_lo = sorted(set(cell_lo))
+    need = np.zeros(len(cell_lo) - 1)
+    for g in grids:
+        dens = group_density(g, species)
+        for k in range(len(cell_lo) - 1):
+            lo, hi = float(cell_lo[k]), float(cell_lo[k + 1])
+            e = v = 0.0
+            for c0, cells, d, var in dens:
+                ov = max(0.0, min(hi, c0 + cells) - max(lo, c0))
+                e += ov * d
+                v += ov * var
+            need[k] = max(need[k], e + 6.0 * np.sqrt(max(v, 1.0)))
+    caps = [int(scale * x) + extra for x in need]
+    slot_lo = [0]
+    for c in caps:
+        slot_lo.append(slot_lo[-1] + c)
+    return [int(c) for c in cell_lo], slot_lo
+
+
 class ShardLayout:
     """Geometry of one rank's flat buffer: header, block tables, slab regions of rows (identical on every rank)."""
 
-    def __init__(self, n_cells_max, n_pairs, slab_cells, slab_cap):
+    def __init__(self, n_cells_max, n_pairs, slab_cells=None, slab_cap=None, cell_lo=None, slot_lo=None):
+        """Either uniform slabs (``slab_cells`` cells and ``slab_cap`` slots each) or explicit bounds (``slab_plan``)."""
         self.W = int(n_pairs) + 3
         self.NB = (int(n_cells_max) + 31) // 32
-        self.slab_cells = int(slab_cells)
-        self.n_slabs = max(1, -(-int(n_cells_max) // self.slab_cells))
-        self.slab_cap = int(slab_cap)
+        if cell_lo is None:
+            n_slabs = max(1, -(-int(n_cells_max) // int(slab_cells)))
+            cell_lo = [min(int(n_cells_max), k * int(slab_cells)) for k in range(n_slabs)] + [int(n_cells_max)]
+            slot_lo = [k * int(slab_cap) for k in range(n_slabs + 1)]
+        self.cell_lo = [int(c) for c in cell_lo]
+        self.slot_lo = [int(x) for x in slot_lo]
+        self.n_slabs = len(self.cell_lo) - 1
+        self.slots = self.slot_lo[-1]
         self.blk_off = HDR
         self.rows_off = HDR + 3 * self.NB
         self.rows_off += (-self.rows_off) % 4                    # rows start 16-byte aligned
-        self.total = self.rows_off + self.n_slabs * self.slab_cap * self.W
+        self.total = self.rows_off + self.slots * self.W
+        self.total += (-self.total) % 4
 
     def slab_words(self, k):
-        lo = self.rows_off + k * self.slab_cap * self.W
-        return lo, lo + self.slab_cap * self.W
+        return self.rows_off + self.slot_lo[k] * self.W, self.rows_off + self.slot_lo[k + 1] * self.W
 
 
 def pack_flat(L, blk, rows, status=0, n_cells=0, slots_used=0):
-    """A rank's flat int32 buffer (numpy) from block tables [3, <= NB] and rows [<= n_slabs * slab_cap, W] — the layout the
+    """A rank's flat int32 buffer (numpy) from block tables [3, <= NB] and rows [<= L.slots, W] — the layout the
     kernels fill in place on the device; used by the host-side tests of the exchange."""
     flat = np.zeros(L.total, np.int32)
     u = flat.view(np.uint32)
@@ -113,7 +171,7 @@ def unpack_flat(L, flat, n_pairs):
     n_cells, status = int(flat[3]), int(flat[2])
     NB = (n_cells + 31) // 32
     blk = u[L.blk_off:L.blk_off + 3 * L.NB].reshape(3, L.NB)
-    rows = u[L.rows_off:L.rows_off + L.n_slabs * L.slab_cap * L.W].reshape(-1, L.W)
+    rows = u[L.rows_off:L.rows_off + L.slots * L.W].reshape(-1, L.W)
     return n_cells, status, CompactResult(n_cells, int(n_pairs), L.W, 0, rows.shape[0], 0, blk[0, :NB], blk[1, :NB], blk[2, :NB], rows)
 
 
@@ -133,7 +191,8 @@ class ShardedRun:
     """One rank's share of a run, resident on its GPU: plan, flat result buffer, gathered buffer, streams."""
 
     def __init__(self, fac, days, species, grid, rank, world, device, *, precision=32, seed=0, max_daily_fish=100000,
-                 kernel_variant=0, slab_cells=None, slab_cap=None, n_cells_max=None, group=None, exchange="auto", gather_to="root"):
+                 kernel_variant=0, slab_cells=None, slab_cap=None, n_cells_max=None, group=None, exchange="auto", gather_to="root",
+                 slabs=None):
         """``gather_to``: "root" — every rank's rows end up on rank 0, the one rank that writes the frames (each rank pushes
         1/(N-1) of what "all" costs it); "all" — on every rank (the all-reduce semantics: any rank can run ``summary()``)."""
         import torch
@@ -149,12 +208,19 @@ class ShardedRun:
         self.plan = engine.Plan(fac, days, species, grid, None, None, device=device, precision=precision, seed=seed,
                                 max_daily_fish=max_daily_fish, kernel_variant=kernel_variant)
         n_max = int(n_cells_max if n_cells_max is not None else self.n_cells)
-        est = expected_slots(grid, np.asarray(species).reshape(-1, 20))
-        if slab_cells is None:
-            slab_cells = default_slab_cells(n_max, est * (fac.n_pairs + 3) * 4)
-        if slab_cap is None:       # (expected_slots carries the margin; a slab that overflows is reported: slab_overflow -> the caller retries)
-            slab_cap = max(1024, int(est / max(1, -(-n_max // slab_cells)) * 1.04) + 1024)
-        self.L = ShardLayout(n_max, fac.n_pairs, slab_cells, slab_cap)
+        if slabs is not None:                                    # (cell_lo, slot_lo) of slab_plan: the same on every rank
+            self.L = ShardLayout(n_max, fac.n_pairs, cell_lo=slabs[0], slot_lo=slabs[1])
+        elif slab_cells is None and slab_cap is None:            # (ranks whose grids differ must be given a common plan)
+            cell_lo, slot_lo = slab_plan([grid], np.asarray(species).reshape(-1, 20), n_max,
+                                         shares=SLAB_SHARES if int(world) > 1 else (0.25,) * N_SLABS)
+            self.L = ShardLayout(n_max, fac.n_pairs, cell_lo=cell_lo, slot_lo=slot_lo)
+        else:
+            est = expected_slots(grid, np.asarray(species).reshape(-1, 20))
+            if slab_cells is None:
+                slab_cells = default_slab_cells(n_max, est * (fac.n_pairs + 3) * 4)
+            if slab_cap is None:   # (expected_slots carries the margin; a slab that overflows is reported: slab_overflow -> the caller retries)
+                slab_cap = max(1024, int(est / max(1, -(-n_max // slab_cells)) * 1.04) + 1024)
+            self.L = ShardLayout(n_max, fac.n_pairs, slab_cells, slab_cap)
         L = self.L
         self.mode = "gather"
         self.symm = None
@@ -175,7 +241,7 @@ class ShardedRun:
         self.buf = self.gathered[self.rank * L.total:(self.rank + 1) * L.total]
         self.buf.zero_()
         self.cell_n = torch.zeros(max(self.n_cells, 1), dtype=torch.int32, device=self.dev)
-        self.rows = self.buf[L.rows_off:L.rows_off + L.n_slabs * L.slab_cap * L.W].view(L.n_slabs * L.slab_cap, L.W)
+        self.rows = self.buf[L.rows_off:L.rows_off + L.slots * L.W].view(L.slots, L.W)
         self.blk = self.buf[L.blk_off:L.blk_off + 3 * L.NB].view(3, L.NB)
         self.slots_after = torch.zeros(L.n_slabs + 1, dtype=torch.int64, device=self.dev)
         self.compute = torch.cuda.current_stream(self.dev)
@@ -202,10 +268,10 @@ class ShardedRun:
         for ps in self.peer_streams.values():
             self.compute.wait_stream(ps)
         for k in range(L.n_slabs):
-            lo, hi = k * L.slab_cells, min(nC, (k + 1) * L.slab_cells)
+            lo, hi = min(nC, L.cell_lo[k]), min(nC, L.cell_lo[k + 1])
             if lo >= hi:
                 break
-            self.plan.launch_compact(self.cell_n, self.rows, lo, hi, first_slot=k * L.slab_cap,
+            self.plan.launch_compact(self.cell_n, self.rows, lo, hi, first_slot=L.slot_lo[k],
                                      slots_after=self.slots_after[k:k + 1], stream=cs)
             self.slab_events[k].record(self.compute)
             w0, w1 = L.slab_words(k)
@@ -225,8 +291,7 @@ class ShardedRun:
         torch, dist, L = self.torch, self.dist, self.L
         hdr = torch.tensor([0, 0, int(status_code), self.n_cells], dtype=torch.int32)
         self.buf[2:4].copy_(hdr[2:4].to(self.dev, non_blocking=True), non_blocking=True)
-        self.buf[0:2].copy_(self.slots_after[max(0, min(L.n_slabs, -(-self.n_cells // L.slab_cells)) - 1):][:1].view(torch.int32)[:2],
-                            non_blocking=True)
+        self.buf[0:2].copy_(self.slots_after[max(0, self.slabs_used() - 1):][:1].view(torch.int32)[:2], non_blocking=True)
         if self.world > 1:
             if self.mode == "push":
                 base = self.rank * L.total
@@ -271,15 +336,22 @@ class ShardedRun:
         g = self.gathered.cpu().numpy().reshape(self.world, self.L.total)
         return [unpack_flat(self.L, g[r], self.fac.n_pairs) for r in range(self.world)]
 
+    def slabs_used(self):
+        """Slabs that hold cells of this rank (the last ones may be empty on a rank with fewer cells than ``n_cells_max``)."""
+        return sum(1 for k in range(self.L.n_slabs) if self.L.cell_lo[k] < self.n_cells)
+
+    def slots_used(self):
+        """Rows this rank's last pass wrote (synchronises)."""
+        self.torch.cuda.synchronize(self.dev)
+        after = self.slots_after.cpu().numpy()
+        return int(sum(int(after[k]) - self.L.slot_lo[k] for k in range(self.slabs_used())))
+
     def slab_overflow(self):
-        """True when some slab used more slots than its region holds (the caller retries with a larger ``slab_cap``)."""
+        """True when some slab used more slots than its region holds (the caller retries with larger regions)."""
         self.torch.cuda.synchronize(self.dev)
         after = self.slots_after.cpu().numpy()
         L = self.L
-        for k in range(L.n_slabs):
-            if k * L.slab_cells < self.n_cells and after[k] > (k + 1) * L.slab_cap:
-                return True
-        return False
+        return any(after[k] > L.slot_lo[k + 1] for k in range(self.slabs_used()))
 
     def close(self):
         self.plan.close()
@@ -320,12 +392,9 @@ def run_sharded(plan_host, rank, world, device, *, precision=32, seed=0, max_dai
     species = plan_host.species_table
     cap_scale = 1.0
     while True:
-        est = max(expected_slots(g, species) for g in grids)
-        slab_cells = default_slab_cells(n_max, est * (plan_host.fac.n_pairs + 3) * 4)
-        n_slabs = max(1, -(-n_max // slab_cells))
         run = ShardedRun(plan_host.fac, plan_host.days, species, mine, rank, world, device, precision=precision, seed=seed,
-                         max_daily_fish=max_daily_fish, slab_cells=slab_cells,
-                         slab_cap=int(cap_scale * (est / n_slabs * 1.04 + 1024)), n_cells_max=n_max, group=group, gather_to=gather_to)
+                         max_daily_fish=max_daily_fish, n_cells_max=n_max, group=group, gather_to=gather_to,
+                         slabs=slab_plan(grids, species, n_max, scale=cap_scale))
         code, msg = 0, ""
         try:
             run.launch(seed)

@@ -307,3 +307,36 @@ def test_fallback_store_exports_to_parquet_and_csv(tmp_path):
         import pytest
         with pytest.raises(RuntimeError, match="PyTables"):
             store.export(path, str(tmp_path / "x.h5"))
+
+
+def test_slab_plan_and_layout():
+    """Slab bounds are multiples of the range alignment, cover the cells, decrease in size; every slab's region of the rows
+    buffer holds the rows the slab is expected to write (checked against an actual draw of the presence rolls)."""
+    from stryke_b200 import workloads as W
+    from stryke_b200.distributed import ALIGN, SLAB_SHARES, ShardLayout, slab_plan
+    prj = W.c3_population(n_species=6, iterations=1000, days=60, scenarios=["A", "B"], facility_scenario_column=False)
+    sim, plan = W.make_plan(prj, "slabplan")
+    world = 2
+    grids = [plan.grid.iterations_slice(r / world, (r + 1) / world) for r in range(world)]
+    n_max = max(g.n_cells for g in grids)
+    assert n_max >= (1 << 18)
+    cell_lo, slot_lo = slab_plan(grids, plan.species_table, n_max)
+    assert cell_lo[0] == 0 and cell_lo[-1] == n_max and len(cell_lo) == len(SLAB_SHARES) + 1
+    assert all(c % ALIGN == 0 for c in cell_lo[:-1])
+    sizes = np.diff(cell_lo)
+    assert all(sizes[i] >= sizes[i + 1] for i in range(len(sizes) - 1))
+    L = ShardLayout(n_max, plan.fac.n_pairs, cell_lo=cell_lo, slot_lo=slot_lo)
+    assert L.n_slabs == len(SLAB_SHARES) and L.slots == slot_lo[-1] and L.total % 4 == 0
+    assert [L.slab_words(k)[1] - L.slab_words(k)[0] for k in range(L.n_slabs)] == [int(x) * L.W for x in np.diff(slot_lo)]
+    rng = np.random.default_rng(3)
+    for g in grids:
+        day, spc, ids = g.explicit()
+        occur = plan.species_table[spc, 17]
+        present = rng.random(len(spc)) <= np.where(np.isfinite(occur), occur, 1.0)
+        for k in range(L.n_slabs):
+            assert int(present[cell_lo[k]:cell_lo[k + 1]].sum()) <= slot_lo[k + 1] - slot_lo[k]
+    # small lists: one slab; the uniform constructor still works
+    one = slab_plan(grids, plan.species_table, 5000)
+    assert one[0] == [0, 5000] and len(one[1]) == 2
+    U = ShardLayout(5000, plan.fac.n_pairs, slab_cells=2048, slab_cap=3000)
+    assert U.cell_lo == [0, 2048, 4096, 5000] and U.slot_lo == [0, 3000, 6000, 9000]
