@@ -110,27 +110,30 @@ class FrameStore:
         return self._norm(key) in self._manifest["keys"]
 
     def __getitem__(self, key):
+        return self.get(key)
+
+    def get(self, key, categorical=False):
+        """The frame stored under ``key``.  ``categorical=True`` leaves dictionary-encoded label columns as pandas
+        categoricals instead of turning them back into the object columns the writer had (summary() compares long frames by
+        the integer codes and builds the object columns itself)."""
         k = self._norm(key)
         rec = self._manifest["keys"].get(k)
         if rec is None:
             raise KeyError(f"No object named {key} in the file")
-        parts = [self._read_part(os.path.join(self._dir(k), f"part-{i:05d}.parquet"), rec) for i in range(rec["parts"])]
+        parts = [self._read_part(os.path.join(self._dir(k), f"part-{i:05d}.parquet"), rec, categorical) for i in range(rec["parts"])]
         df = parts[0] if len(parts) == 1 else pd.concat(parts, ignore_index=rec.get("range_index", True))
         return df
 
     @staticmethod
-    def _read_part(path, rec):
+    def _read_part(path, rec, categorical=False):
         df = pd.read_parquet(path)
         for c in rec.get("json_columns", []):
             df[c] = pd.Series([json.loads(v) if v is not None else None for v in df[c]], index=df.index, dtype=object)
             df[c] = df[c].where(df[c].notna(), np.nan)
         for c in rec.get("object_columns", []):          # keep what the writer had as plain object columns
-            if c in df.columns and df[c].dtype != object:
+            if c in df.columns and df[c].dtype != object and not (categorical and isinstance(df[c].dtype, pd.CategoricalDtype)):
                 df[c] = df[c].astype(object)
         return df
-
-    def get(self, key):
-        return self[key]
 
     def __setitem__(self, key, df):
         self.put(key, df)
@@ -195,6 +198,9 @@ class _HDF(object):
         return getattr(self._s, name)
 
     def __getitem__(self, key):
+        return self._s[key]
+
+    def get(self, key, categorical=False):      # (same signature as FrameStore.get; HDF tables hold plain object columns)
         return self._s[key]
 
     def __setitem__(self, key, df):

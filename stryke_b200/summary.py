@@ -133,15 +133,19 @@ def _summarize(sim):
         sim.beta_dict = {}
         species = store["Population"].Species.unique()
         scens = store["Flow Scenarios"].Scenario.unique()
-        sim.daily_summary = store["Daily"].copy()
+        sim.daily_summary = store.get("Daily", categorical=True)
         num_cols = list(sim.daily_summary.columns[6:])
         sim.daily_summary[num_cols] = sim.daily_summary[num_cols].astype(float)      # stryke.py:3564
         sim.daily_summary["species_norm"], d_spc, d_spc_l = _stripped(sim.daily_summary["species"])
         sim.daily_summary["scenario_norm"], d_scn, d_scn_l = _stripped(sim.daily_summary["scenario"])
+        daily_index = _DailyIndex(sim.daily_summary)      # (label codes taken while the columns are still categoricals)
+        for c in ("species", "scenario"):                 # the frame the caller sees holds plain strings, as the reference's
+            if isinstance(sim.daily_summary[c].dtype, pd.CategoricalDtype):
+                sim.daily_summary[c] = sim.daily_summary[c].astype(object)
         print("\n" + "=" * 60, flush=True)
         print("SIMULATION SUMMARY STATISTICS", flush=True)
         print("=" * 60, flush=True)
-        state_daily = store["State_Daily"].copy() if "State_Daily" in store else None
+        state_daily = store.get("State_Daily", categorical=True) if "State_Daily" in store else None
         if state_daily is not None:
             state_daily["day"] = pd.to_datetime(state_daily["day"])
             state_daily["move"] = pd.to_numeric(state_daily["move"], errors="coerce").fillna(0).astype(int)
@@ -156,6 +160,7 @@ def _summarize(sim):
             s_order = np.argsort(s_group, kind="stable")
             state_sorted = state_daily.iloc[s_order]
             s_group_sorted = s_group[s_order]
+            st_codes_sorted = st_codes[s_order]
         moves = [int(m) for m in sim.moves]
         final_move = max(moves) if moves else 0
         group_sizes = sim.daily_summary.groupby(["species", "scenario"], sort=False).size() if len(species) > 1 else None
@@ -164,7 +169,7 @@ def _summarize(sim):
                 # the reference rebuilds the yearly summary inside its species loop (stryke.py:3770-3862 sit under
                 # `for i in species`): the table of the last pass is the one that is kept, but every pass draws its
                 # bootstraps from the global stream — replayed here so that a seeded run stays draw-for-draw identical
-                yearly_summary(sim.daily_summary, draws_only=True, sizes=group_sizes)
+                yearly_summary(sim.daily_summary, draws_only=True, sizes=group_sizes, index=daily_index)
             for scen in scens:
                 if state_daily is None:
                     logger.warning("Missing simulation data for key 'simulations/%s/%s'", scen, spc)
@@ -174,7 +179,9 @@ def _summarize(sim):
                     gkey = int(hs[0]) * max(len(s_spc_l), 1) + int(hp[0])
                     lo_, hi_ = np.searchsorted(s_group_sorted, [gkey, gkey + 1])
                     state_dat = state_sorted.iloc[lo_:hi_]
+                    state_codes = (st_codes_sorted[lo_:hi_], st_labels)
                 else:
+                    state_codes = None
                     state_dat = state_daily[_code_mask(s_scn, s_scn_l, str(scen).strip()) & _code_mask(s_spc, s_spc_l, str(spc).strip())]
                 if state_dat.empty:
                     logger.warning("Missing simulation aggregates for scenario '%s' species '%s'", scen, spc)
@@ -203,7 +210,7 @@ def _summarize(sim):
                 cnt_, suc_ = state_dat["count"].to_numpy(dtype=float), state_dat["successes"].to_numpy(dtype=float)
                 prob_ = np.where(cnt_ > 0, suc_ / np.where(cnt_ > 0, cnt_, 1.0), 0.0)
                 mv_ = state_dat["move"].to_numpy()
-                stc_, stl_ = _label_codes(state_dat["state"])
+                stc_, stl_ = state_codes if state_codes is not None else _label_codes(state_dat["state"])
                 key_ = mv_.astype(np.int64) * max(len(stl_), 1) + stc_
                 uk, first, inv = np.unique(key_, return_index=True, return_inverse=True)
                 order_ = np.argsort(np.asarray(inv), kind="stable")
@@ -226,7 +233,7 @@ def _summarize(sim):
             ["state", "survival rate", "variance", "ll", "ul"]].copy()
         sim.beta_df_units_only.rename(columns={"state": "Passage Route", "survival rate": "Mean", "variance": "Variance",
                                                "ll": "Lower 95% CI", "ul": "Upper 95% CI"}, inplace=True)
-        sim.cum_sum = yearly_summary(sim.daily_summary)
+        sim.cum_sum = yearly_summary(sim.daily_summary, index=daily_index)
         if sim.wks_dir and str(sim.wks_dir).endswith((".xlsx", ".xls")):
             try:
                 from . import xlsx
@@ -252,7 +259,36 @@ def _summarize(sim):
     return None
 
 
-def yearly_summary(daily, draws_only=False, sizes=None):
+class _DailyIndex:
+    """The Daily frame's rows grouped by (species, scenario) once: label codes, a stable order that makes every group
+    contiguous, and the numeric columns as arrays in that order.  ``yearly_summary`` runs once per species of the project
+    (the reference rebuilds it inside its species loop) — factorising 1e6-row label columns and masking the frame every
+    time was two thirds of summary()'s time."""
+
+    def __init__(self, daily):
+        self.spc, self.spc_l = _label_codes(daily["species"])
+        self.scn, self.scn_l = _label_codes(daily["scenario"])
+        self.nscn = max(len(self.scn_l), 1)
+        key = self.spc.astype(np.int64) * self.nscn + self.scn
+        self.order = np.argsort(key, kind="stable")
+        self.key_sorted = key[self.order]
+        self.cols = {c: daily[c].to_numpy()[self.order] for c in ("iteration", "num_entrained", "num_survived", "pop_size")}
+        self.first_seen = {}                      # labels in order of first appearance (what .unique() returns)
+        for name, codes, labels in (("species", self.spc, self.spc_l), ("scenario", self.scn, self.scn_l)):
+            _, first = np.unique(codes, return_index=True)
+            self.first_seen[name] = [labels[codes[i]] for i in np.sort(first)]
+
+    def group(self, species, scenario):
+        """Row range [lo, hi) (in the sorted order) of one (species, scenario); empty when a label does not occur."""
+        hs, hc = np.flatnonzero(self.spc_l == str(species)), np.flatnonzero(self.scn_l == str(scenario))
+        if hs.size != 1 or hc.size != 1:
+            return 0, 0
+        k = int(hs[0]) * self.nscn + int(hc[0])
+        lo, hi = np.searchsorted(self.key_sorted, [k, k + 1])
+        return int(lo), int(hi)
+
+
+def yearly_summary(daily, draws_only=False, sizes=None, index=None):
     """Per (species, scenario): entrainment probability, yearly totals with 95 % percentiles over iterations, bootstrap
     means and 1-in-10/100/1000-day quantiles of daily entrainment and mortality (stryke.py:3770-3862).
     ``draws_only``: consume the random draws of one pass and return nothing (see summarize)."""
@@ -263,46 +299,46 @@ def yearly_summary(daily, draws_only=False, sizes=None):
     out = {c: [] for c in cols}
     if draws_only and sizes is None:
         sizes = daily.groupby(["species", "scenario"], sort=False).size()
-    if draws_only:      # same group order as below (groupby sorts its keys) without the sums
-        species_order = sorted({k[0] for k in sizes.index})
-        scenario_order = sorted({k[1] for k in sizes.index})
-    else:
-        groups = daily.groupby(["species", "scenario", "iteration"])[["pop_size", "num_survived", "num_entrained"]].sum().reset_index()
-        species_order, scenario_order = groups.species.unique(), groups.scenario.unique()
-    y_spc, y_spc_l = _label_codes(daily["species"])
-    y_scn, y_scn_l = _label_codes(daily["scenario"])
+    if draws_only and all(_device_for(int(n), 10000) is not None for n in sizes.values):
+        return None                           # every group on the device path: the discarded bootstraps draw nothing
+    D = index if index is not None else _DailyIndex(daily)
+    # the reference's group order: the keys of groupby(["species", "scenario", "iteration"]) (sorted), .unique() of each
+    species_order, scenario_order = sorted(D.first_seen["species"]), sorted(D.first_seen["scenario"])
     for fishy in species_order:
         for scen in scenario_order:
-            if draws_only and _device_for(int(sizes.get((fishy, scen), 0)), 10000) is not None:
+            lo, hi = D.group(fishy, scen)
+            if draws_only and _device_for(hi - lo, 10000) is not None:
                 continue                      # large group on the device path: its discarded bootstraps draw nothing
             out["species"].append(fishy)
             out["scenario"].append(scen)
-            day_dat = daily[_code_mask(y_spc, y_spc_l, str(fishy)) & _code_mask(y_scn, y_scn_l, str(scen))]
-            if len(day_dat) == 0:
+            if hi == lo:
                 for c in cols[2:]:
                     out[c].append(0.0)
                 continue
-            df = day_dat[["day", "iteration", "num_entrained", "num_survived", "pop_size"]].copy()
-            df["num_mortalities"] = df["num_entrained"] - df["num_survived"]
+            ent = D.cols["num_entrained"][lo:hi].astype(float)
+            mort = ent - D.cols["num_survived"][lo:hi].astype(float)
             if draws_only:
-                bootstrap_mean_ci(df["num_entrained"], result_used=False)
-                bootstrap_mean_ci(df["num_mortalities"], result_used=False)
+                bootstrap_mean_ci(ent, result_used=False)
+                bootstrap_mean_ci(mort, result_used=False)
                 continue
-            per_it = df.groupby("iteration")[["pop_size", "num_entrained"]].sum()
-            probs = np.where(per_it["pop_size"] > 0, per_it["num_entrained"] / per_it["pop_size"].where(per_it["pop_size"] > 0, 1.0), 0.0)
+            it_codes, it_labels = pd.factorize(D.cols["iteration"][lo:hi], sort=True)
+            n_it = len(it_labels)
+            pop_it = np.bincount(it_codes, weights=D.cols["pop_size"][lo:hi].astype(float), minlength=n_it)
+            ent_it = np.bincount(it_codes, weights=ent, minlength=n_it)
+            mort_it = np.bincount(it_codes, weights=mort, minlength=n_it)
+            probs = np.where(pop_it > 0, ent_it / np.where(pop_it > 0, pop_it, 1.0), 0.0)
             out["prob_entrainment"].append(float(np.mean(probs)) if len(probs) else 0.0)
             # drawn by the reference (:3832-3833) although nothing reads the results: kept for stream identity on the
             # NumPy path, skipped on the device path
-            bootstrap_mean_ci(df["num_entrained"], result_used=False)
-            bootstrap_mean_ci(df["num_mortalities"], result_used=False)
-            q = {T: 1 - 1 / T for T in (10, 100, 1000)}
-            year = df.groupby(["iteration"])[["num_entrained", "num_mortalities"]].sum().apply(summarize_ci)
-            for what, col in (("entrainment", "num_entrained"), ("mortality", "num_mortalities")):
-                out[f"mean_yearly_{what}"].append(year.at["mean", col])
-                out[f"lcl_yearly_{what}"].append(year.at["lower_95_CI", col])
-                out[f"ucl_yearly_{what}"].append(year.at["upper_95_CI", col])
-                for T, level in q.items():
-                    out[f"1_in_{T}_day_{what}"].append(df[col].quantile(level))
+            bootstrap_mean_ci(ent, result_used=False)
+            bootstrap_mean_ci(mort, result_used=False)
+            for what, per_it, per_day in (("entrainment", ent_it, ent), ("mortality", mort_it, mort)):
+                ci = summarize_ci(pd.Series(per_it))
+                out[f"mean_yearly_{what}"].append(ci["mean"])
+                out[f"lcl_yearly_{what}"].append(ci["lower_95_CI"])
+                out[f"ucl_yearly_{what}"].append(ci["upper_95_CI"])
+                for T in (10, 100, 1000):
+                    out[f"1_in_{T}_day_{what}"].append(float(np.quantile(per_day, 1 - 1 / T)))
     return None if draws_only else pd.DataFrame.from_dict(out, orient="columns")
 
 
