@@ -309,24 +309,30 @@ def frame_table(df, nan_rep="nan", min_itemsize=None, data_columns=False):
     values_cols, data_cols = [], []
 
     def as_strings(cols):
-        sub = np.empty((n, len(cols)), dtype=object)
-        for j, c in enumerate(cols):
+        """[n, len(cols)] fixed-width byte strings; every column is encoded through its distinct values (label columns of
+        long frames hold a handful of them)."""
+        enc, width = [], 1
+        for c in cols:
             col = df[c]
             if isinstance(col.dtype, pd.CategoricalDtype):
-                col = col.astype(object)
-            v = col.to_numpy(dtype=object)
-            mask = pd.isna(v)
-            v = np.array([x if isinstance(x, str) else str(x) for x in v], dtype=object)
-            v[mask] = nan_rep
-            sub[:, j] = v
-        width = max([1] + [len(s.encode("utf-8")) for s in sub.reshape(-1)])
+                codes, uniq = np.asarray(col.cat.codes), list(col.cat.categories)
+            else:
+                try:
+                    codes, uniq = pd.factorize(col, use_na_sentinel=True)
+                    uniq = list(uniq)
+                except TypeError:                                 # unhashable cells (lists): stringify first
+                    codes, uniq = pd.factorize(col.map(str), use_na_sentinel=True)
+                    uniq = list(uniq)
+            labels = [(x if isinstance(x, str) else str(x)).encode("utf-8") for x in uniq] + [nan_rep.encode("utf-8")]      # [-1] = missing
+            width = max([width] + [len(x) for x in labels[:-1]] + ([len(labels[-1])] if (np.asarray(codes) < 0).any() else []))
+            enc.append((np.asarray(codes), labels))
         if isinstance(min_itemsize, dict):
             width = max([width] + [int(min_itemsize[c]) for c in cols if c in min_itemsize])
         elif min_itemsize:
             width = max(width, int(min_itemsize))
         out = np.zeros((n, len(cols)), dtype=f"S{width}")
-        flat = out.reshape(-1)
-        flat[:] = [s.encode("utf-8") for s in sub.reshape(-1)]
+        for j, (codes, labels) in enumerate(enc):
+            out[:, j] = np.array(labels, dtype=f"S{width}")[codes]
         return out, width
 
     blocks = _block_order(df)

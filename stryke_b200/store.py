@@ -90,10 +90,14 @@ class FrameStore:
                 raise RuntimeError(f"{self.dir}: unknown store format {m.get('format')!r} (written by another version; "
                                    "stores are never unpickled — re-run the project)")
             self._manifest = m
+        self._dirty = False
         if mode != "r" and self.h5_path not in _WARNED:
             _WARNED.add(self.h5_path)
-            logger.warning("PyTables is not installed: results go to %s (Parquet parts per HDF key), NOT to %s; convert with "
-                           "`python -m stryke_b200.store %s <target.h5>` where PyTables exists", self.dir, self.h5_path, self.h5_path)
+            logger.warning("PyTables is not installed: results go to %s (Parquet parts per HDF key); %s is written from them by "
+                           "stryke_b200.h5lite when the store is closed (pandas table layout, frames up to STRYKE_B200_H5_MAX_ROWS "
+                           "rows; not verified against libhdf5 on this machine).  `python -m stryke_b200.store %s <target.h5>` "
+                           "converts a store explicitly (through pandas.HDFStore where PyTables exists)",
+                           self.dir, self.h5_path, self.h5_path)
 
     @staticmethod
     def _norm(key):
@@ -160,6 +164,7 @@ class FrameStore:
         rec["rows"] += int(len(df))
         self._manifest["keys"][k] = rec
         self._write_manifest()
+        self._dirty = True
 
     def put(self, key, df, **kwargs):
         self._write_part(self._norm(key), df, fresh=True)
@@ -178,7 +183,39 @@ class FrameStore:
         os.replace(tmp, self._manifest_path)
 
     def close(self):
-        pass
+        """Closing a store that was written to also (re)writes ``<name>.h5`` in the reference's HDF5 layout."""
+        if self._dirty and self.mode != "r":
+            self._dirty = False
+            try:
+                self.write_h5(self.h5_path)
+            except Exception as exc:      # the Parquet store is the working copy; the .h5 is an export
+                logger.warning("could not write %s: %s", self.h5_path, exc)
+
+    def write_h5(self, target, max_rows=None):
+        """Every key of the store as ``/<key>/table`` of one HDF5 file (``stryke_b200.h5lite``).  Keys with more than
+        ``max_rows`` rows (default ``$STRYKE_B200_H5_MAX_ROWS`` or 2 000 000; < 0: no limit, 0: write nothing) are left out
+        with a log line: building a 1e8-row State_Daily table in memory is a deliberate step, not a side effect of close()."""
+        from . import h5lite
+        if max_rows is None:
+            max_rows = int(os.environ.get("STRYKE_B200_H5_MAX_ROWS", "2000000"))
+        if max_rows == 0:
+            return None
+        frames, skipped = {}, []
+        for k in self.keys():
+            if 0 < max_rows < int(self._manifest["keys"][k].get("rows", 0)):
+                skipped.append(k)
+                continue
+            frames[k.strip("/")] = self.get(k, categorical=True)
+        if skipped:
+            logger.warning("%s: %s left out of the HDF5 export (more than %d rows; STRYKE_B200_H5_MAX_ROWS=-1 or "
+                           "`python -m stryke_b200.store %s <target.h5>` writes them)", target, ", ".join(skipped), max_rows, self.h5_path)
+        summary_keys = {"Daily_Summary", "Beta_Distributions", "Beta_Distributions_Units", "Yearly_Summary", "Driver_Diagnostics"}
+        tmp = str(target) + ".tmp"
+        h5lite.write_frames(tmp, frames, data_columns={k for k in frames if k in summary_keys},
+                            min_itemsize={"State_Daily": {"scenario": 128, "species": 128, "state": 256},
+                                          "Route_Flows": {"scenario": 128, "route": 256}, "Unit_Hours": {"scenario": 128, "route": 256}})
+        os.replace(tmp, target)
+        return target
 
     def __enter__(self):
         return self
@@ -236,9 +273,10 @@ def export(path, target, fmt=None):
     fmt = fmt or ("hdf" if str(target).endswith((".h5", ".hdf", ".hdf5")) else "parquet")
     src = FrameStore(path, mode="r")
     keys = src.keys()
+    if fmt == "hdf" and not pytables_available():      # no PyTables here: the built-in writer, every key, no row limit
+        logger.warning("PyTables is not installed: %s is written by stryke_b200.h5lite (pandas table layout)", target)
+        return [src.write_h5(target, max_rows=-1)]
     if fmt == "hdf":
-        if not pytables_available():
-            raise RuntimeError("writing HDF5 needs PyTables (pip install tables); use fmt='parquet' or 'csv' here")
         with pd.HDFStore(target, mode="w") as out:
             for k in keys:
                 df = src[k]

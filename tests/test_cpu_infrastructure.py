@@ -303,10 +303,22 @@ def test_fallback_store_exports_to_parquet_and_csv(tmp_path):
     assert pd.read_parquet(os.path.join(str(tmp_path / "pq"), "Daily.parquet")).equals(daily)
     out = store.export(path, str(tmp_path / "csv"), "csv")
     assert len(out) == 3 and pd.read_csv(out[0]).shape[0] == 2
+    # closing the store also wrote <name>.h5 itself, and export(..., "x.h5") writes one too: with PyTables through
+    # pandas.HDFStore, without it through stryke_b200.h5lite — read here with the tests' own HDF5 reader
+    h5 = store.export(path, str(tmp_path / "x.h5"))
+    assert h5 == [str(tmp_path / "x.h5")] and os.path.isfile(path)
     if not store.pytables_available():
-        import pytest
-        with pytest.raises(RuntimeError, match="PyTables"):
-            store.export(path, str(tmp_path / "x.h5"))
+        import h5parse
+        for file in (path, h5[0]):
+            f = h5parse.File(file)
+            assert sorted(k for k, o in f.walk() if o["kind"] == "dataset") == ["/Daily/table", "/Population/table",
+                                                                               "/simulations/Spring/a/table"]
+            rec = f.read(f.get("Daily/table"))
+            t = f.get("Daily/table")["attrs"]
+            assert t["values_block_0_kind"] == ["iteration", "pop_size"] and np.array_equal(rec["values_block_0"], [[0, 3], [1, 4]])
+            assert t["values_block_1_dtype"] == "datetime64[ns]"
+            assert np.array_equal(rec["values_block_1"][:, 0].view("datetime64[ns]"), daily["day"].to_numpy())
+            assert [x.decode() for x in rec["values_block_2"][:, 0]] == ["a", "b"]
 
 
 def test_slab_plan_and_layout():

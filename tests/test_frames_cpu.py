@@ -147,3 +147,42 @@ def test_iteration_slices_partition_the_grid():
             seen += [int(x) for x in sub.explicit()[2]]
             assert sub.n_cells == len(sub.explicit()[0])
         assert sorted(seen) == sorted(full)
+
+
+@pytest.mark.parametrize("case", ["c3_multi_scenario", "cabot_station"])
+def test_result_file_in_the_reference_layout(case, tmp_path):
+    """The frames run() stores also reach ``<name>.h5`` in the pandas table layout (``/<key>/table`` with ``index`` and
+    ``values_block_N`` members, stryke.py:3344 / :3379): written by the store on close, read back here with the tests' own
+    HDF5 reader (and by ``pandas.HDFStore`` where PyTables exists: tests/test_h5lite_cpu.py)."""
+    import h5parse
+    from stryke_b200 import store
+    g = Golden(case)
+    sim, plan = G.make_plan(g.prj, case)
+    res, _ = golden_dense(g, plan)
+    frames = runner.assemble_frames(sim, plan, runner.group_tallies(plan, [(plan.grid, res)]))
+    path = str(tmp_path / "result.h5")
+    with store.FrameStore(path, mode="w") as st:
+        for key, df in frames.items():
+            if df is not None and len(df):
+                st.append(key, df)
+    f = h5parse.File(path)
+    tables = {k: o for k, o in f.walk() if o["kind"] == "dataset"}
+    assert {"/Daily/table", "/State_Daily/table"} <= set(tables)
+    for key in ("Daily", "State_Daily"):
+        df = frames[key]
+        grp, tab = f.get(key), tables[f"/{key}/table"]
+        assert grp["attrs"]["pandas_type"] == "frame_table" and grp["attrs"]["non_index_axes"] == [(1, [str(c) for c in df.columns])]
+        rec = f.read(tab)
+        assert len(rec) == len(df) and rec.dtype.names[0] == "index"
+        for name in grp["attrs"]["values_cols"]:
+            for j, c in enumerate(tab["attrs"][f"{name}_kind"]):
+                col, kind = df[c], tab["attrs"][f"{name}_dtype"]
+                v = rec[name][:, j]
+                if kind.startswith("bytes"):
+                    assert [x.decode("utf-8") for x in v] == [str(x) for x in col]
+                elif kind == "datetime64[ns]":
+                    assert np.array_equal(v.view("datetime64[ns]"), col.to_numpy().astype("datetime64[ns]"))
+                else:
+                    assert np.array_equal(v, col.to_numpy())
+    sd = tables["/State_Daily/table"]["dtype"]
+    assert max(sd[n].subdtype[0].itemsize for n in sd.names if sd[n].subdtype and sd[n].subdtype[0].kind == "S") >= 256      # min_itemsize of the reference
