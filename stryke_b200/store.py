@@ -22,6 +22,22 @@ import pandas as pd
 
 logger = logging.getLogger(__name__)
 _WARNED = set()
+_EXPORTS = {}      # h5 path -> thread writing it from the Parquet store (see FrameStore.close)
+
+
+def wait_for_exports(path=None):
+    """Block until the ``.h5`` export of ``path`` (default: of every store closed by this process) is on disk."""
+    for p in ([str(path)] if path is not None else list(_EXPORTS)):
+        t = _EXPORTS.pop(p, None)
+        if t is not None:
+            t.join()
+
+
+def _export_job(h5_path):
+    try:
+        FrameStore(h5_path, mode="r").write_h5(h5_path)
+    except Exception as exc:      # the Parquet store is the working copy; the .h5 is an export of it
+        logger.warning("could not write %s: %s", h5_path, exc)
 
 
 def pytables_available():
@@ -76,6 +92,8 @@ class FrameStore:
         self.h5_path = str(path)
         self.dir = self.h5_path + ".store"
         self.mode = mode
+        if mode != "r":
+            wait_for_exports(self.h5_path)      # an export still reading the parts this store is about to change
         if mode == "w" and os.path.isdir(self.dir):
             shutil.rmtree(self.dir)
         if mode == "r" and not os.path.isdir(self.dir):
@@ -183,13 +201,19 @@ class FrameStore:
         os.replace(tmp, self._manifest_path)
 
     def close(self):
-        """Closing a store that was written to also (re)writes ``<name>.h5`` in the reference's HDF5 layout."""
+        """Closing a store that was written to also (re)writes ``<name>.h5`` in the reference's HDF5 layout — on a worker
+        thread (``$STRYKE_B200_H5_EXPORT``: ``async`` default, ``sync``, ``off``): run() and summary() return when the working
+        store is complete; the next writer of the same store, ``wait_for_exports`` and interpreter exit wait for the file."""
         if self._dirty and self.mode != "r":
             self._dirty = False
-            try:
-                self.write_h5(self.h5_path)
-            except Exception as exc:      # the Parquet store is the working copy; the .h5 is an export
-                logger.warning("could not write %s: %s", self.h5_path, exc)
+            how = os.environ.get("STRYKE_B200_H5_EXPORT", "async").lower()
+            if how == "sync":
+                _export_job(self.h5_path)
+            elif how != "off":
+                import threading
+                t = threading.Thread(target=_export_job, args=(self.h5_path,), name="stryke_b200-h5-export")
+                _EXPORTS[self.h5_path] = t
+                t.start()
 
     def write_h5(self, target, max_rows=None):
         """Every key of the store as ``/<key>/table`` of one HDF5 file (``stryke_b200.h5lite``).  Keys with more than

@@ -306,6 +306,7 @@ def test_fallback_store_exports_to_parquet_and_csv(tmp_path):
     # closing the store also wrote <name>.h5 itself, and export(..., "x.h5") writes one too: with PyTables through
     # pandas.HDFStore, without it through stryke_b200.h5lite — read here with the tests' own HDF5 reader
     h5 = store.export(path, str(tmp_path / "x.h5"))
+    store.wait_for_exports(path)
     assert h5 == [str(tmp_path / "x.h5")] and os.path.isfile(path)
     if not store.pytables_available():
         import h5parse

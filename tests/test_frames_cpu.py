@@ -165,6 +165,7 @@ def test_result_file_in_the_reference_layout(case, tmp_path):
         for key, df in frames.items():
             if df is not None and len(df):
                 st.append(key, df)
+    store.wait_for_exports(path)                      # (the file is written on a worker thread after close)
     f = h5parse.File(path)
     tables = {k: o for k, o in f.walk() if o["kind"] == "dataset"}
     assert {"/Daily/table", "/State_Daily/table"} <= set(tables)
