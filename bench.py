@@ -479,6 +479,8 @@ def api_timing(device):
         out[tag] = {"fish_passages": fish, "run_s": t1 - t0, "first_run_s": first, "summary_s": t2 - t1,
                     "run_fish_passages_per_s": fish / (t1 - t0), "run_plus_summary_fish_passages_per_s": fish / (t2 - t0)}
         import shutil
+        from stryke_b200.store import wait_for_exports
+        wait_for_exports()                  # (the .h5 export of the last close runs on a worker thread)
         shutil.rmtree(tmp, ignore_errors=True)
     return out
 
