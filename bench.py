@@ -260,7 +260,7 @@ def measure(name, args, rank, local_rank, world, sampler, main):
     while True:
         run = ShardedRun(plan_h.fac, plan_h.days, species, grid, rank, world, local_rank, precision=args.precision, seed=0x5EED,
                          max_daily_fish=2_000_000_000, kernel_variant=args.kernel_variant, n_cells_max=n_max,
-                         slabs=slab_plan(grids, species, n_max, shares=SLAB_SHARES if world > 1 else (0.25,) * 4, scale=cap_scale))
+                         slabs=slab_plan(grids, species, n_max, shares=SLAB_SHARES if world > 1 else (1.0,), scale=cap_scale))
         flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream()
         for i in range(args.warmup):

@@ -212,7 +212,7 @@ class ShardedRun:
             self.L = ShardLayout(n_max, fac.n_pairs, cell_lo=slabs[0], slot_lo=slabs[1])
         elif slab_cells is None and slab_cap is None:            # (ranks whose grids differ must be given a common plan)
             cell_lo, slot_lo = slab_plan([grid], np.asarray(species).reshape(-1, 20), n_max,
-                                         shares=SLAB_SHARES if int(world) > 1 else (0.25,) * N_SLABS)
+                                         shares=SLAB_SHARES if int(world) > 1 else (1.0,))      # one GPU: nothing to export between launches
             self.L = ShardLayout(n_max, fac.n_pairs, cell_lo=cell_lo, slot_lo=slot_lo)
         else:
             est = expected_slots(grid, np.asarray(species).reshape(-1, 20))
