@@ -234,7 +234,7 @@ class Writer:
         msgs = [
             (0x0001, dataspace_message((n,), (None,))),
             (0x0003, datatype_message(data.dtype)),
-            (0x0005, struct.pack("<BBBBI", 2, 3, 0, 1, 0)),      # fill value v2: incremental allocation, default fill value
+            (0x0005, struct.pack("<BBBBI", 2, 3, 2, 1, 0)),      # fill value v2: incremental allocation, written if set, default value
             (0x0008, struct.pack("<BBBQII", 3, 2, 2, btree_addr, cr, rowsize)),      # layout v3, chunked, rank + 1 dimensions
         ]
         msgs += [(0x000C, attribute_message(k, v)) for k, v in t.attrs.items()]

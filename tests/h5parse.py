@@ -26,16 +26,19 @@ def need(cond, msg):
 class File:
     def __init__(self, path):
         with open(path, "rb") as fh:
-            self.b = fh.read()
-        b = self.b
-        need(b[:8] == b"\x89HDF\r\n\x1a\n", "signature")
+            raw = fh.read()
+        user = 0                                                   # a user block of 512, 1024, ... bytes may precede the superblock
+        while raw[user:user + 8] != b"\x89HDF\r\n\x1a\n":
+            user = 512 if user == 0 else 2 * user
+            need(user < len(raw), "signature")
+        self.b = b = raw[user:]                                    # addresses in the file are relative to the base address
         ver, fsver, rootver, _, shver, so, sl, _ = struct.unpack_from("<8B", b, 8)
         need((ver, fsver, rootver, shver) == (0, 0, 0, 0), "superblock version 0 expected")
         need((so, sl) == (8, 8), "8-byte offsets and lengths expected")
         self.leaf_k, self.internal_k, flags = struct.unpack_from("<HHI", b, 16)
         base, free, eof, drv = struct.unpack_from("<4Q", b, 24)
-        need(base == 0 and free == UNDEF and drv == UNDEF, "base / free-space / driver addresses")
-        need(eof == len(b), f"end-of-file address {eof} != file size {len(b)}")
+        need(base == user and free == UNDEF and drv == UNDEF, "base / free-space / driver addresses")
+        need(eof == len(raw), f"end-of-file address {eof} != file size {len(raw)}")
         name_off, hdr, ctype, _ = struct.unpack_from("<QQII", b, 56)
         need(ctype == 1, "root entry caches its B-tree and heap")
         self.root_btree, self.root_heap = struct.unpack_from("<QQ", b, 80)
@@ -66,8 +69,12 @@ class File:
             elif mtype == 0x0003:
                 out["dtype"], _ = self.datatype(body, 0)
             elif mtype == 0x0005:
-                need(body[0] == 2, "fill value message version 2")
+                need(body[0] in (1, 2), "fill value message version 1 or 2")
                 out["fill"] = tuple(body[1:4])
+                if body[3] or body[0] == 1:
+                    need(struct.unpack_from("<i", body, 4)[0] >= 0, "fill value size")
+            elif mtype in (0x0012, 0x000E):                       # modification time (new / old): informational
+                pass
             elif mtype == 0x0008:
                 out["kind"] = "dataset"
                 out["layout"] = self.layout(body)
@@ -134,6 +141,12 @@ class File:
 
     def layout(self, body):
         ver, cls = body[0], body[1]
+        if ver in (1, 2):                                          # files written by HDF5 <= 1.6: only contiguous is read here
+            nd, cls = body[1], body[2]
+            need(cls == 1, "old-style layout: contiguous only")
+            (addr,) = struct.unpack_from("<Q", body, 8)
+            dims = struct.unpack_from(f"<{nd}I", body, 16)
+            return {"class": "contiguous", "addr": addr, "size": int(np.prod(dims))}
         need(ver == 3, "layout version 3")
         if cls == 1:
             addr, size = struct.unpack_from("<QQ", body, 2)
@@ -242,10 +255,11 @@ class File:
     # ---- datasets -----------------------------------------------------------------------------------------------------------
     def read(self, obj):
         need(obj["kind"] == "dataset", "not a dataset")
-        dt, (n,) = obj["dtype"], obj["shape"]
-        lay = obj["layout"]
+        dt, lay = obj["dtype"], obj["layout"]
         if lay["class"] == "contiguous":
-            return np.frombuffer(self.b, dtype=dt, count=n, offset=lay["addr"]).copy()
+            n = int(np.prod(obj["shape"]))
+            return np.frombuffer(self.b, dtype=dt, count=n, offset=lay["addr"]).copy().reshape(obj["shape"])
+        (n,) = obj["shape"]
         need(lay["elem"] == dt.itemsize and len(lay["chunk"]) == 1, "chunk geometry")
         need(obj["maxshape"] == (None,), "extendible along the row axis")
         cr = lay["chunk"][0]

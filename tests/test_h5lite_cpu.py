@@ -131,3 +131,19 @@ def test_pandas_reads_the_file_back(tmp_path):
         for k, df in frames.items():
             got = st[k]
             pd.testing.assert_frame_equal(got.reset_index(drop=True), df.reset_index(drop=True), check_dtype=False)
+
+
+def test_the_reader_reads_a_file_written_by_libhdf5():
+    """Pins the tests' own HDF5 reader: SciPy ships a MATLAB v7.3 file — written by libhdf5 1.6 behind a 512-byte user block —
+    that uses the very structures h5lite emits for groups, object headers, heaps, float datatypes and string attributes."""
+    import scipy.io
+    path = os.path.join(os.path.dirname(scipy.io.__file__), "matlab", "tests", "data", "testhdf5_7.4_GLNX86.mat")
+    if not os.path.isfile(path):
+        pytest.skip("SciPy's test data are not installed")
+    f = h5parse.File(path)
+    assert (f.leaf_k, f.internal_k) == (4, 16)
+    ds = f.get("testdouble")
+    assert ds["kind"] == "dataset" and ds["dtype"] == np.dtype("<f8") and ds["shape"] == (9, 1)
+    assert ds["attrs"] == {"MATLAB_class": "double"}
+    got = f.read(ds)[:, 0]
+    assert np.allclose(got, np.arange(9) * np.pi / 4)             # scipy's testdouble: 0, pi/4, ..., 2 pi
