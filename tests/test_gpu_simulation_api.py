@@ -114,6 +114,23 @@ def test_run_and_summary_native_rng(tmp_path):
     assert yearly.iloc[0]["prob_entrainment"] > 0.5
     assert set(diag["route"]) == {"U1", "U2", "U3"} and "flow_share" in diag.columns
     assert sim.cum_sum is not None and sim.daily_summary is not None and sim.beta_caption
+    # the result file itself: <name>.h5 in the pandas table layout (by PyTables where it exists, else by stryke_b200.h5lite)
+    from stryke_b200 import store
+    store.wait_for_exports()
+    assert os.path.isfile(sim.hdf_path)
+    if not store.pytables_available():
+        import h5parse
+        f = h5parse.File(sim.hdf_path)
+        tables = {k for k, o in f.walk() if o["kind"] == "dataset"}
+        assert {"/Daily/table", "/State_Daily/table", "/Route_Flows/table", "/Unit_Hours/table", "/Daily_Summary/table",
+                "/Beta_Distributions/table", "/Yearly_Summary/table", "/Population/table"} <= tables
+        tab = f.get("Daily/table")
+        rec = f.read(tab)
+        cols = {c: (name, j) for name in f.get("Daily")["attrs"]["values_cols"] for j, c in enumerate(tab["attrs"][f"{name}_kind"])}
+        name, j = cols["pop_size"]
+        assert len(rec) == 20 and np.array_equal(rec[name][:, j], daily["pop_size"].to_numpy())
+        name, j = cols["species"]
+        assert [x.decode() for x in rec[name][:, j]] == list(daily["species"])
 
 
 def test_population_cap_raises_like_the_reference(tmp_path, monkeypatch):
