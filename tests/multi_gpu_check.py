@@ -115,6 +115,8 @@ def main():
             ok = int(all(st[k].reset_index(drop=True).equals(want[k].reset_index(drop=True)) for k in ("Daily", "State_Daily", "Unit_Hours")))
         print(f"rank 0: sim.run() under torchrun wrote the single-GPU frames: {bool(ok)} ({len(want['Daily'])} Daily rows)", flush=True)
     all_ok(bool(ok), "sim.run() under torchrun")
+    from stryke_b200.store import wait_for_exports
+    wait_for_exports()                        # (rank 0's .h5 export runs on a worker thread)
     shutil.rmtree(tmp, ignore_errors=True)
     dist.destroy_process_group()
     if rank == 0:
