@@ -276,8 +276,9 @@ class Writer:
 
 # ---- pandas "table" layout ----------------------------------------------------------------------------------------
 def _block_order(df):
-    """Columns grouped the way pandas' consolidated BlockManager orders its blocks for ``format='table'``: float, int,
-    (datetime,) object — each block's columns in frame order."""
+    """Columns grouped the way pandas' consolidated BlockManager orders its blocks for ``format='table'`` — by dtype name:
+    bool, datetime64[ns], float64, int64, object — each block's columns in frame order.  (A reader goes by the ``*_kind``
+    attributes, not by the order.)"""
     blocks = {}
     for c in df.columns:
         col = df[c]
@@ -292,7 +293,7 @@ def _block_order(df):
         else:
             k = ("string", None)
         blocks.setdefault(k, []).append(c)
-    order = [("float64", "f8"), ("int64", "i8"), ("bool", "u1"), ("datetime64[ns]", "i8"), ("string", None)]
+    order = [("bool", "u1"), ("datetime64[ns]", "i8"), ("float64", "f8"), ("int64", "i8"), ("string", None)]
     return [(k, blocks[k]) for k in order if k in blocks]
 
 

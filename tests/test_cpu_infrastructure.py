@@ -316,9 +316,9 @@ def test_fallback_store_exports_to_parquet_and_csv(tmp_path):
                                                                                "/simulations/Spring/a/table"]
             rec = f.read(f.get("Daily/table"))
             t = f.get("Daily/table")["attrs"]
-            assert t["values_block_0_kind"] == ["iteration", "pop_size"] and np.array_equal(rec["values_block_0"], [[0, 3], [1, 4]])
-            assert t["values_block_1_dtype"] == "datetime64[ns]"
-            assert np.array_equal(rec["values_block_1"][:, 0].view("datetime64[ns]"), daily["day"].to_numpy())
+            assert t["values_block_1_kind"] == ["iteration", "pop_size"] and np.array_equal(rec["values_block_1"], [[0, 3], [1, 4]])
+            assert t["values_block_0_dtype"] == "datetime64[ns]"
+            assert np.array_equal(rec["values_block_0"][:, 0].view("datetime64[ns]"), daily["day"].to_numpy())
             assert [x.decode() for x in rec["values_block_2"][:, 0]] == ["a", "b"]
 
 
