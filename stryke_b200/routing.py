@@ -86,16 +86,38 @@ def fill_units_in_order(flow, ordered_units, qopt_of, qcap_of, min_start):
     return given
 
 
+def unit_meta(unit_params):
+    """Per-unit lookups of ``unit_flow_allocations`` taken out of the frame once: {unit: (Facility, op_order | None,
+    Qopt | None)} — the tables of a run are built day by day, and cell-by-cell ``DataFrame.at`` was half their time."""
+    if unit_params is None:
+        return None
+    has_order, has_qopt = "op_order" in unit_params.columns, "Qopt" in unit_params.columns
+    out = {}
+    for unit in unit_params.index:
+        order = None
+        if has_order:
+            val = unit_params.at[unit, "op_order"]
+            if not (isinstance(val, float) and math.isnan(val)):
+                order = int(val)
+        out[unit] = (unit_params.at[unit, "Facility"] if "Facility" in unit_params.columns else None, order,
+                     _num(unit_params.at[unit, "Qopt"]) if has_qopt else None)
+    return out
+
+
 def unit_flow_allocations(curr_Q, unit_nodes, min_Q_dict, env_Q_dict, bypass_Q_dict, sta_cap_dict, unit_fac_dict,
-                          penstock_id_dict, penstock_cap_dict, cap_dict, unit_params=None):
+                          penstock_id_dict, penstock_cap_dict, cap_dict, unit_params=None, meta=None):
     """Flow through every unit in ``unit_nodes`` at river discharge ``curr_Q``.
 
     Returns ``(allocations, prod_Q_by_facility, total_env_Q, total_bypass_Q)`` exactly like
-    ``simulation.compute_unit_flow_allocations`` (stryke.py:1657-1821)."""
+    ``simulation.compute_unit_flow_allocations`` (stryke.py:1657-1821).  ``meta`` = ``unit_meta(unit_params)`` when the
+    caller has it (same values, no frame lookups)."""
+    if meta is None:
+        meta = unit_meta(unit_params)
+
     def facility_of(unit):
         fac = unit_fac_dict.get(unit)
-        if fac is None and unit_params is not None and unit in unit_params.index:
-            fac = unit_params.at[unit, "Facility"]
+        if fac is None and meta is not None and unit in meta:
+            fac = meta[unit][0]
         return fac
 
     facilities = []
@@ -115,18 +137,15 @@ def unit_flow_allocations(curr_Q, unit_nodes, min_Q_dict, env_Q_dict, bypass_Q_d
             production[fac] = 0.0
 
     order_of, qopt_of = {}, {}
-    if unit_params is not None:
-        has_order = "op_order" in unit_params.columns
-        has_qopt = "Qopt" in unit_params.columns
+    if meta is not None:
         for unit in unit_nodes:
-            if unit not in unit_params.index:
+            if unit not in meta:
                 continue
-            if has_order:
-                val = unit_params.at[unit, "op_order"]
-                if not (isinstance(val, float) and math.isnan(val)):
-                    order_of[unit] = int(val)
-            if has_qopt:
-                qopt_of[unit] = _num(unit_params.at[unit, "Qopt"])
+            _, order, qopt = meta[unit]
+            if order is not None:
+                order_of[unit] = order
+            if qopt is not None:
+                qopt_of[unit] = qopt
 
     by_facility = {}
     for unit in unit_nodes:
@@ -175,7 +194,7 @@ _ROLE_RANK = {"unit": 0, "env": 1, "bypass": 2, "other": 3, "spill": 4}
 
 
 def route_table(location, neighbours, edge_weight, Q_dict, op_order, cap_dict, unit_fac_dict, penstock_id_dict=None,
-                penstock_cap_dict=None, unit_params=None, facility_params=None):
+                penstock_cap_dict=None, unit_params=None, facility_params=None, meta=None, served_cache=None):
     """Routing decision table of a live fish standing at ``location``.
 
     ``neighbours`` is ``list(graph.neighbors(location))`` (insertion order) and ``edge_weight(n)`` the edge's
@@ -194,7 +213,7 @@ def route_table(location, neighbours, edge_weight, Q_dict, op_order, cap_dict, u
         units_here = [n for n, r in zip(neighbours, roles) if r == "unit"]
         alloc, _, env_total, bypass_total = unit_flow_allocations(
             curr_Q, units_here, min_Q, env_Q, bypass_Q, sta_cap, unit_fac_dict, penstock_id_dict, penstock_cap_dict,
-            cap_dict, unit_params=unit_params)
+            cap_dict, unit_params=unit_params, meta=meta)
         ranked = sorted(neighbours, key=lambda n: (_ROLE_RANK[_role(n)], op_order.get(n, 999) if _role(n) == "unit" else 0))
         n_env = sum(1 for n in ranked if "env" in n.lower())
         n_bypass = sum(1 for n in ranked if "bypass" in n.lower())
@@ -216,10 +235,13 @@ def route_table(location, neighbours, edge_weight, Q_dict, op_order, cap_dict, u
             locs.append(n)
             flows.append(q)
     elif any("spill" in n.lower() for n in neighbours):   # spill branch, stryke.py:1955-2000
-        if facility_params is not None:
-            served = list(facility_params[facility_params.Spillway.isin(neighbours)].index)
+        key = tuple(neighbours)
+        if served_cache is not None and key in served_cache:
+            served = served_cache[key]
         else:
-            served = []
+            served = list(facility_params[facility_params.Spillway.isin(neighbours)].index) if facility_params is not None else []
+            if served_cache is not None:
+                served_cache[key] = served
         cap_total = sum(sta_cap.get(f, 0.0) for f in served)
         env_total = sum(env_Q.get(f, 0.0) for f in served)
         bypass_total = sum(bypass_Q.get(f, 0.0) for f in served)

@@ -150,15 +150,23 @@ class RunContext:
         """All-units allocation that sets ``u_param_dict[u]['Q']`` (stryke.py:2964-2977)."""
         alloc, _, _, _ = routing.unit_flow_allocations(
             Q["curr_Q"], self.units, Q["min_Q"], Q["env_Q"], Q["bypass_Q"], Q["sta_cap"], self.unit_fac,
-            self.penstock_id, self.penstock_cap, self.q_cap, unit_params=self.sim.unit_params)
+            self.penstock_id, self.penstock_cap, self.q_cap, unit_params=self.sim.unit_params, meta=self._meta())
         return {u: float(alloc.get(u, 0.0) or 0.0) for u in self.units}
+
+    def _meta(self):
+        if "_unit_meta" not in self.__dict__:
+            self._unit_meta = routing.unit_meta(self.sim.unit_params)
+            self._served = {}
+        return self._unit_meta
 
     def route(self, location, Q):
         g = self.sim.graph
         nb = list(g.neighbors(location)) if location in g else []
+        meta = self._meta()
         return routing.route_table(location, nb, lambda n: g[location][n].get("weight", 1.0), Q, self.op_order,
                                    self.q_cap, self.unit_fac, self.penstock_id, self.penstock_cap,
-                                   unit_params=self.sim.unit_params, facility_params=self.sim.facility_params)
+                                   unit_params=self.sim.unit_params, facility_params=self.sim.facility_params,
+                                   meta=meta, served_cache=self._served)
 
 
 def barotrauma_required(unit_params):
