@@ -147,3 +147,59 @@ def test_the_reader_reads_a_file_written_by_libhdf5():
     assert ds["attrs"] == {"MATLAB_class": "double"}
     got = f.read(ds)[:, 0]
     assert np.allclose(got, np.arange(9) * np.pi / 4)             # scipy's testdouble: 0, pi/4, ..., 2 pi
+
+
+def test_random_frames_round_trip(tmp_path):
+    """Property test: frames of random shape (float / int / datetime / string columns in any order, NaN and None cells,
+    non-ASCII labels, nested keys, zero rows) come back value for value through the independent reader."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    label = st.text(alphabet=st.characters(blacklist_characters="\x00", blacklist_categories=("Cs",)), min_size=0, max_size=12)
+    kinds = st.lists(st.sampled_from("fids"), min_size=1, max_size=6)
+    counter = [0]
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(kinds=kinds, n=st.integers(0, 40), seed=st.integers(0, 2 ** 16), labels=st.lists(label, min_size=1, max_size=5),
+           nested=st.booleans())
+    def run(kinds, n, seed, labels, nested):
+        rng = np.random.default_rng(seed)
+        cols = {}
+        for j, k in enumerate(kinds):
+            name = f"col {j}"
+            if k == "f":
+                v = rng.normal(size=n)
+                v[rng.random(n) < 0.2] = np.nan
+            elif k == "i":
+                v = rng.integers(-2 ** 40, 2 ** 40, n)
+            elif k == "d":
+                v = (np.datetime64("2001-01-01", "ns") + rng.integers(0, 10 ** 15, n).astype("timedelta64[ns]"))
+            else:
+                v = np.array([labels[i] for i in rng.integers(0, len(labels), n)], dtype=object)
+                v[rng.random(n) < 0.15] = None
+            cols[name] = v
+        df = pd.DataFrame(cols)
+        key = "simulations/some scenario/Genus species" if nested else "Daily"
+        counter[0] += 1
+        path = str(tmp_path / f"r{counter[0]}.h5")
+        h5lite.write_frames(path, {key: df})
+        f = h5parse.File(path)
+        grp, tab = f.get(key), f.get(key + "/table")
+        rec = f.read(tab)
+        assert len(rec) == n and int(tab["attrs"]["NROWS"]) == n
+        seen = set()
+        for name in grp["attrs"]["values_cols"]:
+            for j, c in enumerate(tab["attrs"][f"{name}_kind"]):
+                seen.add(c)
+                v, col = rec[name][:, j], df[c]
+                kind = tab["attrs"][f"{name}_dtype"]
+                if kind == "float64":
+                    assert np.array_equal(v, col.to_numpy(dtype=float), equal_nan=True)
+                elif kind == "int64":
+                    assert np.array_equal(v, col.to_numpy())
+                elif kind == "datetime64[ns]":
+                    assert np.array_equal(v.view("datetime64[ns]"), col.to_numpy().astype("datetime64[ns]"))
+                else:
+                    want = ["nan" if (x is None or (isinstance(x, float) and np.isnan(x))) else x for x in col]
+                    assert [x.decode("utf-8") for x in v] == want
+        assert seen == set(df.columns)
+    run()
