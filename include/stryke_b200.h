@@ -249,7 +249,8 @@ int stryke_b200_plan_launch(StrykePlan* plan, int32_t* d_cell_n, uint32_t* d_dai
  * A range that starts at cell 0 starts a new pass: the status words (error, fish and slot totals) start over.
  * d_slots_after (device, may be NULL) receives the slot count after this range — what a caller that overlaps the copy of one
  * range with the kernels of the next needs to know.  Ranges of one pass go to ONE stream, in order.
- * Rows are zeroed by the launch itself: no memset, no read-modify-write of untouched cells. */
+ * The launch initialises every row it hands out (whole-row stores for the cells one warp simulates alone, zero-fill +
+ * atomic adds for the few whose tiles are split between warps): the caller never clears d_rows. */
 int stryke_b200_plan_launch_compact(StrykePlan* plan, int64_t cell_lo, int64_t cell_hi, int32_t* d_cell_n, uint32_t* d_rows,
                                     int64_t rows_cap, int64_t first_slot, uint64_t* d_slots_after, void* stream);
 /* DEVICE pointers of the plan's per-block tables [n_blocks] and the row geometry. */
